@@ -1,0 +1,14 @@
+"""ananke_abm_b200 -- B200-native GAT-ODE hot path of bobkatla/ananke_abm behind the reference's interfaces.
+
+Public surface:
+    odeint, odeint_adjoint      torchdiffeq-compatible solver seam (fused sm_100a kernels underneath)
+    ModeSepModel, ModeSepConfig reference module signature (mode_sep)
+    SecondOrderDrift            the drift module family the kernels implement
+The CUDA shared library (libananke_b200.so, C ABI in include/ananke_b200.h) is the only compute path.
+"""
+from ._lib import Ab200Error, lib  # noqa: F401
+from .drift import SecondOrderDrift, describe_drift  # noqa: F401
+from .odeint import odeint, odeint_adjoint, set_default_precision, drift_eval  # noqa: F401
+from .mode_sep import ModeSepConfig, ModeSepModel  # noqa: F401
+
+__version__ = "0.1.0"

@@ -1,0 +1,134 @@
+// extern "C" surface of libananke_b200.so -- see include/ananke_b200.h for the contract of each symbol.
+#include <string.h>
+#include "common.cuh"
+
+namespace ab200 {
+static thread_local char g_cuda_err[256] = "";
+void set_cuda_error(cudaError_t e) {
+  strncpy(g_cuda_err, cudaGetErrorString(e), sizeof(g_cuda_err) - 1);
+  g_cuda_err[sizeof(g_cuda_err) - 1] = 0;
+}
+
+// implemented in the kernel translation units
+int pack_drift(const ab200_drift_desc* d, const float* w_flat, float* packed, cudaStream_t st);
+int rk4_forward_f32(const ab200_drift_desc* d, const float* packed, const float* y0, const float* t_dev, int64_t B, int T,
+                    float* y_path, cudaStream_t st);
+int drift_eval_f32(const ab200_drift_desc* d, const float* packed, float t, const float* y, int64_t B, float* out,
+                   cudaStream_t st);
+size_t rk4_backward_f32_workspace(const ab200_drift_desc* d, int64_t B, int T);
+int rk4_backward_f32(const ab200_drift_desc* d, const float* w_flat, const float* t_dev, const float* y_path,
+                     const float* grad_y_path, int64_t B, int T, float* grad_y0, float* grad_w_flat, void* ws, size_t ws_bytes,
+                     cudaStream_t st);
+int rk_stage_combine(const float* y, const float* const* k, const float* coef, int n_k, float dt, float* out, int64_t n,
+                     cudaStream_t st);
+int rk_combine_errnorm(const float* y0, const float* const* k, const float* csol, const float* cerr, int n_k, float dt,
+                       float rtol, float atol, float* y1_out, float* sumsq, int64_t n, cudaStream_t st);
+
+static bool desc_ok(const ab200_drift_desc* d) {
+  return d && d->pos_dim > 0 && d->ctx_dim >= 0 && d->hidden > 0 && d->n_res >= 0 && (d->res_act == 0 || d->res_act == 1);
+}
+static size_t packed_bytes(const ab200_drift_desc* d) {
+  const PackLayout L{d->pos_dim, d->ctx_dim, d->hidden, d->n_res};
+  return align_up((size_t)L.total() * sizeof(float), 256);
+}
+}  // namespace ab200
+
+using namespace ab200;
+
+extern "C" {
+
+int ab200_abi_version(void) { return AB200_ABI_VERSION; }
+
+const char* ab200_status_string(int s) {
+  switch (s) {
+    case AB200_OK: return "ok";
+    case AB200_ERR_BAD_ARG: return "bad argument";
+    case AB200_ERR_UNSUPPORTED: return "drift-net shape or precision not instantiated in this build";
+    case AB200_ERR_WORKSPACE: return "workspace too small";
+    case AB200_ERR_CUDA: return "CUDA error";
+    case AB200_ERR_NOT_MONOTONE: return "t must be strictly increasing or decreasing";
+    case AB200_ERR_DT_UNDERFLOW: return "underflow in dt";
+    case AB200_ERR_MAX_STEPS: return "max_num_steps exceeded";
+    default: return "unknown status";
+  }
+}
+
+const char* ab200_last_cuda_error(void) { return g_cuda_err; }
+
+int64_t ab200_drift_param_count(const ab200_drift_desc* d) {
+  if (!desc_ok(d)) return AB200_ERR_BAD_ARG;
+  const FlatLayout F{d->pos_dim, d->ctx_dim, d->hidden, d->n_res};
+  return F.total();
+}
+
+size_t ab200_rk4_workspace_bytes(const ab200_drift_desc* d, int64_t B, int32_t T, int32_t precision) {
+  if (!desc_ok(d)) return 0;
+  (void)B; (void)T; (void)precision;
+  return packed_bytes(d);
+}
+
+int ab200_rk4_forward(const ab200_drift_desc* d, const float* w_flat, const float* y0, const float* t_dev,
+                      const float* t_host, int64_t B, int32_t T, float* y_path, void* workspace, size_t workspace_bytes,
+                      int32_t precision, ab200_stream_t stream) {
+  if (!desc_ok(d) || !w_flat || !y0 || !t_dev || !y_path || !workspace || B <= 0 || T < 1) return AB200_ERR_BAD_ARG;
+  if (t_host)
+    for (int i = 0; i + 1 < T; ++i)
+      if (!(t_host[i + 1] > t_host[i])) return AB200_ERR_NOT_MONOTONE;
+  if (workspace_bytes < ab200_rk4_workspace_bytes(d, B, T, precision)) return AB200_ERR_WORKSPACE;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (precision == AB200_PREC_F32) {
+    int rc = pack_drift(d, w_flat, (float*)workspace, st);
+    if (rc) return rc;
+    return rk4_forward_f32(d, (const float*)workspace, y0, t_dev, B, T, y_path, st);
+  }
+  return AB200_ERR_UNSUPPORTED;
+}
+
+size_t ab200_rk4_backward_workspace_bytes(const ab200_drift_desc* d, int64_t B, int32_t T, int32_t precision) {
+  if (!desc_ok(d)) return 0;
+  (void)precision;
+  return rk4_backward_f32_workspace(d, B, T);
+}
+
+int ab200_rk4_backward(const ab200_drift_desc* d, const float* w_flat, const float* t_dev, const float* y_path,
+                       const float* grad_y_path, int64_t B, int32_t T, float* grad_y0, float* grad_w_flat, void* workspace,
+                       size_t workspace_bytes, int32_t precision, ab200_stream_t stream) {
+  if (!desc_ok(d) || !w_flat || !t_dev || !y_path || !grad_y_path || !grad_y0 || !grad_w_flat || !workspace || B <= 0 || T < 1)
+    return AB200_ERR_BAD_ARG;
+  if (workspace_bytes < ab200_rk4_backward_workspace_bytes(d, B, T, precision)) return AB200_ERR_WORKSPACE;
+  if (precision != AB200_PREC_F32) return AB200_ERR_UNSUPPORTED;
+  return rk4_backward_f32(d, w_flat, t_dev, y_path, grad_y_path, B, T, grad_y0, grad_w_flat, workspace, workspace_bytes,
+                          (cudaStream_t)stream);
+}
+
+size_t ab200_drift_eval_workspace_bytes(const ab200_drift_desc* d, int64_t B, int32_t precision) {
+  if (!desc_ok(d)) return 0;
+  (void)B; (void)precision;
+  return packed_bytes(d);
+}
+
+int ab200_drift_eval(const ab200_drift_desc* d, const float* w_flat, float t, const float* y, int64_t B, float* out,
+                     void* workspace, size_t workspace_bytes, int32_t precision, ab200_stream_t stream) {
+  if (!desc_ok(d) || !w_flat || !y || !out || !workspace || B <= 0) return AB200_ERR_BAD_ARG;
+  if (workspace_bytes < packed_bytes(d)) return AB200_ERR_WORKSPACE;
+  if (precision != AB200_PREC_F32) return AB200_ERR_UNSUPPORTED;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = pack_drift(d, w_flat, (float*)workspace, st);
+  if (rc) return rc;
+  return drift_eval_f32(d, (const float*)workspace, t, y, B, out, st);
+}
+
+int ab200_rk_stage_combine(const float* y, const float* const* k, const float* coef_host, int32_t n_k, float dt, float* out,
+                           int64_t n, ab200_stream_t stream) {
+  if (!y || !out || n <= 0 || (n_k > 0 && (!k || !coef_host))) return AB200_ERR_BAD_ARG;
+  return rk_stage_combine(y, k, coef_host, n_k, dt, out, n, (cudaStream_t)stream);
+}
+
+int ab200_rk_combine_errnorm(const float* y0, const float* const* k, const float* csol_host, const float* cerr_host,
+                             int32_t n_k, float dt, float rtol, float atol, float* y1_out, float* sumsq, int64_t n,
+                             ab200_stream_t stream) {
+  if (!y0 || !k || !csol_host || !cerr_host || !sumsq || n <= 0) return AB200_ERR_BAD_ARG;
+  return rk_combine_errnorm(y0, k, csol_host, cerr_host, n_k, dt, rtol, atol, y1_out, sumsq, n, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,378 @@
+"""`odeint` / `odeint_adjoint` with torchdiffeq's call signature -- the solver seam of the reference.
+
+The reference calls (all under /root/reference/src/ananke_abm/models/):
+    odeint(self.odefunc, y0, times_union, method="rk4", rtol=..., atol=...)        mode_sep/architecture/model.py:184-191
+    odeint(self.ode_func, y0, times, method='dopri5', options={'dtype': float32})  latent_ode/architecture/model.py:192,196
+    odeint_adjoint(wrapped_func, x0, t, rtol=, atol=, method='dopri5')             latent_ode/architecture/ode_components.py:50
+resolve to this module when it is installed as `torchdiffeq`; the unmodified reference
+model files then run on the CUDA kernels.
+
+Dispatch:
+  * `func` is one of the two reference drift modules (recognised structurally, see `drift.describe_drift`)
+      rk4    -> one fused whole-trajectory launch  (ab200_rk4_forward / ab200_rk4_backward)
+      dopri5 -> drift evaluated by `ab200_drift_eval`, stages combined by `ab200_rk_combine_errnorm`
+  * any other `func` -> func evaluated by the caller's own torch code on the GPU, every stage combine and the
+    error norm by the fused elementwise kernels (`ab200_rk_stage_combine`, `ab200_rk_combine_errnorm`).
+Everything runs on CUDA tensors; there is no CPU path (CPU tensors raise).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import warnings
+from typing import Callable, Optional, Sequence
+
+import torch
+
+from . import _lib
+from .drift import DriftSpec, describe_drift
+
+_DEFAULT_PRECISION = {"value": "f32"}
+
+
+def set_default_precision(p: str) -> None:
+    """'f32' (strict FFMA, 1e-5 parity) or 'bf16' (tcgen05 tensor-core path, stated tolerance)."""
+    if p not in _lib.PRECISIONS:
+        raise ValueError(f"unknown precision {p!r}")
+    _DEFAULT_PRECISION["value"] = p
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(x: torch.Tensor, what: str) -> None:
+    if not x.is_cuda:
+        raise _lib.Ab200Error(f"{what} must be a CUDA tensor: ananke_abm_b200 has no CPU path")
+
+
+def _check_t(t: torch.Tensor) -> torch.Tensor:
+    assert isinstance(t, torch.Tensor), "t must be a torch.Tensor"
+    assert t.ndimension() == 1, "t must be one dimensional"
+    assert torch.is_floating_point(t), "t must be a floating point Tensor"
+    t_host = t.detach().to("cpu", non_blocking=False)
+    if t_host.numel() > 1:
+        d = t_host[1:] - t_host[:-1]
+        if not (bool((d > 0).all()) or bool((d < 0).all())):
+            raise AssertionError("t must be strictly increasing or decreasing")
+    return t_host
+
+
+# --------------------------------------------------------------------------------------------------
+# fused rk4 for the recognised drift nets
+# --------------------------------------------------------------------------------------------------
+class _FusedRK4(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y0, t, w_flat, spec: DriftSpec, precision: int, t_host):
+        L = _lib.lib()
+        B, D = y0.shape
+        T = t.numel()
+        y0c = y0.contiguous().float()
+        tc = t.contiguous().float()
+        wc = w_flat.contiguous().float()
+        th = t_host.contiguous().float()
+        y_path = torch.empty((T, B, D), dtype=torch.float32, device=y0.device)
+        nbytes = L.ab200_rk4_workspace_bytes(C.byref(spec.desc), B, T, precision)
+        ws = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=y0.device)
+        rc = L.ab200_rk4_forward(C.byref(spec.desc), wc.data_ptr(), y0c.data_ptr(), tc.data_ptr(), th.data_ptr(), B, T,
+                                 y_path.data_ptr(), ws.data_ptr(), ws.numel(), precision, _stream_ptr())
+        _lib.check(rc, "ab200_rk4_forward")
+        ctx.spec, ctx.precision = spec, precision
+        ctx.save_for_backward(tc, wc, y_path)
+        return y_path
+
+    @staticmethod
+    def backward(ctx, grad_y_path):
+        L = _lib.lib()
+        tc, wc, y_path = ctx.saved_tensors
+        spec = ctx.spec
+        T, B, D = y_path.shape
+        g = grad_y_path.contiguous().float()
+        gy0 = torch.empty((B, D), dtype=torch.float32, device=g.device)
+        gw = torch.empty_like(wc)
+        # gradients are always taken on the strict-fp32 path unless a tensor-core backward exists for `precision`
+        prec = ctx.precision if ctx.precision in spec.backward_precisions else _lib.PREC_F32
+        nbytes = L.ab200_rk4_backward_workspace_bytes(C.byref(spec.desc), B, T, prec)
+        ws = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=g.device)
+        rc = L.ab200_rk4_backward(C.byref(spec.desc), wc.data_ptr(), tc.data_ptr(), y_path.data_ptr(), g.data_ptr(), B, T,
+                                  gy0.data_ptr(), gw.data_ptr(), ws.data_ptr(), ws.numel(), prec, _stream_ptr())
+        _lib.check(rc, "ab200_rk4_backward")
+        return gy0, None, gw, None, None, None
+
+
+def drift_eval(spec: DriftSpec, w_flat: torch.Tensor, t: float, y: torch.Tensor, precision: int = 0) -> torch.Tensor:
+    """One evaluation f(t, y) of a recognised drift net on the CUDA path (no autograd)."""
+    L = _lib.lib()
+    _require_cuda(y, "y")
+    B = y.shape[0]
+    out = torch.empty_like(y, dtype=torch.float32)
+    nbytes = L.ab200_drift_eval_workspace_bytes(C.byref(spec.desc), B, precision)
+    ws = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=y.device)
+    rc = L.ab200_drift_eval(C.byref(spec.desc), w_flat.contiguous().float().data_ptr(), float(t), y.contiguous().float().data_ptr(),
+                            B, out.data_ptr(), ws.data_ptr(), ws.numel(), precision, _stream_ptr())
+    _lib.check(rc, "ab200_drift_eval")
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# fused elementwise stage algebra for arbitrary `func`
+# --------------------------------------------------------------------------------------------------
+class _StageCombine(torch.autograd.Function):
+    """out = y + dt * sum_j coef[j] * k_j   in one pass (ab200_rk_stage_combine)."""
+
+    @staticmethod
+    def forward(ctx, dt: float, coef: Sequence[float], y, *ks):
+        L = _lib.lib()
+        yc = y.contiguous()
+        kc = [k.contiguous() for k in ks]
+        out = torch.empty_like(yc)
+        n_k = len(kc)
+        ptrs = (C.c_void_p * max(n_k, 1))(*[k.data_ptr() for k in kc])
+        cf = (C.c_float * max(n_k, 1))(*[float(c) for c in coef])
+        rc = L.ab200_rk_stage_combine(yc.data_ptr(), C.cast(ptrs, C.c_void_p), C.cast(cf, C.c_void_p), n_k, float(dt),
+                                      out.data_ptr(), yc.numel(), _stream_ptr())
+        _lib.check(rc, "ab200_rk_stage_combine")
+        ctx.dt, ctx.coef = float(dt), [float(c) for c in coef]
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return (None, None, g) + tuple(g * (ctx.dt * c) for c in ctx.coef)
+
+
+def _combine(y, ks, coef, dt):
+    return _StageCombine.apply(float(dt), list(coef), y, *ks)
+
+
+def _rk4_generic(func, y0, t, t_host):
+    third, two_thirds = 1.0 / 3.0, 2.0 / 3.0
+    sol = [y0]
+    y = y0
+    for i in range(t.numel() - 1):
+        t0, t1 = t[i], t[i + 1]
+        dt_t = t1 - t0
+        dt = float(t_host[i + 1] - t_host[i])
+        k1 = func(t0, y)
+        k2 = func(t0 + dt_t * third, _combine(y, [k1], [third], dt))
+        k3 = func(t0 + dt_t * two_thirds, _combine(y, [k1, k2], [-third, 1.0], dt))
+        k4 = func(t1, _combine(y, [k1, k2, k3], [1.0, -1.0, 1.0], dt))
+        y = _combine(y, [k1, k2, k3, k4], [0.125, 0.375, 0.375, 0.125], dt)
+        sol.append(y)
+    return torch.stack(sol, dim=0)
+
+
+# Dormand-Prince 5(4), Shampine's error weights -- torchdiffeq dopri5.py
+_DP_ALPHA = [1 / 5, 3 / 10, 4 / 5, 8 / 9, 1.0, 1.0]
+_DP_BETA = [
+    [1 / 5],
+    [3 / 40, 9 / 40],
+    [44 / 45, -56 / 15, 32 / 9],
+    [19372 / 6561, -25360 / 2187, 64448 / 6561, -212 / 729],
+    [9017 / 3168, -355 / 33, 46732 / 5247, 49 / 176, -5103 / 18656],
+    [35 / 384, 0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84],
+]
+_DP_C_SOL = [35 / 384, 0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84, 0]
+_DP_C_ERR = [35 / 384 - 1951 / 21600, 0, 500 / 1113 - 22642 / 50085, 125 / 192 - 451 / 720,
+             -2187 / 6784 - -12231 / 42400, 11 / 84 - 649 / 6300, -1.0 / 60.0]
+_DP_C_MID = [6025192743 / 30085553152 / 2, 0, 51252292925 / 65400821598 / 2, -2691868925 / 45128329728 / 2,
+             187940372067 / 1594534317056 / 2, -1776094331 / 19743644256 / 2, 11237099 / 235043384 / 2]
+
+
+class _Dopri5:
+    """Adaptive Dormand-Prince driver (tdq rk_common.py RKAdaptiveStepsizeODESolver).  The drift is evaluated by
+    `f`; stage combines and the RMS error norm are single fused passes over the state.  The accept/reject
+    decision reads ONE float per attempted step from the device (the squared-error sum)."""
+
+    def __init__(self, f: Callable, y0, rtol, atol, first_step=None, safety=0.9, ifactor=10.0, dfactor=0.2,
+                 max_num_steps=2 ** 31 - 1, dtype=torch.float64, norm=None, **unused):
+        if unused:
+            warnings.warn(f"Dopri5: Unexpected arguments {unused}")
+        if norm is not None:
+            raise NotImplementedError("custom norms are not supported on the fused path")
+        self.f, self.y0 = f, y0
+        self.rtol, self.atol = float(rtol), float(atol)
+        self.safety, self.ifactor, self.dfactor = float(safety), float(ifactor), float(dfactor)
+        self.first_step = first_step
+        self.max_num_steps = int(max_num_steps)
+        self.tdtype = torch.promote_types(dtype, y0.dtype)
+        self.n_accepted = self.n_rejected = 0
+        self._sumsq = torch.zeros(1, dtype=torch.float32, device=y0.device)
+
+    def _tt(self, v: float) -> torch.Tensor:
+        return torch.tensor(v, dtype=self.y0.dtype, device=self.y0.device)
+
+    def _cast(self, v: float) -> float:
+        """round a time-like python float to the solver's time dtype (float32 when options['dtype']=float32)."""
+        if self.tdtype == torch.float32:
+            return float(torch.tensor(v, dtype=torch.float32))
+        return float(v)
+
+    def _rms(self, x: torch.Tensor) -> float:
+        return float(x.float().pow(2).mean().sqrt())
+
+    def _initial_step(self, t0: float, f0):
+        y0 = self.y0
+        scale = self.atol + y0.abs() * self.rtol
+        d0, d1 = self._rms(y0 / scale), self._rms(f0 / scale)
+        h0 = 1e-6 if (d0 < 1e-5 or d1 < 1e-5) else 0.01 * d0 / d1
+        y1 = _combine(y0, [f0], [1.0], h0)
+        f1 = self.f(self._tt(self._cast(t0 + h0)), y1)
+        d2 = self._rms((f1 - f0) / scale) / h0
+        if d1 <= 1e-15 and d2 <= 1e-15:
+            h1 = max(1e-6, h0 * 1e-3)
+        else:
+            h1 = (0.01 / max(d1, d2)) ** (1.0 / 5.0)
+        return self._cast(min(100 * h0, h1))
+
+    def _step(self, y0, f0, t0: float, dt: float):
+        L = _lib.lib()
+        ks = [f0]
+        yi = y0
+        t1 = self._cast(t0 + dt)
+        for al, be in zip(_DP_ALPHA, _DP_BETA):
+            ti = t1 if al == 1.0 else self._cast(t0 + al * dt)
+            yi = _combine(y0, ks, be, dt)
+            ks.append(self.f(self._tt(ti), yi))
+        y1, f1 = yi, ks[-1]                     # FSAL: the last stage input is the 5th-order solution
+        # embedded error estimate and its RMS norm in one pass over the state (y1_out = NULL: not re-stored)
+        n = y0.numel()
+        kc = [k.contiguous() for k in ks]
+        ptrs = (C.c_void_p * 8)(*([k.data_ptr() for k in kc] + [0]))
+        csol = (C.c_float * 8)(*([float(c) for c in _DP_C_SOL] + [0.0]))
+        cerr = (C.c_float * 8)(*([float(c) for c in _DP_C_ERR] + [0.0]))
+        self._sumsq.zero_()
+        rc = L.ab200_rk_combine_errnorm(y0.contiguous().data_ptr(), C.cast(ptrs, C.c_void_p), C.cast(csol, C.c_void_p),
+                                        C.cast(cerr, C.c_void_p), 7, float(dt), self.rtol, self.atol, None,
+                                        self._sumsq.data_ptr(), n, _stream_ptr())
+        _lib.check(rc, "ab200_rk_combine_errnorm")
+        ratio = float(torch.sqrt(self._sumsq[0] / n))
+        return y1, f1, ratio, ks
+
+    def _next_dt(self, dt: float, ratio: float) -> float:
+        if ratio == 0:
+            return self._cast(dt * self.ifactor)
+        dfac = 1.0 if ratio < 1 else self.dfactor
+        factor = min(self.ifactor, max(self.safety / ratio ** 0.2, dfac))
+        return self._cast(dt * factor)
+
+    def integrate(self, t_host: torch.Tensor):
+        y0 = self.y0
+        ts = [self._cast(float(v)) for v in t_host.tolist()]
+        f0 = self.f(self._tt(ts[0]), y0)
+        dt = self._initial_step(ts[0], f0) if self.first_step is None else self._cast(float(self.first_step))
+        t0 = t1 = ts[0]
+        y, f = y0, f0
+        coeffs = None
+        out = [y0]
+        for tn in ts[1:]:
+            n_steps = 0
+            while tn > t1:
+                assert n_steps < self.max_num_steps, "max_num_steps exceeded ({}>={})".format(n_steps, self.max_num_steps)
+                assert self._cast(t1 + dt) > t1, "underflow in dt {}".format(dt)
+                y1, f1, ratio, ks = self._step(y, f, t1, dt)
+                if ratio <= 1:
+                    self.n_accepted += 1
+                    ymid = _combine(y, ks, _DP_C_MID, dt)
+                    coeffs = _interp_fit(y, y1, ymid, ks[0], ks[-1], dt)
+                    t0, t1 = t1, self._cast(t1 + dt)
+                    y, f = y1, f1
+                else:
+                    self.n_rejected += 1
+                dt = self._next_dt(dt, ratio)
+                n_steps += 1
+            out.append(_interp_eval(coeffs, t0, t1, tn))
+        return torch.stack(out, dim=0)
+
+
+def _interp_fit(y0, y1, y_mid, f0, f1, dt):
+    a = 2 * dt * (f1 - f0) - 8 * (y1 + y0) + 16 * y_mid
+    b = dt * (5 * f0 - 3 * f1) + 18 * y0 + 14 * y1 - 32 * y_mid
+    c = dt * (f1 - 4 * f0) - 11 * y0 - 5 * y1 + 16 * y_mid
+    d = dt * f0
+    return [y0, d, c, b, a]
+
+
+def _interp_eval(coeffs, t0, t1, t):
+    assert t0 <= t <= t1, "invalid interpolation, fails `t0 <= t <= t1`"
+    x = (t - t0) / (t1 - t0)
+    total = coeffs[0] + x * coeffs[1]
+    xp = x
+    for c in coeffs[2:]:
+        xp = xp * x
+        total = total + xp * c
+    return total
+
+
+_LAST = {"solver": None}
+
+
+# --------------------------------------------------------------------------------------------------
+# public API
+# --------------------------------------------------------------------------------------------------
+def odeint(func, y0, t, *, rtol: float = 1e-7, atol: float = 1e-9, method: Optional[str] = None,
+           options: Optional[dict] = None, event_fn=None):
+    """Drop-in for `torchdiffeq.odeint` on the path the reference uses.  Returns `[len(t), *y0.shape]`."""
+    if event_fn is not None:
+        raise NotImplementedError("event handling is outside the reference's path")
+    if isinstance(y0, (tuple, list)):
+        raise NotImplementedError("tuple states are outside the reference's path (it passes a single [B, D] tensor)")
+    options = {} if options is None else dict(options)
+    method = "dopri5" if method is None else method
+    _require_cuda(y0, "y0")
+    t_host = _check_t(t)
+    t = t.to(y0.device)
+    precision = _lib.PRECISIONS[options.pop("precision", _DEFAULT_PRECISION["value"])]
+
+    decreasing = t_host.numel() > 1 and bool(t_host[0] > t_host[1])
+    spec = describe_drift(func) if (y0.dim() == 2 and not decreasing) else None
+
+    if method == "rk4":
+        for k in ("dtype", "norm"):
+            options.pop(k, None)
+        if options:
+            warnings.warn(f"rk4: Unexpected arguments {options}")
+        if spec is not None and y0.shape[1] == spec.state_dim and y0.dtype == torch.float32:
+            w_flat = spec.flat_params()
+            return _FusedRK4.apply(y0, t, w_flat, spec, precision, t_host)
+        f = _wrap_func(func, y0, decreasing)
+        tt = -t if decreasing else t
+        th = -t_host if decreasing else t_host
+        return _rk4_generic(f, y0, tt.to(y0.dtype), th)
+    if method == "dopri5":
+        if spec is not None and y0.shape[1] == spec.state_dim and not torch.is_grad_enabled():
+            w_flat = spec.flat_params().detach()
+            f = lambda tt, yy: drift_eval(spec, w_flat, float(tt), yy, _lib.PREC_F32)   # noqa: E731
+        else:
+            f = _wrap_func(func, y0, decreasing)
+        th = -t_host if decreasing else t_host
+        solver = _Dopri5(f, y0, rtol, atol, **options)
+        _LAST["solver"] = solver
+        return solver.integrate(th)
+    raise ValueError(f'Invalid method "{method}".')
+
+
+def _wrap_func(func, y0, decreasing: bool):
+    if decreasing:
+        return lambda tt, yy: -func((-tt).to(yy.dtype), yy)
+    return lambda tt, yy: func(tt.to(yy.dtype), yy)
+
+
+def odeint_adjoint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, event_fn=None, adjoint_rtol=None,
+                   adjoint_atol=None, adjoint_method=None, adjoint_options=None, adjoint_params=None):
+    """Drop-in for `torchdiffeq.odeint_adjoint`.
+
+    For the recognised drift nets on a fixed grid the backward pass is the fused discrete adjoint
+    (`ab200_rk4_backward`): O(T) saved rows, gradients equal to autograd through the solver to round-off, which is
+    what the reference's live training path computes.  Other cases integrate the augmented system backwards
+    (tdq adjoint.py), re-seeding y from the saved forward rows.
+    """
+    if adjoint_params is None and not isinstance(func, torch.nn.Module):
+        raise ValueError("func must be an instance of nn.Module to specify the adjoint parameters; alternatively they "
+                         "can be specified explicitly via the `adjoint_params` argument.")
+    method = "dopri5" if method is None else method
+    spec = describe_drift(func) if y0.dim() == 2 else None
+    if method == "rk4" and spec is not None:
+        return odeint(func, y0, t, rtol=rtol, atol=atol, method=method, options=options)
+    from .adjoint import continuous_adjoint
+    return continuous_adjoint(func, y0, t, rtol=rtol, atol=atol, method=method, options=options,
+                              adjoint_rtol=adjoint_rtol, adjoint_atol=adjoint_atol, adjoint_method=adjoint_method,
+                              adjoint_options=adjoint_options, adjoint_params=adjoint_params)

@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py -- agent-steps/s of the GAT-ODE hot path on N B200s (one process per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3] [--precision f32|bf16] [--impl reference]
+
+One "step" = one pass of the hot path over one batch of synthetic agents: the whole trajectory
+(T-1 solver intervals) for every agent of the batch, i.e. B*(T-1) agent-steps.
+  value : whole-job agent-steps/s with inputs resident in HBM (CUDA events, max over ranks)
+  e2e   : the same metric through the public module API with HOST (pinned) inputs, H2D and D2H in the timed region
+  roofline / cpu_baseline / clocks / gpu_launches : see DESIGN.md §Measurement
+`--impl reference` times the reference's CPU implementation of the path (the oracle port: the reference's
+own PyTorch ops + the restated torchdiffeq solver) on the host cores, same config/metric.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import torch
+
+REPO = Path(__file__).resolve().parent
+sys.path.insert(0, str(REPO))
+
+METRIC = "agent-steps/sec, GAT-ODE"
+WORKLOADS = {
+    # BASELINE.json configs[1]: 10k agents x 500-zone graph, 96 RK4 steps/day, single-head GAT, inference
+    "c2": dict(B=10_000, Z=500, T=97, heads=1, mode="inference", method="rk4",
+               name="configs[1]: 10k agents x 500 zones, 96 RK4 steps, 1-head GAT, inference"),
+    # BASELINE.json configs[2] shape with the fixed-grid solver: 1M agents x 10k zones, 4-head GAT, fwd+bwd
+    "c3": dict(B=1_000_000, Z=10_000, T=97, heads=4, mode="train", method="rk4",
+               name="configs[2] shape: 1M agents x 10k zones, 4-head GAT, 96 RK4 steps, fwd+bwd (agent-chunked)"),
+}
+ALG_FLOP_FWD = 755_712          # per agent-step, SURVEY.md §8(d) / BASELINE.md §3
+ALG_FLOP_FWDBWD = 3_022_848     # 4x forward (discrete adjoint with stage recompute)
+ALG_BYTES_FWD = 1_280
+ALG_BYTES_FWDBWD = 3_840
+
+
+def peaks():
+    p = REPO / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(hbm=float(d["hbm_gbs"]), tf_burst=float(d["bf16_tflops"]), tf_sust=float(d["bf16_tflops_sustained"]),
+                    src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(cfg, seed=42, device="cpu"):
+    """Synthetic inputs of SURVEY.md §8(d): one generator per tensor, seeds 42+k, made on the CPU."""
+    B, Z, T = cfg["B"], cfg["Z"], cfg["T"]
+    g = [torch.Generator().manual_seed(seed + k) for k in range(4)]
+    home = torch.randint(0, Z, (B,), generator=g[0])
+    work = torch.randint(0, Z, (B,), generator=g[1])
+    traits = torch.stack([torch.rand(B, generator=g[2]) * 0.72 + 0.18, torch.rand(B, generator=g[3]) * 1.4 + 0.1], dim=-1)
+    t = torch.linspace(0.0, 24.0, T)
+    return home, work, traits, t
+
+
+def build_model(cfg, precision, device):
+    import ananke_abm_b200 as ab
+    torch.manual_seed(42)
+    mc = ab.ModeSepConfig()
+    mc.precision = precision
+    return ab.ModeSepModel(cfg["Z"], mc).to(device)
+
+
+def labels_from_path(model, y_path, t_chunk=8):
+    """argmax zone label per (agent, time) without materialising [B,T,Z] at once (host-side glue)."""
+    T = y_path.shape[0]
+    out = []
+    for s in range(0, T, t_chunk):
+        _, logits, _ = model.head(y_path[s:s + t_chunk])
+        out.append(logits.argmax(-1))
+    return torch.cat(out, dim=1)
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    import ananke_abm_b200 as ab
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = dict(WORKLOADS[args.workload])
+    if args.agents:
+        cfg["B"] = args.agents
+    train = cfg["mode"] == "train"
+    chunk = min(cfg["B"], args.chunk)
+    B, T = cfg["B"], cfg["T"]
+    model = build_model(cfg, args.precision, dev)
+    home, work, traits, t = make_inputs(cfg, seed=42 + rank)
+    pin = lambda x: x.pin_memory()   # noqa: E731
+    h_home, h_work, h_traits, h_t = pin(home), pin(work), pin(traits), pin(t)
+    d_home, d_work, d_traits, d_t = (x.to(dev) for x in (home, work, traits, t))
+    params = [p for p in model.parameters()]
+
+    def hot_step(hm, wk, tr, tt):
+        """device-resident pass over all agents of this rank; returns a small device tensor"""
+        if not train:
+            with torch.no_grad():
+                acc = None
+                for s in range(0, B, chunk):
+                    y0 = model.initial_state(hm[s:s + chunk], wk[s:s + chunk], tr[s:s + chunk])
+                    y_path = model.integrate(y0, tt)
+                    acc = y_path[-1, :1, :1]
+                return acc
+        for p in params:
+            p.grad = None
+        total = None
+        for s in range(0, B, chunk):
+            y0 = model.initial_state(hm[s:s + chunk], wk[s:s + chunk], tr[s:s + chunk])
+            y_path = model.integrate(y0, tt)
+            loss = (y_path[:, :, :128] ** 2).mean()
+            loss.backward()
+            total = loss.detach() if total is None else total + loss.detach()
+        if world > 1:
+            flat = torch.cat([p.grad.reshape(-1) if p.grad is not None else torch.zeros_like(p).reshape(-1) for p in params])
+            dist.all_reduce(flat)
+        return total
+
+    def e2e_step():
+        hm = h_home.to(dev, non_blocking=True); wk = h_work.to(dev, non_blocking=True)
+        tr = h_traits.to(dev, non_blocking=True); tt = h_t.to(dev, non_blocking=True)
+        if not train:
+            with torch.no_grad():
+                outs = []
+                for s in range(0, B, chunk):
+                    y0 = model.initial_state(hm[s:s + chunk], wk[s:s + chunk], tr[s:s + chunk])
+                    y_path = model.integrate(y0, tt)
+                    outs.append(labels_from_path(model, y_path).to(torch.int32))
+                res = torch.cat(outs, dim=0)
+        else:
+            res = hot_step(hm, wk, tr, tt).reshape(1)
+        return res.to("cpu", non_blocking=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tms = torch.tensor([ms], device=dev)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            ms = float(tms.item())
+        return ms
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms = timed(lambda: hot_step(d_home, d_work, d_traits, d_t), args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # kernel-only time of the dominant kernel (fused RK4 trajectory) on the launching stream
+    n_chunks = (B + chunk - 1) // chunk
+    with torch.no_grad():
+        y0 = model.initial_state(d_home[:chunk], d_work[:chunk], d_traits[:chunk])
+        for _ in range(2):
+            model.integrate(y0, d_t)
+        torch.cuda.synchronize()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        k0.record()
+        for _ in range(reps):
+            yp = model.integrate(y0, d_t)
+        k1.record()
+        torch.cuda.synchronize()
+        kern_ms = k0.elapsed_time(k1) / reps
+        del yp
+    e2e_ms = timed(e2e_step, max(1, min(args.steps, 3)), 1)
+    e2e_steps = max(1, min(args.steps, 3))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    agent_steps = B * (T - 1)
+    value = world * agent_steps * args.steps / (ms * 1e-3)
+    e2e_value = world * agent_steps * e2e_steps / (e2e_ms * 1e-3)
+    flops_kernel = chunk * (T - 1) * ALG_FLOP_FWD
+    achieved_tf = flops_kernel / (kern_ms * 1e-3) / 1e12
+    bytes_kernel = chunk * (T - 1) * ALG_BYTES_FWD
+    h2d = sum(x.numel() * x.element_size() for x in (h_home, h_work, h_traits, h_t))
+    d2h = (B * T * 4) if not train else 4
+    out = {
+        "metric": METRIC + (" fwd+bwd" if train else " fwd (inference)"), "value": value, "unit": "agent-steps/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if args.precision == "f32" else "bf16 (fp32 accumulate, fp32 state)", "data": "synthetic",
+        "config": {"workload": cfg["name"], "agents_per_gpu": B, "zones": cfg["Z"], "time_points": T, "solver": cfg["method"],
+                   "agent_chunk": chunk, "precision": args.precision,
+                   "l2": "trajectory rows written per step (%.0f MB) exceed L2; weights are L2-resident by design" % (chunk * T * 640 / 1e6)},
+        "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": pk["tf_burst"], "unit": "TFLOP/s",
+                     "frac": achieved_tf / pk["tf_burst"], "traffic": None, "peak_source": pk["src"],
+                     "kernel": "rk4 fused trajectory (forward)", "kernel_ms": kern_ms,
+                     "alg_flop_per_agent_step": ALG_FLOP_FWD, "alg_bytes_per_agent_step": ALG_BYTES_FWD,
+                     "hbm_achieved_gbs": bytes_kernel / (kern_ms * 1e-3) / 1e9, "hbm_peak_gbs": pk["hbm"]},
+        "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms / e2e_steps},
+        "gpu_launches": args.steps * n_chunks * (2 if not train else 7),
+        "clocks": clocks,
+    }
+    if not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(cfg, train, budget_s=20.0)
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(cfg, train, budget_s=20.0, steps=1, warmup=0):
+    """The oracle port (reference's PyTorch ops + restated solver) on the host cores, bounded sample."""
+    from oracle import models_oracle as mo
+    from oracle import torchdiffeq_oracle as tdq
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    Bs = min(cfg["B"], 10_000 if not train else 2_000)
+    Ts = cfg["T"] if not train else min(cfg["T"], 25)
+    sub = dict(cfg, B=Bs, T=Ts)
+    home, work, traits, _ = make_inputs(sub)
+    t = torch.linspace(0.0, 24.0, cfg["T"])[:Ts]
+    torch.manual_seed(42)
+    m = mo.OracleModeSep(cfg["Z"])
+    best = None
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        if not train:
+            with torch.no_grad():
+                y0 = m.initial_state(home, work, traits)
+                tdq.odeint(m.rhs, y0, t, method="rk4")
+        else:
+            m.zero_grad()
+            y0 = m.initial_state(home, work, traits)
+            yp = tdq.odeint(m.rhs, y0, t, method="rk4")
+            (yp[:, :, :128] ** 2).mean().backward()
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            best = dt if best is None else min(best, dt)
+    return {"value": Bs * (Ts - 1) / best, "unit": "agent-steps/s", "cores": cores, "kind": "port",
+            "sample": f"{Bs} agents x {Ts - 1} rk4 steps of the same workload ({'fwd+bwd' if train else 'fwd'}), "
+                      f"torch CPU fp32, {cores} threads, best of {steps}", "seconds": best}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = dict(WORKLOADS[args.workload])
+    train = cfg["mode"] == "train"
+    t0 = time.perf_counter()
+    cb = cpu_baseline(cfg, train, steps=max(1, min(args.steps, 3)), warmup=1 if args.warmup else 0)
+    out = {"impl": "reference", "metric": METRIC + (" fwd+bwd" if train else " fwd (inference)"), "value": cb["value"],
+           "unit": "agent-steps/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": cb["seconds"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic", "config": {"workload": cfg["name"], "sample": cb["sample"]},
+           "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "wall_s": time.perf_counter() - t0}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="f32", choices=["f32", "bf16"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--agents", type=int, default=0, help="override agents per GPU")
+    ap.add_argument("--chunk", type=int, default=262_144, help="agents per fused launch")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

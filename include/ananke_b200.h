@@ -1,0 +1,121 @@
+/* ananke_b200 -- C ABI of the B200-native GAT-ODE hot path.
+ *
+ * Plain C: pointers, sizes, an opaque stream handle.  No torch types cross this boundary; the caller
+ * (PyTorch on the host side) owns every buffer, the library never allocates or frees device memory,
+ * keeps no global state and is stream-ordered and re-entrant.  Every entry point returns 0 on success
+ * or a negative `ab200_status`; nothing throws across the ABI.  Asynchronous CUDA faults surface at the
+ * caller's next synchronisation (the Python wrapper checks `ab200_last_cuda_error`).
+ *
+ * Each entry point cites the reference interface (under /root/reference/src/ananke_abm/models/) it
+ * stands in for.  The solver arithmetic itself lives in the reference's un-vendored dependency
+ * torchdiffeq==0.2.5 (uv.lock:2896-2897); "tdq:" cites that package's module.
+ */
+#ifndef ANANKE_B200_H_
+#define ANANKE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AB200_ABI_VERSION 1
+
+typedef void* ab200_stream_t; /* a cudaStream_t */
+
+typedef enum ab200_status {
+  AB200_OK = 0,
+  AB200_ERR_BAD_ARG = -1,       /* null pointer, non-positive size, T < 1 ... */
+  AB200_ERR_UNSUPPORTED = -2,   /* drift-net shape not instantiated in this build */
+  AB200_ERR_WORKSPACE = -3,     /* workspace too small: call *_workspace_bytes */
+  AB200_ERR_CUDA = -4,          /* launch failed: see ab200_last_cuda_error */
+  AB200_ERR_NOT_MONOTONE = -5,  /* time grid must be strictly increasing (tdq: odeint.py _check_inputs) */
+  AB200_ERR_DT_UNDERFLOW = -6,  /* tdq: rk_common.py "underflow in dt" */
+  AB200_ERR_MAX_STEPS = -7      /* tdq: rk_common.py "max_num_steps exceeded" */
+} ab200_status;
+
+/* Arithmetic mode of the drift-net GEMMs. */
+typedef enum ab200_precision {
+  AB200_PREC_F32 = 0,   /* strict: fp32 FFMA, fp32 accumulate -- the 1e-5 parity path           */
+  AB200_PREC_BF16 = 1,  /* tcgen05 bf16 x bf16 -> fp32 (TMEM accumulators); state stays fp32     */
+  AB200_PREC_BF16X3 = 2 /* tcgen05 3-term bf16 split of both operands (6 MMAs), fp32-grade       */
+} ab200_precision;
+
+/* The "second-order residual-MLP drift" both reference models use as ODE right-hand side:
+ *   y = [p(P), v(P), h(H)],   dy/dt = [v, net([p, v, h, sin(2 pi t/period), cos(2 pi t/period)]) + corr(p), 0]
+ *   net = Linear(2P+H+2, hid) -> ReLU -> n_res x ResidualBlock(hid) -> Linear(hid, P)
+ *   ResidualBlock(x) = act(x + Linear(act(Linear(x))))
+ * mode_sep:   P=64, H=32, hid=128, n_res=2, act=ReLU, no correction
+ *             (mode_sep/architecture/model.py:16-38 ODEFunc/ResidualBlock, :56-73 WrappedSDE.forward)
+ * latent_ode: P=16, H=32, hid=128, n_res=2, act=Tanh, potential correction on p[idx_a], p[idx_b]
+ *             (latent_ode/architecture/model.py:9-17, :46-51, :56-74, :77-117)
+ */
+typedef struct ab200_drift_desc {
+  int32_t pos_dim;        /* P */
+  int32_t ctx_dim;        /* H */
+  int32_t hidden;         /* hid */
+  int32_t n_res;          /* residual blocks */
+  int32_t res_act;        /* 0 = ReLU, 1 = Tanh (activation inside/after residual blocks) */
+  int32_t potential;      /* 0 = none; 1 = latent_ode (sigmoid(p[a]) + sigmoid(p[b]) - 1)^2 correction */
+  int32_t pot_idx_a;      /* index into p of the "is_moving" logit      (latent: 12) */
+  int32_t pot_idx_b;      /* index into p of the "is_stationary" logit  (latent: 8)  */
+  float pot_strength;     /* config.correction_strength */
+  float time_period;      /* 24.0 */
+} ab200_drift_desc;
+
+/* Number of fp32 parameters of the drift net, in `nn.Module.parameters()` order:
+ *   w_in[hid, 2P+H+2], b_in[hid], { w_a[hid,hid], b_a[hid], w_b[hid,hid], b_b[hid] } x n_res,
+ *   w_out[P, hid], b_out[P]          (row-major [out, in], exactly torch's nn.Linear storage). */
+int64_t ab200_drift_param_count(const ab200_drift_desc* d);
+
+int ab200_abi_version(void);
+const char* ab200_status_string(int status);
+/* Last CUDA runtime error string seen by this thread inside the library ("" if none). */
+const char* ab200_last_cuda_error(void);
+
+/* ---- fixed-grid RK4 (3/8 rule), whole trajectory in one launch --------------------------------
+ * Replaces  odeint(self.odefunc, y0, times_union, method="rk4", rtol=, atol=)
+ *           mode_sep/architecture/model.py:184-191     (tdq: fixed_grid.py RK4, rk_common.py rk4_alt_step_func)
+ * y0     [B, D]  fp32, D = 2P+H          t [T] fp32 strictly increasing (host or device copy `t_host` is
+ * y_path [T, B, D] fp32, row 0 = y0      used for validation only and may be NULL)
+ */
+size_t ab200_rk4_workspace_bytes(const ab200_drift_desc* d, int64_t B, int32_t T, int32_t precision);
+int ab200_rk4_forward(const ab200_drift_desc* d, const float* w_flat, const float* y0, const float* t_dev,
+                      const float* t_host, int64_t B, int32_t T, float* y_path, void* workspace,
+                      size_t workspace_bytes, int32_t precision, ab200_stream_t stream);
+
+/* Discrete adjoint of the call above == reverse-mode autograd through every solver op, which is what the
+ * live reference training path does (mode_sep/train/train.py:162 `total.backward()`).
+ * grad_y_path [T, B, D] : dL/dy_path (may alias nothing).   Outputs: grad_y0 [B, D], grad_w_flat
+ * [ab200_drift_param_count] (OVERWRITTEN, not accumulated). */
+size_t ab200_rk4_backward_workspace_bytes(const ab200_drift_desc* d, int64_t B, int32_t T, int32_t precision);
+int ab200_rk4_backward(const ab200_drift_desc* d, const float* w_flat, const float* t_dev, const float* y_path,
+                       const float* grad_y_path, int64_t B, int32_t T, float* grad_y0, float* grad_w_flat,
+                       void* workspace, size_t workspace_bytes, int32_t precision, ab200_stream_t stream);
+
+/* ---- one stand-alone drift evaluation f(t, y) (parity probe; also used by the generic path) ----
+ * Replaces WrappedSDE.forward / ODEFunc.forward (files above).  y, out: [B, D]. */
+size_t ab200_drift_eval_workspace_bytes(const ab200_drift_desc* d, int64_t B, int32_t precision);
+int ab200_drift_eval(const ab200_drift_desc* d, const float* w_flat, float t, const float* y, int64_t B,
+                     float* out, void* workspace, size_t workspace_bytes, int32_t precision,
+                     ab200_stream_t stream);
+
+/* ---- generic-func path: fused Runge-Kutta stage combine (+ error norm) ------------------------
+ * For an arbitrary `func` evaluated by the caller.  out[i] = y[i] + dt * sum_j coef[j] * k_j[i]
+ * (tdq: rk_common.py `_runge_kutta_step`: yi = y0 + sum(k[..., :i+1] * (beta_i * dt))).
+ * `k` is an array of `n_k` device pointers held in HOST memory; n_k <= 8. */
+int ab200_rk_stage_combine(const float* y, const float* const* k, const float* coef_host, int32_t n_k, float dt,
+                           float* out, int64_t n, ab200_stream_t stream);
+/* Same pass additionally forms the embedded error estimate and accumulates
+ *   sum_i ( (dt * sum_j cerr[j] k_j[i]) / (atol + rtol * max(|y0[i]|, |y1[i]|)) )^2   into *sumsq (device,
+ * fp32, must be zeroed by the caller) -- tdq: misc.py `_compute_error_ratio` with `_rms_norm`.
+ * y1 = y0 + dt * sum_j csol[j] k_j  is written to `y1_out` (skipped when `y1_out` is NULL). */
+int ab200_rk_combine_errnorm(const float* y0, const float* const* k, const float* csol_host,
+                             const float* cerr_host, int32_t n_k, float dt, float rtol, float atol,
+                             float* y1_out, float* sumsq, int64_t n, ab200_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ANANKE_B200_H_ */

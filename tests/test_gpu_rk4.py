@@ -1,0 +1,225 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle and the golden vectors."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import models_oracle as mo
+from oracle import torchdiffeq_oracle as tdq
+
+
+def _cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+def _load_sd(model, g, prefix):
+    sd = {k[len(prefix):]: torch.from_numpy(g[k]) for k in g.files if k.startswith(prefix)}
+    model.load_state_dict(sd, strict=True)
+    return model
+
+
+def _rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def test_library_loads_on_gpu_box():
+    import ananke_abm_b200 as ab
+    assert ab.lib().ab200_abi_version() == 1
+
+
+def test_drift_eval_matches_reference_rhs(golden_rhs):
+    import ananke_abm_b200 as ab
+    dev = _cuda()
+    # mode_sep drift
+    m = _load_sd(ab.ModeSepModel(8, ab.ModeSepConfig()), golden_rhs, "ms_sd_").to(dev)
+    y = torch.from_numpy(golden_rhs["ms_y"]).to(dev)
+    for i in range(3):
+        f = m.odefunc(torch.tensor(float(golden_rhs[f"ms_t{i}"])), y).cpu()
+        ref = torch.from_numpy(golden_rhs[f"ms_f{i}"])
+        assert _rel(f, ref) < 1e-5, (i, _rel(f, ref))
+        assert torch.equal(f[:, 128:], torch.zeros_like(f[:, 128:]))
+        assert torch.equal(f[:, :64], y[:, 64:128].cpu())
+    # latent drift (tanh residual blocks + potential correction), via the framework's own drift module
+    lo = _load_sd(mo.OracleLatentODE(8, 7), golden_rhs, "lo_sd_")
+    drift = ab.SecondOrderDrift(16, 32, 128, 2, "tanh", potential=(12, 8, 1.0)).to(dev)
+    drift.net.load_state_dict(lo.ode_func.net.state_dict())
+    y2 = torch.from_numpy(golden_rhs["lo_y"]).to(dev)
+    for i in range(3):
+        f = drift(torch.tensor(float(golden_rhs[f"lo_t{i}"])), y2).cpu()
+        ref = torch.from_numpy(golden_rhs[f"lo_f{i}"])
+        assert _rel(f, ref) < 1e-5, (i, _rel(f, ref))
+
+
+def test_mode_sep_fixture_forward_matches_golden(golden_mode_sep):
+    """BASELINE config 1: reference fixtures, B=2, T=91, Z=8, rk4, seed 42."""
+    import ananke_abm_b200 as ab
+    dev = _cuda()
+    g = golden_mode_sep
+    m = _load_sd(ab.ModeSepModel(8, ab.ModeSepConfig()), g, "sd_").to(dev)
+    t = torch.from_numpy(g["times_union"]).to(dev)
+    home, work, traits = (torch.from_numpy(g[k]).to(dev) for k in ("home_idx", "work_idx", "traits"))
+    with torch.no_grad():
+        y0 = m.initial_state(home, work, traits)
+        y_path = m.integrate(y0, t)
+        pred, logits, v_t = m.head(y_path)
+    assert y_path.shape == (91, 2, 160)
+    assert torch.equal(y_path[0], y0)
+    assert _rel(y_path.cpu(), torch.from_numpy(g["y_path"])) < 1e-5
+    assert _rel(pred.cpu(), torch.from_numpy(g["pred_emb"])) < 1e-5
+    assert _rel(v_t.cpu(), torch.from_numpy(g["v_t"])) < 1e-5
+    assert np.array_equal(logits.argmax(-1).cpu().numpy(), g["labels"])
+    # h is carried unchanged
+    assert torch.equal(y_path[:, :, 128:], y0[None, :, 128:].expand(91, -1, -1))
+
+
+@pytest.mark.parametrize("B,T", [(1, 2), (63, 5), (64, 3), (65, 4), (300, 25)])
+def test_rk4_forward_ragged_sizes_vs_oracle(B, T):
+    import ananke_abm_b200 as ab
+    dev = _cuda()
+    torch.manual_seed(11)
+    oracle = mo.OracleModeSep(8)
+    m = ab.ModeSepModel(8, ab.ModeSepConfig())
+    m.load_state_dict(oracle.state_dict())
+    m = m.to(dev)
+    g = torch.Generator().manual_seed(B * 1000 + T)
+    y0 = torch.randn(B, 160, generator=g) * 0.3
+    t = torch.sort(torch.rand(T, generator=g) * 24.0).values
+    t = t + torch.arange(T) * 1e-3
+    ref = tdq.odeint(oracle.rhs, y0, t, method="rk4")
+    with torch.no_grad():
+        out = ab.odeint(m.odefunc, y0.to(dev), t.to(dev), method="rk4", rtol=1e-5, atol=1e-5)
+    assert out.shape == ref.shape
+    assert _rel(out.cpu(), ref.detach()) < 1e-5
+
+
+def test_rk4_single_time_point_returns_y0():
+    import ananke_abm_b200 as ab
+    dev = _cuda()
+    m = ab.ModeSepModel(8, ab.ModeSepConfig()).to(dev)
+    y0 = torch.randn(5, 160, device=dev)
+    out = ab.odeint(m.odefunc, y0, torch.tensor([3.0], device=dev), method="rk4")
+    assert out.shape == (1, 5, 160) and torch.equal(out[0], y0)
+
+
+def test_errors_mirror_torchdiffeq():
+    import ananke_abm_b200 as ab
+    dev = _cuda()
+    m = ab.ModeSepModel(8, ab.ModeSepConfig()).to(dev)
+    y0 = torch.randn(4, 160, device=dev)
+    with pytest.raises(AssertionError):
+        ab.odeint(m.odefunc, y0, torch.tensor([0.0, 2.0, 1.0], device=dev), method="rk4")
+    with pytest.raises(ValueError):
+        ab.odeint(m.odefunc, y0, torch.tensor([0.0, 2.0], device=dev), method="no_such_method")
+    with pytest.raises(ab.Ab200Error):
+        ab.odeint(m.odefunc, y0.cpu(), torch.tensor([0.0, 2.0]), method="rk4")
+
+
+def test_rk4_backward_matches_autograd_through_oracle():
+    import ananke_abm_b200 as ab
+    dev = _cuda()
+    torch.manual_seed(5)
+    oracle = mo.OracleModeSep(8)
+    m = ab.ModeSepModel(8, ab.ModeSepConfig())
+    m.load_state_dict(oracle.state_dict())
+    m = m.to(dev)
+    B, T = 45, 7
+    g = torch.Generator().manual_seed(3)
+    y0 = (torch.randn(B, 160, generator=g) * 0.3)
+    t = torch.linspace(0.0, 6.0, T)
+    w = torch.randn(T, B, 160, generator=g)
+
+    y0_ref = y0.clone().requires_grad_(True)
+    ref = tdq.odeint(oracle.rhs, y0_ref, t, method="rk4")
+    (ref * w).sum().backward()
+
+    y0_dev = y0.to(dev).requires_grad_(True)
+    out = ab.odeint(m.odefunc, y0_dev, t.to(dev), method="rk4")
+    (out * w.to(dev)).sum().backward()
+
+    assert _rel(out.detach().cpu(), ref.detach()) < 1e-5
+    assert _rel(y0_dev.grad.cpu(), y0_ref.grad) < 1e-5
+    ref_grads = dict(oracle.odefunc.func.net.named_parameters())
+    for name, p in m.odefunc.func.net.named_parameters():
+        r = ref_grads[name].grad
+        assert p.grad is not None, name
+        assert _rel(p.grad.cpu(), r) < 2e-5, (name, _rel(p.grad.cpu(), r))
+
+
+def test_mode_sep_fixture_training_gradients_match_golden(golden_mode_sep):
+    """Full reference training loss (mode_sep/train/train.py:101-159) on the fixtures: every parameter gradient."""
+    import ananke_abm_b200 as ab
+    from tests.ref_losses import mode_sep_training_loss
+    dev = _cuda()
+    g = golden_mode_sep
+    m = _load_sd(ab.ModeSepModel(8, ab.ModeSepConfig()), g, "sd_").to(dev)
+    t = torch.from_numpy(g["times_union"]).to(dev)
+    home, work, traits = (torch.from_numpy(g[k]).to(dev) for k in ("home_idx", "work_idx", "traits"))
+    pred, logits, v = m(t, home, work, traits)
+    loss = mode_sep_training_loss(g, pred, logits, v, m.class_table, dev)
+    assert abs(float(loss) - float(g["loss_total"])) < 1e-4 * abs(float(g["loss_total"]))
+    loss.backward()
+    for name, p in m.named_parameters():
+        ref = torch.from_numpy(g["grad_" + name])
+        got = p.grad.cpu() if p.grad is not None else torch.zeros_like(ref)
+        scale = ref.abs().max().clamp_min(1e-12)
+        assert float((got - ref).abs().max() / scale) < 5e-5, (name, float((got - ref).abs().max() / scale))
+
+
+def test_latent_drift_rk4_forward_and_backward_vs_oracle(golden_rhs):
+    import ananke_abm_b200 as ab
+    dev = _cuda()
+    lo = _load_sd(mo.OracleLatentODE(8, 7), golden_rhs, "lo_sd_")
+    drift = ab.SecondOrderDrift(16, 32, 128, 2, "tanh", potential=(12, 8, 1.0)).to(dev)
+    drift.net.load_state_dict(lo.ode_func.net.state_dict())
+    g = torch.Generator().manual_seed(9)
+    B, T = 37, 6
+    y0 = torch.randn(B, 64, generator=g) * 0.4
+    t = torch.linspace(0, 3.0, T)
+    w = torch.randn(T, B, 64, generator=g)
+    y0r = y0.clone().requires_grad_(True)
+    ref = tdq.odeint(lo.rhs, y0r, t, method="rk4")
+    (ref * w).sum().backward()
+    y0d = y0.to(dev).requires_grad_(True)
+    out = ab.odeint(drift, y0d, t.to(dev), method="rk4")
+    (out * w.to(dev)).sum().backward()
+    assert _rel(out.detach().cpu(), ref.detach()) < 1e-5
+    assert _rel(y0d.grad.cpu(), y0r.grad) < 2e-5
+    ref_grads = dict(lo.ode_func.net.named_parameters())
+    for name, p in drift.net.named_parameters():
+        assert _rel(p.grad.cpu(), ref_grads[name].grad) < 5e-5, name
+
+
+def test_generic_func_rk4_and_dopri5_vs_oracle():
+    import ananke_abm_b200 as ab
+    dev = _cuda()
+
+    class F(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            torch.manual_seed(0)
+            self.a = torch.nn.Linear(6, 6)
+
+        def forward(self, t, y):
+            return torch.tanh(self.a(y)) * torch.cos(t)
+    f_cpu = F()
+    f_dev = F().to(dev)
+    y0 = torch.randn(50, 6, generator=torch.Generator().manual_seed(1))
+    t = torch.linspace(0, 2.0, 9)
+    ref = tdq.odeint(f_cpu, y0, t, method="rk4")
+    out = ab.odeint(f_dev, y0.to(dev), t.to(dev), method="rk4")
+    assert _rel(out.detach().cpu(), ref.detach()) < 1e-5
+    ref5 = tdq.odeint(f_cpu, y0, t, method="dopri5", rtol=1e-5, atol=1e-6)
+    n_ref = tdq._LAST_SOLVER["solver"].n_accepted
+    out5 = ab.odeint(f_dev, y0.to(dev), t.to(dev), method="dopri5", rtol=1e-5, atol=1e-6)
+    from ananke_abm_b200 import odeint as oi
+    assert _rel(out5.detach().cpu(), ref5.detach()) < 1e-4
+    assert abs(oi._LAST["solver"].n_accepted - n_ref) <= 2
+    # decreasing time grid
+    tr = torch.linspace(2.0, 0.0, 9)
+    refr = tdq.odeint(f_cpu, y0, tr, method="rk4")
+    outr = ab.odeint(f_dev, y0.to(dev), tr.to(dev), method="rk4")
+    assert _rel(outr.detach().cpu(), refr.detach()) < 1e-5
