@@ -71,6 +71,7 @@ def _parse_net(net) -> Optional[Tuple[List[torch.Tensor], int, int, int, int, in
             return None
         params += [l1.weight, l1.bias, l2.weight, l2.bias]
     n_res = len(mods) - 3
+    params += [last.weight, last.bias]
     return params, first.in_features, first.out_features, n_res, (act_code or 0), last.out_features
 
 

@@ -70,6 +70,9 @@ class _FusedRK4(torch.autograd.Function):
         tc = t.contiguous().float()
         wc = w_flat.contiguous().float()
         th = t_host.contiguous().float()
+        n_par = L.ab200_drift_param_count(C.byref(spec.desc))
+        if wc.numel() != n_par:
+            raise _lib.Ab200Error(f"drift parameter vector has {wc.numel()} elements, the descriptor needs {n_par}")
         y_path = torch.empty((T, B, D), dtype=torch.float32, device=y0.device)
         nbytes = L.ab200_rk4_workspace_bytes(C.byref(spec.desc), B, T, precision)
         ws = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=y0.device)
@@ -104,6 +107,9 @@ def drift_eval(spec: DriftSpec, w_flat: torch.Tensor, t: float, y: torch.Tensor,
     L = _lib.lib()
     _require_cuda(y, "y")
     B = y.shape[0]
+    n_par = L.ab200_drift_param_count(C.byref(spec.desc))
+    if w_flat.numel() != n_par:
+        raise _lib.Ab200Error(f"drift parameter vector has {w_flat.numel()} elements, the descriptor needs {n_par}")
     out = torch.empty_like(y, dtype=torch.float32)
     nbytes = L.ab200_drift_eval_workspace_bytes(C.byref(spec.desc), B, precision)
     ws = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=y.device)
