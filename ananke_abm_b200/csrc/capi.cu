@@ -24,6 +24,12 @@ int rk_stage_combine(const float* y, const float* const* k, const float* coef, i
 int rk_combine_errnorm(const float* y0, const float* const* k, const float* csol, const float* cerr, int n_k, float dt,
                        float rtol, float atol, float* y1_out, float* sumsq, int64_t n, cudaStream_t st);
 
+int umma_probe(const float* A, const float* B, float* D, int N, int K, int a_mode, int b_mode, int* status, cudaStream_t st);
+
+size_t rk4_tc_workspace(const ab200_drift_desc* d);
+int rk4_forward_tc(const ab200_drift_desc* d, const float* w_flat, const float* y0, const float* t_dev, int64_t B, int T,
+                   float* y_path, void* ws, size_t ws_bytes, cudaStream_t st);
+
 static bool desc_ok(const ab200_drift_desc* d) {
   return d && d->pos_dim > 0 && d->ctx_dim >= 0 && d->hidden > 0 && d->n_res >= 0 && (d->res_act == 0 || d->res_act == 1);
 }
@@ -63,7 +69,8 @@ int64_t ab200_drift_param_count(const ab200_drift_desc* d) {
 
 size_t ab200_rk4_workspace_bytes(const ab200_drift_desc* d, int64_t B, int32_t T, int32_t precision) {
   if (!desc_ok(d)) return 0;
-  (void)B; (void)T; (void)precision;
+  (void)B; (void)T;
+  if (precision == AB200_PREC_BF16) return rk4_tc_workspace(d);
   return packed_bytes(d);
 }
 
@@ -74,12 +81,17 @@ int ab200_rk4_forward(const ab200_drift_desc* d, const float* w_flat, const floa
   if (t_host)
     for (int i = 0; i + 1 < T; ++i)
       if (!(t_host[i + 1] > t_host[i])) return AB200_ERR_NOT_MONOTONE;
+  if (precision == AB200_PREC_BF16 && rk4_tc_workspace(d) == 0) return AB200_ERR_UNSUPPORTED;
   if (workspace_bytes < ab200_rk4_workspace_bytes(d, B, T, precision)) return AB200_ERR_WORKSPACE;
   cudaStream_t st = (cudaStream_t)stream;
   if (precision == AB200_PREC_F32) {
     int rc = pack_drift(d, w_flat, (float*)workspace, st);
     if (rc) return rc;
     return rk4_forward_f32(d, (const float*)workspace, y0, t_dev, B, T, y_path, st);
+  }
+  if (precision == AB200_PREC_BF16) {
+    if (rk4_tc_workspace(d) == 0) return AB200_ERR_UNSUPPORTED;
+    return rk4_forward_tc(d, w_flat, y0, t_dev, B, T, y_path, workspace, workspace_bytes, st);
   }
   return AB200_ERR_UNSUPPORTED;
 }
@@ -129,6 +141,12 @@ int ab200_rk_combine_errnorm(const float* y0, const float* const* k, const float
                              ab200_stream_t stream) {
   if (!y0 || !k || !csol_host || !cerr_host || !sumsq || n <= 0) return AB200_ERR_BAD_ARG;
   return rk_combine_errnorm(y0, k, csol_host, cerr_host, n_k, dt, rtol, atol, y1_out, sumsq, n, (cudaStream_t)stream);
+}
+
+int ab200_debug_umma_probe(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t a_mode, int32_t b_mode,
+                           int32_t* status, ab200_stream_t stream) {
+  if (!A || !B || !D || !status) return AB200_ERR_BAD_ARG;
+  return umma_probe(A, B, D, N, K, a_mode, b_mode, status, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -115,6 +115,12 @@ int ab200_rk_combine_errnorm(const float* y0, const float* const* k, const float
                              const float* cerr_host, int32_t n_k, float dt, float rtol, float atol,
                              float* y1_out, float* sumsq, int64_t n, ab200_stream_t stream);
 
+/* ---- self-test of the tcgen05 plumbing (one CTA): D[128,N] = A[128,K] * B[N,K]^T, bf16 operands, fp32 result.
+ * a_mode 0/1/2 = A in TMEM / smem un-swizzled / smem 128B-swizzled; b_mode 1/2 = B un-swizzled / 128B-swizzled.
+ * `status` (device int) receives 0, or 1 if the MMA completion barrier timed out.  No reference counterpart. */
+int ab200_debug_umma_probe(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t a_mode,
+                           int32_t b_mode, int32_t* status, ab200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -224,3 +224,53 @@ def test_generic_func_rk4_and_dopri5_vs_oracle():
     refr = tdq.odeint(f_cpu, y0, tr, method="rk4")
     outr = ab.odeint(f_dev, y0.to(dev), tr.to(dev), method="rk4")
     assert _rel(outr.detach().cpu(), refr.detach()) < 1e-5
+
+
+def test_umma_probe_all_operand_layouts():
+    """tcgen05 plumbing self-test: every A/B placement and shared-memory layout the kernels may use."""
+    import ananke_abm_b200 as ab
+    dev = _cuda()
+    L = ab.lib()
+    torch.manual_seed(0)
+    for (N, K) in [(128, 128), (64, 128), (128, 192)]:
+        A = torch.randn(128, K, device=dev)
+        B = torch.randn(N, K, device=dev)
+        ref = A.bfloat16().float() @ B.bfloat16().float().T
+        for a_mode in (0, 1, 2):
+            for b_mode in (1, 2):
+                D = torch.zeros(128, N, device=dev)
+                st = torch.full((1,), -7, dtype=torch.int32, device=dev)
+                rc = L.ab200_debug_umma_probe(A.data_ptr(), B.data_ptr(), D.data_ptr(), N, K, a_mode, b_mode, st.data_ptr(),
+                                              torch.cuda.current_stream().cuda_stream)
+                torch.cuda.synchronize()
+                assert rc == 0 and int(st) == 0, (N, K, a_mode, b_mode, rc, int(st))
+                assert float((D - ref).abs().max()) < 1e-3, (N, K, a_mode, b_mode)
+
+
+# Stated tolerance of the tensor-core (bf16 operands, fp32 accumulate, fp32 state) path against the strict path:
+# 2e-2 of the trajectory's scale over a full 96-step day, and >= 99% identical predicted zone labels.
+BF16_TRAJ_TOL = 2e-2
+
+
+@pytest.mark.parametrize("B,T", [(1, 3), (127, 4), (128, 2), (129, 9), (1000, 97)])
+def test_rk4_bf16_tensor_core_path_within_stated_tolerance(B, T):
+    import ananke_abm_b200 as ab
+    dev = _cuda()
+    torch.manual_seed(42)
+    m = ab.ModeSepModel(50, ab.ModeSepConfig()).to(dev)
+    g = torch.Generator().manual_seed(B + T)
+    home = torch.randint(0, 50, (B,), generator=g).to(dev)
+    work = torch.randint(0, 50, (B,), generator=g).to(dev)
+    traits = torch.rand(B, 2, generator=g).to(dev)
+    t = torch.linspace(0.0, 24.0 * (T - 1) / 96.0, T, device=dev)
+    with torch.no_grad():
+        y0 = m.initial_state(home, work, traits)
+        ref = ab.odeint(m.odefunc, y0, t, method="rk4", options={"precision": "f32"})
+        out = ab.odeint(m.odefunc, y0, t, method="rk4", options={"precision": "bf16"})
+    assert out.shape == ref.shape and not torch.isnan(out).any()
+    assert torch.equal(out[0], y0)
+    assert torch.equal(out[:, :, 128:], ref[:, :, 128:])          # h is carried exactly
+    assert _rel(out, ref) < BF16_TRAJ_TOL, _rel(out, ref)
+    lab_ref = m.head(ref)[1].argmax(-1)
+    lab = m.head(out)[1].argmax(-1)
+    assert float((lab == lab_ref).float().mean()) >= 0.99
