@@ -10,5 +10,9 @@ from ._lib import Ab200Error, lib  # noqa: F401
 from .drift import SecondOrderDrift, describe_drift  # noqa: F401
 from .odeint import odeint, odeint_adjoint, set_default_precision, drift_eval  # noqa: F401
 from .mode_sep import ModeSepConfig, ModeSepModel  # noqa: F401
+from .gnn_embed import GATEmbed, gnn_embed  # noqa: F401
+from .graph import ZoneCSR, build_zone_csr  # noqa: F401
+from .run import GATODEModel  # noqa: F401
+from . import inference, run  # noqa: F401
 
 __version__ = "0.1.0"

@@ -11,8 +11,8 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libananke_b200.so"
-SOURCES = ["capi.cu", "rk4_f32.cu", "rk4_bwd_f32.cu", "rk_combine.cu", "umma_probe.cu"]
-OPTIONAL = ["rk4_tc.cu", "gat.cu", "dopri5_f32.cu", "head.cu"]
+SOURCES = ["capi.cu", "rk4_f32.cu", "rk4_bwd_f32.cu", "rk_combine.cu", "umma_probe.cu", "rk4_tc.cu", "gat.cu"]
+OPTIONAL = ["dopri5_f32.cu", "head.cu", "rk4_bwd_tc.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",

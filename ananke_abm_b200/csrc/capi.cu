@@ -30,6 +30,16 @@ size_t rk4_tc_workspace(const ab200_drift_desc* d);
 int rk4_forward_tc(const ab200_drift_desc* d, const float* w_flat, const float* y0, const float* t_dev, int64_t B, int T,
                    float* y_path, void* ws, size_t ws_bytes, cudaStream_t st);
 
+int gat_forward(const int* rowptr, const int* col, int Z, int nnz, const float* x, int F_in, const float* W, const float* att_src,
+                const float* att_dst, const float* bias, int heads, int F_out, int concat, float slope, float* out, float* xw,
+                float* a_src, float* a_dst, float* alpha, cudaStream_t st);
+size_t gat_backward_workspace(int Z, int nnz, int heads, int F_out);
+int gat_backward(const int* rowptr, const int* col, const int* rowptr_t, const int* col_t, const int* eid_t, int Z, int nnz,
+                 const float* x, int F_in, const float* W, const float* att_src, const float* att_dst, int heads, int F_out,
+                 int concat, float slope, const float* xw, const float* a_src, const float* a_dst, const float* alpha,
+                 const float* gout, float* grad_x, float* grad_W, float* grad_att_src, float* grad_att_dst, float* grad_bias,
+                 void* ws, size_t ws_bytes, cudaStream_t st);
+
 static bool desc_ok(const ab200_drift_desc* d) {
   return d && d->pos_dim > 0 && d->ctx_dim >= 0 && d->hidden > 0 && d->n_res >= 0 && (d->res_act == 0 || d->res_act == 1);
 }
@@ -141,6 +151,35 @@ int ab200_rk_combine_errnorm(const float* y0, const float* const* k, const float
                              ab200_stream_t stream) {
   if (!y0 || !k || !csol_host || !cerr_host || !sumsq || n <= 0) return AB200_ERR_BAD_ARG;
   return rk_combine_errnorm(y0, k, csol_host, cerr_host, n_k, dt, rtol, atol, y1_out, sumsq, n, (cudaStream_t)stream);
+}
+
+int ab200_gat_forward(const int32_t* rowptr, const int32_t* col, int32_t Z, int32_t nnz, const float* x, int32_t F_in,
+                      const float* W, const float* att_src, const float* att_dst, const float* bias, int32_t heads, int32_t F_out,
+                      int32_t concat, float negative_slope, float* out, float* xw, float* a_src, float* a_dst, float* alpha,
+                      ab200_stream_t stream) {
+  if (!rowptr || !col || !x || !W || !att_src || !att_dst || !out || !xw || !a_src || !a_dst || !alpha || Z <= 0 || nnz < 0)
+    return AB200_ERR_BAD_ARG;
+  return gat_forward(rowptr, col, Z, nnz, x, F_in, W, att_src, att_dst, bias, heads, F_out, concat, negative_slope, out, xw, a_src,
+                     a_dst, alpha, (cudaStream_t)stream);
+}
+
+size_t ab200_gat_backward_workspace_bytes(int32_t Z, int32_t nnz, int32_t heads, int32_t F_out) {
+  if (Z <= 0 || nnz < 0 || heads <= 0 || F_out <= 0) return 0;
+  return gat_backward_workspace(Z, nnz, heads, F_out);
+}
+
+int ab200_gat_backward(const int32_t* rowptr, const int32_t* col, const int32_t* rowptr_t, const int32_t* col_t, const int32_t* eid_t,
+                       int32_t Z, int32_t nnz, const float* x, int32_t F_in, const float* W, const float* att_src,
+                       const float* att_dst, int32_t heads, int32_t F_out, int32_t concat, float negative_slope, const float* xw,
+                       const float* a_src, const float* a_dst, const float* alpha, const float* grad_out, float* grad_x,
+                       float* grad_W, float* grad_att_src, float* grad_att_dst, float* grad_bias, void* workspace,
+                       size_t workspace_bytes, ab200_stream_t stream) {
+  if (!rowptr || !col || !rowptr_t || !col_t || !eid_t || !x || !W || !att_src || !att_dst || !xw || !a_src || !a_dst || !alpha ||
+      !grad_out || !grad_W || !grad_att_src || !grad_att_dst || !workspace || Z <= 0)
+    return AB200_ERR_BAD_ARG;
+  return gat_backward(rowptr, col, rowptr_t, col_t, eid_t, Z, nnz, x, F_in, W, att_src, att_dst, heads, F_out, concat, negative_slope,
+                      xw, a_src, a_dst, alpha, grad_out, grad_x, grad_W, grad_att_src, grad_att_dst, grad_bias, workspace,
+                      workspace_bytes, (cudaStream_t)stream);
 }
 
 int ab200_debug_umma_probe(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t a_mode, int32_t b_mode,

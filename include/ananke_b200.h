@@ -115,6 +115,30 @@ int ab200_rk_combine_errnorm(const float* y0, const float* const* k, const float
                              const float* cerr_host, int32_t n_k, float dt, float rtol, float atol,
                              float* y1_out, float* sumsq, int64_t n, ab200_stream_t stream);
 
+/* ---- graph attention over the zone graph (the `gnn_embed` slot) ------------------------------------
+ * No reference implementation exists (README.md:5,57,80 promise it; pyproject.toml:25 declares torch-geometric
+ * 2.6.1, never imported): semantics are PyG `GATConv` -- x'_i = ||_h sum_{j in N(i)+i}
+ * alpha^h_ij W^h x_j + b, alpha = softmax_j LeakyReLU(a_src^h . W^h x_j + a_dst^h . W^h x_i).
+ * Graph: CSR sorted by DESTINATION over the symmetrised zone graph with self loops (data_generator/
+ * load_data.py:104-110 builds the same adjacency): rowptr[Z+1], col[nnz] = source of each in-edge (int32).
+ * The transposed CSR (rowptr_t/col_t by SOURCE) and eid_t[nnz] (index of that edge in the by-destination order)
+ * are needed by the backward pass only.  W [heads*F_out, F_in] (nn.Linear storage), att_* [heads*F_out].
+ * Saved for backward (caller-allocated): xw [Z, heads*F_out], a_src/a_dst [Z, heads], alpha [nnz, heads].
+ * out: [Z, heads*F_out] (concat=1) or [Z, F_out] (concat=0, mean over heads).  F_out: power of two >= 4. */
+int ab200_gat_forward(const int32_t* rowptr, const int32_t* col, int32_t Z, int32_t nnz, const float* x, int32_t F_in,
+                      const float* W, const float* att_src, const float* att_dst, const float* bias, int32_t heads,
+                      int32_t F_out, int32_t concat, float negative_slope, float* out, float* xw, float* a_src,
+                      float* a_dst, float* alpha, ab200_stream_t stream);
+size_t ab200_gat_backward_workspace_bytes(int32_t Z, int32_t nnz, int32_t heads, int32_t F_out);
+/* grad_x and grad_bias may be NULL.  All gradient outputs are OVERWRITTEN. */
+int ab200_gat_backward(const int32_t* rowptr, const int32_t* col, const int32_t* rowptr_t, const int32_t* col_t,
+                       const int32_t* eid_t, int32_t Z, int32_t nnz, const float* x, int32_t F_in, const float* W,
+                       const float* att_src, const float* att_dst, int32_t heads, int32_t F_out, int32_t concat,
+                       float negative_slope, const float* xw, const float* a_src, const float* a_dst,
+                       const float* alpha, const float* grad_out, float* grad_x, float* grad_W, float* grad_att_src,
+                       float* grad_att_dst, float* grad_bias, void* workspace, size_t workspace_bytes,
+                       ab200_stream_t stream);
+
 /* ---- self-test of the tcgen05 plumbing (one CTA): D[128,N] = A[128,K] * B[N,K]^T, bf16 operands, fp32 result.
  * a_mode 0/1/2 = A in TMEM / smem un-swizzled / smem 128B-swizzled; b_mode 1/2 = B un-swizzled / 128B-swizzled.
  * `status` (device int) receives 0, or 1 if the MMA completion barrier timed out.  No reference counterpart. */
