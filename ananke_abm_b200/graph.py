@@ -7,7 +7,9 @@ adjacency built at /root/reference/src/ananke_abm/data_generator/load_data.py:10
 """
 from __future__ import annotations
 
+import math
 from dataclasses import dataclass
+from typing import Tuple
 
 import torch
 
@@ -54,3 +56,36 @@ def build_zone_csr(edge_index: torch.Tensor, Z: int, symmetrise: bool = True, ad
     rowptr_t = torch.zeros(Z + 1, dtype=torch.int64)
     rowptr_t[1:] = torch.cumsum(torch.bincount(s, minlength=Z), 0)
     return ZoneCSR(Z, nnz, rowptr.int(), s.int(), rowptr_t.int(), d[order].int(), order.int(), torch.stack([s, d]))
+
+
+def synthetic_zone_graph(Z: int, k: int = 6, seed: int = 42) -> Tuple[torch.Tensor, torch.Tensor]:
+    """jittered sqrt(Z) x sqrt(Z) lattice, undirected k-NN graph; returns (edge_index [2,E] with
+    each undirected edge once, zone features [Z,7] ~ U[0,1))."""
+    g = torch.Generator().manual_seed(seed)
+    side = int(math.ceil(math.sqrt(Z)))
+    idx = torch.arange(Z)
+    xy = torch.stack([(idx % side).float(), (idx // side).float()], dim=-1) + torch.rand(Z, 2, generator=g)
+    feats = torch.rand(Z, 7, generator=g)
+    # k nearest neighbours via a cell grid: candidates within +-2 lattice cells
+    cand = []
+    for dx in range(-2, 3):
+        for dy in range(-2, 3):
+            if dx == 0 and dy == 0:
+                continue
+            cx, cy = idx % side + dx, idx // side + dy
+            ok = (cx >= 0) & (cx < side) & (cy >= 0) & (cy < side)
+            nb = cy * side + cx
+            ok = ok & (nb < Z)
+            cand.append(torch.where(ok, nb, torch.full_like(nb, -1)))
+    cand = torch.stack(cand, dim=1)                                  # [Z, 24]
+    d = (xy.unsqueeze(1) - xy[cand.clamp(min=0)]).pow(2).sum(-1)
+    d = torch.where(cand >= 0, d, torch.full_like(d, float("inf")))
+    nn_idx = d.topk(k, dim=1, largest=False).indices
+    nbr = cand.gather(1, nn_idx)
+    src = idx.unsqueeze(1).expand(-1, k).reshape(-1)
+    dst = nbr.reshape(-1)
+    ok = dst >= 0
+    src, dst = src[ok], dst[ok]
+    lo, hi = torch.minimum(src, dst), torch.maximum(src, dst)
+    key = torch.unique(lo * Z + hi)
+    return torch.stack([key // Z, key % Z]), feats

@@ -45,16 +45,43 @@ def _require_cuda(x: torch.Tensor, what: str) -> None:
         raise _lib.Ab200Error(f"{what} must be a CUDA tensor: ananke_abm_b200 has no CPU path")
 
 
+_T_CACHE: dict = {}
+
+
 def _check_t(t: torch.Tensor) -> torch.Tensor:
+    """torchdiffeq's input checks (odeint.py `_check_inputs`).  The host copy of a time grid is cached per
+    (storage, version) so that repeated solves on the same grid do not force a device->host sync each call."""
     assert isinstance(t, torch.Tensor), "t must be a torch.Tensor"
     assert t.ndimension() == 1, "t must be one dimensional"
     assert torch.is_floating_point(t), "t must be a floating point Tensor"
+    key = (t.data_ptr(), t._version, t.numel(), t.dtype, str(t.device))
+    hit = _T_CACHE.get(key)
+    if hit is not None:
+        return hit
     t_host = t.detach().to("cpu", non_blocking=False)
     if t_host.numel() > 1:
         d = t_host[1:] - t_host[:-1]
         if not (bool((d > 0).all()) or bool((d < 0).all())):
             raise AssertionError("t must be strictly increasing or decreasing")
+    if len(_T_CACHE) > 64:
+        _T_CACHE.clear()
+    _T_CACHE[key] = t_host
     return t_host
+
+
+def rk4_forward_into(spec: DriftSpec, w_flat: torch.Tensor, y0: torch.Tensor, t: torch.Tensor, y_path: torch.Tensor,
+                     workspace: torch.Tensor, precision: int) -> None:
+    """Raw fused launch into caller-owned buffers (no allocation, no sync, no autograd): the call the bench times."""
+    L = _lib.lib()
+    B, D = y0.shape
+    rc = L.ab200_rk4_forward(C.byref(spec.desc), w_flat.data_ptr(), y0.data_ptr(), t.data_ptr(), None, B, t.numel(),
+                             y_path.data_ptr(), workspace.data_ptr(), workspace.numel(), precision, _stream_ptr())
+    _lib.check(rc, "ab200_rk4_forward")
+
+
+def rk4_workspace(spec: DriftSpec, B: int, T: int, precision: int, device) -> torch.Tensor:
+    nbytes = _lib.lib().ab200_rk4_workspace_bytes(C.byref(spec.desc), B, T, precision)
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
 
 
 # --------------------------------------------------------------------------------------------------

@@ -54,7 +54,9 @@ def test_zone_csr_matches_oracle_edge_order():
 
 def test_synthetic_graph_degree():
     ei, feats = go.synthetic_zone_graph(500, k=6)
-    from ananke_abm_b200.graph import build_zone_csr
+    from ananke_abm_b200.graph import build_zone_csr, synthetic_zone_graph
+    ei2, feats2 = synthetic_zone_graph(500, k=6)
+    assert torch.equal(ei, ei2) and torch.equal(feats, feats2)
     csr = build_zone_csr(ei, 500)
     deg = (csr.rowptr[1:] - csr.rowptr[:-1]).float()
     assert feats.shape == (500, 7) and 6.5 < float(deg.mean()) < 10.0 and int(deg.min()) >= 2
