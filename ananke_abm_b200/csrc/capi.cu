@@ -40,6 +40,28 @@ int gat_backward(const int* rowptr, const int* col, const int* rowptr_t, const i
                  const float* gout, float* grad_x, float* grad_W, float* grad_att_src, float* grad_att_dst, float* grad_bias,
                  void* ws, size_t ws_bytes, cudaStream_t st);
 
+size_t stage_tc_image_bytes();
+int stage_tc_pack(const float* w_flat, uint8_t* image, cudaStream_t st);
+int stage_fwd_tc(const ab200_drift_desc* d, const uint8_t* image, const float* y0, const float* const* a_ptrs, const void* desc_v,
+                 int64_t B, float* a_out, float* y_out, double* err_sumsq, cudaStream_t st);
+int stage_bwd_tc(const ab200_drift_desc* d, const uint8_t* image, const float* y0, const float* const* a_ptrs, const void* desc_v,
+                 int64_t B, const float* g_a, float* G_y0, float* const* G_a, void* spill, int blob0, int nblobs, float* g_bout,
+                 cudaStream_t st);
+size_t wgrad_spill_bytes(int nblobs);
+size_t wgrad_partial_bytes();
+int wgrad_num_ctas();
+float* wgrad_bout_ptr(void* partial);
+int wgrad_tc(const void* spill, int nblobs, int used, void* partial, cudaStream_t st);
+int wgrad_finalize(const void* partial, float* grad_w_flat, cudaStream_t st);
+int pv_combine(const ab200_drift_desc* d, const float* y0, const float* const* a_ptrs, int n_a, float cpv, const float* cpa,
+               const float* cva, int64_t B, float* out, cudaStream_t st);
+int pv_combine_bwd(const ab200_drift_desc* d, const float* g, int n_a, float cpv, const float* cpa, const float* cva, int64_t B,
+                   float* G_y0, float* const* G_a, int accumulate, cudaStream_t st);
+
+static bool stage_shape_ok(const ab200_drift_desc* d) {
+  return d && d->pos_dim == 64 && d->ctx_dim == 32 && d->hidden == 128 && d->n_res == 2 && d->res_act == 0 && d->potential == 0;
+}
+
 static bool desc_ok(const ab200_drift_desc* d) {
   return d && d->pos_dim > 0 && d->ctx_dim >= 0 && d->hidden > 0 && d->n_res >= 0 && (d->res_act == 0 || d->res_act == 1);
 }
@@ -151,6 +173,75 @@ int ab200_rk_combine_errnorm(const float* y0, const float* const* k, const float
                              ab200_stream_t stream) {
   if (!y0 || !k || !csol_host || !cerr_host || !sumsq || n <= 0) return AB200_ERR_BAD_ARG;
   return rk_combine_errnorm(y0, k, csol_host, cerr_host, n_k, dt, rtol, atol, y1_out, sumsq, n, (cudaStream_t)stream);
+}
+
+size_t ab200_stage_image_bytes(const ab200_drift_desc* d) { return stage_shape_ok(d) ? stage_tc_image_bytes() : 0; }
+
+int ab200_stage_pack(const ab200_drift_desc* d, const float* w_flat, void* image, size_t image_bytes, ab200_stream_t stream) {
+  if (!d || !w_flat || !image) return AB200_ERR_BAD_ARG;
+  if (!stage_shape_ok(d)) return AB200_ERR_UNSUPPORTED;
+  if (image_bytes < stage_tc_image_bytes()) return AB200_ERR_WORKSPACE;
+  cudaError_t e = cudaMemsetAsync((uint8_t*)image + stage_tc_image_bytes() - 256, 0, 256, (cudaStream_t)stream);
+  if (e != cudaSuccess) { set_cuda_error(e); return AB200_ERR_CUDA; }
+  return stage_tc_pack(w_flat, (uint8_t*)image, (cudaStream_t)stream);
+}
+
+int ab200_stage_forward(const ab200_drift_desc* d, const void* image, const float* y0, const float* const* a,
+                        const ab200_stage_desc* s, int64_t B, float* a_out, float* y_out, double* err_sumsq,
+                        ab200_stream_t stream) {
+  if (!d || !image || !y0 || !s || B <= 0 || (s->n_a > 0 && !a)) return AB200_ERR_BAD_ARG;
+  if (!stage_shape_ok(d)) return AB200_ERR_UNSUPPORTED;
+  if (err_sumsq && !y_out) return AB200_ERR_BAD_ARG;
+  return stage_fwd_tc(d, (const uint8_t*)image, y0, a, s, B, a_out, y_out, err_sumsq, (cudaStream_t)stream);
+}
+
+size_t ab200_stage_spill_bytes(const ab200_drift_desc* d, int32_t nblobs) {
+  return (stage_shape_ok(d) && nblobs > 0) ? wgrad_spill_bytes(nblobs) : 0;
+}
+size_t ab200_wgrad_partial_bytes(const ab200_drift_desc* d) { return stage_shape_ok(d) ? wgrad_partial_bytes() : 0; }
+
+int ab200_stage_backward(const ab200_drift_desc* d, const void* image, const float* y0, const float* const* a,
+                         const ab200_stage_desc* s, int64_t B, const float* g_a, float* G_y0, float* const* G_a, void* spill,
+                         size_t spill_bytes, int32_t blob0, int32_t nblobs, void* partial, ab200_stream_t stream) {
+  if (!d || !image || !y0 || !s || !g_a || !G_y0 || !spill || !partial || B <= 0 || (s->n_a > 0 && (!a || !G_a)))
+    return AB200_ERR_BAD_ARG;
+  if (!stage_shape_ok(d)) return AB200_ERR_UNSUPPORTED;
+  if (nblobs <= 0 || spill_bytes < wgrad_spill_bytes(nblobs)) return AB200_ERR_WORKSPACE;
+  return stage_bwd_tc(d, (const uint8_t*)image, y0, a, s, B, g_a, G_y0, G_a, spill, blob0, nblobs, wgrad_bout_ptr(partial),
+                      (cudaStream_t)stream);
+}
+
+int ab200_wgrad_accumulate(const ab200_drift_desc* d, const void* spill, int32_t nblobs, int32_t used, void* partial,
+                           ab200_stream_t stream) {
+  if (!d || !spill || !partial || nblobs <= 0 || used < 0 || used > nblobs) return AB200_ERR_BAD_ARG;
+  if (!stage_shape_ok(d)) return AB200_ERR_UNSUPPORTED;
+  return wgrad_tc(spill, nblobs, used, partial, (cudaStream_t)stream);
+}
+
+int ab200_wgrad_finalize(const ab200_drift_desc* d, const void* partial, float* grad_w_flat, ab200_stream_t stream) {
+  if (!d || !partial || !grad_w_flat) return AB200_ERR_BAD_ARG;
+  if (!stage_shape_ok(d)) return AB200_ERR_UNSUPPORTED;
+  return wgrad_finalize(partial, grad_w_flat, (cudaStream_t)stream);
+}
+
+int ab200_stage_status_offset(const ab200_drift_desc* d, int64_t* image_status_byte, int64_t* partial_status_byte) {
+  if (!stage_shape_ok(d)) return AB200_ERR_UNSUPPORTED;
+  if (image_status_byte) *image_status_byte = (int64_t)stage_tc_image_bytes() - 256;
+  if (partial_status_byte) *partial_status_byte = (int64_t)wgrad_partial_bytes() - 256;
+  return AB200_OK;
+}
+
+int ab200_pv_combine(const ab200_drift_desc* d, const float* y0, const float* const* a, int32_t n_a, float cpv,
+                     const float* cpa_host, const float* cva_host, int64_t B, float* out, ab200_stream_t stream) {
+  if (!desc_ok(d) || !y0 || !out || B <= 0 || (n_a > 0 && (!a || !cpa_host || !cva_host))) return AB200_ERR_BAD_ARG;
+  return pv_combine(d, y0, a, n_a, cpv, cpa_host, cva_host, B, out, (cudaStream_t)stream);
+}
+
+int ab200_pv_combine_backward(const ab200_drift_desc* d, const float* g, int32_t n_a, float cpv, const float* cpa_host,
+                              const float* cva_host, int64_t B, float* G_y0, float* const* G_a, int32_t accumulate,
+                              ab200_stream_t stream) {
+  if (!desc_ok(d) || !g || !G_y0 || B <= 0 || (n_a > 0 && (!G_a || !cpa_host || !cva_host))) return AB200_ERR_BAD_ARG;
+  return pv_combine_bwd(d, g, n_a, cpv, cpa_host, cva_host, B, G_y0, G_a, accumulate, (cudaStream_t)stream);
 }
 
 int ab200_gat_forward(const int32_t* rowptr, const int32_t* col, int32_t Z, int32_t nnz, const float* x, int32_t F_in,

@@ -1,0 +1,353 @@
+// Tensor-core backward STAGE kernel: the vector-Jacobian product of one drift evaluation (see stage_fwd_tc.cu).
+//
+// Given dL/da_out for a stage whose input was  p = p0 + cpv v0 + sum cpa[j] a_j,  v = v0 + sum cva[j] a_j, it
+//   1. rebuilds the stage input and re-runs the five hidden layers on the tensor core, keeping only the ReLU masks
+//      (bits) and the residual stream in registers,
+//   2. back-propagates through the net with six dgrad GEMMs that read the SAME resident weight image MN-major
+//      (W^T without a transposed copy),
+//   3. scatters dL/d(stage input) into the step's gradient accumulators
+//         G_y0.p += g_p ; G_y0.v += cpv g_p + g_v ; G_y0.h += g_h ; G_a[j] += cpa[j] g_p + cva[j] g_v
+//      (every element is owned by one thread: plain read-modify-write, no atomics),
+//   4. writes every layer's (input activation, output gradient) pair as bf16 "blobs" already laid out as the
+//      canonical MN-major UMMA operand image (K = agent), which wgrad_tc.cu streams straight into shared memory.
+// The weight gradient cannot be fused here: its fp32 accumulators (95,168 floats = 372 KiB) exceed the 256 KiB of
+// tensor memory of one SM, see DESIGN.md.
+#include "stage_tc.cuh"
+#include "wgrad_layout.cuh"
+
+namespace ab200 {
+using namespace stc;
+
+struct StageBwdArgs {
+  const uint8_t* wimg;
+  const float* y0;            // [B][160]
+  const float* a[MAX_A];      // [B][64]
+  int n_a;
+  Combo in;
+  float t, period;
+  const float* g_a;           // [B][64]  dL/da_out of this stage
+  float* G_y0;                // [B][160] accumulated
+  float* G_a[MAX_A];          // [B][64]  accumulated (only j < n_a)
+  uint8_t* spill;             // blob buffer (SpillLayout)
+  float* g_bout;              // [64] atomically accumulated column sums of g_a (bias gradient of the output layer)
+  int64_t B;
+  int ntiles;
+  int blob0;                  // blob index of tile 0 of this launch
+  int nblobs;                 // blobs the spill buffer was sized for
+  int* status;
+};
+
+// store this thread's 32 columns (16 packed pairs = 4 feature groups) of a blob: feature group fg0.., row = agent
+__device__ __forceinline__ void spill16(uint8_t* blob, int fg0, int row, const uint32_t (&o)[16]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    *reinterpret_cast<uint4*>(blob + (size_t)(fg0 + q) * wg::FG_BYTES + (size_t)row * 16) =
+        make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+}
+
+// forward hidden epilogue with mask capture and spill.  RES: residual add of z.  Result -> ACT, z (if KEEP), blob.
+template <bool RES, bool KEEP>
+__device__ __forceinline__ void bwd_fwd_epi(const SlotCtx& c, uint32_t (&z)[32], uint32_t (&mask)[2], uint8_t* blob) {
+#pragma unroll
+  for (int ch = 0; ch < 2; ++ch) {
+    uint32_t r[32];
+    tmem_ld32(c.tmem + c.lane_sel + C_ACC + (uint32_t)(c.hf * 64 + ch * 32), r);
+    tmem_ld_wait();
+    uint32_t o[16];
+    uint32_t m = 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float x0 = __uint_as_float(r[2 * j]), x1 = __uint_as_float(r[2 * j + 1]);
+      if (RES) { x0 += bf16lo(z[ch * 16 + j]); x1 += bf16hi(z[ch * 16 + j]); }
+      o[j] = pack_relu_bf16(x0, x1);
+      m |= ((o[j] & 0xffffu) ? 1u : 0u) << (2 * j);
+      m |= ((o[j] >> 16) ? 1u : 0u) << (2 * j + 1);
+      if (KEEP) z[ch * 16 + j] = o[j];
+    }
+    mask[ch] = m;
+    tmem_st16(c.tmem + c.lane_sel + C_ACT + (uint32_t)(c.hf * 32 + ch * 16), o);
+    spill16(blob, c.hf * 8 + ch * 4, c.row, o);
+  }
+}
+
+// backward hidden epilogue: g = (acc [+ skip]) * mask -> ACT, blob; SKIP_IN adds the skip-path gradient held in
+// `gs`, SKIP_OUT stores the result into `gs` (it is the gradient of the residual stream one block further down).
+template <bool SKIP_IN, bool SKIP_OUT>
+__device__ __forceinline__ void bwd_bwd_epi(const SlotCtx& c, uint32_t (&gs)[32], const uint32_t (&mask)[2], uint8_t* blob) {
+#pragma unroll
+  for (int ch = 0; ch < 2; ++ch) {
+    uint32_t r[32];
+    tmem_ld32(c.tmem + c.lane_sel + C_ACC + (uint32_t)(c.hf * 64 + ch * 32), r);
+    tmem_ld_wait();
+    uint32_t o[16];
+    const uint32_t m = mask[ch];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float x0 = __uint_as_float(r[2 * j]), x1 = __uint_as_float(r[2 * j + 1]);
+      if (SKIP_IN) { x0 += bf16lo(gs[ch * 16 + j]); x1 += bf16hi(gs[ch * 16 + j]); }
+      x0 = ((m >> (2 * j)) & 1u) ? x0 : 0.0f;
+      x1 = ((m >> (2 * j + 1)) & 1u) ? x1 : 0.0f;
+      o[j] = pack_bf16(x0, x1);
+      if (SKIP_OUT) gs[ch * 16 + j] = o[j];
+    }
+    tmem_st16(c.tmem + c.lane_sel + C_ACT + (uint32_t)(c.hf * 32 + ch * 16), o);
+    spill16(blob, c.hf * 8 + ch * 4, c.row, o);
+  }
+}
+
+__global__ void __launch_bounds__(THREADS, 1) stage_bwd_tc_kernel(const __grid_constant__ StageBwdArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bars[NSLOT];
+  __shared__ uint32_t tmem_base_s;
+  SlotCtx c = stage_setup(smem, a.wimg, bars, &tmem_base_s, a.status);
+  const uint32_t tmem_base = tmem_base_s;
+  const wg::SpillLayout S{a.nblobs};
+  const int lane = threadIdx.x & 31;
+
+#pragma unroll 1
+  for (int tile = blockIdx.x * NSLOT + c.slot; tile < a.ntiles; tile += gridDim.x * NSLOT) {
+    const int64_t g = (int64_t)tile * TM + c.row;
+    const bool valid = g < a.B;
+    const int64_t gi = valid ? g : a.B - 1;
+    const float* yrow = a.y0 + gi * D;
+    const int blob = a.blob0 + tile;
+
+    // ---- stage input -> ACT / HB / TB and the X blob (features: p 0..63, v 64..127, h 128..159, sin, cos, 1)
+    uint8_t* xb = a.spill + S.x1(blob);
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+      const int d0 = c.hf * 32 + ch * 16;
+      float pin[16], vin[16];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 pv = *reinterpret_cast<const float4*>(yrow + d0 + 4 * j);
+        const float4 vv = *reinterpret_cast<const float4*>(yrow + P + d0 + 4 * j);
+        pin[4 * j] = pv.x + a.in.cpv * vv.x; pin[4 * j + 1] = pv.y + a.in.cpv * vv.y;
+        pin[4 * j + 2] = pv.z + a.in.cpv * vv.z; pin[4 * j + 3] = pv.w + a.in.cpv * vv.w;
+        vin[4 * j] = vv.x; vin[4 * j + 1] = vv.y; vin[4 * j + 2] = vv.z; vin[4 * j + 3] = vv.w;
+      }
+#pragma unroll
+      for (int s = 0; s < MAX_A; ++s) {
+        if (s < a.n_a) {
+          const float* ar = a.a[s] + gi * P + d0;
+          const float cp = a.in.cpa[s], cv = a.in.cva[s];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 x = *reinterpret_cast<const float4*>(ar + 4 * j);
+            pin[4 * j] += cp * x.x; pin[4 * j + 1] += cp * x.y; pin[4 * j + 2] += cp * x.z; pin[4 * j + 3] += cp * x.w;
+            vin[4 * j] += cv * x.x; vin[4 * j + 1] += cv * x.y; vin[4 * j + 2] += cv * x.z; vin[4 * j + 3] += cv * x.w;
+          }
+        }
+      }
+      uint32_t o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = pack_bf16(pin[2 * j], pin[2 * j + 1]);
+      tmem_st8(c.tmem + c.lane_sel + C_ACT + (uint32_t)(d0 / 2), o);
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+        *reinterpret_cast<uint4*>(xb + (size_t)(d0 / 8 + q) * wg::FG_BYTES + (size_t)c.row * 16) =
+            make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = pack_bf16(vin[2 * j], vin[2 * j + 1]);
+      tmem_st8(c.tmem + c.lane_sel + C_ACT + (uint32_t)(P / 2 + d0 / 2), o);
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+        *reinterpret_cast<uint4*>(xb + (size_t)((P + d0) / 8 + q) * wg::FG_BYTES + (size_t)c.row * 16) =
+            make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+    }
+    {
+      uint32_t o[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 x = *reinterpret_cast<const float4*>(yrow + 2 * P + c.hf * 16 + 4 * j);
+        o[2 * j] = pack_bf16(x.x, x.y);
+        o[2 * j + 1] = pack_bf16(x.z, x.w);
+      }
+      tmem_st8(c.tmem + c.lane_sel + C_HB + (uint32_t)(c.hf * 8), o);
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+        *reinterpret_cast<uint4*>(xb + (size_t)((2 * P + c.hf * 16) / 8 + q) * wg::FG_BYTES + (size_t)c.row * 16) =
+            make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+    }
+    write_time_block(c, a.t, a.period);
+    if (c.hf == 0) {   // time-feature / bias feature groups of the X blob: [sin, cos, 1, 0...], [0...]
+      float s, co;
+      time_features(a.t, a.period, s, co);
+      *reinterpret_cast<uint4*>(xb + (size_t)((2 * P + H) / 8) * wg::FG_BYTES + (size_t)c.row * 16) =
+          make_uint4(pack_bf16(s, co), pack_bf16(1.0f, 0.0f), 0u, 0u);
+      *reinterpret_cast<uint4*>(xb + (size_t)((2 * P + H) / 8 + 1) * wg::FG_BYTES + (size_t)c.row * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+
+    // ---- forward recompute (hidden layers only), masks + blobs
+    uint32_t z[32];
+    uint32_t m_z0[2], m_u0[2], m_z1[2], m_u1[2], m_z2[2];
+    run_layer<false>(c, C_ACT, (2 * P + H) / 16, true, OFF_W1, HID, HID);
+    bwd_fwd_epi<false, true>(c, z, m_z0, a.spill + S.act(0, blob));
+    run_layer<false>(c, C_ACT, HID / 16, true, off_hh(0), HID, HID);
+    bwd_fwd_epi<false, false>(c, z, m_u0, a.spill + S.act(1, blob));
+    run_layer<false>(c, C_ACT, HID / 16, true, off_hh(1), HID, HID);
+    bwd_fwd_epi<true, true>(c, z, m_z1, a.spill + S.act(2, blob));
+    run_layer<false>(c, C_ACT, HID / 16, true, off_hh(2), HID, HID);
+    bwd_fwd_epi<false, false>(c, z, m_u1, a.spill + S.act(3, blob));
+    run_layer<false>(c, C_ACT, HID / 16, true, off_hh(3), HID, HID);
+    bwd_fwd_epi<true, false>(c, z, m_z2, a.spill + S.act(4, blob));
+
+    // ---- upstream gradient of the output layer -> ACT (K = 64) + gO blob + bias column sums
+    {
+      const float* gr = a.g_a + gi * P + c.hf * 32;
+      uint32_t o[16];
+      float gv[32];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 x = valid ? *reinterpret_cast<const float4*>(gr + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        gv[4 * j] = x.x; gv[4 * j + 1] = x.y; gv[4 * j + 2] = x.z; gv[4 * j + 3] = x.w;
+        o[2 * j] = pack_bf16(x.x, x.y);
+        o[2 * j + 1] = pack_bf16(x.z, x.w);
+      }
+      tmem_st16(c.tmem + c.lane_sel + C_ACT + (uint32_t)(c.hf * 16), o);
+      spill16(a.spill + S.go(blob), c.hf * 4, c.row, o);
+      // column sums over the warp's 32 agents: transpose-reduce, lane j ends up with column j
+#pragma unroll
+      for (int w = 16; w >= 1; w >>= 1) {
+#pragma unroll
+        for (int j = 0; j < w; ++j) {
+          const bool up = (lane & w) != 0;
+          const float send = up ? gv[j] : gv[j + w];
+          const float keep = up ? gv[j + w] : gv[j];
+          gv[j] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+        }
+      }
+      atomicAdd(a.g_bout + c.hf * 32 + lane, gv[0]);
+    }
+
+    // ---- backward through the net (dgrad GEMMs on the MN-major view of the weight image)
+    run_layer<true>(c, C_ACT, P / 16, false, OFF_WO, P, HID);                       // g_z2 = gO W_O
+    bwd_bwd_epi<false, true>(c, z, m_z2, a.spill + S.grad(4, blob));                // gB1 = g_z2 * [z2 > 0]  (skip -> z)
+    run_layer<true>(c, C_ACT, HID / 16, false, off_hh(3), HID, HID);                // g_u1 = gB1 W_B1
+    {
+      uint32_t dummy[32];
+      bwd_bwd_epi<false, false>(c, dummy, m_u1, a.spill + S.grad(3, blob));         // gA1
+    }
+    run_layer<true>(c, C_ACT, HID / 16, false, off_hh(2), HID, HID);                // gA1 W_A1 (+ skip)
+    bwd_bwd_epi<true, true>(c, z, m_z1, a.spill + S.grad(2, blob));                 // gB0
+    run_layer<true>(c, C_ACT, HID / 16, false, off_hh(1), HID, HID);
+    {
+      uint32_t dummy[32];
+      bwd_bwd_epi<false, false>(c, dummy, m_u0, a.spill + S.grad(1, blob));         // gA0
+    }
+    run_layer<true>(c, C_ACT, HID / 16, false, off_hh(0), HID, HID);
+    bwd_bwd_epi<true, false>(c, z, m_z0, a.spill + S.grad(0, blob));                // g1
+    run_layer<true>(c, C_ACT, HID / 16, false, OFF_W1, HID, 2 * P + H);             // g_x[128 x 160] = g1 W_1[:, :160]
+
+    // ---- scatter into the step's gradient accumulators (tcgen05.ld is warp-collective: issued by every lane, the
+    //      global read-modify-writes only by lanes that own a real agent)
+    {
+      float* Gy = a.G_y0 + gi * D;
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {     // 16 dims per pass
+        const int d0 = c.hf * 32 + ch * 16;
+        uint32_t rp[16], rv[16];
+        tmem_ld16(c.tmem + c.lane_sel + C_ACC + (uint32_t)d0, rp);
+        tmem_ld16(c.tmem + c.lane_sel + C_ACC + (uint32_t)(P + d0), rv);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float4* pp = reinterpret_cast<float4*>(Gy + d0 + 4 * j);
+            float4* pv = reinterpret_cast<float4*>(Gy + P + d0 + 4 * j);
+            float4 x = *pp, y = *pv;
+            const float gp0 = __uint_as_float(rp[4 * j]), gp1 = __uint_as_float(rp[4 * j + 1]), gp2 = __uint_as_float(rp[4 * j + 2]),
+                        gp3 = __uint_as_float(rp[4 * j + 3]);
+            x.x += gp0; x.y += gp1; x.z += gp2; x.w += gp3;
+            y.x += a.in.cpv * gp0 + __uint_as_float(rv[4 * j]);
+            y.y += a.in.cpv * gp1 + __uint_as_float(rv[4 * j + 1]);
+            y.z += a.in.cpv * gp2 + __uint_as_float(rv[4 * j + 2]);
+            y.w += a.in.cpv * gp3 + __uint_as_float(rv[4 * j + 3]);
+            *pp = x;
+            *pv = y;
+          }
+#pragma unroll
+          for (int s = 0; s < MAX_A; ++s) {
+            if (s < a.n_a) {
+              float* Ga = a.G_a[s] + g * P + d0;
+              const float cp = a.in.cpa[s], cv = a.in.cva[s];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float4* q = reinterpret_cast<float4*>(Ga + 4 * j);
+                float4 x = *q;
+                x.x += cp * __uint_as_float(rp[4 * j]) + cv * __uint_as_float(rv[4 * j]);
+                x.y += cp * __uint_as_float(rp[4 * j + 1]) + cv * __uint_as_float(rv[4 * j + 1]);
+                x.z += cp * __uint_as_float(rp[4 * j + 2]) + cv * __uint_as_float(rv[4 * j + 2]);
+                x.w += cp * __uint_as_float(rp[4 * j + 3]) + cv * __uint_as_float(rv[4 * j + 3]);
+                *q = x;
+              }
+            }
+          }
+        }
+      }
+      {
+        uint32_t rh[16];
+        tmem_ld16(c.tmem + c.lane_sel + C_ACC + (uint32_t)(2 * P + c.hf * 16), rh);
+        tmem_ld_wait();
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float4* q = reinterpret_cast<float4*>(Gy + 2 * P + c.hf * 16 + 4 * j);
+            float4 x = *q;
+            x.x += __uint_as_float(rh[4 * j]); x.y += __uint_as_float(rh[4 * j + 1]);
+            x.z += __uint_as_float(rh[4 * j + 2]); x.w += __uint_as_float(rh[4 * j + 3]);
+            *q = x;
+          }
+        }
+      }
+    }
+  }
+  stage_teardown(tmem_base);
+}
+
+struct StageBwdHost {   // mirrors the head of ab200_stage_desc
+  int32_t n_a;
+  float in_cpv, in_cpa[MAX_A], in_cva[MAX_A];
+  float t;
+};
+
+int stage_bwd_tc(const ab200_drift_desc* d, const uint8_t* image, const float* y0, const float* const* a_ptrs, const void* desc_v,
+                 int64_t B, const float* g_a, float* G_y0, float* const* G_a, void* spill, int blob0, int nblobs, float* g_bout,
+                 cudaStream_t st) {
+  const StageBwdHost& h = *reinterpret_cast<const StageBwdHost*>(desc_v);
+  if (h.n_a < 0 || h.n_a > MAX_A) return AB200_ERR_BAD_ARG;
+  StageBwdArgs k{};
+  k.wimg = image;
+  k.y0 = y0;
+  k.n_a = h.n_a;
+  for (int i = 0; i < MAX_A; ++i) {
+    k.a[i] = (i < h.n_a) ? a_ptrs[i] : nullptr;
+    k.G_a[i] = (i < h.n_a) ? G_a[i] : nullptr;
+    k.in.cpa[i] = h.in_cpa[i];
+    k.in.cva[i] = h.in_cva[i];
+  }
+  k.in.cpv = h.in_cpv;
+  k.t = h.t;
+  k.period = d->time_period;
+  k.g_a = g_a;
+  k.G_y0 = G_y0;
+  k.spill = (uint8_t*)spill;
+  k.g_bout = g_bout;
+  k.B = B;
+  k.ntiles = (int)((B + TM - 1) / TM);
+  k.blob0 = blob0;
+  k.nblobs = nblobs;
+  if (blob0 < 0 || blob0 + k.ntiles > nblobs) return AB200_ERR_BAD_ARG;
+  k.status = reinterpret_cast<int*>(const_cast<uint8_t*>(image) + align_up(W_BYTES, 256));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int need = (k.ntiles + NSLOT - 1) / NSLOT;
+  const int grid = need < sms ? need : sms;
+  cudaError_t e = cudaFuncSetAttribute(stage_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W_BYTES);
+  if (e != cudaSuccess) { set_cuda_error(e); return AB200_ERR_CUDA; }
+  stage_bwd_tc_kernel<<<grid, THREADS, W_BYTES, st>>>(k);
+  return check_launch();
+}
+
+}  // namespace ab200

@@ -1,0 +1,304 @@
+// Tensor-core forward STAGE kernel: one drift evaluation at a Runge-Kutta stage input, for every agent.
+//
+//   stage input   p = p0 + cpv v0 + sum_j cpa[j] a_j ,  v = v0 + sum_j cva[j] a_j      (fp32, from HBM/L2)
+//   drift net     6 tcgen05 layers (bf16 x bf16 -> fp32 in TMEM), bias + time features inside the MMA
+//   outputs       a_out = net(p, v, h, t)                                           [B][64]   (optional)
+//                 y_out = [p0 + ocpv v0 + sum ocpa a_j + ocpa[n] a_out,  v0 + sum ocva a_j + ocva[n] a_out, h]   (optional)
+//                 err   += sum_i ( e_i / (atol + rtol max(|y0_i|, |y_out_i|)) )^2,   e = sum_j (epa|eva)[j] a_j (+ a_out)
+// which covers every stage of torchdiffeq's fixed-grid rk4 (rk_common.py rk4_alt_step_func) and adaptive dopri5
+// (rk_common.py _runge_kutta_step + misc.py _compute_error_ratio): the host passes the tableau as `Combo`s.
+// Two 128-agent tiles ("slots") are in flight per CTA; see stage_tc.cuh.
+#include "stage_tc.cuh"
+
+namespace ab200 {
+using namespace stc;
+
+// ---- prepack: torch-layout fp32 weights -> bf16 UMMA image with bias / time-feature K extensions ---------------
+__global__ void stage_pack_kernel(const float* __restrict__ w, uint8_t* __restrict__ out) {
+  const FlatLayout F{P, H, HID, NRES};
+  const int IN = 2 * P + H + 2;
+  const int n_w1 = HID * K1, n_hh = HID * KH, n_wo = P * KH;
+  const int total = n_w1 + 2 * NRES * n_hh + n_wo;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int n, k, N, Kmain;
+    uint32_t base;
+    const float* wsrc;
+    const float* bsrc;
+    int ldw;
+    if (i < n_w1) {
+      n = i / K1; k = i % K1; N = HID; Kmain = 2 * P + H; base = OFF_W1;
+      wsrc = w + F.off_win(); bsrc = w + F.off_bin(); ldw = IN;
+    } else if (i < n_w1 + 2 * NRES * n_hh) {
+      const int q = i - n_w1, m = q / n_hh, r = q % n_hh;
+      n = r / KH; k = r % KH; N = HID; Kmain = HID; base = off_hh(m);
+      wsrc = w + ((m & 1) ? F.off_wb(m >> 1) : F.off_wa(m >> 1));
+      bsrc = w + ((m & 1) ? F.off_bb(m >> 1) : F.off_ba(m >> 1));
+      ldw = HID;
+    } else {
+      const int q = i - n_w1 - 2 * NRES * n_hh;
+      n = q / KH; k = q % KH; N = P; Kmain = HID; base = OFF_WO;
+      wsrc = w + F.off_wout(); bsrc = w + F.off_bout(); ldw = HID;
+    }
+    float v = 0.0f;
+    if (k < Kmain) {
+      v = wsrc[(size_t)n * ldw + k];
+    } else {
+      const int e = k - Kmain;
+      auto hi = [](float x) { return __bfloat162float(__float2bfloat16_rn(x)); };
+      if (base == OFF_W1 && e < 6) {
+        const float wt = wsrc[(size_t)n * ldw + Kmain + (e < 3 ? 0 : 1)];     // sin column, cos column of w_in
+        const int r = e % 3;
+        v = (r == 1) ? wt - hi(wt) : wt;                                      // hi, lo, hi
+      } else if (e == 6) {
+        v = bsrc[n];
+      } else if (e == 7) {
+        v = bsrc[n] - hi(bsrc[n]);
+      }
+    }
+    *reinterpret_cast<__nv_bfloat16*>(out + base + off_kmajor_noswz(n, k, lbo(N), SBO)) = __float2bfloat16_rn(v);
+  }
+}
+
+size_t stage_tc_image_bytes() { return align_up(W_BYTES, 256) + 256; }   // image + status word
+
+int stage_tc_pack(const float* w_flat, uint8_t* image, cudaStream_t st) {
+  stage_pack_kernel<<<148, 256, 0, st>>>(w_flat, image);
+  return check_launch();
+}
+
+struct StageFwdArgs {
+  const uint8_t* wimg;
+  const float* y0;            // [B][160]
+  const float* a[MAX_A];      // [B][64] each
+  int n_a;
+  Combo in;                   // stage input
+  float t, period;
+  float* a_out;               // [B][64] or null
+  float* y_out;               // [B][160] or null
+  Combo out;                  // y_out combination; index n_a of cpa/cva multiplies this stage's own output
+  double* err_sumsq;          // or null
+  Combo err;                  // error combination (cpv unused); index n_a multiplies this stage's own output
+  float rtol, atol;
+  int64_t B;
+  int ntiles;
+  int* status;
+};
+
+__global__ void __launch_bounds__(THREADS, 1) stage_fwd_tc_kernel(const __grid_constant__ StageFwdArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bars[NSLOT];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ double err_red[THREADS / 32];
+  SlotCtx c = stage_setup(smem, a.wimg, bars, &tmem_base_s, a.status);
+  const uint32_t tmem_base = tmem_base_s;
+  double err_local = 0.0;
+
+#pragma unroll 1
+  for (int tile = blockIdx.x * NSLOT + c.slot; tile < a.ntiles; tile += gridDim.x * NSLOT) {
+    const int64_t g = (int64_t)tile * TM + c.row;
+    const bool valid = g < a.B;
+    const int64_t gi = valid ? g : a.B - 1;
+    const float* yrow = a.y0 + gi * D;
+
+    // ---- stage input -> ACT (bf16), context h -> HB, time/bias block -> TB
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {       // 16 dims of p and of v per pass
+      const int d0 = c.hf * 32 + ch * 16;
+      float pin[16], vin[16];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 pv = *reinterpret_cast<const float4*>(yrow + d0 + 4 * j);
+        const float4 vv = *reinterpret_cast<const float4*>(yrow + P + d0 + 4 * j);
+        pin[4 * j] = pv.x + a.in.cpv * vv.x; pin[4 * j + 1] = pv.y + a.in.cpv * vv.y;
+        pin[4 * j + 2] = pv.z + a.in.cpv * vv.z; pin[4 * j + 3] = pv.w + a.in.cpv * vv.w;
+        vin[4 * j] = vv.x; vin[4 * j + 1] = vv.y; vin[4 * j + 2] = vv.z; vin[4 * j + 3] = vv.w;
+      }
+#pragma unroll
+      for (int s = 0; s < MAX_A; ++s) {
+        if (s < a.n_a) {
+          const float* ar = a.a[s] + gi * P + d0;
+          const float cp = a.in.cpa[s], cv = a.in.cva[s];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 x = *reinterpret_cast<const float4*>(ar + 4 * j);
+            pin[4 * j] += cp * x.x; pin[4 * j + 1] += cp * x.y; pin[4 * j + 2] += cp * x.z; pin[4 * j + 3] += cp * x.w;
+            vin[4 * j] += cv * x.x; vin[4 * j + 1] += cv * x.y; vin[4 * j + 2] += cv * x.z; vin[4 * j + 3] += cv * x.w;
+          }
+        }
+      }
+      uint32_t o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = pack_bf16(pin[2 * j], pin[2 * j + 1]);
+      tmem_st8(c.tmem + c.lane_sel + C_ACT + (uint32_t)(d0 / 2), o);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = pack_bf16(vin[2 * j], vin[2 * j + 1]);
+      tmem_st8(c.tmem + c.lane_sel + C_ACT + (uint32_t)(P / 2 + d0 / 2), o);
+    }
+    {
+      uint32_t o[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 x = *reinterpret_cast<const float4*>(yrow + 2 * P + c.hf * 16 + 4 * j);
+        o[2 * j] = pack_bf16(x.x, x.y);
+        o[2 * j + 1] = pack_bf16(x.z, x.w);
+      }
+      tmem_st8(c.tmem + c.lane_sel + C_HB + (uint32_t)(c.hf * 8), o);
+    }
+    write_time_block(c, a.t, a.period);
+
+    // ---- drift net
+    uint32_t z[32];
+    run_layer<false>(c, C_ACT, (2 * P + H) / 16, true, OFF_W1, HID, HID);
+    epi_relu<true>(c, z);
+#pragma unroll 1
+    for (int r = 0; r < NRES; ++r) {
+      uint32_t dummy[32];
+      run_layer<false>(c, C_ACT, HID / 16, true, off_hh(2 * r), HID, HID);
+      epi_relu<false>(c, dummy);
+      run_layer<false>(c, C_ACT, HID / 16, true, off_hh(2 * r + 1), HID, HID);
+      epi_residual(c, z);
+    }
+    run_layer<false>(c, C_ACT, HID / 16, true, OFF_WO, P, P);
+
+    // ---- output epilogue: this thread's 32 acceleration dims (hf*32 ..)
+    {
+      uint32_t r[32];
+      tmem_ld32(c.tmem + c.lane_sel + C_ACC + (uint32_t)(c.hf * 32), r);
+      tmem_ld_wait();
+      const int d0 = c.hf * 32;
+      if (a.a_out != nullptr && valid) {
+        float4* dst = reinterpret_cast<float4*>(a.a_out + g * P + d0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                               __uint_as_float(r[4 * j + 3]));
+      }
+      if (a.y_out != nullptr) {
+        const bool want_err = a.err_sumsq != nullptr;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {     // 8 dims per pass
+          const int dd = d0 + ch * 8;
+          float po[8], vo[8], ep[8], ev[8], p0r[8], v0r[8];
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const float4 pv = *reinterpret_cast<const float4*>(yrow + dd + 4 * j);
+            const float4 vv = *reinterpret_cast<const float4*>(yrow + P + dd + 4 * j);
+            p0r[4 * j] = pv.x; p0r[4 * j + 1] = pv.y; p0r[4 * j + 2] = pv.z; p0r[4 * j + 3] = pv.w;
+            v0r[4 * j] = vv.x; v0r[4 * j + 1] = vv.y; v0r[4 * j + 2] = vv.z; v0r[4 * j + 3] = vv.w;
+          }
+          const float oc = a.out.cpa[a.n_a], ov = a.out.cva[a.n_a], ecp = a.err.cpa[a.n_a], ecv = a.err.cva[a.n_a];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float ao = __uint_as_float(r[ch * 8 + j]);
+            po[j] = p0r[j] + a.out.cpv * v0r[j] + oc * ao;
+            vo[j] = v0r[j] + ov * ao;
+            ep[j] = ecp * ao;
+            ev[j] = ecv * ao;
+          }
+#pragma unroll
+          for (int s = 0; s < MAX_A; ++s) {
+            if (s < a.n_a) {
+              const float* ar = a.a[s] + gi * P + dd;
+              const float cp = a.out.cpa[s], cv = a.out.cva[s], xp = a.err.cpa[s], xv = a.err.cva[s];
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                const float4 x = *reinterpret_cast<const float4*>(ar + 4 * j);
+                const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  po[4 * j + e] += cp * xs[e];
+                  vo[4 * j + e] += cv * xs[e];
+                  ep[4 * j + e] += xp * xs[e];
+                  ev[4 * j + e] += xv * xs[e];
+                }
+              }
+            }
+          }
+          if (valid) {
+            float4* dp = reinterpret_cast<float4*>(a.y_out + g * D + dd);
+            float4* dv = reinterpret_cast<float4*>(a.y_out + g * D + P + dd);
+            dp[0] = make_float4(po[0], po[1], po[2], po[3]); dp[1] = make_float4(po[4], po[5], po[6], po[7]);
+            dv[0] = make_float4(vo[0], vo[1], vo[2], vo[3]); dv[1] = make_float4(vo[4], vo[5], vo[6], vo[7]);
+            if (want_err) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float tp = a.atol + a.rtol * fmaxf(fabsf(p0r[j]), fabsf(po[j]));
+                const float tv = a.atol + a.rtol * fmaxf(fabsf(v0r[j]), fabsf(vo[j]));
+                const float qp = ep[j] / tp, qv = ev[j] / tv;
+                err_local += (double)(qp * qp + qv * qv);
+              }
+            }
+          }
+        }
+        if (valid) {   // context h rides along unchanged (dh/dt = 0)
+          const float4* hs = reinterpret_cast<const float4*>(yrow + 2 * P + c.hf * 16);
+          float4* hd = reinterpret_cast<float4*>(a.y_out + g * D + 2 * P + c.hf * 16);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) hd[j] = hs[j];
+        }
+      }
+    }
+  }
+
+  if (a.err_sumsq != nullptr) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) err_local += __shfl_xor_sync(0xffffffffu, err_local, o);
+    if ((threadIdx.x & 31) == 0) err_red[threadIdx.x >> 5] = err_local;
+  }
+  stage_teardown(tmem_base);
+  if (a.err_sumsq != nullptr && threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < THREADS / 32; ++i) s += err_red[i];
+    atomicAdd(a.err_sumsq, s);
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------------
+struct StageFwdHost {   // mirrors ab200_stage_desc in the public header
+  int32_t n_a;
+  float in_cpv, in_cpa[MAX_A], in_cva[MAX_A];
+  float t;
+  float out_cpv, out_cpa[MAX_A + 1], out_cva[MAX_A + 1];
+  float err_pa[MAX_A + 1], err_va[MAX_A + 1];
+  float rtol, atol;
+};
+
+int stage_fwd_tc(const ab200_drift_desc* d, const uint8_t* image, const float* y0, const float* const* a_ptrs, const void* desc_v,
+                 int64_t B, float* a_out, float* y_out, double* err_sumsq, cudaStream_t st) {
+  const StageFwdHost& h = *reinterpret_cast<const StageFwdHost*>(desc_v);
+  if (h.n_a < 0 || h.n_a > MAX_A) return AB200_ERR_BAD_ARG;
+  StageFwdArgs k{};
+  k.wimg = image;
+  k.y0 = y0;
+  for (int i = 0; i < MAX_A; ++i) k.a[i] = (i < h.n_a) ? a_ptrs[i] : nullptr;
+  k.n_a = h.n_a;
+  k.in.cpv = h.in_cpv;
+  k.out.cpv = h.out_cpv;
+  k.err.cpv = 0.f;
+  for (int i = 0; i < MAX_A; ++i) { k.in.cpa[i] = h.in_cpa[i]; k.in.cva[i] = h.in_cva[i]; }
+  for (int i = 0; i <= MAX_A; ++i) {
+    k.out.cpa[i] = h.out_cpa[i]; k.out.cva[i] = h.out_cva[i];
+    k.err.cpa[i] = h.err_pa[i]; k.err.cva[i] = h.err_va[i];
+  }
+  k.t = h.t;
+  k.period = d->time_period;
+  k.a_out = a_out;
+  k.y_out = y_out;
+  k.err_sumsq = err_sumsq;
+  k.rtol = h.rtol;
+  k.atol = h.atol;
+  k.B = B;
+  k.ntiles = (int)((B + TM - 1) / TM);
+  k.status = reinterpret_cast<int*>(const_cast<uint8_t*>(image) + align_up(W_BYTES, 256));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int need = (k.ntiles + NSLOT - 1) / NSLOT;
+  const int grid = need < sms ? need : sms;
+  cudaError_t e = cudaFuncSetAttribute(stage_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W_BYTES);
+  if (e != cudaSuccess) { set_cuda_error(e); return AB200_ERR_CUDA; }
+  stage_fwd_tc_kernel<<<grid, THREADS, W_BYTES, st>>>(k);
+  return check_launch();
+}
+
+}  // namespace ab200

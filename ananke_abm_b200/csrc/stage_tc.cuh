@@ -1,0 +1,216 @@
+// Shared machinery of the tensor-core STAGE kernels (stage_fwd_tc.cu, stage_bwd_tc.cu, wgrad_tc.cu).
+//
+// A "stage" is one evaluation of the drift net at a Runge-Kutta stage input that is a linear combination of the
+// step's base state y0 = [p0, v0, h] and the accelerations a_1..a_s of earlier stages (the drift is second order:
+// k_j = (v_in_j, a_j), so every stage input, the step solution, the dense-output rows and the embedded error are
+// linear in (p0, v0, a_1..a_s)).  The stage kernels keep NO Runge-Kutta state in registers, which is what lets one
+// CTA run TWO 128-agent tiles at once ("slots", 8 warps each): while one slot is in its epilogue (tcgen05.ld ->
+// ReLU -> bf16 -> tcgen05.st) the tensor core runs the other slot's layer, sharing one resident copy of the weights.
+//
+//   shared memory : the six weight matrices as bf16 in the canonical un-swizzled K-major UMMA layout, each with a
+//                   16-wide K extension that carries the bias (hi + lo bf16 split) and, for the first layer, the
+//                   sin/cos time-feature columns -- bias and time features are applied by the tensor core, the
+//                   epilogue is a bare ReLU + pack.  The same image read MN-major is W^T (used by the dgrad GEMMs).
+//   tensor memory : per slot 256 columns: ACC fp32 [0,160) | ACT bf16 pairs [160,224) | HB (context h) [224,240)
+//                   | TB ("time/bias block": sin, cos hi/lo splits and two ones) [240,248)
+#pragma once
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace ab200 {
+namespace stc {
+using namespace umma;
+
+constexpr int P = 64, H = 32, HID = 128, NRES = 2, D = 2 * P + H;
+constexpr int SLOT_THREADS = 256, NSLOT = 2, THREADS = SLOT_THREADS * NSLOT;
+constexpr int TM = 128;                        // agents per tile == UMMA M
+constexpr int KX = 16;                         // K extension (one UMMA K step)
+constexpr int K1 = 2 * P + H + KX;             // 176
+constexpr int KH = HID + KX;                   // 144
+constexpr long long STAGE_WAIT_CYCLES = 100000000LL;   // ~50 ms: a layer takes microseconds
+constexpr int MAX_A = 7;                       // accelerations a stage may combine (dopri5: 6 + FSAL)
+
+// ---- weight image (bytes) ------------------------------------------------------------------------------
+constexpr uint32_t SBO = 128u;                                       // MN-adjacent core matrices
+__host__ __device__ constexpr uint32_t lbo(int N) { return (uint32_t)N * 16u; }   // K-adjacent core matrices
+constexpr uint32_t OFF_W1 = 0, SZ_W1 = (uint32_t)HID * K1 * 2;       // [128][176]
+constexpr uint32_t OFF_RES = OFF_W1 + SZ_W1, SZ_HH = (uint32_t)HID * KH * 2;   // 4 x [128][144]: A0, B0, A1, B1
+constexpr uint32_t OFF_WO = OFF_RES + 2u * NRES * SZ_HH, SZ_WO = (uint32_t)P * KH * 2;   // [64][144]
+constexpr uint32_t W_BYTES = OFF_WO + SZ_WO;                         // 210,944
+__host__ __device__ constexpr uint32_t off_hh(int m) { return OFF_RES + (uint32_t)m * SZ_HH; }
+// position of the extension columns inside a K extension block (A side holds the matching constants)
+//   0: s_hi*ws_hi  1: s_hi*ws_lo  2: s_lo*ws_hi  3: c_hi*wc_hi  4: c_hi*wc_lo  5: c_lo*wc_hi  6: 1*b_hi  7: 1*b_lo
+
+// ---- tensor-memory columns (per slot) ------------------------------------------------------------------
+constexpr uint32_t SLOT_COLS = 256, C_ACC = 0, C_ACT = 160, C_HB = 224, C_TB = 240;
+
+__device__ __forceinline__ void slot_sync(int slot) {
+  asm volatile("bar.sync %0, %1;" ::"r"(slot + 1), "n"(SLOT_THREADS) : "memory");
+}
+// d = {hi: bf16(a), lo: bf16(b)} with ReLU applied
+__device__ __forceinline__ uint32_t pack_relu_bf16(float lo_v, float hi_v) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi_v), "f"(lo_v));
+  return d;
+}
+__device__ __forceinline__ float bf16lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf16hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+
+// Per-thread view of its slot.
+struct SlotCtx {
+  uint32_t tmem;        // TMEM base of the slot (column 0, lane 0)
+  uint32_t lane_sel;    // (32 * (warp % 4)) << 16 : the TMEM lanes this warp may touch
+  uint32_t sbase;       // shared-memory address of the weight image
+  uint64_t* bar;        // MMA-completion mbarrier of the slot
+  int* status;
+  uint32_t phase;
+  int slot, stid, row, hf;   // thread index inside the slot, agent row (TMEM lane), column half
+  bool alive;
+};
+
+// One layer:  ACC[128 x N] = A * W^T  (K-major image)  or  A * W  (MN-major view of the same image, `TRANS`).
+//   A = `nks` K-steps of bf16 pairs starting at TMEM column a_col, optionally followed by the TB block (`ext`).
+// Called by all threads of the slot; returns when the accumulator is complete.
+template <bool TRANS>
+__device__ __forceinline__ void run_layer(SlotCtx& c, uint32_t a_col, int nks, bool ext, uint32_t w_off, int n_img, int N) {
+  tmem_st_wait();
+  tc_fence_before();
+  slot_sync(c.slot);
+  if (c.stid == 0) {
+    tc_fence_after();
+    const uint32_t idesc = make_idesc_bf16(TM, N, false, false, TRANS);
+    const uint32_t acc = c.tmem + C_ACC;
+    if (!TRANS) {
+      const uint32_t l = lbo(n_img);
+#pragma unroll 1
+      for (int ks = 0; ks < nks; ++ks)
+        mma_ts(acc, c.tmem + a_col + (uint32_t)ks * 8u, make_smem_desc(c.sbase + w_off + (uint32_t)ks * 2u * l, l, SBO, SWZ_NONE),
+               idesc, ks > 0 ? 1u : 0u);
+      if (ext)
+        mma_ts(acc, c.tmem + C_TB, make_smem_desc(c.sbase + w_off + (uint32_t)nks * 2u * l, l, SBO, SWZ_NONE), idesc, 1u);
+    } else {
+      // B'[n' = in][k' = out] = W[out][in]: K-direction cores are the image's 8-row groups (128 B apart), MN-direction
+      // cores are its 8-column groups (lbo(n_img) apart)
+      const uint32_t l = lbo(n_img);
+#pragma unroll 1
+      for (int ks = 0; ks < nks; ++ks)
+        mma_ts(acc, c.tmem + a_col + (uint32_t)ks * 8u, make_smem_desc(c.sbase + w_off + (uint32_t)ks * 2u * SBO, SBO, l, SWZ_NONE),
+               idesc, ks > 0 ? 1u : 0u);
+    }
+    mma_commit(c.bar);
+  }
+  __syncwarp();
+  if (c.alive && !mbar_wait(c.bar, c.phase, STAGE_WAIT_CYCLES)) { c.alive = false; *c.status = 1; }
+  c.phase ^= 1;
+  __syncwarp();
+  tc_fence_after();
+}
+
+// ---- hidden-layer epilogues: this thread's 64 columns (hf*64 ..) of its row ------------------------------
+// plain: act = relu(acc) -> ACT.  If KEEP, the packed result is also kept in z[32] (residual stream).
+template <bool KEEP>
+__device__ __forceinline__ void epi_relu(const SlotCtx& c, uint32_t (&z)[32]) {
+#pragma unroll
+  for (int ch = 0; ch < 2; ++ch) {
+    uint32_t r[32];
+    tmem_ld32(c.tmem + c.lane_sel + C_ACC + (uint32_t)(c.hf * 64 + ch * 32), r);
+    tmem_ld_wait();
+    uint32_t o[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      o[j] = pack_relu_bf16(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+      if (KEEP) z[ch * 16 + j] = o[j];
+    }
+    tmem_st16(c.tmem + c.lane_sel + C_ACT + (uint32_t)(c.hf * 32 + ch * 16), o);
+  }
+}
+// residual: z <- relu(acc + z) -> ACT
+__device__ __forceinline__ void epi_residual(const SlotCtx& c, uint32_t (&z)[32]) {
+#pragma unroll
+  for (int ch = 0; ch < 2; ++ch) {
+    uint32_t r[32];
+    tmem_ld32(c.tmem + c.lane_sel + C_ACC + (uint32_t)(c.hf * 64 + ch * 32), r);
+    tmem_ld_wait();
+    uint32_t o[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const uint32_t zz = z[ch * 16 + j];
+      o[j] = pack_relu_bf16(__uint_as_float(r[2 * j]) + bf16lo(zz), __uint_as_float(r[2 * j + 1]) + bf16hi(zz));
+      z[ch * 16 + j] = o[j];
+    }
+    tmem_st16(c.tmem + c.lane_sel + C_ACT + (uint32_t)(c.hf * 32 + ch * 16), o);
+  }
+}
+
+// TB block of this row: [s_hi, s_hi, s_lo, c_hi, c_hi, c_lo, 1, 1, 0 x 8] as 8 packed columns
+__device__ __forceinline__ void write_time_block(const SlotCtx& c, float t, float period) {
+  if (c.hf != 0) return;
+  float s, co;
+  time_features(t, period, s, co);
+  const float s_hi = __bfloat162float(__float2bfloat16_rn(s)), c_hi = __bfloat162float(__float2bfloat16_rn(co));
+  uint32_t o[8];
+  o[0] = pack_bf16(s_hi, s_hi);
+  o[1] = pack_bf16(s - s_hi, c_hi);
+  o[2] = pack_bf16(c_hi, co - c_hi);
+  o[3] = pack_bf16(1.0f, 1.0f);
+  o[4] = o[5] = o[6] = o[7] = 0u;
+  tmem_st8(c.tmem + c.lane_sel + C_TB, o);
+}
+
+// Host-visible description of how a stage input / output is combined from (p0, v0, a_1..a_n).
+//   p = p0 + cpv * v0 + sum_j cpa[j] * a_j        v = v0 + sum_j cva[j] * a_j
+struct Combo {
+  float cpv;
+  float cpa[MAX_A + 1];
+  float cva[MAX_A + 1];
+};
+
+// setup shared by the kernels: weights -> smem, TMEM, barriers.  Returns the per-thread slot context.
+__device__ __forceinline__ SlotCtx stage_setup(uint8_t* smem, const uint8_t* wimg, uint64_t* bars, uint32_t* tmem_base_s,
+                                               int* status) {
+  const int tid = threadIdx.x, warp = tid >> 5;
+  {
+    const int4* src = reinterpret_cast<const int4*>(wimg);
+    int4* dst = reinterpret_cast<int4*>(smem);
+    for (uint32_t i = tid; i < W_BYTES / 16; i += THREADS) dst[i] = src[i];
+  }
+  if (warp == 0) tmem_alloc<512>(tmem_base_s);
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_fence_init();
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  SlotCtx c;
+  c.slot = tid / SLOT_THREADS;
+  c.stid = tid % SLOT_THREADS;
+  const int sw = c.stid >> 5, lane = tid & 31;
+  const int q = warp & 3;
+  c.hf = sw >> 2;
+  c.row = q * 32 + lane;
+  c.tmem = *tmem_base_s + (uint32_t)c.slot * SLOT_COLS;
+  c.lane_sel = (uint32_t)(q * 32) << 16;
+  c.sbase = smem_u32(smem);
+  c.bar = &bars[c.slot];
+  c.status = status;
+  c.phase = 0;
+  c.alive = true;
+  return c;
+}
+
+__device__ __forceinline__ void stage_teardown(uint32_t tmem_base) {
+  tc_fence_before();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 0) tmem_dealloc<512>(tmem_base);
+}
+
+}  // namespace stc
+
+// host entry points (stage_fwd_tc.cu / stage_bwd_tc.cu / wgrad_tc.cu)
+size_t stage_tc_image_bytes();
+int stage_tc_pack(const float* w_flat, uint8_t* image, cudaStream_t st);
+
+}  // namespace ab200

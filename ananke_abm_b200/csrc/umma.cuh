@@ -37,6 +37,19 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, long l
   return true;
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 1-D bulk copy global -> shared (TMA engine, no tensor map); completion is signalled on `bar` as transaction bytes
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // ---- fences -------------------------------------------------------------------------------------------
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -68,9 +81,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   return d;
 }
 // instruction descriptor for kind::f16 with BF16 A/B, FP32 accumulate, both operands K-major
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool negate_a = false) {
+// a_mn / b_mn: operand is MN-major (the M resp. N index is the contiguous one in shared memory) instead of K-major
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool negate_a = false, bool a_mn = false,
+                                                       bool b_mn = false) {
   return (1u << 4) /* D = f32 */ | (1u << 7) /* A = bf16 */ | (1u << 10) /* B = bf16 */ | ((negate_a ? 1u : 0u) << 13) |
-         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+         ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 // ---- MMA issue (a single thread executes these) --------------------------------------------------------
@@ -143,6 +158,11 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 // no swizzle: 8x8 core matrices (8 rows x 16 B, 128 B contiguous); MN-adjacent cores SBO apart, K-adjacent LBO apart
 __device__ __forceinline__ uint32_t off_kmajor_noswz(int row, int k, uint32_t lbo, uint32_t sbo) {
   return (uint32_t)(row >> 3) * sbo + (uint32_t)(k >> 3) * lbo + (uint32_t)(row & 7) * 16u + (uint32_t)(k & 7) * 2u;
+}
+// MN-major, no swizzle: core matrix = 8 k-rows x 16 B (8 consecutive MN elements); K-adjacent cores LBO apart,
+// MN-adjacent cores SBO apart.  (The K-major image of a [N][K] matrix read this way is its transpose.)
+__device__ __forceinline__ uint32_t off_mnmajor_noswz(int mn, int k, uint32_t lbo, uint32_t sbo) {
+  return (uint32_t)(mn >> 3) * sbo + (uint32_t)(k >> 3) * lbo + (uint32_t)(k & 7) * 16u + (uint32_t)(mn & 7) * 2u;
 }
 // 128B swizzle: rows of 64 bf16 (128 B), 8-row groups of 1024 B, 16-byte chunk index XORed with (row % 8);
 // K beyond 64 continues in the next [rows x 64] atom, `atom_bytes` further on.  Base must be 1024-byte aligned.

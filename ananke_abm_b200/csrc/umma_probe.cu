@@ -3,6 +3,8 @@
 // against a CPU product, so a wrong descriptor encoding shows up here and not inside the fused solver kernel.
 //   a_mode: 0 = A in TMEM (tcgen05.st, TS form)   1 = A in smem, no swizzle   2 = A in smem, 128B swizzle
 //   b_mode:                                        1 = B in smem, no swizzle   2 = B in smem, 128B swizzle
+//   a_mode / b_mode 3 = operand in smem MN-major, no swizzle (LBO = K-direction core stride, SBO = MN-direction)
+//   a_mode / b_mode 4 = same bytes, LBO / SBO fields exchanged in the descriptor (to pin the field semantics)
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -42,17 +44,23 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(const float* __restr
       tmem_st16(tA + lane_sel + (uint32_t)(k0 / 2), r);
     }
     tmem_st_wait();
-  } else {
+  } else if (a_mode <= 2) {
     for (int k = 0; k < K; ++k) {
       const uint32_t off = (a_mode == 1) ? off_kmajor_noswz(row, k, a_lbo, a_sbo) : off_kmajor_sw128(row, k, 128u * 128u);
       *reinterpret_cast<__nv_bfloat16*>(sA + off) = __float2bfloat16_rn(A[row * K + k]);
     }
+  } else {
+    for (int k = 0; k < K; ++k)
+      *reinterpret_cast<__nv_bfloat16*>(sA + off_mnmajor_noswz(row, k, 128u, (uint32_t)(K / 8) * 128u)) =
+          __float2bfloat16_rn(A[row * K + k]);
   }
   // ---- operand B: all threads
   const uint32_t b_lbo = (uint32_t)N * 16u, b_sbo = 128u;
   for (int i = tid; i < N * K; i += blockDim.x) {
     const int n = i / K, k = i % K;
-    const uint32_t off = (b_mode == 1) ? off_kmajor_noswz(n, k, b_lbo, b_sbo) : off_kmajor_sw128(n, k, (uint32_t)N * 128u);
+    const uint32_t off = (b_mode == 1) ? off_kmajor_noswz(n, k, b_lbo, b_sbo)
+                         : (b_mode == 2) ? off_kmajor_sw128(n, k, (uint32_t)N * 128u)
+                                         : off_mnmajor_noswz(n, k, 128u, (uint32_t)(K / 8) * 128u);
     *reinterpret_cast<__nv_bfloat16*>(sB + off) = __float2bfloat16_rn(B[n * K + k]);
   }
   fence_async_smem();      // generic-proxy writes -> visible to the tensor core's async-proxy reads
@@ -61,16 +69,21 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(const float* __restr
 
   if (tid == 0) {
     tc_fence_after();
-    const uint32_t idesc = make_idesc_bf16(128, N);
+    const uint32_t idesc = make_idesc_bf16(128, N, false, a_mode >= 3, b_mode >= 3);
+    const uint32_t mn_lbo = 128u, mn_sbo = (uint32_t)(K / 8) * 128u;
     for (int ks = 0; ks < K / 16; ++ks) {
       uint64_t bdesc;
       if (b_mode == 1) bdesc = make_smem_desc(smem_u32(sB) + (uint32_t)ks * 2u * b_lbo, b_lbo, b_sbo, SWZ_NONE);
+      else if (b_mode == 3) bdesc = make_smem_desc(smem_u32(sB) + (uint32_t)ks * 2u * mn_lbo, mn_lbo, mn_sbo, SWZ_NONE);
+      else if (b_mode == 4) bdesc = make_smem_desc(smem_u32(sB) + (uint32_t)ks * 2u * mn_lbo, mn_sbo, mn_lbo, SWZ_NONE);
       else bdesc = make_smem_desc(smem_u32(sB) + (uint32_t)(ks >> 2) * (uint32_t)N * 128u + (uint32_t)(ks & 3) * 32u, 16u, 1024u, SWZ_128B);
       if (a_mode == 0) {
         mma_ts(tD, tA + (uint32_t)ks * 8u, bdesc, idesc, ks > 0 ? 1u : 0u);
       } else {
         uint64_t adesc;
         if (a_mode == 1) adesc = make_smem_desc(smem_u32(sA) + (uint32_t)ks * 2u * a_lbo, a_lbo, a_sbo, SWZ_NONE);
+        else if (a_mode == 3) adesc = make_smem_desc(smem_u32(sA) + (uint32_t)ks * 2u * mn_lbo, mn_lbo, mn_sbo, SWZ_NONE);
+        else if (a_mode == 4) adesc = make_smem_desc(smem_u32(sA) + (uint32_t)ks * 2u * mn_lbo, mn_sbo, mn_lbo, SWZ_NONE);
         else adesc = make_smem_desc(smem_u32(sA) + (uint32_t)(ks >> 2) * 128u * 128u + (uint32_t)(ks & 3) * 32u, 16u, 1024u, SWZ_128B);
         mma_ss(tD, adesc, bdesc, idesc, ks > 0 ? 1u : 0u);
       }
@@ -98,7 +111,7 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(const float* __restr
 
 int umma_probe(const float* A, const float* B, float* D, int N, int K, int a_mode, int b_mode, int* status, cudaStream_t st) {
   if ((N != 64 && N != 128) || K % 32 != 0 || K < 32 || K > 192) return AB200_ERR_BAD_ARG;
-  if (a_mode < 0 || a_mode > 2 || b_mode < 1 || b_mode > 2) return AB200_ERR_BAD_ARG;
+  if (a_mode < 0 || a_mode > 4 || b_mode < 1 || b_mode > 4) return AB200_ERR_BAD_ARG;
   if ((a_mode == 2 || b_mode == 2) && K % 64 != 0) return AB200_ERR_BAD_ARG;
   const size_t smem = 1024 + ((128 * K * 2 + 1023) / 1024) * 1024 + ((size_t)N * K * 2 + 1023) / 1024 * 1024;
   cudaError_t e = cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

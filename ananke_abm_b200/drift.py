@@ -38,6 +38,11 @@ class DriftSpec:
         """Differentiable flatten in `ab200_drift_desc` order; autograd routes the flat gradient back."""
         return torch.cat([p.reshape(-1) for p in self.params])
 
+    def tc_stage_supported(self) -> bool:
+        """shape instantiated in the tensor-core stage kernels (stage_tc.cuh)"""
+        d = self.desc
+        return (d.pos_dim, d.ctx_dim, d.hidden, d.n_res, d.res_act, d.potential) == (64, 32, 128, 2, 0, 0)
+
     def supported(self) -> bool:
         d = self.desc
         return (d.pos_dim, d.ctx_dim, d.hidden, d.n_res, d.res_act, d.potential) in _SUPPORTED

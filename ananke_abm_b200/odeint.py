@@ -129,6 +129,28 @@ class _FusedRK4(torch.autograd.Function):
         return gy0, None, gw, None, None, None
 
 
+class _StageRK4TC(torch.autograd.Function):
+    """rk4 on the tensor-core STAGE kernels with the discrete adjoint (bf16 operands, fp32 accumulation and state):
+    the training path of `precision='bf16'`.  Saves the trajectory rows and the three stage accelerations per step."""
+
+    @staticmethod
+    def forward(ctx, y0, t, w_flat, spec: DriftSpec, t_host):
+        from . import stage
+        eng = stage.TcEngine(spec, w_flat)
+        th = [float(v) for v in t_host.tolist()]
+        y_path, acc = stage.rk4_forward(eng, y0.contiguous().float(), th, save_stages=True)
+        ctx.eng, ctx.th = eng, th
+        ctx.save_for_backward(y_path, acc)
+        return y_path
+
+    @staticmethod
+    def backward(ctx, grad_y_path):
+        from . import stage
+        y_path, acc = ctx.saved_tensors
+        gy0, gw = stage.rk4_backward(ctx.eng, ctx.th, y_path, acc, grad_y_path.contiguous().float())
+        return gy0, None, gw, None, None
+
+
 def drift_eval(spec: DriftSpec, w_flat: torch.Tensor, t: float, y: torch.Tensor, precision: int = 0) -> torch.Tensor:
     """One evaluation f(t, y) of a recognised drift net on the CUDA path (no autograd)."""
     L = _lib.lib()
@@ -365,6 +387,9 @@ def odeint(func, y0, t, *, rtol: float = 1e-7, atol: float = 1e-9, method: Optio
             warnings.warn(f"rk4: Unexpected arguments {options}")
         if spec is not None and y0.shape[1] == spec.state_dim and y0.dtype == torch.float32:
             w_flat = spec.flat_params()
+            needs_grad = torch.is_grad_enabled() and (y0.requires_grad or w_flat.requires_grad)
+            if precision == _lib.PREC_BF16 and needs_grad and spec.tc_stage_supported():
+                return _StageRK4TC.apply(y0, t, w_flat, spec, t_host)
             return _FusedRK4.apply(y0, t, w_flat, spec, precision, t_host)
         f = _wrap_func(func, y0, decreasing)
         tt = -t if decreasing else t

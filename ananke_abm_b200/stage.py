@@ -1,0 +1,268 @@
+"""Tensor-core STAGE path: explicit Runge-Kutta solvers assembled on the host from one-drift-evaluation launches
+(`ab200_stage_forward` / `ab200_stage_backward` / `ab200_wgrad_*`, include/ananke_b200.h).
+
+The drift of both reference models is second order (dp/dt = v), so every stage input, step solution, dense-output
+row and embedded error of torchdiffeq's solvers is linear in the step's base state y0 = [p0, v0, h] and the stage
+accelerations a_j; the host only computes those coefficients (`Tableau.combo`) -- all arithmetic runs in the library.
+
+  rk4     torchdiffeq fixed_grid.py RK4 / rk_common.py rk4_alt_step_func (3/8 rule), one step per grid interval
+          -- the call at /root/reference/src/ananke_abm/models/mode_sep/architecture/model.py:184-191
+  dopri5  torchdiffeq dopri5.py + rk_common.py RKAdaptiveStepsizeODESolver (FSAL, dense output)
+          -- the call at /root/reference/src/ananke_abm/models/latent_ode/architecture/model.py:196
+The backward pass is the discrete adjoint of the accepted steps == reverse-mode autograd through the solver ops,
+which is what the reference's training loops compute (mode_sep/train/train.py:162, latent_ode/train/train.py:73).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import _lib
+from .drift import DriftSpec
+
+MAX_A = 7
+TM = 128
+
+
+class StageDesc(C.Structure):
+    """Mirror of `ab200_stage_desc`."""
+    _fields_ = [
+        ("n_a", C.c_int32),
+        ("in_cpv", C.c_float), ("in_cpa", C.c_float * MAX_A), ("in_cva", C.c_float * MAX_A),
+        ("t", C.c_float),
+        ("out_cpv", C.c_float), ("out_cpa", C.c_float * (MAX_A + 1)), ("out_cva", C.c_float * (MAX_A + 1)),
+        ("err_pa", C.c_float * (MAX_A + 1)), ("err_va", C.c_float * (MAX_A + 1)),
+        ("rtol", C.c_float), ("atol", C.c_float),
+    ]
+
+
+@dataclass
+class Combo:
+    """p = p0 + cpv v0 + sum cpa[j] a_j ;  v = v0 + sum cva[j] a_j"""
+    cpv: float
+    cpa: List[float]
+    cva: List[float]
+
+
+class Tableau:
+    def __init__(self, c: Sequence[float], beta: Sequence[Sequence[float]], b: Sequence[float],
+                 b_err: Optional[Sequence[float]] = None, b_mid: Optional[Sequence[float]] = None):
+        self.c, self.beta, self.b, self.b_err, self.b_mid = list(c), [list(r) for r in beta], list(b), b_err, b_mid
+        self.s = len(self.beta)
+
+    def combo(self, w: Sequence[float], dt: float) -> Combo:
+        """y0 + dt sum_j w_j k_j with k_j = (v_in_j, a_j) written over (p0, v0, a_1..a_n)."""
+        n = len(w)
+        cva_rows = [[dt * x for x in self.beta[j]] + [0.0] * (n - len(self.beta[j])) for j in range(n)]
+        cpa = [dt * sum(w[j] * cva_rows[j][l] for j in range(n)) for l in range(n)]
+        return Combo(dt * sum(w), cpa, [dt * x for x in w])
+
+    def stage_input(self, i: int, dt: float) -> Combo:
+        """input of stage i (0-based): combination of a_0..a_{i-1}"""
+        return self.combo(self.beta[i], dt)
+
+
+RK38 = Tableau(c=[0.0, 1 / 3, 2 / 3, 1.0], beta=[[], [1 / 3], [-1 / 3, 1.0], [1.0, -1.0, 1.0]], b=[1 / 8, 3 / 8, 3 / 8, 1 / 8])
+
+_DP_BETA = [
+    [],
+    [1 / 5],
+    [3 / 40, 9 / 40],
+    [44 / 45, -56 / 15, 32 / 9],
+    [19372 / 6561, -25360 / 2187, 64448 / 6561, -212 / 729],
+    [9017 / 3168, -355 / 33, 46732 / 5247, 49 / 176, -5103 / 18656],
+    [35 / 384, 0.0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84],
+]
+_DP_C_SOL = [35 / 384, 0.0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84, 0.0]
+_DP_C_ERR = [35 / 384 - 1951 / 21600, 0.0, 500 / 1113 - 22642 / 50085, 125 / 192 - 451 / 720,
+             -2187 / 6784 - -12231 / 42400, 11 / 84 - 649 / 6300, -1.0 / 60.0]
+_DP_C_MID = [6025192743 / 30085553152 / 2, 0.0, 51252292925 / 65400821598 / 2, -2691868925 / 45128329728 / 2,
+             187940372067 / 1594534317056 / 2, -1776094331 / 19743644256 / 2, 11237099 / 235043384 / 2]
+DOPRI5 = Tableau(c=[0.0, 1 / 5, 3 / 10, 4 / 5, 8 / 9, 1.0, 1.0], beta=_DP_BETA, b=_DP_C_SOL, b_err=_DP_C_ERR, b_mid=_DP_C_MID)
+
+
+def dopri5_interp_weights(x: float) -> List[float]:
+    """Weights W_j(x) with y(t0 + x dt) = y0 + dt sum_j W_j k_j: torchdiffeq's quartic dense output
+    (interp.py `_interp_fit` / `_interp_evaluate`) expanded over the seven stage derivatives."""
+    e1 = [1.0, 0, 0, 0, 0, 0, 0]
+    e7 = [0, 0, 0, 0, 0, 0, 1.0]
+    cs, cm = _DP_C_SOL, _DP_C_MID
+    out = []
+    for j in range(7):
+        c2 = e7[j] - 4 * e1[j] - 5 * cs[j] + 16 * cm[j]
+        c3 = 5 * e1[j] - 3 * e7[j] + 14 * cs[j] - 32 * cm[j]
+        c4 = 2 * (e7[j] - e1[j]) - 8 * cs[j] + 16 * cm[j]
+        out.append(x * e1[j] + x * x * c2 + x ** 3 * c3 + x ** 4 * c4)
+    return out
+
+
+def _ptr_array(tensors: Sequence[torch.Tensor]):
+    n = max(len(tensors), 1)
+    return (C.c_void_p * n)(*[t.data_ptr() for t in tensors])
+
+
+def _fill(dst, vals):
+    for i, v in enumerate(vals):
+        dst[i] = float(v)
+
+
+class TcEngine:
+    """Holds the packed bf16 weight image for one parameter version and issues stage launches on the current stream."""
+
+    def __init__(self, spec: DriftSpec, w_flat: torch.Tensor):
+        self.L = _lib.lib()
+        self.spec, self.desc = spec, spec.desc
+        self.dev = w_flat.device
+        nbytes = self.L.ab200_stage_image_bytes(C.byref(self.desc))
+        if nbytes == 0:
+            raise _lib.Ab200Error("the tensor-core stage path is instantiated for the mode_sep drift shape only")
+        self.image = torch.empty(int(nbytes), dtype=torch.uint8, device=self.dev)
+        self.w = w_flat.detach().contiguous().float()
+        _lib.check(self.L.ab200_stage_pack(C.byref(self.desc), self.w.data_ptr(), self.image.data_ptr(), self.image.numel(),
+                                           _stream()), "ab200_stage_pack")
+        off_i, off_p = C.c_int64(0), C.c_int64(0)
+        self.L.ab200_stage_status_offset(C.byref(self.desc), C.byref(off_i), C.byref(off_p))
+        self._img_status, self._part_status = int(off_i.value), int(off_p.value)
+        self.P, self.H = self.desc.pos_dim, self.desc.ctx_dim
+        self.D = 2 * self.P + self.H
+
+    # ---- forward ------------------------------------------------------------------------------------
+    def stage_forward(self, y0, a: Sequence[torch.Tensor], cin: Combo, t: float, a_out=None, y_out=None, cout: Optional[Combo] = None,
+                      err_sumsq=None, cerr: Optional[Combo] = None, rtol: float = 0.0, atol: float = 0.0) -> None:
+        s = StageDesc()
+        s.n_a = len(a)
+        s.in_cpv = cin.cpv
+        _fill(s.in_cpa, cin.cpa[:len(a)])
+        _fill(s.in_cva, cin.cva[:len(a)])
+        s.t = float(t)
+        if cout is not None:
+            s.out_cpv = cout.cpv
+            _fill(s.out_cpa, cout.cpa[:len(a) + 1])
+            _fill(s.out_cva, cout.cva[:len(a) + 1])
+        if cerr is not None:
+            _fill(s.err_pa, cerr.cpa[:len(a) + 1])
+            _fill(s.err_va, cerr.cva[:len(a) + 1])
+        s.rtol, s.atol = float(rtol), float(atol)
+        rc = self.L.ab200_stage_forward(C.byref(self.desc), self.image.data_ptr(), y0.data_ptr(), C.cast(_ptr_array(a), C.c_void_p),
+                                        C.byref(s), y0.shape[0], None if a_out is None else a_out.data_ptr(),
+                                        None if y_out is None else y_out.data_ptr(),
+                                        None if err_sumsq is None else err_sumsq.data_ptr(), _stream())
+        _lib.check(rc, "ab200_stage_forward")
+
+    def combine(self, y0, a: Sequence[torch.Tensor], c: Combo, out) -> None:
+        n = len(a)
+        cpa = (C.c_float * max(n, 1))(*[float(x) for x in c.cpa[:n]])
+        cva = (C.c_float * max(n, 1))(*[float(x) for x in c.cva[:n]])
+        rc = self.L.ab200_pv_combine(C.byref(self.desc), y0.data_ptr(), C.cast(_ptr_array(a), C.c_void_p), n, float(c.cpv),
+                                     C.cast(cpa, C.c_void_p), C.cast(cva, C.c_void_p), y0.shape[0], out.data_ptr(), _stream())
+        _lib.check(rc, "ab200_pv_combine")
+
+    # ---- backward -----------------------------------------------------------------------------------
+    def backward_begin(self, B: int, stages_per_flush: int) -> None:
+        self.ntiles = (B + TM - 1) // TM
+        self.nblobs = self.ntiles * stages_per_flush
+        nb = self.L.ab200_stage_spill_bytes(C.byref(self.desc), self.nblobs)
+        self.spill = torch.empty(int(nb), dtype=torch.uint8, device=self.dev)
+        npart = self.L.ab200_wgrad_partial_bytes(C.byref(self.desc))
+        self.partial = torch.zeros(int(npart), dtype=torch.uint8, device=self.dev)
+        self.used = 0
+
+    def combine_backward(self, g, c: Combo, G_y0, G_a: Sequence[torch.Tensor], accumulate: bool) -> None:
+        n = len(G_a)
+        cpa = (C.c_float * max(n, 1))(*[float(x) for x in c.cpa[:n]])
+        cva = (C.c_float * max(n, 1))(*[float(x) for x in c.cva[:n]])
+        rc = self.L.ab200_pv_combine_backward(C.byref(self.desc), g.data_ptr(), n, float(c.cpv), C.cast(cpa, C.c_void_p),
+                                              C.cast(cva, C.c_void_p), g.shape[0], G_y0.data_ptr(), C.cast(_ptr_array(G_a), C.c_void_p),
+                                              1 if accumulate else 0, _stream())
+        _lib.check(rc, "ab200_pv_combine_backward")
+
+    def stage_backward(self, y0, a: Sequence[torch.Tensor], cin: Combo, t: float, g_a, G_y0, G_a: Sequence[torch.Tensor]) -> None:
+        if self.used + self.ntiles > self.nblobs:
+            self.flush()
+        s = StageDesc()
+        s.n_a = len(a)
+        s.in_cpv = cin.cpv
+        _fill(s.in_cpa, cin.cpa[:len(a)])
+        _fill(s.in_cva, cin.cva[:len(a)])
+        s.t = float(t)
+        rc = self.L.ab200_stage_backward(C.byref(self.desc), self.image.data_ptr(), y0.data_ptr(), C.cast(_ptr_array(a), C.c_void_p),
+                                         C.byref(s), y0.shape[0], g_a.data_ptr(), G_y0.data_ptr(), C.cast(_ptr_array(G_a), C.c_void_p),
+                                         self.spill.data_ptr(), self.spill.numel(), self.used, self.nblobs, self.partial.data_ptr(),
+                                         _stream())
+        _lib.check(rc, "ab200_stage_backward")
+        self.used += self.ntiles
+
+    def flush(self) -> None:
+        if self.used:
+            rc = self.L.ab200_wgrad_accumulate(C.byref(self.desc), self.spill.data_ptr(), self.nblobs, self.used,
+                                               self.partial.data_ptr(), _stream())
+            _lib.check(rc, "ab200_wgrad_accumulate")
+            self.used = 0
+
+    def backward_end(self) -> torch.Tensor:
+        self.flush()
+        gw = torch.empty_like(self.w)
+        _lib.check(self.L.ab200_wgrad_finalize(C.byref(self.desc), self.partial.data_ptr(), gw.data_ptr(), _stream()),
+                   "ab200_wgrad_finalize")
+        self.spill = None
+        return gw
+
+    def check_status(self) -> None:
+        """Debug aid (host sync): raises if any tensor-core kernel hit its bounded barrier wait."""
+        st = int(self.image[self._img_status:self._img_status + 4].view(torch.int32).item())
+        sp = 0
+        if getattr(self, "partial", None) is not None:
+            sp = int(self.partial[self._part_status:self._part_status + 4].view(torch.int32).item())
+        if st or sp:
+            raise _lib.Ab200Error(f"tensor-core kernel barrier timeout (stage status {st}, wgrad status {sp})")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+# --------------------------------------------------------------------------------------------------------
+# fixed-grid rk4 (3/8 rule) with the discrete adjoint
+# --------------------------------------------------------------------------------------------------------
+def rk4_forward(eng: TcEngine, y0: torch.Tensor, t_host: Sequence[float], save_stages: bool):
+    """-> y_path [T, B, D], acc [T-1, 3, B, P] (stage accelerations a_1..a_3 of every step) or None."""
+    B, T = y0.shape[0], len(t_host)
+    y_path = torch.empty((T, B, eng.D), dtype=torch.float32, device=y0.device)
+    y_path[0].copy_(y0)
+    n_keep = T - 1 if save_stages else 1
+    acc = torch.empty((n_keep, 3, B, eng.P), dtype=torch.float32, device=y0.device)
+    for n in range(T - 1):
+        t0, dt = float(t_host[n]), float(t_host[n + 1]) - float(t_host[n])
+        A = acc[n if save_stages else 0]
+        yn = y_path[n]
+        for i in range(3):
+            eng.stage_forward(yn, [A[j] for j in range(i)], RK38.stage_input(i, dt), t0 + RK38.c[i] * dt, a_out=A[i])
+        eng.stage_forward(yn, [A[0], A[1], A[2]], RK38.stage_input(3, dt), float(t_host[n + 1]), y_out=y_path[n + 1],
+                          cout=RK38.combo(RK38.b, dt))
+    return y_path, (acc if save_stages else None)
+
+
+def rk4_backward(eng: TcEngine, t_host: Sequence[float], y_path: torch.Tensor, acc: torch.Tensor, grad_y_path: torch.Tensor):
+    """-> (grad_y0 [B, D], grad_w_flat)."""
+    T, B, D = y_path.shape
+    dev = y_path.device
+    eng.backward_begin(B, stages_per_flush=4)
+    lam = grad_y_path[T - 1].contiguous().clone()
+    G_y0 = torch.empty_like(lam)
+    G_a = [torch.empty((B, eng.P), dtype=torch.float32, device=dev) for _ in range(4)]
+    for n in range(T - 2, -1, -1):
+        t0, dt = float(t_host[n]), float(t_host[n + 1]) - float(t_host[n])
+        A = acc[n]
+        yn = y_path[n]
+        eng.combine_backward(lam, RK38.combo(RK38.b, dt), G_y0, G_a, accumulate=False)
+        for i in (3, 2, 1, 0):
+            t_i = float(t_host[n + 1]) if i == 3 else t0 + RK38.c[i] * dt
+            eng.stage_backward(yn, [A[j] for j in range(i)], RK38.stage_input(i, dt), t_i, G_a[i], G_y0, G_a[:i])
+        eng.flush()
+        G_y0.add_(grad_y_path[n])
+        lam, G_y0 = G_y0, lam
+    gw = eng.backward_end()
+    return lam, gw

@@ -115,6 +115,64 @@ int ab200_rk_combine_errnorm(const float* y0, const float* const* k, const float
                              const float* cerr_host, int32_t n_k, float dt, float rtol, float atol,
                              float* y1_out, float* sumsq, int64_t n, ab200_stream_t stream);
 
+/* ---- tensor-core STAGE path: one drift evaluation per launch, any explicit Runge-Kutta tableau ----------------
+ * The drift is second order (dp/dt = v), so every stage input, step solution, dense-output row and embedded error
+ * estimate of torchdiffeq's rk4 (rk_common.py rk4_alt_step_func) and dopri5 (rk_common.py _runge_kutta_step,
+ * _adaptive_step; interp.py; misc.py _compute_error_ratio) is LINEAR in the step's base state y0 = [p0, v0, h] and
+ * the stage accelerations a_1..a_s.  A stage launch evaluates
+ *     p = p0 + in_cpv v0 + sum_j in_cpa[j] a_j ,  v = v0 + sum_j in_cva[j] a_j ,  a_out = net(p, v, h, t)
+ * on the tcgen05 tensor cores (bf16 operands, fp32 accumulation in tensor memory) and optionally
+ *     y_out = [p0 + out_cpv v0 + sum_j out_cpa[j] a_j ,  v0 + sum_j out_cva[j] a_j , h]     (index n_a = a_out)
+ *     *err_sumsq += sum_i ( e_i / (atol + rtol max(|y0_i|, |y_out_i|)) )^2 ,  e.p = sum_j err_pa[j] a_j, e.v likewise.
+ * Replaces the Python-level stage loop inside torchdiffeq that the reference's odeint calls run
+ * (mode_sep/architecture/model.py:184-191, latent_ode/architecture/model.py:196).  mode_sep drift shape only. */
+#define AB200_STAGE_MAX_A 7
+typedef struct ab200_stage_desc {
+  int32_t n_a;                                   /* accelerations combined into the stage input (0..7) */
+  float in_cpv, in_cpa[AB200_STAGE_MAX_A], in_cva[AB200_STAGE_MAX_A];
+  float t;                                       /* stage time */
+  float out_cpv, out_cpa[AB200_STAGE_MAX_A + 1], out_cva[AB200_STAGE_MAX_A + 1];
+  float err_pa[AB200_STAGE_MAX_A + 1], err_va[AB200_STAGE_MAX_A + 1];
+  float rtol, atol;
+} ab200_stage_desc;
+
+/* bf16 UMMA image of the drift weights (+ a status word); build once per parameter update with ab200_stage_pack */
+size_t ab200_stage_image_bytes(const ab200_drift_desc* d);
+int ab200_stage_pack(const ab200_drift_desc* d, const float* w_flat, void* image, size_t image_bytes, ab200_stream_t stream);
+/* `a` : host array of n_a device pointers ([B][P] fp32 each).  a_out [B][P], y_out [B][D], err_sumsq (device double,
+ * accumulated) may each be NULL. */
+int ab200_stage_forward(const ab200_drift_desc* d, const void* image, const float* y0, const float* const* a,
+                        const ab200_stage_desc* s, int64_t B, float* a_out, float* y_out, double* err_sumsq,
+                        ab200_stream_t stream);
+/* Vector-Jacobian product of one stage = what autograd does for the ops of one `func` call inside the solver
+ * (mode_sep/train/train.py:162).  g_a [B][P] is dL/da_out.  ACCUMULATES dL/d(stage input) into G_y0 [B][D] and
+ * G_a[j] [B][P] (j < n_a), and writes the layer (activation, gradient) blobs of tile i to blob index blob0 + i of
+ * `spill` (sized by ab200_stage_spill_bytes(nblobs)); ab200_wgrad_accumulate turns filled blobs into weight
+ * gradients.  `partial` (ab200_wgrad_partial_bytes, ZEROED by the caller before the first stage of a backward pass)
+ * holds the per-SM partial weight gradients; ab200_wgrad_finalize writes grad_w_flat (OVERWRITTEN) in
+ * ab200_drift_param_count order. */
+size_t ab200_stage_spill_bytes(const ab200_drift_desc* d, int32_t nblobs);
+size_t ab200_wgrad_partial_bytes(const ab200_drift_desc* d);
+int ab200_stage_backward(const ab200_drift_desc* d, const void* image, const float* y0, const float* const* a,
+                         const ab200_stage_desc* s, int64_t B, const float* g_a, float* G_y0, float* const* G_a,
+                         void* spill, size_t spill_bytes, int32_t blob0, int32_t nblobs, void* partial,
+                         ab200_stream_t stream);
+int ab200_wgrad_accumulate(const ab200_drift_desc* d, const void* spill, int32_t nblobs, int32_t used, void* partial,
+                           ab200_stream_t stream);
+int ab200_wgrad_finalize(const ab200_drift_desc* d, const void* partial, float* grad_w_flat, ab200_stream_t stream);
+/* 1 if any tensor-core kernel that used `image` / `partial` hit its bounded mbarrier wait (a bug, never expected) */
+int ab200_stage_status_offset(const ab200_drift_desc* d, int64_t* image_status_byte, int64_t* partial_status_byte);
+
+/* Elementwise companions (one HBM pass): out = [p0 + cpv v0 + sum cpa[j] a_j, v0 + sum cva[j] a_j, h]  (dense-output
+ * rows: tdq interp.py _interp_evaluate; step solutions) and the adjoint scatter
+ *   G_y0.p (+)= g.p ; G_y0.v (+)= cpv g.p + g.v ; G_y0.h (+)= g.h ; G_a[j] (+)= cpa[j] g.p + cva[j] g.v
+ * (accumulate = 0 overwrites).  n_a <= 8; `a` / `G_a` are host arrays of device pointers. */
+int ab200_pv_combine(const ab200_drift_desc* d, const float* y0, const float* const* a, int32_t n_a, float cpv,
+                     const float* cpa_host, const float* cva_host, int64_t B, float* out, ab200_stream_t stream);
+int ab200_pv_combine_backward(const ab200_drift_desc* d, const float* g, int32_t n_a, float cpv, const float* cpa_host,
+                              const float* cva_host, int64_t B, float* G_y0, float* const* G_a, int32_t accumulate,
+                              ab200_stream_t stream);
+
 /* ---- graph attention over the zone graph (the `gnn_embed` slot) ------------------------------------
  * No reference implementation exists (README.md:5,57,80 promise it; pyproject.toml:25 declares torch-geometric
  * 2.6.1, never imported): semantics are PyG `GATConv` -- x'_i = ||_h sum_{j in N(i)+i}
@@ -140,7 +198,8 @@ int ab200_gat_backward(const int32_t* rowptr, const int32_t* col, const int32_t*
                        ab200_stream_t stream);
 
 /* ---- self-test of the tcgen05 plumbing (one CTA): D[128,N] = A[128,K] * B[N,K]^T, bf16 operands, fp32 result.
- * a_mode 0/1/2 = A in TMEM / smem un-swizzled / smem 128B-swizzled; b_mode 1/2 = B un-swizzled / 128B-swizzled.
+ * a_mode 0/1/2 = A in TMEM / smem un-swizzled / smem 128B-swizzled; b_mode 1/2 = B un-swizzled / 128B-swizzled;
+ * mode 3 (either operand) = smem MN-major un-swizzled, mode 4 = the same bytes with LBO/SBO exchanged.
  * `status` (device int) receives 0, or 1 if the MMA completion barrier timed out.  No reference counterpart. */
 int ab200_debug_umma_probe(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t a_mode,
                            int32_t b_mode, int32_t* status, ab200_stream_t stream);

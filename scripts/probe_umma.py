@@ -8,8 +8,8 @@ for (N, K) in [(128, 128), (64, 128), (128, 64), (128, 192)]:
     A = torch.randn(128, K, device=dev)
     B = torch.randn(N, K, device=dev)
     ref = (A.bfloat16().float() @ B.bfloat16().float().T)
-    for a_mode in (0, 1, 2):
-        for b_mode in (1, 2):
+    for a_mode in (0, 1, 2, 3, 4):
+        for b_mode in (1, 2, 3, 4):
             D = torch.zeros(128, N, device=dev)
             st = torch.full((1,), -7, dtype=torch.int32, device=dev)
             rc = L.ab200_debug_umma_probe(A.data_ptr(), B.data_ptr(), D.data_ptr(), N, K, a_mode, b_mode, st.data_ptr(), torch.cuda.current_stream().cuda_stream)
