@@ -58,6 +58,8 @@ int pv_combine(const ab200_drift_desc* d, const float* y0, const float* const* a
 int pv_combine_bwd(const ab200_drift_desc* d, const float* g, int n_a, float cpv, const float* cpa, const float* cva, int64_t B,
                    float* G_y0, float* const* G_a, int accumulate, cudaStream_t st);
 
+int rows_transpose(const float* src, float* dst, int64_t B, int F, int mode, cudaStream_t st);
+
 static bool stage_shape_ok(const ab200_drift_desc* d) {
   return d && d->pos_dim == 64 && d->ctx_dim == 32 && d->hidden == 128 && d->n_res == 2 && d->res_act == 0 && d->potential == 0;
 }
@@ -173,6 +175,17 @@ int ab200_rk_combine_errnorm(const float* y0, const float* const* k, const float
                              ab200_stream_t stream) {
   if (!y0 || !k || !csol_host || !cerr_host || !sumsq || n <= 0) return AB200_ERR_BAD_ARG;
   return rk_combine_errnorm(y0, k, csol_host, cerr_host, n_k, dt, rtol, atol, y1_out, sumsq, n, (cudaStream_t)stream);
+}
+
+int ab200_rows_block(const float* src_rowmajor, float* dst_blocked, int64_t B, int32_t F, int32_t accumulate,
+                     ab200_stream_t stream) {
+  if (!src_rowmajor || !dst_blocked || B <= 0) return AB200_ERR_BAD_ARG;
+  return rows_transpose(src_rowmajor, dst_blocked, B, F, accumulate ? 1 : 0, (cudaStream_t)stream);
+}
+
+int ab200_rows_unblock(const float* src_blocked, float* dst_rowmajor, int64_t B, int32_t F, ab200_stream_t stream) {
+  if (!src_blocked || !dst_rowmajor || B <= 0) return AB200_ERR_BAD_ARG;
+  return rows_transpose(src_blocked, dst_rowmajor, B, F, 2, (cudaStream_t)stream);
 }
 
 size_t ab200_stage_image_bytes(const ab200_drift_desc* d) { return stage_shape_ok(d) ? stage_tc_image_bytes() : 0; }

@@ -10,8 +10,9 @@
 //      (every element is owned by one thread: plain read-modify-write, no atomics),
 //   4. writes every layer's (input activation, output gradient) pair as bf16 "blobs" already laid out as the
 //      canonical MN-major UMMA operand image (K = agent), which wgrad_tc.cu streams straight into shared memory.
-// The weight gradient cannot be fused here: its fp32 accumulators (95,168 floats = 372 KiB) exceed the 256 KiB of
-// tensor memory of one SM, see DESIGN.md.
+// All per-agent fp32 buffers are tile-blocked (stage_tc.cuh), so every global access of a warp is one contiguous
+// 512-byte segment.  The weight gradient cannot be fused here: its fp32 accumulators (95,168 floats = 372 KiB)
+// exceed the 256 KiB of tensor memory of one SM, see DESIGN.md.
 #include "stage_tc.cuh"
 #include "wgrad_layout.cuh"
 
@@ -20,14 +21,14 @@ using namespace stc;
 
 struct StageBwdArgs {
   const uint8_t* wimg;
-  const float* y0;            // [B][160]
-  const float* a[MAX_A];      // [B][64]
+  const float* y0;            // blocked [Bp][160]
+  const float* a[MAX_A];      // blocked [Bp][64]
   int n_a;
   Combo in;
   float t, period;
-  const float* g_a;           // [B][64]  dL/da_out of this stage
-  float* G_y0;                // [B][160] accumulated
-  float* G_a[MAX_A];          // [B][64]  accumulated (only j < n_a)
+  const float* g_a;           // blocked [Bp][64]  dL/da_out of this stage
+  float* G_y0;                // blocked [Bp][160] accumulated
+  float* G_a[MAX_A];          // blocked [Bp][64]  accumulated (only j < n_a)
   uint8_t* spill;             // blob buffer (SpillLayout)
   float* g_bout;              // [64] atomically accumulated column sums of g_a (bias gradient of the output layer)
   int64_t B;
@@ -37,16 +38,19 @@ struct StageBwdArgs {
   int* status;
 };
 
-// store this thread's 32 columns (16 packed pairs = 4 feature groups) of a blob: feature group fg0.., row = agent
-__device__ __forceinline__ void spill16(uint8_t* blob, int fg0, int row, const uint32_t (&o)[16]) {
+// store packed pairs as feature groups of a blob: NG groups starting at fg0, row = agent
+template <int NG>
+__device__ __forceinline__ void spill_groups(uint8_t* blob, int fg0, int row, const uint32_t* o) {
 #pragma unroll
-  for (int q = 0; q < 4; ++q)
+  for (int q = 0; q < NG; ++q)
     *reinterpret_cast<uint4*>(blob + (size_t)(fg0 + q) * wg::FG_BYTES + (size_t)row * 16) =
         make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
 }
 
-// forward hidden epilogue with mask capture and spill.  RES: residual add of z.  Result -> ACT, z (if KEEP), blob.
-template <bool RES, bool KEEP>
+// forward hidden epilogue with mask capture and spill.  RES: residual add of z.  Result -> ACT (if TO_ACT), z (if KEEP),
+// blob.  The last hidden layer must NOT touch ACT: its columns are about to receive the output-layer gradient from
+// the other column-half's warp, and nothing orders the two stores.
+template <bool RES, bool KEEP, bool TO_ACT = true>
 __device__ __forceinline__ void bwd_fwd_epi(const SlotCtx& c, uint32_t (&z)[32], uint32_t (&mask)[2], uint8_t* blob) {
 #pragma unroll
   for (int ch = 0; ch < 2; ++ch) {
@@ -65,8 +69,8 @@ __device__ __forceinline__ void bwd_fwd_epi(const SlotCtx& c, uint32_t (&z)[32],
       if (KEEP) z[ch * 16 + j] = o[j];
     }
     mask[ch] = m;
-    tmem_st16(c.tmem + c.lane_sel + C_ACT + (uint32_t)(c.hf * 32 + ch * 16), o);
-    spill16(blob, c.hf * 8 + ch * 4, c.row, o);
+    if (TO_ACT) tmem_st16(c.tmem + c.lane_sel + C_ACT + (uint32_t)(c.hf * 32 + ch * 16), o);
+    spill_groups<4>(blob, c.hf * 8 + ch * 4, c.row, o);
   }
 }
 
@@ -91,13 +95,13 @@ __device__ __forceinline__ void bwd_bwd_epi(const SlotCtx& c, uint32_t (&gs)[32]
       if (SKIP_OUT) gs[ch * 16 + j] = o[j];
     }
     tmem_st16(c.tmem + c.lane_sel + C_ACT + (uint32_t)(c.hf * 32 + ch * 16), o);
-    spill16(blob, c.hf * 8 + ch * 4, c.row, o);
+    spill_groups<4>(blob, c.hf * 8 + ch * 4, c.row, o);
   }
 }
 
 __global__ void __launch_bounds__(THREADS, 1) stage_bwd_tc_kernel(const __grid_constant__ StageBwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bars[NSLOT];
+  __shared__ uint64_t bars[NSLOT + 1];
   __shared__ uint32_t tmem_base_s;
   SlotCtx c = stage_setup(smem, a.wimg, bars, &tmem_base_s, a.status);
   const uint32_t tmem_base = tmem_base_s;
@@ -106,22 +110,19 @@ __global__ void __launch_bounds__(THREADS, 1) stage_bwd_tc_kernel(const __grid_c
 
 #pragma unroll 1
   for (int tile = blockIdx.x * NSLOT + c.slot; tile < a.ntiles; tile += gridDim.x * NSLOT) {
-    const int64_t g = (int64_t)tile * TM + c.row;
-    const bool valid = g < a.B;
-    const int64_t gi = valid ? g : a.B - 1;
-    const float* yrow = a.y0 + gi * D;
+    const bool valid = (int64_t)tile * TM + c.row < a.B;      // padding rows: zeros in, nothing stored
     const int blob = a.blob0 + tile;
 
     // ---- stage input -> ACT / HB / TB and the X blob (features: p 0..63, v 64..127, h 128..159, sin, cos, 1)
     uint8_t* xb = a.spill + S.x1(blob);
 #pragma unroll
     for (int ch = 0; ch < 2; ++ch) {
-      const int d0 = c.hf * 32 + ch * 16;
+      const int f0 = c.hf * 8 + ch * 4;
       float pin[16], vin[16];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float4 pv = *reinterpret_cast<const float4*>(yrow + d0 + 4 * j);
-        const float4 vv = *reinterpret_cast<const float4*>(yrow + P + d0 + 4 * j);
+        const float4 pv = *blk4(a.y0, tile, YF4, f0 + j, c.row);
+        const float4 vv = *blk4(a.y0, tile, YF4, AF4 + f0 + j, c.row);
         pin[4 * j] = pv.x + a.in.cpv * vv.x; pin[4 * j + 1] = pv.y + a.in.cpv * vv.y;
         pin[4 * j + 2] = pv.z + a.in.cpv * vv.z; pin[4 * j + 3] = pv.w + a.in.cpv * vv.w;
         vin[4 * j] = vv.x; vin[4 * j + 1] = vv.y; vin[4 * j + 2] = vv.z; vin[4 * j + 3] = vv.w;
@@ -129,11 +130,10 @@ __global__ void __launch_bounds__(THREADS, 1) stage_bwd_tc_kernel(const __grid_c
 #pragma unroll
       for (int s = 0; s < MAX_A; ++s) {
         if (s < a.n_a) {
-          const float* ar = a.a[s] + gi * P + d0;
           const float cp = a.in.cpa[s], cv = a.in.cva[s];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float4 x = *reinterpret_cast<const float4*>(ar + 4 * j);
+            const float4 x = *blk4(a.a[s], tile, AF4, f0 + j, c.row);
             pin[4 * j] += cp * x.x; pin[4 * j + 1] += cp * x.y; pin[4 * j + 2] += cp * x.z; pin[4 * j + 3] += cp * x.w;
             vin[4 * j] += cv * x.x; vin[4 * j + 1] += cv * x.y; vin[4 * j + 2] += cv * x.z; vin[4 * j + 3] += cv * x.w;
           }
@@ -142,40 +142,30 @@ __global__ void __launch_bounds__(THREADS, 1) stage_bwd_tc_kernel(const __grid_c
       uint32_t o[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = pack_bf16(pin[2 * j], pin[2 * j + 1]);
-      tmem_st8(c.tmem + c.lane_sel + C_ACT + (uint32_t)(d0 / 2), o);
-#pragma unroll
-      for (int q = 0; q < 2; ++q)
-        *reinterpret_cast<uint4*>(xb + (size_t)(d0 / 8 + q) * wg::FG_BYTES + (size_t)c.row * 16) =
-            make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+      tmem_st8(c.tmem + c.lane_sel + C_ACT + (uint32_t)(f0 * 2), o);
+      spill_groups<2>(xb, f0 / 2, c.row, o);
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = pack_bf16(vin[2 * j], vin[2 * j + 1]);
-      tmem_st8(c.tmem + c.lane_sel + C_ACT + (uint32_t)(P / 2 + d0 / 2), o);
-#pragma unroll
-      for (int q = 0; q < 2; ++q)
-        *reinterpret_cast<uint4*>(xb + (size_t)((P + d0) / 8 + q) * wg::FG_BYTES + (size_t)c.row * 16) =
-            make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+      tmem_st8(c.tmem + c.lane_sel + C_ACT + (uint32_t)(P / 2 + f0 * 2), o);
+      spill_groups<2>(xb, P / 8 + f0 / 2, c.row, o);
     }
     {
       uint32_t o[8];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float4 x = *reinterpret_cast<const float4*>(yrow + 2 * P + c.hf * 16 + 4 * j);
+        const float4 x = *blk4(a.y0, tile, YF4, 2 * AF4 + c.hf * 4 + j, c.row);
         o[2 * j] = pack_bf16(x.x, x.y);
         o[2 * j + 1] = pack_bf16(x.z, x.w);
       }
       tmem_st8(c.tmem + c.lane_sel + C_HB + (uint32_t)(c.hf * 8), o);
-#pragma unroll
-      for (int q = 0; q < 2; ++q)
-        *reinterpret_cast<uint4*>(xb + (size_t)((2 * P + c.hf * 16) / 8 + q) * wg::FG_BYTES + (size_t)c.row * 16) =
-            make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+      spill_groups<2>(xb, 2 * P / 8 + c.hf * 2, c.row, o);
     }
     write_time_block(c, a.t, a.period);
     if (c.hf == 0) {   // time-feature / bias feature groups of the X blob: [sin, cos, 1, 0...], [0...]
       float s, co;
       time_features(a.t, a.period, s, co);
-      *reinterpret_cast<uint4*>(xb + (size_t)((2 * P + H) / 8) * wg::FG_BYTES + (size_t)c.row * 16) =
-          make_uint4(pack_bf16(s, co), pack_bf16(1.0f, 0.0f), 0u, 0u);
-      *reinterpret_cast<uint4*>(xb + (size_t)((2 * P + H) / 8 + 1) * wg::FG_BYTES + (size_t)c.row * 16) = make_uint4(0u, 0u, 0u, 0u);
+      const uint32_t o[8] = {pack_bf16(s, co), pack_bf16(1.0f, 0.0f), 0u, 0u, 0u, 0u, 0u, 0u};
+      spill_groups<2>(xb, (2 * P + H) / 8, c.row, o);
     }
 
     // ---- forward recompute (hidden layers only), masks + blobs
@@ -190,22 +180,21 @@ __global__ void __launch_bounds__(THREADS, 1) stage_bwd_tc_kernel(const __grid_c
     run_layer<false>(c, C_ACT, HID / 16, true, off_hh(2), HID, HID);
     bwd_fwd_epi<false, false>(c, z, m_u1, a.spill + S.act(3, blob));
     run_layer<false>(c, C_ACT, HID / 16, true, off_hh(3), HID, HID);
-    bwd_fwd_epi<true, false>(c, z, m_z2, a.spill + S.act(4, blob));
+    bwd_fwd_epi<true, false, false>(c, z, m_z2, a.spill + S.act(4, blob));
 
     // ---- upstream gradient of the output layer -> ACT (K = 64) + gO blob + bias column sums
     {
-      const float* gr = a.g_a + gi * P + c.hf * 32;
       uint32_t o[16];
       float gv[32];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float4 x = valid ? *reinterpret_cast<const float4*>(gr + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 x = *blk4(a.g_a, tile, AF4, c.hf * 8 + j, c.row);     // padding rows are zero
         gv[4 * j] = x.x; gv[4 * j + 1] = x.y; gv[4 * j + 2] = x.z; gv[4 * j + 3] = x.w;
         o[2 * j] = pack_bf16(x.x, x.y);
         o[2 * j + 1] = pack_bf16(x.z, x.w);
       }
       tmem_st16(c.tmem + c.lane_sel + C_ACT + (uint32_t)(c.hf * 16), o);
-      spill16(a.spill + S.go(blob), c.hf * 4, c.row, o);
+      spill_groups<4>(a.spill + S.go(blob), c.hf * 4, c.row, o);
       // column sums over the warp's 32 agents: transpose-reduce, lane j ends up with column j
 #pragma unroll
       for (int w = 16; w >= 1; w >>= 1) {
@@ -241,63 +230,59 @@ __global__ void __launch_bounds__(THREADS, 1) stage_bwd_tc_kernel(const __grid_c
 
     // ---- scatter into the step's gradient accumulators (tcgen05.ld is warp-collective: issued by every lane, the
     //      global read-modify-writes only by lanes that own a real agent)
-    {
-      float* Gy = a.G_y0 + gi * D;
 #pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {     // 16 dims per pass
-        const int d0 = c.hf * 32 + ch * 16;
-        uint32_t rp[16], rv[16];
-        tmem_ld16(c.tmem + c.lane_sel + C_ACC + (uint32_t)d0, rp);
-        tmem_ld16(c.tmem + c.lane_sel + C_ACC + (uint32_t)(P + d0), rv);
-        tmem_ld_wait();
-        if (valid) {
+    for (int ch = 0; ch < 2; ++ch) {     // 16 dims per pass
+      const int f0 = c.hf * 8 + ch * 4;
+      uint32_t rp[16], rv[16];
+      tmem_ld16(c.tmem + c.lane_sel + C_ACC + (uint32_t)(f0 * 4), rp);
+      tmem_ld16(c.tmem + c.lane_sel + C_ACC + (uint32_t)(P + f0 * 4), rv);
+      tmem_ld_wait();
+      if (valid) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float4* pp = reinterpret_cast<float4*>(Gy + d0 + 4 * j);
-            float4* pv = reinterpret_cast<float4*>(Gy + P + d0 + 4 * j);
-            float4 x = *pp, y = *pv;
-            const float gp0 = __uint_as_float(rp[4 * j]), gp1 = __uint_as_float(rp[4 * j + 1]), gp2 = __uint_as_float(rp[4 * j + 2]),
-                        gp3 = __uint_as_float(rp[4 * j + 3]);
-            x.x += gp0; x.y += gp1; x.z += gp2; x.w += gp3;
-            y.x += a.in.cpv * gp0 + __uint_as_float(rv[4 * j]);
-            y.y += a.in.cpv * gp1 + __uint_as_float(rv[4 * j + 1]);
-            y.z += a.in.cpv * gp2 + __uint_as_float(rv[4 * j + 2]);
-            y.w += a.in.cpv * gp3 + __uint_as_float(rv[4 * j + 3]);
-            *pp = x;
-            *pv = y;
-          }
+        for (int j = 0; j < 4; ++j) {
+          float4* pp = blk4(a.G_y0, tile, YF4, f0 + j, c.row);
+          float4* pv = blk4(a.G_y0, tile, YF4, AF4 + f0 + j, c.row);
+          float4 x = *pp, y = *pv;
+          const float gp0 = __uint_as_float(rp[4 * j]), gp1 = __uint_as_float(rp[4 * j + 1]), gp2 = __uint_as_float(rp[4 * j + 2]),
+                      gp3 = __uint_as_float(rp[4 * j + 3]);
+          x.x += gp0; x.y += gp1; x.z += gp2; x.w += gp3;
+          y.x += a.in.cpv * gp0 + __uint_as_float(rv[4 * j]);
+          y.y += a.in.cpv * gp1 + __uint_as_float(rv[4 * j + 1]);
+          y.z += a.in.cpv * gp2 + __uint_as_float(rv[4 * j + 2]);
+          y.w += a.in.cpv * gp3 + __uint_as_float(rv[4 * j + 3]);
+          *pp = x;
+          *pv = y;
+        }
 #pragma unroll
-          for (int s = 0; s < MAX_A; ++s) {
-            if (s < a.n_a) {
-              float* Ga = a.G_a[s] + g * P + d0;
-              const float cp = a.in.cpa[s], cv = a.in.cva[s];
+        for (int s = 0; s < MAX_A; ++s) {
+          if (s < a.n_a) {
+            const float cp = a.in.cpa[s], cv = a.in.cva[s];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float4* q = reinterpret_cast<float4*>(Ga + 4 * j);
-                float4 x = *q;
-                x.x += cp * __uint_as_float(rp[4 * j]) + cv * __uint_as_float(rv[4 * j]);
-                x.y += cp * __uint_as_float(rp[4 * j + 1]) + cv * __uint_as_float(rv[4 * j + 1]);
-                x.z += cp * __uint_as_float(rp[4 * j + 2]) + cv * __uint_as_float(rv[4 * j + 2]);
-                x.w += cp * __uint_as_float(rp[4 * j + 3]) + cv * __uint_as_float(rv[4 * j + 3]);
-                *q = x;
-              }
+            for (int j = 0; j < 4; ++j) {
+              float4* q = blk4(a.G_a[s], tile, AF4, f0 + j, c.row);
+              float4 x = *q;
+              x.x += cp * __uint_as_float(rp[4 * j]) + cv * __uint_as_float(rv[4 * j]);
+              x.y += cp * __uint_as_float(rp[4 * j + 1]) + cv * __uint_as_float(rv[4 * j + 1]);
+              x.z += cp * __uint_as_float(rp[4 * j + 2]) + cv * __uint_as_float(rv[4 * j + 2]);
+              x.w += cp * __uint_as_float(rp[4 * j + 3]) + cv * __uint_as_float(rv[4 * j + 3]);
+              *q = x;
             }
           }
         }
       }
-      {
-        uint32_t rh[16];
-        tmem_ld16(c.tmem + c.lane_sel + C_ACC + (uint32_t)(2 * P + c.hf * 16), rh);
-        tmem_ld_wait();
-        if (valid) {
+    }
+    {
+      uint32_t rh[16];
+      tmem_ld16(c.tmem + c.lane_sel + C_ACC + (uint32_t)(2 * P + c.hf * 16), rh);
+      tmem_ld_wait();
+      if (valid) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float4* q = reinterpret_cast<float4*>(Gy + 2 * P + c.hf * 16 + 4 * j);
-            float4 x = *q;
-            x.x += __uint_as_float(rh[4 * j]); x.y += __uint_as_float(rh[4 * j + 1]);
-            x.z += __uint_as_float(rh[4 * j + 2]); x.w += __uint_as_float(rh[4 * j + 3]);
-            *q = x;
-          }
+        for (int j = 0; j < 4; ++j) {
+          float4* q = blk4(a.G_y0, tile, YF4, 2 * AF4 + c.hf * 4 + j, c.row);
+          float4 x = *q;
+          x.x += __uint_as_float(rh[4 * j]); x.y += __uint_as_float(rh[4 * j + 1]);
+          x.z += __uint_as_float(rh[4 * j + 2]); x.w += __uint_as_float(rh[4 * j + 3]);
+          *q = x;
         }
       }
     }

@@ -1,6 +1,7 @@
-// Elementwise companions of the stage kernels: linear combinations of the step's base state y0 = [p0, v0, h] and
-// stage accelerations a_j (dense-output rows, step solutions) and their adjoints.  One pass over the state each,
-// 128-bit accesses, HBM-bound.
+// Elementwise companions of the stage kernels, all on the tile-blocked fp32 layout of stage_tc.cuh: linear
+// combinations of the step's base state y0 = [p0, v0, h] and stage accelerations a_j (dense-output rows, step
+// solutions), their adjoints, and the converters between blocked buffers and public row-major tensors.
+// One pass over the state each, 128-bit accesses, HBM-bound.
 //   forward :  out.p = p0 + cpv v0 + sum cpa[j] a_j ;  out.v = v0 + sum cva[j] a_j ;  out.h = h
 //   adjoint :  G_y0.p (+)= g.p ; G_y0.v (+)= cpv g.p + g.v ; G_y0.h (+)= g.h ; G_a[j] (+)= cpa[j] g.p + cva[j] g.v
 // (tdq: rk_common.py `_runge_kutta_step` y1 = y0 + dt sum c_sol k; interp.py `_interp_evaluate`.)
@@ -9,67 +10,78 @@
 namespace ab200 {
 
 constexpr int EL_MAX_A = 8;
+constexpr int EL_TM = 128;
 struct ElemArgs {
   const float* y0;
   const float* a[EL_MAX_A];
   float* G_a[EL_MAX_A];
-  float* out;        // forward: out [B][D];  adjoint: G_y0 [B][D]
-  const float* g;    // adjoint: upstream gradient [B][D]
+  float* out;        // forward: out (blocked [Bp][D]);  adjoint: G_y0 (blocked [Bp][D])
+  const float* g;    // adjoint: upstream gradient (blocked [Bp][D])
   float cpv, cpa[EL_MAX_A], cva[EL_MAX_A];
   int n_a, accumulate;
-  int64_t B;
+  int ntiles;
   int P, H;
 };
 
+// work item i -> (tile, group, row): group < P/4 handles the float4 of p AND v with that index, group >= P/4 the h part
+__device__ __forceinline__ void decode(int64_t i, int P4, int H4, int& tile, int& grp, int& row) {
+  row = (int)(i % EL_TM);
+  const int64_t q = i / EL_TM;
+  grp = (int)(q % (P4 + H4));
+  tile = (int)(q / (P4 + H4));
+}
+
 __global__ void __launch_bounds__(256) pv_combine_kernel(const __grid_constant__ ElemArgs a) {
-  const int P4 = a.P / 4, H4 = a.H / 4, D = 2 * a.P + a.H;
-  const int64_t n = a.B * (P4 + H4);
+  const int P4 = a.P / 4, H4 = a.H / 4, Y4 = 2 * P4 + H4;
+  const int64_t n = (int64_t)a.ntiles * (P4 + H4) * EL_TM;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t b = i / (P4 + H4);
-    const int c = (int)(i % (P4 + H4));
-    const float* yr = a.y0 + b * D;
-    float* o = a.out + b * D;
-    if (c >= P4) {
-      reinterpret_cast<float4*>(o + 2 * a.P)[c - P4] = reinterpret_cast<const float4*>(yr + 2 * a.P)[c - P4];
+    int tile, grp, row;
+    decode(i, P4, H4, tile, grp, row);
+    const float4* y4 = reinterpret_cast<const float4*>(a.y0) + (size_t)tile * Y4 * EL_TM + row;
+    float4* o4 = reinterpret_cast<float4*>(a.out) + (size_t)tile * Y4 * EL_TM + row;
+    if (grp >= P4) {
+      const int f = 2 * P4 + (grp - P4);
+      o4[(size_t)f * EL_TM] = y4[(size_t)f * EL_TM];
       continue;
     }
-    const float4 p0 = reinterpret_cast<const float4*>(yr)[c], v0 = reinterpret_cast<const float4*>(yr + a.P)[c];
+    const float4 p0 = y4[(size_t)grp * EL_TM], v0 = y4[(size_t)(P4 + grp) * EL_TM];
     float4 p = make_float4(p0.x + a.cpv * v0.x, p0.y + a.cpv * v0.y, p0.z + a.cpv * v0.z, p0.w + a.cpv * v0.w), v = v0;
 #pragma unroll
     for (int s = 0; s < EL_MAX_A; ++s) {
       if (s < a.n_a) {
-        const float4 x = reinterpret_cast<const float4*>(a.a[s] + b * a.P)[c];
+        const float4 x = reinterpret_cast<const float4*>(a.a[s])[((size_t)tile * P4 + grp) * EL_TM + row];
         const float cp = a.cpa[s], cv = a.cva[s];
         p.x += cp * x.x; p.y += cp * x.y; p.z += cp * x.z; p.w += cp * x.w;
         v.x += cv * x.x; v.y += cv * x.y; v.z += cv * x.z; v.w += cv * x.w;
       }
     }
-    reinterpret_cast<float4*>(o)[c] = p;
-    reinterpret_cast<float4*>(o + a.P)[c] = v;
+    o4[(size_t)grp * EL_TM] = p;
+    o4[(size_t)(P4 + grp) * EL_TM] = v;
   }
 }
 
 __global__ void __launch_bounds__(256) pv_combine_bwd_kernel(const __grid_constant__ ElemArgs a) {
-  const int P4 = a.P / 4, H4 = a.H / 4, D = 2 * a.P + a.H;
-  const int64_t n = a.B * (P4 + H4);
+  const int P4 = a.P / 4, H4 = a.H / 4, Y4 = 2 * P4 + H4;
+  const int64_t n = (int64_t)a.ntiles * (P4 + H4) * EL_TM;
   const bool acc = a.accumulate != 0;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t b = i / (P4 + H4);
-    const int c = (int)(i % (P4 + H4));
-    const float* gr = a.g + b * D;
-    float* o = a.out + b * D;
-    if (c >= P4) {
-      float4 x = reinterpret_cast<const float4*>(gr + 2 * a.P)[c - P4];
-      float4* q = reinterpret_cast<float4*>(o + 2 * a.P) + (c - P4);
+    int tile, grp, row;
+    decode(i, P4, H4, tile, grp, row);
+    const float4* g4 = reinterpret_cast<const float4*>(a.g) + (size_t)tile * Y4 * EL_TM + row;
+    float4* o4 = reinterpret_cast<float4*>(a.out) + (size_t)tile * Y4 * EL_TM + row;
+    if (grp >= P4) {
+      const int f = 2 * P4 + (grp - P4);
+      float4 x = g4[(size_t)f * EL_TM];
+      float4* q = o4 + (size_t)f * EL_TM;
       if (acc) { const float4 y = *q; x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w; }
       *q = x;
       continue;
     }
-    const float4 gp = reinterpret_cast<const float4*>(gr)[c], gv = reinterpret_cast<const float4*>(gr + a.P)[c];
+    const float4 gp = g4[(size_t)grp * EL_TM], gv = g4[(size_t)(P4 + grp) * EL_TM];
     float4 xp = gp;
     float4 xv = make_float4(a.cpv * gp.x + gv.x, a.cpv * gp.y + gv.y, a.cpv * gp.z + gv.z, a.cpv * gp.w + gv.w);
-    float4* qp = reinterpret_cast<float4*>(o) + c;
-    float4* qv = reinterpret_cast<float4*>(o + a.P) + c;
+    float4* qp = o4 + (size_t)grp * EL_TM;
+    float4* qv = o4 + (size_t)(P4 + grp) * EL_TM;
     if (acc) {
       const float4 y = *qp, z = *qv;
       xp.x += y.x; xp.y += y.y; xp.z += y.z; xp.w += y.w;
@@ -82,7 +94,7 @@ __global__ void __launch_bounds__(256) pv_combine_bwd_kernel(const __grid_consta
       if (s < a.n_a) {
         const float cp = a.cpa[s], cv = a.cva[s];
         float4 x = make_float4(cp * gp.x + cv * gv.x, cp * gp.y + cv * gv.y, cp * gp.z + cv * gv.z, cp * gp.w + cv * gv.w);
-        float4* q = reinterpret_cast<float4*>(a.G_a[s] + b * a.P) + c;
+        float4* q = reinterpret_cast<float4*>(a.G_a[s]) + ((size_t)tile * P4 + grp) * EL_TM + row;
         if (acc) { const float4 y = *q; x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w; }
         *q = x;
       }
@@ -90,8 +102,53 @@ __global__ void __launch_bounds__(256) pv_combine_bwd_kernel(const __grid_consta
   }
 }
 
-static int launch_cfg(int64_t B, int P, int H) {
-  const int64_t n = B * ((P + H) / 4);
+// ---- row-major <-> blocked ---------------------------------------------------------------------------------
+// One CTA moves 32 rows x F floats through shared memory so that both the row-major side (rows contiguous) and the
+// blocked side (32 consecutive agents of one float4 group contiguous) are accessed in full 128-byte lines.
+//   mode 0: blocked  = row-major (padding rows zeroed)   mode 1: blocked += row-major   mode 2: row-major = blocked
+constexpr int TR_ROWS = 32;
+__global__ void __launch_bounds__(256) rows_transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t B,
+                                                             int64_t Bp, int F4, int mode) {
+  extern __shared__ float4 tile_s[];     // [TR_ROWS][F4 + 1]
+  const int ld = F4 + 1;
+  const int64_t row0 = (int64_t)blockIdx.x * TR_ROWS;
+  const int n = TR_ROWS * F4;
+  if (mode != 2) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int r = i / F4, c = i % F4;
+      const int64_t g = row0 + r;
+      tile_s[r * ld + c] = (g < B) ? reinterpret_cast<const float4*>(src)[g * F4 + c] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int c = i / TR_ROWS, r = i % TR_ROWS;
+      const int64_t g = row0 + r;
+      if (g >= Bp) continue;
+      float4* q = reinterpret_cast<float4*>(dst) + ((g / EL_TM) * F4 + c) * EL_TM + (g % EL_TM);
+      float4 x = tile_s[r * ld + c];
+      if (mode == 1) {
+        if (g >= B) continue;
+        const float4 y = *q;
+        x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;
+      }
+      *q = x;
+    }
+  } else {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int c = i / TR_ROWS, r = i % TR_ROWS;
+      const int64_t g = row0 + r;
+      if (g < Bp) tile_s[r * ld + c] = reinterpret_cast<const float4*>(src)[((g / EL_TM) * F4 + c) * EL_TM + (g % EL_TM)];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int r = i / F4, c = i % F4;
+      const int64_t g = row0 + r;
+      if (g < B) reinterpret_cast<float4*>(dst)[g * F4 + c] = tile_s[r * ld + c];
+    }
+  }
+}
+
+static int launch_cfg(int64_t n) {
   int64_t blocks = (n + 255) / 256;
   const int64_t cap = 148 * 16;
   return (int)(blocks < cap ? blocks : cap);
@@ -101,9 +158,10 @@ int pv_combine(const ab200_drift_desc* d, const float* y0, const float* const* a
                const float* cva, int64_t B, float* out, cudaStream_t st) {
   if (n_a < 0 || n_a > EL_MAX_A || d->pos_dim % 4 || d->ctx_dim % 4) return AB200_ERR_BAD_ARG;
   ElemArgs k{};
-  k.y0 = y0; k.out = out; k.cpv = cpv; k.n_a = n_a; k.B = B; k.P = d->pos_dim; k.H = d->ctx_dim;
+  k.y0 = y0; k.out = out; k.cpv = cpv; k.n_a = n_a; k.P = d->pos_dim; k.H = d->ctx_dim;
+  k.ntiles = (int)((B + EL_TM - 1) / EL_TM);
   for (int i = 0; i < n_a; ++i) { k.a[i] = a_ptrs[i]; k.cpa[i] = cpa[i]; k.cva[i] = cva[i]; }
-  pv_combine_kernel<<<launch_cfg(B, k.P, k.H), 256, 0, st>>>(k);
+  pv_combine_kernel<<<launch_cfg((int64_t)k.ntiles * EL_TM * ((k.P + k.H) / 4)), 256, 0, st>>>(k);
   return check_launch();
 }
 
@@ -111,9 +169,25 @@ int pv_combine_bwd(const ab200_drift_desc* d, const float* g, int n_a, float cpv
                    float* G_y0, float* const* G_a, int accumulate, cudaStream_t st) {
   if (n_a < 0 || n_a > EL_MAX_A || d->pos_dim % 4 || d->ctx_dim % 4) return AB200_ERR_BAD_ARG;
   ElemArgs k{};
-  k.g = g; k.out = G_y0; k.cpv = cpv; k.n_a = n_a; k.B = B; k.P = d->pos_dim; k.H = d->ctx_dim; k.accumulate = accumulate;
+  k.g = g; k.out = G_y0; k.cpv = cpv; k.n_a = n_a; k.P = d->pos_dim; k.H = d->ctx_dim; k.accumulate = accumulate;
+  k.ntiles = (int)((B + EL_TM - 1) / EL_TM);
   for (int i = 0; i < n_a; ++i) { k.G_a[i] = G_a[i]; k.cpa[i] = cpa[i]; k.cva[i] = cva[i]; }
-  pv_combine_bwd_kernel<<<launch_cfg(B, k.P, k.H), 256, 0, st>>>(k);
+  pv_combine_bwd_kernel<<<launch_cfg((int64_t)k.ntiles * EL_TM * ((k.P + k.H) / 4)), 256, 0, st>>>(k);
+  return check_launch();
+}
+
+int rows_transpose(const float* src, float* dst, int64_t B, int F, int mode, cudaStream_t st) {
+  if (F % 4 || F <= 0 || F > 1024 || mode < 0 || mode > 2) return AB200_ERR_BAD_ARG;
+  const int64_t Bp = (B + EL_TM - 1) / EL_TM * EL_TM;
+  const int F4 = F / 4;
+  const int64_t rows = (mode == 0) ? Bp : B;
+  const int grid = (int)((rows + TR_ROWS - 1) / TR_ROWS);
+  const size_t smem = (size_t)TR_ROWS * (F4 + 1) * sizeof(float4);
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(rows_transpose_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_cuda_error(e); return AB200_ERR_CUDA; }
+  }
+  rows_transpose_kernel<<<grid, 256, smem, st>>>(src, dst, B, Bp, F4, mode);
   return check_launch();
 }
 

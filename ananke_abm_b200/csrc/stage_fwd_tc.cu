@@ -68,13 +68,13 @@ int stage_tc_pack(const float* w_flat, uint8_t* image, cudaStream_t st) {
 
 struct StageFwdArgs {
   const uint8_t* wimg;
-  const float* y0;            // [B][160]
-  const float* a[MAX_A];      // [B][64] each
+  const float* y0;            // blocked [Bp][160]
+  const float* a[MAX_A];      // blocked [Bp][64] each
   int n_a;
   Combo in;                   // stage input
   float t, period;
-  float* a_out;               // [B][64] or null
-  float* y_out;               // [B][160] or null
+  float* a_out;               // blocked [Bp][64] or null
+  float* y_out;               // blocked [Bp][160] or null
   Combo out;                  // y_out combination; index n_a of cpa/cva multiplies this stage's own output
   double* err_sumsq;          // or null
   Combo err;                  // error combination (cpv unused); index n_a multiplies this stage's own output
@@ -86,7 +86,7 @@ struct StageFwdArgs {
 
 __global__ void __launch_bounds__(THREADS, 1) stage_fwd_tc_kernel(const __grid_constant__ StageFwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bars[NSLOT];
+  __shared__ uint64_t bars[NSLOT + 1];
   __shared__ uint32_t tmem_base_s;
   __shared__ double err_red[THREADS / 32];
   SlotCtx c = stage_setup(smem, a.wimg, bars, &tmem_base_s, a.status);
@@ -95,20 +95,17 @@ __global__ void __launch_bounds__(THREADS, 1) stage_fwd_tc_kernel(const __grid_c
 
 #pragma unroll 1
   for (int tile = blockIdx.x * NSLOT + c.slot; tile < a.ntiles; tile += gridDim.x * NSLOT) {
-    const int64_t g = (int64_t)tile * TM + c.row;
-    const bool valid = g < a.B;
-    const int64_t gi = valid ? g : a.B - 1;
-    const float* yrow = a.y0 + gi * D;
+    const bool valid = (int64_t)tile * TM + c.row < a.B;      // padding rows hold zeros and are never stored to
 
-    // ---- stage input -> ACT (bf16), context h -> HB, time/bias block -> TB
+    // ---- stage input -> ACT (bf16), context h -> HB, time/bias block -> TB          (all buffers blocked, see stage_tc.cuh)
 #pragma unroll
     for (int ch = 0; ch < 2; ++ch) {       // 16 dims of p and of v per pass
-      const int d0 = c.hf * 32 + ch * 16;
+      const int f0 = c.hf * 8 + ch * 4;    // first float4 group of this pass
       float pin[16], vin[16];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float4 pv = *reinterpret_cast<const float4*>(yrow + d0 + 4 * j);
-        const float4 vv = *reinterpret_cast<const float4*>(yrow + P + d0 + 4 * j);
+        const float4 pv = *blk4(a.y0, tile, YF4, f0 + j, c.row);
+        const float4 vv = *blk4(a.y0, tile, YF4, AF4 + f0 + j, c.row);
         pin[4 * j] = pv.x + a.in.cpv * vv.x; pin[4 * j + 1] = pv.y + a.in.cpv * vv.y;
         pin[4 * j + 2] = pv.z + a.in.cpv * vv.z; pin[4 * j + 3] = pv.w + a.in.cpv * vv.w;
         vin[4 * j] = vv.x; vin[4 * j + 1] = vv.y; vin[4 * j + 2] = vv.z; vin[4 * j + 3] = vv.w;
@@ -116,11 +113,10 @@ __global__ void __launch_bounds__(THREADS, 1) stage_fwd_tc_kernel(const __grid_c
 #pragma unroll
       for (int s = 0; s < MAX_A; ++s) {
         if (s < a.n_a) {
-          const float* ar = a.a[s] + gi * P + d0;
           const float cp = a.in.cpa[s], cv = a.in.cva[s];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float4 x = *reinterpret_cast<const float4*>(ar + 4 * j);
+            const float4 x = *blk4(a.a[s], tile, AF4, f0 + j, c.row);
             pin[4 * j] += cp * x.x; pin[4 * j + 1] += cp * x.y; pin[4 * j + 2] += cp * x.z; pin[4 * j + 3] += cp * x.w;
             vin[4 * j] += cv * x.x; vin[4 * j + 1] += cv * x.y; vin[4 * j + 2] += cv * x.z; vin[4 * j + 3] += cv * x.w;
           }
@@ -129,16 +125,16 @@ __global__ void __launch_bounds__(THREADS, 1) stage_fwd_tc_kernel(const __grid_c
       uint32_t o[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = pack_bf16(pin[2 * j], pin[2 * j + 1]);
-      tmem_st8(c.tmem + c.lane_sel + C_ACT + (uint32_t)(d0 / 2), o);
+      tmem_st8(c.tmem + c.lane_sel + C_ACT + (uint32_t)(f0 * 2), o);
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = pack_bf16(vin[2 * j], vin[2 * j + 1]);
-      tmem_st8(c.tmem + c.lane_sel + C_ACT + (uint32_t)(P / 2 + d0 / 2), o);
+      tmem_st8(c.tmem + c.lane_sel + C_ACT + (uint32_t)(P / 2 + f0 * 2), o);
     }
     {
       uint32_t o[8];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float4 x = *reinterpret_cast<const float4*>(yrow + 2 * P + c.hf * 16 + 4 * j);
+        const float4 x = *blk4(a.y0, tile, YF4, 2 * AF4 + c.hf * 4 + j, c.row);
         o[2 * j] = pack_bf16(x.x, x.y);
         o[2 * j + 1] = pack_bf16(x.z, x.w);
       }
@@ -160,81 +156,69 @@ __global__ void __launch_bounds__(THREADS, 1) stage_fwd_tc_kernel(const __grid_c
     }
     run_layer<false>(c, C_ACT, HID / 16, true, OFF_WO, P, P);
 
-    // ---- output epilogue: this thread's 32 acceleration dims (hf*32 ..)
+    // ---- output epilogue: this thread's 32 acceleration dims (float4 groups hf*8 ..)
     {
       uint32_t r[32];
       tmem_ld32(c.tmem + c.lane_sel + C_ACC + (uint32_t)(c.hf * 32), r);
       tmem_ld_wait();
-      const int d0 = c.hf * 32;
+      const int f0 = c.hf * 8;
       if (a.a_out != nullptr && valid) {
-        float4* dst = reinterpret_cast<float4*>(a.a_out + g * P + d0);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          dst[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                               __uint_as_float(r[4 * j + 3]));
+          *blk4(a.a_out, tile, AF4, f0 + j, c.row) = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                                  __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
       }
       if (a.y_out != nullptr) {
         const bool want_err = a.err_sumsq != nullptr;
+        const float oc = a.out.cpa[a.n_a], ov = a.out.cva[a.n_a], ecp = a.err.cpa[a.n_a], ecv = a.err.cva[a.n_a];
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {     // 8 dims per pass
-          const int dd = d0 + ch * 8;
-          float po[8], vo[8], ep[8], ev[8], p0r[8], v0r[8];
+        for (int j = 0; j < 8; ++j) {       // one float4 group of p and of v per pass
+          const float4 p0 = *blk4(a.y0, tile, YF4, f0 + j, c.row);
+          const float4 v0 = *blk4(a.y0, tile, YF4, AF4 + f0 + j, c.row);
+          const float ao[4] = {__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                               __uint_as_float(r[4 * j + 3])};
+          const float p0r[4] = {p0.x, p0.y, p0.z, p0.w}, v0r[4] = {v0.x, v0.y, v0.z, v0.w};
+          float po[4], vo[4], ep[4], ev[4];
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const float4 pv = *reinterpret_cast<const float4*>(yrow + dd + 4 * j);
-            const float4 vv = *reinterpret_cast<const float4*>(yrow + P + dd + 4 * j);
-            p0r[4 * j] = pv.x; p0r[4 * j + 1] = pv.y; p0r[4 * j + 2] = pv.z; p0r[4 * j + 3] = pv.w;
-            v0r[4 * j] = vv.x; v0r[4 * j + 1] = vv.y; v0r[4 * j + 2] = vv.z; v0r[4 * j + 3] = vv.w;
-          }
-          const float oc = a.out.cpa[a.n_a], ov = a.out.cva[a.n_a], ecp = a.err.cpa[a.n_a], ecv = a.err.cva[a.n_a];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float ao = __uint_as_float(r[ch * 8 + j]);
-            po[j] = p0r[j] + a.out.cpv * v0r[j] + oc * ao;
-            vo[j] = v0r[j] + ov * ao;
-            ep[j] = ecp * ao;
-            ev[j] = ecv * ao;
+          for (int e = 0; e < 4; ++e) {
+            po[e] = p0r[e] + a.out.cpv * v0r[e] + oc * ao[e];
+            vo[e] = v0r[e] + ov * ao[e];
+            ep[e] = ecp * ao[e];
+            ev[e] = ecv * ao[e];
           }
 #pragma unroll
           for (int s = 0; s < MAX_A; ++s) {
             if (s < a.n_a) {
-              const float* ar = a.a[s] + gi * P + dd;
+              const float4 x = *blk4(a.a[s], tile, AF4, f0 + j, c.row);
+              const float xs[4] = {x.x, x.y, x.z, x.w};
               const float cp = a.out.cpa[s], cv = a.out.cva[s], xp = a.err.cpa[s], xv = a.err.cva[s];
 #pragma unroll
-              for (int j = 0; j < 2; ++j) {
-                const float4 x = *reinterpret_cast<const float4*>(ar + 4 * j);
-                const float xs[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  po[4 * j + e] += cp * xs[e];
-                  vo[4 * j + e] += cv * xs[e];
-                  ep[4 * j + e] += xp * xs[e];
-                  ev[4 * j + e] += xv * xs[e];
-                }
+              for (int e = 0; e < 4; ++e) {
+                po[e] += cp * xs[e];
+                vo[e] += cv * xs[e];
+                ep[e] += xp * xs[e];
+                ev[e] += xv * xs[e];
               }
             }
           }
           if (valid) {
-            float4* dp = reinterpret_cast<float4*>(a.y_out + g * D + dd);
-            float4* dv = reinterpret_cast<float4*>(a.y_out + g * D + P + dd);
-            dp[0] = make_float4(po[0], po[1], po[2], po[3]); dp[1] = make_float4(po[4], po[5], po[6], po[7]);
-            dv[0] = make_float4(vo[0], vo[1], vo[2], vo[3]); dv[1] = make_float4(vo[4], vo[5], vo[6], vo[7]);
+            *blk4(a.y_out, tile, YF4, f0 + j, c.row) = make_float4(po[0], po[1], po[2], po[3]);
+            *blk4(a.y_out, tile, YF4, AF4 + f0 + j, c.row) = make_float4(vo[0], vo[1], vo[2], vo[3]);
             if (want_err) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float tp = a.atol + a.rtol * fmaxf(fabsf(p0r[j]), fabsf(po[j]));
-                const float tv = a.atol + a.rtol * fmaxf(fabsf(v0r[j]), fabsf(vo[j]));
-                const float qp = ep[j] / tp, qv = ev[j] / tv;
+              for (int e = 0; e < 4; ++e) {
+                const float tp = a.atol + a.rtol * fmaxf(fabsf(p0r[e]), fabsf(po[e]));
+                const float tv = a.atol + a.rtol * fmaxf(fabsf(v0r[e]), fabsf(vo[e]));
+                const float qp = ep[e] / tp, qv = ev[e] / tv;
                 err_local += (double)(qp * qp + qv * qv);
               }
             }
           }
         }
         if (valid) {   // context h rides along unchanged (dh/dt = 0)
-          const float4* hs = reinterpret_cast<const float4*>(yrow + 2 * P + c.hf * 16);
-          float4* hd = reinterpret_cast<float4*>(a.y_out + g * D + 2 * P + c.hf * 16);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) hd[j] = hs[j];
+          for (int j = 0; j < 4; ++j)
+            *blk4(a.y_out, tile, YF4, 2 * AF4 + c.hf * 4 + j, c.row) = *blk4(a.y0, tile, YF4, 2 * AF4 + c.hf * 4 + j, c.row);
         }
       }
     }

@@ -165,25 +165,41 @@ struct Combo {
   float cva[MAX_A + 1];
 };
 
-// setup shared by the kernels: weights -> smem, TMEM, barriers.  Returns the per-thread slot context.
+// ---- "blocked" fp32 matrices --------------------------------------------------------------------------------
+// Every per-agent buffer the stage kernels touch ([B][160] states and their adjoints, [B][64] accelerations and their
+// adjoints) is stored tile-blocked: rows are padded to a multiple of 128; inside a 128-agent tile the float4 holding
+// features 4 f4 .. 4 f4 + 3 of agent r sits at float4 index  (tile * F/4 + f4) * 128 + r.  A thread that owns one
+// agent row (= one TMEM lane) therefore reads/writes 16 B that are adjacent to its neighbour lanes' 16 B: every
+// warp-wide access is one contiguous 512 B segment, where a row-major layout would touch 32 cache lines.
+// `ab200_rows_block` / `ab200_rows_unblock` convert from / to the public row-major tensors.
+__device__ __forceinline__ float4* blk4(float* base, int tile, int F4, int f4, int row) {
+  return reinterpret_cast<float4*>(base) + ((size_t)tile * F4 + f4) * TM + row;
+}
+__device__ __forceinline__ const float4* blk4(const float* base, int tile, int F4, int f4, int row) {
+  return reinterpret_cast<const float4*>(base) + ((size_t)tile * F4 + f4) * TM + row;
+}
+constexpr int YF4 = D / 4, AF4 = P / 4;       // float4 groups per row of a state / an acceleration buffer
+
+// setup shared by the kernels: weights -> smem (one bulk copy engine transfer), TMEM, barriers.
 __device__ __forceinline__ SlotCtx stage_setup(uint8_t* smem, const uint8_t* wimg, uint64_t* bars, uint32_t* tmem_base_s,
                                                int* status) {
   const int tid = threadIdx.x, warp = tid >> 5;
-  {
-    const int4* src = reinterpret_cast<const int4*>(wimg);
-    int4* dst = reinterpret_cast<int4*>(smem);
-    for (uint32_t i = tid; i < W_BYTES / 16; i += THREADS) dst[i] = src[i];
-  }
   if (warp == 0) tmem_alloc<512>(tmem_base_s);
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], 1);
     mbar_fence_init();
+    constexpr uint32_t CH = 52736;             // W_BYTES / 4, multiple of 16
+    static_assert(CH * 4 == W_BYTES, "image chunking");
+    mbar_arrive_expect_tx(&bars[2], W_BYTES);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) bulk_g2s(smem + i * CH, wimg + i * CH, CH, &bars[2]);
   }
-  fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (!mbar_wait(&bars[2], 0, STAGE_WAIT_CYCLES)) *status = 6;
   SlotCtx c;
   c.slot = tid / SLOT_THREADS;
   c.stid = tid % SLOT_THREADS;

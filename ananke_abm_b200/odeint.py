@@ -138,16 +138,16 @@ class _StageRK4TC(torch.autograd.Function):
         from . import stage
         eng = stage.TcEngine(spec, w_flat)
         th = [float(v) for v in t_host.tolist()]
-        y_path, acc = stage.rk4_forward(eng, y0.contiguous().float(), th, save_stages=True)
+        y_path, (yb, acc) = stage.rk4_forward(eng, y0.contiguous().float(), th, save_stages=True)
         ctx.eng, ctx.th = eng, th
-        ctx.save_for_backward(y_path, acc)
+        ctx.save_for_backward(yb, acc)
         return y_path
 
     @staticmethod
     def backward(ctx, grad_y_path):
         from . import stage
-        y_path, acc = ctx.saved_tensors
-        gy0, gw = stage.rk4_backward(ctx.eng, ctx.th, y_path, acc, grad_y_path.contiguous().float())
+        yb, acc = ctx.saved_tensors
+        gy0, gw = stage.rk4_backward(ctx.eng, ctx.th, (yb, acc), grad_y_path.contiguous().float())
         return gy0, None, gw, None, None
 
 

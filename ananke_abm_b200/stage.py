@@ -130,7 +130,7 @@ class TcEngine:
         self.D = 2 * self.P + self.H
 
     # ---- forward ------------------------------------------------------------------------------------
-    def stage_forward(self, y0, a: Sequence[torch.Tensor], cin: Combo, t: float, a_out=None, y_out=None, cout: Optional[Combo] = None,
+    def stage_forward(self, y0, a: Sequence[torch.Tensor], cin: Combo, t: float, B: int, a_out=None, y_out=None, cout: Optional[Combo] = None,
                       err_sumsq=None, cerr: Optional[Combo] = None, rtol: float = 0.0, atol: float = 0.0) -> None:
         s = StageDesc()
         s.n_a = len(a)
@@ -147,17 +147,17 @@ class TcEngine:
             _fill(s.err_va, cerr.cva[:len(a) + 1])
         s.rtol, s.atol = float(rtol), float(atol)
         rc = self.L.ab200_stage_forward(C.byref(self.desc), self.image.data_ptr(), y0.data_ptr(), C.cast(_ptr_array(a), C.c_void_p),
-                                        C.byref(s), y0.shape[0], None if a_out is None else a_out.data_ptr(),
+                                        C.byref(s), B, None if a_out is None else a_out.data_ptr(),
                                         None if y_out is None else y_out.data_ptr(),
                                         None if err_sumsq is None else err_sumsq.data_ptr(), _stream())
         _lib.check(rc, "ab200_stage_forward")
 
-    def combine(self, y0, a: Sequence[torch.Tensor], c: Combo, out) -> None:
+    def combine(self, y0, a: Sequence[torch.Tensor], c: Combo, B: int, out) -> None:
         n = len(a)
         cpa = (C.c_float * max(n, 1))(*[float(x) for x in c.cpa[:n]])
         cva = (C.c_float * max(n, 1))(*[float(x) for x in c.cva[:n]])
         rc = self.L.ab200_pv_combine(C.byref(self.desc), y0.data_ptr(), C.cast(_ptr_array(a), C.c_void_p), n, float(c.cpv),
-                                     C.cast(cpa, C.c_void_p), C.cast(cva, C.c_void_p), y0.shape[0], out.data_ptr(), _stream())
+                                     C.cast(cpa, C.c_void_p), C.cast(cva, C.c_void_p), B, out.data_ptr(), _stream())
         _lib.check(rc, "ab200_pv_combine")
 
     # ---- backward -----------------------------------------------------------------------------------
@@ -170,16 +170,16 @@ class TcEngine:
         self.partial = torch.zeros(int(npart), dtype=torch.uint8, device=self.dev)
         self.used = 0
 
-    def combine_backward(self, g, c: Combo, G_y0, G_a: Sequence[torch.Tensor], accumulate: bool) -> None:
+    def combine_backward(self, g, c: Combo, B: int, G_y0, G_a: Sequence[torch.Tensor], accumulate: bool) -> None:
         n = len(G_a)
         cpa = (C.c_float * max(n, 1))(*[float(x) for x in c.cpa[:n]])
         cva = (C.c_float * max(n, 1))(*[float(x) for x in c.cva[:n]])
         rc = self.L.ab200_pv_combine_backward(C.byref(self.desc), g.data_ptr(), n, float(c.cpv), C.cast(cpa, C.c_void_p),
-                                              C.cast(cva, C.c_void_p), g.shape[0], G_y0.data_ptr(), C.cast(_ptr_array(G_a), C.c_void_p),
+                                              C.cast(cva, C.c_void_p), B, G_y0.data_ptr(), C.cast(_ptr_array(G_a), C.c_void_p),
                                               1 if accumulate else 0, _stream())
         _lib.check(rc, "ab200_pv_combine_backward")
 
-    def stage_backward(self, y0, a: Sequence[torch.Tensor], cin: Combo, t: float, g_a, G_y0, G_a: Sequence[torch.Tensor]) -> None:
+    def stage_backward(self, y0, a: Sequence[torch.Tensor], cin: Combo, t: float, B: int, g_a, G_y0, G_a: Sequence[torch.Tensor]) -> None:
         if self.used + self.ntiles > self.nblobs:
             self.flush()
         s = StageDesc()
@@ -189,7 +189,7 @@ class TcEngine:
         _fill(s.in_cva, cin.cva[:len(a)])
         s.t = float(t)
         rc = self.L.ab200_stage_backward(C.byref(self.desc), self.image.data_ptr(), y0.data_ptr(), C.cast(_ptr_array(a), C.c_void_p),
-                                         C.byref(s), y0.shape[0], g_a.data_ptr(), G_y0.data_ptr(), C.cast(_ptr_array(G_a), C.c_void_p),
+                                         C.byref(s), B, g_a.data_ptr(), G_y0.data_ptr(), C.cast(_ptr_array(G_a), C.c_void_p),
                                          self.spill.data_ptr(), self.spill.numel(), self.used, self.nblobs, self.partial.data_ptr(),
                                          _stream())
         _lib.check(rc, "ab200_stage_backward")
@@ -225,44 +225,86 @@ def _stream() -> int:
 
 
 # --------------------------------------------------------------------------------------------------------
+# blocked buffers
+# --------------------------------------------------------------------------------------------------------
+def padded_rows(B: int) -> int:
+    return (B + TM - 1) // TM * TM
+
+
+def blocked_zeros(B: int, F: int, device) -> torch.Tensor:
+    """A zeroed tile-blocked [Bp, F] buffer (flat storage; see include/ananke_b200.h for the layout)."""
+    return torch.zeros(padded_rows(B) * F, dtype=torch.float32, device=device)
+
+
+def rows_block(src: torch.Tensor, dst: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    """row-major [B, F] -> blocked (dst = src, or dst += src)."""
+    L = _lib.lib()
+    B, F = src.shape
+    src = src.contiguous()
+    if dst is None:
+        dst = torch.empty(padded_rows(B) * F, dtype=torch.float32, device=src.device)
+        assert not accumulate
+    _lib.check(L.ab200_rows_block(src.data_ptr(), dst.data_ptr(), B, F, 1 if accumulate else 0, _stream()), "ab200_rows_block")
+    return dst
+
+
+def rows_unblock(src: torch.Tensor, B: int, F: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """blocked -> row-major [B, F]."""
+    L = _lib.lib()
+    if out is None:
+        out = torch.empty((B, F), dtype=torch.float32, device=src.device)
+    assert out.is_contiguous()
+    _lib.check(L.ab200_rows_unblock(src.data_ptr(), out.data_ptr(), B, F, _stream()), "ab200_rows_unblock")
+    return out
+
+
+# --------------------------------------------------------------------------------------------------------
 # fixed-grid rk4 (3/8 rule) with the discrete adjoint
 # --------------------------------------------------------------------------------------------------------
 def rk4_forward(eng: TcEngine, y0: torch.Tensor, t_host: Sequence[float], save_stages: bool):
-    """-> y_path [T, B, D], acc [T-1, 3, B, P] (stage accelerations a_1..a_3 of every step) or None."""
+    """y0 row-major [B, D] -> y_path row-major [T, B, D]; when `save_stages`, also the blocked per-step states
+    yb [T, Bp*D] and stage accelerations acc [T-1, 3, Bp*P] the adjoint needs."""
     B, T = y0.shape[0], len(t_host)
-    y_path = torch.empty((T, B, eng.D), dtype=torch.float32, device=y0.device)
+    dev = y0.device
+    Bp = padded_rows(B)
+    y_path = torch.empty((T, B, eng.D), dtype=torch.float32, device=dev)
     y_path[0].copy_(y0)
     n_keep = T - 1 if save_stages else 1
-    acc = torch.empty((n_keep, 3, B, eng.P), dtype=torch.float32, device=y0.device)
+    acc = torch.zeros((n_keep, 3, Bp * eng.P), dtype=torch.float32, device=dev)
+    yb = torch.zeros((T if save_stages else 2, Bp * eng.D), dtype=torch.float32, device=dev)
+    rows_block(y0, yb[0])
     for n in range(T - 1):
         t0, dt = float(t_host[n]), float(t_host[n + 1]) - float(t_host[n])
         A = acc[n if save_stages else 0]
-        yn = y_path[n]
+        yn = yb[n if save_stages else n % 2]
+        yn1 = yb[n + 1 if save_stages else (n + 1) % 2]
         for i in range(3):
-            eng.stage_forward(yn, [A[j] for j in range(i)], RK38.stage_input(i, dt), t0 + RK38.c[i] * dt, a_out=A[i])
-        eng.stage_forward(yn, [A[0], A[1], A[2]], RK38.stage_input(3, dt), float(t_host[n + 1]), y_out=y_path[n + 1],
+            eng.stage_forward(yn, [A[j] for j in range(i)], RK38.stage_input(i, dt), t0 + RK38.c[i] * dt, B, a_out=A[i])
+        eng.stage_forward(yn, [A[0], A[1], A[2]], RK38.stage_input(3, dt), float(t_host[n + 1]), B, y_out=yn1,
                           cout=RK38.combo(RK38.b, dt))
-    return y_path, (acc if save_stages else None)
+        rows_unblock(yn1, B, eng.D, out=y_path[n + 1])
+    return y_path, ((yb, acc) if save_stages else None)
 
 
-def rk4_backward(eng: TcEngine, t_host: Sequence[float], y_path: torch.Tensor, acc: torch.Tensor, grad_y_path: torch.Tensor):
-    """-> (grad_y0 [B, D], grad_w_flat)."""
-    T, B, D = y_path.shape
-    dev = y_path.device
+def rk4_backward(eng: TcEngine, t_host: Sequence[float], saved, grad_y_path: torch.Tensor):
+    """-> (grad_y0 row-major [B, D], grad_w_flat)."""
+    yb, acc = saved
+    T, B, D = grad_y_path.shape
+    dev = grad_y_path.device
     eng.backward_begin(B, stages_per_flush=4)
-    lam = grad_y_path[T - 1].contiguous().clone()
-    G_y0 = torch.empty_like(lam)
-    G_a = [torch.empty((B, eng.P), dtype=torch.float32, device=dev) for _ in range(4)]
+    lam = rows_block(grad_y_path[T - 1])
+    G_y0 = blocked_zeros(B, D, dev)
+    G_a = [blocked_zeros(B, eng.P, dev) for _ in range(4)]
     for n in range(T - 2, -1, -1):
         t0, dt = float(t_host[n]), float(t_host[n + 1]) - float(t_host[n])
         A = acc[n]
-        yn = y_path[n]
-        eng.combine_backward(lam, RK38.combo(RK38.b, dt), G_y0, G_a, accumulate=False)
+        yn = yb[n]
+        eng.combine_backward(lam, RK38.combo(RK38.b, dt), B, G_y0, G_a, accumulate=False)
         for i in (3, 2, 1, 0):
             t_i = float(t_host[n + 1]) if i == 3 else t0 + RK38.c[i] * dt
-            eng.stage_backward(yn, [A[j] for j in range(i)], RK38.stage_input(i, dt), t_i, G_a[i], G_y0, G_a[:i])
+            eng.stage_backward(yn, [A[j] for j in range(i)], RK38.stage_input(i, dt), t_i, B, G_a[i], G_y0, G_a[:i])
         eng.flush()
-        G_y0.add_(grad_y_path[n])
+        rows_block(grad_y_path[n], G_y0, accumulate=True)
         lam, G_y0 = G_y0, lam
     gw = eng.backward_end()
-    return lam, gw
+    return rows_unblock(lam, B, D), gw

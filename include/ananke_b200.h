@@ -136,11 +136,22 @@ typedef struct ab200_stage_desc {
   float rtol, atol;
 } ab200_stage_desc;
 
+/* LAYOUT of every per-agent fp32 buffer of the stage path (y0, y_out, a[], a_out, g_a, G_y0, G_a[] and the operands
+ * of ab200_pv_combine*): "tile-blocked".  Rows are padded to Bp = ceil(B / 128) * 128; inside a 128-agent tile the
+ * float4 with features 4 f4 .. 4 f4 + 3 of agent r is float4 number (tile * F/4 + f4) * 128 + r of the buffer, so a warp
+ * whose lanes own consecutive agents (= consecutive tensor-memory lanes) touches one contiguous 512-byte segment per
+ * access.  Padding rows must hold zeros (ab200_rows_block writes them; the kernels never store to them).
+ * ab200_rows_block / ab200_rows_unblock convert from / to the reference's row-major [B][F] tensors
+ * (accumulate = 1: blocked += row-major). */
+int ab200_rows_block(const float* src_rowmajor, float* dst_blocked, int64_t B, int32_t F, int32_t accumulate,
+                     ab200_stream_t stream);
+int ab200_rows_unblock(const float* src_blocked, float* dst_rowmajor, int64_t B, int32_t F, ab200_stream_t stream);
+
 /* bf16 UMMA image of the drift weights (+ a status word); build once per parameter update with ab200_stage_pack */
 size_t ab200_stage_image_bytes(const ab200_drift_desc* d);
 int ab200_stage_pack(const ab200_drift_desc* d, const float* w_flat, void* image, size_t image_bytes, ab200_stream_t stream);
-/* `a` : host array of n_a device pointers ([B][P] fp32 each).  a_out [B][P], y_out [B][D], err_sumsq (device double,
- * accumulated) may each be NULL. */
+/* `a` : host array of n_a device pointers (blocked [Bp][P] fp32 each).  a_out (blocked [Bp][P]), y_out (blocked
+ * [Bp][D]) and err_sumsq (device double, accumulated) may each be NULL. */
 int ab200_stage_forward(const ab200_drift_desc* d, const void* image, const float* y0, const float* const* a,
                         const ab200_stage_desc* s, int64_t B, float* a_out, float* y_out, double* err_sumsq,
                         ab200_stream_t stream);

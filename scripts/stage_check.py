@@ -34,8 +34,9 @@ def inputs(B):
 for B in (100, 1000, 4096 + 17):
     y0 = inputs(B)
     eng = stage.TcEngine(spec, w)
-    a_out = torch.full((B, 64), float('nan'), device=dev)
-    eng.stage_forward(y0, [], stage.Combo(0.0, [], []), 3.7, a_out=a_out)
+    ab_ = stage.blocked_zeros(B, 64, dev)
+    eng.stage_forward(stage.rows_block(y0), [], stage.Combo(0.0, [], []), 3.7, B, a_out=ab_)
+    a_out = stage.rows_unblock(ab_, B, 64)
     torch.cuda.synchronize()
     eng.check_status()
     ref = drift_eval(spec, w, 3.7, y0)[:, 64:128]
@@ -73,10 +74,10 @@ th = [float(v) for v in t.tolist()]
 eng = stage.TcEngine(spec, w)
 for it in range(2):
     torch.cuda.synchronize(); t0 = time.perf_counter()
-    yp, acc = stage.rk4_forward(eng, y0, th, save_stages=True)
+    yp, saved = stage.rk4_forward(eng, y0, th, save_stages=True)
     torch.cuda.synchronize(); t1 = time.perf_counter()
     g = torch.ones_like(yp) / yp.numel()
-    gy0, gw = stage.rk4_backward(eng, th, yp, acc, g)
+    gy0, gw = stage.rk4_backward(eng, th, saved, g)
     torch.cuda.synchronize(); t2 = time.perf_counter()
     eng.check_status()
     n = B * (T - 1)
