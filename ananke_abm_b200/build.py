@@ -18,6 +18,8 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",
 ]
+if os.environ.get("AB200_STAGE_TRACE") == "1":      # debug build: cycle trace of the stage kernels (scripts/trace_stage.py)
+    NVCC_FLAGS.append("-DAB200_STAGE_TRACE")
 
 
 def _nvcc() -> str:

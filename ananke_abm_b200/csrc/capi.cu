@@ -45,8 +45,10 @@ int stage_tc_pack(const float* w_flat, uint8_t* image, cudaStream_t st);
 int stage_fwd_tc(const ab200_drift_desc* d, const uint8_t* image, const float* y0, const float* const* a_ptrs, const void* desc_v,
                  int64_t B, float* a_out, float* y_out, double* err_sumsq, cudaStream_t st);
 int stage_bwd_tc(const ab200_drift_desc* d, const uint8_t* image, const float* y0, const float* const* a_ptrs, const void* desc_v,
-                 int64_t B, const float* g_a, float* G_y0, float* const* G_a, void* spill, int blob0, int nblobs, float* g_bout,
-                 cudaStream_t st);
+                 int64_t B, const float* g_base, const float* const* gx_ptrs, int n_g, const float* dp, const float* dv, float* gx_out,
+                 void* spill, int blob0, int nblobs, float* g_bout, cudaStream_t st);
+int adjoint_gather(const ab200_drift_desc* d, const float* base, const float* const* gx, int n, const float* cpv, int64_t B, float* out,
+                   cudaStream_t st);
 size_t wgrad_spill_bytes(int nblobs);
 size_t wgrad_partial_bytes();
 int wgrad_num_ctas();
@@ -214,14 +216,22 @@ size_t ab200_stage_spill_bytes(const ab200_drift_desc* d, int32_t nblobs) {
 size_t ab200_wgrad_partial_bytes(const ab200_drift_desc* d) { return stage_shape_ok(d) ? wgrad_partial_bytes() : 0; }
 
 int ab200_stage_backward(const ab200_drift_desc* d, const void* image, const float* y0, const float* const* a,
-                         const ab200_stage_desc* s, int64_t B, const float* g_a, float* G_y0, float* const* G_a, void* spill,
-                         size_t spill_bytes, int32_t blob0, int32_t nblobs, void* partial, ab200_stream_t stream) {
-  if (!d || !image || !y0 || !s || !g_a || !G_y0 || !spill || !partial || B <= 0 || (s->n_a > 0 && (!a || !G_a)))
+                         const ab200_stage_desc* s, int64_t B, const float* g_base, const float* const* gx, int32_t n_g,
+                         const float* dp_host, const float* dv_host, float* gx_out, void* spill, size_t spill_bytes, int32_t blob0,
+                         int32_t nblobs, void* partial, ab200_stream_t stream) {
+  if (!d || !image || !y0 || !s || !gx_out || !spill || !partial || B <= 0 || (s->n_a > 0 && !a) ||
+      (n_g > 0 && (!gx || !dp_host || !dv_host)) || (n_g == 0 && !g_base))
     return AB200_ERR_BAD_ARG;
   if (!stage_shape_ok(d)) return AB200_ERR_UNSUPPORTED;
   if (nblobs <= 0 || spill_bytes < wgrad_spill_bytes(nblobs)) return AB200_ERR_WORKSPACE;
-  return stage_bwd_tc(d, (const uint8_t*)image, y0, a, s, B, g_a, G_y0, G_a, spill, blob0, nblobs, wgrad_bout_ptr(partial),
-                      (cudaStream_t)stream);
+  return stage_bwd_tc(d, (const uint8_t*)image, y0, a, s, B, g_base, gx, n_g, dp_host, dv_host, gx_out, spill, blob0, nblobs,
+                      wgrad_bout_ptr(partial), (cudaStream_t)stream);
+}
+
+int ab200_adjoint_gather(const ab200_drift_desc* d, const float* base, const float* const* gx, int32_t n, const float* cpv_host,
+                         int64_t B, float* out, ab200_stream_t stream) {
+  if (!desc_ok(d) || !base || !out || B <= 0 || (n > 0 && (!gx || !cpv_host))) return AB200_ERR_BAD_ARG;
+  return adjoint_gather(d, base, gx, n, cpv_host, B, out, (cudaStream_t)stream);
 }
 
 int ab200_wgrad_accumulate(const ab200_drift_desc* d, const void* spill, int32_t nblobs, int32_t used, void* partial,

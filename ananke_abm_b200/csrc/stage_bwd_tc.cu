@@ -5,9 +5,11 @@
 //      (bits) and the residual stream in registers,
 //   2. back-propagates through the net with six dgrad GEMMs that read the SAME resident weight image MN-major
 //      (W^T without a transposed copy),
-//   3. scatters dL/d(stage input) into the step's gradient accumulators
-//         G_y0.p += g_p ; G_y0.v += cpv g_p + g_v ; G_y0.h += g_h ; G_a[j] += cpa[j] g_p + cva[j] g_v
-//      (every element is owned by one thread: plain read-modify-write, no atomics),
+//   3. WRITES dL/d(stage input) = gx = [g_p, g_v, g_h] (no read-modify-write anywhere: the upstream gradient of a
+//      stage is itself assembled in the prologue as a linear combination
+//         dL/da_out = g_base + sum_l dp[l] gx_l.p + dv[l] gx_l.v
+//      of the step-level term g_base and the gx of the LATER stages that consumed a_out, mirroring how the forward
+//      stage input is assembled from earlier stages; `ab200_adjoint_gather` folds all gx into dL/dy0 at the end),
 //   4. writes every layer's (input activation, output gradient) pair as bf16 "blobs" already laid out as the
 //      canonical MN-major UMMA operand image (K = agent), which wgrad_tc.cu streams straight into shared memory.
 // All per-agent fp32 buffers are tile-blocked (stage_tc.cuh), so every global access of a warp is one contiguous
@@ -26,15 +28,18 @@ struct StageBwdArgs {
   int n_a;
   Combo in;
   float t, period;
-  const float* g_a;           // blocked [Bp][64]  dL/da_out of this stage
-  float* G_y0;                // blocked [Bp][160] accumulated
-  float* G_a[MAX_A];          // blocked [Bp][64]  accumulated (only j < n_a)
+  const float* g_base;        // blocked [Bp][64] or null: step-level part of dL/da_out
+  const float* gx[MAX_A];     // blocked [Bp][160]: dL/d(stage input) of the later stages that read a_out
+  int n_g;
+  float dp[MAX_A], dv[MAX_A]; // their coefficients (the later stage's in.cpa / in.cva entry for a_out)
+  float* gx_out;              // blocked [Bp][160]: [g_p, g_v, g_h] of this stage (written)
   uint8_t* spill;             // blob buffer (SpillLayout)
-  float* g_bout;              // [64] atomically accumulated column sums of g_a (bias gradient of the output layer)
+  float* g_bout;              // [64] atomically accumulated column sums of dL/da_out (bias gradient of the output layer)
   int64_t B;
   int ntiles;
   int blob0;                  // blob index of tile 0 of this launch
   int nblobs;                 // blobs the spill buffer was sized for
+  int flags;
   int* status;
 };
 
@@ -64,8 +69,10 @@ __device__ __forceinline__ void bwd_fwd_epi(const SlotCtx& c, uint32_t (&z)[32],
       float x0 = __uint_as_float(r[2 * j]), x1 = __uint_as_float(r[2 * j + 1]);
       if (RES) { x0 += bf16lo(z[ch * 16 + j]); x1 += bf16hi(z[ch * 16 + j]); }
       o[j] = pack_relu_bf16(x0, x1);
-      m |= ((o[j] & 0xffffu) ? 1u : 0u) << (2 * j);
-      m |= ((o[j] >> 16) ? 1u : 0u) << (2 * j + 1);
+      // ReLU mask bits on the whole 32-bit word: bit 15 / 31 of t is set iff the low / high bf16 is non-zero;
+      // pair j lands at mask bits (15 - j) and (31 - j)
+      const uint32_t t = ((o[j] & 0x7FFF7FFFu) + 0x7FFF7FFFu) & 0x80008000u;
+      m |= t >> j;
       if (KEEP) z[ch * 16 + j] = o[j];
     }
     mask[ch] = m;
@@ -89,8 +96,8 @@ __device__ __forceinline__ void bwd_bwd_epi(const SlotCtx& c, uint32_t (&gs)[32]
     for (int j = 0; j < 16; ++j) {
       float x0 = __uint_as_float(r[2 * j]), x1 = __uint_as_float(r[2 * j + 1]);
       if (SKIP_IN) { x0 += bf16lo(gs[ch * 16 + j]); x1 += bf16hi(gs[ch * 16 + j]); }
-      x0 = ((m >> (2 * j)) & 1u) ? x0 : 0.0f;
-      x1 = ((m >> (2 * j + 1)) & 1u) ? x1 : 0.0f;
+      x0 = (m & (0x8000u >> j)) ? x0 : 0.0f;
+      x1 = (m & (0x80000000u >> j)) ? x1 : 0.0f;
       o[j] = pack_bf16(x0, x1);
       if (SKIP_OUT) gs[ch * 16 + j] = o[j];
     }
@@ -103,7 +110,8 @@ __global__ void __launch_bounds__(THREADS, 1) stage_bwd_tc_kernel(const __grid_c
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bars[NSLOT + 1];
   __shared__ uint32_t tmem_base_s;
-  SlotCtx c = stage_setup(smem, a.wimg, bars, &tmem_base_s, a.status);
+  __shared__ int issue_lock;
+  SlotCtx c = stage_setup(smem, a.wimg, bars, &tmem_base_s, &issue_lock, a.status, a.flags);
   const uint32_t tmem_base = tmem_base_s;
   const wg::SpillLayout S{a.nblobs};
   const int lane = threadIdx.x & 31;
@@ -112,6 +120,15 @@ __global__ void __launch_bounds__(THREADS, 1) stage_bwd_tc_kernel(const __grid_c
   for (int tile = blockIdx.x * NSLOT + c.slot; tile < a.ntiles; tile += gridDim.x * NSLOT) {
     const bool valid = (int64_t)tile * TM + c.row < a.B;      // padding rows: zeros in, nothing stored
     const int blob = a.blob0 + tile;
+    if (c.stid == 0 && (a.flags & 2)) {   // next tile of this slot -> L2 while this one computes
+      const int nt = tile + gridDim.x * NSLOT;
+      if (nt < a.ntiles) {
+        prefetch_tile_l2(a.y0, nt, YF4);
+        for (int s = 0; s < a.n_a; ++s) prefetch_tile_l2(a.a[s], nt, AF4);
+        if (a.g_base != nullptr) prefetch_tile_l2(a.g_base, nt, AF4);
+        for (int s = 0; s < a.n_g; ++s) prefetch_tile_l2(a.gx[s], nt, YF4);
+      }
+    }
 
     // ---- stage input -> ACT / HB / TB and the X blob (features: p 0..63, v 64..127, h 128..159, sin, cos, 1)
     uint8_t* xb = a.spill + S.x1(blob);
@@ -121,8 +138,8 @@ __global__ void __launch_bounds__(THREADS, 1) stage_bwd_tc_kernel(const __grid_c
       float pin[16], vin[16];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float4 pv = *blk4(a.y0, tile, YF4, f0 + j, c.row);
-        const float4 vv = *blk4(a.y0, tile, YF4, AF4 + f0 + j, c.row);
+        const float4 pv = ldro(blk4(a.y0, tile, YF4, f0 + j, c.row));
+        const float4 vv = ldro(blk4(a.y0, tile, YF4, AF4 + f0 + j, c.row));
         pin[4 * j] = pv.x + a.in.cpv * vv.x; pin[4 * j + 1] = pv.y + a.in.cpv * vv.y;
         pin[4 * j + 2] = pv.z + a.in.cpv * vv.z; pin[4 * j + 3] = pv.w + a.in.cpv * vv.w;
         vin[4 * j] = vv.x; vin[4 * j + 1] = vv.y; vin[4 * j + 2] = vv.z; vin[4 * j + 3] = vv.w;
@@ -133,7 +150,7 @@ __global__ void __launch_bounds__(THREADS, 1) stage_bwd_tc_kernel(const __grid_c
           const float cp = a.in.cpa[s], cv = a.in.cva[s];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float4 x = *blk4(a.a[s], tile, AF4, f0 + j, c.row);
+            const float4 x = ldro(blk4(a.a[s], tile, AF4, f0 + j, c.row));
             pin[4 * j] += cp * x.x; pin[4 * j + 1] += cp * x.y; pin[4 * j + 2] += cp * x.z; pin[4 * j + 3] += cp * x.w;
             vin[4 * j] += cv * x.x; vin[4 * j + 1] += cv * x.y; vin[4 * j + 2] += cv * x.z; vin[4 * j + 3] += cv * x.w;
           }
@@ -153,7 +170,7 @@ __global__ void __launch_bounds__(THREADS, 1) stage_bwd_tc_kernel(const __grid_c
       uint32_t o[8];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float4 x = *blk4(a.y0, tile, YF4, 2 * AF4 + c.hf * 4 + j, c.row);
+        const float4 x = ldro(blk4(a.y0, tile, YF4, 2 * AF4 + c.hf * 4 + j, c.row));
         o[2 * j] = pack_bf16(x.x, x.y);
         o[2 * j + 1] = pack_bf16(x.z, x.w);
       }
@@ -171,15 +188,15 @@ __global__ void __launch_bounds__(THREADS, 1) stage_bwd_tc_kernel(const __grid_c
     // ---- forward recompute (hidden layers only), masks + blobs
     uint32_t z[32];
     uint32_t m_z0[2], m_u0[2], m_z1[2], m_u1[2], m_z2[2];
-    run_layer<false>(c, C_ACT, (2 * P + H) / 16, true, OFF_W1, HID, HID);
+    run_layer<false, (2 * P + H) / 16, true, HID, HID>(c, C_ACT, OFF_W1);
     bwd_fwd_epi<false, true>(c, z, m_z0, a.spill + S.act(0, blob));
-    run_layer<false>(c, C_ACT, HID / 16, true, off_hh(0), HID, HID);
+    run_layer<false, HID / 16, true, HID, HID>(c, C_ACT, off_hh(0));
     bwd_fwd_epi<false, false>(c, z, m_u0, a.spill + S.act(1, blob));
-    run_layer<false>(c, C_ACT, HID / 16, true, off_hh(1), HID, HID);
+    run_layer<false, HID / 16, true, HID, HID>(c, C_ACT, off_hh(1));
     bwd_fwd_epi<true, true>(c, z, m_z1, a.spill + S.act(2, blob));
-    run_layer<false>(c, C_ACT, HID / 16, true, off_hh(2), HID, HID);
+    run_layer<false, HID / 16, true, HID, HID>(c, C_ACT, off_hh(2));
     bwd_fwd_epi<false, false>(c, z, m_u1, a.spill + S.act(3, blob));
-    run_layer<false>(c, C_ACT, HID / 16, true, off_hh(3), HID, HID);
+    run_layer<false, HID / 16, true, HID, HID>(c, C_ACT, off_hh(3));
     bwd_fwd_epi<true, false, false>(c, z, m_z2, a.spill + S.act(4, blob));
 
     // ---- upstream gradient of the output layer -> ACT (K = 64) + gO blob + bias column sums
@@ -188,7 +205,17 @@ __global__ void __launch_bounds__(THREADS, 1) stage_bwd_tc_kernel(const __grid_c
       float gv[32];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float4 x = *blk4(a.g_a, tile, AF4, c.hf * 8 + j, c.row);     // padding rows are zero
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.g_base != nullptr) x = ldro(blk4(a.g_base, tile, AF4, c.hf * 8 + j, c.row));     // padding rows are zero
+#pragma unroll
+        for (int s = 0; s < MAX_A; ++s) {
+          if (s < a.n_g) {
+            const float4 gp = ldro(blk4(a.gx[s], tile, YF4, c.hf * 8 + j, c.row));
+            const float4 gq = ldro(blk4(a.gx[s], tile, YF4, AF4 + c.hf * 8 + j, c.row));
+            const float dp = a.dp[s], dv = a.dv[s];
+            x.x += dp * gp.x + dv * gq.x; x.y += dp * gp.y + dv * gq.y; x.z += dp * gp.z + dv * gq.z; x.w += dp * gp.w + dv * gq.w;
+          }
+        }
         gv[4 * j] = x.x; gv[4 * j + 1] = x.y; gv[4 * j + 2] = x.z; gv[4 * j + 3] = x.w;
         o[2 * j] = pack_bf16(x.x, x.y);
         o[2 * j + 1] = pack_bf16(x.z, x.w);
@@ -210,26 +237,26 @@ __global__ void __launch_bounds__(THREADS, 1) stage_bwd_tc_kernel(const __grid_c
     }
 
     // ---- backward through the net (dgrad GEMMs on the MN-major view of the weight image)
-    run_layer<true>(c, C_ACT, P / 16, false, OFF_WO, P, HID);                       // g_z2 = gO W_O
+    run_layer<true, P / 16, false, P, HID>(c, C_ACT, OFF_WO);                       // g_z2 = gO W_O
     bwd_bwd_epi<false, true>(c, z, m_z2, a.spill + S.grad(4, blob));                // gB1 = g_z2 * [z2 > 0]  (skip -> z)
-    run_layer<true>(c, C_ACT, HID / 16, false, off_hh(3), HID, HID);                // g_u1 = gB1 W_B1
+    run_layer<true, HID / 16, false, HID, HID>(c, C_ACT, off_hh(3));                // g_u1 = gB1 W_B1
     {
       uint32_t dummy[32];
       bwd_bwd_epi<false, false>(c, dummy, m_u1, a.spill + S.grad(3, blob));         // gA1
     }
-    run_layer<true>(c, C_ACT, HID / 16, false, off_hh(2), HID, HID);                // gA1 W_A1 (+ skip)
+    run_layer<true, HID / 16, false, HID, HID>(c, C_ACT, off_hh(2));                // gA1 W_A1 (+ skip)
     bwd_bwd_epi<true, true>(c, z, m_z1, a.spill + S.grad(2, blob));                 // gB0
-    run_layer<true>(c, C_ACT, HID / 16, false, off_hh(1), HID, HID);
+    run_layer<true, HID / 16, false, HID, HID>(c, C_ACT, off_hh(1));
     {
       uint32_t dummy[32];
       bwd_bwd_epi<false, false>(c, dummy, m_u0, a.spill + S.grad(1, blob));         // gA0
     }
-    run_layer<true>(c, C_ACT, HID / 16, false, off_hh(0), HID, HID);
+    run_layer<true, HID / 16, false, HID, HID>(c, C_ACT, off_hh(0));
     bwd_bwd_epi<true, false>(c, z, m_z0, a.spill + S.grad(0, blob));                // g1
-    run_layer<true>(c, C_ACT, HID / 16, false, OFF_W1, HID, 2 * P + H);             // g_x[128 x 160] = g1 W_1[:, :160]
+    run_layer<true, HID / 16, false, HID, 2 * P + H>(c, C_ACT, OFF_W1);             // g_x[128 x 160] = g1 W_1[:, :160]
 
-    // ---- scatter into the step's gradient accumulators (tcgen05.ld is warp-collective: issued by every lane, the
-    //      global read-modify-writes only by lanes that own a real agent)
+    // ---- dL/d(stage input) -> gx_out (tcgen05.ld is warp-collective: issued by every lane; only lanes that own a real
+    //      agent store)
 #pragma unroll
     for (int ch = 0; ch < 2; ++ch) {     // 16 dims per pass
       const int f0 = c.hf * 8 + ch * 4;
@@ -240,34 +267,10 @@ __global__ void __launch_bounds__(THREADS, 1) stage_bwd_tc_kernel(const __grid_c
       if (valid) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          float4* pp = blk4(a.G_y0, tile, YF4, f0 + j, c.row);
-          float4* pv = blk4(a.G_y0, tile, YF4, AF4 + f0 + j, c.row);
-          float4 x = *pp, y = *pv;
-          const float gp0 = __uint_as_float(rp[4 * j]), gp1 = __uint_as_float(rp[4 * j + 1]), gp2 = __uint_as_float(rp[4 * j + 2]),
-                      gp3 = __uint_as_float(rp[4 * j + 3]);
-          x.x += gp0; x.y += gp1; x.z += gp2; x.w += gp3;
-          y.x += a.in.cpv * gp0 + __uint_as_float(rv[4 * j]);
-          y.y += a.in.cpv * gp1 + __uint_as_float(rv[4 * j + 1]);
-          y.z += a.in.cpv * gp2 + __uint_as_float(rv[4 * j + 2]);
-          y.w += a.in.cpv * gp3 + __uint_as_float(rv[4 * j + 3]);
-          *pp = x;
-          *pv = y;
-        }
-#pragma unroll
-        for (int s = 0; s < MAX_A; ++s) {
-          if (s < a.n_a) {
-            const float cp = a.in.cpa[s], cv = a.in.cva[s];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float4* q = blk4(a.G_a[s], tile, AF4, f0 + j, c.row);
-              float4 x = *q;
-              x.x += cp * __uint_as_float(rp[4 * j]) + cv * __uint_as_float(rv[4 * j]);
-              x.y += cp * __uint_as_float(rp[4 * j + 1]) + cv * __uint_as_float(rv[4 * j + 1]);
-              x.z += cp * __uint_as_float(rp[4 * j + 2]) + cv * __uint_as_float(rv[4 * j + 2]);
-              x.w += cp * __uint_as_float(rp[4 * j + 3]) + cv * __uint_as_float(rv[4 * j + 3]);
-              *q = x;
-            }
-          }
+          *blk4(a.gx_out, tile, YF4, f0 + j, c.row) = make_float4(__uint_as_float(rp[4 * j]), __uint_as_float(rp[4 * j + 1]),
+                                                                   __uint_as_float(rp[4 * j + 2]), __uint_as_float(rp[4 * j + 3]));
+          *blk4(a.gx_out, tile, YF4, AF4 + f0 + j, c.row) = make_float4(__uint_as_float(rv[4 * j]), __uint_as_float(rv[4 * j + 1]),
+                                                                         __uint_as_float(rv[4 * j + 2]), __uint_as_float(rv[4 * j + 3]));
         }
       }
     }
@@ -277,13 +280,10 @@ __global__ void __launch_bounds__(THREADS, 1) stage_bwd_tc_kernel(const __grid_c
       tmem_ld_wait();
       if (valid) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float4* q = blk4(a.G_y0, tile, YF4, 2 * AF4 + c.hf * 4 + j, c.row);
-          float4 x = *q;
-          x.x += __uint_as_float(rh[4 * j]); x.y += __uint_as_float(rh[4 * j + 1]);
-          x.z += __uint_as_float(rh[4 * j + 2]); x.w += __uint_as_float(rh[4 * j + 3]);
-          *q = x;
-        }
+        for (int j = 0; j < 4; ++j)
+          *blk4(a.gx_out, tile, YF4, 2 * AF4 + c.hf * 4 + j, c.row) =
+              make_float4(__uint_as_float(rh[4 * j]), __uint_as_float(rh[4 * j + 1]), __uint_as_float(rh[4 * j + 2]),
+                          __uint_as_float(rh[4 * j + 3]));
       }
     }
   }
@@ -297,31 +297,35 @@ struct StageBwdHost {   // mirrors the head of ab200_stage_desc
 };
 
 int stage_bwd_tc(const ab200_drift_desc* d, const uint8_t* image, const float* y0, const float* const* a_ptrs, const void* desc_v,
-                 int64_t B, const float* g_a, float* G_y0, float* const* G_a, void* spill, int blob0, int nblobs, float* g_bout,
-                 cudaStream_t st) {
+                 int64_t B, const float* g_base, const float* const* gx_ptrs, int n_g, const float* dp, const float* dv, float* gx_out,
+                 void* spill, int blob0, int nblobs, float* g_bout, cudaStream_t st) {
   const StageBwdHost& h = *reinterpret_cast<const StageBwdHost*>(desc_v);
-  if (h.n_a < 0 || h.n_a > MAX_A) return AB200_ERR_BAD_ARG;
+  if (h.n_a < 0 || h.n_a > MAX_A || n_g < 0 || n_g > MAX_A) return AB200_ERR_BAD_ARG;
   StageBwdArgs k{};
   k.wimg = image;
   k.y0 = y0;
   k.n_a = h.n_a;
   for (int i = 0; i < MAX_A; ++i) {
     k.a[i] = (i < h.n_a) ? a_ptrs[i] : nullptr;
-    k.G_a[i] = (i < h.n_a) ? G_a[i] : nullptr;
     k.in.cpa[i] = h.in_cpa[i];
     k.in.cva[i] = h.in_cva[i];
+    k.gx[i] = (i < n_g) ? gx_ptrs[i] : nullptr;
+    k.dp[i] = (i < n_g) ? dp[i] : 0.f;
+    k.dv[i] = (i < n_g) ? dv[i] : 0.f;
   }
+  k.n_g = n_g;
   k.in.cpv = h.in_cpv;
   k.t = h.t;
   k.period = d->time_period;
-  k.g_a = g_a;
-  k.G_y0 = G_y0;
+  k.g_base = g_base;
+  k.gx_out = gx_out;
   k.spill = (uint8_t*)spill;
   k.g_bout = g_bout;
   k.B = B;
   k.ntiles = (int)((B + TM - 1) / TM);
   k.blob0 = blob0;
   k.nblobs = nblobs;
+  k.flags = stage_flags();
   if (blob0 < 0 || blob0 + k.ntiles > nblobs) return AB200_ERR_BAD_ARG;
   k.status = reinterpret_cast<int*>(const_cast<uint8_t*>(image) + align_up(W_BYTES, 256));
   int dev = 0, sms = 148;

@@ -102,6 +102,51 @@ __global__ void __launch_bounds__(256) pv_combine_bwd_kernel(const __grid_consta
   }
 }
 
+// out = base + sum_l [gx_l.p ; cpv_l gx_l.p + gx_l.v ; gx_l.h]   (dL/dy0 of a step from the per-stage dL/d(stage input))
+struct GatherArgs {
+  const float* base;
+  const float* gx[EL_MAX_A];
+  float cpv[EL_MAX_A];
+  float* out;
+  int n, ntiles, P, H;
+};
+__global__ void __launch_bounds__(256) adjoint_gather_kernel(const __grid_constant__ GatherArgs a) {
+  const int P4 = a.P / 4, H4 = a.H / 4, Y4 = 2 * P4 + H4;
+  const int64_t n = (int64_t)a.ntiles * (P4 + H4) * EL_TM;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int tile, grp, row;
+    decode(i, P4, H4, tile, grp, row);
+    const size_t t0 = (size_t)tile * Y4 * EL_TM + row;
+    const float4* b4 = reinterpret_cast<const float4*>(a.base) + t0;
+    float4* o4 = reinterpret_cast<float4*>(a.out) + t0;
+    if (grp >= P4) {
+      const size_t f = (size_t)(2 * P4 + (grp - P4)) * EL_TM;
+      float4 x = b4[f];
+#pragma unroll
+      for (int s = 0; s < EL_MAX_A; ++s)
+        if (s < a.n) {
+          const float4 g = (reinterpret_cast<const float4*>(a.gx[s]) + t0)[f];
+          x.x += g.x; x.y += g.y; x.z += g.z; x.w += g.w;
+        }
+      o4[f] = x;
+      continue;
+    }
+    const size_t fp = (size_t)grp * EL_TM, fv = (size_t)(P4 + grp) * EL_TM;
+    float4 xp = b4[fp], xv = b4[fv];
+#pragma unroll
+    for (int s = 0; s < EL_MAX_A; ++s)
+      if (s < a.n) {
+        const float4* g4 = reinterpret_cast<const float4*>(a.gx[s]) + t0;
+        const float4 gp = g4[fp], gv = g4[fv];
+        const float c = a.cpv[s];
+        xp.x += gp.x; xp.y += gp.y; xp.z += gp.z; xp.w += gp.w;
+        xv.x += c * gp.x + gv.x; xv.y += c * gp.y + gv.y; xv.z += c * gp.z + gv.z; xv.w += c * gp.w + gv.w;
+      }
+    o4[fp] = xp;
+    o4[fv] = xv;
+  }
+}
+
 // ---- row-major <-> blocked ---------------------------------------------------------------------------------
 // One CTA moves 32 rows x F floats through shared memory so that both the row-major side (rows contiguous) and the
 // blocked side (32 consecutive agents of one float4 group contiguous) are accessed in full 128-byte lines.
@@ -173,6 +218,17 @@ int pv_combine_bwd(const ab200_drift_desc* d, const float* g, int n_a, float cpv
   k.ntiles = (int)((B + EL_TM - 1) / EL_TM);
   for (int i = 0; i < n_a; ++i) { k.G_a[i] = G_a[i]; k.cpa[i] = cpa[i]; k.cva[i] = cva[i]; }
   pv_combine_bwd_kernel<<<launch_cfg((int64_t)k.ntiles * EL_TM * ((k.P + k.H) / 4)), 256, 0, st>>>(k);
+  return check_launch();
+}
+
+int adjoint_gather(const ab200_drift_desc* d, const float* base, const float* const* gx, int n, const float* cpv, int64_t B, float* out,
+                   cudaStream_t st) {
+  if (n < 0 || n > EL_MAX_A || d->pos_dim % 4 || d->ctx_dim % 4) return AB200_ERR_BAD_ARG;
+  GatherArgs k{};
+  k.base = base; k.out = out; k.n = n; k.P = d->pos_dim; k.H = d->ctx_dim;
+  k.ntiles = (int)((B + EL_TM - 1) / EL_TM);
+  for (int i = 0; i < n; ++i) { k.gx[i] = gx[i]; k.cpv[i] = cpv[i]; }
+  adjoint_gather_kernel<<<launch_cfg((int64_t)k.ntiles * EL_TM * ((k.P + k.H) / 4)), 256, 0, st>>>(k);
   return check_launch();
 }
 

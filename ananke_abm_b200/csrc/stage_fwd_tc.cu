@@ -8,10 +8,21 @@
 // which covers every stage of torchdiffeq's fixed-grid rk4 (rk_common.py rk4_alt_step_func) and adaptive dopri5
 // (rk_common.py _runge_kutta_step + misc.py _compute_error_ratio): the host passes the tableau as `Combo`s.
 // Two 128-agent tiles ("slots") are in flight per CTA; see stage_tc.cuh.
+#include <stdlib.h>
 #include "stage_tc.cuh"
 
 namespace ab200 {
 using namespace stc;
+
+#ifdef AB200_STAGE_TRACE
+extern "C" int ab200_debug_stage_trace(long long* host_out, int* counts) {
+  cudaMemcpyFromSymbol(host_out, stc::g_stage_trace, sizeof(long long) * 8192);
+  cudaMemcpyFromSymbol(counts, stc::g_stage_trace_n, sizeof(int) * 2);
+  int z[2] = {0, 0};
+  cudaMemcpyToSymbol(stc::g_stage_trace_n, z, sizeof(z));
+  return 0;
+}
+#endif
 
 // ---- prepack: torch-layout fp32 weights -> bf16 UMMA image with bias / time-feature K extensions ---------------
 __global__ void stage_pack_kernel(const float* __restrict__ w, uint8_t* __restrict__ out) {
@@ -59,6 +70,15 @@ __global__ void stage_pack_kernel(const float* __restrict__ w, uint8_t* __restri
   }
 }
 
+int stage_flags() {
+  static int f = -1;
+  if (f < 0) {
+    const char* e = getenv("AB200_STAGE_FLAGS");
+    f = e ? atoi(e) : 0;   // measured on B200: neither the issue mutex nor the bulk L2 prefetch pays (profiles/r01_stage_notes.md)
+  }
+  return f;
+}
+
 size_t stage_tc_image_bytes() { return align_up(W_BYTES, 256) + 256; }   // image + status word
 
 int stage_tc_pack(const float* w_flat, uint8_t* image, cudaStream_t st) {
@@ -81,6 +101,7 @@ struct StageFwdArgs {
   float rtol, atol;
   int64_t B;
   int ntiles;
+  int flags;
   int* status;
 };
 
@@ -89,13 +110,22 @@ __global__ void __launch_bounds__(THREADS, 1) stage_fwd_tc_kernel(const __grid_c
   __shared__ uint64_t bars[NSLOT + 1];
   __shared__ uint32_t tmem_base_s;
   __shared__ double err_red[THREADS / 32];
-  SlotCtx c = stage_setup(smem, a.wimg, bars, &tmem_base_s, a.status);
+  __shared__ int issue_lock;
+  SlotCtx c = stage_setup(smem, a.wimg, bars, &tmem_base_s, &issue_lock, a.status, a.flags);
   const uint32_t tmem_base = tmem_base_s;
   double err_local = 0.0;
 
 #pragma unroll 1
   for (int tile = blockIdx.x * NSLOT + c.slot; tile < a.ntiles; tile += gridDim.x * NSLOT) {
     const bool valid = (int64_t)tile * TM + c.row < a.B;      // padding rows hold zeros and are never stored to
+    STAGE_TRACE(c, 9);
+    if (c.stid == 0 && (a.flags & 2)) {   // next tile of this slot -> L2 while this one computes
+      const int nt = tile + gridDim.x * NSLOT;
+      if (nt < a.ntiles) {
+        prefetch_tile_l2(a.y0, nt, YF4);
+        for (int s = 0; s < a.n_a; ++s) prefetch_tile_l2(a.a[s], nt, AF4);
+      }
+    }
 
     // ---- stage input -> ACT (bf16), context h -> HB, time/bias block -> TB          (all buffers blocked, see stage_tc.cuh)
 #pragma unroll
@@ -104,8 +134,8 @@ __global__ void __launch_bounds__(THREADS, 1) stage_fwd_tc_kernel(const __grid_c
       float pin[16], vin[16];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float4 pv = *blk4(a.y0, tile, YF4, f0 + j, c.row);
-        const float4 vv = *blk4(a.y0, tile, YF4, AF4 + f0 + j, c.row);
+        const float4 pv = ldro(blk4(a.y0, tile, YF4, f0 + j, c.row));
+        const float4 vv = ldro(blk4(a.y0, tile, YF4, AF4 + f0 + j, c.row));
         pin[4 * j] = pv.x + a.in.cpv * vv.x; pin[4 * j + 1] = pv.y + a.in.cpv * vv.y;
         pin[4 * j + 2] = pv.z + a.in.cpv * vv.z; pin[4 * j + 3] = pv.w + a.in.cpv * vv.w;
         vin[4 * j] = vv.x; vin[4 * j + 1] = vv.y; vin[4 * j + 2] = vv.z; vin[4 * j + 3] = vv.w;
@@ -116,7 +146,7 @@ __global__ void __launch_bounds__(THREADS, 1) stage_fwd_tc_kernel(const __grid_c
           const float cp = a.in.cpa[s], cv = a.in.cva[s];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const float4 x = *blk4(a.a[s], tile, AF4, f0 + j, c.row);
+            const float4 x = ldro(blk4(a.a[s], tile, AF4, f0 + j, c.row));
             pin[4 * j] += cp * x.x; pin[4 * j + 1] += cp * x.y; pin[4 * j + 2] += cp * x.z; pin[4 * j + 3] += cp * x.w;
             vin[4 * j] += cv * x.x; vin[4 * j + 1] += cv * x.y; vin[4 * j + 2] += cv * x.z; vin[4 * j + 3] += cv * x.w;
           }
@@ -134,29 +164,31 @@ __global__ void __launch_bounds__(THREADS, 1) stage_fwd_tc_kernel(const __grid_c
       uint32_t o[8];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const float4 x = *blk4(a.y0, tile, YF4, 2 * AF4 + c.hf * 4 + j, c.row);
+        const float4 x = ldro(blk4(a.y0, tile, YF4, 2 * AF4 + c.hf * 4 + j, c.row));
         o[2 * j] = pack_bf16(x.x, x.y);
         o[2 * j + 1] = pack_bf16(x.z, x.w);
       }
       tmem_st8(c.tmem + c.lane_sel + C_HB + (uint32_t)(c.hf * 8), o);
     }
     write_time_block(c, a.t, a.period);
+    STAGE_TRACE(c, 10);
 
     // ---- drift net
     uint32_t z[32];
-    run_layer<false>(c, C_ACT, (2 * P + H) / 16, true, OFF_W1, HID, HID);
+    run_layer<false, (2 * P + H) / 16, true, HID, HID>(c, C_ACT, OFF_W1);
     epi_relu<true>(c, z);
 #pragma unroll 1
     for (int r = 0; r < NRES; ++r) {
       uint32_t dummy[32];
-      run_layer<false>(c, C_ACT, HID / 16, true, off_hh(2 * r), HID, HID);
+      run_layer<false, HID / 16, true, HID, HID>(c, C_ACT, off_hh(2 * r));
       epi_relu<false>(c, dummy);
-      run_layer<false>(c, C_ACT, HID / 16, true, off_hh(2 * r + 1), HID, HID);
+      run_layer<false, HID / 16, true, HID, HID>(c, C_ACT, off_hh(2 * r + 1));
       epi_residual(c, z);
     }
-    run_layer<false>(c, C_ACT, HID / 16, true, OFF_WO, P, P);
+    run_layer<false, HID / 16, true, P, P>(c, C_ACT, OFF_WO);
 
     // ---- output epilogue: this thread's 32 acceleration dims (float4 groups hf*8 ..)
+    STAGE_TRACE(c, 11);
     {
       uint32_t r[32];
       tmem_ld32(c.tmem + c.lane_sel + C_ACC + (uint32_t)(c.hf * 32), r);
@@ -173,8 +205,8 @@ __global__ void __launch_bounds__(THREADS, 1) stage_fwd_tc_kernel(const __grid_c
         const float oc = a.out.cpa[a.n_a], ov = a.out.cva[a.n_a], ecp = a.err.cpa[a.n_a], ecv = a.err.cva[a.n_a];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {       // one float4 group of p and of v per pass
-          const float4 p0 = *blk4(a.y0, tile, YF4, f0 + j, c.row);
-          const float4 v0 = *blk4(a.y0, tile, YF4, AF4 + f0 + j, c.row);
+          const float4 p0 = ldro(blk4(a.y0, tile, YF4, f0 + j, c.row));
+          const float4 v0 = ldro(blk4(a.y0, tile, YF4, AF4 + f0 + j, c.row));
           const float ao[4] = {__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
                                __uint_as_float(r[4 * j + 3])};
           const float p0r[4] = {p0.x, p0.y, p0.z, p0.w}, v0r[4] = {v0.x, v0.y, v0.z, v0.w};
@@ -189,7 +221,7 @@ __global__ void __launch_bounds__(THREADS, 1) stage_fwd_tc_kernel(const __grid_c
 #pragma unroll
           for (int s = 0; s < MAX_A; ++s) {
             if (s < a.n_a) {
-              const float4 x = *blk4(a.a[s], tile, AF4, f0 + j, c.row);
+              const float4 x = ldro(blk4(a.a[s], tile, AF4, f0 + j, c.row));
               const float xs[4] = {x.x, x.y, x.z, x.w};
               const float cp = a.out.cpa[s], cv = a.out.cva[s], xp = a.err.cpa[s], xv = a.err.cva[s];
 #pragma unroll
@@ -218,7 +250,7 @@ __global__ void __launch_bounds__(THREADS, 1) stage_fwd_tc_kernel(const __grid_c
         if (valid) {   // context h rides along unchanged (dh/dt = 0)
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            *blk4(a.y_out, tile, YF4, 2 * AF4 + c.hf * 4 + j, c.row) = *blk4(a.y0, tile, YF4, 2 * AF4 + c.hf * 4 + j, c.row);
+            *blk4(a.y_out, tile, YF4, 2 * AF4 + c.hf * 4 + j, c.row) = ldro(blk4(a.y0, tile, YF4, 2 * AF4 + c.hf * 4 + j, c.row));
         }
       }
     }
@@ -273,6 +305,7 @@ int stage_fwd_tc(const ab200_drift_desc* d, const uint8_t* image, const float* y
   k.atol = h.atol;
   k.B = B;
   k.ntiles = (int)((B + TM - 1) / TM);
+  k.flags = stage_flags();
   k.status = reinterpret_cast<int*>(const_cast<uint8_t*>(image) + align_up(W_BYTES, 256));
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);

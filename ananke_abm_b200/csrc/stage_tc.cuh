@@ -44,6 +44,21 @@ __host__ __device__ constexpr uint32_t off_hh(int m) { return OFF_RES + (uint32_
 // ---- tensor-memory columns (per slot) ------------------------------------------------------------------
 constexpr uint32_t SLOT_COLS = 256, C_ACC = 0, C_ACT = 160, C_HB = 224, C_TB = 240;
 
+// Optional cycle trace (compile with -DAB200_STAGE_TRACE): thread 0 of every slot of CTA 0 appends (tag, clock) pairs.
+#ifdef AB200_STAGE_TRACE
+static __device__ long long g_stage_trace[8192];     // one copy per translation unit (no -rdc)
+static __device__ int g_stage_trace_n[2];
+#define STAGE_TRACE(c, tag)                                                                  \
+  do {                                                                                        \
+    if (blockIdx.x == 0 && (c).stid == 0) {                                                   \
+      const int i_ = g_stage_trace_n[(c).slot]++;                                             \
+      if (i_ < 2048) { g_stage_trace[((c).slot * 2048 + i_) * 2] = (tag); g_stage_trace[((c).slot * 2048 + i_) * 2 + 1] = clock64(); } \
+    }                                                                                         \
+  } while (0)
+#else
+#define STAGE_TRACE(c, tag) do { } while (0)
+#endif
+
 __device__ __forceinline__ void slot_sync(int slot) {
   asm volatile("bar.sync %0, %1;" ::"r"(slot + 1), "n"(SLOT_THREADS) : "memory");
 }
@@ -62,6 +77,8 @@ struct SlotCtx {
   uint32_t lane_sel;    // (32 * (warp % 4)) << 16 : the TMEM lanes this warp may touch
   uint32_t sbase;       // shared-memory address of the weight image
   uint64_t* bar;        // MMA-completion mbarrier of the slot
+  int* lock;            // CTA-wide "MMA issue" mutex (shared memory)
+  int flags;            // tuning switches (stage_flags()): 1 = issue mutex, 2 = L2 prefetch of the next tile
   int* status;
   uint32_t phase;
   int slot, stid, row, hf;   // thread index inside the slot, agent row (TMEM lane), column half
@@ -69,41 +86,51 @@ struct SlotCtx {
 };
 
 // One layer:  ACC[128 x N] = A * W^T  (K-major image)  or  A * W  (MN-major view of the same image, `TRANS`).
-//   A = `nks` K-steps of bf16 pairs starting at TMEM column a_col, optionally followed by the TB block (`ext`).
-// Called by all threads of the slot; returns when the accumulator is complete.
-template <bool TRANS>
-__device__ __forceinline__ void run_layer(SlotCtx& c, uint32_t a_col, int nks, bool ext, uint32_t w_off, int n_img, int N) {
+//   A = NKS K-steps of bf16 pairs starting at TMEM column a_col, optionally followed by the TB block (EXT).
+// Called by all threads of the slot; returns when the accumulator is complete.  Everything about the shape is a
+// template parameter so that the single issuing thread runs a fully unrolled stream of tcgen05.mma whose descriptors
+// differ by a compile-time constant (the tensor core needs a new MMA every 64 cycles; a descriptor rebuilt with
+// shifts and masks per K-step does not keep up).
+template <bool TRANS, int NKS, bool EXT, int N_IMG, int N>
+__device__ __forceinline__ void run_layer(SlotCtx& c, uint32_t a_col, uint32_t w_off) {
+  STAGE_TRACE(c, 1);
   tmem_st_wait();
   tc_fence_before();
+  STAGE_TRACE(c, 2);
   slot_sync(c.slot);
+  STAGE_TRACE(c, 3);
   if (c.stid == 0) {
     tc_fence_after();
-    const uint32_t idesc = make_idesc_bf16(TM, N, false, false, TRANS);
-    const uint32_t acc = c.tmem + C_ACC;
-    if (!TRANS) {
-      const uint32_t l = lbo(n_img);
-#pragma unroll 1
-      for (int ks = 0; ks < nks; ++ks)
-        mma_ts(acc, c.tmem + a_col + (uint32_t)ks * 8u, make_smem_desc(c.sbase + w_off + (uint32_t)ks * 2u * l, l, SBO, SWZ_NONE),
-               idesc, ks > 0 ? 1u : 0u);
-      if (ext)
-        mma_ts(acc, c.tmem + C_TB, make_smem_desc(c.sbase + w_off + (uint32_t)nks * 2u * l, l, SBO, SWZ_NONE), idesc, 1u);
-    } else {
-      // B'[n' = in][k' = out] = W[out][in]: K-direction cores are the image's 8-row groups (128 B apart), MN-direction
-      // cores are its 8-column groups (lbo(n_img) apart)
-      const uint32_t l = lbo(n_img);
-#pragma unroll 1
-      for (int ks = 0; ks < nks; ++ks)
-        mma_ts(acc, c.tmem + a_col + (uint32_t)ks * 8u, make_smem_desc(c.sbase + w_off + (uint32_t)ks * 2u * SBO, SBO, l, SWZ_NONE),
-               idesc, ks > 0 ? 1u : 0u);
+    // The two slots take turns ISSUING a layer: all MMAs of one slot's layer enter the tensor-core queue ahead of the
+    // other slot's, so the first one completes after 1x (not 2x) the layer time and the slots fall into anti-phase --
+    // one slot's epilogue runs under the other slot's MMAs instead of both slots doing the same thing at once.
+    if (c.flags & 1) {
+      const long long t0 = clock64();
+      while (atomicCAS(c.lock, 0, 1) != 0) {
+        if (clock64() - t0 > STAGE_WAIT_CYCLES) { *c.status = 7; break; }
+      }
     }
+    constexpr uint32_t idesc = make_idesc_bf16(TM, N, false, false, TRANS);
+    constexpr uint32_t L = lbo(N_IMG);
+    // K-major: K-adjacent cores L apart (LBO), MN-adjacent cores 128 B apart (SBO); a K-step spans two K cores.
+    // MN-major view: B'[n' = in][k' = out] = W[out][in]; K-direction cores are the image's 8-row groups (128 B
+    // apart), MN-direction cores its 8-column groups (L apart).
+    constexpr uint32_t step16 = (TRANS ? 2u * SBO : 2u * L) >> 4;       // descriptor start-address units per K-step
+    const uint64_t d0 = TRANS ? make_smem_desc(c.sbase + w_off, SBO, L, SWZ_NONE) : make_smem_desc(c.sbase + w_off, L, SBO, SWZ_NONE);
+    const uint32_t acc = c.tmem + C_ACC, a0 = c.tmem + a_col;
+#pragma unroll
+    for (int ks = 0; ks < NKS; ++ks) mma_ts(acc, a0 + (uint32_t)ks * 8u, d0 + (uint64_t)(ks * step16), idesc, ks > 0 ? 1u : 0u);
+    if (EXT) mma_ts(acc, c.tmem + C_TB, d0 + (uint64_t)(NKS * step16), idesc, 1u);
     mma_commit(c.bar);
+    if (c.flags & 1) atomicExch(c.lock, 0);
   }
+  STAGE_TRACE(c, 4);
   __syncwarp();
   if (c.alive && !mbar_wait(c.bar, c.phase, STAGE_WAIT_CYCLES)) { c.alive = false; *c.status = 1; }
   c.phase ^= 1;
   __syncwarp();
   tc_fence_after();
+  STAGE_TRACE(c, 5);
 }
 
 // ---- hidden-layer epilogues: this thread's 64 columns (hf*64 ..) of its row ------------------------------
@@ -178,14 +205,22 @@ __device__ __forceinline__ float4* blk4(float* base, int tile, int F4, int f4, i
 __device__ __forceinline__ const float4* blk4(const float* base, int tile, int F4, int f4, int row) {
   return reinterpret_cast<const float4*>(base) + ((size_t)tile * F4 + f4) * TM + row;
 }
+// read-only 128-bit load (ld.global.nc): lets the compiler hoist input loads above the blob / output stores
+__device__ __forceinline__ float4 ldro(const float4* p) { return __ldg(p); }
+// ask the L2 for a whole tile of a blocked buffer (contiguous F * 512 bytes); one thread, no registers, no wait
+__device__ __forceinline__ void prefetch_tile_l2(const float* base, int tile, int F4) {
+  const char* p = reinterpret_cast<const char*>(base) + (size_t)tile * F4 * TM * 16;
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"((uint32_t)(F4 * TM * 16)) : "memory");
+}
 constexpr int YF4 = D / 4, AF4 = P / 4;       // float4 groups per row of a state / an acceleration buffer
 
 // setup shared by the kernels: weights -> smem (one bulk copy engine transfer), TMEM, barriers.
 __device__ __forceinline__ SlotCtx stage_setup(uint8_t* smem, const uint8_t* wimg, uint64_t* bars, uint32_t* tmem_base_s,
-                                               int* status) {
+                                               int* lock, int* status, int flags) {
   const int tid = threadIdx.x, warp = tid >> 5;
   if (warp == 0) tmem_alloc<512>(tmem_base_s);
   if (tid == 0) {
+    *lock = 0;
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
     mbar_init(&bars[2], 1);
@@ -211,6 +246,8 @@ __device__ __forceinline__ SlotCtx stage_setup(uint8_t* smem, const uint8_t* wim
   c.lane_sel = (uint32_t)(q * 32) << 16;
   c.sbase = smem_u32(smem);
   c.bar = &bars[c.slot];
+  c.lock = lock;
+  c.flags = flags;
   c.status = status;
   c.phase = 0;
   c.alive = true;
@@ -224,6 +261,9 @@ __device__ __forceinline__ void stage_teardown(uint32_t tmem_base) {
 }
 
 }  // namespace stc
+
+// tuning switches, read once from the environment (AB200_STAGE_FLAGS, default 0 = both off)
+int stage_flags();
 
 // host entry points (stage_fwd_tc.cu / stage_bwd_tc.cu / wgrad_tc.cu)
 size_t stage_tc_image_bytes();

@@ -150,8 +150,9 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
 }
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);   // .x = lo (low 16 bits), .y = hi
-  return *reinterpret_cast<uint32_t*>(&v);
+  uint32_t d;   // d = {hi: bf16(hi), lo: bf16(lo)}, round to nearest even; pure register op (no address-taken temporaries)
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
 }
 
 // ---- canonical K-major operand layouts in shared memory (bf16) ----------------------------------------------

@@ -179,7 +179,9 @@ class TcEngine:
                                               1 if accumulate else 0, _stream())
         _lib.check(rc, "ab200_pv_combine_backward")
 
-    def stage_backward(self, y0, a: Sequence[torch.Tensor], cin: Combo, t: float, B: int, g_a, G_y0, G_a: Sequence[torch.Tensor]) -> None:
+    def stage_backward(self, y0, a: Sequence[torch.Tensor], cin: Combo, t: float, B: int, g_base, gx: Sequence[torch.Tensor],
+                       dp: Sequence[float], dv: Sequence[float], gx_out) -> None:
+        """dL/da_out = g_base + sum_l dp[l] gx[l].p + dv[l] gx[l].v  ->  gx_out = dL/d(stage input) (+ blobs)."""
         if self.used + self.ntiles > self.nblobs:
             self.flush()
         s = StageDesc()
@@ -188,12 +190,23 @@ class TcEngine:
         _fill(s.in_cpa, cin.cpa[:len(a)])
         _fill(s.in_cva, cin.cva[:len(a)])
         s.t = float(t)
+        n = len(gx)
+        dpa = (C.c_float * max(n, 1))(*[float(x) for x in dp])
+        dva = (C.c_float * max(n, 1))(*[float(x) for x in dv])
         rc = self.L.ab200_stage_backward(C.byref(self.desc), self.image.data_ptr(), y0.data_ptr(), C.cast(_ptr_array(a), C.c_void_p),
-                                         C.byref(s), B, g_a.data_ptr(), G_y0.data_ptr(), C.cast(_ptr_array(G_a), C.c_void_p),
-                                         self.spill.data_ptr(), self.spill.numel(), self.used, self.nblobs, self.partial.data_ptr(),
-                                         _stream())
+                                         C.byref(s), B, None if g_base is None else g_base.data_ptr(),
+                                         C.cast(_ptr_array(gx), C.c_void_p), n, C.cast(dpa, C.c_void_p), C.cast(dva, C.c_void_p),
+                                         gx_out.data_ptr(), self.spill.data_ptr(), self.spill.numel(), self.used, self.nblobs,
+                                         self.partial.data_ptr(), _stream())
         _lib.check(rc, "ab200_stage_backward")
         self.used += self.ntiles
+
+    def adjoint_gather(self, base, gx: Sequence[torch.Tensor], cpv: Sequence[float], B: int, out) -> None:
+        n = len(gx)
+        ca = (C.c_float * max(n, 1))(*[float(x) for x in cpv])
+        rc = self.L.ab200_adjoint_gather(C.byref(self.desc), base.data_ptr(), C.cast(_ptr_array(gx), C.c_void_p), n,
+                                         C.cast(ca, C.c_void_p), B, out.data_ptr(), _stream())
+        _lib.check(rc, "ab200_adjoint_gather")
 
     def flush(self) -> None:
         if self.used:
@@ -286,6 +299,20 @@ def rk4_forward(eng: TcEngine, y0: torch.Tensor, t_host: Sequence[float], save_s
     return y_path, ((yb, acc) if save_stages else None)
 
 
+def step_backward(eng: TcEngine, tab: Tableau, B: int, yn, A: Sequence[torch.Tensor], stage_times: Sequence[float], dt: float,
+                  G_y0_base, G_a_base: Sequence[Optional[torch.Tensor]], gx: Sequence[torch.Tensor], out) -> None:
+    """Adjoint of the stages of ONE explicit Runge-Kutta step (any tableau), latest stage first.  G_y0_base / G_a_base
+    hold the step-level gradients w.r.t. y0 and the stage accelerations (from the step's linear outputs); `out` receives
+    dL/dy0 of the step.  `gx[i]` is scratch for stage i's dL/d(stage input)."""
+    s = len(stage_times)
+    combos = [tab.stage_input(i, dt) for i in range(s)]
+    for i in range(s - 1, -1, -1):
+        later = [l for l in range(i + 1, s) if combos[l].cpa[i] != 0.0 or combos[l].cva[i] != 0.0]
+        eng.stage_backward(yn, [A[j] for j in range(i)], combos[i], stage_times[i], B, G_a_base[i], [gx[l] for l in later],
+                           [combos[l].cpa[i] for l in later], [combos[l].cva[i] for l in later], gx[i])
+    eng.adjoint_gather(G_y0_base, [gx[i] for i in range(s)], [combos[i].cpv for i in range(s)], B, out)
+
+
 def rk4_backward(eng: TcEngine, t_host: Sequence[float], saved, grad_y_path: torch.Tensor):
     """-> (grad_y0 row-major [B, D], grad_w_flat)."""
     yb, acc = saved
@@ -293,18 +320,17 @@ def rk4_backward(eng: TcEngine, t_host: Sequence[float], saved, grad_y_path: tor
     dev = grad_y_path.device
     eng.backward_begin(B, stages_per_flush=4)
     lam = rows_block(grad_y_path[T - 1])
+    lam_next = blocked_zeros(B, D, dev)
     G_y0 = blocked_zeros(B, D, dev)
     G_a = [blocked_zeros(B, eng.P, dev) for _ in range(4)]
+    gx = [blocked_zeros(B, D, dev) for _ in range(4)]
     for n in range(T - 2, -1, -1):
         t0, dt = float(t_host[n]), float(t_host[n + 1]) - float(t_host[n])
-        A = acc[n]
-        yn = yb[n]
         eng.combine_backward(lam, RK38.combo(RK38.b, dt), B, G_y0, G_a, accumulate=False)
-        for i in (3, 2, 1, 0):
-            t_i = float(t_host[n + 1]) if i == 3 else t0 + RK38.c[i] * dt
-            eng.stage_backward(yn, [A[j] for j in range(i)], RK38.stage_input(i, dt), t_i, B, G_a[i], G_y0, G_a[:i])
+        times = [t0, t0 + RK38.c[1] * dt, t0 + RK38.c[2] * dt, float(t_host[n + 1])]
+        step_backward(eng, RK38, B, yb[n], [acc[n][j] for j in range(3)], times, dt, G_y0, G_a, gx, lam_next)
         eng.flush()
-        rows_block(grad_y_path[n], G_y0, accumulate=True)
-        lam, G_y0 = G_y0, lam
+        rows_block(grad_y_path[n], lam_next, accumulate=True)
+        lam, lam_next = lam_next, lam
     gw = eng.backward_end()
     return rows_unblock(lam, B, D), gw

@@ -156,18 +156,25 @@ int ab200_stage_forward(const ab200_drift_desc* d, const void* image, const floa
                         const ab200_stage_desc* s, int64_t B, float* a_out, float* y_out, double* err_sumsq,
                         ab200_stream_t stream);
 /* Vector-Jacobian product of one stage = what autograd does for the ops of one `func` call inside the solver
- * (mode_sep/train/train.py:162).  g_a [B][P] is dL/da_out.  ACCUMULATES dL/d(stage input) into G_y0 [B][D] and
- * G_a[j] [B][P] (j < n_a), and writes the layer (activation, gradient) blobs of tile i to blob index blob0 + i of
- * `spill` (sized by ab200_stage_spill_bytes(nblobs)); ab200_wgrad_accumulate turns filled blobs into weight
+ * (mode_sep/train/train.py:162).  The upstream gradient is assembled in the kernel as
+ *     dL/da_out = g_base + sum_{l < n_g} dp[l] gx[l].p + dv[l] gx[l].v
+ * where g_base (blocked [Bp][P], may be NULL when n_g > 0) is the step-level part (ab200_pv_combine_backward of the
+ * step's outputs) and gx[l] (blocked [Bp][D]) are the gx_out of the LATER stages whose input used a_out with
+ * coefficients (dp[l], dv[l]) = that stage's (in_cpa, in_cva) entry for a_out.  WRITES gx_out (blocked [Bp][D]) =
+ * dL/d(stage input) = [g_p, g_v, g_h] and the layer (activation, gradient) blobs of tile i to blob index blob0 + i
+ * of `spill` (sized by ab200_stage_spill_bytes(nblobs)); ab200_wgrad_accumulate turns filled blobs into weight
  * gradients.  `partial` (ab200_wgrad_partial_bytes, ZEROED by the caller before the first stage of a backward pass)
  * holds the per-SM partial weight gradients; ab200_wgrad_finalize writes grad_w_flat (OVERWRITTEN) in
- * ab200_drift_param_count order. */
+ * ab200_drift_param_count order.  ab200_adjoint_gather folds the stages of one step into dL/dy0:
+ *     out = base + sum_l [gx[l].p ; cpv[l] gx[l].p + gx[l].v ; gx[l].h]      (cpv[l] = that stage's in_cpv). */
 size_t ab200_stage_spill_bytes(const ab200_drift_desc* d, int32_t nblobs);
 size_t ab200_wgrad_partial_bytes(const ab200_drift_desc* d);
 int ab200_stage_backward(const ab200_drift_desc* d, const void* image, const float* y0, const float* const* a,
-                         const ab200_stage_desc* s, int64_t B, const float* g_a, float* G_y0, float* const* G_a,
-                         void* spill, size_t spill_bytes, int32_t blob0, int32_t nblobs, void* partial,
-                         ab200_stream_t stream);
+                         const ab200_stage_desc* s, int64_t B, const float* g_base, const float* const* gx, int32_t n_g,
+                         const float* dp_host, const float* dv_host, float* gx_out, void* spill, size_t spill_bytes,
+                         int32_t blob0, int32_t nblobs, void* partial, ab200_stream_t stream);
+int ab200_adjoint_gather(const ab200_drift_desc* d, const float* base, const float* const* gx, int32_t n,
+                         const float* cpv_host, int64_t B, float* out, ab200_stream_t stream);
 int ab200_wgrad_accumulate(const ab200_drift_desc* d, const void* spill, int32_t nblobs, int32_t used, void* partial,
                            ab200_stream_t stream);
 int ab200_wgrad_finalize(const ab200_drift_desc* d, const void* partial, float* grad_w_flat, ab200_stream_t stream);

@@ -16,12 +16,13 @@ eng = stage.TcEngine(spec, w)
 dt = 0.25
 eng.backward_begin(B, 4)
 G_y0 = stage.blocked_zeros(B, 160, dev); G_a = [stage.blocked_zeros(B, 64, dev) for _ in range(4)]
+GX = [stage.blocked_zeros(B, 160, dev) for _ in range(4)]
 for it in range(3):
     eng.stage_forward(y0, [], stage.RK38.stage_input(0, dt), 1.0, B, a_out=aout)
     eng.stage_forward(y0, A, stage.RK38.stage_input(3, dt), 1.0, B, y_out=yout, cout=stage.RK38.combo(stage.RK38.b, dt))
     eng.used = 0
     for i in (3, 2, 1, 0):
-        eng.stage_backward(y0, A[:i], stage.RK38.stage_input(i, dt), 1.0, B, G_a[i], G_y0, G_a[:i])
+        eng.stage_backward(y0, A[:i], stage.RK38.stage_input(i, dt), 1.0, B, G_a[i], GX[i + 1:], [0.1] * (3 - i), [0.2] * (3 - i), GX[i])
     eng.flush()
 torch.cuda.synchronize()
 eng.check_status()

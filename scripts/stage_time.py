@@ -45,11 +45,12 @@ eng.backward_begin(B, 4)
 G_y0 = stage.blocked_zeros(B, 160, dev)
 G_a = [stage.blocked_zeros(B, 64, dev) for _ in range(4)]
 lam = stage.rows_block(torch.randn(B, 160, device=dev))
+GX = [stage.blocked_zeros(B, 160, dev) for _ in range(4)]
 
 
 def bwd_stage(i):
     eng.used = 0
-    eng.stage_backward(y0, A[:i], stage.RK38.stage_input(i, dt), 1.0, B, G_a[i], G_y0, G_a[:i])
+    eng.stage_backward(y0, A[:i], stage.RK38.stage_input(i, dt), 1.0, B, G_a[i], GX[i + 1:], [0.1] * (3 - i), [0.2] * (3 - i), GX[i])
 
 
 BWD_FLOP = 2 * (176 * 128 + 4 * 144 * 128) + 2 * (64 * 128 + 4 * 128 * 128 + 128 * 160)
