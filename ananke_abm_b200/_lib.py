@@ -98,7 +98,12 @@ def lib() -> C.CDLL:
     return handle
 
 
+LAUNCHES = 0     # C-ABI calls that launched kernels since the counter was last reset (bench.py reports it)
+
+
 def check(status: int, what: str) -> None:
+    global LAUNCHES
+    LAUNCHES += 1
     if status == 0:
         return
     L = lib()

@@ -136,6 +136,7 @@ def run_ours(args):
     from ananke_abm_b200 import dist as abd
     from ananke_abm_b200 import odeint as _unused  # noqa: F401
     import importlib
+    from ananke_abm_b200 import _lib
     oi = importlib.import_module("ananke_abm_b200.odeint")
 
     rank = int(os.environ.get("RANK", "0"))
@@ -230,29 +231,73 @@ def run_ours(args):
     ms = timed(lambda: hot_step(d_home, d_work, d_traits, d_t), args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
 
-    # kernel-only time of the dominant kernel (fused RK4 trajectory): raw C-ABI launches into preallocated buffers,
-    # CUDA events on the launching stream, no allocation or host sync between launches
+    # kernel-only time of the dominant kernel: raw C-ABI launches into preallocated buffers, CUDA events on the
+    # launching stream, no allocation or host sync between launches
     n_chunks = (B + chunk - 1) // chunk
+    tc_train = train and args.precision == "bf16"
     with torch.no_grad():
         table, zemb = model.zone_tables(zfeat, csr)
         y0 = model.initial_state(table, zemb, d_home[:chunk], d_work[:chunk], d_traits[:chunk]).contiguous()
         spec = ab.describe_drift(model.odefunc)
         wflat = spec.flat_params().detach().contiguous()
-        prec = {"f32": 0, "bf16": 1}[args.precision]
-        ybuf = torch.empty((T, y0.shape[0], y0.shape[1]), dtype=torch.float32, device=dev)
-        wsb = oi.rk4_workspace(spec, y0.shape[0], T, prec, dev)
-        for _ in range(3):
-            oi.rk4_forward_into(spec, wflat, y0, d_t, ybuf, wsb, prec)
-        torch.cuda.synchronize()
-        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         reps = 5
-        k0.record()
-        for _ in range(reps):
-            oi.rk4_forward_into(spec, wflat, y0, d_t, ybuf, wsb, prec)
-        k1.record()
-        torch.cuda.synchronize()
-        kern_ms = k0.elapsed_time(k1) / reps
-        del ybuf
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if tc_train:
+            # backward stage kernel (stage_bwd_tc_kernel): 4 launches per solver step, the largest share of a training step
+            from ananke_abm_b200 import stage as st
+            Bc = y0.shape[0]
+            eng = st.TcEngine(spec, wflat)
+            eng.backward_begin(Bc, 4)
+            yb = st.rows_block(y0)
+            A = [st.rows_block(torch.randn(Bc, 64, device=dev) * 0.1) for _ in range(3)]
+            Gb = st.rows_block(torch.randn(Bc, 64, device=dev) * 1e-3)
+            GX = [st.blocked_zeros(Bc, 160, dev) for _ in range(4)]
+            dtk = 0.25
+            combos = [st.RK38.stage_input(i, dtk) for i in range(4)]
+
+            def one_step_bwd_stages():
+                eng.used = 0
+                for i in (3, 2, 1, 0):
+                    later = list(range(i + 1, 4))
+                    eng.stage_backward(yb, A[:i], combos[i], 1.0, Bc, Gb, [GX[l] for l in later], [combos[l].cpa[i] for l in later],
+                                       [combos[l].cva[i] for l in later], GX[i])
+            for _ in range(3):
+                one_step_bwd_stages()
+            torch.cuda.synchronize()
+            k0.record()
+            for _ in range(reps):
+                one_step_bwd_stages()
+            k1.record()
+            torch.cuda.synchronize()
+            eng.check_status()
+            kern_ms = k0.elapsed_time(k1) / (reps * 4)
+            kern_units = Bc                      # agent-stage evaluations per launch
+            kern_name = "stage_bwd_tc_kernel (one Runge-Kutta stage: recompute + dgrad + blob spill)"
+            kern_flop_unit = ALG_FLOP_FWD // 4 * 2    # recompute + dgrad of one stage (wgrad runs in wgrad_tc_kernel)
+            kern_bytes_unit = ALG_BYTES_FWDBWD / 4.0
+            del eng, yb, A, Gb, GX
+        else:
+            prec = {"f32": 0, "bf16": 1}[args.precision]
+            ybuf = torch.empty((T, y0.shape[0], y0.shape[1]), dtype=torch.float32, device=dev)
+            wsb = oi.rk4_workspace(spec, y0.shape[0], T, prec, dev)
+            for _ in range(3):
+                oi.rk4_forward_into(spec, wflat, y0, d_t, ybuf, wsb, prec)
+            torch.cuda.synchronize()
+            k0.record()
+            for _ in range(reps):
+                oi.rk4_forward_into(spec, wflat, y0, d_t, ybuf, wsb, prec)
+            k1.record()
+            torch.cuda.synchronize()
+            kern_ms = k0.elapsed_time(k1) / reps
+            kern_units = y0.shape[0] * (T - 1)   # agent-steps per launch
+            kern_name = "rk4 fused trajectory (forward), %s" % ("rk4_tc_kernel" if prec == 1 else "rk4_f32_kernel")
+            kern_flop_unit = ALG_FLOP_FWD
+            kern_bytes_unit = ALG_BYTES_FWD
+            del ybuf
+    _lib.LAUNCHES = 0
+    hot_step(d_home, d_work, d_traits, d_t)
+    torch.cuda.synchronize()
+    launches_per_step = _lib.LAUNCHES
     e2e_ms = timed(e2e_step, max(1, min(args.steps, 3)), 1)
     e2e_steps = max(1, min(args.steps, 3))
 
@@ -264,9 +309,9 @@ def run_ours(args):
     agent_steps = B * (T - 1)
     value = world * agent_steps * args.steps / (ms * 1e-3)
     e2e_value = world * agent_steps * e2e_steps / (e2e_ms * 1e-3)
-    flops_kernel = chunk * (T - 1) * ALG_FLOP_FWD
+    flops_kernel = kern_units * kern_flop_unit
     achieved_tf = flops_kernel / (kern_ms * 1e-3) / 1e12
-    bytes_kernel = chunk * (T - 1) * ALG_BYTES_FWD
+    bytes_kernel = kern_units * kern_bytes_unit
     h2d = sum(x.numel() * x.element_size() for x in (h_home, h_work, h_traits, h_t))
     d2h = (B * T * 4) if not train else 4
     out = {
@@ -279,12 +324,14 @@ def run_ours(args):
                    "l2": "trajectory rows written per step (%.0f MB) exceed L2; weights are L2-resident by design" % (chunk * T * 640 / 1e6)},
         "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": pk["tf_burst"], "unit": "TFLOP/s",
                      "frac": achieved_tf / pk["tf_burst"], "traffic": None, "peak_source": pk["src"],
-                     "kernel": "rk4 fused trajectory (forward)", "kernel_ms": kern_ms,
-                     "alg_flop_per_agent_step": ALG_FLOP_FWD, "alg_bytes_per_agent_step": ALG_BYTES_FWD,
+                     "kernel": kern_name, "kernel_ms": kern_ms, "units_per_launch": kern_units,
+                     "alg_flop_per_unit": kern_flop_unit, "alg_bytes_per_unit": kern_bytes_unit,
+                     "alg_flop_per_agent_step": ALG_FLOP_FWDBWD if train else ALG_FLOP_FWD,
+                     "alg_bytes_per_agent_step": ALG_BYTES_FWDBWD if train else ALG_BYTES_FWD,
                      "hbm_achieved_gbs": bytes_kernel / (kern_ms * 1e-3) / 1e9, "hbm_peak_gbs": pk["hbm"]},
         "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / e2e_steps},
-        "gpu_launches": args.steps * n_chunks * (2 if not train else 7),
+        "gpu_launches": args.steps * launches_per_step,
         "clocks": clocks,
     }
     if not args.no_cpu_baseline:
@@ -349,11 +396,11 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--precision", default="f32", choices=["f32", "bf16"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="bf16", choices=["f32", "bf16"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--agents", type=int, default=0, help="override agents per GPU")
-    ap.add_argument("--chunk", type=int, default=262_144, help="agents per fused launch")
+    ap.add_argument("--chunk", type=int, default=131_072, help="agents per fused launch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
