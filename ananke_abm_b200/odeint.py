@@ -151,6 +151,31 @@ class _StageRK4TC(torch.autograd.Function):
         return gy0, None, gw, None, None
 
 
+class _StageDopri5TC(torch.autograd.Function):
+    """dopri5 on the tensor-core STAGE kernels: adaptive forward with dense output, discrete adjoint of the accepted
+    steps in backward (what autograd through torchdiffeq's solver ops computes; the step-size controller is constant,
+    as it runs under no_grad there)."""
+
+    @staticmethod
+    def forward(ctx, y0, t, w_flat, spec: DriftSpec, t_host, rtol, atol, opts):
+        from . import stage
+        eng = stage.TcEngine(spec, w_flat)
+        th = [float(v) for v in t_host.tolist()]
+        need = torch.is_grad_enabled() or y0.requires_grad or w_flat.requires_grad
+        stats = stage.Dopri5Stats()
+        y_path, steps, _ = stage.dopri5_forward(eng, y0.contiguous().float(), th, rtol, atol, save_steps=need, stats=stats, **opts)
+        ctx.eng, ctx.steps = eng, steps
+        _LAST["solver"] = stats
+        return y_path
+
+    @staticmethod
+    def backward(ctx, grad_y_path):
+        from . import stage
+        gy0, gw = stage.dopri5_backward(ctx.eng, ctx.steps, grad_y_path.contiguous().float())
+        ctx.steps = None
+        return gy0, None, gw, None, None, None, None, None
+
+
 def drift_eval(spec: DriftSpec, w_flat: torch.Tensor, t: float, y: torch.Tensor, precision: int = 0) -> torch.Tensor:
     """One evaluation f(t, y) of a recognised drift net on the CUDA path (no autograd)."""
     L = _lib.lib()
@@ -396,6 +421,22 @@ def odeint(func, y0, t, *, rtol: float = 1e-7, atol: float = 1e-9, method: Optio
         th = -t_host if decreasing else t_host
         return _rk4_generic(f, y0, tt.to(y0.dtype), th)
     if method == "dopri5":
+        if (spec is not None and y0.shape[1] == spec.state_dim and precision == _lib.PREC_BF16 and spec.tc_stage_supported()
+                and y0.dtype == torch.float32):
+            opts = {}
+            for k_ in ("first_step", "safety", "ifactor", "dfactor", "max_num_steps"):
+                if k_ in options:
+                    opts[k_] = options.pop(k_)
+            opts["time_dtype"] = torch.promote_types(options.pop("dtype", torch.float64), torch.float32)
+            options.pop("norm", None)
+            if options:
+                warnings.warn(f"dopri5: Unexpected arguments {options}")
+            w_flat = spec.flat_params()
+            needs_grad = torch.is_grad_enabled() and (y0.requires_grad or w_flat.requires_grad)
+            if needs_grad:
+                return _StageDopri5TC.apply(y0, t, w_flat, spec, t_host, float(rtol), float(atol), opts)
+            with torch.no_grad():
+                return _StageDopri5TC.apply(y0, t, w_flat.detach(), spec, t_host, float(rtol), float(atol), opts)
         if spec is not None and y0.shape[1] == spec.state_dim and not torch.is_grad_enabled():
             w_flat = spec.flat_params().detach()
             f = lambda tt, yy: drift_eval(spec, w_flat, float(tt), yy, _lib.PREC_F32)   # noqa: E731

@@ -334,3 +334,152 @@ def rk4_backward(eng: TcEngine, t_host: Sequence[float], saved, grad_y_path: tor
         lam, lam_next = lam_next, lam
     gw = eng.backward_end()
     return rows_unblock(lam, B, D), gw
+
+
+# --------------------------------------------------------------------------------------------------------
+# adaptive dopri5 (torchdiffeq dopri5.py + rk_common.py RKAdaptiveStepsizeODESolver) with the discrete adjoint
+# --------------------------------------------------------------------------------------------------------
+@dataclass
+class _Dopri5Step:
+    yb: torch.Tensor                 # blocked state at the start of the accepted step
+    A: List[torch.Tensor]            # blocked a_1..a_7 of the step (a_7 = FSAL evaluation at the step's end)
+    t0: float
+    dt: float
+    outputs: List                    # [(row index k into y_path, x = (t_k - t0) / dt)]
+
+
+class Dopri5Stats:
+    def __init__(self):
+        self.n_accepted = self.n_rejected = self.n_evals = 0
+
+
+def _cast_time(v: float, time_dtype) -> float:
+    if time_dtype == torch.float32:
+        return float(torch.tensor(v, dtype=torch.float32))
+    return float(v)
+
+
+def dopri5_forward(eng: TcEngine, y0: torch.Tensor, t_host: Sequence[float], rtol: float, atol: float, *, first_step=None,
+                   safety: float = 0.9, ifactor: float = 10.0, dfactor: float = 0.2, max_num_steps: int = 2 ** 31 - 1,
+                   time_dtype=torch.float64, save_steps: bool = False, stats: Optional[Dopri5Stats] = None):
+    """y0 row-major [B, D] -> y_path [T, B, D] (dense output at the requested times), and the accepted steps when
+    `save_steps`.  One host read of the squared-error sum per attempted step decides accept / reject."""
+    B, T = y0.shape[0], len(t_host)
+    dev = y0.device
+    D, P = eng.D, eng.P
+    stats = stats if stats is not None else Dopri5Stats()
+    ts = [_cast_time(float(v), time_dtype) for v in t_host]
+    y_path = torch.empty((T, B, D), dtype=torch.float32, device=dev)
+    y_path[0].copy_(y0)
+    y_cur = rows_block(y0)
+    y_next = blocked_zeros(B, D, dev)
+    A = [blocked_zeros(B, P, dev) for _ in range(7)]
+    out_b = blocked_zeros(B, D, dev)
+    sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
+    zero = Combo(0.0, [], [])
+    eng.stage_forward(y_cur, [], zero, ts[0], B, a_out=A[0])
+    stats.n_evals += 1
+
+    # ---- initial step size (torchdiffeq misc.py _select_initial_step; Hairer, Norsett & Wanner II.4)
+    if first_step is None:
+        def rms(x):
+            return float(x.double().pow(2).mean().sqrt())
+        y0f = y0.float()
+        f0 = torch.cat([y0f[:, P:2 * P], rows_unblock(A[0], B, P), torch.zeros(B, D - 2 * P, device=dev)], dim=1)
+        scale = atol + y0f.abs() * rtol
+        d0, d1 = rms(y0f / scale), rms(f0 / scale)
+        h0 = 1e-6 if (d0 < 1e-5 or d1 < 1e-5) else 0.01 * d0 / d1
+        eng.stage_forward(y_cur, [A[0]], Combo(h0, [0.0], [h0]), _cast_time(ts[0] + h0, time_dtype), B, a_out=A[1])
+        stats.n_evals += 1
+        f1 = torch.cat([y0f[:, P:2 * P] + h0 * f0[:, P:2 * P], rows_unblock(A[1], B, P), torch.zeros(B, D - 2 * P, device=dev)], dim=1)
+        d2 = rms((f1 - f0) / scale) / h0
+        h1 = max(1e-6, h0 * 1e-3) if (d1 <= 1e-15 and d2 <= 1e-15) else (0.01 / max(d1, d2)) ** (1.0 / 5.0)
+        dt = _cast_time(min(100 * h0, h1), time_dtype)
+    else:
+        dt = _cast_time(float(first_step), time_dtype)
+
+    steps: List[_Dopri5Step] = []
+    t0 = t1 = ts[0]
+    k = 1
+    n_steps = 0
+    c_sol, c_err = DOPRI5.b, DOPRI5.b_err
+    while k < T:
+        # ---- one attempted step from t1 with size dt
+        assert n_steps < max_num_steps, "max_num_steps exceeded ({}>={})".format(n_steps, max_num_steps)
+        assert _cast_time(t1 + dt, time_dtype) > t1, "underflow in dt {}".format(dt)
+        ta = t1
+        tb = _cast_time(ta + dt, time_dtype)
+        for i in range(1, 6):
+            eng.stage_forward(y_cur, A[:i], DOPRI5.stage_input(i, dt), _cast_time(ta + DOPRI5.c[i] * dt, time_dtype), B, a_out=A[i])
+        sumsq.zero_()
+        eng.stage_forward(y_cur, A[:6], DOPRI5.stage_input(6, dt), tb, B, a_out=A[6], y_out=y_next, cout=DOPRI5.combo(c_sol, dt),
+                          err_sumsq=sumsq, cerr=DOPRI5.combo(c_err, dt), rtol=rtol, atol=atol)
+        stats.n_evals += 6
+        ratio = float(torch.sqrt(sumsq[0] / (B * D)))
+        n_steps += 1
+        if ratio <= 1.0:
+            stats.n_accepted += 1
+            outs = []
+            while k < T and ts[k] <= tb:
+                x = (ts[k] - ta) / (tb - ta)
+                eng.combine(y_cur, A, DOPRI5.combo(dopri5_interp_weights(x), dt), B, out_b)
+                rows_unblock(out_b, B, D, out=y_path[k])
+                outs.append((k, x))
+                k += 1
+            if save_steps:
+                steps.append(_Dopri5Step(y_cur, A, ta, dt, outs))
+                y_cur, y_next = y_next, blocked_zeros(B, D, dev)
+                A = [A[6]] + [blocked_zeros(B, P, dev) for _ in range(6)]
+            else:
+                y_cur, y_next = y_next, y_cur
+                A[0], A[6] = A[6], A[0]
+            t0, t1 = ta, tb
+        else:
+            stats.n_rejected += 1
+        # ---- next step size (misc.py _optimal_step_size)
+        if ratio == 0.0:
+            dt = _cast_time(dt * ifactor, time_dtype)
+        else:
+            dfac = 1.0 if ratio < 1.0 else dfactor
+            dt = _cast_time(dt * min(ifactor, max(safety / ratio ** 0.2, dfac)), time_dtype)
+    return y_path, (steps if save_steps else None), stats
+
+
+def dopri5_backward(eng: TcEngine, steps: List[_Dopri5Step], grad_y_path: torch.Tensor):
+    """Discrete adjoint of the accepted steps (step sizes are constants, as in torchdiffeq where the controller runs
+    under no_grad) -> (grad_y0 row-major, grad_w_flat).  The FSAL evaluation is differentiated where it is used: as
+    stage 1 of the following step and, when a dense-output row needs k_7, as stage 7 of its own step."""
+    T, B, D = grad_y_path.shape
+    dev = grad_y_path.device
+    P = eng.P
+    eng.backward_begin(B, stages_per_flush=7)
+    lam = blocked_zeros(B, D, dev)          # dL/dy at the end of the step being processed
+    lam_prev = blocked_zeros(B, D, dev)
+    G_y0 = blocked_zeros(B, D, dev)
+    G_a = [blocked_zeros(B, P, dev) for _ in range(7)]
+    gx = [blocked_zeros(B, D, dev) for _ in range(7)]
+    g_blk = blocked_zeros(B, D, dev)
+    for st in reversed(steps):
+        dt = st.dt
+        # step-level gradients: the end state y1 = y0 + dt sum c_sol k, and every dense-output row inside the step
+        eng.combine_backward(lam, DOPRI5.combo(DOPRI5.b, dt), B, G_y0, G_a, accumulate=False)
+        for (k, x) in st.outputs:
+            rows_block(grad_y_path[k], g_blk)
+            eng.combine_backward(g_blk, DOPRI5.combo(dopri5_interp_weights(x), dt), B, G_y0, G_a, accumulate=True)
+        n_stage = 7 if st.outputs else 6      # without dense output nothing depends on k_7 inside this step
+        times = [st.t0 + DOPRI5.c[i] * dt for i in range(n_stage)]
+        _step_backward_n(eng, DOPRI5, B, st.yb, st.A, times, dt, G_y0, G_a, gx, lam_prev, n_stage)
+        eng.flush()
+        lam, lam_prev = lam_prev, lam
+    rows_block(grad_y_path[0], lam, accumulate=True)
+    gw = eng.backward_end()
+    return rows_unblock(lam, B, D), gw
+
+
+def _step_backward_n(eng, tab, B, yn, A, stage_times, dt, G_y0_base, G_a_base, gx, out, n_stage):
+    combos = [tab.stage_input(i, dt) for i in range(n_stage)]
+    for i in range(n_stage - 1, -1, -1):
+        later = [l for l in range(i + 1, n_stage) if combos[l].cpa[i] != 0.0 or combos[l].cva[i] != 0.0]
+        eng.stage_backward(yn, [A[j] for j in range(i)], combos[i], stage_times[i], B, G_a_base[i], [gx[l] for l in later],
+                           [combos[l].cpa[i] for l in later], [combos[l].cva[i] for l in later], gx[i])
+    eng.adjoint_gather(G_y0_base, [gx[i] for i in range(n_stage)], [combos[i].cpv for i in range(n_stage)], B, out)

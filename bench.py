@@ -114,6 +114,7 @@ def build_model(cfg, precision, device):
     torch.manual_seed(42)
     mc = ab.ModeSepConfig()
     mc.precision = precision
+    mc.ode_method = cfg["method"]            # rtol = atol = 1e-5 (mode_sep/config.py:27-28) apply to dopri5 only
     model = ab.GATODEModel(7, mc, heads=cfg["heads"]).to(device)
     ei, feats = synthetic_zone_graph(cfg["Z"], k=6, seed=42)
     csr = ab.build_zone_csr(ei, cfg["Z"]).to(device)
@@ -149,6 +150,9 @@ def run_ours(args):
     cfg = dict(WORKLOADS[args.workload])
     if args.agents:
         cfg["B"] = args.agents
+    if args.solver:
+        cfg["method"] = args.solver
+        cfg["name"] = cfg["name"].replace("96 RK4 steps", "dopri5 rtol=atol=1e-5" if args.solver == "dopri5" else "96 RK4 steps")
     train = cfg["mode"] == "train"
     chunk = min(cfg["B"], args.chunk)
     B, T = cfg["B"], cfg["T"]
@@ -159,6 +163,19 @@ def run_ours(args):
     d_home, d_work, d_traits, d_t = (x.to(dev) for x in (home, work, traits, t))
     params = [p for p in model.parameters()]
 
+    adaptive = cfg["method"] == "dopri5"
+    counter = {"agent_steps": 0, "accepted": 0, "rejected": 0}
+
+    def count(nb):
+        """agent-steps of the chunk just integrated: grid intervals for rk4, ACCEPTED steps for dopri5"""
+        if adaptive:
+            st = oi._LAST["solver"]
+            counter["agent_steps"] += nb * st.n_accepted
+            counter["accepted"] += st.n_accepted
+            counter["rejected"] += st.n_rejected
+        else:
+            counter["agent_steps"] += nb * (T - 1)
+
     def hot_step(hm, wk, tr, tt):
         """device-resident pass over all agents of this rank; returns a small device tensor"""
         if not train:
@@ -168,6 +185,7 @@ def run_ours(args):
                 for s in range(0, B, chunk):
                     y0 = model.initial_state(table, zemb, hm[s:s + chunk], wk[s:s + chunk], tr[s:s + chunk])
                     y_path = model.integrate(y0, tt)
+                    count(y0.shape[0])
                     acc = y_path[-1, :1, :1]
                     del y_path
                 return acc
@@ -178,6 +196,7 @@ def run_ours(args):
             table, zemb = model.zone_tables(zfeat, csr)
             y0 = model.initial_state(table, zemb, hm[s:s + chunk], wk[s:s + chunk], tr[s:s + chunk])
             y_path = model.integrate(y0, tt)
+            count(y0.shape[0])
             loss = (y_path[:, :, :128] ** 2).mean() * (min(B, s + chunk) - s) / B
             loss.backward()
             total = loss.detach() if total is None else total + loss.detach()
@@ -196,6 +215,7 @@ def run_ours(args):
                 for s in range(0, B, chunk):
                     y0 = model.initial_state(table, zemb, hm[s:s + chunk], wk[s:s + chunk], tr[s:s + chunk])
                     y_path = model.integrate(y0, tt)
+                    count(y0.shape[0])
                     outs.append(labels_from_path(model, y_path, table).to(torch.int32))
                     del y_path
                 res = torch.cat(outs, dim=0)
@@ -212,6 +232,7 @@ def run_ours(args):
         for _ in range(warmup):
             fn()
         barrier()
+        counter.update(agent_steps=0, accepted=0, rejected=0)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
@@ -230,6 +251,7 @@ def run_ours(args):
         sampler.start()
     ms = timed(lambda: hot_step(d_home, d_work, d_traits, d_t), args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
+    steps_counted = dict(counter)
 
     # kernel-only time of the dominant kernel: raw C-ABI launches into preallocated buffers, CUDA events on the
     # launching stream, no allocation or host sync between launches
@@ -300,15 +322,15 @@ def run_ours(args):
     launches_per_step = _lib.LAUNCHES
     e2e_ms = timed(e2e_step, max(1, min(args.steps, 3)), 1)
     e2e_steps = max(1, min(args.steps, 3))
+    e2e_counted = dict(counter)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     pk = peaks()
-    agent_steps = B * (T - 1)
-    value = world * agent_steps * args.steps / (ms * 1e-3)
-    e2e_value = world * agent_steps * e2e_steps / (e2e_ms * 1e-3)
+    value = world * steps_counted["agent_steps"] / (ms * 1e-3)          # every rank runs the same workload (weak scaling)
+    e2e_value = world * e2e_counted["agent_steps"] / (e2e_ms * 1e-3)
     flops_kernel = kern_units * kern_flop_unit
     achieved_tf = flops_kernel / (kern_ms * 1e-3) / 1e12
     bytes_kernel = kern_units * kern_bytes_unit
@@ -321,6 +343,9 @@ def run_ours(args):
         "dtype": "f32" if args.precision == "f32" else "bf16 (fp32 accumulate, fp32 state)", "data": "synthetic",
         "config": {"workload": cfg["name"], "agents_per_gpu": B, "zones": cfg["Z"], "time_points": T, "solver": cfg["method"],
                    "agent_chunk": chunk, "precision": args.precision,
+                   "solver_steps": ({"accepted_per_trajectory": steps_counted["accepted"] / max(1, args.steps * ((B + chunk - 1) // chunk)),
+                                     "rejected_per_trajectory": steps_counted["rejected"] / max(1, args.steps * ((B + chunk - 1) // chunk)),
+                                     "rtol": model.config.rtol, "atol": model.config.atol} if adaptive else {"grid_intervals": T - 1}),
                    "l2": "trajectory rows written per step (%.0f MB) exceed L2; weights are L2-resident by design" % (chunk * T * 640 / 1e6)},
         "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": pk["tf_burst"], "unit": "TFLOP/s",
                      "frac": achieved_tf / pk["tf_burst"], "traffic": None, "peak_source": pk["src"],
@@ -347,30 +372,35 @@ def cpu_baseline(cfg, train, budget_s=20.0, steps=1, warmup=0):
     from oracle import torchdiffeq_oracle as tdq
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    adaptive = cfg["method"] == "dopri5"
     Bs = min(cfg["B"], 10_000 if not train else 2_000)
-    Ts = cfg["T"] if not train else min(cfg["T"], 25)
+    Ts = cfg["T"] if (not train or adaptive) else min(cfg["T"], 25)
     sub = dict(cfg, B=Bs, T=Ts)
     home, work, traits, _ = make_inputs(sub)
     t = torch.linspace(0.0, 24.0, cfg["T"])[:Ts]
     torch.manual_seed(42)
     m = mo.OracleModeSep(cfg["Z"])
-    best = None
+    kw = dict(method="dopri5", rtol=1e-5, atol=1e-5) if adaptive else dict(method="rk4")
+    best, n_steps = None, Ts - 1
     for it in range(warmup + steps):
         t0 = time.perf_counter()
         if not train:
             with torch.no_grad():
                 y0 = m.initial_state(home, work, traits)
-                tdq.odeint(m.rhs, y0, t, method="rk4")
+                tdq.odeint(m.rhs, y0, t, **kw)
         else:
             m.zero_grad()
             y0 = m.initial_state(home, work, traits)
-            yp = tdq.odeint(m.rhs, y0, t, method="rk4")
+            yp = tdq.odeint(m.rhs, y0, t, **kw)
             (yp[:, :, :128] ** 2).mean().backward()
         dt = time.perf_counter() - t0
+        if adaptive:
+            n_steps = sum(1 for (_, _, ok) in tdq._LAST_SOLVER["solver"].step_log if ok)
         if it >= warmup:
             best = dt if best is None else min(best, dt)
-    return {"value": Bs * (Ts - 1) / best, "unit": "agent-steps/s", "cores": cores, "kind": "port",
-            "sample": f"{Bs} agents x {Ts - 1} rk4 steps of the same workload ({'fwd+bwd' if train else 'fwd'}), "
+    what = f"{n_steps} accepted dopri5 steps (rtol=atol=1e-5)" if adaptive else f"{Ts - 1} rk4 steps"
+    return {"value": Bs * n_steps / best, "unit": "agent-steps/s", "cores": cores, "kind": "port",
+            "sample": f"{Bs} agents x {what} of the same workload ({'fwd+bwd' if train else 'fwd'}), "
                       f"torch CPU fp32, {cores} threads, best of {steps}", "seconds": best}
 
 
@@ -379,6 +409,11 @@ def run_reference(args):
     if rank != 0:
         return
     cfg = dict(WORKLOADS[args.workload])
+    if args.agents:
+        cfg["B"] = args.agents
+    if args.solver:
+        cfg["method"] = args.solver
+        cfg["name"] = cfg["name"].replace("96 RK4 steps", "dopri5 rtol=atol=1e-5" if args.solver == "dopri5" else "96 RK4 steps")
     train = cfg["mode"] == "train"
     t0 = time.perf_counter()
     cb = cpu_baseline(cfg, train, steps=max(1, min(args.steps, 3)), warmup=1 if args.warmup else 0)
@@ -401,6 +436,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--agents", type=int, default=0, help="override agents per GPU")
     ap.add_argument("--chunk", type=int, default=131_072, help="agents per fused launch")
+    ap.add_argument("--solver", default="", choices=["", "rk4", "dopri5"], help="override the workload's solver")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
