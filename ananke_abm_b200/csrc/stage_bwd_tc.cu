@@ -120,6 +120,20 @@ __global__ void __launch_bounds__(THREADS, 1) stage_bwd_tc_kernel(const __grid_c
   for (int tile = blockIdx.x * NSLOT + c.slot; tile < a.ntiles; tile += gridDim.x * NSLOT) {
     const bool valid = (int64_t)tile * TM + c.row < a.B;      // padding rows: zeros in, nothing stored
     const int blob = a.blob0 + tile;
+    if (a.flags & 4) {   // per-line prefetch of exactly the rows this thread will read in its next tile
+      const int nt = tile + gridDim.x * NSLOT;
+      if (nt < a.ntiles) {
+        prefetch_rows_l2(a.y0, nt, YF4, c.hf * 8, 8, c.row);
+        prefetch_rows_l2(a.y0, nt, YF4, AF4 + c.hf * 8, 8, c.row);
+        prefetch_rows_l2(a.y0, nt, YF4, 2 * AF4 + c.hf * 4, 4, c.row);
+        for (int s = 0; s < a.n_a; ++s) prefetch_rows_l2(a.a[s], nt, AF4, c.hf * 8, 8, c.row);
+        if (a.g_base != nullptr) prefetch_rows_l2(a.g_base, nt, AF4, c.hf * 8, 8, c.row);
+        for (int s = 0; s < a.n_g; ++s) {
+          prefetch_rows_l2(a.gx[s], nt, YF4, c.hf * 8, 8, c.row);
+          prefetch_rows_l2(a.gx[s], nt, YF4, AF4 + c.hf * 8, 8, c.row);
+        }
+      }
+    }
     if (c.stid == 0 && (a.flags & 2)) {   // next tile of this slot -> L2 while this one computes
       const int nt = tile + gridDim.x * NSLOT;
       if (nt < a.ntiles) {
@@ -144,9 +158,9 @@ __global__ void __launch_bounds__(THREADS, 1) stage_bwd_tc_kernel(const __grid_c
         pin[4 * j + 2] = pv.z + a.in.cpv * vv.z; pin[4 * j + 3] = pv.w + a.in.cpv * vv.w;
         vin[4 * j] = vv.x; vin[4 * j + 1] = vv.y; vin[4 * j + 2] = vv.z; vin[4 * j + 3] = vv.w;
       }
-#pragma unroll
-      for (int s = 0; s < MAX_A; ++s) {
-        if (s < a.n_a) {
+#pragma unroll 1
+      for (int s = 0; s < a.n_a; ++s) {
+        {
           const float cp = a.in.cpa[s], cv = a.in.cva[s];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -188,15 +202,15 @@ __global__ void __launch_bounds__(THREADS, 1) stage_bwd_tc_kernel(const __grid_c
     // ---- forward recompute (hidden layers only), masks + blobs
     uint32_t z[32];
     uint32_t m_z0[2], m_u0[2], m_z1[2], m_u1[2], m_z2[2];
-    run_layer<false, (2 * P + H) / 16, true, HID, HID>(c, C_ACT, OFF_W1);
+    run_layer<false, (2 * P + H) / 16, true, HID, HID, true>(c, C_ACT, OFF_W1);
     bwd_fwd_epi<false, true>(c, z, m_z0, a.spill + S.act(0, blob));
-    run_layer<false, HID / 16, true, HID, HID>(c, C_ACT, off_hh(0));
+    run_layer<false, HID / 16, true, HID, HID, true>(c, C_ACT, off_hh(0));
     bwd_fwd_epi<false, false>(c, z, m_u0, a.spill + S.act(1, blob));
-    run_layer<false, HID / 16, true, HID, HID>(c, C_ACT, off_hh(1));
+    run_layer<false, HID / 16, true, HID, HID, true>(c, C_ACT, off_hh(1));
     bwd_fwd_epi<true, true>(c, z, m_z1, a.spill + S.act(2, blob));
-    run_layer<false, HID / 16, true, HID, HID>(c, C_ACT, off_hh(2));
+    run_layer<false, HID / 16, true, HID, HID, true>(c, C_ACT, off_hh(2));
     bwd_fwd_epi<false, false>(c, z, m_u1, a.spill + S.act(3, blob));
-    run_layer<false, HID / 16, true, HID, HID>(c, C_ACT, off_hh(3));
+    run_layer<false, HID / 16, true, HID, HID, true>(c, C_ACT, off_hh(3));
     bwd_fwd_epi<true, false, false>(c, z, m_z2, a.spill + S.act(4, blob));
 
     // ---- upstream gradient of the output layer -> ACT (K = 64) + gO blob + bias column sums
@@ -207,9 +221,9 @@ __global__ void __launch_bounds__(THREADS, 1) stage_bwd_tc_kernel(const __grid_c
       for (int j = 0; j < 8; ++j) {
         float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
         if (a.g_base != nullptr) x = ldro(blk4(a.g_base, tile, AF4, c.hf * 8 + j, c.row));     // padding rows are zero
-#pragma unroll
-        for (int s = 0; s < MAX_A; ++s) {
-          if (s < a.n_g) {
+#pragma unroll 1
+        for (int s = 0; s < a.n_g; ++s) {
+          {
             const float4 gp = ldro(blk4(a.gx[s], tile, YF4, c.hf * 8 + j, c.row));
             const float4 gq = ldro(blk4(a.gx[s], tile, YF4, AF4 + c.hf * 8 + j, c.row));
             const float dp = a.dp[s], dv = a.dv[s];
@@ -237,23 +251,23 @@ __global__ void __launch_bounds__(THREADS, 1) stage_bwd_tc_kernel(const __grid_c
     }
 
     // ---- backward through the net (dgrad GEMMs on the MN-major view of the weight image)
-    run_layer<true, P / 16, false, P, HID>(c, C_ACT, OFF_WO);                       // g_z2 = gO W_O
+    run_layer<true, P / 16, false, P, HID, true>(c, C_ACT, OFF_WO);                       // g_z2 = gO W_O
     bwd_bwd_epi<false, true>(c, z, m_z2, a.spill + S.grad(4, blob));                // gB1 = g_z2 * [z2 > 0]  (skip -> z)
-    run_layer<true, HID / 16, false, HID, HID>(c, C_ACT, off_hh(3));                // g_u1 = gB1 W_B1
+    run_layer<true, HID / 16, false, HID, HID, true>(c, C_ACT, off_hh(3));                // g_u1 = gB1 W_B1
     {
       uint32_t dummy[32];
       bwd_bwd_epi<false, false>(c, dummy, m_u1, a.spill + S.grad(3, blob));         // gA1
     }
-    run_layer<true, HID / 16, false, HID, HID>(c, C_ACT, off_hh(2));                // gA1 W_A1 (+ skip)
+    run_layer<true, HID / 16, false, HID, HID, true>(c, C_ACT, off_hh(2));                // gA1 W_A1 (+ skip)
     bwd_bwd_epi<true, true>(c, z, m_z1, a.spill + S.grad(2, blob));                 // gB0
-    run_layer<true, HID / 16, false, HID, HID>(c, C_ACT, off_hh(1));
+    run_layer<true, HID / 16, false, HID, HID, true>(c, C_ACT, off_hh(1));
     {
       uint32_t dummy[32];
       bwd_bwd_epi<false, false>(c, dummy, m_u0, a.spill + S.grad(1, blob));         // gA0
     }
-    run_layer<true, HID / 16, false, HID, HID>(c, C_ACT, off_hh(0));
+    run_layer<true, HID / 16, false, HID, HID, true>(c, C_ACT, off_hh(0));
     bwd_bwd_epi<true, false>(c, z, m_z0, a.spill + S.grad(0, blob));                // g1
-    run_layer<true, HID / 16, false, HID, 2 * P + H>(c, C_ACT, OFF_W1);             // g_x[128 x 160] = g1 W_1[:, :160]
+    run_layer<true, HID / 16, false, HID, 2 * P + H, true>(c, C_ACT, OFF_W1);             // g_x[128 x 160] = g1 W_1[:, :160]
 
     // ---- dL/d(stage input) -> gx_out (tcgen05.ld is warp-collective: issued by every lane; only lanes that own a real
     //      agent store)

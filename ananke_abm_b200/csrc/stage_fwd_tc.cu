@@ -119,6 +119,15 @@ __global__ void __launch_bounds__(THREADS, 1) stage_fwd_tc_kernel(const __grid_c
   for (int tile = blockIdx.x * NSLOT + c.slot; tile < a.ntiles; tile += gridDim.x * NSLOT) {
     const bool valid = (int64_t)tile * TM + c.row < a.B;      // padding rows hold zeros and are never stored to
     STAGE_TRACE(c, 9);
+    if (a.flags & 4) {   // per-line prefetch of exactly the rows this thread will read in its next tile
+      const int nt = tile + gridDim.x * NSLOT;
+      if (nt < a.ntiles) {
+        prefetch_rows_l2(a.y0, nt, YF4, c.hf * 8, 8, c.row);
+        prefetch_rows_l2(a.y0, nt, YF4, AF4 + c.hf * 8, 8, c.row);
+        prefetch_rows_l2(a.y0, nt, YF4, 2 * AF4 + c.hf * 4, 4, c.row);
+        for (int s = 0; s < a.n_a; ++s) prefetch_rows_l2(a.a[s], nt, AF4, c.hf * 8, 8, c.row);
+      }
+    }
     if (c.stid == 0 && (a.flags & 2)) {   // next tile of this slot -> L2 while this one computes
       const int nt = tile + gridDim.x * NSLOT;
       if (nt < a.ntiles) {
@@ -140,9 +149,9 @@ __global__ void __launch_bounds__(THREADS, 1) stage_fwd_tc_kernel(const __grid_c
         pin[4 * j + 2] = pv.z + a.in.cpv * vv.z; pin[4 * j + 3] = pv.w + a.in.cpv * vv.w;
         vin[4 * j] = vv.x; vin[4 * j + 1] = vv.y; vin[4 * j + 2] = vv.z; vin[4 * j + 3] = vv.w;
       }
-#pragma unroll
-      for (int s = 0; s < MAX_A; ++s) {
-        if (s < a.n_a) {
+#pragma unroll 1
+      for (int s = 0; s < a.n_a; ++s) {
+        {
           const float cp = a.in.cpa[s], cv = a.in.cva[s];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -218,9 +227,9 @@ __global__ void __launch_bounds__(THREADS, 1) stage_fwd_tc_kernel(const __grid_c
             ep[e] = ecp * ao[e];
             ev[e] = ecv * ao[e];
           }
-#pragma unroll
-          for (int s = 0; s < MAX_A; ++s) {
-            if (s < a.n_a) {
+#pragma unroll 1
+          for (int s = 0; s < a.n_a; ++s) {
+            {
               const float4 x = ldro(blk4(a.a[s], tile, AF4, f0 + j, c.row));
               const float xs[4] = {x.x, x.y, x.z, x.w};
               const float cp = a.out.cpa[s], cv = a.out.cva[s], xp = a.err.cpa[s], xv = a.err.cva[s];

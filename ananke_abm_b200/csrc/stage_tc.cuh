@@ -91,7 +91,22 @@ struct SlotCtx {
 // template parameter so that the single issuing thread runs a fully unrolled stream of tcgen05.mma whose descriptors
 // differ by a compile-time constant (the tensor core needs a new MMA every 64 cycles; a descriptor rebuilt with
 // shifts and masks per K-step does not keep up).
-template <bool TRANS, int NKS, bool EXT, int N_IMG, int N>
+// The MMA stream of one layer, issued by ONE thread.  Deliberately not inlined and rolled: the stage kernels are
+// 80-130 KB of SASS (every layer's epilogue is specialised), far beyond the instruction cache, and this code runs on a
+// single thread per slot -- one shared copy costs a call, eleven inlined copies cost instruction-cache misses for all
+// sixteen warps.  ~10 instructions per MMA keep ahead of the 64-cycle MMA.
+static __device__ __noinline__ void issue_mmas(uint32_t acc, uint32_t a0, uint32_t tb, uint64_t d0, uint32_t step16, uint32_t idesc, int nks,
+                                        uint64_t* bar) {
+#pragma unroll 1
+  for (int ks = 0; ks < nks; ++ks) mma_ts(acc, a0 + (uint32_t)ks * 8u, d0 + (uint64_t)((uint32_t)ks * step16), idesc, ks > 0 ? 1u : 0u);
+  if (tb != 0xffffffffu) mma_ts(acc, tb, d0 + (uint64_t)((uint32_t)nks * step16), idesc, 1u);
+  mma_commit(bar);
+}
+static __device__ __noinline__ bool wait_mma(uint64_t* bar, uint32_t phase) { return mbar_wait(bar, phase, STAGE_WAIT_CYCLES); }
+
+// SHARED_ISSUE: use the out-of-line issue routine (backward kernel) or an unrolled inline stream (forward kernel, which
+// is smaller and more sensitive to issue latency; measured 95 vs 103 us).
+template <bool TRANS, int NKS, bool EXT, int N_IMG, int N, bool SHARED_ISSUE = false>
 __device__ __forceinline__ void run_layer(SlotCtx& c, uint32_t a_col, uint32_t w_off) {
   STAGE_TRACE(c, 1);
   tmem_st_wait();
@@ -101,10 +116,7 @@ __device__ __forceinline__ void run_layer(SlotCtx& c, uint32_t a_col, uint32_t w
   STAGE_TRACE(c, 3);
   if (c.stid == 0) {
     tc_fence_after();
-    // The two slots take turns ISSUING a layer: all MMAs of one slot's layer enter the tensor-core queue ahead of the
-    // other slot's, so the first one completes after 1x (not 2x) the layer time and the slots fall into anti-phase --
-    // one slot's epilogue runs under the other slot's MMAs instead of both slots doing the same thing at once.
-    if (c.flags & 1) {
+    if (c.flags & 1) {      // optional issue mutex (measured: no gain)
       const long long t0 = clock64();
       while (atomicCAS(c.lock, 0, 1) != 0) {
         if (clock64() - t0 > STAGE_WAIT_CYCLES) { *c.status = 7; break; }
@@ -117,16 +129,20 @@ __device__ __forceinline__ void run_layer(SlotCtx& c, uint32_t a_col, uint32_t w
     // apart), MN-direction cores its 8-column groups (L apart).
     constexpr uint32_t step16 = (TRANS ? 2u * SBO : 2u * L) >> 4;       // descriptor start-address units per K-step
     const uint64_t d0 = TRANS ? make_smem_desc(c.sbase + w_off, SBO, L, SWZ_NONE) : make_smem_desc(c.sbase + w_off, L, SBO, SWZ_NONE);
-    const uint32_t acc = c.tmem + C_ACC, a0 = c.tmem + a_col;
+    if (SHARED_ISSUE) {
+      issue_mmas(c.tmem + C_ACC, c.tmem + a_col, EXT ? c.tmem + C_TB : 0xffffffffu, d0, step16, idesc, NKS, c.bar);
+    } else {
+      const uint32_t acc = c.tmem + C_ACC, a0 = c.tmem + a_col;
 #pragma unroll
-    for (int ks = 0; ks < NKS; ++ks) mma_ts(acc, a0 + (uint32_t)ks * 8u, d0 + (uint64_t)(ks * step16), idesc, ks > 0 ? 1u : 0u);
-    if (EXT) mma_ts(acc, c.tmem + C_TB, d0 + (uint64_t)(NKS * step16), idesc, 1u);
-    mma_commit(c.bar);
+      for (int ks = 0; ks < NKS; ++ks) mma_ts(acc, a0 + (uint32_t)ks * 8u, d0 + (uint64_t)(ks * step16), idesc, ks > 0 ? 1u : 0u);
+      if (EXT) mma_ts(acc, c.tmem + C_TB, d0 + (uint64_t)(NKS * step16), idesc, 1u);
+      mma_commit(c.bar);
+    }
     if (c.flags & 1) atomicExch(c.lock, 0);
   }
   STAGE_TRACE(c, 4);
   __syncwarp();
-  if (c.alive && !mbar_wait(c.bar, c.phase, STAGE_WAIT_CYCLES)) { c.alive = false; *c.status = 1; }
+  if (c.alive && !(SHARED_ISSUE ? wait_mma(c.bar, c.phase) : mbar_wait(c.bar, c.phase, STAGE_WAIT_CYCLES))) { c.alive = false; *c.status = 1; }
   c.phase ^= 1;
   __syncwarp();
   tc_fence_after();
@@ -211,6 +227,15 @@ __device__ __forceinline__ float4 ldro(const float4* p) { return __ldg(p); }
 __device__ __forceinline__ void prefetch_tile_l2(const float* base, int tile, int F4) {
   const char* p = reinterpret_cast<const char*>(base) + (size_t)tile * F4 * TM * 16;
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"((uint32_t)(F4 * TM * 16)) : "memory");
+}
+// per-line L2 prefetch of the float4 groups [f4_begin, f4_begin + n) of this thread's row in the NEXT tile: lanes whose
+// row is a multiple of 8 cover one 128-byte line each (8 rows x 16 B)
+__device__ __forceinline__ void prefetch_rows_l2(const float* base, int tile, int F4, int f4_begin, int n, int row) {
+  if (row & 7) return;
+  for (int j = 0; j < n; ++j) {
+    const float4* p = reinterpret_cast<const float4*>(base) + ((size_t)tile * F4 + f4_begin + j) * TM + row;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+  }
 }
 constexpr int YF4 = D / 4, AF4 = P / 4;       // float4 groups per row of a state / an acceleration buffer
 
