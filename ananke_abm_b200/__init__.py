@@ -13,6 +13,8 @@ from .mode_sep import ModeSepConfig, ModeSepModel  # noqa: F401
 from .gnn_embed import GATEmbed, gnn_embed  # noqa: F401
 from .graph import ZoneCSR, build_zone_csr  # noqa: F401
 from .run import GATODEModel  # noqa: F401
-from . import inference, run  # noqa: F401
+from .latent_ode import GenerativeODE, GenerativeODEConfig  # noqa: F401
+from .batching import UnionBatch, build_union_batch, unify_and_interpolate_batch  # noqa: F401
+from . import inference, run, batching, latent_ode, stage  # noqa: F401
 
 __version__ = "0.1.0"
