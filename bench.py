@@ -408,6 +408,18 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if "TORCHELASTIC_RUN_ID" in os.environ and os.environ.get("AB200_REF_CHILD") != "1":
+        # torchrun pins OMP_NUM_THREADS=1 for its workers; the CPU arm must see all host cores as it does at N=1:
+        # re-run this arm in a clean child process and relay its line
+        env = {k: v for k, v in os.environ.items() if k not in ("OMP_NUM_THREADS", "MKL_NUM_THREADS")}
+        env["AB200_REF_CHILD"] = "1"
+        out = subprocess.run([sys.executable, str(REPO / "bench.py")] + sys.argv[1:], env=env, capture_output=True, text=True)
+        line = [l for l in out.stdout.splitlines() if l.startswith("{")]
+        if line:
+            d = json.loads(line[-1])
+            d["n_gpus"] = int(os.environ.get("WORLD_SIZE", "1"))
+            print(json.dumps(d))
+            return
     cfg = dict(WORKLOADS[args.workload])
     if args.agents:
         cfg["B"] = args.agents
@@ -435,7 +447,8 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["f32", "bf16"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--agents", type=int, default=0, help="override agents per GPU")
-    ap.add_argument("--chunk", type=int, default=131_072, help="agents per fused launch")
+    ap.add_argument("--chunk", type=int, default=189_440,
+                    help="agents per launch sequence; default = 5 x (148 SMs x 2 slots x 128 agents): whole waves of tiles")
     ap.add_argument("--solver", default="", choices=["", "rk4", "dopri5"], help="override the workload's solver")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
