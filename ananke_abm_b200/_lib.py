@@ -60,7 +60,7 @@ SIGNATURES = {
     "ab200_rows_unblock": (C.c_int, [_vp, _vp, _i64, _i32, _vp]),
     "ab200_stage_image_bytes": (_sz, [_dp]),
     "ab200_stage_pack": (C.c_int, [_dp, _vp, _vp, _sz, _vp]),
-    "ab200_stage_forward": (C.c_int, [_dp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "ab200_stage_forward": (C.c_int, [_dp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i32, _vp]),
     "ab200_stage_spill_bytes": (_sz, [_dp, _i32]),
     "ab200_wgrad_partial_bytes": (_sz, [_dp]),
     "ab200_stage_backward": (C.c_int, [_dp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _sz, _i32, _i32, _vp, _vp]),

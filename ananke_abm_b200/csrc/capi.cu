@@ -43,7 +43,7 @@ int gat_backward(const int* rowptr, const int* col, const int* rowptr_t, const i
 size_t stage_tc_image_bytes();
 int stage_tc_pack(const float* w_flat, uint8_t* image, cudaStream_t st);
 int stage_fwd_tc(const ab200_drift_desc* d, const uint8_t* image, const float* y0, const float* const* a_ptrs, const void* desc_v,
-                 int64_t B, float* a_out, float* y_out, double* err_sumsq, cudaStream_t st);
+                 int64_t B, float* a_out, float* y_out, double* err_sumsq, int half_ops, cudaStream_t st);
 int stage_bwd_tc(const ab200_drift_desc* d, const uint8_t* image, const float* y0, const float* const* a_ptrs, const void* desc_v,
                  int64_t B, const float* g_base, const float* const* gx_ptrs, int n_g, const float* dp, const float* dv, float* gx_out,
                  void* spill, int blob0, int nblobs, float* g_bout, cudaStream_t st);
@@ -203,11 +203,11 @@ int ab200_stage_pack(const ab200_drift_desc* d, const float* w_flat, void* image
 
 int ab200_stage_forward(const ab200_drift_desc* d, const void* image, const float* y0, const float* const* a,
                         const ab200_stage_desc* s, int64_t B, float* a_out, float* y_out, double* err_sumsq,
-                        ab200_stream_t stream) {
+                        int32_t operand_format, ab200_stream_t stream) {
   if (!d || !image || !y0 || !s || B <= 0 || (s->n_a > 0 && !a)) return AB200_ERR_BAD_ARG;
   if (!stage_shape_ok(d)) return AB200_ERR_UNSUPPORTED;
-  if (err_sumsq && !y_out) return AB200_ERR_BAD_ARG;
-  return stage_fwd_tc(d, (const uint8_t*)image, y0, a, s, B, a_out, y_out, err_sumsq, (cudaStream_t)stream);
+  if ((err_sumsq && !y_out) || operand_format < 0 || operand_format > 1) return AB200_ERR_BAD_ARG;
+  return stage_fwd_tc(d, (const uint8_t*)image, y0, a, s, B, a_out, y_out, err_sumsq, operand_format, (cudaStream_t)stream);
 }
 
 size_t ab200_stage_spill_bytes(const ab200_drift_desc* d, int32_t nblobs) {

@@ -341,7 +341,7 @@ int stage_bwd_tc(const ab200_drift_desc* d, const uint8_t* image, const float* y
   k.nblobs = nblobs;
   k.flags = stage_flags();
   if (blob0 < 0 || blob0 + k.ntiles > nblobs) return AB200_ERR_BAD_ARG;
-  k.status = reinterpret_cast<int*>(const_cast<uint8_t*>(image) + align_up(W_BYTES, 256));
+  k.status = reinterpret_cast<int*>(const_cast<uint8_t*>(image) + 2 * IMG_STRIDE);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -8,6 +8,7 @@
 // which covers every stage of torchdiffeq's fixed-grid rk4 (rk_common.py rk4_alt_step_func) and adaptive dopri5
 // (rk_common.py _runge_kutta_step + misc.py _compute_error_ratio): the host passes the tableau as `Combo`s.
 // Two 128-agent tiles ("slots") are in flight per CTA; see stage_tc.cuh.
+#include <cuda_fp16.h>
 #include <stdlib.h>
 #include "stage_tc.cuh"
 
@@ -25,6 +26,7 @@ extern "C" int ab200_debug_stage_trace(long long* host_out, int* counts) {
 #endif
 
 // ---- prepack: torch-layout fp32 weights -> bf16 UMMA image with bias / time-feature K extensions ---------------
+template <bool HALF>
 __global__ void stage_pack_kernel(const float* __restrict__ w, uint8_t* __restrict__ out) {
   const FlatLayout F{P, H, HID, NRES};
   const int IN = 2 * P + H + 2;
@@ -55,7 +57,7 @@ __global__ void stage_pack_kernel(const float* __restrict__ w, uint8_t* __restri
       v = wsrc[(size_t)n * ldw + k];
     } else {
       const int e = k - Kmain;
-      auto hi = [](float x) { return __bfloat162float(__float2bfloat16_rn(x)); };
+      auto hi = [](float x) { return HALF ? __half2float(__float2half_rn(x)) : __bfloat162float(__float2bfloat16_rn(x)); };
       if (base == OFF_W1 && e < 6) {
         const float wt = wsrc[(size_t)n * ldw + Kmain + (e < 3 ? 0 : 1)];     // sin column, cos column of w_in
         const int r = e % 3;
@@ -66,7 +68,8 @@ __global__ void stage_pack_kernel(const float* __restrict__ w, uint8_t* __restri
         v = bsrc[n] - hi(bsrc[n]);
       }
     }
-    *reinterpret_cast<__nv_bfloat16*>(out + base + off_kmajor_noswz(n, k, lbo(N), SBO)) = __float2bfloat16_rn(v);
+    if (HALF) *reinterpret_cast<__half*>(out + base + off_kmajor_noswz(n, k, lbo(N), SBO)) = __float2half_rn(v);
+    else *reinterpret_cast<__nv_bfloat16*>(out + base + off_kmajor_noswz(n, k, lbo(N), SBO)) = __float2bfloat16_rn(v);
   }
 }
 
@@ -79,10 +82,11 @@ int stage_flags() {
   return f;
 }
 
-size_t stage_tc_image_bytes() { return align_up(W_BYTES, 256) + 256; }   // image + status word
+size_t stage_tc_image_bytes() { return 2 * IMG_STRIDE + 256; }   // bf16 image, fp16 image, status word
 
 int stage_tc_pack(const float* w_flat, uint8_t* image, cudaStream_t st) {
-  stage_pack_kernel<<<148, 256, 0, st>>>(w_flat, image);
+  stage_pack_kernel<false><<<148, 256, 0, st>>>(w_flat, image);
+  stage_pack_kernel<true><<<148, 256, 0, st>>>(w_flat, image + IMG_STRIDE);
   return check_launch();
 }
 
@@ -105,6 +109,7 @@ struct StageFwdArgs {
   int* status;
 };
 
+template <bool HALF>
 __global__ void __launch_bounds__(THREADS, 1) stage_fwd_tc_kernel(const __grid_constant__ StageFwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bars[NSLOT + 1];
@@ -163,10 +168,10 @@ __global__ void __launch_bounds__(THREADS, 1) stage_fwd_tc_kernel(const __grid_c
       }
       uint32_t o[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = pack_bf16(pin[2 * j], pin[2 * j + 1]);
+      for (int j = 0; j < 8; ++j) o[j] = pack2<HALF>(pin[2 * j], pin[2 * j + 1]);
       tmem_st8(c.tmem + c.lane_sel + C_ACT + (uint32_t)(f0 * 2), o);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = pack_bf16(vin[2 * j], vin[2 * j + 1]);
+      for (int j = 0; j < 8; ++j) o[j] = pack2<HALF>(vin[2 * j], vin[2 * j + 1]);
       tmem_st8(c.tmem + c.lane_sel + C_ACT + (uint32_t)(P / 2 + f0 * 2), o);
     }
     {
@@ -174,27 +179,27 @@ __global__ void __launch_bounds__(THREADS, 1) stage_fwd_tc_kernel(const __grid_c
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float4 x = ldro(blk4(a.y0, tile, YF4, 2 * AF4 + c.hf * 4 + j, c.row));
-        o[2 * j] = pack_bf16(x.x, x.y);
-        o[2 * j + 1] = pack_bf16(x.z, x.w);
+        o[2 * j] = pack2<HALF>(x.x, x.y);
+        o[2 * j + 1] = pack2<HALF>(x.z, x.w);
       }
       tmem_st8(c.tmem + c.lane_sel + C_HB + (uint32_t)(c.hf * 8), o);
     }
-    write_time_block(c, a.t, a.period);
+    write_time_block<HALF>(c, a.t, a.period);
     STAGE_TRACE(c, 10);
 
     // ---- drift net
     uint32_t z[32];
-    run_layer<false, (2 * P + H) / 16, true, HID, HID>(c, C_ACT, OFF_W1);
-    epi_relu<true>(c, z);
+    run_layer<false, (2 * P + H) / 16, true, HID, HID, false, HALF>(c, C_ACT, OFF_W1);
+    epi_relu<true, HALF>(c, z);
 #pragma unroll 1
     for (int r = 0; r < NRES; ++r) {
       uint32_t dummy[32];
-      run_layer<false, HID / 16, true, HID, HID>(c, C_ACT, off_hh(2 * r));
-      epi_relu<false>(c, dummy);
-      run_layer<false, HID / 16, true, HID, HID>(c, C_ACT, off_hh(2 * r + 1));
-      epi_residual(c, z);
+      run_layer<false, HID / 16, true, HID, HID, false, HALF>(c, C_ACT, off_hh(2 * r));
+      epi_relu<false, HALF>(c, dummy);
+      run_layer<false, HID / 16, true, HID, HID, false, HALF>(c, C_ACT, off_hh(2 * r + 1));
+      epi_residual<HALF>(c, z);
     }
-    run_layer<false, HID / 16, true, P, P>(c, C_ACT, OFF_WO);
+    run_layer<false, HID / 16, true, P, P, false, HALF>(c, C_ACT, OFF_WO);
 
     // ---- output epilogue: this thread's 32 acceleration dims (float4 groups hf*8 ..)
     STAGE_TRACE(c, 11);
@@ -289,11 +294,11 @@ struct StageFwdHost {   // mirrors ab200_stage_desc in the public header
 };
 
 int stage_fwd_tc(const ab200_drift_desc* d, const uint8_t* image, const float* y0, const float* const* a_ptrs, const void* desc_v,
-                 int64_t B, float* a_out, float* y_out, double* err_sumsq, cudaStream_t st) {
+                 int64_t B, float* a_out, float* y_out, double* err_sumsq, int half_ops, cudaStream_t st) {
   const StageFwdHost& h = *reinterpret_cast<const StageFwdHost*>(desc_v);
   if (h.n_a < 0 || h.n_a > MAX_A) return AB200_ERR_BAD_ARG;
   StageFwdArgs k{};
-  k.wimg = image;
+  k.wimg = image + (half_ops ? IMG_STRIDE : 0);
   k.y0 = y0;
   for (int i = 0; i < MAX_A; ++i) k.a[i] = (i < h.n_a) ? a_ptrs[i] : nullptr;
   k.n_a = h.n_a;
@@ -315,15 +320,16 @@ int stage_fwd_tc(const ab200_drift_desc* d, const uint8_t* image, const float* y
   k.B = B;
   k.ntiles = (int)((B + TM - 1) / TM);
   k.flags = stage_flags();
-  k.status = reinterpret_cast<int*>(const_cast<uint8_t*>(image) + align_up(W_BYTES, 256));
+  k.status = reinterpret_cast<int*>(const_cast<uint8_t*>(image) + 2 * IMG_STRIDE);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int need = (k.ntiles + NSLOT - 1) / NSLOT;
   const int grid = need < sms ? need : sms;
-  cudaError_t e = cudaFuncSetAttribute(stage_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W_BYTES);
+  auto kern = half_ops ? stage_fwd_tc_kernel<true> : stage_fwd_tc_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W_BYTES);
   if (e != cudaSuccess) { set_cuda_error(e); return AB200_ERR_CUDA; }
-  stage_fwd_tc_kernel<<<grid, THREADS, W_BYTES, st>>>(k);
+  kern<<<grid, THREADS, W_BYTES, st>>>(k);
   return check_launch();
 }
 

@@ -71,6 +71,39 @@ __device__ __forceinline__ uint32_t pack_relu_bf16(float lo_v, float hi_v) {
 __device__ __forceinline__ float bf16lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
+// Operand-format generic versions (HALF = IEEE fp16 operands: 11-bit significand, 8x less rounding noise than bf16 --
+// what an adaptive solver's error estimate needs; values of this net stay far inside the fp16 range).
+template <bool HALF>
+__device__ __forceinline__ uint32_t pack2(float lo_v, float hi_v) {
+  uint32_t d;
+  if (HALF) asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi_v), "f"(lo_v));
+  else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi_v), "f"(lo_v));
+  return d;
+}
+template <bool HALF>
+__device__ __forceinline__ uint32_t pack2_relu(float lo_v, float hi_v) {
+  uint32_t d;
+  if (HALF) asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi_v), "f"(lo_v));
+  else asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi_v), "f"(lo_v));
+  return d;
+}
+template <bool HALF>
+__device__ __forceinline__ float un_lo(uint32_t v) {
+  if (!HALF) return bf16lo(v);
+  float f;
+  asm("{.reg .b16 l, h; mov.b32 {l, h}, %1; cvt.f32.f16 %0, l;}" : "=f"(f) : "r"(v));
+  return f;
+}
+template <bool HALF>
+__device__ __forceinline__ float un_hi(uint32_t v) {
+  if (!HALF) return bf16hi(v);
+  float f;
+  asm("{.reg .b16 l, h; mov.b32 {l, h}, %1; cvt.f32.f16 %0, h;}" : "=f"(f) : "r"(v));
+  return f;
+}
+template <bool HALF>
+__device__ __forceinline__ float round16(float x) { return un_lo<HALF>(pack2<HALF>(x, 0.0f)); }
+
 // Per-thread view of its slot.
 struct SlotCtx {
   uint32_t tmem;        // TMEM base of the slot (column 0, lane 0)
@@ -106,7 +139,7 @@ static __device__ __noinline__ bool wait_mma(uint64_t* bar, uint32_t phase) { re
 
 // SHARED_ISSUE: use the out-of-line issue routine (backward kernel) or an unrolled inline stream (forward kernel, which
 // is smaller and more sensitive to issue latency; measured 95 vs 103 us).
-template <bool TRANS, int NKS, bool EXT, int N_IMG, int N, bool SHARED_ISSUE = false>
+template <bool TRANS, int NKS, bool EXT, int N_IMG, int N, bool SHARED_ISSUE = false, bool HALF = false>
 __device__ __forceinline__ void run_layer(SlotCtx& c, uint32_t a_col, uint32_t w_off) {
   STAGE_TRACE(c, 1);
   tmem_st_wait();
@@ -122,7 +155,7 @@ __device__ __forceinline__ void run_layer(SlotCtx& c, uint32_t a_col, uint32_t w
         if (clock64() - t0 > STAGE_WAIT_CYCLES) { *c.status = 7; break; }
       }
     }
-    constexpr uint32_t idesc = make_idesc_bf16(TM, N, false, false, TRANS);
+    constexpr uint32_t idesc = make_idesc_bf16(TM, N, false, false, TRANS, HALF);
     constexpr uint32_t L = lbo(N_IMG);
     // K-major: K-adjacent cores L apart (LBO), MN-adjacent cores 128 B apart (SBO); a K-step spans two K cores.
     // MN-major view: B'[n' = in][k' = out] = W[out][in]; K-direction cores are the image's 8-row groups (128 B
@@ -151,7 +184,7 @@ __device__ __forceinline__ void run_layer(SlotCtx& c, uint32_t a_col, uint32_t w
 
 // ---- hidden-layer epilogues: this thread's 64 columns (hf*64 ..) of its row ------------------------------
 // plain: act = relu(acc) -> ACT.  If KEEP, the packed result is also kept in z[32] (residual stream).
-template <bool KEEP>
+template <bool KEEP, bool HALF = false>
 __device__ __forceinline__ void epi_relu(const SlotCtx& c, uint32_t (&z)[32]) {
 #pragma unroll
   for (int ch = 0; ch < 2; ++ch) {
@@ -161,13 +194,14 @@ __device__ __forceinline__ void epi_relu(const SlotCtx& c, uint32_t (&z)[32]) {
     uint32_t o[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      o[j] = pack_relu_bf16(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+      o[j] = pack2_relu<HALF>(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
       if (KEEP) z[ch * 16 + j] = o[j];
     }
     tmem_st16(c.tmem + c.lane_sel + C_ACT + (uint32_t)(c.hf * 32 + ch * 16), o);
   }
 }
 // residual: z <- relu(acc + z) -> ACT
+template <bool HALF = false>
 __device__ __forceinline__ void epi_residual(const SlotCtx& c, uint32_t (&z)[32]) {
 #pragma unroll
   for (int ch = 0; ch < 2; ++ch) {
@@ -178,7 +212,7 @@ __device__ __forceinline__ void epi_residual(const SlotCtx& c, uint32_t (&z)[32]
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       const uint32_t zz = z[ch * 16 + j];
-      o[j] = pack_relu_bf16(__uint_as_float(r[2 * j]) + bf16lo(zz), __uint_as_float(r[2 * j + 1]) + bf16hi(zz));
+      o[j] = pack2_relu<HALF>(__uint_as_float(r[2 * j]) + un_lo<HALF>(zz), __uint_as_float(r[2 * j + 1]) + un_hi<HALF>(zz));
       z[ch * 16 + j] = o[j];
     }
     tmem_st16(c.tmem + c.lane_sel + C_ACT + (uint32_t)(c.hf * 32 + ch * 16), o);
@@ -186,16 +220,17 @@ __device__ __forceinline__ void epi_residual(const SlotCtx& c, uint32_t (&z)[32]
 }
 
 // TB block of this row: [s_hi, s_hi, s_lo, c_hi, c_hi, c_lo, 1, 1, 0 x 8] as 8 packed columns
+template <bool HALF = false>
 __device__ __forceinline__ void write_time_block(const SlotCtx& c, float t, float period) {
   if (c.hf != 0) return;
   float s, co;
   time_features(t, period, s, co);
-  const float s_hi = __bfloat162float(__float2bfloat16_rn(s)), c_hi = __bfloat162float(__float2bfloat16_rn(co));
+  const float s_hi = round16<HALF>(s), c_hi = round16<HALF>(co);
   uint32_t o[8];
-  o[0] = pack_bf16(s_hi, s_hi);
-  o[1] = pack_bf16(s - s_hi, c_hi);
-  o[2] = pack_bf16(c_hi, co - c_hi);
-  o[3] = pack_bf16(1.0f, 1.0f);
+  o[0] = pack2<HALF>(s_hi, s_hi);
+  o[1] = pack2<HALF>(s - s_hi, c_hi);
+  o[2] = pack2<HALF>(c_hi, co - c_hi);
+  o[3] = pack2<HALF>(1.0f, 1.0f);
   o[4] = o[5] = o[6] = o[7] = 0u;
   tmem_st8(c.tmem + c.lane_sel + C_TB, o);
 }
@@ -293,5 +328,6 @@ int stage_flags();
 // host entry points (stage_fwd_tc.cu / stage_bwd_tc.cu / wgrad_tc.cu)
 size_t stage_tc_image_bytes();
 int stage_tc_pack(const float* w_flat, uint8_t* image, cudaStream_t st);
+constexpr size_t IMG_STRIDE = (stc::W_BYTES + 255) / 256 * 256;   // bf16 image at 0, fp16 image at IMG_STRIDE, status word after both
 
 }  // namespace ab200

@@ -82,9 +82,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 }
 // instruction descriptor for kind::f16 with BF16 A/B, FP32 accumulate, both operands K-major
 // a_mn / b_mn: operand is MN-major (the M resp. N index is the contiguous one in shared memory) instead of K-major
+// half_ops: operands are IEEE fp16 (format code 0) instead of bf16 (format code 1); accumulation is fp32 either way
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool negate_a = false, bool a_mn = false,
-                                                       bool b_mn = false) {
-  return (1u << 4) /* D = f32 */ | (1u << 7) /* A = bf16 */ | (1u << 10) /* B = bf16 */ | ((negate_a ? 1u : 0u) << 13) |
+                                                       bool b_mn = false, bool half_ops = false) {
+  return (1u << 4) /* D = f32 */ | ((half_ops ? 0u : 1u) << 7) /* A */ | ((half_ops ? 0u : 1u) << 10) /* B */ |
+         ((negate_a ? 1u : 0u) << 13) |
          ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 

@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import ctypes as C
 import warnings
+import weakref
 from typing import Callable, Optional, Sequence
 
 import torch
@@ -50,14 +51,14 @@ _T_CACHE: dict = {}
 
 def _check_t(t: torch.Tensor) -> torch.Tensor:
     """torchdiffeq's input checks (odeint.py `_check_inputs`).  The host copy of a time grid is cached per
-    (storage, version) so that repeated solves on the same grid do not force a device->host sync each call."""
+    live tensor object and version (a data_ptr key can alias a freed tensor's memory) so that repeated solves on the same grid do not force a device->host sync each call."""
     assert isinstance(t, torch.Tensor), "t must be a torch.Tensor"
     assert t.ndimension() == 1, "t must be one dimensional"
     assert torch.is_floating_point(t), "t must be a floating point Tensor"
-    key = (t.data_ptr(), t._version, t.numel(), t.dtype, str(t.device))
+    key = id(t)
     hit = _T_CACHE.get(key)
-    if hit is not None:
-        return hit
+    if hit is not None and hit[0]() is t and hit[1] == t._version:       # same live tensor object, not modified since
+        return hit[2]
     t_host = t.detach().to("cpu", non_blocking=False)
     if t_host.numel() > 1:
         d = t_host[1:] - t_host[:-1]
@@ -65,7 +66,7 @@ def _check_t(t: torch.Tensor) -> torch.Tensor:
             raise AssertionError("t must be strictly increasing or decreasing")
     if len(_T_CACHE) > 64:
         _T_CACHE.clear()
-    _T_CACHE[key] = t_host
+    _T_CACHE[key] = (weakref.ref(t), t._version, t_host)
     return t_host
 
 
@@ -424,7 +425,7 @@ def odeint(func, y0, t, *, rtol: float = 1e-7, atol: float = 1e-9, method: Optio
         if (spec is not None and y0.shape[1] == spec.state_dim and precision == _lib.PREC_BF16 and spec.tc_stage_supported()
                 and y0.dtype == torch.float32):
             opts = {}
-            for k_ in ("first_step", "safety", "ifactor", "dfactor", "max_num_steps"):
+            for k_ in ("first_step", "safety", "ifactor", "dfactor", "max_num_steps", "fp16_forward"):
                 if k_ in options:
                     opts[k_] = options.pop(k_)
             opts["time_dtype"] = torch.promote_types(options.pop("dtype", torch.float64), torch.float32)

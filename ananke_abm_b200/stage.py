@@ -128,10 +128,14 @@ class TcEngine:
         self._img_status, self._part_status = int(off_i.value), int(off_p.value)
         self.P, self.H = self.desc.pos_dim, self.desc.ctx_dim
         self.D = 2 * self.P + self.H
+        # forward stage evaluations use IEEE fp16 operands (values of this net stay far inside the fp16 range): 8x less
+        # rounding noise than bf16 at the same speed -- trajectories 4x closer to fp32 and an adaptive error estimate that is
+        # not noise-limited at rtol = atol = 1e-5.  Backward kernels keep bf16 (gradient range).
+        self.fp16_forward = True
 
     # ---- forward ------------------------------------------------------------------------------------
     def stage_forward(self, y0, a: Sequence[torch.Tensor], cin: Combo, t: float, B: int, a_out=None, y_out=None, cout: Optional[Combo] = None,
-                      err_sumsq=None, cerr: Optional[Combo] = None, rtol: float = 0.0, atol: float = 0.0) -> None:
+                      err_sumsq=None, cerr: Optional[Combo] = None, rtol: float = 0.0, atol: float = 0.0, fp16: Optional[bool] = None) -> None:
         s = StageDesc()
         s.n_a = len(a)
         s.in_cpv = cin.cpv
@@ -149,7 +153,8 @@ class TcEngine:
         rc = self.L.ab200_stage_forward(C.byref(self.desc), self.image.data_ptr(), y0.data_ptr(), C.cast(_ptr_array(a), C.c_void_p),
                                         C.byref(s), B, None if a_out is None else a_out.data_ptr(),
                                         None if y_out is None else y_out.data_ptr(),
-                                        None if err_sumsq is None else err_sumsq.data_ptr(), _stream())
+                                        None if err_sumsq is None else err_sumsq.data_ptr(),
+                                        1 if (self.fp16_forward if fp16 is None else fp16) else 0, _stream())
         _lib.check(rc, "ab200_stage_forward")
 
     def combine(self, y0, a: Sequence[torch.Tensor], c: Combo, B: int, out) -> None:
@@ -361,13 +366,14 @@ def _cast_time(v: float, time_dtype) -> float:
 
 def dopri5_forward(eng: TcEngine, y0: torch.Tensor, t_host: Sequence[float], rtol: float, atol: float, *, first_step=None,
                    safety: float = 0.9, ifactor: float = 10.0, dfactor: float = 0.2, max_num_steps: int = 2 ** 31 - 1,
-                   time_dtype=torch.float64, save_steps: bool = False, stats: Optional[Dopri5Stats] = None):
+                   time_dtype=torch.float64, save_steps: bool = False, stats: Optional[Dopri5Stats] = None, fp16_forward: bool = True):
     """y0 row-major [B, D] -> y_path [T, B, D] (dense output at the requested times), and the accepted steps when
     `save_steps`.  One host read of the squared-error sum per attempted step decides accept / reject."""
     B, T = y0.shape[0], len(t_host)
     dev = y0.device
     D, P = eng.D, eng.P
     stats = stats if stats is not None else Dopri5Stats()
+    prev_fmt, eng.fp16_forward = eng.fp16_forward, bool(fp16_forward)
     ts = [_cast_time(float(v), time_dtype) for v in t_host]
     y_path = torch.empty((T, B, D), dtype=torch.float32, device=dev)
     y_path[0].copy_(y0)
@@ -416,6 +422,8 @@ def dopri5_forward(eng: TcEngine, y0: torch.Tensor, t_host: Sequence[float], rto
                           err_sumsq=sumsq, cerr=DOPRI5.combo(c_err, dt), rtol=rtol, atol=atol)
         stats.n_evals += 6
         ratio = float(torch.sqrt(sumsq[0] / (B * D)))
+        if ratio != ratio:
+            raise _lib.Ab200Error("dopri5: non-finite error estimate (state or drift overflowed)")
         n_steps += 1
         if ratio <= 1.0:
             stats.n_accepted += 1
@@ -442,6 +450,7 @@ def dopri5_forward(eng: TcEngine, y0: torch.Tensor, t_host: Sequence[float], rto
         else:
             dfac = 1.0 if ratio < 1.0 else dfactor
             dt = _cast_time(dt * min(ifactor, max(safety / ratio ** 0.2, dfac)), time_dtype)
+    eng.fp16_forward = prev_fmt
     return y_path, (steps if save_steps else None), stats
 
 

@@ -33,9 +33,10 @@ WORKLOADS = {
     # BASELINE.json configs[1]: 10k agents x 500-zone graph, 96 RK4 steps/day, single-head GAT, inference
     "c2": dict(B=10_000, Z=500, T=97, heads=1, mode="inference", method="rk4",
                name="configs[1]: 10k agents x 500 zones, 96 RK4 steps, 1-head GAT, inference"),
-    # BASELINE.json configs[2] shape with the fixed-grid solver: 1M agents x 10k zones, 4-head GAT, fwd+bwd
-    "c3": dict(B=1_000_000, Z=10_000, T=97, heads=4, mode="train", method="rk4",
-               name="configs[2] shape: 1M agents x 10k zones, 4-head GAT, 96 RK4 steps, fwd+bwd (agent-chunked)"),
+    # BASELINE.json configs[2]: 1M agents x 10k zones, 4-head GAT, dopri5 adaptive (rtol = atol = 1e-5, mode_sep/config.py:27-28),
+    # fwd+bwd; dense output at the 97 grid points of the day.  `--solver rk4` runs the fixed-grid variant (96 steps).
+    "c3": dict(B=1_000_000, Z=10_000, T=97, heads=4, mode="train", method="dopri5",
+               name="configs[2]: 1M agents x 10k zones, 4-head GAT, dopri5 rtol=atol=1e-5, fwd+bwd (agent-chunked)"),
 }
 ALG_FLOP_FWD = 755_712          # per agent-step, SURVEY.md §8(d) / BASELINE.md §3
 ALG_FLOP_FWDBWD = 3_022_848     # 4x forward (discrete adjoint with stage recompute)
@@ -152,7 +153,8 @@ def run_ours(args):
         cfg["B"] = args.agents
     if args.solver:
         cfg["method"] = args.solver
-        cfg["name"] = cfg["name"].replace("96 RK4 steps", "dopri5 rtol=atol=1e-5" if args.solver == "dopri5" else "96 RK4 steps")
+        cfg["name"] = cfg["name"].replace("96 RK4 steps", "dopri5 rtol=atol=1e-5") if args.solver == "dopri5" else \
+            cfg["name"].replace("dopri5 rtol=atol=1e-5", "96 RK4 steps")
     train = cfg["mode"] == "train"
     chunk = min(cfg["B"], args.chunk)
     B, T = cfg["B"], cfg["T"]
@@ -340,7 +342,7 @@ def run_ours(args):
         "metric": METRIC + (" fwd+bwd" if train else " fwd (inference)"), "value": value, "unit": "agent-steps/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32" if args.precision == "f32" else "bf16 (fp32 accumulate, fp32 state)", "data": "synthetic",
+        "dtype": "f32" if args.precision == "f32" else ("fp16 fwd / bf16 bwd operands (fp32 accumulate, fp32 state)" if train else "bf16 (fp32 accumulate, fp32 state)"), "data": "synthetic",
         "config": {"workload": cfg["name"], "agents_per_gpu": B, "zones": cfg["Z"], "time_points": T, "solver": cfg["method"],
                    "agent_chunk": chunk, "precision": args.precision,
                    "solver_steps": ({"accepted_per_trajectory": steps_counted["accepted"] / max(1, args.steps * ((B + chunk - 1) // chunk)),
@@ -425,7 +427,8 @@ def run_reference(args):
         cfg["B"] = args.agents
     if args.solver:
         cfg["method"] = args.solver
-        cfg["name"] = cfg["name"].replace("96 RK4 steps", "dopri5 rtol=atol=1e-5" if args.solver == "dopri5" else "96 RK4 steps")
+        cfg["name"] = cfg["name"].replace("96 RK4 steps", "dopri5 rtol=atol=1e-5") if args.solver == "dopri5" else \
+            cfg["name"].replace("dopri5 rtol=atol=1e-5", "96 RK4 steps")
     train = cfg["mode"] == "train"
     t0 = time.perf_counter()
     cb = cpu_baseline(cfg, train, steps=max(1, min(args.steps, 3)), warmup=1 if args.warmup else 0)

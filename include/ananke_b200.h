@@ -151,10 +151,12 @@ int ab200_rows_unblock(const float* src_blocked, float* dst_rowmajor, int64_t B,
 size_t ab200_stage_image_bytes(const ab200_drift_desc* d);
 int ab200_stage_pack(const ab200_drift_desc* d, const float* w_flat, void* image, size_t image_bytes, ab200_stream_t stream);
 /* `a` : host array of n_a device pointers (blocked [Bp][P] fp32 each).  a_out (blocked [Bp][P]), y_out (blocked
- * [Bp][D]) and err_sumsq (device double, accumulated) may each be NULL. */
+ * [Bp][D]) and err_sumsq (device double, accumulated) may each be NULL.  operand_format: 0 = bf16 operands,
+ * 1 = IEEE fp16 operands (same speed, 8x less rounding noise -- what dopri5's embedded error estimate needs at
+ * rtol = atol = 1e-5; the image holds both encodings of the weights). */
 int ab200_stage_forward(const ab200_drift_desc* d, const void* image, const float* y0, const float* const* a,
                         const ab200_stage_desc* s, int64_t B, float* a_out, float* y_out, double* err_sumsq,
-                        ab200_stream_t stream);
+                        int32_t operand_format, ab200_stream_t stream);
 /* Vector-Jacobian product of one stage = what autograd does for the ops of one `func` call inside the solver
  * (mode_sep/train/train.py:162).  The upstream gradient is assembled in the kernel as
  *     dL/da_out = g_base + sum_{l < n_g} dp[l] gx[l].p + dv[l] gx[l].v
