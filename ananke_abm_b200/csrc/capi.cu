@@ -47,6 +47,8 @@ int stage_fwd_tc(const ab200_drift_desc* d, const uint8_t* image, const float* y
 int stage_bwd_tc(const ab200_drift_desc* d, const uint8_t* image, const float* y0, const float* const* a_ptrs, const void* desc_v,
                  int64_t B, const float* g_base, const float* const* gx_ptrs, int n_g, const float* dp, const float* dv, float* gx_out,
                  void* spill, int blob0, int nblobs, float* g_bout, cudaStream_t st);
+int ga_assemble(const ab200_drift_desc* d, const float* base, const float* const* gx, int n, const float* dp, const float* dv,
+                int64_t B, float* out, cudaStream_t st);
 int adjoint_gather(const ab200_drift_desc* d, const float* base, const float* const* gx, int n, const float* cpv, int64_t B, float* out,
                    cudaStream_t st);
 size_t wgrad_spill_bytes(int nblobs);
@@ -226,6 +228,12 @@ int ab200_stage_backward(const ab200_drift_desc* d, const void* image, const flo
   if (nblobs <= 0 || spill_bytes < wgrad_spill_bytes(nblobs)) return AB200_ERR_WORKSPACE;
   return stage_bwd_tc(d, (const uint8_t*)image, y0, a, s, B, g_base, gx, n_g, dp_host, dv_host, gx_out, spill, blob0, nblobs,
                       wgrad_bout_ptr(partial), (cudaStream_t)stream);
+}
+
+int ab200_stage_upstream(const ab200_drift_desc* d, const float* g_base, const float* const* gx, int32_t n_g, const float* dp_host,
+                         const float* dv_host, int64_t B, float* g_a_out, ab200_stream_t stream) {
+  if (!desc_ok(d) || !g_base || !g_a_out || B <= 0 || (n_g > 0 && (!gx || !dp_host || !dv_host))) return AB200_ERR_BAD_ARG;
+  return ga_assemble(d, g_base, gx, n_g, dp_host, dv_host, B, g_a_out, (cudaStream_t)stream);
 }
 
 int ab200_adjoint_gather(const ab200_drift_desc* d, const float* base, const float* const* gx, int32_t n, const float* cpv_host,

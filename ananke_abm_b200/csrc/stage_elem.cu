@@ -147,6 +147,35 @@ __global__ void __launch_bounds__(256) adjoint_gather_kernel(const __grid_consta
   }
 }
 
+// out (blocked [Bp][P]) = base + sum_l dp[l] gx_l.p + dv[l] gx_l.v : the upstream gradient of a stage written out as a buffer
+// (needed when the stage itself is differentiated elsewhere: dopri5's FSAL evaluation belongs to the previous step)
+struct AssembleArgs {
+  const float* base;
+  const float* gx[EL_MAX_A];
+  float dp[EL_MAX_A], dv[EL_MAX_A];
+  float* out;
+  int n, ntiles, P, H;
+};
+__global__ void __launch_bounds__(256) ga_assemble_kernel(const __grid_constant__ AssembleArgs a) {
+  const int P4 = a.P / 4, Y4 = 2 * P4 + a.H / 4;
+  const int64_t n = (int64_t)a.ntiles * P4 * EL_TM;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int row = (int)(i % EL_TM);
+    const int64_t q = i / EL_TM;
+    const int grp = (int)(q % P4), tile = (int)(q / P4);
+    float4 x = reinterpret_cast<const float4*>(a.base)[((size_t)tile * P4 + grp) * EL_TM + row];
+#pragma unroll
+    for (int s = 0; s < EL_MAX_A; ++s)
+      if (s < a.n) {
+        const float4* g4 = reinterpret_cast<const float4*>(a.gx[s]) + (size_t)tile * Y4 * EL_TM + row;
+        const float4 gp = g4[(size_t)grp * EL_TM], gv = g4[(size_t)(P4 + grp) * EL_TM];
+        const float dp = a.dp[s], dv = a.dv[s];
+        x.x += dp * gp.x + dv * gv.x; x.y += dp * gp.y + dv * gv.y; x.z += dp * gp.z + dv * gv.z; x.w += dp * gp.w + dv * gv.w;
+      }
+    reinterpret_cast<float4*>(a.out)[((size_t)tile * P4 + grp) * EL_TM + row] = x;
+  }
+}
+
 // ---- row-major <-> blocked ---------------------------------------------------------------------------------
 // One CTA moves 32 rows x F floats through shared memory so that both the row-major side (rows contiguous) and the
 // blocked side (32 consecutive agents of one float4 group contiguous) are accessed in full 128-byte lines.
@@ -229,6 +258,17 @@ int adjoint_gather(const ab200_drift_desc* d, const float* base, const float* co
   k.ntiles = (int)((B + EL_TM - 1) / EL_TM);
   for (int i = 0; i < n; ++i) { k.gx[i] = gx[i]; k.cpv[i] = cpv[i]; }
   adjoint_gather_kernel<<<launch_cfg((int64_t)k.ntiles * EL_TM * ((k.P + k.H) / 4)), 256, 0, st>>>(k);
+  return check_launch();
+}
+
+int ga_assemble(const ab200_drift_desc* d, const float* base, const float* const* gx, int n, const float* dp, const float* dv,
+                int64_t B, float* out, cudaStream_t st) {
+  if (n < 0 || n > EL_MAX_A || d->pos_dim % 4 || d->ctx_dim % 4) return AB200_ERR_BAD_ARG;
+  AssembleArgs k{};
+  k.base = base; k.out = out; k.n = n; k.P = d->pos_dim; k.H = d->ctx_dim;
+  k.ntiles = (int)((B + EL_TM - 1) / EL_TM);
+  for (int i = 0; i < n; ++i) { k.gx[i] = gx[i]; k.dp[i] = dp[i]; k.dv[i] = dv[i]; }
+  ga_assemble_kernel<<<launch_cfg((int64_t)k.ntiles * EL_TM * (k.P / 4)), 256, 0, st>>>(k);
   return check_launch();
 }
 

@@ -206,6 +206,15 @@ class TcEngine:
         _lib.check(rc, "ab200_stage_backward")
         self.used += self.ntiles
 
+    def stage_upstream(self, g_base, gx: Sequence[torch.Tensor], dp: Sequence[float], dv: Sequence[float], B: int, out) -> None:
+        """out = g_base + sum_l dp[l] gx[l].p + dv[l] gx[l].v (the upstream gradient of a stage, as a buffer)."""
+        n = len(gx)
+        dpa = (C.c_float * max(n, 1))(*[float(x) for x in dp])
+        dva = (C.c_float * max(n, 1))(*[float(x) for x in dv])
+        rc = self.L.ab200_stage_upstream(C.byref(self.desc), g_base.data_ptr(), C.cast(_ptr_array(gx), C.c_void_p), n,
+                                         C.cast(dpa, C.c_void_p), C.cast(dva, C.c_void_p), B, out.data_ptr(), _stream())
+        _lib.check(rc, "ab200_stage_upstream")
+
     def adjoint_gather(self, base, gx: Sequence[torch.Tensor], cpv: Sequence[float], B: int, out) -> None:
         n = len(gx)
         ca = (C.c_float * max(n, 1))(*[float(x) for x in cpv])
@@ -456,28 +465,46 @@ def dopri5_forward(eng: TcEngine, y0: torch.Tensor, t_host: Sequence[float], rto
 
 def dopri5_backward(eng: TcEngine, steps: List[_Dopri5Step], grad_y_path: torch.Tensor):
     """Discrete adjoint of the accepted steps (step sizes are constants, as in torchdiffeq where the controller runs
-    under no_grad) -> (grad_y0 row-major, grad_w_flat).  The FSAL evaluation is differentiated where it is used: as
-    stage 1 of the following step and, when a dense-output row needs k_7, as stage 7 of its own step."""
+    under no_grad) -> (grad_y0 row-major, grad_w_flat).  The FSAL evaluation k_7 of a step is the k_1 of the next one
+    (one forward evaluation): the next step hands the gradient w.r.t. its k_1 back (`lam_a`) and this step
+    differentiates the evaluation once, as its stage 7; only the very first step differentiates its own stage 1."""
     T, B, D = grad_y_path.shape
     dev = grad_y_path.device
     P = eng.P
     eng.backward_begin(B, stages_per_flush=7)
     lam = blocked_zeros(B, D, dev)          # dL/dy at the end of the step being processed
     lam_prev = blocked_zeros(B, D, dev)
+    lam_a = None                            # dL/da_7 handed over by the following step (None: nothing depends on it)
+    lam_a_buf = [blocked_zeros(B, P, dev) for _ in range(2)]
     G_y0 = blocked_zeros(B, D, dev)
     G_a = [blocked_zeros(B, P, dev) for _ in range(7)]
     gx = [blocked_zeros(B, D, dev) for _ in range(7)]
     g_blk = blocked_zeros(B, D, dev)
-    for st in reversed(steps):
+    for si in range(len(steps) - 1, -1, -1):
+        st = steps[si]
         dt = st.dt
         # step-level gradients: the end state y1 = y0 + dt sum c_sol k, and every dense-output row inside the step
         eng.combine_backward(lam, DOPRI5.combo(DOPRI5.b, dt), B, G_y0, G_a, accumulate=False)
         for (k, x) in st.outputs:
             rows_block(grad_y_path[k], g_blk)
             eng.combine_backward(g_blk, DOPRI5.combo(dopri5_interp_weights(x), dt), B, G_y0, G_a, accumulate=True)
-        n_stage = 7 if st.outputs else 6      # without dense output nothing depends on k_7 inside this step
-        times = [st.t0 + DOPRI5.c[i] * dt for i in range(n_stage)]
-        _step_backward_n(eng, DOPRI5, B, st.yb, st.A, times, dt, G_y0, G_a, gx, lam_prev, n_stage)
+        if lam_a is not None:
+            G_a[6].add_(lam_a)
+        last = 6 if (st.outputs or lam_a is not None) else 5      # stage 7 only matters if something used k_7
+        first = 0 if si == 0 else 1                                # k_1 of a later step belongs to the previous step
+        combos = [DOPRI5.stage_input(i, dt) for i in range(7)]
+        times = [st.t0 + DOPRI5.c[i] * dt for i in range(7)]
+        for i in range(last, first - 1, -1):
+            later = [l for l in range(i + 1, last + 1) if combos[l].cpa[i] != 0.0 or combos[l].cva[i] != 0.0]
+            eng.stage_backward(st.yb, [st.A[j] for j in range(i)], combos[i], times[i], B, G_a[i], [gx[l] for l in later],
+                               [combos[l].cpa[i] for l in later], [combos[l].cva[i] for l in later], gx[i])
+        used = list(range(first, last + 1))
+        eng.adjoint_gather(G_y0, [gx[i] for i in used], [combos[i].cpv for i in used], B, lam_prev)
+        if first == 1:
+            later = [l for l in range(1, last + 1) if combos[l].cpa[0] != 0.0 or combos[l].cva[0] != 0.0]
+            lam_a = lam_a_buf[si % 2]
+            eng.stage_upstream(G_a[0], [gx[l] for l in later], [combos[l].cpa[0] for l in later], [combos[l].cva[0] for l in later],
+                               B, lam_a)
         eng.flush()
         lam, lam_prev = lam_prev, lam
     rows_block(grad_y_path[0], lam, accumulate=True)

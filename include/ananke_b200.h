@@ -177,6 +177,12 @@ int ab200_stage_backward(const ab200_drift_desc* d, const void* image, const flo
                          int32_t blob0, int32_t nblobs, void* partial, ab200_stream_t stream);
 int ab200_adjoint_gather(const ab200_drift_desc* d, const float* base, const float* const* gx, int32_t n,
                          const float* cpv_host, int64_t B, float* out, ab200_stream_t stream);
+/* The upstream gradient of a stage written out as a buffer instead of being consumed by ab200_stage_backward:
+ *     g_a_out (blocked [Bp][P]) = g_base + sum_l dp[l] gx[l].p + dv[l] gx[l].v
+ * dopri5's first stage of a step IS the last (FSAL) evaluation of the previous step (tdq rk_common.py _adaptive_step:
+ * f1 is carried over as f0), so its gradient is handed to that step's stage 7 rather than differentiated twice. */
+int ab200_stage_upstream(const ab200_drift_desc* d, const float* g_base, const float* const* gx, int32_t n_g,
+                         const float* dp_host, const float* dv_host, int64_t B, float* g_a_out, ab200_stream_t stream);
 int ab200_wgrad_accumulate(const ab200_drift_desc* d, const void* spill, int32_t nblobs, int32_t used, void* partial,
                            ab200_stream_t stream);
 int ab200_wgrad_finalize(const ab200_drift_desc* d, const void* partial, float* grad_w_flat, ab200_stream_t stream);
