@@ -61,9 +61,12 @@ SIGNATURES = {
     "ab200_stage_image_bytes": (_sz, [_dp]),
     "ab200_stage_pack": (C.c_int, [_dp, _vp, _vp, _sz, _vp]),
     "ab200_stage_forward": (C.c_int, [_dp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i32, _vp]),
+    "ab200_stage_forward_fused": (C.c_int, [_dp, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _vp, _vp, _i32, _vp]),
     "ab200_stage_spill_bytes": (_sz, [_dp, _i32]),
     "ab200_wgrad_partial_bytes": (_sz, [_dp]),
     "ab200_stage_backward": (C.c_int, [_dp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _sz, _i32, _i32, _vp, _vp]),
+    "ab200_stage_backward_fused": (C.c_int, [_dp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _sz, _i32, _i32,
+                                             _vp, _vp]),
     "ab200_adjoint_gather": (C.c_int, [_dp, _vp, _vp, _i32, _vp, _i64, _vp, _vp]),
     "ab200_stage_upstream": (C.c_int, [_dp, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _vp]),
     "ab200_wgrad_accumulate": (C.c_int, [_dp, _vp, _i32, _i32, _vp, _vp]),

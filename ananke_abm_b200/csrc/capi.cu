@@ -44,11 +44,17 @@ size_t stage_tc_image_bytes();
 int stage_tc_pack(const float* w_flat, uint8_t* image, cudaStream_t st);
 int stage_fwd_tc(const ab200_drift_desc* d, const uint8_t* image, const float* y0, const float* const* a_ptrs, const void* desc_v,
                  int64_t B, float* a_out, float* y_out, double* err_sumsq, int half_ops, cudaStream_t st);
+int stage_fwd_tc_multi(const ab200_drift_desc* d, const uint8_t* image, const float* y0, const float* const* a_ptrs, const void* descs_v,
+                       int n_stage, float* const* a_outs, int64_t B, float* y_out, double* err_sumsq, int half_ops, cudaStream_t st);
 int stage_bwd_tc(const ab200_drift_desc* d, const uint8_t* image, const float* y0, const float* const* a_ptrs, const void* desc_v,
                  int64_t B, const float* g_base, const float* const* gx_ptrs, int n_g, const float* dp, const float* dv, float* gx_out,
                  void* spill, int blob0, int nblobs, float* g_bout, cudaStream_t st);
 int ga_assemble(const ab200_drift_desc* d, const float* base, const float* const* gx, int n, const float* dp, const float* dv,
                 int64_t B, float* out, cudaStream_t st);
+int stage_bwd_tc_multi(const ab200_drift_desc* d, const uint8_t* image, const float* y0, const float* const* a_ptrs,
+                       const void* descs_v, int n_stage, const float* const* g_base, float* const* gx_out, const int32_t* n_g,
+                       const int32_t* gx_src, const float* const* gx_ext, const float* dp, const float* dv, int64_t B, void* spill,
+                       int blob0, int nblobs, float* g_bout, cudaStream_t st);
 int adjoint_gather(const ab200_drift_desc* d, const float* base, const float* const* gx, int n, const float* cpv, int64_t B, float* out,
                    cudaStream_t st);
 size_t wgrad_spill_bytes(int nblobs);
@@ -212,6 +218,16 @@ int ab200_stage_forward(const ab200_drift_desc* d, const void* image, const floa
   return stage_fwd_tc(d, (const uint8_t*)image, y0, a, s, B, a_out, y_out, err_sumsq, operand_format, (cudaStream_t)stream);
 }
 
+int ab200_stage_forward_fused(const ab200_drift_desc* d, const void* image, const float* y0, const float* const* a,
+                              const ab200_stage_desc* stages, int32_t n_stage, float* const* a_out, int64_t B, float* y_out,
+                              double* err_sumsq, int32_t operand_format, ab200_stream_t stream) {
+  if (!d || !image || !y0 || !stages || !a || B <= 0 || n_stage < 1 || n_stage > AB200_STAGE_MAX_A) return AB200_ERR_BAD_ARG;
+  if (!stage_shape_ok(d)) return AB200_ERR_UNSUPPORTED;
+  if ((err_sumsq && !y_out) || operand_format < 0 || operand_format > 1) return AB200_ERR_BAD_ARG;
+  return stage_fwd_tc_multi(d, (const uint8_t*)image, y0, a, stages, n_stage, a_out, B, y_out, err_sumsq, operand_format,
+                            (cudaStream_t)stream);
+}
+
 size_t ab200_stage_spill_bytes(const ab200_drift_desc* d, int32_t nblobs) {
   return (stage_shape_ok(d) && nblobs > 0) ? wgrad_spill_bytes(nblobs) : 0;
 }
@@ -228,6 +244,20 @@ int ab200_stage_backward(const ab200_drift_desc* d, const void* image, const flo
   if (nblobs <= 0 || spill_bytes < wgrad_spill_bytes(nblobs)) return AB200_ERR_WORKSPACE;
   return stage_bwd_tc(d, (const uint8_t*)image, y0, a, s, B, g_base, gx, n_g, dp_host, dv_host, gx_out, spill, blob0, nblobs,
                       wgrad_bout_ptr(partial), (cudaStream_t)stream);
+}
+
+int ab200_stage_backward_fused(const ab200_drift_desc* d, const void* image, const float* y0, const float* const* a,
+                               const ab200_stage_desc* stages, int32_t n_stage, const float* const* g_base, float* const* gx_out,
+                               const int32_t* n_g, const int32_t* gx_src, const float* const* gx_ext, const float* dp_host,
+                               const float* dv_host, int64_t B, void* spill, size_t spill_bytes, int32_t blob0, int32_t nblobs,
+                               void* partial, ab200_stream_t stream) {
+  if (!d || !image || !y0 || !a || !stages || !g_base || !gx_out || !n_g || !gx_src || !dp_host || !dv_host || !spill || !partial ||
+      B <= 0 || n_stage < 1 || n_stage > AB200_STAGE_MAX_A)
+    return AB200_ERR_BAD_ARG;
+  if (!stage_shape_ok(d)) return AB200_ERR_UNSUPPORTED;
+  if (nblobs <= 0 || spill_bytes < wgrad_spill_bytes(nblobs)) return AB200_ERR_WORKSPACE;
+  return stage_bwd_tc_multi(d, (const uint8_t*)image, y0, a, stages, n_stage, g_base, gx_out, n_g, gx_src, gx_ext, dp_host, dv_host, B,
+                            spill, blob0, nblobs, wgrad_bout_ptr(partial), (cudaStream_t)stream);
 }
 
 int ab200_stage_upstream(const ab200_drift_desc* d, const float* g_base, const float* const* gx, int32_t n_g, const float* dp_host,

@@ -21,23 +21,29 @@
 namespace ab200 {
 using namespace stc;
 
+struct BwdStageParams {       // one stage of a fused (latest-first) sequence
+  int n_a;                    // the stage input combined a[0 .. n_a)
+  Combo in;
+  float t;
+  const float* g_base;        // blocked [Bp][64] or null: step-level part of dL/da_out
+  int n_g;                    // later stages (earlier entries of this launch, or buffers of earlier launches) that read a_out
+  const float* gx[MAX_A];     // their dL/d(stage input), blocked [Bp][160]
+  float dp[MAX_A], dv[MAX_A]; // and coefficients (that stage's in.cpa / in.cva entry for a_out)
+  float* gx_out;              // blocked [Bp][160]: [g_p, g_v, g_h] of this stage (written)
+  int blob0;                  // blob index of tile 0 for this stage
+};
+
 struct StageBwdArgs {
   const uint8_t* wimg;
   const float* y0;            // blocked [Bp][160]
   const float* a[MAX_A];      // blocked [Bp][64]
-  int n_a;
-  Combo in;
-  float t, period;
-  const float* g_base;        // blocked [Bp][64] or null: step-level part of dL/da_out
-  const float* gx[MAX_A];     // blocked [Bp][160]: dL/d(stage input) of the later stages that read a_out
-  int n_g;
-  float dp[MAX_A], dv[MAX_A]; // their coefficients (the later stage's in.cpa / in.cva entry for a_out)
-  float* gx_out;              // blocked [Bp][160]: [g_p, g_v, g_h] of this stage (written)
+  int n_stage;
+  BwdStageParams st[MAX_A];
+  float period;
   uint8_t* spill;             // blob buffer (SpillLayout)
   float* g_bout;              // [64] atomically accumulated column sums of dL/da_out (bias gradient of the output layer)
   int64_t B;
   int ntiles;
-  int blob0;                  // blob index of tile 0 of this launch
   int nblobs;                 // blobs the spill buffer was sized for
   int flags;
   int* status;
@@ -48,8 +54,8 @@ template <int NG>
 __device__ __forceinline__ void spill_groups(uint8_t* blob, int fg0, int row, const uint32_t* o) {
 #pragma unroll
   for (int q = 0; q < NG; ++q)
-    *reinterpret_cast<uint4*>(blob + (size_t)(fg0 + q) * wg::FG_BYTES + (size_t)row * 16) =
-        make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+    __stcs(reinterpret_cast<uint4*>(blob + (size_t)(fg0 + q) * wg::FG_BYTES + (size_t)row * 16),
+           make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]));     // streaming: blobs must not evict what the next stage re-reads
 }
 
 // forward hidden epilogue with mask capture and spill.  RES: residual add of z.  Result -> ACT (if TO_ACT), z (if KEEP),
@@ -119,30 +125,10 @@ __global__ void __launch_bounds__(THREADS, 1) stage_bwd_tc_kernel(const __grid_c
 #pragma unroll 1
   for (int tile = blockIdx.x * NSLOT + c.slot; tile < a.ntiles; tile += gridDim.x * NSLOT) {
     const bool valid = (int64_t)tile * TM + c.row < a.B;      // padding rows: zeros in, nothing stored
-    const int blob = a.blob0 + tile;
-    if (a.flags & 4) {   // per-line prefetch of exactly the rows this thread will read in its next tile
-      const int nt = tile + gridDim.x * NSLOT;
-      if (nt < a.ntiles) {
-        prefetch_rows_l2(a.y0, nt, YF4, c.hf * 8, 8, c.row);
-        prefetch_rows_l2(a.y0, nt, YF4, AF4 + c.hf * 8, 8, c.row);
-        prefetch_rows_l2(a.y0, nt, YF4, 2 * AF4 + c.hf * 4, 4, c.row);
-        for (int s = 0; s < a.n_a; ++s) prefetch_rows_l2(a.a[s], nt, AF4, c.hf * 8, 8, c.row);
-        if (a.g_base != nullptr) prefetch_rows_l2(a.g_base, nt, AF4, c.hf * 8, 8, c.row);
-        for (int s = 0; s < a.n_g; ++s) {
-          prefetch_rows_l2(a.gx[s], nt, YF4, c.hf * 8, 8, c.row);
-          prefetch_rows_l2(a.gx[s], nt, YF4, AF4 + c.hf * 8, 8, c.row);
-        }
-      }
-    }
-    if (c.stid == 0 && (a.flags & 2)) {   // next tile of this slot -> L2 while this one computes
-      const int nt = tile + gridDim.x * NSLOT;
-      if (nt < a.ntiles) {
-        prefetch_tile_l2(a.y0, nt, YF4);
-        for (int s = 0; s < a.n_a; ++s) prefetch_tile_l2(a.a[s], nt, AF4);
-        if (a.g_base != nullptr) prefetch_tile_l2(a.g_base, nt, AF4);
-        for (int s = 0; s < a.n_g; ++s) prefetch_tile_l2(a.gx[s], nt, YF4);
-      }
-    }
+#pragma unroll 1
+   for (int si = 0; si < a.n_stage; ++si) {                   // all stages of the step for this tile: later stages' gx come from L2
+    const BwdStageParams& sp = a.st[si];
+    const int blob = sp.blob0 + tile;
 
     // ---- stage input -> ACT / HB / TB and the X blob (features: p 0..63, v 64..127, h 128..159, sin, cos, 1)
     uint8_t* xb = a.spill + S.x1(blob);
@@ -154,14 +140,15 @@ __global__ void __launch_bounds__(THREADS, 1) stage_bwd_tc_kernel(const __grid_c
       for (int j = 0; j < 4; ++j) {
         const float4 pv = ldro(blk4(a.y0, tile, YF4, f0 + j, c.row));
         const float4 vv = ldro(blk4(a.y0, tile, YF4, AF4 + f0 + j, c.row));
-        pin[4 * j] = pv.x + a.in.cpv * vv.x; pin[4 * j + 1] = pv.y + a.in.cpv * vv.y;
-        pin[4 * j + 2] = pv.z + a.in.cpv * vv.z; pin[4 * j + 3] = pv.w + a.in.cpv * vv.w;
+        const float cpv = sp.in.cpv;
+        pin[4 * j] = pv.x + cpv * vv.x; pin[4 * j + 1] = pv.y + cpv * vv.y;
+        pin[4 * j + 2] = pv.z + cpv * vv.z; pin[4 * j + 3] = pv.w + cpv * vv.w;
         vin[4 * j] = vv.x; vin[4 * j + 1] = vv.y; vin[4 * j + 2] = vv.z; vin[4 * j + 3] = vv.w;
       }
 #pragma unroll 1
-      for (int s = 0; s < a.n_a; ++s) {
+      for (int s = 0; s < sp.n_a; ++s) {
         {
-          const float cp = a.in.cpa[s], cv = a.in.cva[s];
+          const float cp = sp.in.cpa[s], cv = sp.in.cva[s];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float4 x = ldro(blk4(a.a[s], tile, AF4, f0 + j, c.row));
@@ -191,10 +178,10 @@ __global__ void __launch_bounds__(THREADS, 1) stage_bwd_tc_kernel(const __grid_c
       tmem_st8(c.tmem + c.lane_sel + C_HB + (uint32_t)(c.hf * 8), o);
       spill_groups<2>(xb, 2 * P / 8 + c.hf * 2, c.row, o);
     }
-    write_time_block(c, a.t, a.period);
+    write_time_block(c, sp.t, a.period);
     if (c.hf == 0) {   // time-feature / bias feature groups of the X blob: [sin, cos, 1, 0...], [0...]
       float s, co;
-      time_features(a.t, a.period, s, co);
+      time_features(sp.t, a.period, s, co);
       const uint32_t o[8] = {pack_bf16(s, co), pack_bf16(1.0f, 0.0f), 0u, 0u, 0u, 0u, 0u, 0u};
       spill_groups<2>(xb, (2 * P + H) / 8, c.row, o);
     }
@@ -220,13 +207,13 @@ __global__ void __launch_bounds__(THREADS, 1) stage_bwd_tc_kernel(const __grid_c
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (a.g_base != nullptr) x = ldro(blk4(a.g_base, tile, AF4, c.hf * 8 + j, c.row));     // padding rows are zero
+        if (sp.g_base != nullptr) x = ldro(blk4(sp.g_base, tile, AF4, c.hf * 8 + j, c.row));     // padding rows are zero
 #pragma unroll 1
-        for (int s = 0; s < a.n_g; ++s) {
-          {
-            const float4 gp = ldro(blk4(a.gx[s], tile, YF4, c.hf * 8 + j, c.row));
-            const float4 gq = ldro(blk4(a.gx[s], tile, YF4, AF4 + c.hf * 8 + j, c.row));
-            const float dp = a.dp[s], dv = a.dv[s];
+        for (int s = 0; s < sp.n_g; ++s) {
+          {   // coherent loads: an earlier stage of THIS launch (same thread) may have written these
+            const float4 gp = *blk4(sp.gx[s], tile, YF4, c.hf * 8 + j, c.row);
+            const float4 gq = *blk4(sp.gx[s], tile, YF4, AF4 + c.hf * 8 + j, c.row);
+            const float dp = sp.dp[s], dv = sp.dv[s];
             x.x += dp * gp.x + dv * gq.x; x.y += dp * gp.y + dv * gq.y; x.z += dp * gp.z + dv * gq.z; x.w += dp * gp.w + dv * gq.w;
           }
         }
@@ -281,9 +268,9 @@ __global__ void __launch_bounds__(THREADS, 1) stage_bwd_tc_kernel(const __grid_c
       if (valid) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          *blk4(a.gx_out, tile, YF4, f0 + j, c.row) = make_float4(__uint_as_float(rp[4 * j]), __uint_as_float(rp[4 * j + 1]),
+          *blk4(sp.gx_out, tile, YF4, f0 + j, c.row) = make_float4(__uint_as_float(rp[4 * j]), __uint_as_float(rp[4 * j + 1]),
                                                                    __uint_as_float(rp[4 * j + 2]), __uint_as_float(rp[4 * j + 3]));
-          *blk4(a.gx_out, tile, YF4, AF4 + f0 + j, c.row) = make_float4(__uint_as_float(rv[4 * j]), __uint_as_float(rv[4 * j + 1]),
+          *blk4(sp.gx_out, tile, YF4, AF4 + f0 + j, c.row) = make_float4(__uint_as_float(rv[4 * j]), __uint_as_float(rv[4 * j + 1]),
                                                                          __uint_as_float(rv[4 * j + 2]), __uint_as_float(rv[4 * j + 3]));
         }
       }
@@ -295,11 +282,12 @@ __global__ void __launch_bounds__(THREADS, 1) stage_bwd_tc_kernel(const __grid_c
       if (valid) {
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          *blk4(a.gx_out, tile, YF4, 2 * AF4 + c.hf * 4 + j, c.row) =
+          *blk4(sp.gx_out, tile, YF4, 2 * AF4 + c.hf * 4 + j, c.row) =
               make_float4(__uint_as_float(rh[4 * j]), __uint_as_float(rh[4 * j + 1]), __uint_as_float(rh[4 * j + 2]),
                           __uint_as_float(rh[4 * j + 3]));
       }
     }
+   }
   }
   stage_teardown(tmem_base);
 }
@@ -308,39 +296,54 @@ struct StageBwdHost {   // mirrors the head of ab200_stage_desc
   int32_t n_a;
   float in_cpv, in_cpa[MAX_A], in_cva[MAX_A];
   float t;
+  float rest[4 * (MAX_A + 1) + 3];      // out_* / err_* / rtol / atol of ab200_stage_desc (unused here)
 };
+static_assert(sizeof(StageBwdHost) == sizeof(ab200_stage_desc), "stage descriptor layout");
 
-int stage_bwd_tc(const ab200_drift_desc* d, const uint8_t* image, const float* y0, const float* const* a_ptrs, const void* desc_v,
-                 int64_t B, const float* g_base, const float* const* gx_ptrs, int n_g, const float* dp, const float* dv, float* gx_out,
-                 void* spill, int blob0, int nblobs, float* g_bout, cudaStream_t st) {
-  const StageBwdHost& h = *reinterpret_cast<const StageBwdHost*>(desc_v);
-  if (h.n_a < 0 || h.n_a > MAX_A || n_g < 0 || n_g > MAX_A) return AB200_ERR_BAD_ARG;
+// Fused sequence, latest stage first.  Stage s: upstream gradient = g_base[s] + sum over its n_g[s] sources; a source is
+// gx_src[s][l] >= 0 -> the gx_out of entry gx_src[s][l] of THIS sequence, or < 0 -> external buffer gx_ext[-1 - idx].
+int stage_bwd_tc_multi(const ab200_drift_desc* d, const uint8_t* image, const float* y0, const float* const* a_ptrs,
+                       const void* descs_v, int n_stage, const float* const* g_base, float* const* gx_out, const int32_t* n_g,
+                       const int32_t* gx_src, const float* const* gx_ext, const float* dp, const float* dv, int64_t B, void* spill,
+                       int blob0, int nblobs, float* g_bout, cudaStream_t st) {
+  const StageBwdHost* hs = reinterpret_cast<const StageBwdHost*>(descs_v);
+  if (n_stage < 1 || n_stage > MAX_A) return AB200_ERR_BAD_ARG;
   StageBwdArgs k{};
   k.wimg = image;
   k.y0 = y0;
-  k.n_a = h.n_a;
-  for (int i = 0; i < MAX_A; ++i) {
-    k.a[i] = (i < h.n_a) ? a_ptrs[i] : nullptr;
-    k.in.cpa[i] = h.in_cpa[i];
-    k.in.cva[i] = h.in_cva[i];
-    k.gx[i] = (i < n_g) ? gx_ptrs[i] : nullptr;
-    k.dp[i] = (i < n_g) ? dp[i] : 0.f;
-    k.dv[i] = (i < n_g) ? dv[i] : 0.f;
+  k.ntiles = (int)((B + TM - 1) / TM);
+  int max_a = 0;
+  for (int s = 0; s < n_stage; ++s) {
+    const StageBwdHost& h = hs[s];
+    if (h.n_a < 0 || h.n_a > MAX_A || n_g[s] < 0 || n_g[s] > MAX_A || !gx_out[s]) return AB200_ERR_BAD_ARG;
+    if (n_g[s] == 0 && !g_base[s]) return AB200_ERR_BAD_ARG;
+    max_a = h.n_a > max_a ? h.n_a : max_a;
+    BwdStageParams& sp = k.st[s];
+    sp.n_a = h.n_a;
+    sp.in.cpv = h.in_cpv;
+    for (int i = 0; i < MAX_A; ++i) { sp.in.cpa[i] = h.in_cpa[i]; sp.in.cva[i] = h.in_cva[i]; }
+    sp.t = h.t;
+    sp.g_base = g_base[s];
+    sp.n_g = n_g[s];
+    for (int l = 0; l < n_g[s]; ++l) {
+      const int src = gx_src[s * MAX_A + l];
+      if (src >= s) return AB200_ERR_BAD_ARG;                      // only stages processed earlier in this sequence
+      sp.gx[l] = src >= 0 ? gx_out[src] : gx_ext[-1 - src];
+      sp.dp[l] = dp[s * MAX_A + l];
+      sp.dv[l] = dv[s * MAX_A + l];
+    }
+    sp.gx_out = gx_out[s];
+    sp.blob0 = blob0 + s * k.ntiles;
   }
-  k.n_g = n_g;
-  k.in.cpv = h.in_cpv;
-  k.t = h.t;
+  if (blob0 < 0 || blob0 + n_stage * k.ntiles > nblobs) return AB200_ERR_BAD_ARG;
+  for (int i = 0; i < MAX_A; ++i) k.a[i] = (i < max_a) ? a_ptrs[i] : nullptr;
+  k.n_stage = n_stage;
   k.period = d->time_period;
-  k.g_base = g_base;
-  k.gx_out = gx_out;
   k.spill = (uint8_t*)spill;
   k.g_bout = g_bout;
   k.B = B;
-  k.ntiles = (int)((B + TM - 1) / TM);
-  k.blob0 = blob0;
   k.nblobs = nblobs;
   k.flags = stage_flags();
-  if (blob0 < 0 || blob0 + k.ntiles > nblobs) return AB200_ERR_BAD_ARG;
   k.status = reinterpret_cast<int*>(const_cast<uint8_t*>(image) + 2 * IMG_STRIDE);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -351,6 +354,19 @@ int stage_bwd_tc(const ab200_drift_desc* d, const uint8_t* image, const float* y
   if (e != cudaSuccess) { set_cuda_error(e); return AB200_ERR_CUDA; }
   stage_bwd_tc_kernel<<<grid, THREADS, W_BYTES, st>>>(k);
   return check_launch();
+}
+
+int stage_bwd_tc(const ab200_drift_desc* d, const uint8_t* image, const float* y0, const float* const* a_ptrs, const void* desc_v,
+                 int64_t B, const float* g_base, const float* const* gx_ptrs, int n_g, const float* dp, const float* dv, float* gx_out,
+                 void* spill, int blob0, int nblobs, float* g_bout, cudaStream_t st) {
+  if (n_g < 0 || n_g > MAX_A) return AB200_ERR_BAD_ARG;
+  const float* gb[1] = {g_base};
+  float* go[1] = {gx_out};
+  int32_t ng[1] = {n_g};
+  int32_t src[MAX_A];
+  float dpa[MAX_A], dva[MAX_A];
+  for (int l = 0; l < MAX_A; ++l) { src[l] = -1 - l; dpa[l] = l < n_g ? dp[l] : 0.f; dva[l] = l < n_g ? dv[l] : 0.f; }
+  return stage_bwd_tc_multi(d, image, y0, a_ptrs, desc_v, 1, gb, go, ng, src, gx_ptrs, dpa, dva, B, spill, blob0, nblobs, g_bout, st);
 }
 
 }  // namespace ab200

@@ -90,25 +90,34 @@ int stage_tc_pack(const float* w_flat, uint8_t* image, cudaStream_t st) {
   return check_launch();
 }
 
-struct StageFwdArgs {
-  const uint8_t* wimg;
-  const float* y0;            // blocked [Bp][160]
-  const float* a[MAX_A];      // blocked [Bp][64] each
-  int n_a;
+struct StageParams {          // one stage of a fused sequence
+  int n_a;                    // reads a[0 .. n_a)
   Combo in;                   // stage input
-  float t, period;
+  float t;
   float* a_out;               // blocked [Bp][64] or null
   float* y_out;               // blocked [Bp][160] or null
   Combo out;                  // y_out combination; index n_a of cpa/cva multiplies this stage's own output
-  double* err_sumsq;          // or null
   Combo err;                  // error combination (cpv unused); index n_a multiplies this stage's own output
-  float rtol, atol;
+  int want_err;
+};
+
+struct StageFwdArgs {
+  const uint8_t* wimg;
+  const float* y0;            // blocked [Bp][160]
+  const float* a[MAX_A];      // blocked [Bp][64] each; a stage may read what an EARLIER stage of this launch wrote
+  int n_stage;
+  StageParams st[MAX_A];
+  double* err_sumsq;          // or null
+  float rtol, atol, period;
   int64_t B;
   int ntiles;
   int flags;
   int* status;
 };
 
+// All stages of one solver step (or attempt) for a tile before moving to the next tile: the accelerations a stage needs
+// were written by the SAME thread a few microseconds earlier and are still in L2, so HBM sees y0 once, each a_j once
+// (its write) and the step result once -- instead of re-reading every earlier a_j from HBM in every stage launch.
 template <bool HALF>
 __global__ void __launch_bounds__(THREADS, 1) stage_fwd_tc_kernel(const __grid_constant__ StageFwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -124,56 +133,7 @@ __global__ void __launch_bounds__(THREADS, 1) stage_fwd_tc_kernel(const __grid_c
   for (int tile = blockIdx.x * NSLOT + c.slot; tile < a.ntiles; tile += gridDim.x * NSLOT) {
     const bool valid = (int64_t)tile * TM + c.row < a.B;      // padding rows hold zeros and are never stored to
     STAGE_TRACE(c, 9);
-    if (a.flags & 4) {   // per-line prefetch of exactly the rows this thread will read in its next tile
-      const int nt = tile + gridDim.x * NSLOT;
-      if (nt < a.ntiles) {
-        prefetch_rows_l2(a.y0, nt, YF4, c.hf * 8, 8, c.row);
-        prefetch_rows_l2(a.y0, nt, YF4, AF4 + c.hf * 8, 8, c.row);
-        prefetch_rows_l2(a.y0, nt, YF4, 2 * AF4 + c.hf * 4, 4, c.row);
-        for (int s = 0; s < a.n_a; ++s) prefetch_rows_l2(a.a[s], nt, AF4, c.hf * 8, 8, c.row);
-      }
-    }
-    if (c.stid == 0 && (a.flags & 2)) {   // next tile of this slot -> L2 while this one computes
-      const int nt = tile + gridDim.x * NSLOT;
-      if (nt < a.ntiles) {
-        prefetch_tile_l2(a.y0, nt, YF4);
-        for (int s = 0; s < a.n_a; ++s) prefetch_tile_l2(a.a[s], nt, AF4);
-      }
-    }
-
-    // ---- stage input -> ACT (bf16), context h -> HB, time/bias block -> TB          (all buffers blocked, see stage_tc.cuh)
-#pragma unroll
-    for (int ch = 0; ch < 2; ++ch) {       // 16 dims of p and of v per pass
-      const int f0 = c.hf * 8 + ch * 4;    // first float4 group of this pass
-      float pin[16], vin[16];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 pv = ldro(blk4(a.y0, tile, YF4, f0 + j, c.row));
-        const float4 vv = ldro(blk4(a.y0, tile, YF4, AF4 + f0 + j, c.row));
-        pin[4 * j] = pv.x + a.in.cpv * vv.x; pin[4 * j + 1] = pv.y + a.in.cpv * vv.y;
-        pin[4 * j + 2] = pv.z + a.in.cpv * vv.z; pin[4 * j + 3] = pv.w + a.in.cpv * vv.w;
-        vin[4 * j] = vv.x; vin[4 * j + 1] = vv.y; vin[4 * j + 2] = vv.z; vin[4 * j + 3] = vv.w;
-      }
-#pragma unroll 1
-      for (int s = 0; s < a.n_a; ++s) {
-        {
-          const float cp = a.in.cpa[s], cv = a.in.cva[s];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 x = ldro(blk4(a.a[s], tile, AF4, f0 + j, c.row));
-            pin[4 * j] += cp * x.x; pin[4 * j + 1] += cp * x.y; pin[4 * j + 2] += cp * x.z; pin[4 * j + 3] += cp * x.w;
-            vin[4 * j] += cv * x.x; vin[4 * j + 1] += cv * x.y; vin[4 * j + 2] += cv * x.z; vin[4 * j + 3] += cv * x.w;
-          }
-        }
-      }
-      uint32_t o[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = pack2<HALF>(pin[2 * j], pin[2 * j + 1]);
-      tmem_st8(c.tmem + c.lane_sel + C_ACT + (uint32_t)(f0 * 2), o);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = pack2<HALF>(vin[2 * j], vin[2 * j + 1]);
-      tmem_st8(c.tmem + c.lane_sel + C_ACT + (uint32_t)(P / 2 + f0 * 2), o);
-    }
+    // context h -> HB once per tile (constant along the step)
     {
       uint32_t o[8];
 #pragma unroll
@@ -184,39 +144,76 @@ __global__ void __launch_bounds__(THREADS, 1) stage_fwd_tc_kernel(const __grid_c
       }
       tmem_st8(c.tmem + c.lane_sel + C_HB + (uint32_t)(c.hf * 8), o);
     }
-    write_time_block<HALF>(c, a.t, a.period);
-    STAGE_TRACE(c, 10);
 
-    // ---- drift net
-    uint32_t z[32];
-    run_layer<false, (2 * P + H) / 16, true, HID, HID, false, HALF>(c, C_ACT, OFF_W1);
-    epi_relu<true, HALF>(c, z);
 #pragma unroll 1
-    for (int r = 0; r < NRES; ++r) {
-      uint32_t dummy[32];
-      run_layer<false, HID / 16, true, HID, HID, false, HALF>(c, C_ACT, off_hh(2 * r));
-      epi_relu<false, HALF>(c, dummy);
-      run_layer<false, HID / 16, true, HID, HID, false, HALF>(c, C_ACT, off_hh(2 * r + 1));
-      epi_residual<HALF>(c, z);
-    }
-    run_layer<false, HID / 16, true, P, P, false, HALF>(c, C_ACT, OFF_WO);
+    for (int si = 0; si < a.n_stage; ++si) {
+      const StageParams& sp = a.st[si];
+      const int n_a = sp.n_a;
+      // ---- stage input -> ACT (16-bit), time/bias block -> TB          (all buffers blocked, see stage_tc.cuh)
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {       // 16 dims of p and of v per pass
+        const int f0 = c.hf * 8 + ch * 4;    // first float4 group of this pass
+        float pin[16], vin[16];
+        const float cpv = sp.in.cpv;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 pv = ldro(blk4(a.y0, tile, YF4, f0 + j, c.row));
+          const float4 vv = ldro(blk4(a.y0, tile, YF4, AF4 + f0 + j, c.row));
+          pin[4 * j] = pv.x + cpv * vv.x; pin[4 * j + 1] = pv.y + cpv * vv.y;
+          pin[4 * j + 2] = pv.z + cpv * vv.z; pin[4 * j + 3] = pv.w + cpv * vv.w;
+          vin[4 * j] = vv.x; vin[4 * j + 1] = vv.y; vin[4 * j + 2] = vv.z; vin[4 * j + 3] = vv.w;
+        }
+#pragma unroll 1
+        for (int s = 0; s < n_a; ++s) {
+          const float cp = sp.in.cpa[s], cv = sp.in.cva[s];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 x = *blk4(a.a[s], tile, AF4, f0 + j, c.row);      // coherent load: may have been written by this launch
+            pin[4 * j] += cp * x.x; pin[4 * j + 1] += cp * x.y; pin[4 * j + 2] += cp * x.z; pin[4 * j + 3] += cp * x.w;
+            vin[4 * j] += cv * x.x; vin[4 * j + 1] += cv * x.y; vin[4 * j + 2] += cv * x.z; vin[4 * j + 3] += cv * x.w;
+          }
+        }
+        uint32_t o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = pack2<HALF>(pin[2 * j], pin[2 * j + 1]);
+        tmem_st8(c.tmem + c.lane_sel + C_ACT + (uint32_t)(f0 * 2), o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = pack2<HALF>(vin[2 * j], vin[2 * j + 1]);
+        tmem_st8(c.tmem + c.lane_sel + C_ACT + (uint32_t)(P / 2 + f0 * 2), o);
+      }
+      write_time_block<HALF>(c, sp.t, a.period);
+      STAGE_TRACE(c, 10);
 
-    // ---- output epilogue: this thread's 32 acceleration dims (float4 groups hf*8 ..)
-    STAGE_TRACE(c, 11);
-    {
+      // ---- drift net
+      uint32_t z[32];
+      run_layer<false, (2 * P + H) / 16, true, HID, HID, false, HALF>(c, C_ACT, OFF_W1);
+      epi_relu<true, HALF>(c, z);
+#pragma unroll 1
+      for (int r = 0; r < NRES; ++r) {
+        uint32_t dummy[32];
+        run_layer<false, HID / 16, true, HID, HID, false, HALF>(c, C_ACT, off_hh(2 * r));
+        epi_relu<false, HALF>(c, dummy);
+        run_layer<false, HID / 16, true, HID, HID, false, HALF>(c, C_ACT, off_hh(2 * r + 1));
+        epi_residual<HALF>(c, z);
+      }
+      run_layer<false, HID / 16, true, P, P, false, HALF>(c, C_ACT, OFF_WO);
+
+      // ---- output epilogue: this thread's 32 acceleration dims (float4 groups hf*8 ..)
+      STAGE_TRACE(c, 11);
       uint32_t r[32];
       tmem_ld32(c.tmem + c.lane_sel + C_ACC + (uint32_t)(c.hf * 32), r);
       tmem_ld_wait();
       const int f0 = c.hf * 8;
-      if (a.a_out != nullptr && valid) {
+      if (sp.a_out != nullptr && valid) {
 #pragma unroll
         for (int j = 0; j < 8; ++j)
-          *blk4(a.a_out, tile, AF4, f0 + j, c.row) = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                                                  __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+          *blk4(sp.a_out, tile, AF4, f0 + j, c.row) = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                                   __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
       }
-      if (a.y_out != nullptr) {
-        const bool want_err = a.err_sumsq != nullptr;
-        const float oc = a.out.cpa[a.n_a], ov = a.out.cva[a.n_a], ecp = a.err.cpa[a.n_a], ecv = a.err.cva[a.n_a];
+      if (sp.y_out != nullptr) {
+        const bool want_err = sp.want_err != 0;
+        const float oc = sp.out.cpa[n_a], ov = sp.out.cva[n_a], ecp = sp.err.cpa[n_a], ecv = sp.err.cva[n_a];
+        const float ocpv = sp.out.cpv;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {       // one float4 group of p and of v per pass
           const float4 p0 = ldro(blk4(a.y0, tile, YF4, f0 + j, c.row));
@@ -227,29 +224,27 @@ __global__ void __launch_bounds__(THREADS, 1) stage_fwd_tc_kernel(const __grid_c
           float po[4], vo[4], ep[4], ev[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            po[e] = p0r[e] + a.out.cpv * v0r[e] + oc * ao[e];
+            po[e] = p0r[e] + ocpv * v0r[e] + oc * ao[e];
             vo[e] = v0r[e] + ov * ao[e];
             ep[e] = ecp * ao[e];
             ev[e] = ecv * ao[e];
           }
 #pragma unroll 1
-          for (int s = 0; s < a.n_a; ++s) {
-            {
-              const float4 x = ldro(blk4(a.a[s], tile, AF4, f0 + j, c.row));
-              const float xs[4] = {x.x, x.y, x.z, x.w};
-              const float cp = a.out.cpa[s], cv = a.out.cva[s], xp = a.err.cpa[s], xv = a.err.cva[s];
+          for (int s = 0; s < n_a; ++s) {
+            const float4 x = *blk4(a.a[s], tile, AF4, f0 + j, c.row);
+            const float xs[4] = {x.x, x.y, x.z, x.w};
+            const float cp = sp.out.cpa[s], cv = sp.out.cva[s], xp = sp.err.cpa[s], xv = sp.err.cva[s];
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                po[e] += cp * xs[e];
-                vo[e] += cv * xs[e];
-                ep[e] += xp * xs[e];
-                ev[e] += xv * xs[e];
-              }
+            for (int e = 0; e < 4; ++e) {
+              po[e] += cp * xs[e];
+              vo[e] += cv * xs[e];
+              ep[e] += xp * xs[e];
+              ev[e] += xv * xs[e];
             }
           }
           if (valid) {
-            *blk4(a.y_out, tile, YF4, f0 + j, c.row) = make_float4(po[0], po[1], po[2], po[3]);
-            *blk4(a.y_out, tile, YF4, AF4 + f0 + j, c.row) = make_float4(vo[0], vo[1], vo[2], vo[3]);
+            *blk4(sp.y_out, tile, YF4, f0 + j, c.row) = make_float4(po[0], po[1], po[2], po[3]);
+            *blk4(sp.y_out, tile, YF4, AF4 + f0 + j, c.row) = make_float4(vo[0], vo[1], vo[2], vo[3]);
             if (want_err) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
@@ -264,7 +259,7 @@ __global__ void __launch_bounds__(THREADS, 1) stage_fwd_tc_kernel(const __grid_c
         if (valid) {   // context h rides along unchanged (dh/dt = 0)
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            *blk4(a.y_out, tile, YF4, 2 * AF4 + c.hf * 4 + j, c.row) = ldro(blk4(a.y0, tile, YF4, 2 * AF4 + c.hf * 4 + j, c.row));
+            *blk4(sp.y_out, tile, YF4, 2 * AF4 + c.hf * 4 + j, c.row) = ldro(blk4(a.y0, tile, YF4, 2 * AF4 + c.hf * 4 + j, c.row));
         }
       }
     }
@@ -293,30 +288,41 @@ struct StageFwdHost {   // mirrors ab200_stage_desc in the public header
   float rtol, atol;
 };
 
-int stage_fwd_tc(const ab200_drift_desc* d, const uint8_t* image, const float* y0, const float* const* a_ptrs, const void* desc_v,
-                 int64_t B, float* a_out, float* y_out, double* err_sumsq, int half_ops, cudaStream_t st) {
-  const StageFwdHost& h = *reinterpret_cast<const StageFwdHost*>(desc_v);
-  if (h.n_a < 0 || h.n_a > MAX_A) return AB200_ERR_BAD_ARG;
+// n_stage fused stages: stage s reads a_ptrs[0 .. descs[s].n_a), writes a_outs[s] (may be null); the LAST stage may also
+// write y_out (+ the error norm) with its out / err combinations.
+int stage_fwd_tc_multi(const ab200_drift_desc* d, const uint8_t* image, const float* y0, const float* const* a_ptrs, const void* descs_v,
+                       int n_stage, float* const* a_outs, int64_t B, float* y_out, double* err_sumsq, int half_ops, cudaStream_t st) {
+  const StageFwdHost* hs = reinterpret_cast<const StageFwdHost*>(descs_v);
+  if (n_stage < 1 || n_stage > MAX_A) return AB200_ERR_BAD_ARG;
   StageFwdArgs k{};
   k.wimg = image + (half_ops ? IMG_STRIDE : 0);
   k.y0 = y0;
-  for (int i = 0; i < MAX_A; ++i) k.a[i] = (i < h.n_a) ? a_ptrs[i] : nullptr;
-  k.n_a = h.n_a;
-  k.in.cpv = h.in_cpv;
-  k.out.cpv = h.out_cpv;
-  k.err.cpv = 0.f;
-  for (int i = 0; i < MAX_A; ++i) { k.in.cpa[i] = h.in_cpa[i]; k.in.cva[i] = h.in_cva[i]; }
-  for (int i = 0; i <= MAX_A; ++i) {
-    k.out.cpa[i] = h.out_cpa[i]; k.out.cva[i] = h.out_cva[i];
-    k.err.cpa[i] = h.err_pa[i]; k.err.cva[i] = h.err_va[i];
+  int max_a = 0;
+  for (int s = 0; s < n_stage; ++s) {
+    const StageFwdHost& h = hs[s];
+    if (h.n_a < 0 || h.n_a > MAX_A) return AB200_ERR_BAD_ARG;
+    max_a = h.n_a > max_a ? h.n_a : max_a;
+    StageParams& sp = k.st[s];
+    sp.n_a = h.n_a;
+    sp.in.cpv = h.in_cpv;
+    sp.out.cpv = h.out_cpv;
+    sp.err.cpv = 0.f;
+    for (int i = 0; i < MAX_A; ++i) { sp.in.cpa[i] = h.in_cpa[i]; sp.in.cva[i] = h.in_cva[i]; }
+    for (int i = 0; i <= MAX_A; ++i) {
+      sp.out.cpa[i] = h.out_cpa[i]; sp.out.cva[i] = h.out_cva[i];
+      sp.err.cpa[i] = h.err_pa[i]; sp.err.cva[i] = h.err_va[i];
+    }
+    sp.t = h.t;
+    sp.a_out = a_outs ? a_outs[s] : nullptr;
+    sp.y_out = (s == n_stage - 1) ? y_out : nullptr;
+    sp.want_err = (s == n_stage - 1 && err_sumsq != nullptr) ? 1 : 0;
   }
-  k.t = h.t;
+  for (int i = 0; i < MAX_A; ++i) k.a[i] = (i < max_a) ? a_ptrs[i] : nullptr;
+  k.n_stage = n_stage;
   k.period = d->time_period;
-  k.a_out = a_out;
-  k.y_out = y_out;
   k.err_sumsq = err_sumsq;
-  k.rtol = h.rtol;
-  k.atol = h.atol;
+  k.rtol = hs[n_stage - 1].rtol;
+  k.atol = hs[n_stage - 1].atol;
   k.B = B;
   k.ntiles = (int)((B + TM - 1) / TM);
   k.flags = stage_flags();
@@ -331,6 +337,12 @@ int stage_fwd_tc(const ab200_drift_desc* d, const uint8_t* image, const float* y
   if (e != cudaSuccess) { set_cuda_error(e); return AB200_ERR_CUDA; }
   kern<<<grid, THREADS, W_BYTES, st>>>(k);
   return check_launch();
+}
+
+int stage_fwd_tc(const ab200_drift_desc* d, const uint8_t* image, const float* y0, const float* const* a_ptrs, const void* desc_v,
+                 int64_t B, float* a_out, float* y_out, double* err_sumsq, int half_ops, cudaStream_t st) {
+  float* outs[1] = {a_out};
+  return stage_fwd_tc_multi(d, image, y0, a_ptrs, desc_v, 1, outs, B, y_out, err_sumsq, half_ops, st);
 }
 
 }  // namespace ab200

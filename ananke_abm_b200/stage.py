@@ -157,6 +157,41 @@ class TcEngine:
                                         1 if (self.fp16_forward if fp16 is None else fp16) else 0, _stream())
         _lib.check(rc, "ab200_stage_forward")
 
+    def stage_forward_fused(self, y0, a_bufs: Sequence[torch.Tensor], stages: Sequence, B: int, y_out=None, cout: Optional[Combo] = None,
+                            err_sumsq=None, cerr: Optional[Combo] = None, rtol: float = 0.0, atol: float = 0.0,
+                            fp16: Optional[bool] = None) -> None:
+        """Consecutive stages of one step in ONE launch.  `stages` = [(n_a, Combo in, t, a_out tensor or None), ...]: stage s
+        reads a_bufs[:n_a] (possibly written by earlier stages of this call) and writes its a_out; the last stage may
+        also produce y_out (cout) and the error norm (cerr)."""
+        n = len(stages)
+        descs = (StageDesc * n)()
+        outs = (C.c_void_p * n)()
+        for i, (n_a, cin, t, a_out) in enumerate(stages):
+            s = descs[i]
+            s.n_a = n_a
+            s.in_cpv = cin.cpv
+            _fill(s.in_cpa, cin.cpa[:n_a])
+            _fill(s.in_cva, cin.cva[:n_a])
+            s.t = float(t)
+            outs[i] = None if a_out is None else a_out.data_ptr()
+        last = descs[n - 1]
+        n_last = stages[-1][0]
+        if cout is not None:
+            last.out_cpv = cout.cpv
+            _fill(last.out_cpa, cout.cpa[:n_last + 1])
+            _fill(last.out_cva, cout.cva[:n_last + 1])
+        if cerr is not None:
+            _fill(last.err_pa, cerr.cpa[:n_last + 1])
+            _fill(last.err_va, cerr.cva[:n_last + 1])
+        last.rtol, last.atol = float(rtol), float(atol)
+        ptrs = (C.c_void_p * MAX_A)(*([t.data_ptr() for t in a_bufs[:MAX_A]] + [None] * (MAX_A - min(len(a_bufs), MAX_A))))
+        rc = self.L.ab200_stage_forward_fused(C.byref(self.desc), self.image.data_ptr(), y0.data_ptr(), C.cast(ptrs, C.c_void_p),
+                                              C.cast(descs, C.c_void_p), n, C.cast(outs, C.c_void_p), B,
+                                              None if y_out is None else y_out.data_ptr(),
+                                              None if err_sumsq is None else err_sumsq.data_ptr(),
+                                              1 if (self.fp16_forward if fp16 is None else fp16) else 0, _stream())
+        _lib.check(rc, "ab200_stage_forward_fused")
+
     def combine(self, y0, a: Sequence[torch.Tensor], c: Combo, B: int, out) -> None:
         n = len(a)
         cpa = (C.c_float * max(n, 1))(*[float(x) for x in c.cpa[:n]])
@@ -214,6 +249,43 @@ class TcEngine:
         rc = self.L.ab200_stage_upstream(C.byref(self.desc), g_base.data_ptr(), C.cast(_ptr_array(gx), C.c_void_p), n,
                                          C.cast(dpa, C.c_void_p), C.cast(dva, C.c_void_p), B, out.data_ptr(), _stream())
         _lib.check(rc, "ab200_stage_upstream")
+
+    def stage_backward_fused(self, y0, a_bufs: Sequence[torch.Tensor], stages: Sequence, B: int) -> None:
+        """The backward stages of one step in ONE launch.  `stages` (latest stage first) =
+        [(n_a, Combo in, t, g_base tensor or None, [(src, dp, dv), ...], gx_out tensor)], where `src` is the position of an
+        earlier entry of `stages` whose gx_out feeds this stage's upstream gradient."""
+        n = len(stages)
+        if self.used + n * self.ntiles > self.nblobs:
+            self.flush()
+        descs = (StageDesc * n)()
+        g_base = (C.c_void_p * n)()
+        gx_out = (C.c_void_p * n)()
+        n_g = (C.c_int32 * n)()
+        src = (C.c_int32 * (n * MAX_A))()
+        dp = (C.c_float * (n * MAX_A))()
+        dv = (C.c_float * (n * MAX_A))()
+        for i, (n_a, cin, t, gb, sources, gout) in enumerate(stages):
+            s = descs[i]
+            s.n_a = n_a
+            s.in_cpv = cin.cpv
+            _fill(s.in_cpa, cin.cpa[:n_a])
+            _fill(s.in_cva, cin.cva[:n_a])
+            s.t = float(t)
+            g_base[i] = None if gb is None else gb.data_ptr()
+            gx_out[i] = gout.data_ptr()
+            n_g[i] = len(sources)
+            for l, (sidx, a_, b_) in enumerate(sources):
+                src[i * MAX_A + l] = sidx
+                dp[i * MAX_A + l] = float(a_)
+                dv[i * MAX_A + l] = float(b_)
+        ptrs = (C.c_void_p * MAX_A)(*([t.data_ptr() for t in a_bufs[:MAX_A]] + [None] * (MAX_A - min(len(a_bufs), MAX_A))))
+        rc = self.L.ab200_stage_backward_fused(C.byref(self.desc), self.image.data_ptr(), y0.data_ptr(), C.cast(ptrs, C.c_void_p),
+                                               C.cast(descs, C.c_void_p), n, C.cast(g_base, C.c_void_p), C.cast(gx_out, C.c_void_p),
+                                               C.cast(n_g, C.c_void_p), C.cast(src, C.c_void_p), None, C.cast(dp, C.c_void_p),
+                                               C.cast(dv, C.c_void_p), B, self.spill.data_ptr(), self.spill.numel(), self.used,
+                                               self.nblobs, self.partial.data_ptr(), _stream())
+        _lib.check(rc, "ab200_stage_backward_fused")
+        self.used += n * self.ntiles
 
     def adjoint_gather(self, base, gx: Sequence[torch.Tensor], cpv: Sequence[float], B: int, out) -> None:
         n = len(gx)
@@ -305,25 +377,35 @@ def rk4_forward(eng: TcEngine, y0: torch.Tensor, t_host: Sequence[float], save_s
         A = acc[n if save_stages else 0]
         yn = yb[n if save_stages else n % 2]
         yn1 = yb[n + 1 if save_stages else (n + 1) % 2]
-        for i in range(3):
-            eng.stage_forward(yn, [A[j] for j in range(i)], RK38.stage_input(i, dt), t0 + RK38.c[i] * dt, B, a_out=A[i])
-        eng.stage_forward(yn, [A[0], A[1], A[2]], RK38.stage_input(3, dt), float(t_host[n + 1]), B, y_out=yn1,
-                          cout=RK38.combo(RK38.b, dt))
+        stages = [(i, RK38.stage_input(i, dt), t0 + RK38.c[i] * dt, A[i]) for i in range(3)]
+        stages.append((3, RK38.stage_input(3, dt), float(t_host[n + 1]), None))
+        eng.stage_forward_fused(yn, [A[0], A[1], A[2]], stages, B, y_out=yn1, cout=RK38.combo(RK38.b, dt))
         rows_unblock(yn1, B, eng.D, out=y_path[n + 1])
     return y_path, ((yb, acc) if save_stages else None)
 
 
+def stages_backward(eng: TcEngine, tab: Tableau, B: int, yn, A: Sequence[torch.Tensor], stage_times: Sequence[float], dt: float,
+                    G_a_base: Sequence[Optional[torch.Tensor]], gx: Sequence[torch.Tensor], first: int, last: int):
+    """Backward of stages last..first of ONE explicit Runge-Kutta step in a single fused launch (latest stage first).
+    Returns the stage input combinations (their cpv feed `adjoint_gather`)."""
+    combos = [tab.stage_input(i, dt) for i in range(last + 1)]
+    order = list(range(last, first - 1, -1))
+    pos = {i: k for k, i in enumerate(order)}
+    stages = []
+    for i in order:
+        later = [l for l in range(i + 1, last + 1) if combos[l].cpa[i] != 0.0 or combos[l].cva[i] != 0.0]
+        stages.append((i, combos[i], stage_times[i], G_a_base[i], [(pos[l], combos[l].cpa[i], combos[l].cva[i]) for l in later], gx[i]))
+    eng.stage_backward_fused(yn, list(A), stages, B)
+    return combos
+
+
 def step_backward(eng: TcEngine, tab: Tableau, B: int, yn, A: Sequence[torch.Tensor], stage_times: Sequence[float], dt: float,
                   G_y0_base, G_a_base: Sequence[Optional[torch.Tensor]], gx: Sequence[torch.Tensor], out) -> None:
-    """Adjoint of the stages of ONE explicit Runge-Kutta step (any tableau), latest stage first.  G_y0_base / G_a_base
-    hold the step-level gradients w.r.t. y0 and the stage accelerations (from the step's linear outputs); `out` receives
-    dL/dy0 of the step.  `gx[i]` is scratch for stage i's dL/d(stage input)."""
+    """Adjoint of the stages of ONE explicit Runge-Kutta step (any tableau).  G_y0_base / G_a_base hold the step-level
+    gradients w.r.t. y0 and the stage accelerations (from the step's linear outputs); `out` receives dL/dy0 of the step.
+    `gx[i]` is scratch for stage i's dL/d(stage input)."""
     s = len(stage_times)
-    combos = [tab.stage_input(i, dt) for i in range(s)]
-    for i in range(s - 1, -1, -1):
-        later = [l for l in range(i + 1, s) if combos[l].cpa[i] != 0.0 or combos[l].cva[i] != 0.0]
-        eng.stage_backward(yn, [A[j] for j in range(i)], combos[i], stage_times[i], B, G_a_base[i], [gx[l] for l in later],
-                           [combos[l].cpa[i] for l in later], [combos[l].cva[i] for l in later], gx[i])
+    combos = stages_backward(eng, tab, B, yn, A, stage_times, dt, G_a_base, gx, 0, s - 1)
     eng.adjoint_gather(G_y0_base, [gx[i] for i in range(s)], [combos[i].cpv for i in range(s)], B, out)
 
 
@@ -424,11 +506,11 @@ def dopri5_forward(eng: TcEngine, y0: torch.Tensor, t_host: Sequence[float], rto
         assert _cast_time(t1 + dt, time_dtype) > t1, "underflow in dt {}".format(dt)
         ta = t1
         tb = _cast_time(ta + dt, time_dtype)
-        for i in range(1, 6):
-            eng.stage_forward(y_cur, A[:i], DOPRI5.stage_input(i, dt), _cast_time(ta + DOPRI5.c[i] * dt, time_dtype), B, a_out=A[i])
+        stages = [(i, DOPRI5.stage_input(i, dt), _cast_time(ta + DOPRI5.c[i] * dt, time_dtype), A[i]) for i in range(1, 6)]
+        stages.append((6, DOPRI5.stage_input(6, dt), tb, A[6]))
         sumsq.zero_()
-        eng.stage_forward(y_cur, A[:6], DOPRI5.stage_input(6, dt), tb, B, a_out=A[6], y_out=y_next, cout=DOPRI5.combo(c_sol, dt),
-                          err_sumsq=sumsq, cerr=DOPRI5.combo(c_err, dt), rtol=rtol, atol=atol)
+        eng.stage_forward_fused(y_cur, A, stages, B, y_out=y_next, cout=DOPRI5.combo(c_sol, dt), err_sumsq=sumsq,
+                                cerr=DOPRI5.combo(c_err, dt), rtol=rtol, atol=atol)
         stats.n_evals += 6
         ratio = float(torch.sqrt(sumsq[0] / (B * D)))
         if ratio != ratio:
@@ -494,10 +576,7 @@ def dopri5_backward(eng: TcEngine, steps: List[_Dopri5Step], grad_y_path: torch.
         first = 0 if si == 0 else 1                                # k_1 of a later step belongs to the previous step
         combos = [DOPRI5.stage_input(i, dt) for i in range(7)]
         times = [st.t0 + DOPRI5.c[i] * dt for i in range(7)]
-        for i in range(last, first - 1, -1):
-            later = [l for l in range(i + 1, last + 1) if combos[l].cpa[i] != 0.0 or combos[l].cva[i] != 0.0]
-            eng.stage_backward(st.yb, [st.A[j] for j in range(i)], combos[i], times[i], B, G_a[i], [gx[l] for l in later],
-                               [combos[l].cpa[i] for l in later], [combos[l].cva[i] for l in later], gx[i])
+        stages_backward(eng, DOPRI5, B, st.yb, st.A, times, dt, G_a, gx, first, last)
         used = list(range(first, last + 1))
         eng.adjoint_gather(G_y0, [gx[i] for i in used], [combos[i].cpv for i in used], B, lam_prev)
         if first == 1:

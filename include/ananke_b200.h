@@ -157,6 +157,14 @@ int ab200_stage_pack(const ab200_drift_desc* d, const float* w_flat, void* image
 int ab200_stage_forward(const ab200_drift_desc* d, const void* image, const float* y0, const float* const* a,
                         const ab200_stage_desc* s, int64_t B, float* a_out, float* y_out, double* err_sumsq,
                         int32_t operand_format, ab200_stream_t stream);
+/* Several consecutive stages of ONE step (or step attempt) in a single launch: stage s reads a[0 .. stages[s].n_a) --
+ * which may include buffers an earlier stage of the same launch wrote through a_out[] -- and writes a_out[s] (NULL =
+ * not stored); only the last stage may produce y_out / err_sumsq (its out_* / err_* fields).  Each tile runs all stages
+ * before the next tile, so the accelerations are re-read from L2, not HBM.  `a` must hold AB200_STAGE_MAX_A entries. */
+int ab200_stage_forward_fused(const ab200_drift_desc* d, const void* image, const float* y0, const float* const* a,
+                              const ab200_stage_desc* stages, int32_t n_stage, float* const* a_out, int64_t B,
+                              float* y_out, double* err_sumsq, int32_t operand_format, ab200_stream_t stream);
+
 /* Vector-Jacobian product of one stage = what autograd does for the ops of one `func` call inside the solver
  * (mode_sep/train/train.py:162).  The upstream gradient is assembled in the kernel as
  *     dL/da_out = g_base + sum_{l < n_g} dp[l] gx[l].p + dv[l] gx[l].v
@@ -177,6 +185,17 @@ int ab200_stage_backward(const ab200_drift_desc* d, const void* image, const flo
                          int32_t blob0, int32_t nblobs, void* partial, ab200_stream_t stream);
 int ab200_adjoint_gather(const ab200_drift_desc* d, const float* base, const float* const* gx, int32_t n,
                          const float* cpv_host, int64_t B, float* out, ab200_stream_t stream);
+/* The backward stages of ONE step in a single launch, latest stage first: entry s of `stages` / g_base / gx_out / n_g is
+ * one stage; its n_g[s] gradient sources are gx_src[s * 7 + l] >= 0 -> gx_out of an EARLIER entry of this call, or
+ * < 0 -> the external buffer gx_ext[-1 - index]; coefficients dp/dv[s * 7 + l].  Blobs of entry s go to blob indices
+ * blob0 + s * ntiles + tile.  Each tile runs all stages before the next tile, so the gx of later stages and the stage
+ * inputs are re-read from L2 (the blobs are written with streaming stores so that they do not evict them).
+ * `a` must hold AB200_STAGE_MAX_A entries. */
+int ab200_stage_backward_fused(const ab200_drift_desc* d, const void* image, const float* y0, const float* const* a,
+                               const ab200_stage_desc* stages, int32_t n_stage, const float* const* g_base,
+                               float* const* gx_out, const int32_t* n_g, const int32_t* gx_src, const float* const* gx_ext,
+                               const float* dp_host, const float* dv_host, int64_t B, void* spill, size_t spill_bytes,
+                               int32_t blob0, int32_t nblobs, void* partial, ab200_stream_t stream);
 /* The upstream gradient of a stage written out as a buffer instead of being consumed by ab200_stage_backward:
  *     g_a_out (blocked [Bp][P]) = g_base + sum_l dp[l] gx[l].p + dv[l] gx[l].v
  * dopri5's first stage of a step IS the last (FSAL) evaluation of the previous step (tdq rk_common.py _adaptive_step:
