@@ -335,6 +335,15 @@ def blocked_zeros(B: int, F: int, device) -> torch.Tensor:
     return torch.zeros(padded_rows(B) * F, dtype=torch.float32, device=device)
 
 
+def blocked_empty(B: int, F: int, device) -> torch.Tensor:
+    """Like `blocked_zeros` but only the padding rows of the last tile are zeroed (the kernels overwrite every real row)."""
+    Bp = padded_rows(B)
+    buf = torch.empty(Bp * F, dtype=torch.float32, device=device)
+    if Bp != B:
+        buf.view(Bp // TM, F // 4, TM, 4)[-1, :, B % TM:, :] = 0.0
+    return buf
+
+
 def rows_block(src: torch.Tensor, dst: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
     """row-major [B, F] -> blocked (dst = src, or dst += src)."""
     L = _lib.lib()
@@ -527,8 +536,8 @@ def dopri5_forward(eng: TcEngine, y0: torch.Tensor, t_host: Sequence[float], rto
                 k += 1
             if save_steps:
                 steps.append(_Dopri5Step(y_cur, A, ta, dt, outs))
-                y_cur, y_next = y_next, blocked_zeros(B, D, dev)
-                A = [A[6]] + [blocked_zeros(B, P, dev) for _ in range(6)]
+                y_cur, y_next = y_next, blocked_empty(B, D, dev)
+                A = [A[6]] + [blocked_empty(B, P, dev) for _ in range(6)]
             else:
                 y_cur, y_next = y_next, y_cur
                 A[0], A[6] = A[6], A[0]

@@ -277,14 +277,16 @@ def run_ours(args):
             Gb = st.rows_block(torch.randn(Bc, 64, device=dev) * 1e-3)
             GX = [st.blocked_zeros(Bc, 160, dev) for _ in range(4)]
             dtk = 0.25
-            combos = [st.RK38.stage_input(i, dtk) for i in range(4)]
+            tab, first, last = (st.DOPRI5, 1, 6) if adaptive else (st.RK38, 0, 3)      # the fused launch of one step's backward stages
+            A = A + [st.rows_block(torch.randn(Bc, 64, device=dev) * 0.1) for _ in range(4)]
+            GX = GX + [st.blocked_zeros(Bc, 160, dev) for _ in range(3)]
+            times = [1.0 + tab.c[i] * dtk for i in range(last + 1)]
+            n_fused = last - first + 1
+            eng.backward_begin(Bc, n_fused)
 
             def one_step_bwd_stages():
                 eng.used = 0
-                for i in (3, 2, 1, 0):
-                    later = list(range(i + 1, 4))
-                    eng.stage_backward(yb, A[:i], combos[i], 1.0, Bc, Gb, [GX[l] for l in later], [combos[l].cpa[i] for l in later],
-                                       [combos[l].cva[i] for l in later], GX[i])
+                st.stages_backward(eng, tab, Bc, yb, A[:last], times, dtk, [Gb] * 7, GX, first, last)
             for _ in range(3):
                 one_step_bwd_stages()
             torch.cuda.synchronize()
@@ -294,9 +296,9 @@ def run_ours(args):
             k1.record()
             torch.cuda.synchronize()
             eng.check_status()
-            kern_ms = k0.elapsed_time(k1) / (reps * 4)
-            kern_units = Bc                      # agent-stage evaluations per launch
-            kern_name = "stage_bwd_tc_kernel (one Runge-Kutta stage: recompute + dgrad + blob spill)"
+            kern_ms = k0.elapsed_time(k1) / reps
+            kern_units = Bc * n_fused            # agent-stage evaluations per launch
+            kern_name = "stage_bwd_tc_kernel (%d fused Runge-Kutta stages per launch: recompute + dgrad + blob spill)" % n_fused
             kern_flop_unit = ALG_FLOP_FWD // 4 * 2    # recompute + dgrad of one stage (wgrad runs in wgrad_tc_kernel)
             kern_bytes_unit = ALG_BYTES_FWDBWD / 4.0
             del eng, yb, A, Gb, GX

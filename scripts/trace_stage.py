@@ -17,13 +17,13 @@ for it in range(3):
     eng.stage_forward(y0, [], stage.RK38.stage_input(0, 0.25), 1.0, B, a_out=aout)
     torch.cuda.synchronize()
     L.ab200_debug_stage_trace(buf, cnt)
-names = {1: 'enter', 2: 'st_wait+fence', 3: 'slot_sync', 4: 'issued', 5: 'mma_done', 9: 'tile_start', 10: 'prologue_done', 11: 'net_done'}
+names = {31: 'i:enter', 32: 'i:fenced', 33: 'i:ready', 34: 'i:mma0', 35: 'i:mmaN', 36: 'i:commit', 1: 'enter', 2: 'st_wait+fence', 3: 'slot_sync', 4: 'issued', 5: 'mma_done', 9: 'tile_start', 10: 'prologue_done', 11: 'net_done'}
 for slot in range(2):
     n = min(cnt[slot], 2048)
     ev = [(buf[(slot * 2048 + i) * 2], buf[(slot * 2048 + i) * 2 + 1]) for i in range(n)]
     t0 = ev[0][1]
     print(f"slot {slot}: {n} events")
     prev = t0
-    for tag, t in ev[:70]:
+    for tag, t in ev[40:110]:
         print(f"   {names.get(tag, tag):14s} t={t - t0:8d}  +{t - prev:6d}")
         prev = t
