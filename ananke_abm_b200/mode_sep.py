@@ -38,6 +38,14 @@ class ModeSepConfig:                       # mode_sep/config.py:9-71 (fields the
     sde_noise_strength: float = 0.01
     softmax_tau: float = 0.2
     precision: str = "f32"                 # ananke_b200 extension: 'f32' | 'bf16' (tensor-core drift GEMMs)
+    error_norm: str = "shard"              # dopri5 across ranks: 'global' = one RMS norm over all shards (single-process parity)
+
+
+def _solver_options(config) -> dict:
+    opt = {"precision": getattr(config, "precision", "f32")}
+    if config.ode_method == "dopri5" and opt["precision"] == "bf16":
+        opt["error_norm"] = getattr(config, "error_norm", "shard")
+    return opt
 
 
 class ODEFunc(nn.Module):                  # model.py:30-38 -- parameter holder; evaluated through WrappedSDE
@@ -89,7 +97,7 @@ class ModeSepModel(nn.Module):
         if self.config.enable_sde and self.config.sde_noise_strength > 0.0:
             raise NotImplementedError("the SDE branch is out of scope (SURVEY.md §8f-4)")
         return odeint(self.odefunc, y0, times_union, method=self.config.ode_method, rtol=self.config.rtol,
-                      atol=self.config.atol, options={"precision": getattr(self.config, "precision", "f32")})
+                      atol=self.config.atol, options=_solver_options(self.config))
 
     def head(self, y_path: torch.Tensor):
         E, H = self.config.emb_dim, self.config.context_dim

@@ -17,7 +17,7 @@ from torch import nn
 
 from .gnn_embed import GATEmbed
 from .graph import ZoneCSR
-from .mode_sep import ModeSepConfig, ODEFunc, WrappedSDE
+from .mode_sep import ModeSepConfig, ODEFunc, WrappedSDE, _solver_options
 from .odeint import odeint
 
 
@@ -45,7 +45,7 @@ class GATODEModel(nn.Module):
 
     def integrate(self, y0, times_union) -> torch.Tensor:
         return odeint(self.odefunc, y0, times_union, method=self.config.ode_method, rtol=self.config.rtol,
-                      atol=self.config.atol, options={"precision": getattr(self.config, "precision", "f32")})
+                      atol=self.config.atol, options=_solver_options(self.config))
 
     def head(self, y_path, class_table):
         E, H = self.config.emb_dim, self.config.context_dim

@@ -466,9 +466,19 @@ def _cast_time(v: float, time_dtype) -> float:
 
 def dopri5_forward(eng: TcEngine, y0: torch.Tensor, t_host: Sequence[float], rtol: float, atol: float, *, first_step=None,
                    safety: float = 0.9, ifactor: float = 10.0, dfactor: float = 0.2, max_num_steps: int = 2 ** 31 - 1,
-                   time_dtype=torch.float64, save_steps: bool = False, stats: Optional[Dopri5Stats] = None, fp16_forward: bool = True):
+                   time_dtype=torch.float64, save_steps: bool = False, stats: Optional[Dopri5Stats] = None, fp16_forward: bool = True,
+                   error_norm: str = "shard", group=None):
     """y0 row-major [B, D] -> y_path [T, B, D] (dense output at the requested times), and the accepted steps when
-    `save_steps`.  One host read of the squared-error sum per attempted step decides accept / reject."""
+    `save_steps`.  One host read of the squared-error sum per attempted step decides accept / reject.
+    error_norm="global": when agents are sharded over ranks, the squared-error sum and the element count are all-reduced
+    (2 doubles per attempt) so that every rank takes the step sequence a single process would take on the whole batch --
+    torchdiffeq's RMS norm runs over ALL agents; "shard" uses the local agents only."""
+    import torch.distributed as dist
+    use_global = error_norm == "global" and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    n_elems = torch.tensor([float(y0.shape[0] * y0.shape[1])], dtype=torch.float64, device=y0.device)
+    if use_global:
+        dist.all_reduce(n_elems, group=group)
+    n_elems = float(n_elems.item())
     B, T = y0.shape[0], len(t_host)
     dev = y0.device
     D, P = eng.D, eng.P
@@ -489,7 +499,10 @@ def dopri5_forward(eng: TcEngine, y0: torch.Tensor, t_host: Sequence[float], rto
     # ---- initial step size (torchdiffeq misc.py _select_initial_step; Hairer, Norsett & Wanner II.4)
     if first_step is None:
         def rms(x):
-            return float(x.double().pow(2).mean().sqrt())
+            v = torch.stack([x.double().pow(2).sum(), torch.tensor(float(x.numel()), dtype=torch.float64, device=x.device)])
+            if use_global:
+                dist.all_reduce(v, group=group)
+            return float((v[0] / v[1]).sqrt())
         y0f = y0.float()
         f0 = torch.cat([y0f[:, P:2 * P], rows_unblock(A[0], B, P), torch.zeros(B, D - 2 * P, device=dev)], dim=1)
         scale = atol + y0f.abs() * rtol
@@ -521,7 +534,9 @@ def dopri5_forward(eng: TcEngine, y0: torch.Tensor, t_host: Sequence[float], rto
         eng.stage_forward_fused(y_cur, A, stages, B, y_out=y_next, cout=DOPRI5.combo(c_sol, dt), err_sumsq=sumsq,
                                 cerr=DOPRI5.combo(c_err, dt), rtol=rtol, atol=atol)
         stats.n_evals += 6
-        ratio = float(torch.sqrt(sumsq[0] / (B * D)))
+        if use_global:
+            dist.all_reduce(sumsq, group=group)
+        ratio = float(torch.sqrt(sumsq[0] / n_elems))
         if ratio != ratio:
             raise _lib.Ab200Error("dopri5: non-finite error estimate (state or drift overflowed)")
         n_steps += 1

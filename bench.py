@@ -116,6 +116,7 @@ def build_model(cfg, precision, device):
     mc = ab.ModeSepConfig()
     mc.precision = precision
     mc.ode_method = cfg["method"]            # rtol = atol = 1e-5 (mode_sep/config.py:27-28) apply to dopri5 only
+    mc.error_norm = "global"                 # N > 1: one RMS error norm over all ranks' agents, as a single process would use
     model = ab.GATODEModel(7, mc, heads=cfg["heads"]).to(device)
     ei, feats = synthetic_zone_graph(cfg["Z"], k=6, seed=42)
     csr = ab.build_zone_csr(ei, cfg["Z"]).to(device)
@@ -147,6 +148,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep NCCL's banner / debug lines out of the JSON stream
         dist.init_process_group("nccl", device_id=dev)
     cfg = dict(WORKLOADS[args.workload])
     if args.agents:
