@@ -70,6 +70,10 @@ int pv_combine_bwd(const ab200_drift_desc* d, const float* g, int n_a, float cpv
 
 int rows_transpose(const float* src, float* dst, int64_t B, int F, int mode, cudaStream_t st);
 
+size_t head_workspace_bytes(int Z);
+int head_argmax(const float* emb, const float* table, int64_t M, int Z, int E, float tau, int64_t* labels, float* best, void* ws,
+                size_t ws_bytes, cudaStream_t st);
+
 static bool stage_shape_ok(const ab200_drift_desc* d) {
   return d && d->pos_dim == 64 && d->ctx_dim == 32 && d->hidden == 128 && d->n_res == 2 && d->res_act == 0 && d->potential == 0;
 }
@@ -303,6 +307,14 @@ int ab200_pv_combine_backward(const ab200_drift_desc* d, const float* g, int32_t
                               ab200_stream_t stream) {
   if (!desc_ok(d) || !g || !G_y0 || B <= 0 || (n_a > 0 && (!G_a || !cpa_host || !cva_host))) return AB200_ERR_BAD_ARG;
   return pv_combine_bwd(d, g, n_a, cpv, cpa_host, cva_host, B, G_y0, G_a, accumulate, (cudaStream_t)stream);
+}
+
+size_t ab200_head_workspace_bytes(int32_t Z, int32_t E) { return (Z > 0 && E == 64) ? head_workspace_bytes(Z) : 0; }
+
+int ab200_head_argmax(const float* pred_emb, const float* class_table, int64_t M, int32_t Z, int32_t E, float tau, int64_t* labels,
+                      float* best_logit, void* workspace, size_t workspace_bytes, ab200_stream_t stream) {
+  if (!pred_emb || !class_table || !labels || !workspace || M <= 0 || Z <= 0 || !(tau > 0.0f)) return AB200_ERR_BAD_ARG;
+  return head_argmax(pred_emb, class_table, M, Z, E, tau, labels, best_logit, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int ab200_gat_forward(const int32_t* rowptr, const int32_t* col, int32_t Z, int32_t nnz, const float* x, int32_t F_in,

@@ -1,0 +1,259 @@
+// Fused classification head + label prediction: never materialises the [B, T, Z] logits tensor.
+//
+//   reference   emb_norm = pred_emb / (|pred_emb| + 1e-8) ; table_norm = class_table / (|class_table| + 1e-8)
+//               logits = einsum("bte,ze->btz", emb_norm, table_norm) / tau            mode_sep/architecture/model.py:196-199
+//               labels = logits.argmax(-1)                                             mode_sep/inference/inference.py:57,63
+//   at configs[2] scale logits would be 1M x 97 x 10k x 4 B = 3.9 TB.
+//
+// One CTA per 128 rows (a row = one (agent, time) pair), persistent over row tiles; the zone table is streamed in
+// 128-zone chunks:
+//   warp 0      TMA producer : cp.async.bulk of the prepacked table chunk (48 KiB UMMA image) into a 3-slot ring
+//   warp 1      MMA issuer   : D[128 x 128] = A'[128 x 192] B'[128 x 192]^T on tcgen05, two TMEM accumulators ping-pong
+//   warps 2-5   epilogue     : tcgen05.ld, running top-2 (value, zone) per row; build the A' tile of the next row tile
+// Exactness: operands are 2-term bf16 splits (A' = [e_hi|e_hi|e_lo], B' = [t_hi|t_lo|t_hi], K = 3 x 64: products exact
+// to ~2^-16), the tensor cores only NOMINATE the two best zones per row; both are re-scored with fp32 FMAs on the fp32
+// normalised vectors and the winner (lower index on ties, like torch.argmax) is the label -- the reference's fp32 argmax
+// unless more than two zones lie within 1e-5 of the maximum.
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace ab200 {
+using namespace umma;
+
+constexpr int HD_E = 64, HD_K = 3 * HD_E, HD_TM = 128, HD_TN = 128;
+constexpr uint32_t HD_A_BYTES = HD_TM * HD_K * 2;          // 49,152
+constexpr uint32_t HD_B_BYTES = HD_TN * HD_K * 2;          // 49,152 per table chunk
+constexpr int HD_NS = 3;
+constexpr uint32_t HD_SMEM = HD_A_BYTES + HD_NS * HD_B_BYTES;
+constexpr int HD_THREADS = 192;
+constexpr uint32_t HD_LBO = 128u * 16u, HD_SBO = 128u;     // [128 rows][K] K-major, un-swizzled
+constexpr long long HD_WAIT = 400000000LL;
+
+// ---- table prep: normalise, keep fp32 copy, write split-bf16 UMMA images chunk by chunk ----------------------------
+__global__ void __launch_bounds__(128) head_pack_table_kernel(const float* __restrict__ table, int Z, float* __restrict__ tn,
+                                                              uint8_t* __restrict__ img) {
+  const int chunk = blockIdx.x, n = threadIdx.x, z = chunk * HD_TN + n;
+  float v[HD_E];
+  float ss = 0.0f;
+#pragma unroll
+  for (int k = 0; k < HD_E; ++k) {
+    v[k] = z < Z ? table[(size_t)z * HD_E + k] : 0.0f;
+    ss += v[k] * v[k];
+  }
+  const float inv = 1.0f / (sqrtf(ss) + 1e-8f);
+  uint8_t* blob = img + (size_t)chunk * HD_B_BYTES;
+#pragma unroll
+  for (int k = 0; k < HD_E; ++k) {
+    const float t = v[k] * inv;
+    tn[(size_t)z * HD_E + k] = t;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(t);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(t - __bfloat162float(hi));
+    *reinterpret_cast<__nv_bfloat16*>(blob + off_kmajor_noswz(n, k, HD_LBO, HD_SBO)) = hi;
+    *reinterpret_cast<__nv_bfloat16*>(blob + off_kmajor_noswz(n, HD_E + k, HD_LBO, HD_SBO)) = lo;
+    *reinterpret_cast<__nv_bfloat16*>(blob + off_kmajor_noswz(n, 2 * HD_E + k, HD_LBO, HD_SBO)) = hi;
+  }
+}
+
+struct HeadArgs {
+  const float* emb;       // [M][64] un-normalised pred_emb
+  const float* tn;        // [Zp][64] fp32 normalised table
+  const uint8_t* img;     // [nchunk][48 KiB]
+  int64_t M;
+  int Z, nchunk;
+  int ntiles;
+  float inv_tau;
+  int64_t* labels;        // [M]
+  float* best;            // [M] or null: the winning logit
+  int* status;
+};
+
+__global__ void __launch_bounds__(HD_THREADS, 1) head_argmax_kernel(const __grid_constant__ HeadArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t full[HD_NS], empty[HD_NS], acc_full[2], acc_empty[2], a_ready, a_free;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + HD_A_BYTES;
+
+  if (warp == 0) tmem_alloc<256>(&tmem_base_s);
+  if (tid == 0) {
+    for (int i = 0; i < HD_NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+    mbar_init(&a_ready, 128);
+    mbar_init(&a_free, 1);
+    mbar_fence_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const int my_tiles = (a.ntiles > (int)blockIdx.x) ? (a.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      bool ok = true;
+      for (int t = 0; t < my_tiles && ok; ++t)
+        for (int c = 0; c < a.nchunk; ++c, ++it) {
+          const int slot = it % HD_NS;
+          if (!mbar_wait(&empty[slot], (uint32_t)(((it / HD_NS) & 1) ^ 1), HD_WAIT)) { *a.status = 2; ok = false; break; }
+          mbar_arrive_expect_tx(&full[slot], HD_B_BYTES);
+          bulk_g2s(sB + slot * HD_B_BYTES, a.img + (size_t)c * HD_B_BYTES, HD_B_BYTES, &full[slot]);
+        }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(HD_TM, HD_TN);
+      const uint64_t adesc0 = make_smem_desc(smem_u32(sA), HD_LBO, HD_SBO, SWZ_NONE);
+      constexpr uint32_t step16 = (2u * HD_LBO) >> 4;
+      int it = 0, nacc = 0;
+      bool ok = true;
+      for (int t = 0; t < my_tiles && ok; ++t) {
+        if (!mbar_wait(&a_ready, (uint32_t)(t & 1), HD_WAIT)) { *a.status = 3; break; }
+        tc_fence_after();
+        for (int c = 0; c < a.nchunk; ++c, ++it, ++nacc) {
+          const int slot = it % HD_NS, buf = nacc & 1;
+          if (!mbar_wait(&acc_empty[buf], (uint32_t)(((nacc >> 1) & 1) ^ 1), HD_WAIT)) { *a.status = 4; ok = false; break; }
+          if (!mbar_wait(&full[slot], (uint32_t)((it / HD_NS) & 1), HD_WAIT)) { *a.status = 5; ok = false; break; }
+          tc_fence_after();
+          const uint64_t bdesc0 = make_smem_desc(smem_u32(sB + slot * HD_B_BYTES), HD_LBO, HD_SBO, SWZ_NONE);
+#pragma unroll
+          for (int ks = 0; ks < HD_K / 16; ++ks)
+            mma_ss(tmem + (uint32_t)buf * HD_TN, adesc0 + (uint64_t)(ks * step16), bdesc0 + (uint64_t)(ks * step16), idesc, ks > 0 ? 1u : 0u);
+          mma_commit(&empty[slot]);
+          mma_commit(&acc_full[buf]);
+        }
+        mma_commit(&a_free);      // the A' tile may be overwritten once every MMA of this row tile has read it
+      }
+    }
+  } else {
+    // ---- epilogue warps: thread = row
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    int nacc = 0;
+    for (int t = 0; t < my_tiles; ++t) {
+      const int tile = blockIdx.x + t * gridDim.x;
+      const int64_t m = (int64_t)tile * HD_TM + row;
+      const bool valid = m < a.M;
+      // -- A' tile: normalised row, split into hi / lo bf16
+      float inv = 0.0f;
+      {
+        const float4* er = reinterpret_cast<const float4*>(a.emb + (valid ? m : 0) * HD_E);
+        float ss = 0.0f;
+#pragma unroll
+        for (int j = 0; j < HD_E / 4; ++j) {
+          const float4 x = valid ? er[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+          ss += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+        }
+        inv = 1.0f / (sqrtf(ss) + 1e-8f);
+        if (t > 0 && !mbar_wait(&a_free, (uint32_t)((t - 1) & 1), HD_WAIT)) { *a.status = 6; break; }
+#pragma unroll
+        for (int j = 0; j < HD_E / 8; ++j) {     // 8 features -> one 16-byte core-matrix row, for each of the three K segments
+          const float4 x0 = valid ? er[2 * j] : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 x1 = valid ? er[2 * j + 1] : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float e[8] = {x0.x * inv, x0.y * inv, x0.z * inv, x0.w * inv, x1.x * inv, x1.y * inv, x1.z * inv, x1.w * inv};
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            hi[p] = pack_bf16(e[2 * p], e[2 * p + 1]);
+            const float h0 = __uint_as_float(hi[p] << 16), h1 = __uint_as_float(hi[p] & 0xffff0000u);
+            lo[p] = pack_bf16(e[2 * p] - h0, e[2 * p + 1] - h1);
+          }
+          const uint32_t o = off_kmajor_noswz(row, 8 * j, HD_LBO, HD_SBO);
+          *reinterpret_cast<uint4*>(sA + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(sA + o + (HD_E / 8) * HD_LBO) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(sA + o + 2 * (HD_E / 8) * HD_LBO) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        fence_async_smem();
+        mbar_arrive(&a_ready);
+      }
+      // -- stream the zone chunks: running top-2 of this row
+      float b1 = -INFINITY, b2 = -INFINITY;
+      int i1 = 0, i2 = 0;
+      bool dead = false;
+      for (int c = 0; c < a.nchunk; ++c, ++nacc) {
+        const int buf = nacc & 1;
+        if (!mbar_wait(&acc_full[buf], (uint32_t)((nacc >> 1) & 1), HD_WAIT)) { *a.status = 7; dead = true; break; }
+        tc_fence_after();
+        const int zbase = c * HD_TN;
+#pragma unroll 1
+        for (int c0 = 0; c0 < HD_TN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(tmem + lane_sel + (uint32_t)(buf * HD_TN + c0), r);
+          tmem_ld_wait();
+          float mx = -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, (zbase + c0 + j < a.Z) ? __uint_as_float(r[j]) : -INFINITY);
+          if (mx > b2) {        // rare after the first chunks: only then look at the individual columns
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int z = zbase + c0 + j;
+              const float v = __uint_as_float(r[j]);
+              if (z < a.Z) {
+                if (v > b1) { b2 = b1; i2 = i1; b1 = v; i1 = z; }
+                else if (v > b2) { b2 = v; i2 = z; }
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&acc_empty[buf]);
+      }
+      if (dead) break;
+      // -- exact fp32 re-score of the two nominees
+      if (valid) {
+        const float4* er = reinterpret_cast<const float4*>(a.emb + m * HD_E);
+        const float4* t1 = reinterpret_cast<const float4*>(a.tn + (size_t)i1 * HD_E);
+        const float4* t2 = reinterpret_cast<const float4*>(a.tn + (size_t)i2 * HD_E);
+        float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+        for (int j = 0; j < HD_E / 4; ++j) {
+          const float4 x = er[j], u = t1[j], w = t2[j];
+          const float e0 = x.x * inv, e1 = x.y * inv, e2 = x.z * inv, e3 = x.w * inv;
+          s1 = fmaf(e0, u.x, s1); s1 = fmaf(e1, u.y, s1); s1 = fmaf(e2, u.z, s1); s1 = fmaf(e3, u.w, s1);
+          s2 = fmaf(e0, w.x, s2); s2 = fmaf(e1, w.y, s2); s2 = fmaf(e2, w.z, s2); s2 = fmaf(e3, w.w, s2);
+        }
+        const bool second = (a.Z > 1) && (s2 > s1 || (s2 == s1 && i2 < i1));
+        a.labels[m] = second ? i2 : i1;
+        if (a.best != nullptr) a.best[m] = (second ? s2 : s1) * a.inv_tau;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<256>(tmem);
+}
+
+// ---- host side --------------------------------------------------------------------------------------------------
+static int head_chunks(int Z) { return (Z + HD_TN - 1) / HD_TN; }
+size_t head_workspace_bytes(int Z) {
+  const size_t nc = head_chunks(Z);
+  return align_up(nc * HD_TN * HD_E * sizeof(float), 256) + nc * HD_B_BYTES + 256;
+}
+
+int head_argmax(const float* emb, const float* table, int64_t M, int Z, int E, float tau, int64_t* labels, float* best, void* ws,
+                size_t ws_bytes, cudaStream_t st) {
+  if (E != HD_E) return AB200_ERR_UNSUPPORTED;
+  if (ws_bytes < head_workspace_bytes(Z)) return AB200_ERR_WORKSPACE;
+  const int nc = head_chunks(Z);
+  float* tn = (float*)ws;
+  uint8_t* img = (uint8_t*)ws + align_up((size_t)nc * HD_TN * HD_E * sizeof(float), 256);
+  int* status = (int*)(img + (size_t)nc * HD_B_BYTES);
+  cudaError_t e = cudaMemsetAsync(status, 0, sizeof(int), st);
+  if (e != cudaSuccess) { set_cuda_error(e); return AB200_ERR_CUDA; }
+  head_pack_table_kernel<<<nc, 128, 0, st>>>(table, Z, tn, img);
+  int rc = check_launch();
+  if (rc) return rc;
+  HeadArgs k{emb, tn, img, M, Z, nc, (int)((M + HD_TM - 1) / HD_TM), 1.0f / tau, labels, best, status};
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = k.ntiles < sms ? k.ntiles : sms;
+  e = cudaFuncSetAttribute(head_argmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HD_SMEM);
+  if (e != cudaSuccess) { set_cuda_error(e); return AB200_ERR_CUDA; }
+  head_argmax_kernel<<<grid, HD_THREADS, HD_SMEM, st>>>(k);
+  return check_launch();
+}
+
+}  // namespace ab200

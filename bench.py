@@ -125,11 +125,13 @@ def build_model(cfg, precision, device):
 
 def labels_from_path(model, y_path, class_table, t_chunk=8):
     """argmax zone label per (agent, time) without materialising [B,T,Z] at once (host-side glue)."""
+    from ananke_abm_b200.inference import head_argmax
     T = y_path.shape[0]
+    E = model.config.emb_dim
     out = []
     for s in range(0, T, t_chunk):
-        _, logits, _ = model.head(y_path[s:s + t_chunk], class_table)
-        out.append(logits.argmax(-1))
+        pred_emb = model.decoder(y_path[s:s + t_chunk, :, :E].permute(1, 0, 2))      # decoder MLP: library GEMMs
+        out.append(head_argmax(pred_emb, class_table, model.config.softmax_tau))   # fused cosine head + argmax (tcgen05)
     return torch.cat(out, dim=1)
 
 

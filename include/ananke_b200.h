@@ -218,6 +218,18 @@ int ab200_pv_combine_backward(const ab200_drift_desc* d, const float* g, int32_t
                               const float* cva_host, int64_t B, float* G_y0, float* const* G_a, int32_t accumulate,
                               ab200_stream_t stream);
 
+/* ---- fused classification head + label prediction ------------------------------------------------------------
+ * Replaces  emb_norm = pred_emb / (|pred_emb| + 1e-8); table_norm = class_table / (|class_table| + 1e-8);
+ *           logits = einsum("bte,ze->btz", emb_norm, table_norm) / softmax_tau      mode_sep/architecture/model.py:196-199
+ *           labels = logits.argmax(-1)                      mode_sep/inference/inference.py:57,63; train/train.py:168
+ * without materialising [B, T, Z] (3.9 TB at 1M agents x 97 x 10k zones).  pred_emb [M][E] fp32 row-major with
+ * M = B*T rows, class_table [Z][E] fp32, E = 64.  labels [M] int64 (first index on ties); best_logit [M] fp32 (the
+ * winning logit, may be NULL).  tcgen05 nominates the two best zones per row on 2-term bf16 splits, the winner is
+ * decided by an fp32 re-score.  Workspace: ab200_head_workspace_bytes(Z, E). */
+size_t ab200_head_workspace_bytes(int32_t Z, int32_t E);
+int ab200_head_argmax(const float* pred_emb, const float* class_table, int64_t M, int32_t Z, int32_t E, float tau,
+                      int64_t* labels, float* best_logit, void* workspace, size_t workspace_bytes, ab200_stream_t stream);
+
 /* ---- graph attention over the zone graph (the `gnn_embed` slot) ------------------------------------
  * No reference implementation exists (README.md:5,57,80 promise it; pyproject.toml:25 declares torch-geometric
  * 2.6.1, never imported): semantics are PyG `GATConv` -- x'_i = ||_h sum_{j in N(i)+i}
