@@ -129,6 +129,7 @@ class _ResidualBlock(nn.Module):
 class SecondOrderDrift(nn.Module):
     """dy/dt = [v, net([p, v, h, sin, cos]) (+ potential correction), 0] with the reference's parameter tree
     under `.net`, evaluated by the fused kernels only.  `forward(t, y)` is one `ab200_drift_eval` call."""
+    _ab200_kernel_only = True     # forward() is a kernel call without autograd: odeint routes training accordingly
 
     def __init__(self, pos_dim: int, ctx_dim: int, hidden: int = 128, n_res: int = 2, res_act: str = "relu",
                  potential: Optional[Tuple[int, int, float]] = None, period: float = 24.0):

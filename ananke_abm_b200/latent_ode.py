@@ -43,6 +43,7 @@ class GenerativeODEConfig:                  # latent_ode/config.py:18-71 (fields
 
 
 class ODEFunc(nn.Module):                   # model.py:19-117 -- parameter holder; `describe_drift` recognises this shape
+    _ab200_kernel_only = True     # forward() is a kernel call without autograd: odeint routes training accordingly
     def __init__(self, config, state_dim: int, position_dim: int, hidden_dim: int, num_residual_blocks: int):
         super().__init__()
         self.config, self.state_dim, self.position_dim = config, state_dim, position_dim

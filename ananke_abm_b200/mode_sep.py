@@ -58,6 +58,7 @@ class ODEFunc(nn.Module):                  # model.py:30-38 -- parameter holder;
 
 
 class WrappedSDE(nn.Module):               # model.py:49-73 -- f(t, y) = [v, net([p, v, h, sin, cos]), 0]
+    _ab200_kernel_only = True     # forward() is a kernel call without autograd: odeint routes training accordingly
     def __init__(self, func: ODEFunc, emb_dim: int, context_dim: int):
         super().__init__()
         self.func, self.emb_dim, self.context_dim = func, emb_dim, context_dim

@@ -422,6 +422,18 @@ def odeint(func, y0, t, *, rtol: float = 1e-7, atol: float = 1e-9, method: Optio
         th = -t_host if decreasing else t_host
         return _rk4_generic(f, y0, tt.to(y0.dtype), th)
     if method == "dopri5":
+        # Modules whose forward() is a bare kernel call (this package's mirrors) cannot be differentiated by autograd: a
+        # training call on them takes the tensor-core stage path (the only differentiable dopri5 for them) or fails loudly.
+        kernel_only = bool(getattr(func, "_ab200_kernel_only", False))
+        wants_grad = spec is not None and torch.is_grad_enabled() and (y0.requires_grad or any(p.requires_grad for p in spec.params))
+        if kernel_only and wants_grad and precision != _lib.PREC_BF16:
+            if spec.tc_stage_supported():
+                warnings.warn("dopri5 training on a kernel-evaluated drift runs on the tensor-core stage path "
+                              "(options={'precision': 'bf16'}); the strict-fp32 dopri5 path is forward-only")
+                precision = _lib.PREC_BF16
+            else:
+                raise _lib.Ab200Error("dopri5 training needs the tensor-core stage path, which is instantiated for the mode_sep "
+                                      "drift shape only; use method='rk4' (fused fp32 adjoint) or the reference's torch module")
         if (spec is not None and y0.shape[1] == spec.state_dim and precision == _lib.PREC_BF16 and spec.tc_stage_supported()
                 and y0.dtype == torch.float32):
             opts = {}
@@ -472,6 +484,13 @@ def odeint_adjoint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=No
     spec = describe_drift(func) if y0.dim() == 2 else None
     if method == "rk4" and spec is not None:
         return odeint(func, y0, t, rtol=rtol, atol=atol, method=method, options=options)
+    if method == "dopri5" and spec is not None and spec.tc_stage_supported() and (
+            getattr(func, "_ab200_kernel_only", False) or (options or {}).get("precision", _DEFAULT_PRECISION["value"]) == "bf16"):
+        # discrete adjoint of the accepted steps on the tensor-core stage kernels: O(steps) saved state, gradients equal to
+        # the continuous adjoint up to the solver tolerance (documented deviation)
+        opt = dict(options or {})
+        opt["precision"] = "bf16"
+        return odeint(func, y0, t, rtol=rtol, atol=atol, method=method, options=opt)
     from .adjoint import continuous_adjoint
     return continuous_adjoint(func, y0, t, rtol=rtol, atol=atol, method=method, options=options,
                               adjoint_rtol=adjoint_rtol, adjoint_atol=adjoint_atol, adjoint_method=adjoint_method,

@@ -210,3 +210,34 @@ def test_stage_dopri5_forward_and_adjoint_vs_oracle():
     with torch.no_grad():
         out2 = ab.odeint(model.odefunc, y0.detach(), t.to(dev), method="dopri5", rtol=1e-3, atol=1e-3, options={"precision": "bf16"})
     assert _rel(out2, out.detach()) < 1e-6
+
+
+def test_dopri5_training_dispatch_on_kernel_only_drifts():
+    """a training call with dopri5 on this package's kernel-evaluated drift modules is never silently non-differentiable:
+    mode_sep shape -> tensor-core stage path (with a warning when fp32 was asked for); latent shape -> loud error;
+    odeint_adjoint on the mode_sep drift -> the same discrete adjoint."""
+    import warnings
+    import ananke_abm_b200 as ab
+    dev = _cuda()
+    _, model = _pair()
+    model = model.to(dev)
+    home, work, traits = _agents(64, 8)
+    t = torch.linspace(0.0, 2.0, 4, device=dev)
+    y0 = model.initial_state(home.to(dev), work.to(dev), traits.to(dev)).detach().requires_grad_(True)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        out = ab.odeint(model.odefunc, y0, t, method="dopri5", rtol=1e-3, atol=1e-3)          # default precision f32
+    assert any("tensor-core stage path" in str(x.message) for x in w)
+    out[:, :, :128].pow(2).mean().backward()
+    assert y0.grad is not None and float(y0.grad.abs().max()) > 0
+    g1 = y0.grad.clone()
+    y0.grad = None
+    out2 = ab.odeint_adjoint(model.odefunc, y0, t, method="dopri5", rtol=1e-3, atol=1e-3)
+    out2[:, :, :128].pow(2).mean().backward()
+    assert _rel(y0.grad, g1) < 1e-6
+    drift = ab.SecondOrderDrift(16, 32, 128, 2, "tanh", potential=(12, 8, 1.0)).to(dev)
+    yl = torch.randn(10, 64, device=dev, requires_grad=True)
+    with pytest.raises(ab.Ab200Error):
+        ab.odeint(drift, yl, t, method="dopri5", rtol=1e-3, atol=1e-3)
+    with torch.no_grad():                      # inference on the latent shape keeps working (fp32 drift kernel)
+        assert ab.odeint(drift, yl.detach(), t, method="dopri5", rtol=1e-4, atol=1e-5).shape == (4, 10, 64)
