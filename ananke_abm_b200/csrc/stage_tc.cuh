@@ -76,14 +76,14 @@ __device__ __forceinline__ float bf16hi(uint32_t v) { return __uint_as_float(v &
 template <bool HALF>
 __device__ __forceinline__ uint32_t pack2(float lo_v, float hi_v) {
   uint32_t d;
-  if (HALF) asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi_v), "f"(lo_v));
+  if (HALF) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi_v), "f"(lo_v));   // saturate, never inf
   else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi_v), "f"(lo_v));
   return d;
 }
 template <bool HALF>
 __device__ __forceinline__ uint32_t pack2_relu(float lo_v, float hi_v) {
   uint32_t d;
-  if (HALF) asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi_v), "f"(lo_v));
+  if (HALF) asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi_v), "f"(lo_v));
   else asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi_v), "f"(lo_v));
   return d;
 }
