@@ -204,22 +204,37 @@ __global__ void __launch_bounds__(THREADS, 1) stage_bwd_tc_kernel(const __grid_c
     {
       uint32_t o[16];
       float gv[32];
+      // all loads of one source are issued before any is consumed: a later stage's gx usually comes from L2, and a
+      // load -> FMA -> load chain per float4 (as a naive loop nest gives) exposes that latency 8 x n_g times per tile
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
         if (sp.g_base != nullptr) x = ldro(blk4(sp.g_base, tile, AF4, c.hf * 8 + j, c.row));     // padding rows are zero
+        gv[4 * j] = x.x; gv[4 * j + 1] = x.y; gv[4 * j + 2] = x.z; gv[4 * j + 3] = x.w;
+      }
 #pragma unroll 1
-        for (int s = 0; s < sp.n_g; ++s) {
-          {   // coherent loads: an earlier stage of THIS launch (same thread) may have written these
-            const float4 gp = *blk4(sp.gx[s], tile, YF4, c.hf * 8 + j, c.row);
-            const float4 gq = *blk4(sp.gx[s], tile, YF4, AF4 + c.hf * 8 + j, c.row);
-            const float dp = sp.dp[s], dv = sp.dv[s];
-            x.x += dp * gp.x + dv * gq.x; x.y += dp * gp.y + dv * gq.y; x.z += dp * gp.z + dv * gq.z; x.w += dp * gp.w + dv * gq.w;
+      for (int s = 0; s < sp.n_g; ++s) {
+        const float dp = sp.dp[s], dv = sp.dv[s];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float4 gp[4], gq[4];     // coherent loads: an earlier stage of THIS launch (same thread) may have written these
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            gp[j] = *blk4(sp.gx[s], tile, YF4, c.hf * 8 + half * 4 + j, c.row);
+            gq[j] = *blk4(sp.gx[s], tile, YF4, AF4 + c.hf * 8 + half * 4 + j, c.row);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int b = (half * 4 + j) * 4;
+            gv[b] += dp * gp[j].x + dv * gq[j].x; gv[b + 1] += dp * gp[j].y + dv * gq[j].y;
+            gv[b + 2] += dp * gp[j].z + dv * gq[j].z; gv[b + 3] += dp * gp[j].w + dv * gq[j].w;
           }
         }
-        gv[4 * j] = x.x; gv[4 * j + 1] = x.y; gv[4 * j + 2] = x.z; gv[4 * j + 3] = x.w;
-        o[2 * j] = pack_bf16(x.x, x.y);
-        o[2 * j + 1] = pack_bf16(x.z, x.w);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        o[2 * j] = pack_bf16(gv[4 * j], gv[4 * j + 1]);
+        o[2 * j + 1] = pack_bf16(gv[4 * j + 2], gv[4 * j + 3]);
       }
       tmem_st16(c.tmem + c.lane_sel + C_ACT + (uint32_t)(c.hf * 16), o);
       spill_groups<4>(a.spill + S.go(blob), c.hf * 4, c.row, o);

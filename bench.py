@@ -305,6 +305,9 @@ def run_ours(args):
             kern_name = "stage_bwd_tc_kernel (%d fused Runge-Kutta stages per launch: recompute + dgrad + blob spill)" % n_fused
             kern_flop_unit = ALG_FLOP_FWD // 4 * 2    # recompute + dgrad of one stage (wgrad runs in wgrad_tc_kernel)
             kern_bytes_unit = ALG_BYTES_FWDBWD / 4.0
+            # DRAM bytes per agent-stage of this kernel from `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum =
+            # 1.566 + 3.162 GB for a fused 4-stage launch over 189,440 agents; profiles/r01_fused_step_ncu_summary.txt)
+            kern_traffic_unit = (1.565723e9 + 3.162459e9) / (189440 * 4)
             del eng, yb, A, Gb, GX
         else:
             prec = {"f32": 0, "bf16": 1}[args.precision]
@@ -323,6 +326,7 @@ def run_ours(args):
             kern_name = "rk4 fused trajectory (forward), %s" % ("rk4_tc_kernel" if prec == 1 else "rk4_f32_kernel")
             kern_flop_unit = ALG_FLOP_FWD
             kern_bytes_unit = ALG_BYTES_FWD
+            kern_traffic_unit = None
             del ybuf
     _lib.LAUNCHES = 0
     hot_step(d_home, d_work, d_traits, d_t)
@@ -356,7 +360,10 @@ def run_ours(args):
                                      "rtol": model.config.rtol, "atol": model.config.atol} if adaptive else {"grid_intervals": T - 1}),
                    "l2": "trajectory rows written per step (%.0f MB) exceed L2; weights are L2-resident by design" % (chunk * T * 640 / 1e6)},
         "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": pk["tf_burst"], "unit": "TFLOP/s",
-                     "frac": achieved_tf / pk["tf_burst"], "traffic": None, "peak_source": pk["src"],
+                     "frac": achieved_tf / pk["tf_burst"],
+                     "traffic": (kern_traffic_unit * kern_units if kern_traffic_unit else None),
+                     "traffic_note": "DRAM bytes per launch scaled from one ncu --set full capture (profiles/r01_fused_step_ncu_summary.txt)"
+                     if kern_traffic_unit else None, "peak_source": pk["src"],
                      "kernel": kern_name, "kernel_ms": kern_ms, "units_per_launch": kern_units,
                      "alg_flop_per_unit": kern_flop_unit, "alg_bytes_per_unit": kern_bytes_unit,
                      "alg_flop_per_agent_step": ALG_FLOP_FWDBWD if train else ALG_FLOP_FWD,
