@@ -63,27 +63,30 @@ __device__ __forceinline__ void spill_groups(uint8_t* blob, int fg0, int row, co
 // the other column-half's warp, and nothing orders the two stores.
 template <bool RES, bool KEEP, bool TO_ACT = true>
 __device__ __forceinline__ void bwd_fwd_epi(const SlotCtx& c, uint32_t (&z)[32], uint32_t (&mask)[2], uint8_t* blob) {
+  // 16-column passes (not 32): the backward kernel lives at the 128-register cap and every live register counts
+  mask[0] = mask[1] = 0u;
 #pragma unroll
-  for (int ch = 0; ch < 2; ++ch) {
-    uint32_t r[32];
-    tmem_ld32(c.tmem + c.lane_sel + C_ACC + (uint32_t)(c.hf * 64 + ch * 32), r);
+  for (int q = 0; q < 4; ++q) {
+    uint32_t r[16];
+    tmem_ld16(c.tmem + c.lane_sel + C_ACC + (uint32_t)(c.hf * 64 + q * 16), r);
     tmem_ld_wait();
-    uint32_t o[16];
+    uint32_t o[8];
     uint32_t m = 0;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
+    for (int j = 0; j < 8; ++j) {
+      const int zi = q * 8 + j;
       float x0 = __uint_as_float(r[2 * j]), x1 = __uint_as_float(r[2 * j + 1]);
-      if (RES) { x0 += bf16lo(z[ch * 16 + j]); x1 += bf16hi(z[ch * 16 + j]); }
+      if (RES) { x0 += bf16lo(z[zi]); x1 += bf16hi(z[zi]); }
       o[j] = pack_relu_bf16(x0, x1);
       // ReLU mask bits on the whole 32-bit word: bit 15 / 31 of t is set iff the low / high bf16 is non-zero;
-      // pair j lands at mask bits (15 - j) and (31 - j)
+      // pair jj = (q % 2) * 8 + j of mask word q / 2 lands at bits (15 - jj) and (31 - jj)
       const uint32_t t = ((o[j] & 0x7FFF7FFFu) + 0x7FFF7FFFu) & 0x80008000u;
-      m |= t >> j;
-      if (KEEP) z[ch * 16 + j] = o[j];
+      m |= t >> ((q & 1) * 8 + j);
+      if (KEEP) z[zi] = o[j];
     }
-    mask[ch] = m;
-    if (TO_ACT) tmem_st16(c.tmem + c.lane_sel + C_ACT + (uint32_t)(c.hf * 32 + ch * 16), o);
-    spill_groups<4>(blob, c.hf * 8 + ch * 4, c.row, o);
+    mask[q >> 1] |= m;
+    if (TO_ACT) tmem_st8(c.tmem + c.lane_sel + C_ACT + (uint32_t)(c.hf * 32 + q * 8), o);
+    spill_groups<2>(blob, c.hf * 8 + q * 2, c.row, o);
   }
 }
 
@@ -92,23 +95,24 @@ __device__ __forceinline__ void bwd_fwd_epi(const SlotCtx& c, uint32_t (&z)[32],
 template <bool SKIP_IN, bool SKIP_OUT>
 __device__ __forceinline__ void bwd_bwd_epi(const SlotCtx& c, uint32_t (&gs)[32], const uint32_t (&mask)[2], uint8_t* blob) {
 #pragma unroll
-  for (int ch = 0; ch < 2; ++ch) {
-    uint32_t r[32];
-    tmem_ld32(c.tmem + c.lane_sel + C_ACC + (uint32_t)(c.hf * 64 + ch * 32), r);
+  for (int q = 0; q < 4; ++q) {
+    uint32_t r[16];
+    tmem_ld16(c.tmem + c.lane_sel + C_ACC + (uint32_t)(c.hf * 64 + q * 16), r);
     tmem_ld_wait();
-    uint32_t o[16];
-    const uint32_t m = mask[ch];
+    uint32_t o[8];
+    const uint32_t m = mask[q >> 1];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
+    for (int j = 0; j < 8; ++j) {
+      const int zi = q * 8 + j, jj = (q & 1) * 8 + j;
       float x0 = __uint_as_float(r[2 * j]), x1 = __uint_as_float(r[2 * j + 1]);
-      if (SKIP_IN) { x0 += bf16lo(gs[ch * 16 + j]); x1 += bf16hi(gs[ch * 16 + j]); }
-      x0 = (m & (0x8000u >> j)) ? x0 : 0.0f;
-      x1 = (m & (0x80000000u >> j)) ? x1 : 0.0f;
+      if (SKIP_IN) { x0 += bf16lo(gs[zi]); x1 += bf16hi(gs[zi]); }
+      x0 = (m & (0x8000u >> jj)) ? x0 : 0.0f;
+      x1 = (m & (0x80000000u >> jj)) ? x1 : 0.0f;
       o[j] = pack_bf16(x0, x1);
-      if (SKIP_OUT) gs[ch * 16 + j] = o[j];
+      if (SKIP_OUT) gs[zi] = o[j];
     }
-    tmem_st16(c.tmem + c.lane_sel + C_ACT + (uint32_t)(c.hf * 32 + ch * 16), o);
-    spill_groups<4>(blob, c.hf * 8 + ch * 4, c.row, o);
+    tmem_st8(c.tmem + c.lane_sel + C_ACT + (uint32_t)(c.hf * 32 + q * 8), o);
+    spill_groups<2>(blob, c.hf * 8 + q * 2, c.row, o);
   }
 }
 
