@@ -49,6 +49,8 @@ int stage_fwd_tc_multi(const ab200_drift_desc* d, const uint8_t* image, const fl
 int stage_bwd_tc(const ab200_drift_desc* d, const uint8_t* image, const float* y0, const float* const* a_ptrs, const void* desc_v,
                  int64_t B, const float* g_base, const float* const* gx_ptrs, int n_g, const float* dp, const float* dv, float* gx_out,
                  void* spill, int blob0, int nblobs, float* g_bout, cudaStream_t st);
+int pv_combine_bwd_multi(const ab200_drift_desc* d, const float* const* g, int n_src, const float* cpv, const float* cpa, const float* cva,
+                         int n_a, int64_t B, float* G_y0, float* const* G_a, int accumulate, cudaStream_t st);
 int ga_assemble(const ab200_drift_desc* d, const float* base, const float* const* gx, int n, const float* dp, const float* dv,
                 int64_t B, float* out, cudaStream_t st);
 int stage_bwd_tc_multi(const ab200_drift_desc* d, const uint8_t* image, const float* y0, const float* const* a_ptrs,
@@ -56,7 +58,7 @@ int stage_bwd_tc_multi(const ab200_drift_desc* d, const uint8_t* image, const fl
                        const int32_t* gx_src, const float* const* gx_ext, const float* dp, const float* dv, int64_t B, void* spill,
                        int blob0, int nblobs, float* g_bout, cudaStream_t st);
 int adjoint_gather(const ab200_drift_desc* d, const float* base, const float* const* gx, int n, const float* cpv, int64_t B, float* out,
-                   cudaStream_t st);
+                   const float* ga_base, const float* dp, const float* dv, float* ga_out, cudaStream_t st);
 size_t wgrad_spill_bytes(int nblobs);
 size_t wgrad_partial_bytes();
 int wgrad_num_ctas();
@@ -264,6 +266,13 @@ int ab200_stage_backward_fused(const ab200_drift_desc* d, const void* image, con
                             spill, blob0, nblobs, wgrad_bout_ptr(partial), (cudaStream_t)stream);
 }
 
+int ab200_pv_combine_backward_multi(const ab200_drift_desc* d, const float* const* g, int32_t n_src, const float* cpv_host,
+                                    const float* cpa_host, const float* cva_host, int32_t n_a, int64_t B, float* G_y0,
+                                    float* const* G_a, int32_t accumulate, ab200_stream_t stream) {
+  if (!desc_ok(d) || !g || !cpv_host || !G_y0 || B <= 0 || (n_a > 0 && (!G_a || !cpa_host || !cva_host))) return AB200_ERR_BAD_ARG;
+  return pv_combine_bwd_multi(d, g, n_src, cpv_host, cpa_host, cva_host, n_a, B, G_y0, G_a, accumulate, (cudaStream_t)stream);
+}
+
 int ab200_stage_upstream(const ab200_drift_desc* d, const float* g_base, const float* const* gx, int32_t n_g, const float* dp_host,
                          const float* dv_host, int64_t B, float* g_a_out, ab200_stream_t stream) {
   if (!desc_ok(d) || !g_base || !g_a_out || B <= 0 || (n_g > 0 && (!gx || !dp_host || !dv_host))) return AB200_ERR_BAD_ARG;
@@ -273,7 +282,15 @@ int ab200_stage_upstream(const ab200_drift_desc* d, const float* g_base, const f
 int ab200_adjoint_gather(const ab200_drift_desc* d, const float* base, const float* const* gx, int32_t n, const float* cpv_host,
                          int64_t B, float* out, ab200_stream_t stream) {
   if (!desc_ok(d) || !base || !out || B <= 0 || (n > 0 && (!gx || !cpv_host))) return AB200_ERR_BAD_ARG;
-  return adjoint_gather(d, base, gx, n, cpv_host, B, out, (cudaStream_t)stream);
+  return adjoint_gather(d, base, gx, n, cpv_host, B, out, nullptr, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int ab200_adjoint_gather_upstream(const ab200_drift_desc* d, const float* base, const float* const* gx, int32_t n, const float* cpv_host,
+                                  int64_t B, float* out, const float* g_base, const float* dp_host, const float* dv_host,
+                                  float* g_a_out, ab200_stream_t stream) {
+  if (!desc_ok(d) || !base || !out || !g_base || !g_a_out || !dp_host || !dv_host || B <= 0 || n <= 0 || !gx || !cpv_host)
+    return AB200_ERR_BAD_ARG;
+  return adjoint_gather(d, base, gx, n, cpv_host, B, out, g_base, dp_host, dv_host, g_a_out, (cudaStream_t)stream);
 }
 
 int ab200_wgrad_accumulate(const ab200_drift_desc* d, const void* spill, int32_t nblobs, int32_t used, void* partial,

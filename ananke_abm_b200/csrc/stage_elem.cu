@@ -102,12 +102,84 @@ __global__ void __launch_bounds__(256) pv_combine_bwd_kernel(const __grid_consta
   }
 }
 
+// Several linear outputs of one step folded in ONE pass (each source: upstream gradient g_i and the output's combination):
+//   G_y0.p (+)= sum_i g_i.p ; G_y0.v (+)= sum_i cpv_i g_i.p + g_i.v ; G_y0.h (+)= sum_i g_i.h ; G_a[j] (+)= sum_i cpa_i[j] g_i.p + cva_i[j] g_i.v
+// (the end state of a dopri5 step and every dense-output row inside it; one read-modify-write of the accumulators
+// instead of one per output)
+constexpr int EL_MAX_SRC = 4;
+struct MultiBwdArgs {
+  const float* g[EL_MAX_SRC];
+  float cpv[EL_MAX_SRC], cpa[EL_MAX_SRC][EL_MAX_A], cva[EL_MAX_SRC][EL_MAX_A];
+  float* G_y0;
+  float* G_a[EL_MAX_A];
+  int n_src, n_a, accumulate, ntiles, P, H;
+};
+__global__ void __launch_bounds__(256) pv_combine_bwd_multi_kernel(const __grid_constant__ MultiBwdArgs a) {
+  const int P4 = a.P / 4, H4 = a.H / 4, Y4 = 2 * P4 + H4;
+  const int64_t n = (int64_t)a.ntiles * (P4 + H4) * EL_TM;
+  const bool acc = a.accumulate != 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int tile, grp, row;
+    decode(i, P4, H4, tile, grp, row);
+    const size_t t0 = (size_t)tile * Y4 * EL_TM + row;
+    float4* o4 = reinterpret_cast<float4*>(a.G_y0) + t0;
+    if (grp >= P4) {
+      const size_t f = (size_t)(2 * P4 + (grp - P4)) * EL_TM;
+      float4 x = acc ? o4[f] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int s = 0; s < EL_MAX_SRC; ++s)
+        if (s < a.n_src) {
+          const float4 g = (reinterpret_cast<const float4*>(a.g[s]) + t0)[f];
+          x.x += g.x; x.y += g.y; x.z += g.z; x.w += g.w;
+        }
+      o4[f] = x;
+      continue;
+    }
+    const size_t fp = (size_t)grp * EL_TM, fv = (size_t)(P4 + grp) * EL_TM;
+    float4 gp[EL_MAX_SRC], gv[EL_MAX_SRC];
+#pragma unroll
+    for (int s = 0; s < EL_MAX_SRC; ++s)
+      if (s < a.n_src) {
+        const float4* g4 = reinterpret_cast<const float4*>(a.g[s]) + t0;
+        gp[s] = g4[fp];
+        gv[s] = g4[fv];
+      }
+    float4 xp = acc ? o4[fp] : make_float4(0.f, 0.f, 0.f, 0.f), xv = acc ? o4[fv] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int s = 0; s < EL_MAX_SRC; ++s)
+      if (s < a.n_src) {
+        const float c = a.cpv[s];
+        xp.x += gp[s].x; xp.y += gp[s].y; xp.z += gp[s].z; xp.w += gp[s].w;
+        xv.x += c * gp[s].x + gv[s].x; xv.y += c * gp[s].y + gv[s].y; xv.z += c * gp[s].z + gv[s].z; xv.w += c * gp[s].w + gv[s].w;
+      }
+    o4[fp] = xp;
+    o4[fv] = xv;
+#pragma unroll 1
+    for (int j = 0; j < a.n_a; ++j) {
+      float4* q = reinterpret_cast<float4*>(a.G_a[j]) + ((size_t)tile * P4 + grp) * EL_TM + row;
+      float4 x = acc ? *q : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int s = 0; s < EL_MAX_SRC; ++s)
+        if (s < a.n_src) {
+          const float cp = a.cpa[s][j], cv = a.cva[s][j];
+          x.x += cp * gp[s].x + cv * gv[s].x; x.y += cp * gp[s].y + cv * gv[s].y;
+          x.z += cp * gp[s].z + cv * gv[s].z; x.w += cp * gp[s].w + cv * gv[s].w;
+        }
+      *q = x;
+    }
+  }
+}
+
 // out = base + sum_l [gx_l.p ; cpv_l gx_l.p + gx_l.v ; gx_l.h]   (dL/dy0 of a step from the per-stage dL/d(stage input))
 struct GatherArgs {
   const float* base;
   const float* gx[EL_MAX_A];
   float cpv[EL_MAX_A];
   float* out;
+  // optional second product of the same pass (the gx are read once): ga_out = ga_base + sum_l dp[l] gx_l.p + dv[l] gx_l.v
+  const float* ga_base;
+  float* ga_out;
+  float dp[EL_MAX_A], dv[EL_MAX_A];
   int n, ntiles, P, H;
 };
 __global__ void __launch_bounds__(256) adjoint_gather_kernel(const __grid_constant__ GatherArgs a) {
@@ -133,17 +205,22 @@ __global__ void __launch_bounds__(256) adjoint_gather_kernel(const __grid_consta
     }
     const size_t fp = (size_t)grp * EL_TM, fv = (size_t)(P4 + grp) * EL_TM;
     float4 xp = b4[fp], xv = b4[fv];
+    const size_t ia = ((size_t)tile * P4 + grp) * EL_TM + row;
+    float4 xa = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (a.ga_out != nullptr) xa = reinterpret_cast<const float4*>(a.ga_base)[ia];
 #pragma unroll
     for (int s = 0; s < EL_MAX_A; ++s)
       if (s < a.n) {
         const float4* g4 = reinterpret_cast<const float4*>(a.gx[s]) + t0;
         const float4 gp = g4[fp], gv = g4[fv];
-        const float c = a.cpv[s];
+        const float c = a.cpv[s], dp = a.dp[s], dv = a.dv[s];
         xp.x += gp.x; xp.y += gp.y; xp.z += gp.z; xp.w += gp.w;
         xv.x += c * gp.x + gv.x; xv.y += c * gp.y + gv.y; xv.z += c * gp.z + gv.z; xv.w += c * gp.w + gv.w;
+        xa.x += dp * gp.x + dv * gv.x; xa.y += dp * gp.y + dv * gv.y; xa.z += dp * gp.z + dv * gv.z; xa.w += dp * gp.w + dv * gv.w;
       }
     o4[fp] = xp;
     o4[fv] = xv;
+    if (a.ga_out != nullptr) reinterpret_cast<float4*>(a.ga_out)[ia] = xa;
   }
 }
 
@@ -251,13 +328,30 @@ int pv_combine_bwd(const ab200_drift_desc* d, const float* g, int n_a, float cpv
 }
 
 int adjoint_gather(const ab200_drift_desc* d, const float* base, const float* const* gx, int n, const float* cpv, int64_t B, float* out,
-                   cudaStream_t st) {
+                   const float* ga_base, const float* dp, const float* dv, float* ga_out, cudaStream_t st) {
   if (n < 0 || n > EL_MAX_A || d->pos_dim % 4 || d->ctx_dim % 4) return AB200_ERR_BAD_ARG;
   GatherArgs k{};
   k.base = base; k.out = out; k.n = n; k.P = d->pos_dim; k.H = d->ctx_dim;
+  k.ga_base = ga_base; k.ga_out = ga_out;
   k.ntiles = (int)((B + EL_TM - 1) / EL_TM);
-  for (int i = 0; i < n; ++i) { k.gx[i] = gx[i]; k.cpv[i] = cpv[i]; }
+  for (int i = 0; i < n; ++i) { k.gx[i] = gx[i]; k.cpv[i] = cpv[i]; k.dp[i] = ga_out ? dp[i] : 0.f; k.dv[i] = ga_out ? dv[i] : 0.f; }
   adjoint_gather_kernel<<<launch_cfg((int64_t)k.ntiles * EL_TM * ((k.P + k.H) / 4)), 256, 0, st>>>(k);
+  return check_launch();
+}
+
+int pv_combine_bwd_multi(const ab200_drift_desc* d, const float* const* g, int n_src, const float* cpv, const float* cpa, const float* cva,
+                         int n_a, int64_t B, float* G_y0, float* const* G_a, int accumulate, cudaStream_t st) {
+  if (n_src < 1 || n_src > EL_MAX_SRC || n_a < 0 || n_a > EL_MAX_A || d->pos_dim % 4 || d->ctx_dim % 4) return AB200_ERR_BAD_ARG;
+  MultiBwdArgs k{};
+  k.G_y0 = G_y0; k.n_src = n_src; k.n_a = n_a; k.accumulate = accumulate; k.P = d->pos_dim; k.H = d->ctx_dim;
+  k.ntiles = (int)((B + EL_TM - 1) / EL_TM);
+  for (int s = 0; s < n_src; ++s) {
+    k.g[s] = g[s];
+    k.cpv[s] = cpv[s];
+    for (int j = 0; j < n_a; ++j) { k.cpa[s][j] = cpa[s * EL_MAX_A + j]; k.cva[s][j] = cva[s * EL_MAX_A + j]; }
+  }
+  for (int j = 0; j < n_a; ++j) k.G_a[j] = G_a[j];
+  pv_combine_bwd_multi_kernel<<<launch_cfg((int64_t)k.ntiles * EL_TM * ((k.P + k.H) / 4)), 256, 0, st>>>(k);
   return check_launch();
 }
 

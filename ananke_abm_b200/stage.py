@@ -241,6 +241,25 @@ class TcEngine:
         _lib.check(rc, "ab200_stage_backward")
         self.used += self.ntiles
 
+    def combine_backward_multi(self, sources: Sequence, B: int, G_y0, G_a: Sequence[torch.Tensor], accumulate: bool) -> None:
+        """`sources` = [(g blocked tensor, Combo), ...]: all folded into G_y0 / G_a in passes of up to 4 sources."""
+        n_a = len(G_a)
+        for s0 in range(0, len(sources), 4):
+            grp = sources[s0:s0 + 4]
+            n = len(grp)
+            gp = (C.c_void_p * n)(*[g.data_ptr() for g, _ in grp])
+            cpv = (C.c_float * n)(*[float(c.cpv) for _, c in grp])
+            cpa = (C.c_float * (n * 8))()
+            cva = (C.c_float * (n * 8))()
+            for i, (_, c) in enumerate(grp):
+                for j in range(n_a):
+                    cpa[i * 8 + j] = float(c.cpa[j])
+                    cva[i * 8 + j] = float(c.cva[j])
+            rc = self.L.ab200_pv_combine_backward_multi(C.byref(self.desc), C.cast(gp, C.c_void_p), n, C.cast(cpv, C.c_void_p),
+                                                        C.cast(cpa, C.c_void_p), C.cast(cva, C.c_void_p), n_a, B, G_y0.data_ptr(),
+                                                        C.cast(_ptr_array(G_a), C.c_void_p), 1 if (accumulate or s0 > 0) else 0, _stream())
+            _lib.check(rc, "ab200_pv_combine_backward_multi")
+
     def stage_upstream(self, g_base, gx: Sequence[torch.Tensor], dp: Sequence[float], dv: Sequence[float], B: int, out) -> None:
         """out = g_base + sum_l dp[l] gx[l].p + dv[l] gx[l].v (the upstream gradient of a stage, as a buffer)."""
         n = len(gx)
@@ -286,6 +305,18 @@ class TcEngine:
                                                self.nblobs, self.partial.data_ptr(), _stream())
         _lib.check(rc, "ab200_stage_backward_fused")
         self.used += n * self.ntiles
+
+    def adjoint_gather_upstream(self, base, gx: Sequence[torch.Tensor], cpv: Sequence[float], B: int, out, g_base,
+                                dp: Sequence[float], dv: Sequence[float], g_a_out) -> None:
+        """adjoint_gather + stage_upstream over the same gx list in one pass."""
+        n = len(gx)
+        ca = (C.c_float * n)(*[float(x) for x in cpv])
+        dpa = (C.c_float * n)(*[float(x) for x in dp])
+        dva = (C.c_float * n)(*[float(x) for x in dv])
+        rc = self.L.ab200_adjoint_gather_upstream(C.byref(self.desc), base.data_ptr(), C.cast(_ptr_array(gx), C.c_void_p), n,
+                                                  C.cast(ca, C.c_void_p), B, out.data_ptr(), g_base.data_ptr(), C.cast(dpa, C.c_void_p),
+                                                  C.cast(dva, C.c_void_p), g_a_out.data_ptr(), _stream())
+        _lib.check(rc, "ab200_adjoint_gather_upstream")
 
     def adjoint_gather(self, base, gx: Sequence[torch.Tensor], cpv: Sequence[float], B: int, out) -> None:
         n = len(gx)
@@ -585,15 +616,18 @@ def dopri5_backward(eng: TcEngine, steps: List[_Dopri5Step], grad_y_path: torch.
     G_y0 = blocked_zeros(B, D, dev)
     G_a = [blocked_zeros(B, P, dev) for _ in range(7)]
     gx = [blocked_zeros(B, D, dev) for _ in range(7)]
-    g_blk = blocked_zeros(B, D, dev)
+    g_blk = [blocked_zeros(B, D, dev)]
     for si in range(len(steps) - 1, -1, -1):
         st = steps[si]
         dt = st.dt
         # step-level gradients: the end state y1 = y0 + dt sum c_sol k, and every dense-output row inside the step
-        eng.combine_backward(lam, DOPRI5.combo(DOPRI5.b, dt), B, G_y0, G_a, accumulate=False)
-        for (k, x) in st.outputs:
-            rows_block(grad_y_path[k], g_blk)
-            eng.combine_backward(g_blk, DOPRI5.combo(dopri5_interp_weights(x), dt), B, G_y0, G_a, accumulate=True)
+        sources = [(lam, DOPRI5.combo(DOPRI5.b, dt))]
+        for n_o, (k, x) in enumerate(st.outputs):
+            if n_o >= len(g_blk):
+                g_blk.append(blocked_zeros(B, D, dev))
+            rows_block(grad_y_path[k], g_blk[n_o])
+            sources.append((g_blk[n_o], DOPRI5.combo(dopri5_interp_weights(x), dt)))
+        eng.combine_backward_multi(sources, B, G_y0, G_a, accumulate=False)
         if lam_a is not None:
             G_a[6].add_(lam_a)
         last = 6 if (st.outputs or lam_a is not None) else 5      # stage 7 only matters if something used k_7
@@ -602,12 +636,12 @@ def dopri5_backward(eng: TcEngine, steps: List[_Dopri5Step], grad_y_path: torch.
         times = [st.t0 + DOPRI5.c[i] * dt for i in range(7)]
         stages_backward(eng, DOPRI5, B, st.yb, st.A, times, dt, G_a, gx, first, last)
         used = list(range(first, last + 1))
-        eng.adjoint_gather(G_y0, [gx[i] for i in used], [combos[i].cpv for i in used], B, lam_prev)
-        if first == 1:
-            later = [l for l in range(1, last + 1) if combos[l].cpa[0] != 0.0 or combos[l].cva[0] != 0.0]
+        if first == 1:      # one pass: dL/dy0 of the step and the gradient handed to the previous step's FSAL evaluation
             lam_a = lam_a_buf[si % 2]
-            eng.stage_upstream(G_a[0], [gx[l] for l in later], [combos[l].cpa[0] for l in later], [combos[l].cva[0] for l in later],
-                               B, lam_a)
+            eng.adjoint_gather_upstream(G_y0, [gx[i] for i in used], [combos[i].cpv for i in used], B, lam_prev, G_a[0],
+                                        [combos[i].cpa[0] for i in used], [combos[i].cva[0] for i in used], lam_a)
+        else:
+            eng.adjoint_gather(G_y0, [gx[i] for i in used], [combos[i].cpv for i in used], B, lam_prev)
         eng.flush()
         lam, lam_prev = lam_prev, lam
     rows_block(grad_y_path[0], lam, accumulate=True)

@@ -196,6 +196,17 @@ int ab200_stage_backward_fused(const ab200_drift_desc* d, const void* image, con
                                float* const* gx_out, const int32_t* n_g, const int32_t* gx_src, const float* const* gx_ext,
                                const float* dp_host, const float* dv_host, int64_t B, void* spill, size_t spill_bytes,
                                int32_t blob0, int32_t nblobs, void* partial, ab200_stream_t stream);
+/* ab200_adjoint_gather and ab200_stage_upstream over the same gx list in ONE pass (each gx is read once):
+ *     out = base + sum_l [...]  and  g_a_out = g_base + sum_l dp[l] gx[l].p + dv[l] gx[l].v   (dp/dv may be 0 for some l). */
+int ab200_adjoint_gather_upstream(const ab200_drift_desc* d, const float* base, const float* const* gx, int32_t n,
+                                  const float* cpv_host, int64_t B, float* out, const float* g_base, const float* dp_host,
+                                  const float* dv_host, float* g_a_out, ab200_stream_t stream);
+/* ab200_pv_combine_backward for up to 4 linear outputs of the same step in ONE pass (source i: gradient g[i], blocked
+ * [Bp][D], and its combination cpv[i], cpa[i * 8 + j], cva[i * 8 + j], j < n_a): the accumulators are written once
+ * instead of once per output (a dopri5 step's end state plus the dense-output rows that fall inside it). */
+int ab200_pv_combine_backward_multi(const ab200_drift_desc* d, const float* const* g, int32_t n_src, const float* cpv_host,
+                                    const float* cpa_host, const float* cva_host, int32_t n_a, int64_t B, float* G_y0,
+                                    float* const* G_a, int32_t accumulate, ab200_stream_t stream);
 /* The upstream gradient of a stage written out as a buffer instead of being consumed by ab200_stage_backward:
  *     g_a_out (blocked [Bp][P]) = g_base + sum_l dp[l] gx[l].p + dv[l] gx[l].v
  * dopri5's first stage of a step IS the last (FSAL) evaluation of the previous step (tdq rk_common.py _adaptive_step:
