@@ -67,6 +67,8 @@ int wgrad_tc(const void* spill, int nblobs, int used, void* partial, cudaStream_
 int wgrad_finalize(const void* partial, float* grad_w_flat, cudaStream_t st);
 int pv_combine(const ab200_drift_desc* d, const float* y0, const float* const* a_ptrs, int n_a, float cpv, const float* cpa,
                const float* cva, int64_t B, float* out, cudaStream_t st);
+int pv_combine_rowmajor(const ab200_drift_desc* d, const float* y0, const float* const* a_ptrs, int n_a, float cpv, const float* cpa,
+                        const float* cva, int64_t B, float* out_rowmajor, cudaStream_t st);
 int pv_combine_bwd(const ab200_drift_desc* d, const float* g, int n_a, float cpv, const float* cpa, const float* cva, int64_t B,
                    float* G_y0, float* const* G_a, int accumulate, cudaStream_t st);
 
@@ -317,6 +319,12 @@ int ab200_pv_combine(const ab200_drift_desc* d, const float* y0, const float* co
                      const float* cpa_host, const float* cva_host, int64_t B, float* out, ab200_stream_t stream) {
   if (!desc_ok(d) || !y0 || !out || B <= 0 || (n_a > 0 && (!a || !cpa_host || !cva_host))) return AB200_ERR_BAD_ARG;
   return pv_combine(d, y0, a, n_a, cpv, cpa_host, cva_host, B, out, (cudaStream_t)stream);
+}
+
+int ab200_pv_combine_rowmajor(const ab200_drift_desc* d, const float* y0, const float* const* a, int32_t n_a, float cpv,
+                              const float* cpa_host, const float* cva_host, int64_t B, float* out_rowmajor, ab200_stream_t stream) {
+  if (!desc_ok(d) || !y0 || !out_rowmajor || B <= 0 || (n_a > 0 && (!a || !cpa_host || !cva_host))) return AB200_ERR_BAD_ARG;
+  return pv_combine_rowmajor(d, y0, a, n_a, cpv, cpa_host, cva_host, B, out_rowmajor, (cudaStream_t)stream);
 }
 
 int ab200_pv_combine_backward(const ab200_drift_desc* d, const float* g, int32_t n_a, float cpv, const float* cpa_host,

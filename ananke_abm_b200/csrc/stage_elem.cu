@@ -11,6 +11,7 @@ namespace ab200 {
 
 constexpr int EL_MAX_A = 8;
 constexpr int EL_TM = 128;
+constexpr int TR_ROWS = 32;       // rows per CTA of the transposing kernels
 struct ElemArgs {
   const float* y0;
   const float* a[EL_MAX_A];
@@ -257,7 +258,6 @@ __global__ void __launch_bounds__(256) ga_assemble_kernel(const __grid_constant_
 // One CTA moves 32 rows x F floats through shared memory so that both the row-major side (rows contiguous) and the
 // blocked side (32 consecutive agents of one float4 group contiguous) are accessed in full 128-byte lines.
 //   mode 0: blocked  = row-major (padding rows zeroed)   mode 1: blocked += row-major   mode 2: row-major = blocked
-constexpr int TR_ROWS = 32;
 __global__ void __launch_bounds__(256) rows_transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int64_t B,
                                                              int64_t Bp, int F4, int mode) {
   extern __shared__ float4 tile_s[];     // [TR_ROWS][F4 + 1]
@@ -299,6 +299,46 @@ __global__ void __launch_bounds__(256) rows_transpose_kernel(const float* __rest
   }
 }
 
+// pv_combine with a ROW-MAJOR result (the public trajectory row): blocked inputs are read in full 512 B segments, the
+// 32 x F result tile is transposed through shared memory and written as contiguous rows -- saves the blocked round trip
+__global__ void __launch_bounds__(256) pv_combine_rowmajor_kernel(const __grid_constant__ ElemArgs a, int64_t B) {
+  extern __shared__ float4 tile_s[];     // [TR_ROWS][F4 + 1]
+  const int P4 = a.P / 4, H4 = a.H / 4, F4 = 2 * P4 + H4, ld = F4 + 1;
+  const int64_t row0 = (int64_t)blockIdx.x * TR_ROWS;
+  const int n_work = TR_ROWS * (P4 + H4);
+  for (int i = threadIdx.x; i < n_work; i += blockDim.x) {
+    const int grp = i / TR_ROWS, r = i % TR_ROWS;
+    const int64_t g = row0 + r;
+    if (g >= B) continue;
+    const int tile = (int)(g / EL_TM), row = (int)(g % EL_TM);
+    const float4* y4 = reinterpret_cast<const float4*>(a.y0) + (size_t)tile * F4 * EL_TM + row;
+    if (grp >= P4) {
+      const int f = 2 * P4 + (grp - P4);
+      tile_s[r * ld + f] = y4[(size_t)f * EL_TM];
+      continue;
+    }
+    const float4 p0 = y4[(size_t)grp * EL_TM], v0 = y4[(size_t)(P4 + grp) * EL_TM];
+    float4 p = make_float4(p0.x + a.cpv * v0.x, p0.y + a.cpv * v0.y, p0.z + a.cpv * v0.z, p0.w + a.cpv * v0.w), v = v0;
+#pragma unroll
+    for (int s = 0; s < EL_MAX_A; ++s) {
+      if (s < a.n_a) {
+        const float4 x = reinterpret_cast<const float4*>(a.a[s])[((size_t)tile * P4 + grp) * EL_TM + row];
+        const float cp = a.cpa[s], cv = a.cva[s];
+        p.x += cp * x.x; p.y += cp * x.y; p.z += cp * x.z; p.w += cp * x.w;
+        v.x += cv * x.x; v.y += cv * x.y; v.z += cv * x.z; v.w += cv * x.w;
+      }
+    }
+    tile_s[r * ld + grp] = p;
+    tile_s[r * ld + P4 + grp] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < TR_ROWS * F4; i += blockDim.x) {
+    const int r = i / F4, c = i % F4;
+    const int64_t g = row0 + r;
+    if (g < B) reinterpret_cast<float4*>(a.out)[g * F4 + c] = tile_s[r * ld + c];
+  }
+}
+
 static int launch_cfg(int64_t n) {
   int64_t blocks = (n + 255) / 256;
   const int64_t cap = 148 * 16;
@@ -313,6 +353,19 @@ int pv_combine(const ab200_drift_desc* d, const float* y0, const float* const* a
   k.ntiles = (int)((B + EL_TM - 1) / EL_TM);
   for (int i = 0; i < n_a; ++i) { k.a[i] = a_ptrs[i]; k.cpa[i] = cpa[i]; k.cva[i] = cva[i]; }
   pv_combine_kernel<<<launch_cfg((int64_t)k.ntiles * EL_TM * ((k.P + k.H) / 4)), 256, 0, st>>>(k);
+  return check_launch();
+}
+
+int pv_combine_rowmajor(const ab200_drift_desc* d, const float* y0, const float* const* a_ptrs, int n_a, float cpv, const float* cpa,
+                        const float* cva, int64_t B, float* out_rowmajor, cudaStream_t st) {
+  if (n_a < 0 || n_a > EL_MAX_A || d->pos_dim % 4 || d->ctx_dim % 4) return AB200_ERR_BAD_ARG;
+  ElemArgs k{};
+  k.y0 = y0; k.out = out_rowmajor; k.cpv = cpv; k.n_a = n_a; k.P = d->pos_dim; k.H = d->ctx_dim;
+  k.ntiles = (int)((B + EL_TM - 1) / EL_TM);
+  for (int i = 0; i < n_a; ++i) { k.a[i] = a_ptrs[i]; k.cpa[i] = cpa[i]; k.cva[i] = cva[i]; }
+  const int F4 = (2 * k.P + k.H) / 4;
+  const size_t smem = (size_t)TR_ROWS * (F4 + 1) * sizeof(float4);
+  pv_combine_rowmajor_kernel<<<(int)((B + TR_ROWS - 1) / TR_ROWS), 256, smem, st>>>(k, B);
   return check_launch();
 }
 

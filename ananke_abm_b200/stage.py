@@ -200,6 +200,16 @@ class TcEngine:
                                      C.cast(cpa, C.c_void_p), C.cast(cva, C.c_void_p), B, out.data_ptr(), _stream())
         _lib.check(rc, "ab200_pv_combine")
 
+    def combine_rowmajor(self, y0, a: Sequence[torch.Tensor], c: Combo, B: int, out_rowmajor) -> None:
+        """`combine` written straight into a row-major [B, D] tensor (a trajectory row)."""
+        n = len(a)
+        assert out_rowmajor.is_contiguous()
+        cpa = (C.c_float * max(n, 1))(*[float(x) for x in c.cpa[:n]])
+        cva = (C.c_float * max(n, 1))(*[float(x) for x in c.cva[:n]])
+        rc = self.L.ab200_pv_combine_rowmajor(C.byref(self.desc), y0.data_ptr(), C.cast(_ptr_array(a), C.c_void_p), n, float(c.cpv),
+                                              C.cast(cpa, C.c_void_p), C.cast(cva, C.c_void_p), B, out_rowmajor.data_ptr(), _stream())
+        _lib.check(rc, "ab200_pv_combine_rowmajor")
+
     # ---- backward -----------------------------------------------------------------------------------
     def backward_begin(self, B: int, stages_per_flush: int) -> None:
         self.ntiles = (B + TM - 1) // TM
@@ -576,8 +586,7 @@ def dopri5_forward(eng: TcEngine, y0: torch.Tensor, t_host: Sequence[float], rto
             outs = []
             while k < T and ts[k] <= tb:
                 x = (ts[k] - ta) / (tb - ta)
-                eng.combine(y_cur, A, DOPRI5.combo(dopri5_interp_weights(x), dt), B, out_b)
-                rows_unblock(out_b, B, D, out=y_path[k])
+                eng.combine_rowmajor(y_cur, A, DOPRI5.combo(dopri5_interp_weights(x), dt), B, y_path[k])
                 outs.append((k, x))
                 k += 1
             if save_steps:

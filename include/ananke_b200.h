@@ -225,6 +225,9 @@ int ab200_stage_status_offset(const ab200_drift_desc* d, int64_t* image_status_b
  * (accumulate = 0 overwrites).  n_a <= 8; `a` / `G_a` are host arrays of device pointers. */
 int ab200_pv_combine(const ab200_drift_desc* d, const float* y0, const float* const* a, int32_t n_a, float cpv,
                      const float* cpa_host, const float* cva_host, int64_t B, float* out, ab200_stream_t stream);
+/* ab200_pv_combine whose result is the reference's ROW-MAJOR [B][D] trajectory row (blocked inputs, transposed on chip) */
+int ab200_pv_combine_rowmajor(const ab200_drift_desc* d, const float* y0, const float* const* a, int32_t n_a, float cpv,
+                              const float* cpa_host, const float* cva_host, int64_t B, float* out_rowmajor, ab200_stream_t stream);
 int ab200_pv_combine_backward(const ab200_drift_desc* d, const float* g, int32_t n_a, float cpv, const float* cpa_host,
                               const float* cva_host, int64_t B, float* G_y0, float* const* G_a, int32_t accumulate,
                               ab200_stream_t stream);
