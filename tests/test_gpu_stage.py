@@ -241,3 +241,60 @@ def test_dopri5_training_dispatch_on_kernel_only_drifts():
         ab.odeint(drift, yl, t, method="dopri5", rtol=1e-3, atol=1e-3)
     with torch.no_grad():                      # inference on the latent shape keeps working (fp32 drift kernel)
         assert ab.odeint(drift, yl.detach(), t, method="dopri5", rtol=1e-4, atol=1e-5).shape == (4, 10, 64)
+
+
+def test_rows_are_independent_of_batch_composition_and_chunking():
+    """batch indexing: agent b's trajectory and gradient do not depend on which other agents share its launch
+    (bit-identical rows when the same agents are integrated alone, in a larger batch, or at another tile position)"""
+    import ananke_abm_b200 as ab
+    dev = _cuda()
+    _, model = _pair(Z=50)
+    model = model.to(dev)
+    B = 1000
+    home, work, traits = _agents(B, 50)
+    t = torch.linspace(0.0, 2.0, 6, device=dev)
+    with torch.no_grad():
+        y0 = model.initial_state(home.to(dev), work.to(dev), traits.to(dev)).contiguous()
+    outs = {}
+    for name, sel in (("all", slice(0, B)), ("head", slice(0, 130)), ("mid", slice(300, 430))):
+        ys = y0[sel].clone().requires_grad_(True)
+        for p in model.parameters():
+            p.grad = None
+        yp = ab.odeint(model.odefunc, ys, t, method="rk4", options={"precision": "bf16"})
+        yp[:, :, :128].pow(2).sum().backward()
+        outs[name] = (yp.detach(), ys.grad.clone())
+    assert torch.equal(outs["all"][0][:, 0:130], outs["head"][0]) and torch.equal(outs["all"][1][0:130], outs["head"][1])
+    assert torch.equal(outs["all"][0][:, 300:430], outs["mid"][0]) and torch.equal(outs["all"][1][300:430], outs["mid"][1])
+
+
+def test_full_chunk_properties_dopri5():
+    """size-independent properties at the bench's chunk size (189,440 agents = 5 whole waves of tiles), dopri5:
+    row 0 is y0, the context h is carried unchanged, everything finite, a zero upstream gradient gives zero gradients,
+    and the adjoint is linear in the upstream gradient."""
+    import importlib
+    import ananke_abm_b200 as ab
+    from ananke_abm_b200 import stage
+    oi = importlib.import_module("ananke_abm_b200.odeint")
+    dev = _cuda()
+    _, model = _pair(Z=200)
+    model = model.to(dev)
+    B = 189_440
+    home, work, traits = _agents(B, 200)
+    with torch.no_grad():
+        y0 = model.initial_state(home.to(dev), work.to(dev), traits.to(dev)).contiguous()
+    spec = ab.describe_drift(model.odefunc)
+    eng = stage.TcEngine(spec, spec.flat_params().detach())
+    th = [0.0, 1.0, 2.5, 4.0]
+    stats = stage.Dopri5Stats()
+    yp, steps, _ = stage.dopri5_forward(eng, y0, th, 1e-4, 1e-4, save_steps=True, stats=stats)
+    assert torch.equal(yp[0], y0) and torch.equal(yp[:, :, 128:], y0[None, :, 128:].expand(4, -1, -1))
+    assert bool(torch.isfinite(yp).all()) and 1 <= stats.n_accepted < 100 and len(steps) == stats.n_accepted
+    g = torch.randn(yp.shape, device=dev, generator=torch.Generator(device=dev).manual_seed(3)) / yp.numel()
+    gy1, gw1 = stage.dopri5_backward(eng, steps, g)
+    gy2, gw2 = stage.dopri5_backward(eng, steps, 4.0 * g)
+    gy0, gw0 = stage.dopri5_backward(eng, steps, torch.zeros_like(g))
+    torch.cuda.synchronize()
+    eng.check_status()
+    assert float(gy0.abs().max()) == 0.0 and float(gw0.abs().max()) == 0.0
+    assert bool(torch.isfinite(gy1).all()) and bool(torch.isfinite(gw1).all())
+    assert _rel(gy2, 4.0 * gy1) < 1e-5 and _rms(gw2, 4.0 * gw1) < 1e-3
