@@ -21,6 +21,16 @@
 namespace ab200 {
 using namespace stc;
 
+#ifdef AB200_STAGE_TRACE
+extern "C" int ab200_debug_stage_trace_bwd(long long* host_out, int* counts) {
+  cudaMemcpyFromSymbol(host_out, stc::g_stage_trace, sizeof(long long) * 8192);
+  cudaMemcpyFromSymbol(counts, stc::g_stage_trace_n, sizeof(int) * 2);
+  int z[2] = {0, 0};
+  cudaMemcpyToSymbol(stc::g_stage_trace_n, z, sizeof(z));
+  return 0;
+}
+#endif
+
 struct BwdStageParams {       // one stage of a fused (latest-first) sequence
   int n_a;                    // the stage input combined a[0 .. n_a)
   Combo in;
@@ -52,6 +62,8 @@ struct StageBwdArgs {
 // store packed pairs as feature groups of a blob: NG groups starting at fg0, row = agent
 template <int NG>
 __device__ __forceinline__ void spill_groups(uint8_t* blob, int fg0, int row, const uint32_t* o) {
+#pragma unroll
+  if (blob == nullptr) return;     // AB200_STAGE_FLAGS bit 16: timing experiment without the blob spill
 #pragma unroll
   for (int q = 0; q < NG; ++q)
     __stcs(reinterpret_cast<uint4*>(blob + (size_t)(fg0 + q) * wg::FG_BYTES + (size_t)row * 16),
@@ -125,17 +137,20 @@ __global__ void __launch_bounds__(THREADS, 1) stage_bwd_tc_kernel(const __grid_c
   const uint32_t tmem_base = tmem_base_s;
   const wg::SpillLayout S{a.nblobs};
   const int lane = threadIdx.x & 31;
+  const bool no_spill = (c.flags & 16) != 0, no_gx = (c.flags & 32) != 0;     // timing experiments only (results invalid)
+  auto blob_at = [&](size_t off) -> uint8_t* { return no_spill ? nullptr : a.spill + off; };
 
 #pragma unroll 1
   for (int tile = blockIdx.x * NSLOT + c.slot; tile < a.ntiles; tile += gridDim.x * NSLOT) {
-    const bool valid = (int64_t)tile * TM + c.row < a.B;      // padding rows: zeros in, nothing stored
+    const bool valid = (int64_t)tile * TM + c.row < a.B && !no_gx;      // padding rows: zeros in, nothing stored
 #pragma unroll 1
    for (int si = 0; si < a.n_stage; ++si) {                   // all stages of the step for this tile: later stages' gx come from L2
     const BwdStageParams& sp = a.st[si];
     const int blob = sp.blob0 + tile;
+    STAGE_TRACE(c, 9);
 
     // ---- stage input -> ACT / HB / TB and the X blob (features: p 0..63, v 64..127, h 128..159, sin, cos, 1)
-    uint8_t* xb = a.spill + S.x1(blob);
+    uint8_t* xb = blob_at(S.x1(blob));
 #pragma unroll
     for (int ch = 0; ch < 2; ++ch) {
       const int f0 = c.hf * 8 + ch * 4;
@@ -190,20 +205,22 @@ __global__ void __launch_bounds__(THREADS, 1) stage_bwd_tc_kernel(const __grid_c
       spill_groups<2>(xb, (2 * P + H) / 8, c.row, o);
     }
 
+    STAGE_TRACE(c, 10);
     // ---- forward recompute (hidden layers only), masks + blobs
     uint32_t z[32];
     uint32_t m_z0[2], m_u0[2], m_z1[2], m_u1[2], m_z2[2];
     run_layer<false, (2 * P + H) / 16, true, HID, HID, true>(c, C_ACT, OFF_W1);
-    bwd_fwd_epi<false, true>(c, z, m_z0, a.spill + S.act(0, blob));
+    bwd_fwd_epi<false, true>(c, z, m_z0, blob_at(S.act(0, blob)));
     run_layer<false, HID / 16, true, HID, HID, true>(c, C_ACT, off_hh(0));
-    bwd_fwd_epi<false, false>(c, z, m_u0, a.spill + S.act(1, blob));
+    bwd_fwd_epi<false, false>(c, z, m_u0, blob_at(S.act(1, blob)));
     run_layer<false, HID / 16, true, HID, HID, true>(c, C_ACT, off_hh(1));
-    bwd_fwd_epi<true, true>(c, z, m_z1, a.spill + S.act(2, blob));
+    bwd_fwd_epi<true, true>(c, z, m_z1, blob_at(S.act(2, blob)));
     run_layer<false, HID / 16, true, HID, HID, true>(c, C_ACT, off_hh(2));
-    bwd_fwd_epi<false, false>(c, z, m_u1, a.spill + S.act(3, blob));
+    bwd_fwd_epi<false, false>(c, z, m_u1, blob_at(S.act(3, blob)));
     run_layer<false, HID / 16, true, HID, HID, true>(c, C_ACT, off_hh(3));
-    bwd_fwd_epi<true, false, false>(c, z, m_z2, a.spill + S.act(4, blob));
+    bwd_fwd_epi<true, false, false>(c, z, m_z2, blob_at(S.act(4, blob)));
 
+    STAGE_TRACE(c, 12);
     // ---- upstream gradient of the output layer -> ACT (K = 64) + gO blob + bias column sums
     {
       uint32_t o[16];
@@ -241,7 +258,7 @@ __global__ void __launch_bounds__(THREADS, 1) stage_bwd_tc_kernel(const __grid_c
         o[2 * j + 1] = pack_bf16(gv[4 * j + 2], gv[4 * j + 3]);
       }
       tmem_st16(c.tmem + c.lane_sel + C_ACT + (uint32_t)(c.hf * 16), o);
-      spill_groups<4>(a.spill + S.go(blob), c.hf * 4, c.row, o);
+      spill_groups<4>(blob_at(S.go(blob)), c.hf * 4, c.row, o);
       // column sums over the warp's 32 agents: transpose-reduce, lane j ends up with column j
 #pragma unroll
       for (int w = 16; w >= 1; w >>= 1) {
@@ -256,25 +273,27 @@ __global__ void __launch_bounds__(THREADS, 1) stage_bwd_tc_kernel(const __grid_c
       atomicAdd(a.g_bout + c.hf * 32 + lane, gv[0]);
     }
 
+    STAGE_TRACE(c, 13);
     // ---- backward through the net (dgrad GEMMs on the MN-major view of the weight image)
     run_layer<true, P / 16, false, P, HID, true>(c, C_ACT, OFF_WO);                       // g_z2 = gO W_O
-    bwd_bwd_epi<false, true>(c, z, m_z2, a.spill + S.grad(4, blob));                // gB1 = g_z2 * [z2 > 0]  (skip -> z)
+    bwd_bwd_epi<false, true>(c, z, m_z2, blob_at(S.grad(4, blob)));                // gB1 = g_z2 * [z2 > 0]  (skip -> z)
     run_layer<true, HID / 16, false, HID, HID, true>(c, C_ACT, off_hh(3));                // g_u1 = gB1 W_B1
     {
       uint32_t dummy[32];
-      bwd_bwd_epi<false, false>(c, dummy, m_u1, a.spill + S.grad(3, blob));         // gA1
+      bwd_bwd_epi<false, false>(c, dummy, m_u1, blob_at(S.grad(3, blob)));         // gA1
     }
     run_layer<true, HID / 16, false, HID, HID, true>(c, C_ACT, off_hh(2));                // gA1 W_A1 (+ skip)
-    bwd_bwd_epi<true, true>(c, z, m_z1, a.spill + S.grad(2, blob));                 // gB0
+    bwd_bwd_epi<true, true>(c, z, m_z1, blob_at(S.grad(2, blob)));                 // gB0
     run_layer<true, HID / 16, false, HID, HID, true>(c, C_ACT, off_hh(1));
     {
       uint32_t dummy[32];
-      bwd_bwd_epi<false, false>(c, dummy, m_u0, a.spill + S.grad(1, blob));         // gA0
+      bwd_bwd_epi<false, false>(c, dummy, m_u0, blob_at(S.grad(1, blob)));         // gA0
     }
     run_layer<true, HID / 16, false, HID, HID, true>(c, C_ACT, off_hh(0));
-    bwd_bwd_epi<true, false>(c, z, m_z0, a.spill + S.grad(0, blob));                // g1
+    bwd_bwd_epi<true, false>(c, z, m_z0, blob_at(S.grad(0, blob)));                // g1
     run_layer<true, HID / 16, false, HID, 2 * P + H, true>(c, C_ACT, OFF_W1);             // g_x[128 x 160] = g1 W_1[:, :160]
 
+    STAGE_TRACE(c, 11);
     // ---- dL/d(stage input) -> gx_out (tcgen05.ld is warp-collective: issued by every lane; only lanes that own a real
     //      agent store)
 #pragma unroll

@@ -148,9 +148,7 @@ __device__ __forceinline__ void run_layer(SlotCtx& c, uint32_t a_col, uint32_t w
   slot_sync(c.slot);
   STAGE_TRACE(c, 3);
   if (c.stid == 0) {
-    STAGE_TRACE(c, 31);
     tc_fence_after();
-    STAGE_TRACE(c, 32);
     if (c.flags & 1) {      // optional issue mutex (measured: no gain)
       const long long t0 = clock64();
       while (atomicCAS(c.lock, 0, 1) != 0) {
@@ -168,17 +166,13 @@ __device__ __forceinline__ void run_layer(SlotCtx& c, uint32_t a_col, uint32_t w
       issue_mmas(c.tmem + C_ACC, c.tmem + a_col, EXT ? c.tmem + C_TB : 0xffffffffu, d0, step16, idesc, NKS, c.bar);
     } else {
       const uint32_t acc = c.tmem + C_ACC, a0 = c.tmem + a_col;
-      STAGE_TRACE(c, 33);
-#pragma unroll
+  #pragma unroll
       for (int ks = 0; ks < NKS; ++ks) {
         mma_ts(acc, a0 + (uint32_t)ks * 8u, d0 + (uint64_t)(ks * step16), idesc, ks > 0 ? 1u : 0u);
-        if (ks == 0) STAGE_TRACE(c, 34);
       }
       if (EXT) mma_ts(acc, c.tmem + C_TB, d0 + (uint64_t)(NKS * step16), idesc, 1u);
-      STAGE_TRACE(c, 35);
-      mma_commit(c.bar);
-      STAGE_TRACE(c, 36);
-    }
+        mma_commit(c.bar);
+      }
     if (c.flags & 1) atomicExch(c.lock, 0);
   }
   STAGE_TRACE(c, 4);

@@ -17,7 +17,7 @@ import torch
 from torch import nn
 
 from .drift import _ResidualBlock
-from .odeint import odeint
+from .odeint import odeint, odeint_adjoint
 
 
 @dataclass
@@ -97,8 +97,10 @@ class ModeSepModel(nn.Module):
     def integrate(self, y0: torch.Tensor, times_union: torch.Tensor) -> torch.Tensor:
         if self.config.enable_sde and self.config.sde_noise_strength > 0.0:
             raise NotImplementedError("the SDE branch is out of scope (SURVEY.md §8f-4)")
-        return odeint(self.odefunc, y0, times_union, method=self.config.ode_method, rtol=self.config.rtol,
-                      atol=self.config.atol, options=_solver_options(self.config))
+        # config.adjoint (not a reference field): go through the odeint_adjoint seam (latent_ode/architecture/ode_components.py:50)
+        solve = odeint_adjoint if getattr(self.config, "adjoint", False) else odeint
+        return solve(self.odefunc, y0, times_union, method=self.config.ode_method, rtol=self.config.rtol,
+                     atol=self.config.atol, options=_solver_options(self.config))
 
     def head(self, y_path: torch.Tensor):
         E, H = self.config.emb_dim, self.config.context_dim

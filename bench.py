@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- agent-steps/s of the GAT-ODE hot path on N B200s (one process per GPU).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3] [--precision f32|bf16] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c5] [--precision f32|bf16] [--impl reference]
 
 One "step" = one pass of the hot path over one batch of synthetic agents: the whole trajectory
 (T-1 solver intervals) for every agent of the batch, i.e. B*(T-1) agent-steps.
@@ -37,6 +37,10 @@ WORKLOADS = {
     # fwd+bwd; dense output at the 97 grid points of the day.  `--solver rk4` runs the fixed-grid variant (96 steps).
     "c3": dict(B=1_000_000, Z=10_000, T=97, heads=4, mode="train", method="dopri5",
                name="configs[2]: 1M agents x 10k zones, 4-head GAT, dopri5 rtol=atol=1e-5, fwd+bwd (agent-chunked)"),
+    # BASELINE.json configs[4]: 8M agents x 10k zones, adjoint backward (the odeint_adjoint seam), bf16 tensor-core projection.
+    # Agents are independent, so the adjoint runs chunk by chunk: the saved steps of one chunk (not of 8M agents) live in HBM.
+    "c5": dict(B=8_000_000, Z=10_000, T=97, heads=4, mode="train", method="dopri5", adjoint=True,
+               name="configs[4]: 8M agents x 10k zones, 4-head GAT, dopri5 rtol=atol=1e-5, odeint_adjoint fwd+bwd (agent-chunked)"),
 }
 ALG_FLOP_FWD = 755_712          # per agent-step, SURVEY.md §8(d) / BASELINE.md §3
 ALG_FLOP_FWDBWD = 3_022_848     # 4x forward (discrete adjoint with stage recompute)
@@ -116,6 +120,7 @@ def build_model(cfg, precision, device):
     mc = ab.ModeSepConfig()
     mc.precision = precision
     mc.ode_method = cfg["method"]            # rtol = atol = 1e-5 (mode_sep/config.py:27-28) apply to dopri5 only
+    mc.adjoint = bool(cfg.get("adjoint", False))
     mc.error_norm = "global"                 # N > 1: one RMS error norm over all ranks' agents, as a single process would use
     model = ab.GATODEModel(7, mc, heads=cfg["heads"]).to(device)
     ei, feats = synthetic_zone_graph(cfg["Z"], k=6, seed=42)

@@ -201,7 +201,7 @@ def test_stage_dopri5_forward_and_adjoint_vs_oracle():
     assert torch.equal(out[0].detach(), y0.detach())
     assert _rel(out.detach().cpu(), ref.detach()) < 2e-2
     # at rtol = atol = 1e-3 the oracle's own dL/dy0 is 6e-2 (rms) away from the converged gradient and ours 4.5e-2
-    # (scripts/dopri_check.py: both solvers take ~4 steps and differentiate the 4th-order dense output); the weight
+    # (tests/tools/dopri_check.py: both solvers take ~4 steps and differentiate the 4th-order dense output); the weight
     # gradients agree much more closely
     assert _rms(y0.grad.cpu(), y0r.grad) < 0.12
     for (n, p), (_, q) in zip(model.odefunc.func.net.named_parameters(), oracle.odefunc.func.net.named_parameters()):
