@@ -247,6 +247,353 @@ __global__ void gat_bwd_input_kernel(const float* __restrict__ dxw, const float*
   }
 }
 
+
+// =========================================================================================================
+// Sub-warp kernels for the shapes the zone graph uses (heads * F_out = 8 .. 128 channels, F_in <= 8).
+// LPR = channels / 4 lanes own one row (each lane 4 consecutive channels), so a warp works on 32 / LPR rows at once
+// and no lane idles.  The forward is ONE kernel in the reordered (linear) form
+//     out[i,h,:] = W_h (sum_j alpha_ijh x_j),   a_src[j,h] = (W_h^T att_src_h) . x_j
+// i.e. neighbours are gathered in the F_in-dimensional input space (28 B per edge instead of a 256 B projected row);
+// xw, a_src, a_dst and alpha are still written for the backward pass (one coalesced store each).
+// =========================================================================================================
+constexpr int GAT_FIN = 8;
+
+template <int LPR>
+__global__ void __launch_bounds__(256) gat_fwd_fused_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, int Z,
+                                                            const float* __restrict__ x, int F_in, const float* __restrict__ W,
+                                                            const float* __restrict__ att_src, const float* __restrict__ att_dst,
+                                                            const float* __restrict__ bias, int heads, int F_out, int concat,
+                                                            float slope, float* __restrict__ out, float* __restrict__ xw,
+                                                            float* __restrict__ a_src, float* __restrict__ a_dst,
+                                                            float* __restrict__ alpha) {
+  constexpr int RPW = 32 / LPR, HF = 4 * LPR;
+  __shared__ float u_s[32 * GAT_FIN], u_d[32 * GAT_FIN];     // W_h^T att_src_h, W_h^T att_dst_h
+  for (int idx = threadIdx.x; idx < heads * GAT_FIN; idx += blockDim.x) {
+    const int h = idx / GAT_FIN, k = idx % GAT_FIN;
+    float s = 0.f, d = 0.f;
+    if (k < F_in)
+      for (int f = 0; f < F_out; ++f) {
+        const float w = W[(size_t)(h * F_out + f) * F_in + k];
+        s = fmaf(att_src[h * F_out + f], w, s);
+        d = fmaf(att_dst[h * F_out + f], w, d);
+      }
+    u_s[idx] = s; u_d[idx] = d;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, g = lane / LPR, sl = lane % LPR;
+  const int c = 4 * sl, h = c / F_out, lph = F_out / 4;
+  const bool leader = (sl % lph) == 0;
+  float wr[4][GAT_FIN], us[GAT_FIN];
+#pragma unroll
+  for (int k = 0; k < GAT_FIN; ++k) {
+    us[k] = u_s[h * GAT_FIN + k];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) wr[q][k] = k < F_in ? W[(size_t)(c + q) * F_in + k] : 0.f;
+  }
+  const float4 as4 = *reinterpret_cast<const float4*>(att_src + c), ad4 = *reinterpret_cast<const float4*>(att_dst + c);
+  float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (bias) b4 = *reinterpret_cast<const float4*>(bias + (concat ? c : c % F_out));
+  const int nwarp = (gridDim.x * blockDim.x) >> 5;
+  for (int rg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; rg * RPW < Z; rg += nwarp) {
+    const int i = rg * RPW + g;
+    const bool on = i < Z;
+    // ---- own row: projection (kept for the backward pass) and the two attention logits
+    float xi[GAT_FIN];
+#pragma unroll
+    for (int k = 0; k < GAT_FIN; ++k) xi[k] = (on && k < F_in) ? x[(size_t)i * F_in + k] : 0.f;
+    float p[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < GAT_FIN; ++k) acc = fmaf(xi[k], wr[q][k], acc);
+      p[q] = acc;
+    }
+    if (on) *reinterpret_cast<float4*>(xw + (size_t)i * HF + c) = make_float4(p[0], p[1], p[2], p[3]);
+    float ps = p[0] * as4.x + p[1] * as4.y + p[2] * as4.z + p[3] * as4.w;
+    float pd = p[0] * ad4.x + p[1] * ad4.y + p[2] * ad4.z + p[3] * ad4.w;
+    for (int o = lph >> 1; o > 0; o >>= 1) { ps += __shfl_xor_sync(0xffffffffu, ps, o); pd += __shfl_xor_sync(0xffffffffu, pd, o); }
+    if (on && leader) { a_src[(size_t)i * heads + h] = ps; a_dst[(size_t)i * heads + h] = pd; }
+    const float ad = pd;
+    int e0 = 0, deg = 0;
+    if (on) { e0 = rowptr[i]; deg = rowptr[i + 1] - e0; }
+    int maxdeg = deg;
+    for (int o = 16; o > 0; o >>= 1) maxdeg = max(maxdeg, __shfl_xor_sync(0xffffffffu, maxdeg, o));
+    // ---- pass 1: running max and sum of the edge scores (input-space gathers only)
+    float m = -INFINITY, ssum = 0.f;
+    for (int b0 = 0; b0 < maxdeg; b0 += LPR) {
+      const int jm = (b0 + sl < deg) ? col[e0 + b0 + sl] : -1;
+#pragma unroll
+      for (int t = 0; t < LPR; ++t) {
+        if (b0 + t >= maxdeg) break;
+        const int j = __shfl_sync(0xffffffffu, jm, g * LPR + t);
+        if (j >= 0) {
+          float pre = ad;
+#pragma unroll
+          for (int k = 0; k < GAT_FIN; ++k)
+            if (k < F_in) pre = fmaf(us[k], x[(size_t)j * F_in + k], pre);
+          const float sc = lrelu(pre, slope), mn = fmaxf(m, sc);
+          ssum = ssum * __expf(m - mn) + __expf(sc - mn);
+          m = mn;
+        }
+      }
+    }
+    const float inv = deg > 0 ? 1.f / ssum : 0.f;
+    // ---- pass 2: normalised coefficients (stored) and the input-space aggregate
+    float agg[GAT_FIN];
+#pragma unroll
+    for (int k = 0; k < GAT_FIN; ++k) agg[k] = 0.f;
+    for (int b0 = 0; b0 < maxdeg; b0 += LPR) {
+      const int jm = (b0 + sl < deg) ? col[e0 + b0 + sl] : -1;
+#pragma unroll
+      for (int t = 0; t < LPR; ++t) {
+        if (b0 + t >= maxdeg) break;
+        const int j = __shfl_sync(0xffffffffu, jm, g * LPR + t);
+        if (j >= 0) {
+          float xj[GAT_FIN];
+          float pre = ad;
+#pragma unroll
+          for (int k = 0; k < GAT_FIN; ++k) {
+            xj[k] = k < F_in ? x[(size_t)j * F_in + k] : 0.f;
+            pre = fmaf(us[k], xj[k], pre);
+          }
+          const float w = __expf(lrelu(pre, slope) - m) * inv;
+#pragma unroll
+          for (int k = 0; k < GAT_FIN; ++k) agg[k] = fmaf(w, xj[k], agg[k]);
+          if (leader) alpha[(size_t)(e0 + b0 + t) * heads + h] = w;
+        }
+      }
+    }
+    float o4[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < GAT_FIN; ++k) acc = fmaf(agg[k], wr[q][k], acc);
+      o4[q] = acc;
+    }
+    if (concat) {
+      if (on) *reinterpret_cast<float4*>(out + (size_t)i * HF + c) = make_float4(o4[0] + b4.x, o4[1] + b4.y, o4[2] + b4.z, o4[3] + b4.w);
+    } else {
+      // mean over heads: lanes that own the same channels of different heads sit lph * 2^r lanes apart
+      for (int o = lph; o < LPR; o <<= 1) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) o4[q] += __shfl_xor_sync(0xffffffffu, o4[q], o);
+      }
+      const float sc = 1.f / heads;
+      if (on && h == 0) *reinterpret_cast<float4*>(out + (size_t)i * F_out + c) =
+          make_float4(o4[0] * sc + b4.x, o4[1] * sc + b4.y, o4[2] * sc + b4.z, o4[3] * sc + b4.w);
+    }
+  }
+}
+
+// B1 on sub-warps: dalpha_ij = <g_ih, W_h x_j> = (W_h^T g_ih) . x_j, so the destination pass gathers 28 B per edge too
+template <int LPR>
+__global__ void __launch_bounds__(256) gat_bwd_dst_sub_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, int Z,
+                                                              const float* __restrict__ x, int F_in, const float* __restrict__ W,
+                                                              const float* __restrict__ a_src, const float* __restrict__ a_dst,
+                                                              const float* __restrict__ alpha, const float* __restrict__ gout,
+                                                              int heads, int F_out, int concat, float slope, float* __restrict__ de,
+                                                              float* __restrict__ d_adst) {
+  constexpr int RPW = 32 / LPR, HF = 4 * LPR;
+  const int lane = threadIdx.x & 31, g = lane / LPR, sl = lane % LPR;
+  const int c = 4 * sl, h = c / F_out, lph = F_out / 4;
+  const bool leader = (sl % lph) == 0;
+  float wr[4][GAT_FIN];
+#pragma unroll
+  for (int k = 0; k < GAT_FIN; ++k)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) wr[q][k] = k < F_in ? W[(size_t)(c + q) * F_in + k] : 0.f;
+  const int nwarp = (gridDim.x * blockDim.x) >> 5;
+  for (int rg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; rg * RPW < Z; rg += nwarp) {
+    const int i = rg * RPW + g;
+    const bool on = i < Z;
+    float4 gv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (on) {
+      if (concat) gv = *reinterpret_cast<const float4*>(gout + (size_t)i * HF + c);
+      else {
+        const float sc = 1.f / heads;
+        const float4 t = *reinterpret_cast<const float4*>(gout + (size_t)i * F_out + (c % F_out));
+        gv = make_float4(t.x * sc, t.y * sc, t.z * sc, t.w * sc);
+      }
+    }
+    float qv[GAT_FIN];
+#pragma unroll
+    for (int k = 0; k < GAT_FIN; ++k) {
+      float v = gv.x * wr[0][k] + gv.y * wr[1][k] + gv.z * wr[2][k] + gv.w * wr[3][k];
+      for (int o = lph >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      qv[k] = v;
+    }
+    int e0 = 0, deg = 0;
+    if (on) { e0 = rowptr[i]; deg = rowptr[i + 1] - e0; }
+    int maxdeg = deg;
+    for (int o = 16; o > 0; o >>= 1) maxdeg = max(maxdeg, __shfl_xor_sync(0xffffffffu, maxdeg, o));
+    const float ad = on ? a_dst[(size_t)i * heads + h] : 0.f;
+    float ci = 0.f;
+    for (int b0 = 0; b0 < maxdeg; b0 += LPR) {
+      const int jm = (b0 + sl < deg) ? col[e0 + b0 + sl] : -1;
+#pragma unroll
+      for (int t = 0; t < LPR; ++t) {
+        if (b0 + t >= maxdeg) break;
+        const int j = __shfl_sync(0xffffffffu, jm, g * LPR + t);
+        if (j >= 0) {
+          float d = 0.f;
+#pragma unroll
+          for (int k = 0; k < GAT_FIN; ++k)
+            if (k < F_in) d = fmaf(qv[k], x[(size_t)j * F_in + k], d);
+          ci = fmaf(alpha[(size_t)(e0 + b0 + t) * heads + h], d, ci);
+        }
+      }
+    }
+    float dad = 0.f;
+    for (int b0 = 0; b0 < maxdeg; b0 += LPR) {
+      const int jm = (b0 + sl < deg) ? col[e0 + b0 + sl] : -1;
+#pragma unroll
+      for (int t = 0; t < LPR; ++t) {
+        if (b0 + t >= maxdeg) break;
+        const int j = __shfl_sync(0xffffffffu, jm, g * LPR + t);
+        if (j >= 0) {
+          float d = 0.f;
+#pragma unroll
+          for (int k = 0; k < GAT_FIN; ++k)
+            if (k < F_in) d = fmaf(qv[k], x[(size_t)j * F_in + k], d);
+          const size_t eh = (size_t)(e0 + b0 + t) * heads + h;
+          const float pre = a_src[(size_t)j * heads + h] + ad;
+          const float dev = alpha[eh] * (d - ci) * (pre > 0.f ? 1.f : slope);
+          dad += dev;
+          if (leader) de[eh] = dev;
+        }
+      }
+    }
+    if (on && leader) d_adst[(size_t)i * heads + h] = dad;
+  }
+}
+
+// B2 on sub-warps (transposed CSR): same outputs as gat_bwd_src_kernel
+template <int LPR>
+__global__ void __launch_bounds__(256) gat_bwd_src_sub_kernel(const int* __restrict__ rowptr_t, const int* __restrict__ col_t,
+                                                              const int* __restrict__ eid_t, int Z, const float* __restrict__ alpha,
+                                                              const float* __restrict__ de, const float* __restrict__ gout,
+                                                              const float* __restrict__ d_adst, const float* __restrict__ att_src,
+                                                              const float* __restrict__ att_dst, int heads, int F_out, int concat,
+                                                              float* __restrict__ dxw, float* __restrict__ d_asrc) {
+  constexpr int RPW = 32 / LPR, HF = 4 * LPR;
+  const int lane = threadIdx.x & 31, g = lane / LPR, sl = lane % LPR;
+  const int c = 4 * sl, h = c / F_out, lph = F_out / 4;
+  const bool leader = (sl % lph) == 0;
+  const float4 as4 = *reinterpret_cast<const float4*>(att_src + c), at4 = *reinterpret_cast<const float4*>(att_dst + c);
+  const float sc = concat ? 1.f : 1.f / heads;
+  const int nwarp = (gridDim.x * blockDim.x) >> 5;
+  for (int rg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; rg * RPW < Z; rg += nwarp) {
+    const int j = rg * RPW + g;
+    const bool on = j < Z;
+    int e0 = 0, deg = 0;
+    if (on) { e0 = rowptr_t[j]; deg = rowptr_t[j + 1] - e0; }
+    int maxdeg = deg;
+    for (int o = 16; o > 0; o >>= 1) maxdeg = max(maxdeg, __shfl_xor_sync(0xffffffffu, maxdeg, o));
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float das = 0.f;
+    for (int b0 = 0; b0 < maxdeg; b0 += LPR) {
+      const bool has = b0 + sl < deg;
+      const int im = has ? col_t[e0 + b0 + sl] : -1;
+      const int em = has ? eid_t[e0 + b0 + sl] : 0;
+#pragma unroll
+      for (int t = 0; t < LPR; ++t) {
+        if (b0 + t >= maxdeg) break;
+        const int i = __shfl_sync(0xffffffffu, im, g * LPR + t);
+        const int eid = __shfl_sync(0xffffffffu, em, g * LPR + t);
+        if (i >= 0) {
+          const float al = alpha[(size_t)eid * heads + h] * sc;
+          const float4 gv = *reinterpret_cast<const float4*>(gout + (concat ? (size_t)i * HF + c : (size_t)i * F_out + (c % F_out)));
+          acc.x = fmaf(al, gv.x, acc.x); acc.y = fmaf(al, gv.y, acc.y); acc.z = fmaf(al, gv.z, acc.z); acc.w = fmaf(al, gv.w, acc.w);
+          das += de[(size_t)eid * heads + h];
+        }
+      }
+    }
+    if (on) {
+      const float dad = d_adst[(size_t)j * heads + h];
+      acc.x += das * as4.x + dad * at4.x; acc.y += das * as4.y + dad * at4.y;
+      acc.z += das * as4.z + dad * at4.z; acc.w += das * as4.w + dad * at4.w;
+      *reinterpret_cast<float4*>(dxw + (size_t)j * HF + c) = acc;
+      if (leader) d_asrc[(size_t)j * heads + h] = das;
+    }
+  }
+}
+
+// B3, coalesced: thread = (zone lane, channel); every block walks a strided set of zones over ALL channels (row reads
+// of dxw / xw / gout are contiguous), keeps F_in + 3 partial sums per thread and leaves one partial row per block;
+// gat_param_finalize_kernel adds the blocks in a fixed order (deterministic, no atomics).
+template <int HF>
+__global__ void __launch_bounds__(256) gat_bwd_param_tiled_kernel(const float* __restrict__ x, const float* __restrict__ xw,
+                                                                  const float* __restrict__ dxw, const float* __restrict__ d_asrc,
+                                                                  const float* __restrict__ d_adst, const float* __restrict__ gout,
+                                                                  int Z, int F_in, int heads, int F_out, int concat,
+                                                                  float* __restrict__ partial) {
+  constexpr int ZL = 256 / HF, NQ = GAT_FIN + 3;
+  const int c = threadIdx.x % HF, zl = threadIdx.x / HF, h = c / F_out;
+  float acc[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) acc[q] = 0.f;
+  for (int z = blockIdx.x * ZL + zl; z < Z; z += gridDim.x * ZL) {
+    const float d = dxw[(size_t)z * HF + c];
+#pragma unroll
+    for (int k = 0; k < GAT_FIN; ++k)
+      if (k < F_in) acc[k] = fmaf(d, x[(size_t)z * F_in + k], acc[k]);
+    const float v = xw[(size_t)z * HF + c];
+    acc[GAT_FIN] = fmaf(d_asrc[(size_t)z * heads + h], v, acc[GAT_FIN]);
+    acc[GAT_FIN + 1] = fmaf(d_adst[(size_t)z * heads + h], v, acc[GAT_FIN + 1]);
+    if (concat) acc[GAT_FIN + 2] += gout[(size_t)z * HF + c];
+    else if (c < F_out) acc[GAT_FIN + 2] += gout[(size_t)z * F_out + c];
+  }
+  __shared__ float red[NQ][256];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) red[q][threadIdx.x] = acc[q];
+  __syncthreads();
+  if (zl == 0) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      float s = 0.f;
+      for (int l = 0; l < ZL; ++l) s += red[q][l * HF + c];
+      partial[((size_t)blockIdx.x * NQ + q) * HF + c] = s;
+    }
+  }
+}
+
+__global__ void gat_param_finalize_kernel(const float* __restrict__ partial, int nblk, int HF, int F_in, int F_out, int concat,
+                                          float* __restrict__ dW, float* __restrict__ datt_src, float* __restrict__ datt_dst,
+                                          float* __restrict__ dbias) {
+  constexpr int NQ = GAT_FIN + 3;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= NQ * HF) return;
+  const int q = idx / HF, c = idx % HF;
+  float s = 0.f;
+  for (int b = 0; b < nblk; ++b) s += partial[((size_t)b * NQ + q) * HF + c];
+  if (q < GAT_FIN) { if (q < F_in) dW[(size_t)c * F_in + q] = s; }
+  else if (q == GAT_FIN) datt_src[c] = s;
+  else if (q == GAT_FIN + 1) datt_dst[c] = s;
+  else if (dbias && (concat || c < F_out)) dbias[c] = s;
+}
+
+constexpr int GAT_PARAM_BLOCKS = 148 * 4;
+static bool gat_sub_ok(int heads, int F_out, int F_in) {
+  const int HF = heads * F_out;
+  return F_in <= GAT_FIN && heads <= 32 && (HF == 8 || HF == 16 || HF == 32 || HF == 64 || HF == 128);
+}
+static int gat_sub_grid(int Z, int lpr) {
+  const int rows_per_block = 8 * (32 / lpr);
+  const int need = (Z + rows_per_block - 1) / rows_per_block;
+  const int cap = 148 * 8;
+  return need < cap ? (need < 1 ? 1 : need) : cap;
+}
+#define GAT_DISPATCH_LPR(HF_, CALL)              \
+  switch ((HF_) / 4) {                           \
+    case 2: { constexpr int L_ = 2; CALL; } break;   \
+    case 4: { constexpr int L_ = 4; CALL; } break;   \
+    case 8: { constexpr int L_ = 8; CALL; } break;   \
+    case 16: { constexpr int L_ = 16; CALL; } break; \
+    default: { constexpr int L_ = 32; CALL; } break; \
+  }
+
 static bool gat_shape_ok(int heads, int F_out, int F_in) {
   return heads > 0 && F_out >= 4 && F_out % 4 == 0 && (F_out & (F_out - 1)) == 0 && F_in > 0 && F_in <= 32;
 }
@@ -256,6 +603,12 @@ int gat_forward(const int* rowptr, const int* col, int Z, int nnz, const float* 
                 float* a_src, float* a_dst, float* alpha, cudaStream_t st) {
   (void)nnz;
   if (!gat_shape_ok(heads, F_out, F_in)) return AB200_ERR_UNSUPPORTED;
+  if (gat_sub_ok(heads, F_out, F_in)) {
+    const int HF = heads * F_out;
+    GAT_DISPATCH_LPR(HF, (gat_fwd_fused_kernel<L_><<<gat_sub_grid(Z, L_), 256, 0, st>>>(
+                             rowptr, col, Z, x, F_in, W, att_src, att_dst, bias, heads, F_out, concat, slope, out, xw, a_src, a_dst, alpha)));
+    return check_launch();
+  }
   const int wpb = 8, blocks = (Z + wpb - 1) / wpb;
   if (F_out >= 32) {
     cudaMemsetAsync(a_src, 0, sizeof(float) * (size_t)Z * heads, st);
@@ -274,8 +627,10 @@ int gat_forward(const int* rowptr, const int* col, int Z, int nnz, const float* 
 
 size_t gat_backward_workspace(int Z, int nnz, int heads, int F_out) {
   // de [nnz,H], d_adst [Z,H], d_asrc [Z,H], dxw [Z,HF]
+  // + per-block partial rows of the tiled parameter reduction
   return align_up(sizeof(float) * (size_t)nnz * heads, 256) + 2 * align_up(sizeof(float) * (size_t)Z * heads, 256) +
-         align_up(sizeof(float) * (size_t)Z * heads * F_out, 256);
+         align_up(sizeof(float) * (size_t)Z * heads * F_out, 256) +
+         align_up(sizeof(float) * (size_t)GAT_PARAM_BLOCKS * (GAT_FIN + 3) * heads * F_out, 256);
 }
 
 int gat_backward(const int* rowptr, const int* col, const int* rowptr_t, const int* col_t, const int* eid_t, int Z, int nnz,
@@ -289,11 +644,36 @@ int gat_backward(const int* rowptr, const int* col, const int* rowptr_t, const i
   float* de = (float*)p; p += align_up(sizeof(float) * (size_t)nnz * heads, 256);
   float* d_adst = (float*)p; p += align_up(sizeof(float) * (size_t)Z * heads, 256);
   float* d_asrc = (float*)p; p += align_up(sizeof(float) * (size_t)Z * heads, 256);
-  float* dxw = (float*)p;
+  float* dxw = (float*)p; p += align_up(sizeof(float) * (size_t)Z * heads * F_out, 256);
+  float* partial = (float*)p;
   const int HF = heads * F_out;
+  int rc = 0;
+  if (gat_sub_ok(heads, F_out, F_in)) {
+    GAT_DISPATCH_LPR(HF, (gat_bwd_dst_sub_kernel<L_><<<gat_sub_grid(Z, L_), 256, 0, st>>>(
+                             rowptr, col, Z, x, F_in, W, a_src, a_dst, alpha, gout, heads, F_out, concat, slope, de, d_adst)));
+    if ((rc = check_launch())) return rc;
+    GAT_DISPATCH_LPR(HF, (gat_bwd_src_sub_kernel<L_><<<gat_sub_grid(Z, L_), 256, 0, st>>>(
+                             rowptr_t, col_t, eid_t, Z, alpha, de, gout, d_adst, att_src, att_dst, heads, F_out, concat, dxw, d_asrc)));
+    if ((rc = check_launch())) return rc;
+    const int zl = 256 / HF;
+    int nblk = (Z + zl - 1) / zl;
+    if (nblk > GAT_PARAM_BLOCKS) nblk = GAT_PARAM_BLOCKS;
+    GAT_DISPATCH_LPR(HF, (gat_bwd_param_tiled_kernel<4 * L_><<<nblk, 256, 0, st>>>(x, xw, dxw, d_asrc, d_adst, gout, Z, F_in, heads, F_out,
+                                                                                    concat, partial)));
+    if ((rc = check_launch())) return rc;
+    const int nfin = (GAT_FIN + 3) * HF;
+    gat_param_finalize_kernel<<<(nfin + 255) / 256, 256, 0, st>>>(partial, nblk, HF, F_in, F_out, concat, grad_W, grad_att_src,
+                                                                 grad_att_dst, grad_bias);
+    if ((rc = check_launch())) return rc;
+    if (grad_x) {
+      gat_bwd_input_kernel<<<148 * 4, 256, 0, st>>>(dxw, W, Z, F_in, HF, grad_x);
+      rc = check_launch();
+    }
+    return rc;
+  }
   const int wpb = 8, blocks = (Z + wpb - 1) / wpb;
   gat_bwd_dst_kernel<<<blocks, 256, 0, st>>>(rowptr, col, Z, xw, a_src, a_dst, alpha, gout, heads, F_out, concat, slope, de, d_adst);
-  int rc = check_launch();
+  rc = check_launch();
   if (rc) return rc;
   gat_bwd_src_kernel<<<blocks, 256, 0, st>>>(rowptr_t, col_t, eid_t, Z, alpha, de, gout, d_adst, att_src, att_dst, heads, F_out,
                                              concat, dxw, d_asrc);

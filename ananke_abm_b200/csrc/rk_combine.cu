@@ -37,24 +37,51 @@ __global__ void __launch_bounds__(256) stage_combine_kernel(const float* __restr
   }
 }
 
+template <int VEC>
 __global__ void __launch_bounds__(256) combine_errnorm_kernel(const float* __restrict__ y0, KPtrs kp, int n_k, float dt,
                                                               float rtol, float atol, float* __restrict__ y1_out,
                                                               float* __restrict__ sumsq, int64_t n) {
   float local = 0.f;
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    float s = 0.f, e = 0.f;
-    for (int j = 0; j < n_k; ++j) {
-      const float kv = kp.k[j][i];
-      s = fadd(s, fmul(kv, kp.c[j] * dt));
-      e = fadd(e, fmul(kv, kp.e[j] * dt));
-    }
-    const float a = y0[i];
+  auto one = [&](float a, float s, float e) -> float {      // element: solution value + squared error ratio
     const float b = fadd(a, s);
-    if (y1_out) y1_out[i] = b;
     const float tol = atol + rtol * fmaxf(fabsf(a), fabsf(b));
     const float r = e / tol;
     local = fmaf(r, r, local);
+    return b;
+  };
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * VEC;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * VEC; i < n; i += stride) {
+    if (VEC == 4 && i + 3 < n) {
+      // all stage loads are issued before the first is consumed (8 independent 128-bit loads in flight per thread)
+      float4 kv[MAXK];
+#pragma unroll
+      for (int j = 0; j < MAXK; ++j)
+        if (j < n_k) kv[j] = *reinterpret_cast<const float4*>(kp.k[j] + i);
+      const float4 a = *reinterpret_cast<const float4*>(y0 + i);
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f), e = s;
+#pragma unroll
+      for (int j = 0; j < MAXK; ++j)
+        if (j < n_k) {
+          const float c = kp.c[j] * dt, ce = kp.e[j] * dt;
+          s.x = fadd(s.x, fmul(kv[j].x, c)); s.y = fadd(s.y, fmul(kv[j].y, c));
+          s.z = fadd(s.z, fmul(kv[j].z, c)); s.w = fadd(s.w, fmul(kv[j].w, c));
+          e.x = fadd(e.x, fmul(kv[j].x, ce)); e.y = fadd(e.y, fmul(kv[j].y, ce));
+          e.z = fadd(e.z, fmul(kv[j].z, ce)); e.w = fadd(e.w, fmul(kv[j].w, ce));
+        }
+      const float4 b = make_float4(one(a.x, s.x, e.x), one(a.y, s.y, e.y), one(a.z, s.z, e.z), one(a.w, s.w, e.w));
+      if (y1_out) *reinterpret_cast<float4*>(y1_out + i) = b;
+    } else {
+      for (int64_t q = i; q < n && q < i + VEC; ++q) {
+        float s = 0.f, e = 0.f;
+        for (int j = 0; j < n_k; ++j) {
+          const float kv = kp.k[j][q];
+          s = fadd(s, fmul(kv, kp.c[j] * dt));
+          e = fadd(e, fmul(kv, kp.e[j] * dt));
+        }
+        const float b = one(y0[q], s, e);
+        if (y1_out) y1_out[q] = b;
+      }
+    }
   }
   // warp -> block -> one atomic per block
   for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
@@ -94,8 +121,13 @@ int rk_combine_errnorm(const float* y0, const float* const* k, const float* csol
                        float rtol, float atol, float* y1_out, float* sumsq, int64_t n, cudaStream_t st) {
   if (n_k < 0 || n_k > MAXK) return AB200_ERR_BAD_ARG;
   KPtrs kp{};
-  for (int j = 0; j < n_k; ++j) { kp.k[j] = k[j]; kp.c[j] = csol[j]; kp.e[j] = cerr[j]; }
-  combine_errnorm_kernel<<<grid_for(n, 1), 256, 0, st>>>(y0, kp, n_k, dt, rtol, atol, y1_out, sumsq, n);
+  bool aligned = (((uintptr_t)y0 | (uintptr_t)y1_out) & 15) == 0;
+  for (int j = 0; j < n_k; ++j) {
+    kp.k[j] = k[j]; kp.c[j] = csol[j]; kp.e[j] = cerr[j];
+    aligned = aligned && (((uintptr_t)k[j]) & 15) == 0;
+  }
+  if (aligned) combine_errnorm_kernel<4><<<grid_for(n, 4), 256, 0, st>>>(y0, kp, n_k, dt, rtol, atol, y1_out, sumsq, n);
+  else combine_errnorm_kernel<1><<<grid_for(n, 1), 256, 0, st>>>(y0, kp, n_k, dt, rtol, atol, y1_out, sumsq, n);
   return check_launch();
 }
 

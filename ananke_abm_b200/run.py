@@ -18,7 +18,7 @@ from torch import nn
 from .gnn_embed import GATEmbed
 from .graph import ZoneCSR
 from .mode_sep import ModeSepConfig, ODEFunc, WrappedSDE, _solver_options
-from .odeint import odeint
+from .odeint import odeint, odeint_adjoint
 
 
 class GATODEModel(nn.Module):
@@ -44,8 +44,9 @@ class GATODEModel(nn.Module):
         return torch.cat([p0, torch.zeros_like(p0), h], dim=-1)
 
     def integrate(self, y0, times_union) -> torch.Tensor:
-        return odeint(self.odefunc, y0, times_union, method=self.config.ode_method, rtol=self.config.rtol,
-                      atol=self.config.atol, options=_solver_options(self.config))
+        solve = odeint_adjoint if getattr(self.config, "adjoint", False) else odeint     # the odeint_adjoint seam on request
+        return solve(self.odefunc, y0, times_union, method=self.config.ode_method, rtol=self.config.rtol,
+                     atol=self.config.atol, options=_solver_options(self.config))
 
     def head(self, y_path, class_table):
         E, H = self.config.emb_dim, self.config.context_dim
