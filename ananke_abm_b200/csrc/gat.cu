@@ -497,16 +497,31 @@ __global__ void __launch_bounds__(256) gat_bwd_src_sub_kernel(const int* __restr
       const bool has = b0 + sl < deg;
       const int im = has ? col_t[e0 + b0 + sl] : -1;
       const int em = has ? eid_t[e0 + b0 + sl] : 0;
+      constexpr int GRP = LPR < 4 ? LPR : 4;       // loads of a group are independent: issued together
+      for (int t0 = 0; t0 < LPR; t0 += GRP) {
+        if (b0 + t0 >= maxdeg) break;
+        int ii[GRP], ee[GRP];
+        float al[GRP], dd[GRP];
+        float4 gv[GRP];
 #pragma unroll
-      for (int t = 0; t < LPR; ++t) {
-        if (b0 + t >= maxdeg) break;
-        const int i = __shfl_sync(0xffffffffu, im, g * LPR + t);
-        const int eid = __shfl_sync(0xffffffffu, em, g * LPR + t);
-        if (i >= 0) {
-          const float al = alpha[(size_t)eid * heads + h] * sc;
-          const float4 gv = *reinterpret_cast<const float4*>(gout + (concat ? (size_t)i * HF + c : (size_t)i * F_out + (c % F_out)));
-          acc.x = fmaf(al, gv.x, acc.x); acc.y = fmaf(al, gv.y, acc.y); acc.z = fmaf(al, gv.z, acc.z); acc.w = fmaf(al, gv.w, acc.w);
-          das += de[(size_t)eid * heads + h];
+        for (int u = 0; u < GRP; ++u) {
+          ii[u] = __shfl_sync(0xffffffffu, im, g * LPR + t0 + u);
+          ee[u] = __shfl_sync(0xffffffffu, em, g * LPR + t0 + u);
+        }
+#pragma unroll
+        for (int u = 0; u < GRP; ++u) {
+          al[u] = 0.f; dd[u] = 0.f; gv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ii[u] >= 0) {
+            al[u] = alpha[(size_t)ee[u] * heads + h] * sc;
+            dd[u] = de[(size_t)ee[u] * heads + h];
+            gv[u] = *reinterpret_cast<const float4*>(gout + (concat ? (size_t)ii[u] * HF + c : (size_t)ii[u] * F_out + (c % F_out)));
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < GRP; ++u) {
+          acc.x = fmaf(al[u], gv[u].x, acc.x); acc.y = fmaf(al[u], gv[u].y, acc.y);
+          acc.z = fmaf(al[u], gv[u].z, acc.z); acc.w = fmaf(al[u], gv[u].w, acc.w);
+          das += dd[u];
         }
       }
     }
@@ -534,16 +549,30 @@ __global__ void __launch_bounds__(256) gat_bwd_param_tiled_kernel(const float* _
   float acc[NQ];
 #pragma unroll
   for (int q = 0; q < NQ; ++q) acc[q] = 0.f;
-  for (int z = blockIdx.x * ZL + zl; z < Z; z += gridDim.x * ZL) {
-    const float d = dxw[(size_t)z * HF + c];
+  const int zstep = gridDim.x * ZL;
+  for (int z0 = blockIdx.x * ZL + zl; z0 < Z; z0 += 4 * zstep) {
+    float d[4], v[4], ds[4], dd[4], gb[4], xv[4][GAT_FIN];
 #pragma unroll
-    for (int k = 0; k < GAT_FIN; ++k)
-      if (k < F_in) acc[k] = fmaf(d, x[(size_t)z * F_in + k], acc[k]);
-    const float v = xw[(size_t)z * HF + c];
-    acc[GAT_FIN] = fmaf(d_asrc[(size_t)z * heads + h], v, acc[GAT_FIN]);
-    acc[GAT_FIN + 1] = fmaf(d_adst[(size_t)z * heads + h], v, acc[GAT_FIN + 1]);
-    if (concat) acc[GAT_FIN + 2] += gout[(size_t)z * HF + c];
-    else if (c < F_out) acc[GAT_FIN + 2] += gout[(size_t)z * F_out + c];
+    for (int u = 0; u < 4; ++u) {                 // all loads of four zones in flight before the first FMA
+      const int z = z0 + u * zstep;
+      const bool ok = z < Z;
+      d[u] = ok ? dxw[(size_t)z * HF + c] : 0.f;
+      v[u] = ok ? xw[(size_t)z * HF + c] : 0.f;
+      ds[u] = ok ? d_asrc[(size_t)z * heads + h] : 0.f;
+      dd[u] = ok ? d_adst[(size_t)z * heads + h] : 0.f;
+      gb[u] = 0.f;
+      if (ok) { if (concat) gb[u] = gout[(size_t)z * HF + c]; else if (c < F_out) gb[u] = gout[(size_t)z * F_out + c]; }
+#pragma unroll
+      for (int k = 0; k < GAT_FIN; ++k) xv[u][k] = (ok && k < F_in) ? x[(size_t)z * F_in + k] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int k = 0; k < GAT_FIN; ++k) acc[k] = fmaf(d[u], xv[u][k], acc[k]);
+      acc[GAT_FIN] = fmaf(ds[u], v[u], acc[GAT_FIN]);
+      acc[GAT_FIN + 1] = fmaf(dd[u], v[u], acc[GAT_FIN + 1]);
+      acc[GAT_FIN + 2] += gb[u];
+    }
   }
   __shared__ float red[NQ][256];
 #pragma unroll
@@ -574,7 +603,246 @@ __global__ void gat_param_finalize_kernel(const float* __restrict__ partial, int
   else if (dbias && (concat || c < F_out)) dbias[c] = s;
 }
 
-constexpr int GAT_PARAM_BLOCKS = 148 * 4;
+// ---------------------------------------------------------------------------------------------------------
+// Lane = (row, head): `heads` lanes share a destination row, each owns the FO channels of one head.  Nothing about a
+// head's edge softmax is computed twice (the sub-warp kernels above repeat it in every lane of the head), no shuffle
+// sits in the edge loops, and rows of different degree simply diverge at the loop tail.  W lives in shared memory,
+// one padded block per head ([FO][8] + 4 floats: 128-bit rows, heads on different banks).
+// ---------------------------------------------------------------------------------------------------------
+template <int FO>
+__global__ void __launch_bounds__(256, 3) gat_fwd_rowhead_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, int Z,
+                                                              const float* __restrict__ x, int F_in, const float* __restrict__ W,
+                                                              const float* __restrict__ att_src, const float* __restrict__ att_dst,
+                                                              const float* __restrict__ bias, int heads, int concat, float slope,
+                                                              float* __restrict__ out, float* __restrict__ xw,
+                                                              float* __restrict__ a_src, float* __restrict__ a_dst,
+                                                              float* __restrict__ alpha) {
+  constexpr int WS = FO * GAT_FIN + 4;
+  __shared__ __align__(16) float Wsm[128 * GAT_FIN + 32 * 4];
+  __shared__ float att_s[128], att_d[128];
+  const int HF = heads * FO;
+  for (int idx = threadIdx.x; idx < HF * GAT_FIN; idx += blockDim.x) {
+    const int c = idx / GAT_FIN, k = idx % GAT_FIN;
+    Wsm[(c / FO) * WS + (c % FO) * GAT_FIN + k] = k < F_in ? W[(size_t)c * F_in + k] : 0.f;
+  }
+  for (int idx = threadIdx.x; idx < HF; idx += blockDim.x) { att_s[idx] = att_src[idx]; att_d[idx] = att_dst[idx]; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, rpw = 32 / heads, g = lane / heads, h = lane % heads;
+  const float* Wh = Wsm + h * WS;
+  float us[GAT_FIN];                     // W_h^T att_src_h: neighbour logits straight from the input features
+#pragma unroll
+  for (int k = 0; k < GAT_FIN; ++k) us[k] = 0.f;
+  for (int f = 0; f < FO; ++f) {
+    const float a = att_s[h * FO + f];
+#pragma unroll
+    for (int k = 0; k < GAT_FIN; ++k) us[k] = fmaf(a, Wh[f * GAT_FIN + k], us[k]);
+  }
+  const int nwarp = (gridDim.x * blockDim.x) >> 5;
+  for (int rg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; rg * rpw < Z; rg += nwarp) {
+    const int i = rg * rpw + g;
+    const bool on = i < Z;
+    float xi[GAT_FIN];
+#pragma unroll
+    for (int k = 0; k < GAT_FIN; ++k) xi[k] = (on && k < F_in) ? x[(size_t)i * F_in + k] : 0.f;
+    float ps = 0.f, pd = 0.f;
+#pragma unroll 1      // keep W in shared memory: unrolled, the 2 * FO weight rows get hoisted out of the row loop (220 registers)
+    for (int f4 = 0; f4 < FO / 4; ++f4) {
+      float p[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 w0 = *reinterpret_cast<const float4*>(Wh + (f4 * 4 + q) * GAT_FIN);
+        const float4 w1 = *reinterpret_cast<const float4*>(Wh + (f4 * 4 + q) * GAT_FIN + 4);
+        p[q] = xi[0] * w0.x + xi[1] * w0.y + xi[2] * w0.z + xi[3] * w0.w + xi[4] * w1.x + xi[5] * w1.y + xi[6] * w1.z + xi[7] * w1.w;
+        ps = fmaf(p[q], att_s[h * FO + f4 * 4 + q], ps);
+        pd = fmaf(p[q], att_d[h * FO + f4 * 4 + q], pd);
+      }
+      if (on) *reinterpret_cast<float4*>(xw + (size_t)i * HF + h * FO + f4 * 4) = make_float4(p[0], p[1], p[2], p[3]);
+    }
+    int e0 = 0, deg = 0;
+    if (on) {
+      a_src[(size_t)i * heads + h] = ps;
+      a_dst[(size_t)i * heads + h] = pd;
+      e0 = rowptr[i]; deg = rowptr[i + 1] - e0;
+    }
+    const float ad = pd;
+    float m = -INFINITY, ssum = 0.f;
+    for (int e = 0; e < deg; ++e) {
+      const int j = col[e0 + e];
+      float pre = ad;
+#pragma unroll
+      for (int k = 0; k < GAT_FIN; ++k)
+        if (k < F_in) pre = fmaf(us[k], x[(size_t)j * F_in + k], pre);
+      const float sc = lrelu(pre, slope), mn = fmaxf(m, sc);
+      ssum = ssum * __expf(m - mn) + __expf(sc - mn);
+      m = mn;
+    }
+    const float inv = deg > 0 ? 1.f / ssum : 0.f;
+    float agg[GAT_FIN];
+#pragma unroll
+    for (int k = 0; k < GAT_FIN; ++k) agg[k] = 0.f;
+    for (int e = 0; e < deg; ++e) {
+      const int j = col[e0 + e];
+      float xj[GAT_FIN];
+      float pre = ad;
+#pragma unroll
+      for (int k = 0; k < GAT_FIN; ++k) {
+        xj[k] = k < F_in ? x[(size_t)j * F_in + k] : 0.f;
+        pre = fmaf(us[k], xj[k], pre);
+      }
+      const float w = __expf(lrelu(pre, slope) - m) * inv;
+      alpha[(size_t)(e0 + e) * heads + h] = w;
+#pragma unroll
+      for (int k = 0; k < GAT_FIN; ++k) agg[k] = fmaf(w, xj[k], agg[k]);
+    }
+    const float sc_mean = 1.f / heads;
+#pragma unroll 1      // keep W in shared memory: unrolled, the 2 * FO weight rows get hoisted out of the row loop (220 registers)
+    for (int f4 = 0; f4 < FO / 4; ++f4) {
+      float o[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 w0 = *reinterpret_cast<const float4*>(Wh + (f4 * 4 + q) * GAT_FIN);
+        const float4 w1 = *reinterpret_cast<const float4*>(Wh + (f4 * 4 + q) * GAT_FIN + 4);
+        o[q] = agg[0] * w0.x + agg[1] * w0.y + agg[2] * w0.z + agg[3] * w0.w + agg[4] * w1.x + agg[5] * w1.y + agg[6] * w1.z + agg[7] * w1.w;
+      }
+      if (concat) {
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bias) b = *reinterpret_cast<const float4*>(bias + h * FO + f4 * 4);
+        if (on) *reinterpret_cast<float4*>(out + (size_t)i * HF + h * FO + f4 * 4) = make_float4(o[0] + b.x, o[1] + b.y, o[2] + b.z, o[3] + b.w);
+      } else {
+        for (int w = 1; w < heads; w <<= 1) {       // mean over the heads of the row (adjacent lanes)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) o[q] += __shfl_xor_sync(0xffffffffu, o[q], w);
+        }
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bias) b = *reinterpret_cast<const float4*>(bias + f4 * 4);
+        if (on && h == 0) *reinterpret_cast<float4*>(out + (size_t)i * FO + f4 * 4) =
+            make_float4(o[0] * sc_mean + b.x, o[1] * sc_mean + b.y, o[2] * sc_mean + b.z, o[3] * sc_mean + b.w);
+      }
+    }
+  }
+}
+
+template <int FO>
+__global__ void __launch_bounds__(256) gat_bwd_dst_rowhead_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, int Z,
+                                                                  const float* __restrict__ x, int F_in, const float* __restrict__ W,
+                                                                  const float* __restrict__ a_src, const float* __restrict__ a_dst,
+                                                                  const float* __restrict__ alpha, const float* __restrict__ gout,
+                                                                  int heads, int concat, float slope, float* __restrict__ de,
+                                                                  float* __restrict__ d_adst) {
+  constexpr int WS = FO * GAT_FIN + 4;
+  __shared__ __align__(16) float Wsm[128 * GAT_FIN + 32 * 4];
+  const int HF = heads * FO;
+  for (int idx = threadIdx.x; idx < HF * GAT_FIN; idx += blockDim.x) {
+    const int c = idx / GAT_FIN, k = idx % GAT_FIN;
+    Wsm[(c / FO) * WS + (c % FO) * GAT_FIN + k] = k < F_in ? W[(size_t)c * F_in + k] : 0.f;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, rpw = 32 / heads, g = lane / heads, h = lane % heads;
+  const float* Wh = Wsm + h * WS;
+  const float sc = concat ? 1.f : 1.f / heads;
+  const int nwarp = (gridDim.x * blockDim.x) >> 5;
+  for (int rg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; rg * rpw < Z; rg += nwarp) {
+    const int i = rg * rpw + g;
+    if (i >= Z) continue;
+    float qv[GAT_FIN];                    // W_h^T g_ih
+#pragma unroll
+    for (int k = 0; k < GAT_FIN; ++k) qv[k] = 0.f;
+#pragma unroll
+    for (int f4 = 0; f4 < FO / 4; ++f4) {
+      const float4 gv = *reinterpret_cast<const float4*>(gout + (concat ? (size_t)i * HF + h * FO : (size_t)i * FO) + f4 * 4);
+      const float gq[4] = {gv.x * sc, gv.y * sc, gv.z * sc, gv.w * sc};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 w0 = *reinterpret_cast<const float4*>(Wh + (f4 * 4 + q) * GAT_FIN);
+        const float4 w1 = *reinterpret_cast<const float4*>(Wh + (f4 * 4 + q) * GAT_FIN + 4);
+        qv[0] = fmaf(gq[q], w0.x, qv[0]); qv[1] = fmaf(gq[q], w0.y, qv[1]); qv[2] = fmaf(gq[q], w0.z, qv[2]); qv[3] = fmaf(gq[q], w0.w, qv[3]);
+        qv[4] = fmaf(gq[q], w1.x, qv[4]); qv[5] = fmaf(gq[q], w1.y, qv[5]); qv[6] = fmaf(gq[q], w1.z, qv[6]); qv[7] = fmaf(gq[q], w1.w, qv[7]);
+      }
+    }
+    const int e0 = rowptr[i], deg = rowptr[i + 1] - e0;
+    const float ad = a_dst[(size_t)i * heads + h];
+    float ci = 0.f;
+    for (int e = 0; e < deg; ++e) {
+      const int j = col[e0 + e];
+      float d = 0.f;
+#pragma unroll
+      for (int k = 0; k < GAT_FIN; ++k)
+        if (k < F_in) d = fmaf(qv[k], x[(size_t)j * F_in + k], d);
+      ci = fmaf(alpha[(size_t)(e0 + e) * heads + h], d, ci);
+    }
+    float dad = 0.f;
+    for (int e = 0; e < deg; ++e) {
+      const int j = col[e0 + e];
+      float d = 0.f;
+#pragma unroll
+      for (int k = 0; k < GAT_FIN; ++k)
+        if (k < F_in) d = fmaf(qv[k], x[(size_t)j * F_in + k], d);
+      const size_t eh = (size_t)(e0 + e) * heads + h;
+      const float pre = a_src[(size_t)j * heads + h] + ad;
+      const float dev = alpha[eh] * (d - ci) * (pre > 0.f ? 1.f : slope);
+      dad += dev;
+      de[eh] = dev;
+    }
+    d_adst[(size_t)i * heads + h] = dad;
+  }
+}
+
+static bool gat_rowhead_ok(int heads, int F_out, int F_in) {
+  return F_in <= GAT_FIN && heads <= 32 && (heads & (heads - 1)) == 0 && heads * F_out <= 128 &&
+         (F_out == 4 || F_out == 8 || F_out == 16 || F_out == 32);
+}
+static int gat_rowhead_grid(int Z, int heads) {
+  const int rows_per_block = 8 * (32 / heads);
+  const int need = (Z + rows_per_block - 1) / rows_per_block;
+  const int cap = 148 * 8;
+  return need < cap ? (need < 1 ? 1 : need) : cap;
+}
+#define GAT_DISPATCH_FO(FO_, CALL)                  \
+  switch (FO_) {                                    \
+    case 4: { constexpr int F_ = 4; CALL; } break;   \
+    case 8: { constexpr int F_ = 8; CALL; } break;   \
+    case 16: { constexpr int F_ = 16; CALL; } break; \
+    default: { constexpr int F_ = 32; CALL; } break; \
+  }
+
+// dx[z,:] = W^T dxw[z,:] on sub-warps: the row of dxw is read once, coalesced; F_in partial sums are reduced over the
+// LPR lanes of the row
+template <int LPR>
+__global__ void __launch_bounds__(256) gat_bwd_input_sub_kernel(const float* __restrict__ dxw, const float* __restrict__ W, int Z,
+                                                                int F_in, float* __restrict__ dx) {
+  constexpr int RPW = 32 / LPR, HF = 4 * LPR;
+  const int lane = threadIdx.x & 31, g = lane / LPR, sl = lane % LPR, c = 4 * sl;
+  float wr[4][GAT_FIN];
+#pragma unroll
+  for (int k = 0; k < GAT_FIN; ++k)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) wr[q][k] = k < F_in ? W[(size_t)(c + q) * F_in + k] : 0.f;
+  const int nwarp = (gridDim.x * blockDim.x) >> 5;
+  for (int rg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; rg * RPW < Z; rg += nwarp) {
+    const int z = rg * RPW + g;
+    const bool on = z < Z;
+    const float4 d = on ? *reinterpret_cast<const float4*>(dxw + (size_t)z * HF + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float mine = 0.f;
+#pragma unroll
+    for (int k = 0; k < GAT_FIN; ++k) {
+      float v = d.x * wr[0][k] + d.y * wr[1][k] + d.z * wr[2][k] + d.w * wr[3][k];
+      for (int o = LPR >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (sl == k) mine = v;
+    }
+    if (on && sl < F_in) dx[(size_t)z * F_in + sl] = mine;     // LPR >= 2; F_in <= 8 needs LPR >= 8 or the loop below
+    if (LPR < GAT_FIN) {
+      // fewer lanes than input features (8 or 16 channels): lane 0 of the row recomputes the remaining ones
+#pragma unroll
+      for (int k = LPR; k < GAT_FIN; ++k) {
+        float v = d.x * wr[0][k] + d.y * wr[1][k] + d.z * wr[2][k] + d.w * wr[3][k];
+        for (int o = LPR >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (on && sl == 0 && k < F_in) dx[(size_t)z * F_in + k] = v;
+      }
+    }
+  }
+}
+
+constexpr int GAT_PARAM_BLOCKS = 148 * 8;
 static bool gat_sub_ok(int heads, int F_out, int F_in) {
   const int HF = heads * F_out;
   return F_in <= GAT_FIN && heads <= 32 && (HF == 8 || HF == 16 || HF == 32 || HF == 64 || HF == 128);
@@ -603,6 +871,11 @@ int gat_forward(const int* rowptr, const int* col, int Z, int nnz, const float* 
                 float* a_src, float* a_dst, float* alpha, cudaStream_t st) {
   (void)nnz;
   if (!gat_shape_ok(heads, F_out, F_in)) return AB200_ERR_UNSUPPORTED;
+  if (gat_rowhead_ok(heads, F_out, F_in)) {
+    GAT_DISPATCH_FO(F_out, (gat_fwd_rowhead_kernel<F_><<<gat_rowhead_grid(Z, heads), 256, 0, st>>>(
+                               rowptr, col, Z, x, F_in, W, att_src, att_dst, bias, heads, concat, slope, out, xw, a_src, a_dst, alpha)));
+    return check_launch();
+  }
   if (gat_sub_ok(heads, F_out, F_in)) {
     const int HF = heads * F_out;
     GAT_DISPATCH_LPR(HF, (gat_fwd_fused_kernel<L_><<<gat_sub_grid(Z, L_), 256, 0, st>>>(
@@ -649,8 +922,13 @@ int gat_backward(const int* rowptr, const int* col, const int* rowptr_t, const i
   const int HF = heads * F_out;
   int rc = 0;
   if (gat_sub_ok(heads, F_out, F_in)) {
-    GAT_DISPATCH_LPR(HF, (gat_bwd_dst_sub_kernel<L_><<<gat_sub_grid(Z, L_), 256, 0, st>>>(
-                             rowptr, col, Z, x, F_in, W, a_src, a_dst, alpha, gout, heads, F_out, concat, slope, de, d_adst)));
+    if (gat_rowhead_ok(heads, F_out, F_in)) {
+      GAT_DISPATCH_FO(F_out, (gat_bwd_dst_rowhead_kernel<F_><<<gat_rowhead_grid(Z, heads), 256, 0, st>>>(
+                                 rowptr, col, Z, x, F_in, W, a_src, a_dst, alpha, gout, heads, concat, slope, de, d_adst)));
+    } else {
+      GAT_DISPATCH_LPR(HF, (gat_bwd_dst_sub_kernel<L_><<<gat_sub_grid(Z, L_), 256, 0, st>>>(
+                               rowptr, col, Z, x, F_in, W, a_src, a_dst, alpha, gout, heads, F_out, concat, slope, de, d_adst)));
+    }
     if ((rc = check_launch())) return rc;
     GAT_DISPATCH_LPR(HF, (gat_bwd_src_sub_kernel<L_><<<gat_sub_grid(Z, L_), 256, 0, st>>>(
                              rowptr_t, col_t, eid_t, Z, alpha, de, gout, d_adst, att_src, att_dst, heads, F_out, concat, dxw, d_asrc)));
@@ -666,7 +944,7 @@ int gat_backward(const int* rowptr, const int* col, const int* rowptr_t, const i
                                                                  grad_att_dst, grad_bias);
     if ((rc = check_launch())) return rc;
     if (grad_x) {
-      gat_bwd_input_kernel<<<148 * 4, 256, 0, st>>>(dxw, W, Z, F_in, HF, grad_x);
+      GAT_DISPATCH_LPR(HF, (gat_bwd_input_sub_kernel<L_><<<gat_sub_grid(Z, L_), 256, 0, st>>>(dxw, W, Z, F_in, grad_x)));
       rc = check_launch();
     }
     return rc;
