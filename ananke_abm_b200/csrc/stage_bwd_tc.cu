@@ -151,40 +151,43 @@ __global__ void __launch_bounds__(THREADS, 1) stage_bwd_tc_kernel(const __grid_c
 
     // ---- stage input -> ACT / HB / TB and the X blob (features: p 0..63, v 64..127, h 128..159, sin, cos, 1)
     uint8_t* xb = blob_at(S.x1(blob));
+    {   // both 16-dim halves together: one batch of independent 128-bit loads per source (n_a + 1 round trips, not 2x that)
+      const int f0 = c.hf * 8;
+      float pin[32], vin[32];
+      const float cpv = sp.in.cpv;
 #pragma unroll
-    for (int ch = 0; ch < 2; ++ch) {
-      const int f0 = c.hf * 8 + ch * 4;
-      float pin[16], vin[16];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < 8; ++j) {
         const float4 pv = ldro(blk4(a.y0, tile, YF4, f0 + j, c.row));
         const float4 vv = ldro(blk4(a.y0, tile, YF4, AF4 + f0 + j, c.row));
-        const float cpv = sp.in.cpv;
         pin[4 * j] = pv.x + cpv * vv.x; pin[4 * j + 1] = pv.y + cpv * vv.y;
         pin[4 * j + 2] = pv.z + cpv * vv.z; pin[4 * j + 3] = pv.w + cpv * vv.w;
         vin[4 * j] = vv.x; vin[4 * j + 1] = vv.y; vin[4 * j + 2] = vv.z; vin[4 * j + 3] = vv.w;
       }
 #pragma unroll 1
       for (int s = 0; s < sp.n_a; ++s) {
-        {
-          const float cp = sp.in.cpa[s], cv = sp.in.cva[s];
+        const float cp = sp.in.cpa[s], cv = sp.in.cva[s];
+        float4 x[8];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 x = ldro(blk4(a.a[s], tile, AF4, f0 + j, c.row));
-            pin[4 * j] += cp * x.x; pin[4 * j + 1] += cp * x.y; pin[4 * j + 2] += cp * x.z; pin[4 * j + 3] += cp * x.w;
-            vin[4 * j] += cv * x.x; vin[4 * j + 1] += cv * x.y; vin[4 * j + 2] += cv * x.z; vin[4 * j + 3] += cv * x.w;
-          }
+        for (int j = 0; j < 8; ++j) x[j] = ldro(blk4(a.a[s], tile, AF4, f0 + j, c.row));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          pin[4 * j] += cp * x[j].x; pin[4 * j + 1] += cp * x[j].y; pin[4 * j + 2] += cp * x[j].z; pin[4 * j + 3] += cp * x[j].w;
+          vin[4 * j] += cv * x[j].x; vin[4 * j + 1] += cv * x[j].y; vin[4 * j + 2] += cv * x[j].z; vin[4 * j + 3] += cv * x[j].w;
         }
       }
-      uint32_t o[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = pack_bf16(pin[2 * j], pin[2 * j + 1]);
-      tmem_st8(c.tmem + c.lane_sel + C_ACT + (uint32_t)(f0 * 2), o);
-      spill_groups<2>(xb, f0 / 2, c.row, o);
+      for (int ch = 0; ch < 2; ++ch) {
+        const int fc = f0 + ch * 4;
+        uint32_t o[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = pack_bf16(vin[2 * j], vin[2 * j + 1]);
-      tmem_st8(c.tmem + c.lane_sel + C_ACT + (uint32_t)(P / 2 + f0 * 2), o);
-      spill_groups<2>(xb, P / 8 + f0 / 2, c.row, o);
+        for (int j = 0; j < 8; ++j) o[j] = pack_bf16(pin[16 * ch + 2 * j], pin[16 * ch + 2 * j + 1]);
+        tmem_st8(c.tmem + c.lane_sel + C_ACT + (uint32_t)(fc * 2), o);
+        spill_groups<2>(xb, fc / 2, c.row, o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = pack_bf16(vin[16 * ch + 2 * j], vin[16 * ch + 2 * j + 1]);
+        tmem_st8(c.tmem + c.lane_sel + C_ACT + (uint32_t)(P / 2 + fc * 2), o);
+        spill_groups<2>(xb, P / 8 + fc / 2, c.row, o);
+      }
     }
     {
       uint32_t o[8];

@@ -150,13 +150,14 @@ __global__ void __launch_bounds__(THREADS, 1) stage_fwd_tc_kernel(const __grid_c
       const StageParams& sp = a.st[si];
       const int n_a = sp.n_a;
       // ---- stage input -> ACT (16-bit), time/bias block -> TB          (all buffers blocked, see stage_tc.cuh)
-#pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {       // 16 dims of p and of v per pass
-        const int f0 = c.hf * 8 + ch * 4;    // first float4 group of this pass
-        float pin[16], vin[16];
+      // Both 16-dim halves of p and of v are built together: every source (y0, then each a_s) is ONE batch of 8-16
+      // independent 128-bit loads, so the stage input costs n_a + 1 memory round trips instead of 2 * (n_a + 1).
+      {
+        const int f0 = c.hf * 8;             // this thread's 8 float4 groups (32 dims) of p and of v
+        float pin[32], vin[32];
         const float cpv = sp.in.cpv;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < 8; ++j) {
           const float4 pv = ldro(blk4(a.y0, tile, YF4, f0 + j, c.row));
           const float4 vv = ldro(blk4(a.y0, tile, YF4, AF4 + f0 + j, c.row));
           pin[4 * j] = pv.x + cpv * vv.x; pin[4 * j + 1] = pv.y + cpv * vv.y;
@@ -166,20 +167,25 @@ __global__ void __launch_bounds__(THREADS, 1) stage_fwd_tc_kernel(const __grid_c
 #pragma unroll 1
         for (int s = 0; s < n_a; ++s) {
           const float cp = sp.in.cpa[s], cv = sp.in.cva[s];
+          float4 x[8];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float4 x = *blk4(a.a[s], tile, AF4, f0 + j, c.row);      // coherent load: may have been written by this launch
-            pin[4 * j] += cp * x.x; pin[4 * j + 1] += cp * x.y; pin[4 * j + 2] += cp * x.z; pin[4 * j + 3] += cp * x.w;
-            vin[4 * j] += cv * x.x; vin[4 * j + 1] += cv * x.y; vin[4 * j + 2] += cv * x.z; vin[4 * j + 3] += cv * x.w;
+          for (int j = 0; j < 8; ++j) x[j] = *blk4(a.a[s], tile, AF4, f0 + j, c.row);   // coherent: may have been written by this launch
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            pin[4 * j] += cp * x[j].x; pin[4 * j + 1] += cp * x[j].y; pin[4 * j + 2] += cp * x[j].z; pin[4 * j + 3] += cp * x[j].w;
+            vin[4 * j] += cv * x[j].x; vin[4 * j + 1] += cv * x[j].y; vin[4 * j + 2] += cv * x[j].z; vin[4 * j + 3] += cv * x[j].w;
           }
         }
-        uint32_t o[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = pack2<HALF>(pin[2 * j], pin[2 * j + 1]);
-        tmem_st8(c.tmem + c.lane_sel + C_ACT + (uint32_t)(f0 * 2), o);
+        for (int ch = 0; ch < 2; ++ch) {
+          uint32_t o[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = pack2<HALF>(vin[2 * j], vin[2 * j + 1]);
-        tmem_st8(c.tmem + c.lane_sel + C_ACT + (uint32_t)(P / 2 + f0 * 2), o);
+          for (int j = 0; j < 8; ++j) o[j] = pack2<HALF>(pin[16 * ch + 2 * j], pin[16 * ch + 2 * j + 1]);
+          tmem_st8(c.tmem + c.lane_sel + C_ACT + (uint32_t)((f0 + ch * 4) * 2), o);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = pack2<HALF>(vin[16 * ch + 2 * j], vin[16 * ch + 2 * j + 1]);
+          tmem_st8(c.tmem + c.lane_sel + C_ACT + (uint32_t)(P / 2 + (f0 + ch * 4) * 2), o);
+        }
       }
       write_time_block<HALF>(c, sp.t, a.period);
       STAGE_TRACE(c, 10);
@@ -200,62 +206,82 @@ __global__ void __launch_bounds__(THREADS, 1) stage_fwd_tc_kernel(const __grid_c
 
       // ---- output epilogue: this thread's 32 acceleration dims (float4 groups hf*8 ..)
       STAGE_TRACE(c, 11);
-      uint32_t r[32];
-      tmem_ld32(c.tmem + c.lane_sel + C_ACC + (uint32_t)(c.hf * 32), r);
-      tmem_ld_wait();
       const int f0 = c.hf * 8;
-      if (sp.a_out != nullptr && valid) {
+      const bool want_y = sp.y_out != nullptr;
+      const bool want_err = want_y && sp.want_err != 0;
+      float oc = 0.f, ov = 0.f, ecp = 0.f, ecv = 0.f, ocpv = 0.f;
+      if (want_y) { oc = sp.out.cpa[n_a]; ov = sp.out.cva[n_a]; ecp = sp.err.cpa[n_a]; ecv = sp.err.cva[n_a]; ocpv = sp.out.cpv; }
+#pragma unroll 1
+      for (int qd = 0; qd < 2; ++qd) {      // 4 float4 groups (16 dims) per pass: 4-8 loads in flight per source
+        uint32_t r[16];
+        tmem_ld16(c.tmem + c.lane_sel + C_ACC + (uint32_t)(c.hf * 32 + qd * 16), r);
+        tmem_ld_wait();
+        const int fq = f0 + qd * 4;
+        if (sp.a_out != nullptr && valid) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *blk4(sp.a_out, tile, AF4, f0 + j, c.row) = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                                                   __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-      }
-      if (sp.y_out != nullptr) {
-        const bool want_err = sp.want_err != 0;
-        const float oc = sp.out.cpa[n_a], ov = sp.out.cva[n_a], ecp = sp.err.cpa[n_a], ecv = sp.err.cva[n_a];
-        const float ocpv = sp.out.cpv;
+          for (int j = 0; j < 4; ++j)
+            *blk4(sp.a_out, tile, AF4, fq + j, c.row) = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                                     __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+        }
+        if (want_y) {
+          float po[16], vo[16], ep[16], ev[16];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {       // one float4 group of p and of v per pass
-          const float4 p0 = ldro(blk4(a.y0, tile, YF4, f0 + j, c.row));
-          const float4 v0 = ldro(blk4(a.y0, tile, YF4, AF4 + f0 + j, c.row));
-          const float ao[4] = {__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                               __uint_as_float(r[4 * j + 3])};
-          const float p0r[4] = {p0.x, p0.y, p0.z, p0.w}, v0r[4] = {v0.x, v0.y, v0.z, v0.w};
-          float po[4], vo[4], ep[4], ev[4];
+          for (int j = 0; j < 4; ++j) {
+            const float4 p0 = ldro(blk4(a.y0, tile, YF4, fq + j, c.row));
+            const float4 v0 = ldro(blk4(a.y0, tile, YF4, AF4 + fq + j, c.row));
+            const float pb[4] = {p0.x, p0.y, p0.z, p0.w}, vb[4] = {v0.x, v0.y, v0.z, v0.w};
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            po[e] = p0r[e] + ocpv * v0r[e] + oc * ao[e];
-            vo[e] = v0r[e] + ov * ao[e];
-            ep[e] = ecp * ao[e];
-            ev[e] = ecv * ao[e];
+            for (int e = 0; e < 4; ++e) {
+              const float ao = __uint_as_float(r[4 * j + e]);
+              po[4 * j + e] = pb[e] + ocpv * vb[e] + oc * ao;
+              vo[4 * j + e] = vb[e] + ov * ao;
+              ep[4 * j + e] = ecp * ao;
+              ev[4 * j + e] = ecv * ao;
+            }
           }
 #pragma unroll 1
           for (int s = 0; s < n_a; ++s) {
-            const float4 x = *blk4(a.a[s], tile, AF4, f0 + j, c.row);
-            const float xs[4] = {x.x, x.y, x.z, x.w};
+            float4 x[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) x[j] = *blk4(a.a[s], tile, AF4, fq + j, c.row);
             const float cp = sp.out.cpa[s], cv = sp.out.cva[s], xp = sp.err.cpa[s], xv = sp.err.cva[s];
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              po[e] += cp * xs[e];
-              vo[e] += cv * xs[e];
-              ep[e] += xp * xs[e];
-              ev[e] += xv * xs[e];
+            for (int j = 0; j < 4; ++j) {
+              const float xs[4] = {x[j].x, x[j].y, x[j].z, x[j].w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                po[4 * j + e] += cp * xs[e];
+                vo[4 * j + e] += cv * xs[e];
+                ep[4 * j + e] += xp * xs[e];
+                ev[4 * j + e] += xv * xs[e];
+              }
             }
           }
           if (valid) {
-            *blk4(sp.y_out, tile, YF4, f0 + j, c.row) = make_float4(po[0], po[1], po[2], po[3]);
-            *blk4(sp.y_out, tile, YF4, AF4 + f0 + j, c.row) = make_float4(vo[0], vo[1], vo[2], vo[3]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              *blk4(sp.y_out, tile, YF4, fq + j, c.row) = make_float4(po[4 * j], po[4 * j + 1], po[4 * j + 2], po[4 * j + 3]);
+              *blk4(sp.y_out, tile, YF4, AF4 + fq + j, c.row) = make_float4(vo[4 * j], vo[4 * j + 1], vo[4 * j + 2], vo[4 * j + 3]);
+            }
             if (want_err) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float tp = a.atol + a.rtol * fmaxf(fabsf(p0r[e]), fabsf(po[e]));
-                const float tv = a.atol + a.rtol * fmaxf(fabsf(v0r[e]), fabsf(vo[e]));
-                const float qp = ep[e] / tp, qv = ev[e] / tv;
-                err_local += (double)(qp * qp + qv * qv);
+              for (int j = 0; j < 4; ++j) {       // y0 again (L1/L2 hit): keeping it live through the source loop costs 32 registers
+                const float4 p0 = ldro(blk4(a.y0, tile, YF4, fq + j, c.row));
+                const float4 v0 = ldro(blk4(a.y0, tile, YF4, AF4 + fq + j, c.row));
+                const float pb[4] = {p0.x, p0.y, p0.z, p0.w}, vb[4] = {v0.x, v0.y, v0.z, v0.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float tp = a.atol + a.rtol * fmaxf(fabsf(pb[e]), fabsf(po[4 * j + e]));
+                  const float tv = a.atol + a.rtol * fmaxf(fabsf(vb[e]), fabsf(vo[4 * j + e]));
+                  const float qp = ep[4 * j + e] / tp, qv = ev[4 * j + e] / tv;
+                  err_local += (double)(qp * qp + qv * qv);
+                }
               }
             }
           }
         }
+      }
+      if (want_y) {
         if (valid) {   // context h rides along unchanged (dh/dt = 0)
 #pragma unroll
           for (int j = 0; j < 4; ++j)
