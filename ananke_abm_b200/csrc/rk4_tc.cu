@@ -2,12 +2,12 @@
 // same throughput as bf16 and 8x less rounding noise -- every value of this net is far inside the fp16 range), one CTA per SM,
 // one 128-agent tile at a time, the WHOLE trajectory of the tile on chip.
 //
-//   shared memory : all six weight matrices of the drift net as bf16 in the canonical K-major (8x8 core matrix,
+//   shared memory : all six weight matrices of the drift net as 16-bit (fp16) values in the canonical K-major (8x8 core matrix,
 //                   un-swizzled) UMMA layout, resident for the kernel's lifetime (184 KiB), + fp32 biases
 //   tensor memory : ACC  [  0,128)  fp32 accumulator of the current layer           (lane = agent row)
-//                   ACT0 [128,192)  bf16 A operand: stage input [p,v] / residual stream z   (2 values / column)
-//                   HCTX [192,208)  bf16 A operand: the agent's static context h (K-steps 8,9 of layer 1)
-//                   ACT1 [208,272)  bf16 A operand: residual-inner activation u
+//                   ACT0 [128,192)  16-bit A operand: stage input [p,v] / residual stream z   (2 values / column)
+//                   HCTX [192,208)  16-bit A operand: the agent's static context h (K-steps 8,9 of layer 1)
+//                   ACT1 [208,272)  16-bit A operand: residual-inner activation u
 //   registers     : the fp32 Runge-Kutta state of the thread's (agent, 32-dim slice): p0, v0 and two stage
 //                   combinations -- the ODE state never round-trips through HBM inside a step
 // Every layer is: 8 (or 10) tcgen05.mma issued by one thread with A read from TMEM and B from shared memory,
