@@ -401,6 +401,8 @@ def odeint(func, y0, t, *, rtol: float = 1e-7, atol: float = 1e-9, method: Optio
     _require_cuda(y0, "y0")
     t_host = _check_t(t)
     t = t.to(y0.device)
+    if y0.numel() == 0:      # empty batch (a rank with no agents): torchdiffeq returns the stacked, still empty, state
+        return y0.unsqueeze(0).repeat(t_host.numel(), *([1] * y0.dim()))
     precision = _lib.PRECISIONS[options.pop("precision", _DEFAULT_PRECISION["value"])]
 
     decreasing = t_host.numel() > 1 and bool(t_host[0] > t_host[1])

@@ -338,3 +338,21 @@ def test_adjoint_seam_equals_odeint_on_the_stage_path():
     assert torch.equal(res[0][0], res[1][0])
     for a, b in zip(res[0][1], res[1][1]):
         assert torch.allclose(a, b, rtol=1e-3, atol=1e-7)     # wgrad partials are summed by atomics: order may differ
+
+
+@pytest.mark.parametrize("method", ["rk4", "dopri5"])
+@pytest.mark.parametrize("B", [0, 1])
+def test_empty_and_single_agent_batches(method, B):
+    """Edge cases of the batch axis: an empty shard returns [T, 0, D]; one agent equals row 0 of a larger batch."""
+    import ananke_abm_b200 as ab
+    dev = _cuda()
+    torch.manual_seed(5)
+    m = ab.ModeSepModel(8, ab.ModeSepConfig()).to(dev)
+    t = torch.linspace(0.0, 1.0, 4, device=dev)
+    y_big = torch.randn(130, 160, device=dev) * 0.3
+    with torch.no_grad():
+        out = ab.odeint(m.odefunc, y_big[:B], t, method=method, rtol=1e-5, atol=1e-5)
+        assert out.shape == (4, B, 160)
+        if B == 1 and method == "rk4":
+            ref = ab.odeint(m.odefunc, y_big, t, method=method)
+            assert torch.equal(out[:, 0], ref[:, 0])
