@@ -75,6 +75,8 @@ int pv_combine_bwd(const ab200_drift_desc* d, const float* g, int n_a, float cpv
 int rows_transpose(const float* src, float* dst, int64_t B, int F, int mode, cudaStream_t st);
 
 size_t head_workspace_bytes(int Z);
+int head_ce_forward(const float* emb, const float* table, const int64_t* target, int64_t M, int Z, int E, float tau, float* lse,
+                    float* tgt_logit, int64_t* labels, void* ws, size_t ws_bytes, cudaStream_t st);
 int head_argmax(const float* emb, const float* table, int64_t M, int Z, int E, float tau, int64_t* labels, float* best, void* ws,
                 size_t ws_bytes, cudaStream_t st);
 
@@ -340,6 +342,15 @@ int ab200_head_argmax(const float* pred_emb, const float* class_table, int64_t M
                       float* best_logit, void* workspace, size_t workspace_bytes, ab200_stream_t stream) {
   if (!pred_emb || !class_table || !labels || !workspace || M <= 0 || Z <= 0 || !(tau > 0.0f)) return AB200_ERR_BAD_ARG;
   return head_argmax(pred_emb, class_table, M, Z, E, tau, labels, best_logit, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int ab200_head_ce_forward(const float* pred_emb, const float* class_table, const int64_t* target, int64_t M, int32_t Z, int32_t E,
+                          float tau, float* lse, float* target_logit, int64_t* labels, void* workspace, size_t workspace_bytes,
+                          void* stream) {
+  if (!pred_emb || !class_table || !target || !lse || !target_logit || !workspace || M <= 0 || Z <= 0 || !(tau > 0.0f))
+    return AB200_ERR_BAD_ARG;
+  return head_ce_forward(pred_emb, class_table, target, M, Z, E, tau, lse, target_logit, labels, workspace, workspace_bytes,
+                         (cudaStream_t)stream);
 }
 
 int ab200_gat_forward(const int32_t* rowptr, const int32_t* col, int32_t Z, int32_t nnz, const float* x, int32_t F_in,

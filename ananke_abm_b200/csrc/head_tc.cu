@@ -62,9 +62,13 @@ struct HeadArgs {
   int Z, nchunk;
   int ntiles;
   float inv_tau;
-  int64_t* labels;        // [M]
+  int64_t* labels;        // [M] or null
   float* best;            // [M] or null: the winning logit
   int* status;
+  // cross-entropy mode (all three set, or all null): lse[m] = log sum_z exp(logit[m,z]); tgt_logit[m] = logit[m, target[m]]
+  const int64_t* target;  // [M], values outside [0, Z) are read as zone 0 (the caller masks those rows)
+  float* lse;
+  float* tgt_logit;
 };
 
 __global__ void __launch_bounds__(HD_THREADS, 1) head_argmax_kernel(const __grid_constant__ HeadArgs a) {
@@ -172,6 +176,9 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_argmax_kernel(const __grid
       float b1 = -INFINITY, b2 = -INFINITY;
       int i1 = 0, i2 = 0;
       bool dead = false;
+      const bool ce = a.lse != nullptr;
+      const float sc2 = a.inv_tau * 1.4426950408889634f;     // logits in log2 units
+      float run_m = -INFINITY, run_s = 0.0f;                 // running max (cosine units) and sum of exp(logit - max)
       for (int c = 0; c < a.nchunk; ++c, ++nacc) {
         const int buf = nacc & 1;
         if (!mbar_wait(&acc_full[buf], (uint32_t)((nacc >> 1) & 1), HD_WAIT)) { *a.status = 7; dead = true; break; }
@@ -185,6 +192,14 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_argmax_kernel(const __grid
           float mx = -INFINITY;
 #pragma unroll
           for (int j = 0; j < 32; ++j) mx = fmaxf(mx, (zbase + c0 + j < a.Z) ? __uint_as_float(r[j]) : -INFINITY);
+          if (ce && mx > -INFINITY) {       // streaming log-sum-exp over the zones (split-bf16 logits: ~2^-16 relative)
+            if (mx > run_m) { run_s *= exp2f((run_m - mx) * sc2); run_m = mx; }
+            float part = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (zbase + c0 + j < a.Z) part += exp2f((__uint_as_float(r[j]) - run_m) * sc2);
+            run_s += part;
+          }
           if (mx > b2) {        // rare after the first chunks: only then look at the individual columns
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -215,8 +230,21 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_argmax_kernel(const __grid
           s2 = fmaf(e0, w.x, s2); s2 = fmaf(e1, w.y, s2); s2 = fmaf(e2, w.z, s2); s2 = fmaf(e3, w.w, s2);
         }
         const bool second = (a.Z > 1) && (s2 > s1 || (s2 == s1 && i2 < i1));
-        a.labels[m] = second ? i2 : i1;
+        if (a.labels != nullptr) a.labels[m] = second ? i2 : i1;
         if (a.best != nullptr) a.best[m] = (second ? s2 : s1) * a.inv_tau;
+        if (ce) {
+          int64_t tg = a.target[m];
+          if (tg < 0 || tg >= a.Z) tg = 0;
+          const float4* tt = reinterpret_cast<const float4*>(a.tn + (size_t)tg * HD_E);
+          float st = 0.0f;
+#pragma unroll
+          for (int j = 0; j < HD_E / 4; ++j) {
+            const float4 x = er[j], u = tt[j];
+            st = fmaf(x.x * inv, u.x, st); st = fmaf(x.y * inv, u.y, st); st = fmaf(x.z * inv, u.z, st); st = fmaf(x.w * inv, u.w, st);
+          }
+          a.lse[m] = run_m * a.inv_tau + logf(run_s);
+          a.tgt_logit[m] = st * a.inv_tau;
+        }
       }
     }
   }
@@ -232,8 +260,23 @@ size_t head_workspace_bytes(int Z) {
   return align_up(nc * HD_TN * HD_E * sizeof(float), 256) + nc * HD_B_BYTES + 256;
 }
 
+static int head_launch(const float* emb, const float* table, int64_t M, int Z, int E, float tau, int64_t* labels, float* best,
+                       const int64_t* target, float* lse, float* tgt_logit, void* ws, size_t ws_bytes, cudaStream_t st);
+
 int head_argmax(const float* emb, const float* table, int64_t M, int Z, int E, float tau, int64_t* labels, float* best, void* ws,
                 size_t ws_bytes, cudaStream_t st) {
+  return head_launch(emb, table, M, Z, E, tau, labels, best, nullptr, nullptr, nullptr, ws, ws_bytes, st);
+}
+
+// Cross-entropy forward without the [M, Z] logits: per row the log-sum-exp over all zones and the target's logit
+// (loss_row = lse - tgt_logit; masking / averaging is the caller's), optionally the argmax labels in the same pass.
+int head_ce_forward(const float* emb, const float* table, const int64_t* target, int64_t M, int Z, int E, float tau, float* lse,
+                    float* tgt_logit, int64_t* labels, void* ws, size_t ws_bytes, cudaStream_t st) {
+  return head_launch(emb, table, M, Z, E, tau, labels, nullptr, target, lse, tgt_logit, ws, ws_bytes, st);
+}
+
+static int head_launch(const float* emb, const float* table, int64_t M, int Z, int E, float tau, int64_t* labels, float* best,
+                       const int64_t* target, float* lse, float* tgt_logit, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (E != HD_E) return AB200_ERR_UNSUPPORTED;
   if (ws_bytes < head_workspace_bytes(Z)) return AB200_ERR_WORKSPACE;
   const int nc = head_chunks(Z);
@@ -245,7 +288,7 @@ int head_argmax(const float* emb, const float* table, int64_t M, int Z, int E, f
   head_pack_table_kernel<<<nc, 128, 0, st>>>(table, Z, tn, img);
   int rc = check_launch();
   if (rc) return rc;
-  HeadArgs k{emb, tn, img, M, Z, nc, (int)((M + HD_TM - 1) / HD_TM), 1.0f / tau, labels, best, status};
+  HeadArgs k{emb, tn, img, M, Z, nc, (int)((M + HD_TM - 1) / HD_TM), 1.0f / tau, labels, best, status, target, lse, tgt_logit};
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

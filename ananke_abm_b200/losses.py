@@ -1,0 +1,83 @@
+"""Fused classification losses of the mode_sep head.
+
+`ce_at_snaps` of the reference (mode_sep/architecture/losses.py:14-22) takes the `[B, T, Z]` logits, which cannot exist at
+configs[2] scale (3.9 TB).  `ce_at_snaps_fused` takes what the logits are made of -- `pred_emb [B, T, E]` and
+`class_table [Z, E]` (mode_sep/architecture/model.py:196-199: cosine similarity / tau) -- and returns the same scalar:
+the forward streams the zone table through the tensor cores (`ab200_head_ce_forward`: per-row log-sum-exp + target logit,
+no logits in HBM); the backward recomputes the probabilities chunk by chunk.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+
+
+class _HeadCE(torch.autograd.Function):
+    """per-row cross entropy of cos(emb, table) / tau against `target`; rows are independent."""
+
+    @staticmethod
+    def forward(ctx, emb, table, target, tau: float, row_chunk: int):
+        L = _lib.lib()
+        if not emb.is_cuda:
+            raise _lib.Ab200Error("pred_emb must be a CUDA tensor: ananke_abm_b200 has no CPU path")
+        M, E = emb.shape
+        Z = table.shape[0]
+        embc, tablec = emb.detach().contiguous().float(), table.detach().contiguous().float()
+        tgt = target.contiguous().to(torch.int64)
+        nbytes = L.ab200_head_workspace_bytes(Z, E)
+        if nbytes == 0:
+            raise _lib.Ab200Error("fused head is instantiated for emb_dim = 64")
+        ws = torch.empty(int(nbytes), dtype=torch.uint8, device=emb.device)
+        lse = torch.empty(M, dtype=torch.float32, device=emb.device)
+        tl = torch.empty(M, dtype=torch.float32, device=emb.device)
+        rc = L.ab200_head_ce_forward(embc.data_ptr(), tablec.data_ptr(), tgt.data_ptr(), M, Z, E, float(tau), lse.data_ptr(),
+                                     tl.data_ptr(), None, ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "ab200_head_ce_forward")
+        ctx.save_for_backward(embc, tablec, tgt, lse)
+        ctx.tau, ctx.row_chunk = float(tau), int(row_chunk)
+        return lse - tl
+
+    @staticmethod
+    def backward(ctx, g_rows):
+        # d loss_m / d logit_mz = softmax_mz - [z = y_m]; probabilities are recomputed from the saved log-sum-exp, one
+        # block of rows at a time (library GEMMs; the tensor-core backward of this head is the next step)
+        emb, table, tgt, lse = ctx.saved_tensors
+        tau = ctx.tau
+        en = emb.norm(dim=-1, keepdim=True) + 1e-8
+        tn = table.norm(dim=-1, keepdim=True) + 1e-8
+        eh, th = emb / en, table / tn
+        g_eh = torch.empty_like(eh)
+        g_th = torch.zeros_like(th)
+        for s in range(0, emb.shape[0], ctx.row_chunk):
+            sl = slice(s, s + ctx.row_chunk)
+            p = torch.exp(eh[sl] @ th.T / tau - lse[sl, None])
+            p.scatter_add_(1, tgt[sl].clamp(0, table.shape[0] - 1)[:, None], -torch.ones_like(p[:, :1]))
+            p.mul_(g_rows[sl, None] / tau)
+            g_eh[sl] = p @ th
+            g_th.addmm_(p.T, eh[sl])
+        # through x / (|x| + 1e-8)
+        # y = x / (n + eps), n = |x|:  g_x = g_y / (n + eps) - y (g_y . y) / n
+        g_emb = g_eh / en - eh * ((g_eh * eh).sum(-1, keepdim=True) / (en - 1e-8).clamp_min(1e-30))
+        g_table = g_th / tn - th * ((g_th * th).sum(-1, keepdim=True) / (tn - 1e-8).clamp_min(1e-30))
+        return g_emb, g_table, None, None, None
+
+
+def head_ce_rows(pred_emb: torch.Tensor, class_table: torch.Tensor, target: torch.Tensor, tau: float = 0.2,
+                 row_chunk: int = 32_768) -> torch.Tensor:
+    """Per-row cross entropy `-log softmax(cos(pred_emb, class_table) / tau)[target]` for `pred_emb [..., E]`,
+    `target [...]`; rows whose target is outside [0, Z) are scored against zone 0 (mask them)."""
+    lead = pred_emb.shape[:-1]
+    rows = _HeadCE.apply(pred_emb.reshape(-1, pred_emb.shape[-1]), class_table, target.reshape(-1), tau, row_chunk)
+    return rows.view(lead)
+
+
+def ce_at_snaps_fused(pred_emb: torch.Tensor, class_table: torch.Tensor, y_union: torch.Tensor, is_gt_mask: torch.Tensor,
+                      tau: float = 0.2) -> torch.Tensor:
+    """`ce_at_snaps(model.head(...)[1], y_union, is_gt_mask)` of the reference (losses.py:14-22) from the head's inputs:
+    mean cross entropy over the (agent, time) pairs where `is_gt_mask` is set; 0 when the mask is empty."""
+    mask = is_gt_mask
+    if int(mask.sum()) == 0:
+        return torch.tensor(0.0, dtype=pred_emb.dtype, device=pred_emb.device)
+    rows = head_ce_rows(pred_emb[mask], class_table, y_union[mask], tau)
+    return rows.mean()

@@ -244,6 +244,15 @@ size_t ab200_head_workspace_bytes(int32_t Z, int32_t E);
 int ab200_head_argmax(const float* pred_emb, const float* class_table, int64_t M, int32_t Z, int32_t E, float tau,
                       int64_t* labels, float* best_logit, void* workspace, size_t workspace_bytes, ab200_stream_t stream);
 
+/* Cross-entropy forward of the same head -- F.cross_entropy(logits[mask], y[mask]) of `ce_at_snaps`
+ * (mode_sep/architecture/losses.py:14-22) without the [M, Z] logits: per row lse[m] = log sum_z exp(logit[m, z]) (streamed
+ * over the zones on the tensor cores, split-bf16 operands) and target_logit[m] = logit[m, target[m]] (fp32 re-score);
+ * row loss = lse - target_logit, masking and the mean are the caller's.  target values outside [0, Z) are read as zone 0.
+ * labels may be NULL; when given it receives the argmax of ab200_head_argmax from the same pass. */
+int ab200_head_ce_forward(const float* pred_emb, const float* class_table, const int64_t* target, int64_t M, int32_t Z,
+                          int32_t E, float tau, float* lse, float* target_logit, int64_t* labels, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
 /* ---- graph attention over the zone graph (the `gnn_embed` slot) ------------------------------------
  * No reference implementation exists (README.md:5,57,80 promise it; pyproject.toml:25 declares torch-geometric
  * 2.6.1, never imported): semantics are PyG `GATConv` -- x'_i = ||_h sum_{j in N(i)+i}

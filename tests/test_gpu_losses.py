@@ -1,0 +1,78 @@
+"""Fused cross-entropy head against the reference formula: cosine logits / tau
+(mode_sep/architecture/model.py:196-199) into `ce_at_snaps` (mode_sep/architecture/losses.py:14-22)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+def _ref_logits(emb, table, tau):
+    tn = table / (table.norm(dim=-1, keepdim=True) + 1e-8)
+    en = emb / (emb.norm(dim=-1, keepdim=True) + 1e-8)
+    return en @ tn.T / tau
+
+
+@pytest.mark.parametrize("M,Z", [(1, 8), (130, 8), (777, 500), (4096, 10_000), (300, 129)])
+def test_head_ce_rows_match_float64_reference(M, Z):
+    import ananke_abm_b200 as ab
+    dev = _cuda()
+    g = torch.Generator().manual_seed(M + Z)
+    emb = torch.randn(M, 64, generator=g).to(dev)
+    table = torch.randn(Z, 64, generator=g).to(dev)
+    tgt = torch.randint(0, Z, (M,), generator=g).to(dev)
+    rows = ab.head_ce_rows(emb, table, tgt, 0.2)
+    ref = F.cross_entropy(_ref_logits(emb.double(), table.double(), 0.2), tgt, reduction="none")
+    err = float((rows.double() - ref).abs().max() / ref.abs().max())
+    assert err < 1e-5, err
+
+
+def test_ce_at_snaps_fused_value_and_gradients_match_reference_formula():
+    import ananke_abm_b200 as ab
+    dev = _cuda()
+    g = torch.Generator().manual_seed(11)
+    B, T, Z = 37, 9, 500
+    emb = torch.randn(B, T, 64, generator=g).to(dev).requires_grad_(True)
+    table = torch.randn(Z, 64, generator=g).to(dev).requires_grad_(True)
+    y = torch.randint(0, Z, (B, T), generator=g).to(dev)
+    mask = (torch.rand(B, T, generator=g) < 0.3).to(dev)
+    y = torch.where(mask, y, torch.full_like(y, -1))          # -1 where not ground truth, as UnionBatch has it
+    loss = ab.ce_at_snaps_fused(emb, table, y, mask, 0.2)
+    loss.backward()
+    e2, t2 = emb.detach().double().requires_grad_(True), table.detach().double().requires_grad_(True)
+    logits = _ref_logits(e2, t2, 0.2)
+    ref = F.cross_entropy(logits[mask], y[mask], reduction="mean")
+    ref.backward()
+    assert abs(float(loss) - float(ref)) < 1e-5 * abs(float(ref))
+    for a, b in ((emb.grad, e2.grad), (table.grad, t2.grad)):
+        assert float((a.double() - b).abs().max()) < 2e-5 * float(b.abs().max())
+    # empty mask -> 0, like the reference
+    assert float(ab.ce_at_snaps_fused(emb.detach(), table.detach(), y, torch.zeros_like(mask), 0.2)) == 0.0
+
+
+def test_head_ce_labels_equal_head_argmax():
+    """The cross-entropy pass can hand back the argmax labels of the same sweep (C ABI)."""
+    import ctypes as C  # noqa: F401
+    from ananke_abm_b200 import _lib
+    from ananke_abm_b200.inference import head_argmax
+    dev = _cuda()
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(2)
+    M, Z = 1000, 700
+    emb, table = torch.randn(M, 64, generator=g).to(dev), torch.randn(Z, 64, generator=g).to(dev)
+    tgt = torch.randint(0, Z, (M,), generator=g).to(dev)
+    ws = torch.empty(int(L.ab200_head_workspace_bytes(Z, 64)), dtype=torch.uint8, device=dev)
+    lse, tl = torch.empty(M, device=dev), torch.empty(M, device=dev)
+    labels = torch.empty(M, dtype=torch.int64, device=dev)
+    rc = L.ab200_head_ce_forward(emb.data_ptr(), table.data_ptr(), tgt.data_ptr(), M, Z, 64, 0.2, lse.data_ptr(), tl.data_ptr(),
+                                 labels.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, "ab200_head_ce_forward")
+    assert torch.equal(labels, head_argmax(emb, table, 0.2))
+    logits = _ref_logits(emb.double(), table.double(), 0.2)
+    assert float((tl.double() - logits.gather(1, tgt[:, None])[:, 0]).abs().max()) < 1e-5
