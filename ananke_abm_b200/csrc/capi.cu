@@ -75,6 +75,10 @@ int pv_combine_bwd(const ab200_drift_desc* d, const float* g, int n_a, float cpv
 int rows_transpose(const float* src, float* dst, int64_t B, int F, int mode, cudaStream_t st);
 
 size_t head_workspace_bytes(int Z);
+size_t head_ce_backward_workspace_bytes(int64_t M, int Z);
+int head_ce_backward(const float* emb, const float* table, const int64_t* target, const float* lse, const float* g_rows, int64_t M,
+                     int Z, int E, float tau, float* d_emb_n, float* d_table_n, void* ws, size_t ws_bytes, cudaStream_t st);
+int head_ce_backward_status(const void* ws, int64_t M, int Z, int* host_out, cudaStream_t st);
 int head_ce_forward(const float* emb, const float* table, const int64_t* target, int64_t M, int Z, int E, float tau, float* lse,
                     float* tgt_logit, int64_t* labels, void* ws, size_t ws_bytes, cudaStream_t st);
 int head_argmax(const float* emb, const float* table, int64_t M, int Z, int E, float tau, int64_t* labels, float* best, void* ws,
@@ -352,6 +356,26 @@ int ab200_head_ce_forward(const float* pred_emb, const float* class_table, const
   return head_ce_forward(pred_emb, class_table, target, M, Z, E, tau, lse, target_logit, labels, workspace, workspace_bytes,
                          (cudaStream_t)stream);
 }
+
+size_t ab200_head_ce_backward_workspace_bytes(int64_t M, int32_t Z, int32_t E) {
+  return (M > 0 && Z > 0 && E == 64) ? head_ce_backward_workspace_bytes(M, Z) : 0;
+}
+
+int ab200_head_ce_backward(const float* pred_emb, const float* class_table, const int64_t* target, const float* lse,
+                           const float* grad_rows, int64_t M, int32_t Z, int32_t E, float tau, float* grad_emb_normalised,
+                           float* grad_table_normalised, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!pred_emb || !class_table || !target || !lse || !grad_rows || !grad_emb_normalised || !grad_table_normalised || !workspace ||
+      M <= 0 || Z <= 0 || !(tau > 0.0f))
+    return AB200_ERR_BAD_ARG;
+  return head_ce_backward(pred_emb, class_table, target, lse, grad_rows, M, Z, E, tau, grad_emb_normalised, grad_table_normalised,
+                          workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int ab200_head_ce_backward_status(const void* workspace, int64_t M, int32_t Z, int32_t* status_host, void* stream) {
+  if (!workspace || !status_host || M <= 0 || Z <= 0) return AB200_ERR_BAD_ARG;
+  return head_ce_backward_status(workspace, M, Z, status_host, (cudaStream_t)stream);
+}
+
 
 int ab200_gat_forward(const int32_t* rowptr, const int32_t* col, int32_t Z, int32_t nnz, const float* x, int32_t F_in,
                       const float* W, const float* att_src, const float* att_dst, const float* bias, int32_t heads, int32_t F_out,

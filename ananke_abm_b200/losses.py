@@ -4,9 +4,12 @@
 configs[2] scale (3.9 TB).  `ce_at_snaps_fused` takes what the logits are made of -- `pred_emb [B, T, E]` and
 `class_table [Z, E]` (mode_sep/architecture/model.py:196-199: cosine similarity / tau) -- and returns the same scalar:
 the forward streams the zone table through the tensor cores (`ab200_head_ce_forward`: per-row log-sum-exp + target logit,
-no logits in HBM); the backward recomputes the probabilities chunk by chunk.
+no logits in HBM); the backward (`ab200_head_ce_backward`) recomputes the probabilities tile by tile on the tensor
+cores and consumes them on chip.
 """
 from __future__ import annotations
+
+import ctypes as C
 
 import torch
 
@@ -40,26 +43,29 @@ class _HeadCE(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_rows):
-        # d loss_m / d logit_mz = softmax_mz - [z = y_m]; probabilities are recomputed from the saved log-sum-exp, one
-        # block of rows at a time (library GEMMs; the tensor-core backward of this head is the next step)
+        # d loss_m / d logit_mz = softmax_mz - [z = y_m]: recomputed tile by tile on the tensor cores from the saved
+        # log-sum-exp (`ab200_head_ce_backward`: rows-outer pass -> d emb^, zones-outer pass -> d table^, no atomics)
+        L = _lib.lib()
         emb, table, tgt, lse = ctx.saved_tensors
-        tau = ctx.tau
-        en = emb.norm(dim=-1, keepdim=True) + 1e-8
-        tn = table.norm(dim=-1, keepdim=True) + 1e-8
-        eh, th = emb / en, table / tn
-        g_eh = torch.empty_like(eh)
-        g_th = torch.zeros_like(th)
-        for s in range(0, emb.shape[0], ctx.row_chunk):
-            sl = slice(s, s + ctx.row_chunk)
-            p = torch.exp(eh[sl] @ th.T / tau - lse[sl, None])
-            p.scatter_add_(1, tgt[sl].clamp(0, table.shape[0] - 1)[:, None], -torch.ones_like(p[:, :1]))
-            p.mul_(g_rows[sl, None] / tau)
-            g_eh[sl] = p @ th
-            g_th.addmm_(p.T, eh[sl])
-        # through x / (|x| + 1e-8)
-        # y = x / (n + eps), n = |x|:  g_x = g_y / (n + eps) - y (g_y . y) / n
-        g_emb = g_eh / en - eh * ((g_eh * eh).sum(-1, keepdim=True) / (en - 1e-8).clamp_min(1e-30))
-        g_table = g_th / tn - th * ((g_th * th).sum(-1, keepdim=True) / (tn - 1e-8).clamp_min(1e-30))
+        M, E = emb.shape
+        Z = table.shape[0]
+        g = g_rows.contiguous().float()
+        g_eh = torch.empty_like(emb)
+        g_th = torch.empty_like(table)
+        ws = torch.empty(int(L.ab200_head_ce_backward_workspace_bytes(M, Z, E)), dtype=torch.uint8, device=emb.device)
+        stream = torch.cuda.current_stream().cuda_stream
+        rc = L.ab200_head_ce_backward(emb.data_ptr(), table.data_ptr(), tgt.data_ptr(), lse.data_ptr(), g.data_ptr(), M, Z, E, ctx.tau,
+                                      g_eh.data_ptr(), g_th.data_ptr(), ws.data_ptr(), ws.numel(), stream)
+        _lib.check(rc, "ab200_head_ce_backward")
+        st = C.c_int32(0)
+        _lib.check(L.ab200_head_ce_backward_status(ws.data_ptr(), M, Z, C.byref(st), stream), "ab200_head_ce_backward_status")
+        if st.value:
+            raise _lib.Ab200Error(f"head cross-entropy backward: barrier timeout (status {st.value})")
+        # through y = x / (n + eps), n = |x|:  g_x = g_y / (n + eps) - y (g_y . y) / n
+        n_e, n_t = emb.norm(dim=-1, keepdim=True), table.norm(dim=-1, keepdim=True)
+        eh, th = emb / (n_e + 1e-8), table / (n_t + 1e-8)
+        g_emb = g_eh / (n_e + 1e-8) - eh * ((g_eh * eh).sum(-1, keepdim=True) / n_e.clamp_min(1e-30))
+        g_table = g_th / (n_t + 1e-8) - th * ((g_th * th).sum(-1, keepdim=True) / n_t.clamp_min(1e-30))
         return g_emb, g_table, None, None, None
 
 

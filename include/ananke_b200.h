@@ -253,6 +253,18 @@ int ab200_head_ce_forward(const float* pred_emb, const float* class_table, const
                           int32_t E, float tau, float* lse, float* target_logit, int64_t* labels, void* workspace,
                           size_t workspace_bytes, void* stream);
 
+/* Backward of the cross-entropy head on tensor cores: with dlogit[m,z] = grad_rows[m] (softmax[m,z] - [z = target[m]])
+ * recomputed tile by tile from `lse` (never stored), writes the gradients w.r.t. the NORMALISED vectors
+ *   grad_emb_normalised[m,:] = (1/tau) sum_z dlogit[m,z] table^[z,:]      grad_table_normalised[z,:] = (1/tau) sum_m dlogit[m,z] emb^[m,:]
+ * (autograd through the reference's einsum + F.cross_entropy, model.py:196-199 / losses.py:14-22); the caller applies
+ * the Jacobian of x / (|x| + 1e-8).  Deterministic (no atomics).  ab200_head_ce_backward_status copies the kernels'
+ * barrier-timeout word to the host (synchronises the stream; 0 = clean). */
+size_t ab200_head_ce_backward_workspace_bytes(int64_t M, int32_t Z, int32_t E);
+int ab200_head_ce_backward(const float* pred_emb, const float* class_table, const int64_t* target, const float* lse,
+                           const float* grad_rows, int64_t M, int32_t Z, int32_t E, float tau, float* grad_emb_normalised,
+                           float* grad_table_normalised, void* workspace, size_t workspace_bytes, void* stream);
+int ab200_head_ce_backward_status(const void* workspace, int64_t M, int32_t Z, int32_t* status_host, void* stream);
+
 /* ---- graph attention over the zone graph (the `gnn_embed` slot) ------------------------------------
  * No reference implementation exists (README.md:5,57,80 promise it; pyproject.toml:25 declares torch-geometric
  * 2.6.1, never imported): semantics are PyG `GATConv` -- x'_i = ||_h sum_{j in N(i)+i}
