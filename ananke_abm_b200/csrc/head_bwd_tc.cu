@@ -11,7 +11,10 @@
 //   dX[x,:] += dS[x,:] Y^[:, :]            tcgen05 TS, B = the MN-major view of the same Y image (N = 64, K = 128 y)
 // rows-outer pass (X = pred_emb rows, Y = zones) gives d e^; zones-outer pass (X = zones, Y = rows) gives d t^.  Every
 // X tile is owned by one CTA: plain stores, no atomics, deterministic.
-//   warp 0 : TMA producer (X tile, Y ring of 3)     warp 1 : MMA issuer     warps 2-5 : epilogue, thread = x row
+//   warp 0 : TMA producer (X tile, Y ring of 3)     warp 1 : MMA issuer
+//   warps 2-9 : epilogue, thread = (x row, half of the chunk's 128 columns)
+// Work item = (X tile, range of Y chunks): when there are few X tiles (zones-outer: Z / 128 = 79 at configs[2]) the Y
+// stream is split so that every SM has work; the partial dX of the splits are added in a fixed order afterwards.
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -23,7 +26,7 @@ constexpr uint32_t HB_IMG = HB_T * HB_K * 2;                // 49,152 B per 128-
 constexpr uint32_t HB_SEG = HB_T * HB_E * 2;                // 16,384 B per K segment
 constexpr int HB_NS = 3;
 constexpr uint32_t HB_SMEM = (1 + HB_NS) * HB_IMG;
-constexpr int HB_THREADS = 192;
+constexpr int HB_THREADS = 320, HB_EPI = 256;
 constexpr uint32_t HB_LBO = 128u * 16u, HB_SBO = 128u;
 constexpr uint32_t HB_C_S = 0, HB_C_DSH = 256, HB_C_DSL = 320, HB_C_DX = 384;
 constexpr long long HB_WAIT = 400000000LL;
@@ -66,9 +69,23 @@ struct HeadBwdArgs {
   const float* g;           // per ROW upstream gradient
   const int64_t* target;    // per ROW
   float inv_tau;
-  float* dx;                // [NX][64]
+  float* dx;                // [NX][64]                       (nsplit == 1)
+  float* partial;           // [nsplit][nx * 128][64]         (nsplit > 1)
+  int nsplit;               // Y chunks are divided into nsplit contiguous ranges; work item = tile * nsplit + split
   int* status;
 };
+
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void hb_item(const HeadBwdArgs& a, int item, int& tile, int& c_begin, int& c_end, int& split) {
+  tile = item / a.nsplit;
+  split = item - tile * a.nsplit;
+  c_begin = (int)(((int64_t)split * a.ny) / a.nsplit);
+  c_end = (int)(((int64_t)(split + 1) * a.ny) / a.nsplit);
+}
 
 __global__ void __launch_bounds__(HB_THREADS, 1) head_ce_bwd_kernel(const __grid_constant__ HeadBwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -83,29 +100,30 @@ __global__ void __launch_bounds__(HB_THREADS, 1) head_ce_bwd_kernel(const __grid
   if (warp == 0) tmem_alloc<512>(&tmem_base_s);
   if (tid == 0) {
     for (int i = 0; i < HB_NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], HB_EPI); }
     mbar_init(&x_full, 1); mbar_init(&x_free, 1);
-    mbar_init(&ds_full, 128); mbar_init(&ds_free, 1);
-    mbar_init(&dx_full, 1); mbar_init(&dx_empty, 128);
+    mbar_init(&ds_full, HB_EPI); mbar_init(&ds_free, 1);
+    mbar_init(&dx_full, 1); mbar_init(&dx_empty, HB_EPI);
     mbar_fence_init();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
-  const int my_tiles = (a.nx > (int)blockIdx.x) ? (a.nx - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-  const int ny = a.ny;
+  const int n_items = a.nx * a.nsplit;
+  const int my_tiles = (n_items > (int)blockIdx.x) ? (n_items - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;     // work items of this CTA
 
   if (warp == 0) {
     if (lane == 0) {
       int it = 0;
       bool ok = true;
       for (int t = 0; t < my_tiles && ok; ++t) {
-        const int tile = blockIdx.x + t * gridDim.x;
+        int tile, c_begin, c_end, split;
+        hb_item(a, blockIdx.x + t * gridDim.x, tile, c_begin, c_end, split);
         if (t > 0 && !mbar_wait(&x_free, (uint32_t)((t - 1) & 1), HB_WAIT)) { *a.status = 1; break; }
         mbar_arrive_expect_tx(&x_full, HB_IMG);
         bulk_g2s(sX, a.ximg + (size_t)tile * HB_IMG, HB_IMG, &x_full);
-        for (int c = 0; c < ny; ++c, ++it) {
+        for (int c = c_begin; c < c_end; ++c, ++it) {
           const int slot = it % HB_NS;
           if (!mbar_wait(&empty[slot], (uint32_t)(((it / HB_NS) & 1) ^ 1), HB_WAIT)) { *a.status = 2; ok = false; break; }
           mbar_arrive_expect_tx(&full[slot], HB_IMG);
@@ -135,6 +153,9 @@ __global__ void __launch_bounds__(HB_THREADS, 1) head_ce_bwd_kernel(const __grid
         return true;
       };
       for (int t = 0; t < my_tiles && ok; ++t) {
+        int tile, c_begin, c_end, split;
+        hb_item(a, blockIdx.x + t * gridDim.x, tile, c_begin, c_end, split);
+        const int ny = c_end - c_begin;
         if (!mbar_wait(&x_full, (uint32_t)(t & 1), HB_WAIT)) { *a.status = 3; break; }
         tc_fence_after();
         if (!issue_s(nseq)) break;
@@ -165,39 +186,47 @@ __global__ void __launch_bounds__(HB_THREADS, 1) head_ce_bwd_kernel(const __grid
       }
     }
   } else {
-    const int q = warp & 3;
+    const int q = warp & 3;                           // TMEM lane quarter this warp may touch
+    const int hh = (warp - 2) >> 2;                   // which 64 of the chunk's 128 columns
     const int row = q * 32 + lane;                    // x row inside the tile = TMEM lane
-    const int et = (warp - 2) * 32 + lane;            // 0..127: which per-y entry this thread stages
+    const int et = tid - 64;                          // 0..255; the first 128 stage the per-y entries
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
     const float sc2 = a.inv_tau * 1.4426950408889634f;
     int nseq = 0;
     bool dead = false;
     for (int t = 0; t < my_tiles && !dead; ++t) {
-      const int tile = blockIdx.x + t * gridDim.x;
+      int tile, c_begin, c_end, split;
+      hb_item(a, blockIdx.x + t * gridDim.x, tile, c_begin, c_end, split);
       const int64_t xg = (int64_t)tile * HB_T + row;
       const bool xvalid = xg < a.NX;
       float x_lse2 = 0.0f, x_g = 0.0f;
-      int64_t x_tgt = -1;
-      if (a.rows_outer && xvalid) { x_lse2 = a.lse[xg] * 1.4426950408889634f; x_g = a.g[xg] * a.inv_tau; x_tgt = a.target[xg]; }
-      for (int c = 0; c < ny; ++c, ++nseq) {
+      int x_tgt = -1;
+      if (a.rows_outer && xvalid) { x_lse2 = a.lse[xg] * 1.4426950408889634f; x_g = a.g[xg] * a.inv_tau; x_tgt = (int)a.target[xg]; }
+      const int xi = (int)xg;                         // zones-outer: the zone index of this row (Z < 2^31)
+      for (int c = c_begin; c < c_end; ++c, ++nseq) {
         const int buf = nseq & 1;
         const int64_t ybase = (int64_t)c * HB_T;
         if (!a.rows_outer) {          // per-row quantities of this Y chunk -> shared memory (read by every x thread)
-          const int64_t yr = ybase + et;
-          const bool yv = yr < a.NY;
-          y_lse2[buf][et] = yv ? a.lse[yr] * 1.4426950408889634f : 0.0f;
-          y_g[buf][et] = yv ? a.g[yr] * a.inv_tau : 0.0f;
-          y_tgt[buf][et] = yv ? (int)a.target[yr] : -1;
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (et < HB_T) {
+            const int64_t yr = ybase + et;
+            const bool yv = yr < a.NY;
+            y_lse2[buf][et] = yv ? a.lse[yr] * 1.4426950408889634f : 0.0f;
+            y_g[buf][et] = yv ? a.g[yr] * a.inv_tau : 0.0f;            // 0 on padding rows: their dS vanishes
+            y_tgt[buf][et] = yv ? (int)a.target[yr] : -1;
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
         }
         if (!mbar_wait(&acc_full[buf], (uint32_t)((nseq >> 1) & 1), HB_WAIT)) { *a.status = 8; dead = true; break; }
         if (nseq > 0 && !mbar_wait(&ds_free, (uint32_t)((nseq - 1) & 1), HB_WAIT)) { *a.status = 9; dead = true; break; }
         tc_fence_after();
+        const int n_valid = (int)min((int64_t)HB_T, a.NY - ybase);     // columns of this chunk that are real y rows
 #pragma unroll 1
-        for (int c0 = 0; c0 < HB_T; c0 += 32) {
+        for (int c0 = hh * 64; c0 < hh * 64 + 64; c0 += 32) {
           uint32_t r[32], hi[16], lo[16];
           tmem_ld32(tmem + lane_sel + HB_C_S + (uint32_t)(buf * HB_T + c0), r);
           tmem_ld_wait();
+          const int t_loc = a.rows_outer ? x_tgt - (int)ybase - c0 : 0;          // column of the target inside this group
+          const int lim = n_valid - c0;                                          // columns < lim are valid
 #pragma unroll
           for (int jj = 0; jj < 16; ++jj) {
             float d[2];
@@ -207,12 +236,12 @@ __global__ void __launch_bounds__(HB_THREADS, 1) head_ce_bwd_kernel(const __grid
               const float L = __uint_as_float(r[j]);
               float v;
               if (a.rows_outer) {
-                const int64_t z = ybase + c0 + j;
-                const float p = exp2f(L * sc2 - x_lse2);
-                v = (z < a.NY) ? x_g * (p - (z == x_tgt ? 1.0f : 0.0f)) : 0.0f;
+                const float p = ex2_fast(fmaf(L, sc2, -x_lse2));
+                v = x_g * (p - (j == t_loc ? 1.0f : 0.0f));
+                v = j < lim ? v : 0.0f;
               } else {
-                const float p = exp2f(L * sc2 - y_lse2[buf][c0 + j]);
-                v = y_g[buf][c0 + j] * (p - ((int64_t)y_tgt[buf][c0 + j] == xg ? 1.0f : 0.0f));     // y_g = 0 on padding rows
+                const float p = ex2_fast(fmaf(L, sc2, -y_lse2[buf][c0 + j]));
+                v = y_g[buf][c0 + j] * (p - (y_tgt[buf][c0 + j] == xi ? 1.0f : 0.0f));
               }
               d[u] = v;
             }
@@ -231,13 +260,13 @@ __global__ void __launch_bounds__(HB_THREADS, 1) head_ce_bwd_kernel(const __grid
       if (dead) break;
       if (!mbar_wait(&dx_full, (uint32_t)(t & 1), HB_WAIT)) { *a.status = 10; break; }
       tc_fence_after();
-#pragma unroll
-      for (int c0 = 0; c0 < HB_E; c0 += 32) {
+      {
         uint32_t r[32];
-        tmem_ld32(tmem + lane_sel + HB_C_DX + (uint32_t)c0, r);
+        tmem_ld32(tmem + lane_sel + HB_C_DX + (uint32_t)(hh * 32), r);
         tmem_ld_wait();
-        if (xvalid) {
-          float4* o = reinterpret_cast<float4*>(a.dx + xg * HB_E + c0);
+        float* base = a.nsplit > 1 ? a.partial + ((size_t)split * a.nx * HB_T + (size_t)xg) * HB_E : a.dx + (size_t)xg * HB_E;
+        if (xvalid || a.nsplit > 1) {      // the partial buffer is padded to whole tiles
+          float4* o = reinterpret_cast<float4*>(base + hh * 32);
 #pragma unroll
           for (int j = 0; j < 8; ++j)
             o[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
@@ -252,11 +281,35 @@ __global__ void __launch_bounds__(HB_THREADS, 1) head_ce_bwd_kernel(const __grid
   if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
+// dx[x][f] = sum over splits (fixed order) of partial[split][x][f]
+__global__ void head_reduce_splits_kernel(const float* __restrict__ partial, int nsplit, int64_t rows_padded, int64_t n_rows,
+                                          float* __restrict__ dx) {
+  const int64_t n = n_rows * HB_E;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float s = 0.0f;
+    for (int k = 0; k < nsplit; ++k) s += partial[(size_t)k * rows_padded * HB_E + i];
+    dx[i] = s;
+  }
+}
+
 // ---- host side --------------------------------------------------------------------------------------------------
 static int hb_tiles(int64_t n) { return (int)((n + HB_T - 1) / HB_T); }
+static int hb_nsplit(int nx, int ny, int sms) {       // enough work items for every SM when there are few X tiles
+  if (nx >= 4 * sms) return 1;
+  int want = (8 * sms + nx - 1) / nx;
+  if (want > ny) want = ny;
+  return want < 1 ? 1 : want;
+}
+constexpr int HB_SMS_ASSUMED = 160;                   // workspace sizing only (an upper bound on the split count)
+static size_t hb_partial_bytes(int64_t NX, int64_t NY) {
+  const int nx = hb_tiles(NX), ny = hb_tiles(NY);
+  const int ns = hb_nsplit(nx, ny, HB_SMS_ASSUMED);
+  return ns > 1 ? (size_t)ns * nx * HB_T * HB_E * sizeof(float) : 0;
+}
 
 size_t head_ce_backward_workspace_bytes(int64_t M, int Z) {
-  return (size_t)hb_tiles(M) * HB_IMG + (size_t)hb_tiles(Z) * HB_IMG + 256;
+  const size_t part = hb_partial_bytes(M, Z) > hb_partial_bytes(Z, M) ? hb_partial_bytes(M, Z) : hb_partial_bytes(Z, M);
+  return (size_t)hb_tiles(M) * HB_IMG + (size_t)hb_tiles(Z) * HB_IMG + 256 + part;
 }
 
 // d emb^ [M][64] and d table^ [Z][64] (gradients w.r.t. the NORMALISED vectors; the caller applies x / (|x| + 1e-8)).
@@ -279,14 +332,22 @@ int head_ce_backward(const float* emb, const float* table, const int64_t* target
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   e = cudaFuncSetAttribute(head_ce_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HB_SMEM);
   if (e != cudaSuccess) { set_cuda_error(e); return AB200_ERR_CUDA; }
-  // rows outer: x = rows (d emb^), y = zones
-  HeadBwdArgs k1{eimg, timg, nm, nz, M, (int64_t)Z, 1, 1, lse, g_rows, target, 1.0f / tau, d_emb_n, status};
-  head_ce_bwd_kernel<<<nm < sms ? nm : sms, HB_THREADS, HB_SMEM, st>>>(k1);
-  if ((rc = check_launch())) return rc;
-  // zones outer: x = zones (d table^), y = rows
-  HeadBwdArgs k2{timg, eimg, nz, nm, (int64_t)Z, M, 0, 2, lse, g_rows, target, 1.0f / tau, d_table_n, status};
-  head_ce_bwd_kernel<<<nz < sms ? nz : sms, HB_THREADS, HB_SMEM, st>>>(k2);
-  return check_launch();
+  float* partial = (float*)((uint8_t*)status + 256);
+  auto pass = [&](const uint8_t* ximg, const uint8_t* yimg, int nx, int ny, int64_t NX, int64_t NY, int rows_outer, int y_lo_seg,
+                  float* dx) -> int {
+    int ns = hb_nsplit(nx, ny, sms);
+    const int ns_cap = hb_nsplit(nx, ny, HB_SMS_ASSUMED);
+    if (ns > ns_cap) ns = ns_cap;                      // never beyond what the workspace was sized for
+    HeadBwdArgs k{ximg, yimg, nx, ny, NX, NY, rows_outer, y_lo_seg, lse, g_rows, target, 1.0f / tau, dx, partial, ns, status};
+    const int items = nx * ns;
+    head_ce_bwd_kernel<<<items < sms ? items : sms, HB_THREADS, HB_SMEM, st>>>(k);
+    int r = check_launch();
+    if (r || ns == 1) return r;
+    head_reduce_splits_kernel<<<sms * 4, 256, 0, st>>>(partial, ns, (int64_t)nx * HB_T, NX, dx);
+    return check_launch();
+  };
+  if ((rc = pass(eimg, timg, nm, nz, M, (int64_t)Z, 1, 1, d_emb_n))) return rc;      // rows outer: x = rows (d emb^), y = zones
+  return pass(timg, eimg, nz, nm, (int64_t)Z, M, 0, 2, d_table_n);                   // zones outer: x = zones (d table^), y = rows
 }
 
 int head_ce_backward_status(const void* ws, int64_t M, int Z, int* host_out, cudaStream_t st) {
