@@ -217,7 +217,6 @@ __global__ void __launch_bounds__(HB_THREADS, 1) head_ce_bwd_kernel(const __grid
           asm volatile("bar.sync 1, 256;" ::: "memory");
         }
         if (!mbar_wait(&acc_full[buf], (uint32_t)((nseq >> 1) & 1), HB_WAIT)) { *a.status = 8; dead = true; break; }
-        if (nseq > 0 && !mbar_wait(&ds_free, (uint32_t)((nseq - 1) & 1), HB_WAIT)) { *a.status = 9; dead = true; break; }
         tc_fence_after();
         const int n_valid = (int)min((int64_t)HB_T, a.NY - ybase);     // columns of this chunk that are real y rows
 #pragma unroll 1
@@ -227,6 +226,7 @@ __global__ void __launch_bounds__(HB_THREADS, 1) head_ce_bwd_kernel(const __grid
           tmem_ld_wait();
           const int t_loc = a.rows_outer ? x_tgt - (int)ybase - c0 : 0;          // column of the target inside this group
           const int lim = n_valid - c0;                                          // columns < lim are valid
+          const bool all_valid = lim >= 32;                                      // uniform: only the last chunk is ragged
 #pragma unroll
           for (int jj = 0; jj < 16; ++jj) {
             float d[2];
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(HB_THREADS, 1) head_ce_bwd_kernel(const __grid
               if (a.rows_outer) {
                 const float p = ex2_fast(fmaf(L, sc2, -x_lse2));
                 v = x_g * (p - (j == t_loc ? 1.0f : 0.0f));
-                v = j < lim ? v : 0.0f;
+                if (!all_valid) v = j < lim ? v : 0.0f;
               } else {
                 const float p = ex2_fast(fmaf(L, sc2, -y_lse2[buf][c0 + j]));
                 v = y_g[buf][c0 + j] * (p - (y_tgt[buf][c0 + j] == xi ? 1.0f : 0.0f));
@@ -249,9 +249,16 @@ __global__ void __launch_bounds__(HB_THREADS, 1) head_ce_bwd_kernel(const __grid
             const float h0 = __uint_as_float(hi[jj] << 16), h1 = __uint_as_float(hi[jj] & 0xffff0000u);
             lo[jj] = pack_bf16(d[0] - h0, d[1] - h1);
           }
+          if (c0 == hh * 64 && nseq > 0) {
+            // the dS operand is single-buffered: the previous chunk's dX MMAs must have read it.  Waiting HERE, with the
+            // first 32 columns already computed in registers, overlaps half of the epilogue with those MMAs.
+            if (!mbar_wait(&ds_free, (uint32_t)((nseq - 1) & 1), HB_WAIT)) { *a.status = 9; dead = true; }
+            tc_fence_after();
+          }
           tmem_st16(tmem + lane_sel + HB_C_DSH + (uint32_t)(c0 / 2), hi);
           tmem_st16(tmem + lane_sel + HB_C_DSL + (uint32_t)(c0 / 2), lo);
         }
+        if (dead) break;
         tmem_st_wait();
         tc_fence_before();
         mbar_arrive(&ds_full);

@@ -54,6 +54,12 @@ __global__ void __launch_bounds__(128) head_pack_table_kernel(const float* __res
   }
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 struct HeadArgs {
   const float* emb;       // [M][64] un-normalised pred_emb
   const float* tn;        // [Zp][64] fp32 normalised table
@@ -194,11 +200,17 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_argmax_kernel(const __grid
           for (int j = 0; j < 32; ++j) mx = fmaxf(mx, (zbase + c0 + j < a.Z) ? __uint_as_float(r[j]) : -INFINITY);
           if (ce && mx > -INFINITY) {       // streaming log-sum-exp over the zones (split-bf16 logits: ~2^-16 relative)
             if (mx > run_m) { run_s *= exp2f((run_m - mx) * sc2); run_m = mx; }
-            float part = 0.0f;
+            const float off = -run_m * sc2;
+            float part[4] = {0.0f, 0.0f, 0.0f, 0.0f};          // four independent chains
+            if (zbase + c0 + 32 <= a.Z) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (zbase + c0 + j < a.Z) part += exp2f((__uint_as_float(r[j]) - run_m) * sc2);
-            run_s += part;
+              for (int j = 0; j < 32; ++j) part[j & 3] += ex2_approx(fmaf(__uint_as_float(r[j]), sc2, off));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (zbase + c0 + j < a.Z) part[j & 3] += ex2_approx(fmaf(__uint_as_float(r[j]), sc2, off));
+            }
+            run_s += (part[0] + part[1]) + (part[2] + part[3]);
           }
           if (mx > b2) {        // rare after the first chunks: only then look at the individual columns
 #pragma unroll
