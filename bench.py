@@ -195,6 +195,9 @@ def run_ours(args):
 
     adaptive = cfg["method"] == "dopri5"
     counter = {"agent_steps": 0, "accepted": 0, "rejected": 0}
+    snap_idx = torch.arange(4, T, 8, device=dev)[:12] if train else None                    # 12 snap rows of the day grid
+    snap_target = (torch.randint(0, cfg["Z"], (12, B), generator=torch.Generator().manual_seed(99 + rank)).to(dev)
+                   if (train and args.loss == "ce") else None)
 
     def count(nb):
         """agent-steps of the chunk just integrated: grid intervals for rk4, ACCEPTED steps for dopri5"""
@@ -227,7 +230,14 @@ def run_ours(args):
             y0 = model.initial_state(table, zemb, hm[s:s + chunk], wk[s:s + chunk], tr[s:s + chunk])
             y_path = model.integrate(y0, tt)
             count(y0.shape[0])
-            loss = _TrajectoryLoss.apply(y_path, 128) * ((min(B, s + chunk) - s) / B)
+            if args.loss == "ce":
+                # the reference's training loss at the ground-truth snaps (ce_at_snaps, losses.py:14-22): decoder + fused
+                # cross-entropy head at 12 of the 97 grid points (~12 GT snaps per agent-day)
+                pred_emb = model.decoder(y_path[snap_idx, :, :model.config.emb_dim])
+                rows = ab.head_ce_rows(pred_emb, table, snap_target[:, s:s + chunk], model.config.softmax_tau)
+                loss = rows.sum() / (snap_idx.numel() * B)
+            else:
+                loss = _TrajectoryLoss.apply(y_path, 128) * ((min(B, s + chunk) - s) / B)
             loss.backward()
             total = loss.detach() if total is None else total + loss.detach()
             del y_path, loss
@@ -378,7 +388,7 @@ def run_ours(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if args.precision == "f32" else ("fp16 fwd / bf16 bwd operands (fp32 accumulate, fp32 state)" if train else "bf16 (fp32 accumulate, fp32 state)"), "data": "synthetic",
         "config": {"workload": cfg["name"], "agents_per_gpu": B, "zones": cfg["Z"], "time_points": T, "solver": cfg["method"],
-                   "agent_chunk": chunk, "precision": args.precision,
+                   "agent_chunk": chunk, "precision": args.precision, "loss": (args.loss if train else None),
                    "solver_steps": ({"accepted_per_trajectory": steps_counted["accepted"] / max(1, args.steps * ((B + chunk - 1) // chunk)),
                                      "rejected_per_trajectory": steps_counted["rejected"] / max(1, args.steps * ((B + chunk - 1) // chunk)),
                                      "rtol": model.config.rtol, "atol": model.config.atol} if adaptive else {"grid_intervals": T - 1}),
@@ -491,6 +501,9 @@ def main():
                     help="agents per launch sequence; default = 5 x (148 SMs x 2 slots x 128 agents): whole waves of tiles")
     ap.add_argument("--solver", default="", choices=["", "rk4", "dopri5"], help="override the workload's solver")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--loss", default="traj", choices=["traj", "ce"],
+                    help="training loss in the timed step: 'traj' = mean square of the trajectory (stand-in, default); "
+                         "'ce' = decoder + fused cross-entropy head at 12 snap points per agent (tensor cores)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
