@@ -25,7 +25,7 @@ constexpr uint32_t HD_A_BYTES = HD_TM * HD_K * 2;          // 49,152
 constexpr uint32_t HD_B_BYTES = HD_TN * HD_K * 2;          // 49,152 per table chunk
 constexpr int HD_NS = 3;
 constexpr uint32_t HD_SMEM = HD_A_BYTES + HD_NS * HD_B_BYTES;
-constexpr int HD_THREADS = 192;
+constexpr int HD_THREADS = 320, HD_EPI = 256;       // warps 0/1: producer / MMA issuer; warps 2-9: epilogue (row x column half)
 constexpr uint32_t HD_LBO = 128u * 16u, HD_SBO = 128u;     // [128 rows][K] K-major, un-swizzled
 constexpr long long HD_WAIT = 400000000LL;
 
@@ -81,6 +81,8 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_argmax_kernel(const __grid
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t full[HD_NS], empty[HD_NS], acc_full[2], acc_empty[2], a_ready, a_free;
   __shared__ uint32_t tmem_base_s;
+  __shared__ float x_b1[HD_TM], x_b2[HD_TM], x_m[HD_TM], x_s[HD_TM];     // second column half -> first: top-2 and log-sum-exp state
+  __shared__ int x_i1[HD_TM], x_i2[HD_TM];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint8_t* sA = smem;
   uint8_t* sB = smem + HD_A_BYTES;
@@ -88,7 +90,7 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_argmax_kernel(const __grid
   if (warp == 0) tmem_alloc<256>(&tmem_base_s);
   if (tid == 0) {
     for (int i = 0; i < HD_NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], HD_EPI); }
     mbar_init(&a_ready, 128);
     mbar_init(&a_free, 1);
     mbar_fence_init();
@@ -137,8 +139,10 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_argmax_kernel(const __grid
       }
     }
   } else {
-    // ---- epilogue warps: thread = row
+    // ---- epilogue warps: thread = (row, half of the chunk's 128 zone columns); two warps per scheduler hide each
+    //      other's dependent-issue latency (one warp per scheduler left the SM idle two cycles out of three)
     const int q = warp & 3;
+    const int hh = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
     int nacc = 0;
@@ -157,6 +161,7 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_argmax_kernel(const __grid
           ss += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
         }
         inv = 1.0f / (sqrtf(ss) + 1e-8f);
+        if (hh == 0) {
         if (t > 0 && !mbar_wait(&a_free, (uint32_t)((t - 1) & 1), HD_WAIT)) { *a.status = 6; break; }
 #pragma unroll
         for (int j = 0; j < HD_E / 8; ++j) {     // 8 features -> one 16-byte core-matrix row, for each of the three K segments
@@ -177,6 +182,7 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_argmax_kernel(const __grid
         }
         fence_async_smem();
         mbar_arrive(&a_ready);
+        }
       }
       // -- stream the zone chunks: running top-2 of this row
       float b1 = -INFINITY, b2 = -INFINITY;
@@ -191,7 +197,7 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_argmax_kernel(const __grid
         tc_fence_after();
         const int zbase = c * HD_TN;
 #pragma unroll 1
-        for (int c0 = 0; c0 < HD_TN; c0 += 32) {
+        for (int c0 = hh * (HD_TN / 2); c0 < (hh + 1) * (HD_TN / 2); c0 += 32) {
           uint32_t r[32];
           tmem_ld32(tmem + lane_sel + (uint32_t)(buf * HD_TN + c0), r);
           tmem_ld_wait();
@@ -228,8 +234,32 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_argmax_kernel(const __grid
         mbar_arrive(&acc_empty[buf]);
       }
       if (dead) break;
+      // -- merge the two column halves of the row: top-2 of four candidates (lower zone index wins ties, as a single
+      //    left-to-right sweep would have it), log-sum-exp states combined on the common maximum
+      if (hh == 1) { x_b1[row] = b1; x_i1[row] = i1; x_b2[row] = b2; x_i2[row] = i2; x_m[row] = run_m; x_s[row] = run_s; }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (hh == 0) {
+        const float c1 = x_b1[row], c2 = x_b2[row];
+        const int j1 = x_i1[row], j2 = x_i2[row];
+        // "better" = larger value, lower zone index on ties (what one left-to-right sweep over all zones would keep)
+        auto better = [](float va, int ia, float vb, int ib) { return va > vb || (va == vb && ia < ib); };
+        if (better(c1, j1, b1, i1)) {
+          const bool keep_b1 = better(b1, i1, c2, j2);
+          b2 = keep_b1 ? b1 : c2; i2 = keep_b1 ? i1 : j2;
+          b1 = c1; i1 = j1;
+        } else if (better(c1, j1, b2, i2)) { b2 = c1; i2 = j1; }
+        if (ce) {
+          const float om = x_m[row], os = x_s[row];
+          const float mn = fmaxf(run_m, om);
+          if (mn > -INFINITY) {
+            run_s = (run_m > -INFINITY ? run_s * exp2f((run_m - mn) * sc2) : 0.0f) + (om > -INFINITY ? os * exp2f((om - mn) * sc2) : 0.0f);
+            run_m = mn;
+          }
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");       // the exchange buffers are free for the next row tile
       // -- exact fp32 re-score of the two nominees
-      if (valid) {
+      if (valid && hh == 0) {
         const float4* er = reinterpret_cast<const float4*>(a.emb + m * HD_E);
         const float4* t1 = reinterpret_cast<const float4*>(a.tn + (size_t)i1 * HD_E);
         const float4* t2 = reinterpret_cast<const float4*>(a.tn + (size_t)i2 * HD_E);

@@ -20,7 +20,7 @@ class _HeadCE(torch.autograd.Function):
     """per-row cross entropy of cos(emb, table) / tau against `target`; rows are independent."""
 
     @staticmethod
-    def forward(ctx, emb, table, target, tau: float, row_chunk: int):
+    def forward(ctx, emb, table, target, tau: float):
         L = _lib.lib()
         if not emb.is_cuda:
             raise _lib.Ab200Error("pred_emb must be a CUDA tensor: ananke_abm_b200 has no CPU path")
@@ -38,7 +38,7 @@ class _HeadCE(torch.autograd.Function):
                                      tl.data_ptr(), None, ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
         _lib.check(rc, "ab200_head_ce_forward")
         ctx.save_for_backward(embc, tablec, tgt, lse)
-        ctx.tau, ctx.row_chunk = float(tau), int(row_chunk)
+        ctx.tau = float(tau)
         return lse - tl
 
     @staticmethod
@@ -66,15 +66,14 @@ class _HeadCE(torch.autograd.Function):
         eh, th = emb / (n_e + 1e-8), table / (n_t + 1e-8)
         g_emb = g_eh / (n_e + 1e-8) - eh * ((g_eh * eh).sum(-1, keepdim=True) / n_e.clamp_min(1e-30))
         g_table = g_th / (n_t + 1e-8) - th * ((g_th * th).sum(-1, keepdim=True) / n_t.clamp_min(1e-30))
-        return g_emb, g_table, None, None, None
+        return g_emb, g_table, None, None
 
 
-def head_ce_rows(pred_emb: torch.Tensor, class_table: torch.Tensor, target: torch.Tensor, tau: float = 0.2,
-                 row_chunk: int = 32_768) -> torch.Tensor:
+def head_ce_rows(pred_emb: torch.Tensor, class_table: torch.Tensor, target: torch.Tensor, tau: float = 0.2) -> torch.Tensor:
     """Per-row cross entropy `-log softmax(cos(pred_emb, class_table) / tau)[target]` for `pred_emb [..., E]`,
     `target [...]`; rows whose target is outside [0, Z) are scored against zone 0 (mask them)."""
     lead = pred_emb.shape[:-1]
-    rows = _HeadCE.apply(pred_emb.reshape(-1, pred_emb.shape[-1]), class_table, target.reshape(-1), tau, row_chunk)
+    rows = _HeadCE.apply(pred_emb.reshape(-1, pred_emb.shape[-1]), class_table, target.reshape(-1), tau)
     return rows.view(lead)
 
 
