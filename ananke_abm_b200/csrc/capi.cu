@@ -74,6 +74,9 @@ int pv_combine_bwd(const ab200_drift_desc* d, const float* g, int n_a, float cpv
 
 int rows_transpose(const float* src, float* dst, int64_t B, int F, int mode, cudaStream_t st);
 
+int grad_sumsq(const float* g, int64_t n, double* out, cudaStream_t st);
+int adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, float wd, int step,
+              float max_norm, const double* sumsq, cudaStream_t st);
 size_t head_workspace_bytes(int Z);
 size_t head_ce_backward_workspace_bytes(int64_t M, int Z);
 int head_ce_backward(const float* emb, const float* table, const int64_t* target, const float* lse, const float* g_rows, int64_t M,
@@ -338,6 +341,19 @@ int ab200_pv_combine_backward(const ab200_drift_desc* d, const float* g, int32_t
                               ab200_stream_t stream) {
   if (!desc_ok(d) || !g || !G_y0 || B <= 0 || (n_a > 0 && (!G_a || !cpa_host || !cva_host))) return AB200_ERR_BAD_ARG;
   return pv_combine_bwd(d, g, n_a, cpv, cpa_host, cva_host, B, G_y0, G_a, accumulate, (cudaStream_t)stream);
+}
+
+int ab200_grad_sumsq(const float* flat_grad, int64_t n, double* sumsq_out, void* stream) {
+  if (!flat_grad || !sumsq_out || n <= 0) return AB200_ERR_BAD_ARG;
+  return grad_sumsq(flat_grad, n, sumsq_out, (cudaStream_t)stream);
+}
+
+int ab200_adam_step(float* flat_param, const float* flat_grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                    float beta2, float eps, float weight_decay, int32_t step, float max_grad_norm, const double* grad_sumsq,
+                    void* stream) {
+  if (!flat_param || !flat_grad || !exp_avg || !exp_avg_sq || n <= 0 || step < 1) return AB200_ERR_BAD_ARG;
+  return adam_step(flat_param, flat_grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, step, max_grad_norm, grad_sumsq,
+                   (cudaStream_t)stream);
 }
 
 size_t ab200_head_workspace_bytes(int32_t Z, int32_t E) { return (Z > 0 && E == 64) ? head_workspace_bytes(Z) : 0; }

@@ -232,6 +232,17 @@ int ab200_pv_combine_backward(const ab200_drift_desc* d, const float* g, int32_t
                               const float* cva_host, int64_t B, float* G_y0, float* const* G_a, int32_t accumulate,
                               ab200_stream_t stream);
 
+/* ---- optimiser step over the flat parameter / gradient buffers ----------------------------------------------------
+ * Replaces  torch.nn.utils.clip_grad_norm_(params, max_norm) ; torch.optim.Adam(lr, weight_decay).step()
+ * (mode_sep/train/train.py:68,163-164) on the flat fp32 buffer the NCCL gradient all-reduce already uses: two launches,
+ * no host synchronisation.  ab200_grad_sumsq writes sum(g^2) (double, device); ab200_adam_step applies the clip
+ * coefficient min(1, max_grad_norm / (sqrt(sumsq) + 1e-6)) when max_grad_norm > 0 and grad_sumsq != NULL, then Adam
+ * with L2 weight decay (torch.optim.Adam semantics, not AdamW), `step` counted from 1. */
+int ab200_grad_sumsq(const float* flat_grad, int64_t n, double* sumsq_out, void* stream);
+int ab200_adam_step(float* flat_param, const float* flat_grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                    float beta1, float beta2, float eps, float weight_decay, int32_t step, float max_grad_norm,
+                    const double* grad_sumsq, void* stream);
+
 /* ---- fused classification head + label prediction ------------------------------------------------------------
  * Replaces  emb_norm = pred_emb / (|pred_emb| + 1e-8); table_norm = class_table / (|class_table| + 1e-8);
  *           logits = einsum("bte,ze->btz", emb_norm, table_norm) / softmax_tau      mode_sep/architecture/model.py:196-199
