@@ -55,9 +55,9 @@ SIGNATURES = {
     "ab200_grad_sumsq": (C.c_int, [_vp, _i64, _vp, _vp]),
     "ab200_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _f32, _vp, _vp]),
     "ab200_head_argmax": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _f32, _vp, _vp, _vp, _sz, _vp]),
-    "ab200_head_ce_forward": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ab200_head_ce_forward": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ab200_head_ce_backward_workspace_bytes": (_sz, [_i64, _i32, _i32]),
-    "ab200_head_ce_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _f32, _vp, _vp, _vp, _sz, _vp]),
+    "ab200_head_ce_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _f32, _vp, _vp, _vp, _sz, _vp]),
     "ab200_head_ce_backward_status": (C.c_int, [_vp, _i64, _i32, _vp, _vp]),
     "ab200_gat_forward": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _f32, _vp, _vp, _vp, _vp,
                                     _vp, _vp]),

@@ -79,11 +79,12 @@ int adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr,
               float max_norm, const double* sumsq, cudaStream_t st);
 size_t head_workspace_bytes(int Z);
 size_t head_ce_backward_workspace_bytes(int64_t M, int Z);
-int head_ce_backward(const float* emb, const float* table, const int64_t* target, const float* lse, const float* g_rows, int64_t M,
-                     int Z, int E, float tau, float* d_emb_n, float* d_table_n, void* ws, size_t ws_bytes, cudaStream_t st);
+int head_ce_backward(const float* emb, const float* table, const int64_t* target, const float* lse, const float* g_rows,
+                     const float* g_dist_rows, const float* exp_dist, const float* dist, int64_t M, int Z, int E, float tau,
+                     float* d_emb_n, float* d_table_n, void* ws, size_t ws_bytes, cudaStream_t st);
 int head_ce_backward_status(const void* ws, int64_t M, int Z, int* host_out, cudaStream_t st);
 int head_ce_forward(const float* emb, const float* table, const int64_t* target, int64_t M, int Z, int E, float tau, float* lse,
-                    float* tgt_logit, int64_t* labels, void* ws, size_t ws_bytes, cudaStream_t st);
+                    float* tgt_logit, int64_t* labels, const float* dist, float* exp_dist, void* ws, size_t ws_bytes, cudaStream_t st);
 int head_argmax(const float* emb, const float* table, int64_t M, int Z, int E, float tau, int64_t* labels, float* best, void* ws,
                 size_t ws_bytes, cudaStream_t st);
 
@@ -365,12 +366,13 @@ int ab200_head_argmax(const float* pred_emb, const float* class_table, int64_t M
 }
 
 int ab200_head_ce_forward(const float* pred_emb, const float* class_table, const int64_t* target, int64_t M, int32_t Z, int32_t E,
-                          float tau, float* lse, float* target_logit, int64_t* labels, void* workspace, size_t workspace_bytes,
-                          void* stream) {
-  if (!pred_emb || !class_table || !target || !lse || !target_logit || !workspace || M <= 0 || Z <= 0 || !(tau > 0.0f))
+                          float tau, float* lse, float* target_logit, int64_t* labels, const float* dist_mat, float* expected_dist,
+                          void* workspace, size_t workspace_bytes, void* stream) {
+  if (!pred_emb || !class_table || !target || !lse || !target_logit || !workspace || M <= 0 || Z <= 0 || !(tau > 0.0f) ||
+      ((dist_mat != nullptr) != (expected_dist != nullptr)))
     return AB200_ERR_BAD_ARG;
-  return head_ce_forward(pred_emb, class_table, target, M, Z, E, tau, lse, target_logit, labels, workspace, workspace_bytes,
-                         (cudaStream_t)stream);
+  return head_ce_forward(pred_emb, class_table, target, M, Z, E, tau, lse, target_logit, labels, dist_mat, expected_dist, workspace,
+                         workspace_bytes, (cudaStream_t)stream);
 }
 
 size_t ab200_head_ce_backward_workspace_bytes(int64_t M, int32_t Z, int32_t E) {
@@ -378,13 +380,16 @@ size_t ab200_head_ce_backward_workspace_bytes(int64_t M, int32_t Z, int32_t E) {
 }
 
 int ab200_head_ce_backward(const float* pred_emb, const float* class_table, const int64_t* target, const float* lse,
-                           const float* grad_rows, int64_t M, int32_t Z, int32_t E, float tau, float* grad_emb_normalised,
-                           float* grad_table_normalised, void* workspace, size_t workspace_bytes, void* stream) {
+                           const float* grad_rows, const float* grad_dist_rows, const float* expected_dist, const float* dist_mat,
+                           int64_t M, int32_t Z, int32_t E, float tau, float* grad_emb_normalised, float* grad_table_normalised,
+                           void* workspace, size_t workspace_bytes, void* stream) {
   if (!pred_emb || !class_table || !target || !lse || !grad_rows || !grad_emb_normalised || !grad_table_normalised || !workspace ||
       M <= 0 || Z <= 0 || !(tau > 0.0f))
     return AB200_ERR_BAD_ARG;
-  return head_ce_backward(pred_emb, class_table, target, lse, grad_rows, M, Z, E, tau, grad_emb_normalised, grad_table_normalised,
-                          workspace, workspace_bytes, (cudaStream_t)stream);
+  const int nd = (grad_dist_rows != nullptr) + (expected_dist != nullptr) + (dist_mat != nullptr);
+  if (nd != 0 && nd != 3) return AB200_ERR_BAD_ARG;
+  return head_ce_backward(pred_emb, class_table, target, lse, grad_rows, grad_dist_rows, expected_dist, dist_mat, M, Z, E, tau,
+                          grad_emb_normalised, grad_table_normalised, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int ab200_head_ce_backward_status(const void* workspace, int64_t M, int32_t Z, int32_t* status_host, void* stream) {

@@ -68,6 +68,11 @@ struct HeadBwdArgs {
   const float* lse;         // per ROW (x if rows_outer else y)
   const float* g;           // per ROW upstream gradient
   const int64_t* target;    // per ROW
+  // expected-distance term (all three set or all null): dlogit += g2 * softmax * (dist[target, z] - edist)
+  const float* g2;          // per ROW upstream gradient of the expected distance
+  const float* edist;       // per ROW expected distance (forward output)
+  const float* dist;        // [Z][Z]
+  int Z;
   float inv_tau;
   float* dx;                // [NX][64]                       (nsplit == 1)
   float* partial;           // [nsplit][nx * 128][64]         (nsplit > 1)
@@ -93,6 +98,7 @@ __global__ void __launch_bounds__(HB_THREADS, 1) head_ce_bwd_kernel(const __grid
   __shared__ uint32_t tmem_base_s;
   __shared__ float y_lse2[2][HB_T], y_g[2][HB_T];
   __shared__ int y_tgt[2][HB_T];
+  __shared__ float y_g2[2][HB_T], y_e[2][HB_T];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint8_t* sX = smem;
   uint8_t* sY = smem + HB_IMG;
@@ -201,7 +207,17 @@ __global__ void __launch_bounds__(HB_THREADS, 1) head_ce_bwd_kernel(const __grid
       const bool xvalid = xg < a.NX;
       float x_lse2 = 0.0f, x_g = 0.0f;
       int x_tgt = -1;
-      if (a.rows_outer && xvalid) { x_lse2 = a.lse[xg] * 1.4426950408889634f; x_g = a.g[xg] * a.inv_tau; x_tgt = (int)a.target[xg]; }
+      const bool want_d = a.dist != nullptr;
+      float x_g2 = 0.0f, x_e = 0.0f;
+      const float* drow = nullptr;
+      if (a.rows_outer && xvalid) {
+        x_lse2 = a.lse[xg] * 1.4426950408889634f; x_g = a.g[xg] * a.inv_tau; x_tgt = (int)a.target[xg];
+        if (want_d) {
+          x_g2 = a.g2[xg] * a.inv_tau; x_e = a.edist[xg];
+          const int tc = (x_tgt < 0 || x_tgt >= a.Z) ? 0 : x_tgt;
+          drow = a.dist + (size_t)tc * a.Z;
+        }
+      }
       const int xi = (int)xg;                         // zones-outer: the zone index of this row (Z < 2^31)
       for (int c = c_begin; c < c_end; ++c, ++nseq) {
         const int buf = nseq & 1;
@@ -213,6 +229,7 @@ __global__ void __launch_bounds__(HB_THREADS, 1) head_ce_bwd_kernel(const __grid
             y_lse2[buf][et] = yv ? a.lse[yr] * 1.4426950408889634f : 0.0f;
             y_g[buf][et] = yv ? a.g[yr] * a.inv_tau : 0.0f;            // 0 on padding rows: their dS vanishes
             y_tgt[buf][et] = yv ? (int)a.target[yr] : -1;
+            if (want_d) { y_g2[buf][et] = yv ? a.g2[yr] * a.inv_tau : 0.0f; y_e[buf][et] = yv ? a.edist[yr] : 0.0f; }
           }
           asm volatile("bar.sync 1, 256;" ::: "memory");
         }
@@ -238,10 +255,16 @@ __global__ void __launch_bounds__(HB_THREADS, 1) head_ce_bwd_kernel(const __grid
               if (a.rows_outer) {
                 const float p = ex2_fast(fmaf(L, sc2, -x_lse2));
                 v = x_g * (p - (j == t_loc ? 1.0f : 0.0f));
+                if (want_d && drow != nullptr && j < lim) v = fmaf(x_g2 * p, __ldg(drow + ybase + c0 + j) - x_e, v);
                 if (!all_valid) v = j < lim ? v : 0.0f;
               } else {
                 const float p = ex2_fast(fmaf(L, sc2, -y_lse2[buf][c0 + j]));
-                v = y_g[buf][c0 + j] * (p - (y_tgt[buf][c0 + j] == xi ? 1.0f : 0.0f));
+                const int yt = y_tgt[buf][c0 + j];
+                v = y_g[buf][c0 + j] * (p - (yt == xi ? 1.0f : 0.0f));
+                if (want_d && xvalid) {
+                  const int tc = (yt < 0 || yt >= a.Z) ? 0 : yt;
+                  v = fmaf(y_g2[buf][c0 + j] * p, __ldg(a.dist + (size_t)tc * a.Z + xi) - y_e[buf][c0 + j], v);
+                }
               }
               d[u] = v;
             }
@@ -320,8 +343,9 @@ size_t head_ce_backward_workspace_bytes(int64_t M, int Z) {
 }
 
 // d emb^ [M][64] and d table^ [Z][64] (gradients w.r.t. the NORMALISED vectors; the caller applies x / (|x| + 1e-8)).
-int head_ce_backward(const float* emb, const float* table, const int64_t* target, const float* lse, const float* g_rows, int64_t M,
-                     int Z, int E, float tau, float* d_emb_n, float* d_table_n, void* ws, size_t ws_bytes, cudaStream_t st) {
+int head_ce_backward(const float* emb, const float* table, const int64_t* target, const float* lse, const float* g_rows,
+                     const float* g_dist_rows, const float* exp_dist, const float* dist, int64_t M, int Z, int E, float tau,
+                     float* d_emb_n, float* d_table_n, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (E != HB_E) return AB200_ERR_UNSUPPORTED;
   if (ws_bytes < head_ce_backward_workspace_bytes(M, Z)) return AB200_ERR_WORKSPACE;
   const int nm = hb_tiles(M), nz = hb_tiles(Z);
@@ -345,7 +369,7 @@ int head_ce_backward(const float* emb, const float* table, const int64_t* target
     int ns = hb_nsplit(nx, ny, sms);
     const int ns_cap = hb_nsplit(nx, ny, HB_SMS_ASSUMED);
     if (ns > ns_cap) ns = ns_cap;                      // never beyond what the workspace was sized for
-    HeadBwdArgs k{ximg, yimg, nx, ny, NX, NY, rows_outer, y_lo_seg, lse, g_rows, target, 1.0f / tau, dx, partial, ns, status};
+    HeadBwdArgs k{ximg, yimg, nx, ny, NX, NY, rows_outer, y_lo_seg, lse, g_rows, target, g_dist_rows, exp_dist, dist, Z, 1.0f / tau, dx, partial, ns, status};
     const int items = nx * ns;
     head_ce_bwd_kernel<<<items < sms ? items : sms, HB_THREADS, HB_SMEM, st>>>(k);
     int r = check_launch();

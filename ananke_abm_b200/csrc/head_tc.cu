@@ -75,13 +75,16 @@ struct HeadArgs {
   const int64_t* target;  // [M], values outside [0, Z) are read as zone 0 (the caller masks those rows)
   float* lse;
   float* tgt_logit;
+  // expected distance (optional, with the cross-entropy mode): exp_dist[m] = sum_z softmax[m,z] dist[target[m], z]
+  const float* dist;      // [Z][Z] row-major
+  float* exp_dist;        // [M]
 };
 
 __global__ void __launch_bounds__(HD_THREADS, 1) head_argmax_kernel(const __grid_constant__ HeadArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t full[HD_NS], empty[HD_NS], acc_full[2], acc_empty[2], a_ready, a_free;
   __shared__ uint32_t tmem_base_s;
-  __shared__ float x_b1[HD_TM], x_b2[HD_TM], x_m[HD_TM], x_s[HD_TM];     // second column half -> first: top-2 and log-sum-exp state
+  __shared__ float x_b1[HD_TM], x_b2[HD_TM], x_m[HD_TM], x_s[HD_TM], x_d[HD_TM];     // second column half -> first: top-2 and log-sum-exp state
   __shared__ int x_i1[HD_TM], x_i2[HD_TM];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint8_t* sA = smem;
@@ -191,6 +194,14 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_argmax_kernel(const __grid
       const bool ce = a.lse != nullptr;
       const float sc2 = a.inv_tau * 1.4426950408889634f;     // logits in log2 units
       float run_m = -INFINITY, run_s = 0.0f;                 // running max (cosine units) and sum of exp(logit - max)
+      float run_d = 0.0f;                                    // sum of exp(logit - max) * dist[target, z]
+      const bool want_d = ce && a.dist != nullptr;
+      const float* drow = nullptr;                           // this row's line of the distance matrix
+      if (want_d && valid) {
+        int64_t tg = a.target[m];
+        if (tg < 0 || tg >= a.Z) tg = 0;
+        drow = a.dist + (size_t)tg * a.Z;
+      }
       for (int c = 0; c < a.nchunk; ++c, ++nacc) {
         const int buf = nacc & 1;
         if (!mbar_wait(&acc_full[buf], (uint32_t)((nacc >> 1) & 1), HD_WAIT)) { *a.status = 7; dead = true; break; }
@@ -205,8 +216,22 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_argmax_kernel(const __grid
 #pragma unroll
           for (int j = 0; j < 32; ++j) mx = fmaxf(mx, (zbase + c0 + j < a.Z) ? __uint_as_float(r[j]) : -INFINITY);
           if (ce && mx > -INFINITY) {       // streaming log-sum-exp over the zones (split-bf16 logits: ~2^-16 relative)
-            if (mx > run_m) { run_s *= exp2f((run_m - mx) * sc2); run_m = mx; }
+            if (mx > run_m) { const float f = exp2f((run_m - mx) * sc2); run_s *= f; run_d *= f; run_m = mx; }
             const float off = -run_m * sc2;
+            if (want_d) {       // same sweep, weighted by the target's distance row (rows sorted by target share it: L1 hits)
+              float pd[4] = {0.0f, 0.0f, 0.0f, 0.0f}, ps[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int z = zbase + c0 + j;
+                if (z < a.Z) {
+                  const float e = ex2_approx(fmaf(__uint_as_float(r[j]), sc2, off));
+                  ps[j & 3] += e;
+                  pd[j & 3] = fmaf(e, drow != nullptr ? __ldg(drow + z) : 0.0f, pd[j & 3]);
+                }
+              }
+              run_s += (ps[0] + ps[1]) + (ps[2] + ps[3]);
+              run_d += (pd[0] + pd[1]) + (pd[2] + pd[3]);
+            } else {
             float part[4] = {0.0f, 0.0f, 0.0f, 0.0f};          // four independent chains
             if (zbase + c0 + 32 <= a.Z) {
 #pragma unroll
@@ -217,6 +242,7 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_argmax_kernel(const __grid
                 if (zbase + c0 + j < a.Z) part[j & 3] += ex2_approx(fmaf(__uint_as_float(r[j]), sc2, off));
             }
             run_s += (part[0] + part[1]) + (part[2] + part[3]);
+            }
           }
           if (mx > b2) {        // rare after the first chunks: only then look at the individual columns
 #pragma unroll
@@ -236,7 +262,7 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_argmax_kernel(const __grid
       if (dead) break;
       // -- merge the two column halves of the row: top-2 of four candidates (lower zone index wins ties, as a single
       //    left-to-right sweep would have it), log-sum-exp states combined on the common maximum
-      if (hh == 1) { x_b1[row] = b1; x_i1[row] = i1; x_b2[row] = b2; x_i2[row] = i2; x_m[row] = run_m; x_s[row] = run_s; }
+      if (hh == 1) { x_b1[row] = b1; x_i1[row] = i1; x_b2[row] = b2; x_i2[row] = i2; x_m[row] = run_m; x_s[row] = run_s; x_d[row] = run_d; }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (hh == 0) {
         const float c1 = x_b1[row], c2 = x_b2[row];
@@ -252,7 +278,9 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_argmax_kernel(const __grid
           const float om = x_m[row], os = x_s[row];
           const float mn = fmaxf(run_m, om);
           if (mn > -INFINITY) {
-            run_s = (run_m > -INFINITY ? run_s * exp2f((run_m - mn) * sc2) : 0.0f) + (om > -INFINITY ? os * exp2f((om - mn) * sc2) : 0.0f);
+            const float f0 = run_m > -INFINITY ? exp2f((run_m - mn) * sc2) : 0.0f, f1 = om > -INFINITY ? exp2f((om - mn) * sc2) : 0.0f;
+            run_s = run_s * f0 + os * f1;
+            run_d = run_d * f0 + x_d[row] * f1;
             run_m = mn;
           }
         }
@@ -286,6 +314,7 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_argmax_kernel(const __grid
           }
           a.lse[m] = run_m * a.inv_tau + logf(run_s);
           a.tgt_logit[m] = st * a.inv_tau;
+          if (want_d) a.exp_dist[m] = run_d / run_s;
         }
       }
     }
@@ -303,22 +332,24 @@ size_t head_workspace_bytes(int Z) {
 }
 
 static int head_launch(const float* emb, const float* table, int64_t M, int Z, int E, float tau, int64_t* labels, float* best,
-                       const int64_t* target, float* lse, float* tgt_logit, void* ws, size_t ws_bytes, cudaStream_t st);
+                       const int64_t* target, float* lse, float* tgt_logit, const float* dist, float* exp_dist, void* ws,
+                       size_t ws_bytes, cudaStream_t st);
 
 int head_argmax(const float* emb, const float* table, int64_t M, int Z, int E, float tau, int64_t* labels, float* best, void* ws,
                 size_t ws_bytes, cudaStream_t st) {
-  return head_launch(emb, table, M, Z, E, tau, labels, best, nullptr, nullptr, nullptr, ws, ws_bytes, st);
+  return head_launch(emb, table, M, Z, E, tau, labels, best, nullptr, nullptr, nullptr, nullptr, nullptr, ws, ws_bytes, st);
 }
 
 // Cross-entropy forward without the [M, Z] logits: per row the log-sum-exp over all zones and the target's logit
 // (loss_row = lse - tgt_logit; masking / averaging is the caller's), optionally the argmax labels in the same pass.
 int head_ce_forward(const float* emb, const float* table, const int64_t* target, int64_t M, int Z, int E, float tau, float* lse,
-                    float* tgt_logit, int64_t* labels, void* ws, size_t ws_bytes, cudaStream_t st) {
-  return head_launch(emb, table, M, Z, E, tau, labels, nullptr, target, lse, tgt_logit, ws, ws_bytes, st);
+                    float* tgt_logit, int64_t* labels, const float* dist, float* exp_dist, void* ws, size_t ws_bytes, cudaStream_t st) {
+  return head_launch(emb, table, M, Z, E, tau, labels, nullptr, target, lse, tgt_logit, dist, exp_dist, ws, ws_bytes, st);
 }
 
 static int head_launch(const float* emb, const float* table, int64_t M, int Z, int E, float tau, int64_t* labels, float* best,
-                       const int64_t* target, float* lse, float* tgt_logit, void* ws, size_t ws_bytes, cudaStream_t st) {
+                       const int64_t* target, float* lse, float* tgt_logit, const float* dist, float* exp_dist, void* ws,
+                       size_t ws_bytes, cudaStream_t st) {
   if (E != HD_E) return AB200_ERR_UNSUPPORTED;
   if (ws_bytes < head_workspace_bytes(Z)) return AB200_ERR_WORKSPACE;
   const int nc = head_chunks(Z);
@@ -330,7 +361,7 @@ static int head_launch(const float* emb, const float* table, int64_t M, int Z, i
   head_pack_table_kernel<<<nc, 128, 0, st>>>(table, Z, tn, img);
   int rc = check_launch();
   if (rc) return rc;
-  HeadArgs k{emb, tn, img, M, Z, nc, (int)((M + HD_TM - 1) / HD_TM), 1.0f / tau, labels, best, status, target, lse, tgt_logit};
+  HeadArgs k{emb, tn, img, M, Z, nc, (int)((M + HD_TM - 1) / HD_TM), 1.0f / tau, labels, best, status, target, lse, tgt_logit, dist, exp_dist};
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -259,21 +259,27 @@ int ab200_head_argmax(const float* pred_emb, const float* class_table, int64_t M
  * (mode_sep/architecture/losses.py:14-22) without the [M, Z] logits: per row lse[m] = log sum_z exp(logit[m, z]) (streamed
  * over the zones on the tensor cores, split-bf16 operands) and target_logit[m] = logit[m, target[m]] (fp32 re-score);
  * row loss = lse - target_logit, masking and the mean are the caller's.  target values outside [0, Z) are read as zone 0.
- * labels may be NULL; when given it receives the argmax of ab200_head_argmax from the same pass. */
+ * labels may be NULL; when given it receives the argmax of ab200_head_argmax from the same pass.
+ * dist_mat [Z][Z] + expected_dist [M] (both or neither): the same sweep also yields `expected_distance_at_snaps`
+ * (losses.py:34-44) per row, expected_dist[m] = sum_z softmax[m,z] dist_mat[target[m], z]; rows sorted by target share
+ * their distance row in L1/L2 (the Python wrapper sorts). */
 int ab200_head_ce_forward(const float* pred_emb, const float* class_table, const int64_t* target, int64_t M, int32_t Z,
-                          int32_t E, float tau, float* lse, float* target_logit, int64_t* labels, void* workspace,
-                          size_t workspace_bytes, void* stream);
+                          int32_t E, float tau, float* lse, float* target_logit, int64_t* labels, const float* dist_mat,
+                          float* expected_dist, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Backward of the cross-entropy head on tensor cores: with dlogit[m,z] = grad_rows[m] (softmax[m,z] - [z = target[m]])
  * recomputed tile by tile from `lse` (never stored), writes the gradients w.r.t. the NORMALISED vectors
  *   grad_emb_normalised[m,:] = (1/tau) sum_z dlogit[m,z] table^[z,:]      grad_table_normalised[z,:] = (1/tau) sum_m dlogit[m,z] emb^[m,:]
  * (autograd through the reference's einsum + F.cross_entropy, model.py:196-199 / losses.py:14-22); the caller applies
- * the Jacobian of x / (|x| + 1e-8).  Deterministic (no atomics).  ab200_head_ce_backward_status copies the kernels'
+ * the Jacobian of x / (|x| + 1e-8).  With grad_dist_rows / expected_dist / dist_mat (all three or none) the expected-distance
+ * term is added: dlogit[m,z] += grad_dist_rows[m] softmax[m,z] (dist_mat[target[m], z] - expected_dist[m]).
+ * Deterministic (no atomics).  ab200_head_ce_backward_status copies the kernels'
  * barrier-timeout word to the host (synchronises the stream; 0 = clean). */
 size_t ab200_head_ce_backward_workspace_bytes(int64_t M, int32_t Z, int32_t E);
 int ab200_head_ce_backward(const float* pred_emb, const float* class_table, const int64_t* target, const float* lse,
-                           const float* grad_rows, int64_t M, int32_t Z, int32_t E, float tau, float* grad_emb_normalised,
-                           float* grad_table_normalised, void* workspace, size_t workspace_bytes, void* stream);
+                           const float* grad_rows, const float* grad_dist_rows, const float* expected_dist, const float* dist_mat,
+                           int64_t M, int32_t Z, int32_t E, float tau, float* grad_emb_normalised, float* grad_table_normalised,
+                           void* workspace, size_t workspace_bytes, void* stream);
 int ab200_head_ce_backward_status(const void* workspace, int64_t M, int32_t Z, int32_t* status_host, void* stream);
 
 /* ---- graph attention over the zone graph (the `gnn_embed` slot) ------------------------------------

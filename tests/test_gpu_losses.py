@@ -71,7 +71,7 @@ def test_head_ce_labels_equal_head_argmax():
     lse, tl = torch.empty(M, device=dev), torch.empty(M, device=dev)
     labels = torch.empty(M, dtype=torch.int64, device=dev)
     rc = L.ab200_head_ce_forward(emb.data_ptr(), table.data_ptr(), tgt.data_ptr(), M, Z, 64, 0.2, lse.data_ptr(), tl.data_ptr(),
-                                 labels.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+                                 labels.data_ptr(), None, None, ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
     _lib.check(rc, "ab200_head_ce_forward")
     assert torch.equal(labels, head_argmax(emb, table, 0.2))
     logits = _ref_logits(emb.double(), table.double(), 0.2)
@@ -131,3 +131,31 @@ def test_training_step_with_fused_ce_reaches_every_parameter():
     assert abs(float(loss.detach()) - float(ref)) < 1e-5 * abs(float(ref))
     missing = [n for n, p in model.named_parameters() if p.grad is None or not torch.isfinite(p.grad).all() or float(p.grad.abs().sum()) == 0.0]
     assert not missing, missing
+
+
+@pytest.mark.parametrize("B,T,Z", [(37, 9, 500), (400, 12, 2000)])
+def test_ce_and_expected_distance_fused_match_reference_formulas(B, T, Z):
+    """ce_at_snaps + expected_distance_at_snaps (losses.py:14-22, 34-44) from one sweep: values and gradients of a
+    weighted sum of both against float64 autograd through materialised logits."""
+    import ananke_abm_b200 as ab
+    dev = _cuda()
+    g = torch.Generator().manual_seed(B + Z)
+    emb = torch.randn(B, T, 64, generator=g).to(dev).requires_grad_(True)
+    table = torch.randn(Z, 64, generator=g).to(dev).requires_grad_(True)
+    xy = torch.rand(Z, 2, generator=g)
+    dist = torch.cdist(xy, xy).to(dev)                      # [Z, Z] like the reference's dist_mat
+    y = torch.randint(0, Z, (B, T), generator=g).to(dev)
+    mask = (torch.rand(B, T, generator=g) < 0.35).to(dev)
+    y = torch.where(mask, y, torch.full_like(y, -1))
+    ce, ed = ab.ce_and_expected_distance_at_snaps_fused(emb, table, y, dist, mask, 0.2)
+    (1.0 * ce + 0.5 * ed).backward()                        # w_ce, w_dist of mode_sep/config.py:39-41
+    e2, t2 = emb.detach().double().requires_grad_(True), table.detach().double().requires_grad_(True)
+    logits = _ref_logits(e2, t2, 0.2)
+    ref_ce = F.cross_entropy(logits[mask], y[mask], reduction="mean")
+    probs = torch.softmax(logits, dim=-1)
+    ref_ed = (dist.double()[y.clamp(min=0)] * probs).sum(-1)[mask].mean()
+    (1.0 * ref_ce + 0.5 * ref_ed).backward()
+    assert abs(float(ce.detach()) - float(ref_ce)) < 1e-5 * abs(float(ref_ce))
+    assert abs(float(ed.detach()) - float(ref_ed)) < 2e-5 * abs(float(ref_ed))
+    for a, b in ((emb.grad, e2.grad), (table.grad, t2.grad)):
+        assert float((a.double() - b).abs().max()) < 1e-4 * float(b.abs().max())
