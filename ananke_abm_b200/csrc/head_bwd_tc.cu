@@ -92,6 +92,9 @@ __device__ __forceinline__ void hb_item(const HeadBwdArgs& a, int item, int& til
   c_end = (int)(((int64_t)(split + 1) * a.ny) / a.nsplit);
 }
 
+// ROWS: rows-outer pass (x = row, y = zone) or zones-outer; DIST: with the expected-distance term.  Both are template
+// parameters: the per-element epilogue is the kernel's limiter (16 instructions per element), runtime switches cost ~70 %.
+template <bool ROWS, bool DIST>
 __global__ void __launch_bounds__(HB_THREADS, 1) head_ce_bwd_kernel(const __grid_constant__ HeadBwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t full[HB_NS], empty[HB_NS], acc_full[2], acc_empty[2], x_full, x_free, ds_full, ds_free, dx_full, dx_empty;
@@ -207,10 +210,10 @@ __global__ void __launch_bounds__(HB_THREADS, 1) head_ce_bwd_kernel(const __grid
       const bool xvalid = xg < a.NX;
       float x_lse2 = 0.0f, x_g = 0.0f;
       int x_tgt = -1;
-      const bool want_d = a.dist != nullptr;
+      constexpr bool want_d = DIST;
       float x_g2 = 0.0f, x_e = 0.0f;
       const float* drow = nullptr;
-      if (a.rows_outer && xvalid) {
+      if (ROWS && xvalid) {
         x_lse2 = a.lse[xg] * 1.4426950408889634f; x_g = a.g[xg] * a.inv_tau; x_tgt = (int)a.target[xg];
         if (want_d) {
           x_g2 = a.g2[xg] * a.inv_tau; x_e = a.edist[xg];
@@ -222,7 +225,7 @@ __global__ void __launch_bounds__(HB_THREADS, 1) head_ce_bwd_kernel(const __grid
       for (int c = c_begin; c < c_end; ++c, ++nseq) {
         const int buf = nseq & 1;
         const int64_t ybase = (int64_t)c * HB_T;
-        if (!a.rows_outer) {          // per-row quantities of this Y chunk -> shared memory (read by every x thread)
+        if (!ROWS) {          // per-row quantities of this Y chunk -> shared memory (read by every x thread)
           if (et < HB_T) {
             const int64_t yr = ybase + et;
             const bool yv = yr < a.NY;
@@ -241,9 +244,25 @@ __global__ void __launch_bounds__(HB_THREADS, 1) head_ce_bwd_kernel(const __grid
           uint32_t r[32], hi[16], lo[16];
           tmem_ld32(tmem + lane_sel + HB_C_S + (uint32_t)(buf * HB_T + c0), r);
           tmem_ld_wait();
-          const int t_loc = a.rows_outer ? x_tgt - (int)ybase - c0 : 0;          // column of the target inside this group
+          const int t_loc = ROWS ? x_tgt - (int)ybase - c0 : 0;          // column of the target inside this group
           const int lim = n_valid - c0;                                          // columns < lim are valid
           const bool all_valid = lim >= 32;                                      // uniform: only the last chunk is ragged
+          float dd[32];
+          if (ROWS && want_d) {
+            const bool vec = all_valid && (a.Z & 3) == 0 && drow != nullptr;
+            if (vec) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float4 t4 = __ldg(reinterpret_cast<const float4*>(drow + ybase + c0) + q);
+                dd[4 * q] = t4.x; dd[4 * q + 1] = t4.y; dd[4 * q + 2] = t4.z; dd[4 * q + 3] = t4.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) dd[j] = (drow != nullptr && j < lim) ? __ldg(drow + ybase + c0 + j) : 0.0f;
+            }
+          }
+          int prev_t = -2;            // zones-outer: consecutive rows of a target-sorted chunk share dist[target, zone]
+          float prev_d = 0.0f;
 #pragma unroll
           for (int jj = 0; jj < 16; ++jj) {
             float d[2];
@@ -252,18 +271,22 @@ __global__ void __launch_bounds__(HB_THREADS, 1) head_ce_bwd_kernel(const __grid
               const int j = 2 * jj + u;
               const float L = __uint_as_float(r[j]);
               float v;
-              if (a.rows_outer) {
+              if (ROWS) {
                 const float p = ex2_fast(fmaf(L, sc2, -x_lse2));
                 v = x_g * (p - (j == t_loc ? 1.0f : 0.0f));
-                if (want_d && drow != nullptr && j < lim) v = fmaf(x_g2 * p, __ldg(drow + ybase + c0 + j) - x_e, v);
+                if (want_d) v = fmaf(x_g2 * p, dd[j] - x_e, v);
                 if (!all_valid) v = j < lim ? v : 0.0f;
               } else {
                 const float p = ex2_fast(fmaf(L, sc2, -y_lse2[buf][c0 + j]));
                 const int yt = y_tgt[buf][c0 + j];
                 v = y_g[buf][c0 + j] * (p - (yt == xi ? 1.0f : 0.0f));
                 if (want_d && xvalid) {
-                  const int tc = (yt < 0 || yt >= a.Z) ? 0 : yt;
-                  v = fmaf(y_g2[buf][c0 + j] * p, __ldg(a.dist + (size_t)tc * a.Z + xi) - y_e[buf][c0 + j], v);
+                  if (yt != prev_t) {            // uniform across the warp (yt comes from shared memory)
+                    const int tc = (yt < 0 || yt >= a.Z) ? 0 : yt;
+                    prev_d = __ldg(a.dist + (size_t)tc * a.Z + xi);
+                    prev_t = yt;
+                  }
+                  v = fmaf(y_g2[buf][c0 + j] * p, prev_d - y_e[buf][c0 + j], v);
                 }
               }
               d[u] = v;
@@ -361,8 +384,11 @@ int head_ce_backward(const float* emb, const float* table, const int64_t* target
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  e = cudaFuncSetAttribute(head_ce_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HB_SMEM);
-  if (e != cudaSuccess) { set_cuda_error(e); return AB200_ERR_CUDA; }
+  for (const void* fn : {(const void*)head_ce_bwd_kernel<true, true>, (const void*)head_ce_bwd_kernel<true, false>,
+                         (const void*)head_ce_bwd_kernel<false, true>, (const void*)head_ce_bwd_kernel<false, false>}) {
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HB_SMEM);
+    if (e != cudaSuccess) { set_cuda_error(e); return AB200_ERR_CUDA; }
+  }
   float* partial = (float*)((uint8_t*)status + 256);
   auto pass = [&](const uint8_t* ximg, const uint8_t* yimg, int nx, int ny, int64_t NX, int64_t NY, int rows_outer, int y_lo_seg,
                   float* dx) -> int {
@@ -371,7 +397,15 @@ int head_ce_backward(const float* emb, const float* table, const int64_t* target
     if (ns > ns_cap) ns = ns_cap;                      // never beyond what the workspace was sized for
     HeadBwdArgs k{ximg, yimg, nx, ny, NX, NY, rows_outer, y_lo_seg, lse, g_rows, target, g_dist_rows, exp_dist, dist, Z, 1.0f / tau, dx, partial, ns, status};
     const int items = nx * ns;
-    head_ce_bwd_kernel<<<items < sms ? items : sms, HB_THREADS, HB_SMEM, st>>>(k);
+    const int grid = items < sms ? items : sms;
+    const bool with_dist = dist != nullptr;
+    if (rows_outer) {
+      if (with_dist) head_ce_bwd_kernel<true, true><<<grid, HB_THREADS, HB_SMEM, st>>>(k);
+      else head_ce_bwd_kernel<true, false><<<grid, HB_THREADS, HB_SMEM, st>>>(k);
+    } else {
+      if (with_dist) head_ce_bwd_kernel<false, true><<<grid, HB_THREADS, HB_SMEM, st>>>(k);
+      else head_ce_bwd_kernel<false, false><<<grid, HB_THREADS, HB_SMEM, st>>>(k);
+    }
     int r = check_launch();
     if (r || ns == 1) return r;
     head_reduce_splits_kernel<<<sms * 4, 256, 0, st>>>(partial, ns, (int64_t)nx * HB_T, NX, dx);

@@ -192,6 +192,7 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_argmax_kernel(const __grid
       int i1 = 0, i2 = 0;
       bool dead = false;
       const bool ce = a.lse != nullptr;
+      const bool need_top = a.labels != nullptr || a.best != nullptr;      // pure loss evaluation skips the top-2 tracking
       const float sc2 = a.inv_tau * 1.4426950408889634f;     // logits in log2 units
       float run_m = -INFINITY, run_s = 0.0f;                 // running max (cosine units) and sum of exp(logit - max)
       float run_d = 0.0f;                                    // sum of exp(logit - max) * dist[target, z]
@@ -213,13 +214,34 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_argmax_kernel(const __grid
           tmem_ld32(tmem + lane_sel + (uint32_t)(buf * HD_TN + c0), r);
           tmem_ld_wait();
           float mx = -INFINITY;
+          if (zbase + c0 + 32 <= a.Z) {        // whole group valid (all but the table's last chunk)
 #pragma unroll
-          for (int j = 0; j < 32; ++j) mx = fmaxf(mx, (zbase + c0 + j < a.Z) ? __uint_as_float(r[j]) : -INFINITY);
+            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(r[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, (zbase + c0 + j < a.Z) ? __uint_as_float(r[j]) : -INFINITY);
+          }
           if (ce && mx > -INFINITY) {       // streaming log-sum-exp over the zones (split-bf16 logits: ~2^-16 relative)
             if (mx > run_m) { const float f = exp2f((run_m - mx) * sc2); run_s *= f; run_d *= f; run_m = mx; }
             const float off = -run_m * sc2;
             if (want_d) {       // same sweep, weighted by the target's distance row (rows sorted by target share it: L1 hits)
               float pd[4] = {0.0f, 0.0f, 0.0f, 0.0f}, ps[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+              if (zbase + c0 + 32 <= a.Z && (a.Z & 3) == 0) {      // whole group valid, distance row 16-byte aligned
+                float4 dv[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                  dv[q] = drow != nullptr ? __ldg(reinterpret_cast<const float4*>(drow + zbase + c0) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  const float dd[4] = {dv[q].x, dv[q].y, dv[q].z, dv[q].w};
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                    const float e = ex2_approx(fmaf(__uint_as_float(r[4 * q + u]), sc2, off));
+                    ps[u] += e;
+                    pd[u] = fmaf(e, dd[u], pd[u]);
+                  }
+                }
+              } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
                 const int z = zbase + c0 + j;
@@ -228,6 +250,7 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_argmax_kernel(const __grid
                   ps[j & 3] += e;
                   pd[j & 3] = fmaf(e, drow != nullptr ? __ldg(drow + z) : 0.0f, pd[j & 3]);
                 }
+              }
               }
               run_s += (ps[0] + ps[1]) + (ps[2] + ps[3]);
               run_d += (pd[0] + pd[1]) + (pd[2] + pd[3]);
@@ -244,7 +267,7 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_argmax_kernel(const __grid
             run_s += (part[0] + part[1]) + (part[2] + part[3]);
             }
           }
-          if (mx > b2) {        // rare after the first chunks: only then look at the individual columns
+          if (need_top && mx > b2) {        // per lane rare after the first chunks, but a warp enters when ANY of its rows does
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const int z = zbase + c0 + j;
