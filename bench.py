@@ -386,7 +386,7 @@ def run_ours(args):
         "metric": METRIC + (" fwd+bwd" if train else " fwd (inference)"), "value": value, "unit": "agent-steps/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32" if args.precision == "f32" else ("fp16 fwd / bf16 bwd operands (fp32 accumulate, fp32 state)" if train else "bf16 (fp32 accumulate, fp32 state)"), "data": "synthetic",
+        "dtype": "f32" if args.precision == "f32" else ("fp16 fwd / bf16 bwd operands (fp32 accumulate, fp32 state)" if train else "fp16 operands on tcgen05 (fp32 accumulate, fp32 state)"), "data": "synthetic",
         "config": {"workload": cfg["name"], "agents_per_gpu": B, "zones": cfg["Z"], "time_points": T, "solver": cfg["method"],
                    "agent_chunk": chunk, "precision": args.precision, "loss": (args.loss if train else None),
                    "solver_steps": ({"accepted_per_trajectory": steps_counted["accepted"] / max(1, args.steps * ((B + chunk - 1) // chunk)),
