@@ -408,7 +408,7 @@ def run_ours(args):
         "gpu_launches": args.steps * launches_per_step,
         "clocks": clocks,
     }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # the CPU leg is timed on rank 0 at N = 1 only (torchrun pins OMP threads)
         out["cpu_baseline"] = cpu_baseline(cfg, train, budget_s=20.0)
     print(json.dumps(out))
     if world > 1:
