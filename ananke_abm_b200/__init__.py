@@ -17,6 +17,7 @@ from .latent_ode import GenerativeODE, GenerativeODEConfig  # noqa: F401
 from .batching import UnionBatch, build_union_batch, unify_and_interpolate_batch  # noqa: F401
 from .losses import ce_and_expected_distance_at_snaps_fused, ce_at_snaps_fused, head_ce_rows, head_loss_rows  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
+from .sdeint import sdeint  # noqa: F401
 from . import inference, run, batching, latent_ode, stage  # noqa: F401
 
 __version__ = "0.1.0"

@@ -52,6 +52,7 @@ SIGNATURES = {
     "ab200_rk_stage_combine": (C.c_int, [_vp, _vp, _vp, _i32, _f32, _vp, _i64, _vp]),
     "ab200_rk_combine_errnorm": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _f32, _f32, _f32, _vp, _vp, _i64, _vp]),
     "ab200_head_workspace_bytes": (_sz, [_i32, _i32]),
+    "ab200_sde_euler_step": (C.c_int, [_vp, _vp, _vp, _i32, _i64, _i32, _f32, C.c_uint64, C.c_uint64, _vp, _vp, _vp]),
     "ab200_grad_sumsq": (C.c_int, [_vp, _i64, _vp, _vp]),
     "ab200_adam_step": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _i32, _f32, _vp, _vp]),
     "ab200_head_argmax": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _f32, _vp, _vp, _vp, _sz, _vp]),

@@ -74,6 +74,8 @@ int pv_combine_bwd(const ab200_drift_desc* d, const float* g, int n_a, float cpv
 
 int rows_transpose(const float* src, float* dst, int64_t B, int F, int mode, cudaStream_t st);
 
+int sde_euler_step(const float* y, const float* f, const float* g, int g_per_row, int64_t B, int D, float dt, uint64_t seed,
+                   uint64_t step, float* y_out, float* xi_out, cudaStream_t st);
 int grad_sumsq(const float* g, int64_t n, double* out, cudaStream_t st);
 int adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps, float wd, int step,
               float max_norm, const double* sumsq, cudaStream_t st);
@@ -342,6 +344,12 @@ int ab200_pv_combine_backward(const ab200_drift_desc* d, const float* g, int32_t
                               ab200_stream_t stream) {
   if (!desc_ok(d) || !g || !G_y0 || B <= 0 || (n_a > 0 && (!G_a || !cpa_host || !cva_host))) return AB200_ERR_BAD_ARG;
   return pv_combine_bwd(d, g, n_a, cpv, cpa_host, cva_host, B, G_y0, G_a, accumulate, (cudaStream_t)stream);
+}
+
+int ab200_sde_euler_step(const float* y, const float* drift, const float* diffusion, int32_t diffusion_per_row, int64_t B, int32_t D,
+                         float dt, uint64_t seed, uint64_t step, float* y_out, float* xi_out, void* stream) {
+  if (!y || !drift || !diffusion || !y_out || B <= 0 || D <= 0 || !(dt > 0.0f)) return AB200_ERR_BAD_ARG;
+  return sde_euler_step(y, drift, diffusion, diffusion_per_row, B, D, dt, seed, step, y_out, xi_out, (cudaStream_t)stream);
 }
 
 int ab200_grad_sumsq(const float* flat_grad, int64_t n, double* sumsq_out, void* stream) {

@@ -6,7 +6,8 @@ Mirrors /root/reference/src/ananke_abm/models/latent_ode/architecture/model.py:9
 latent_ode/config.py:18-71.  Same `state_dict` keys, so checkpoints are interchangeable.  The encoder / decoders /
 einsum head are host-side PyTorch plumbing; every drift evaluation and all solver algebra inside `odeint` run in
 libananke_b200.so (`ab200_drift_eval` with the closed-form correction term, `ab200_rk_combine_errnorm`).
-The SDE branch (`enable_sde=True`, the reference default) is out of scope: this mirror runs the ODE
+The SDE branch (`enable_sde=True`, the reference default) runs forward-only (Euler-Maruyama sampling, `sdeint.py`); training
+runs the ODE
 branch and raises if asked for the SDE.  `zone_embed` may be a `gnn_embed.GATEmbed`: the slot a GAT fills (:171-173).
 """
 from __future__ import annotations
@@ -64,6 +65,17 @@ class ODEFunc(nn.Module):                   # model.py:19-117 -- parameter holde
             raise RuntimeError("drift shape not instantiated in libananke_b200.so")
         return drift_eval(spec, spec.flat_params().detach(), float(t), y)
 
+    # torchsde interface of the reference (model.py:119-130): noise on the state only, none on the context h
+    noise_type, sde_type = "diagonal", "ito"
+
+    def f(self, t, y):
+        return self.forward(t, y)
+
+    def g(self, t, y):
+        noise = y.new_zeros(y.shape)
+        noise[:, : self.state_dim] = self.config.sde_noise_strength
+        return noise
+
 
 class GenerativeODE(nn.Module):
     def __init__(self, person_feat_dim: int, num_zone_features: int, config: GenerativeODEConfig,
@@ -86,8 +98,6 @@ class GenerativeODE(nn.Module):
         """`eps` fixes the h0 reparameterisation noise (model.py:181 draws `randn_like`); extra keyword arguments
         (rtol, atol) go to `odeint` -- the reference uses torchdiffeq's defaults."""
         cfg = self.config
-        if cfg.enable_sde:
-            raise NotImplementedError("the SDE branch is out of scope (SURVEY.md §8f-4); set enable_sde=False")
         cand = self.zone_feature_encoder(all_zone_features)
         home = self.zone_feature_encoder(home_zone_features)
         work = self.zone_feature_encoder(work_zone_features)
@@ -98,7 +108,14 @@ class GenerativeODE(nn.Module):
         p0 = torch.cat([home, initial_purpose_features, initial_mode_features], dim=-1)
         s0 = torch.cat([p0, torch.zeros_like(p0)], dim=-1)
         y0 = torch.cat([s0, h0], dim=-1)
-        path = odeint(self.ode_func, y0, times, method=cfg.ode_method, options={"dtype": torch.float32}, **odeint_kwargs)
+        if cfg.enable_sde:
+            # model.py:192-194: sdeint(self.ode_func, y0, times, method='euler', dt=0.01).  Forward only here: sdeint
+            # refuses calls that need gradients (the reference trains through it; that backward is not built)
+            from .sdeint import sdeint
+            path = sdeint(self.ode_func, y0, times, method="euler", dt=0.01, options={"dtype": torch.float32},
+                          seed=odeint_kwargs.pop("seed", None))
+        else:
+            path = odeint(self.ode_func, y0, times, method=cfg.ode_method, options={"dtype": torch.float32}, **odeint_kwargs)
         pred_y = path.permute(1, 0, 2)
         pred_s, _ = torch.split(pred_y, [self.state_dim, cfg.hidden_dim], dim=-1)
         pred_p = torch.split(pred_s, self.position_dim, dim=-1)[0]

@@ -36,6 +36,8 @@ class ModeSepConfig:                       # mode_sep/config.py:9-71 (fields the
     time_match_tol: float = 1e-6
     enable_sde: bool = False
     sde_noise_strength: float = 0.01
+    sde_method: str = "euler"              # config.py:34-35
+    sde_dt: float = 0.01
     softmax_tau: float = 0.2
     precision: str = "f32"                 # ananke_b200 extension: 'f32' | 'bf16' (tensor-core drift GEMMs)
     error_norm: str = "shard"              # dopri5 across ranks: 'global' = one RMS norm over all shards (single-process parity)
@@ -71,6 +73,29 @@ class WrappedSDE(nn.Module):               # model.py:49-73 -- f(t, y) = [v, net
             raise RuntimeError("drift shape not instantiated in libananke_b200.so")
         return drift_eval(spec, spec.flat_params().detach(), float(t), y)
 
+    # torchsde interface of the reference (model.py:75-89): drift f = forward, unit diagonal diffusion on [p, v] only
+    def f(self, t: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        return self.forward(t, y)
+
+    def g(self, t: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        noise = y.new_zeros(y.shape)
+        noise[:, : 2 * self.emb_dim] = 1.0
+        return noise
+
+
+class _ScaledSDE(nn.Module):               # model.py:160-174: diffusion scaled by config.sde_noise_strength
+    noise_type, sde_type = "diagonal", "ito"
+
+    def __init__(self, base: WrappedSDE, scale: float):
+        super().__init__()
+        self.base, self.scale = base, scale
+
+    def f(self, t, y):
+        return self.base.f(t, y)
+
+    def g(self, t, y):
+        return self.base.g(t, y) * self.scale
+
 
 class ModeSepModel(nn.Module):
     def __init__(self, Z: int, config: ModeSepConfig):
@@ -96,7 +121,10 @@ class ModeSepModel(nn.Module):
 
     def integrate(self, y0: torch.Tensor, times_union: torch.Tensor) -> torch.Tensor:
         if self.config.enable_sde and self.config.sde_noise_strength > 0.0:
-            raise NotImplementedError("the SDE branch is out of scope (SURVEY.md §8f-4)")
+            # model.py:158-182: Euler-Maruyama sampling (forward only here; sdeint refuses calls that need gradients)
+            from .sdeint import sdeint
+            return sdeint(_ScaledSDE(self.odefunc, self.config.sde_noise_strength), y0, times_union,
+                          method=self.config.sde_method, dt=self.config.sde_dt, seed=getattr(self.config, "sde_seed", None))
         # config.adjoint (not a reference field): go through the odeint_adjoint seam (latent_ode/architecture/ode_components.py:50)
         solve = odeint_adjoint if getattr(self.config, "adjoint", False) else odeint
         return solve(self.odefunc, y0, times_union, method=self.config.ode_method, rtol=self.config.rtol,

@@ -232,6 +232,15 @@ int ab200_pv_combine_backward(const ab200_drift_desc* d, const float* g, int32_t
                               const float* cva_host, int64_t B, float* G_y0, float* const* G_a, int32_t accumulate,
                               ab200_stream_t stream);
 
+/* ---- SDE branch: one Euler-Maruyama step ----------------------------------------------------------------------
+ * y_out = y + drift * dt + diffusion * sqrt(dt) * xi,  xi ~ N(0, 1): the step of torchsde's `sdeint(..., method="euler")`
+ * for diagonal Ito noise (latent_ode/architecture/model.py:119-130,192-194; mode_sep/architecture/model.py:79-89,158-182).
+ * diffusion is [D] (diffusion_per_row = 0) or [B][D].  The noise is counter-based (Philox4x32-10 keyed by `seed`,
+ * counter = (element group, step); Box-Muller), specified in csrc/sde_em.cu and restated in oracle/sde_oracle.py: an
+ * agent's noise does not depend on the batch it is in.  xi_out (may be NULL) receives the normals.  D % 4 == 0. */
+int ab200_sde_euler_step(const float* y, const float* drift, const float* diffusion, int32_t diffusion_per_row, int64_t B,
+                         int32_t D, float dt, uint64_t seed, uint64_t step, float* y_out, float* xi_out, void* stream);
+
 /* ---- optimiser step over the flat parameter / gradient buffers ----------------------------------------------------
  * Replaces  torch.nn.utils.clip_grad_norm_(params, max_norm) ; torch.optim.Adam(lr, weight_decay).step()
  * (mode_sep/train/train.py:68,163-164) on the flat fp32 buffer the NCCL gradient all-reduce already uses: two launches,

@@ -49,15 +49,24 @@ def test_generative_ode_forward_matches_golden(golden_latent):
     assert abs(st.n_accepted - int(g["n_accepted"])) <= max(3, int(g["n_accepted"]) // 10)
 
 
-def test_generative_ode_rejects_sde_branch():
+def test_generative_ode_sde_branch_samples_but_refuses_training():
+    """enable_sde=True (the reference default): forward-only Euler-Maruyama sampling; a call that needs gradients fails
+    loudly instead of silently training without the SDE."""
     import ananke_abm_b200 as ab
     dev = _cuda()
     cfg = ab.GenerativeODEConfig(enable_sde=True)
     m = ab.GenerativeODE(8, 7, cfg).to(dev)
     z = torch.zeros(2, 7, device=dev)
-    with pytest.raises(NotImplementedError):
-        m(torch.zeros(2, 8, device=dev), z, z, torch.zeros(2, 4, device=dev), torch.zeros(2, 4, device=dev),
-          torch.linspace(0, 1, 3, device=dev), torch.zeros(8, 7, device=dev))
+    args = (torch.zeros(2, 8, device=dev), z, z, torch.zeros(2, 4, device=dev), torch.zeros(2, 4, device=dev),
+            torch.linspace(0, 0.1, 3, device=dev), torch.zeros(8, 7, device=dev))
+    with pytest.raises(ab.Ab200Error):
+        m(*args)
+    with torch.no_grad():
+        out_a = m(*args, eps=torch.zeros(2, cfg.hidden_dim, device=dev), seed=5)
+        out_b = m(*args, eps=torch.zeros(2, cfg.hidden_dim, device=dev), seed=5)
+        out_c = m(*args, eps=torch.zeros(2, cfg.hidden_dim, device=dev), seed=6)
+    assert out_a[0].shape == (2, 3, 8) and torch.isfinite(out_a[1]).all()
+    assert torch.equal(out_a[1], out_b[1]) and not torch.equal(out_a[1], out_c[1])      # reproducible per seed
 
 
 def test_union_batch_on_device_matches_golden(golden_mode_sep):
