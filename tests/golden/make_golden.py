@@ -246,8 +246,35 @@ def rhs_fixture():
     print("rhs fixture written")
 
 
+def loss_terms_fixture():
+    """The reference's own loss functions (mode_sep/architecture/losses.py:14-44, unmodified) on the frozen fixture
+    logits: the terms the fused head reproduces from (pred_emb, class_table) -> loss_terms_fixture.npz."""
+    from ananke_abm.models.mode_sep.architecture.losses import ce_at_snaps, mse_at_snaps, expected_distance_at_snaps
+    g = np.load(HERE / "mode_sep_fixture.npz")
+    logits = torch.from_numpy(g["logits"])
+    pred_emb = torch.from_numpy(g["pred_emb"])
+    table = torch.from_numpy(g["sd_class_table"])
+    dist = torch.from_numpy(g["dist_mat"])
+    y_union, is_gt = torch.from_numpy(g["y_union"]), torch.from_numpy(g["ub_is_gt_union"])
+    y_stay, m_aux = torch.from_numpy(g["ub_stay_loc_ids"]), torch.from_numpy(g["ub_stay_non_gt_mask"])
+    out = {
+        "ce_gt": np.float64(ce_at_snaps(logits, y_union, is_gt).item()),
+        "dist_gt": np.float64(expected_distance_at_snaps(logits, y_union, dist, is_gt).item()),
+        "mse_gt": np.float64(mse_at_snaps(pred_emb, y_union, table, is_gt).item()),
+        "ce_aux": np.float64(ce_at_snaps(logits, y_stay, m_aux).item()),
+        "dist_aux": np.float64(expected_distance_at_snaps(logits, y_stay, dist, m_aux).item()),
+        "n_gt": np.int64(int(is_gt.sum())), "n_aux": np.int64(int(m_aux.sum())),
+    }
+    np.savez_compressed(HERE / "loss_terms_fixture.npz", **out)
+    print("loss terms fixture written", {k: float(v) for k, v in out.items()})
+
+
 if __name__ == "__main__":
     assert REF.exists(), "the reference tree is only present in the authoring container"
+    if len(sys.argv) > 1 and sys.argv[1] == "losses":       # only the loss terms (reads the frozen mode_sep fixture)
+        loss_terms_fixture()
+        sys.exit(0)
     mode_sep_fixture()
     latent_fixture()
     rhs_fixture()
+    loss_terms_fixture()

@@ -159,3 +159,25 @@ def test_ce_and_expected_distance_fused_match_reference_formulas(B, T, Z):
     assert abs(float(ed.detach()) - float(ref_ed)) < 2e-5 * abs(float(ref_ed))
     for a, b in ((emb.grad, e2.grad), (table.grad, t2.grad)):
         assert float((a.double() - b).abs().max()) < 1e-4 * float(b.abs().max())
+
+
+def test_fused_losses_match_the_unmodified_reference_on_the_fixture():
+    """tests/golden/loss_terms_fixture.npz holds ce_at_snaps / expected_distance_at_snaps evaluated by the UNMODIFIED
+    reference (mode_sep/architecture/losses.py) on the frozen fixture logits; the fused head must reproduce them from
+    (pred_emb, class_table) alone -- at the GT snaps and on the stay-aux mask (mode_sep/train/train.py:131-133)."""
+    import numpy as np
+    from pathlib import Path
+    import ananke_abm_b200 as ab
+    dev = _cuda()
+    gd = Path(__file__).parent / "golden"
+    g, lt = np.load(gd / "mode_sep_fixture.npz"), np.load(gd / "loss_terms_fixture.npz")
+    pred_emb = torch.from_numpy(g["pred_emb"]).to(dev)
+    table = torch.from_numpy(g["sd_class_table"]).to(dev)
+    dist = torch.from_numpy(g["dist_mat"]).float().to(dev)
+    for y_key, m_key, ce_key, d_key in (("y_union", "ub_is_gt_union", "ce_gt", "dist_gt"),
+                                        ("ub_stay_loc_ids", "ub_stay_non_gt_mask", "ce_aux", "dist_aux")):
+        y, mask = torch.from_numpy(g[y_key]).to(dev), torch.from_numpy(g[m_key]).to(dev)
+        ce, ed = ab.ce_and_expected_distance_at_snaps_fused(pred_emb, table, y, dist, mask, 0.2)
+        assert abs(float(ce) - float(lt[ce_key])) < 1e-5 * abs(float(lt[ce_key])), (ce_key, float(ce), float(lt[ce_key]))
+        assert abs(float(ed) - float(lt[d_key])) < 2e-5 * abs(float(lt[d_key])), (d_key, float(ed), float(lt[d_key]))
+        assert abs(float(ab.ce_at_snaps_fused(pred_emb, table, y, mask, 0.2)) - float(lt[ce_key])) < 1e-5 * abs(float(lt[ce_key]))
