@@ -268,14 +268,26 @@ __global__ void __launch_bounds__(HD_THREADS, 1) head_argmax_kernel(const __grid
             }
           }
           if (need_top && mx > b2) {        // per lane rare after the first chunks, but a warp enters when ANY of its rows does
+            // The group maximum is known: locate it (lowest column on ties), take the runner-up of the remaining columns,
+            // and merge the pair into the running top-2 -- the same result as a left-to-right scan with strict '>',
+            // at ~4 instead of ~8 instructions per column.
+            const int nv = min(32, a.Z - (zbase + c0));           // valid columns of this group (>= 1 here)
+            int jm = 0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int z = zbase + c0 + j;
-              const float v = __uint_as_float(r[j]);
-              if (z < a.Z) {
-                if (v > b1) { b2 = b1; i2 = i1; b1 = v; i1 = z; }
-                else if (v > b2) { b2 = v; i2 = z; }
-              }
+            for (int j = 31; j >= 0; --j)
+              if (j < nv && __uint_as_float(r[j]) == mx) jm = j;
+            float m2 = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) m2 = fmaxf(m2, (j != jm && j < nv) ? __uint_as_float(r[j]) : -INFINITY);
+            const int zm = zbase + c0 + jm;
+            if (mx > b1) { b2 = b1; i2 = i1; b1 = mx; i1 = zm; }
+            else { b2 = mx; i2 = zm; }
+            if (m2 > b2) {                  // rarer still: the group's runner-up qualifies too (it can only take second place)
+              int j2 = 0;
+#pragma unroll
+              for (int j = 31; j >= 0; --j)
+                if (j != jm && j < nv && __uint_as_float(r[j]) == m2) j2 = j;
+              b2 = m2; i2 = zbase + c0 + j2;
             }
           }
         }
