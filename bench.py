@@ -184,7 +184,10 @@ def run_ours(args):
         cfg["name"] = cfg["name"].replace("96 RK4 steps", "dopri5 rtol=atol=1e-5") if args.solver == "dopri5" else \
             cfg["name"].replace("dopri5 rtol=atol=1e-5", "96 RK4 steps")
     train = cfg["mode"] == "train"
-    chunk = min(cfg["B"], args.chunk)
+    # agents are processed in equal chunks of at most --chunk agents (whole 128-agent tiles): equal parts avoid a small,
+    # badly utilised tail chunk; the saved steps of ONE chunk live in HBM (peak_mem_gb in the JSON line)
+    n_parts = max(1, -(-cfg["B"] // args.chunk))
+    chunk = min(cfg["B"], -(-(-(-cfg["B"] // n_parts)) // 128) * 128)
     B, T = cfg["B"], cfg["T"]
     model, zfeat, csr = build_model(cfg, args.precision, dev)
     home, work, traits, t = make_inputs(cfg, seed=42 + rank)
@@ -406,6 +409,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / e2e_steps},
         "gpu_launches": args.steps * launches_per_step,
+        "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9,
         "clocks": clocks,
     }
     if not args.no_cpu_baseline and world == 1:      # the CPU leg is timed on rank 0 at N = 1 only (torchrun pins OMP threads)
@@ -497,8 +501,9 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["f32", "bf16"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--agents", type=int, default=0, help="override agents per GPU")
-    ap.add_argument("--chunk", type=int, default=189_440,
-                    help="agents per launch sequence; default = 5 x (148 SMs x 2 slots x 128 agents): whole waves of tiles")
+    ap.add_argument("--chunk", type=int, default=378_880,
+                    help="upper bound on agents per launch sequence (the batch is cut into equal parts no larger than this); "
+                         "378,880 = 10 x (148 SMs x 2 slots x 128 agents); dopri5 training keeps ~0.33 MB per agent of the chunk")
     ap.add_argument("--solver", default="", choices=["", "rk4", "dopri5"], help="override the workload's solver")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--loss", default="traj", choices=["traj", "ce"],
