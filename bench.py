@@ -343,8 +343,8 @@ def run_ours(args):
             kern_flop_unit = ALG_FLOP_FWD // 4 * 2    # recompute + dgrad of one stage (wgrad runs in wgrad_tc_kernel)
             kern_bytes_unit = ALG_BYTES_FWDBWD / 4.0
             # DRAM bytes per agent-stage of this kernel from `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum =
-            # 1.566 + 3.162 GB for a fused 4-stage launch over 189,440 agents; profiles/r01_fused_step_ncu_summary.txt)
-            kern_traffic_unit = (1.565723e9 + 3.162459e9) / (189440 * 4)
+            # 1.300 + 2.730 GB for a fused 4-stage launch over 189,440 agents; profiles/r01_fused_step_ncu_summary.txt)
+            kern_traffic_unit = (1.299641e9 + 2.729880e9) / (189440 * 4)
             del eng, yb, A, Gb, GX
         else:
             prec = {"f32": 0, "bf16": 1}[args.precision]
