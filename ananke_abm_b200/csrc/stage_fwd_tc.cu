@@ -77,7 +77,12 @@ int stage_flags() {
   static int f = -1;
   if (f < 0) {
     const char* e = getenv("AB200_STAGE_FLAGS");
-    f = e ? atoi(e) : 0;   // measured on B200: neither the issue mutex nor the bulk L2 prefetch pays (profiles/r01_stage_notes.md)
+    int v = e ? atoi(e) : 0;   // measured on B200: neither the issue mutex nor the bulk L2 prefetch pays (profiles/r01_stage_notes.md)
+    // bits 16 / 32 skip the backward kernel's stores (timing experiments, results INVALID): honoured only together with
+    // AB200_STAGE_TIMING_ONLY=1 so that a stray environment variable cannot silently corrupt gradients
+    const char* u = getenv("AB200_STAGE_TIMING_ONLY");
+    if (!(u && atoi(u) == 1)) v &= 15;
+    f = v;
   }
   return f;
 }

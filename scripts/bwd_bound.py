@@ -1,6 +1,6 @@
 """What bounds the fused backward stage launch?  Times rk4 forward and rk4 backward (8 steps, CUDA events) with the
-wgrad flush optionally disabled; run once per AB200_STAGE_FLAGS value (16 = no blob spill, 32 = no gx stores: timing
-experiments, results invalid).   python scripts/bwd_bound.py [B] [nowgrad]"""
+wgrad flush optionally disabled; run once per AB200_STAGE_FLAGS value with AB200_STAGE_TIMING_ONLY=1 (16 = no blob spill,
+32 = no gx stores: timing experiments, results invalid).   python scripts/bwd_bound.py [B] [nowgrad]"""
 import sys, torch
 sys.path.insert(0, '.')
 import ananke_abm_b200 as ab
