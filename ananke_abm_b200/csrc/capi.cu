@@ -46,6 +46,8 @@ int stage_fwd_tc(const ab200_drift_desc* d, const uint8_t* image, const float* y
                  int64_t B, float* a_out, float* y_out, double* err_sumsq, int half_ops, cudaStream_t st);
 int stage_fwd_tc_multi(const ab200_drift_desc* d, const uint8_t* image, const float* y0, const float* const* a_ptrs, const void* descs_v,
                        int n_stage, float* const* a_outs, int64_t B, float* y_out, double* err_sumsq, int half_ops, cudaStream_t st);
+int stage_fwd2_tc_multi(const ab200_drift_desc* d, const uint8_t* image, const float* y0, const float* const* a_ptrs, const void* descs_v,
+                        int n_stage, float* const* a_outs, int64_t B, float* y_out, double* err_sumsq, cudaStream_t st);
 int stage_bwd_tc(const ab200_drift_desc* d, const uint8_t* image, const float* y0, const float* const* a_ptrs, const void* desc_v,
                  int64_t B, const float* g_base, const float* const* gx_ptrs, int n_g, const float* dp, const float* dv, float* gx_out,
                  void* spill, int blob0, int nblobs, float* g_bout, cudaStream_t st);
@@ -234,7 +236,11 @@ int ab200_stage_forward(const ab200_drift_desc* d, const void* image, const floa
                         int32_t operand_format, ab200_stream_t stream) {
   if (!d || !image || !y0 || !s || B <= 0 || (s->n_a > 0 && !a)) return AB200_ERR_BAD_ARG;
   if (!stage_shape_ok(d)) return AB200_ERR_UNSUPPORTED;
-  if ((err_sumsq && !y_out) || operand_format < 0 || operand_format > 1) return AB200_ERR_BAD_ARG;
+  if ((err_sumsq && !y_out) || operand_format < 0 || operand_format > 2) return AB200_ERR_BAD_ARG;
+  if (operand_format == 2) {
+    float* outs[1] = {a_out};
+    return stage_fwd2_tc_multi(d, (const uint8_t*)image, y0, a, s, 1, outs, B, y_out, err_sumsq, (cudaStream_t)stream);
+  }
   return stage_fwd_tc(d, (const uint8_t*)image, y0, a, s, B, a_out, y_out, err_sumsq, operand_format, (cudaStream_t)stream);
 }
 
@@ -243,7 +249,9 @@ int ab200_stage_forward_fused(const ab200_drift_desc* d, const void* image, cons
                               double* err_sumsq, int32_t operand_format, ab200_stream_t stream) {
   if (!d || !image || !y0 || !stages || !a || B <= 0 || n_stage < 1 || n_stage > AB200_STAGE_MAX_A) return AB200_ERR_BAD_ARG;
   if (!stage_shape_ok(d)) return AB200_ERR_UNSUPPORTED;
-  if ((err_sumsq && !y_out) || operand_format < 0 || operand_format > 1) return AB200_ERR_BAD_ARG;
+  if ((err_sumsq && !y_out) || operand_format < 0 || operand_format > 2) return AB200_ERR_BAD_ARG;
+  if (operand_format == 2)
+    return stage_fwd2_tc_multi(d, (const uint8_t*)image, y0, a, stages, n_stage, a_out, B, y_out, err_sumsq, (cudaStream_t)stream);
   return stage_fwd_tc_multi(d, (const uint8_t*)image, y0, a, stages, n_stage, a_out, B, y_out, err_sumsq, operand_format,
                             (cudaStream_t)stream);
 }

@@ -385,7 +385,7 @@ int stage_bwd_tc_multi(const ab200_drift_desc* d, const uint8_t* image, const fl
   k.B = B;
   k.nblobs = nblobs;
   k.flags = stage_flags();
-  k.status = reinterpret_cast<int*>(const_cast<uint8_t*>(image) + 2 * IMG_STRIDE);
+  k.status = stage_status_ptr(image);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -87,11 +87,13 @@ int stage_flags() {
   return f;
 }
 
-size_t stage_tc_image_bytes() { return 2 * IMG_STRIDE + 256; }   // bf16 image, fp16 image, status word
+size_t stage_tc_image_bytes() { return STATUS_OFFSET + 256; }   // bf16 image, fp16 image, split-activation image + table, status word
 
 int stage_tc_pack(const float* w_flat, uint8_t* image, cudaStream_t st) {
   stage_pack_kernel<false><<<148, 256, 0, st>>>(w_flat, image);
   stage_pack_kernel<true><<<148, 256, 0, st>>>(w_flat, image + IMG_STRIDE);
+  const int rc = stage_fwd2_pack(w_flat, image + IMG2_OFFSET, st);
+  if (rc) return rc;
   return check_launch();
 }
 
@@ -305,6 +307,7 @@ __global__ void __launch_bounds__(THREADS, 1) stage_fwd_tc_kernel(const __grid_c
   if (a.err_sumsq != nullptr && threadIdx.x == 0) {
     double s = 0.0;
     for (int i = 0; i < THREADS / 32; ++i) s += err_red[i];
+    if (*reinterpret_cast<volatile int*>(a.status) != 0) s = __longlong_as_double(0x7ff8000000000000LL);   // a bounded wait expired: poison the norm
     atomicAdd(a.err_sumsq, s);
   }
 }
@@ -357,7 +360,7 @@ int stage_fwd_tc_multi(const ab200_drift_desc* d, const uint8_t* image, const fl
   k.B = B;
   k.ntiles = (int)((B + TM - 1) / TM);
   k.flags = stage_flags();
-  k.status = reinterpret_cast<int*>(const_cast<uint8_t*>(image) + 2 * IMG_STRIDE);
+  k.status = stage_status_ptr(image);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -277,6 +277,7 @@ __device__ __forceinline__ void prefetch_rows_l2(const float* base, int tile, in
 constexpr int YF4 = D / 4, AF4 = P / 4;       // float4 groups per row of a state / an acceleration buffer
 
 // setup shared by the kernels: weights -> smem (one bulk copy engine transfer), TMEM, barriers.
+template <uint32_t IMG_BYTES = W_BYTES>
 __device__ __forceinline__ SlotCtx stage_setup(uint8_t* smem, const uint8_t* wimg, uint64_t* bars, uint32_t* tmem_base_s,
                                                int* lock, int* status, int flags) {
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -287,9 +288,9 @@ __device__ __forceinline__ SlotCtx stage_setup(uint8_t* smem, const uint8_t* wim
     mbar_init(&bars[1], 1);
     mbar_init(&bars[2], 1);
     mbar_fence_init();
-    constexpr uint32_t CH = 52736;             // W_BYTES / 4, multiple of 16
-    static_assert(CH * 4 == W_BYTES, "image chunking");
-    mbar_arrive_expect_tx(&bars[2], W_BYTES);
+    constexpr uint32_t CH = IMG_BYTES / 4;     // 52,736 for the extended image; multiple of 16
+    static_assert(CH * 4 == IMG_BYTES && CH % 16 == 0, "image chunking");
+    mbar_arrive_expect_tx(&bars[2], IMG_BYTES);
 #pragma unroll
     for (int i = 0; i < 4; ++i) bulk_g2s(smem + i * CH, wimg + i * CH, CH, &bars[2]);
   }
@@ -334,6 +335,13 @@ int stage_flags();
 // host entry points (stage_fwd_tc.cu / stage_bwd_tc.cu / wgrad_tc.cu)
 size_t stage_tc_image_bytes();
 int stage_tc_pack(const float* w_flat, uint8_t* image, cudaStream_t st);
-constexpr size_t IMG_STRIDE = (stc::W_BYTES + 255) / 256 * 256;   // bf16 image at 0, fp16 image at IMG_STRIDE, status word after both
+constexpr size_t IMG_STRIDE = (stc::W_BYTES + 255) / 256 * 256;   // bf16 image at 0, fp16 image at IMG_STRIDE
+// Third image (stage_fwd2_tc.cu, the split-activation forward kernel): fp16 matrices WITHOUT K extensions followed by an
+// fp32 table of the time-feature columns and biases (applied in fp32 by the epilogue); the status word follows it.
+constexpr size_t IMG2_OFFSET = 2 * IMG_STRIDE;
+constexpr size_t IMG2_BYTES = 192256;                              // stage_fwd2_tc.cu: f2::IMG_BYTES (static_assert there)
+constexpr size_t STATUS_OFFSET = IMG2_OFFSET + IMG2_BYTES;         // multiple of 256
+inline int* stage_status_ptr(const uint8_t* image) { return reinterpret_cast<int*>(const_cast<uint8_t*>(image) + STATUS_OFFSET); }
+int stage_fwd2_pack(const float* w_flat, uint8_t* image2, cudaStream_t st);
 
 }  // namespace ab200

@@ -47,6 +47,8 @@ def _solver_options(config) -> dict:
     opt = {"precision": getattr(config, "precision", "f32")}
     if config.ode_method == "dopri5" and opt["precision"] == "bf16":
         opt["error_norm"] = getattr(config, "error_norm", "shard")
+        if getattr(config, "forward_operands", None):       # "fp16x2" (default of the solver) | "fp16" | "bf16"
+            opt["forward_operands"] = config.forward_operands
     return opt
 
 

@@ -107,6 +107,11 @@ class _FusedRK4(torch.autograd.Function):
         rc = L.ab200_rk4_forward(C.byref(spec.desc), wc.data_ptr(), y0c.data_ptr(), tc.data_ptr(), th.data_ptr(), B, T,
                                  y_path.data_ptr(), ws.data_ptr(), ws.numel(), precision, _stream_ptr())
         _lib.check(rc, "ab200_rk4_forward")
+        if precision == _lib.PREC_BF16:
+            # the tensor-core trajectory kernel keeps a status word in the last 256 bytes of its workspace: a bounded barrier
+            # wait that expired means the trajectory is garbage (one 4-byte host read per solve)
+            if int(ws[ws.numel() - 256:ws.numel() - 252].view(torch.int32).item()) != 0:
+                raise _lib.Ab200Error("rk4 tensor-core kernel: barrier wait timed out, results discarded")
         ctx.spec, ctx.precision = spec, precision
         ctx.save_for_backward(tc, wc, y_path)
         return y_path
@@ -172,6 +177,9 @@ class _StageDopri5TC(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_y_path):
         from . import stage
+        if ctx.steps is None:
+            raise RuntimeError("dopri5 (tensor-core stage path): the saved steps were freed by the first backward pass; "
+                               "a second backward through the same solve is not supported (re-run the forward)")
         gy0, gw = stage.dopri5_backward(ctx.eng, ctx.steps, grad_y_path.contiguous().float())
         ctx.steps = None
         return gy0, None, gw, None, None, None, None, None
@@ -439,7 +447,7 @@ def odeint(func, y0, t, *, rtol: float = 1e-7, atol: float = 1e-9, method: Optio
         if (spec is not None and y0.shape[1] == spec.state_dim and precision == _lib.PREC_BF16 and spec.tc_stage_supported()
                 and y0.dtype == torch.float32):
             opts = {}
-            for k_ in ("first_step", "safety", "ifactor", "dfactor", "max_num_steps", "fp16_forward", "error_norm", "group"):
+            for k_ in ("first_step", "safety", "ifactor", "dfactor", "max_num_steps", "fp16_forward", "forward_operands", "error_norm", "group"):
                 if k_ in options:
                     opts[k_] = options.pop(k_)
             opts["time_dtype"] = torch.promote_types(options.pop("dtype", torch.float64), torch.float32)

@@ -25,6 +25,21 @@ from .drift import DriftSpec
 
 MAX_A = 7
 TM = 128
+FWD_FORMATS = {"bf16": 0, "fp16": 1, "fp16x2": 2}
+
+
+def fwd_format_code(v) -> int:
+    """operand format of the forward stage kernels from a name, a code, or the legacy fp16_forward bool"""
+    if isinstance(v, str):
+        if v not in FWD_FORMATS:
+            raise ValueError(f"unknown forward operand format {v!r}; choose from {sorted(FWD_FORMATS)}")
+        return FWD_FORMATS[v]
+    if isinstance(v, bool):
+        return 1 if v else 0
+    v = int(v)
+    if v not in (0, 1, 2):
+        raise ValueError(f"unknown forward operand format code {v}")
+    return v
 
 
 class StageDesc(C.Structure):
@@ -128,10 +143,11 @@ class TcEngine:
         self._img_status, self._part_status = int(off_i.value), int(off_p.value)
         self.P, self.H = self.desc.pos_dim, self.desc.ctx_dim
         self.D = 2 * self.P + self.H
-        # forward stage evaluations use IEEE fp16 operands (values of this net stay far inside the fp16 range): 8x less
-        # rounding noise than bf16 at the same speed -- trajectories 4x closer to fp32 and an adaptive error estimate that is
-        # not noise-limited at rtol = atol = 1e-5.  Backward kernels keep bf16 (gradient range).
-        self.fp16_forward = True
+        # forward stage evaluations: operand format of ab200_stage_forward* (FWD_FORMATS).  "fp16" = IEEE fp16 operands
+        # (values of this net stay far inside the fp16 range; 8x less rounding noise than bf16 at the same speed);
+        # "fp16x2" = fp16 weights, activations as two-term fp16 splits: no activation rounding at all, which is what the
+        # embedded error estimate of an adaptive solver needs (dopri5_forward selects it).  Backward kernels keep bf16.
+        self.fwd_format = FWD_FORMATS["fp16"]
 
     # ---- forward ------------------------------------------------------------------------------------
     def stage_forward(self, y0, a: Sequence[torch.Tensor], cin: Combo, t: float, B: int, a_out=None, y_out=None, cout: Optional[Combo] = None,
@@ -154,7 +170,7 @@ class TcEngine:
                                         C.byref(s), B, None if a_out is None else a_out.data_ptr(),
                                         None if y_out is None else y_out.data_ptr(),
                                         None if err_sumsq is None else err_sumsq.data_ptr(),
-                                        1 if (self.fp16_forward if fp16 is None else fp16) else 0, _stream())
+                                        self.fwd_format if fp16 is None else fwd_format_code(fp16), _stream())
         _lib.check(rc, "ab200_stage_forward")
 
     def stage_forward_fused(self, y0, a_bufs: Sequence[torch.Tensor], stages: Sequence, B: int, y_out=None, cout: Optional[Combo] = None,
@@ -189,7 +205,7 @@ class TcEngine:
                                               C.cast(descs, C.c_void_p), n, C.cast(outs, C.c_void_p), B,
                                               None if y_out is None else y_out.data_ptr(),
                                               None if err_sumsq is None else err_sumsq.data_ptr(),
-                                              1 if (self.fp16_forward if fp16 is None else fp16) else 0, _stream())
+                                              self.fwd_format if fp16 is None else fwd_format_code(fp16), _stream())
         _lib.check(rc, "ab200_stage_forward_fused")
 
     def combine(self, y0, a: Sequence[torch.Tensor], c: Combo, B: int, out) -> None:
@@ -348,10 +364,13 @@ class TcEngine:
         _lib.check(self.L.ab200_wgrad_finalize(C.byref(self.desc), self.partial.data_ptr(), gw.data_ptr(), _stream()),
                    "ab200_wgrad_finalize")
         self.spill = None
+        self.check_status()          # one host read per backward pass: a timed-out tensor-core kernel must not yield gradients
         return gw
 
     def check_status(self) -> None:
-        """Debug aid (host sync): raises if any tensor-core kernel hit its bounded barrier wait."""
+        """Host sync: raises if any tensor-core kernel that used this engine's image / partial buffer hit its bounded
+        barrier wait (its results are garbage).  Called by the product path at the end of every rk4 forward, of every
+        backward pass and when dopri5 sees a poisoned error norm."""
         st = int(self.image[self._img_status:self._img_status + 4].view(torch.int32).item())
         sp = 0
         if getattr(self, "partial", None) is not None:
@@ -431,6 +450,7 @@ def rk4_forward(eng: TcEngine, y0: torch.Tensor, t_host: Sequence[float], save_s
         stages.append((3, RK38.stage_input(3, dt), float(t_host[n + 1]), None))
         eng.stage_forward_fused(yn, [A[0], A[1], A[2]], stages, B, y_out=yn1, cout=RK38.combo(RK38.b, dt))
         rows_unblock(yn1, B, eng.D, out=y_path[n + 1])
+    eng.check_status()
     return y_path, ((yb, acc) if save_stages else None)
 
 
@@ -507,8 +527,8 @@ def _cast_time(v: float, time_dtype) -> float:
 
 def dopri5_forward(eng: TcEngine, y0: torch.Tensor, t_host: Sequence[float], rtol: float, atol: float, *, first_step=None,
                    safety: float = 0.9, ifactor: float = 10.0, dfactor: float = 0.2, max_num_steps: int = 2 ** 31 - 1,
-                   time_dtype=torch.float64, save_steps: bool = False, stats: Optional[Dopri5Stats] = None, fp16_forward: bool = True,
-                   error_norm: str = "shard", group=None):
+                   time_dtype=torch.float64, save_steps: bool = False, stats: Optional[Dopri5Stats] = None, fp16_forward=None,
+                   forward_operands="fp16x2", error_norm: str = "shard", group=None):
     """y0 row-major [B, D] -> y_path [T, B, D] (dense output at the requested times), and the accepted steps when
     `save_steps`.  One host read of the squared-error sum per attempted step decides accept / reject.
     error_norm="global": when agents are sharded over ranks, the squared-error sum and the element count are all-reduced
@@ -524,7 +544,10 @@ def dopri5_forward(eng: TcEngine, y0: torch.Tensor, t_host: Sequence[float], rto
     dev = y0.device
     D, P = eng.D, eng.P
     stats = stats if stats is not None else Dopri5Stats()
-    prev_fmt, eng.fp16_forward = eng.fp16_forward, bool(fp16_forward)
+    # forward_operands: "fp16x2" (default; split activations: the step sequence of the fp32 solver), "fp16", "bf16";
+    # the legacy boolean `fp16_forward` (True -> "fp16", False -> "bf16") still wins when given
+    prev_fmt = eng.fwd_format
+    eng.fwd_format = fwd_format_code(forward_operands if fp16_forward is None else bool(fp16_forward))
     ts = [_cast_time(float(v), time_dtype) for v in t_host]
     y_path = torch.empty((T, B, D), dtype=torch.float32, device=dev)
     y_path[0].copy_(y0)
@@ -579,6 +602,7 @@ def dopri5_forward(eng: TcEngine, y0: torch.Tensor, t_host: Sequence[float], rto
             dist.all_reduce(sumsq, group=group)
         ratio = float(torch.sqrt(sumsq[0] / n_elems))
         if ratio != ratio:
+            eng.check_status()       # a kernel whose bounded barrier wait expired poisons the norm: report that, not an overflow
             raise _lib.Ab200Error("dopri5: non-finite error estimate (state or drift overflowed)")
         n_steps += 1
         if ratio <= 1.0:
@@ -605,7 +629,8 @@ def dopri5_forward(eng: TcEngine, y0: torch.Tensor, t_host: Sequence[float], rto
         else:
             dfac = 1.0 if ratio < 1.0 else dfactor
             dt = _cast_time(dt * min(ifactor, max(safety / ratio ** 0.2, dfac)), time_dtype)
-    eng.fp16_forward = prev_fmt
+    eng.fwd_format = prev_fmt
+    eng.check_status()
     return y_path, (steps if save_steps else None), stats
 
 

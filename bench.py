@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """bench.py -- agent-steps/s of the GAT-ODE hot path on N B200s (one process per GPU).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c5] [--precision f32|bf16] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c5] [--precision f32|bf16]
+                    [--impl ours|reference|reference-gpu] [--scaling strong|weak]
 
 One "step" = one pass of the hot path over one batch of synthetic agents: the whole trajectory
 (T-1 solver intervals) for every agent of the batch, i.e. B*(T-1) agent-steps.
@@ -9,7 +10,10 @@ One "step" = one pass of the hot path over one batch of synthetic agents: the wh
   e2e   : the same metric through the public module API with HOST (pinned) inputs, H2D and D2H in the timed region
   roofline / cpu_baseline / clocks / gpu_launches : see DESIGN.md §Measurement
 `--impl reference` times the reference's CPU implementation of the path (the oracle port: the reference's
-own PyTorch ops + the restated torchdiffeq solver) on the host cores, same config/metric.
+own PyTorch ops + the restated torchdiffeq solver + the restated GATConv) on the host cores, same config/metric;
+`--impl reference-gpu` runs the SAME reference-structured modules in eager PyTorch on one B200 (the
+"beat this on the same box" bar).  With N > 1 the workload's agents are SHARDED over the ranks (`--scaling strong`,
+BASELINE.json configs[3]); `--scaling weak` gives every rank the full agent count instead.
 """
 from __future__ import annotations
 
@@ -42,8 +46,11 @@ WORKLOADS = {
     "c5": dict(B=8_000_000, Z=10_000, T=97, heads=4, mode="train", method="dopri5", adjoint=True,
                name="configs[4]: 8M agents x 10k zones, 4-head GAT, dopri5 rtol=atol=1e-5, odeint_adjoint fwd+bwd (agent-chunked)"),
 }
-ALG_FLOP_FWD = 755_712          # per agent-step, SURVEY.md §8(d) / BASELINE.md §3
-ALG_FLOP_FWDBWD = 3_022_848     # 4x forward (discrete adjoint with stage recompute)
+ALG_FLOP_EVAL = 188_928         # one drift evaluation per agent
+ALG_FLOP_FWD = 755_712          # rk4, per agent-step: 4 evaluations (SURVEY.md §8(d) / BASELINE.md §3)
+ALG_FLOP_FWDBWD = 3_022_848     # rk4: 4x forward (discrete adjoint with stage recompute)
+ALG_FLOP_FWD_DOPRI5 = 6 * ALG_FLOP_EVAL          # 1,133,568: six new evaluations per accepted step (FSAL)
+ALG_FLOP_FWDBWD_DOPRI5 = 4 * ALG_FLOP_FWD_DOPRI5  # 4,534,272: + recompute + dgrad + wgrad of the same six evaluations
 ALG_BYTES_FWD = 1_280
 ALG_BYTES_FWDBWD = 3_840
 
@@ -159,11 +166,21 @@ class _TrajectoryLoss(torch.autograd.Function):
         return y_path * (scale * go), None
 
 
+def _config_for(args):
+    cfg = dict(WORKLOADS[args.workload])
+    if args.agents:
+        cfg["B"] = args.agents
+    if args.solver:
+        cfg["method"] = args.solver
+        cfg["name"] = cfg["name"].replace("96 RK4 steps", "dopri5 rtol=atol=1e-5") if args.solver == "dopri5" else \
+            cfg["name"].replace("dopri5 rtol=atol=1e-5", "96 RK4 steps")
+    return cfg
+
+
 def run_ours(args):
     import torch.distributed as dist
     import ananke_abm_b200 as ab
     from ananke_abm_b200 import dist as abd
-    from ananke_abm_b200 import odeint as _unused  # noqa: F401
     import importlib
     from ananke_abm_b200 import _lib
     oi = importlib.import_module("ananke_abm_b200.odeint")
@@ -176,34 +193,41 @@ def run_ours(args):
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # keep NCCL's banner / debug lines out of the JSON stream
         dist.init_process_group("nccl", device_id=dev)
-    cfg = dict(WORKLOADS[args.workload])
-    if args.agents:
-        cfg["B"] = args.agents
-    if args.solver:
-        cfg["method"] = args.solver
-        cfg["name"] = cfg["name"].replace("96 RK4 steps", "dopri5 rtol=atol=1e-5") if args.solver == "dopri5" else \
-            cfg["name"].replace("dopri5 rtol=atol=1e-5", "96 RK4 steps")
+    cfg = _config_for(args)
     train = cfg["mode"] == "train"
+    T = cfg["T"]
+    # N > 1: "strong" = the workload's agents are sharded over the ranks in contiguous blocks (BASELINE.json configs[3]: the same
+    # 1M agents on 2/4/8 GPUs; every rank sees the slice [lo, hi) of the SAME synthetic inputs a single GPU would see);
+    # "weak" = every rank runs the full agent count on inputs of its own seed.
+    strong = args.scaling == "strong"
+    B_total = cfg["B"] if strong else cfg["B"] * world
+    if strong:
+        lo, hi = abd.shard_bounds(cfg["B"], rank, world)
+        home, work, traits, t = make_inputs(cfg, seed=42)
+        home, work, traits = home[lo:hi].clone(), work[lo:hi].clone(), traits[lo:hi].clone()
+    else:
+        lo, hi = 0, cfg["B"]
+        home, work, traits, t = make_inputs(cfg, seed=42 + rank)
+    B = hi - lo
     # agents are processed in equal chunks of at most --chunk agents (whole 128-agent tiles): equal parts avoid a small,
     # badly utilised tail chunk; the saved steps of ONE chunk live in HBM (peak_mem_gb in the JSON line)
-    n_parts = max(1, -(-cfg["B"] // args.chunk))
-    chunk = min(cfg["B"], -(-(-(-cfg["B"] // n_parts)) // 128) * 128)
-    B, T = cfg["B"], cfg["T"]
+    n_parts = max(1, -(-B // args.chunk))
+    chunk = min(B, -(-(-(-B // n_parts)) // 128) * 128)
     model, zfeat, csr = build_model(cfg, args.precision, dev)
-    home, work, traits, t = make_inputs(cfg, seed=42 + rank)
     pin = lambda x: x.pin_memory()   # noqa: E731
     h_home, h_work, h_traits, h_t = pin(home), pin(work), pin(traits), pin(t)
     d_home, d_work, d_traits, d_t = (x.to(dev) for x in (home, work, traits, t))
     params = [p for p in model.parameters()]
 
     adaptive = cfg["method"] == "dopri5"
-    counter = {"agent_steps": 0, "accepted": 0, "rejected": 0}
+    counter = {"agent_steps": 0, "accepted": 0, "rejected": 0, "solves": 0}
     snap_idx = torch.arange(4, T, 8, device=dev)[:12] if train else None                    # 12 snap rows of the day grid
     snap_target = (torch.randint(0, cfg["Z"], (12, B), generator=torch.Generator().manual_seed(99 + rank)).to(dev)
                    if (train and args.loss == "ce") else None)
 
     def count(nb):
         """agent-steps of the chunk just integrated: grid intervals for rk4, ACCEPTED steps for dopri5"""
+        counter["solves"] += 1
         if adaptive:
             st = oi._LAST["solver"]
             counter["agent_steps"] += nb * st.n_accepted
@@ -238,9 +262,9 @@ def run_ours(args):
                 # cross-entropy head at 12 of the 97 grid points (~12 GT snaps per agent-day)
                 pred_emb = model.decoder(y_path[snap_idx, :, :model.config.emb_dim])
                 rows = ab.head_ce_rows(pred_emb, table, snap_target[:, s:s + chunk], model.config.softmax_tau)
-                loss = rows.sum() / (snap_idx.numel() * B)
+                loss = rows.sum() / (snap_idx.numel() * B_total)
             else:
-                loss = _TrajectoryLoss.apply(y_path, 128) * ((min(B, s + chunk) - s) / B)
+                loss = _TrajectoryLoss.apply(y_path, 128) * ((min(B, s + chunk) - s) / B_total)
             loss.backward()
             total = loss.detach() if total is None else total + loss.detach()
             del y_path, loss
@@ -275,7 +299,7 @@ def run_ours(args):
         for _ in range(warmup):
             fn()
         barrier()
-        counter.update(agent_steps=0, accepted=0, rejected=0)
+        counter.update(agent_steps=0, accepted=0, rejected=0, solves=0)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
@@ -289,38 +313,51 @@ def run_ours(args):
             ms = float(tms.item())
         return ms
 
+    def all_ranks(counted):
+        """agent-steps over ALL ranks (they can differ by a few agents per rank when B % N != 0)"""
+        if world == 1:
+            return counted["agent_steps"]
+        v = torch.tensor([float(counted["agent_steps"])], dtype=torch.float64, device=dev)
+        dist.all_reduce(v)
+        return float(v.item())
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     ms = timed(lambda: hot_step(d_home, d_work, d_traits, d_t), args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
     steps_counted = dict(counter)
+    total_agent_steps = all_ranks(steps_counted)
 
     # kernel-only time of the dominant kernel: raw C-ABI launches into preallocated buffers, CUDA events on the
     # launching stream, no allocation or host sync between launches
-    n_chunks = (B + chunk - 1) // chunk
     tc_train = train and args.precision == "bf16"
+    fp32_accepted = None
     with torch.no_grad():
         table, zemb = model.zone_tables(zfeat, csr)
         y0 = model.initial_state(table, zemb, d_home[:chunk], d_work[:chunk], d_traits[:chunk]).contiguous()
         spec = ab.describe_drift(model.odefunc)
         wflat = spec.flat_params().detach().contiguous()
+        if adaptive and rank == 0:
+            # the step count the SAME solver takes when the drift is evaluated in strict fp32 (FFMA kernels) on a slice of
+            # the same agents: what an agent-step of this line is worth in solver work (accepted_steps_vs_fp32)
+            nsl = min(2048, y0.shape[0])
+            ab.odeint(model.odefunc, y0[:nsl].clone(), d_t, method="dopri5", rtol=model.config.rtol, atol=model.config.atol,
+                      options={"precision": "f32"})
+            fp32_accepted = int(oi._LAST["solver"].n_accepted)
         reps = 5
         k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         if tc_train:
-            # backward stage kernel (stage_bwd_tc_kernel): 4 launches per solver step, the largest share of a training step
+            # backward stage kernel (stage_bwd_tc_kernel): one fused launch per solver step, the largest share of a training step
             from ananke_abm_b200 import stage as st
             Bc = y0.shape[0]
             eng = st.TcEngine(spec, wflat)
-            eng.backward_begin(Bc, 4)
             yb = st.rows_block(y0)
-            A = [st.rows_block(torch.randn(Bc, 64, device=dev) * 0.1) for _ in range(3)]
+            A = [st.rows_block(torch.randn(Bc, 64, device=dev) * 0.1) for _ in range(7)]
             Gb = st.rows_block(torch.randn(Bc, 64, device=dev) * 1e-3)
-            GX = [st.blocked_zeros(Bc, 160, dev) for _ in range(4)]
+            GX = [st.blocked_zeros(Bc, 160, dev) for _ in range(7)]
             dtk = 0.25
             tab, first, last = (st.DOPRI5, 1, 6) if adaptive else (st.RK38, 0, 3)      # the fused launch of one step's backward stages
-            A = A + [st.rows_block(torch.randn(Bc, 64, device=dev) * 0.1) for _ in range(4)]
-            GX = GX + [st.blocked_zeros(Bc, 160, dev) for _ in range(3)]
             times = [1.0 + tab.c[i] * dtk for i in range(last + 1)]
             n_fused = last - first + 1
             eng.backward_begin(Bc, n_fused)
@@ -340,7 +377,7 @@ def run_ours(args):
             kern_ms = k0.elapsed_time(k1) / reps
             kern_units = Bc * n_fused            # agent-stage evaluations per launch
             kern_name = "stage_bwd_tc_kernel (%d fused Runge-Kutta stages per launch: recompute + dgrad + blob spill)" % n_fused
-            kern_flop_unit = ALG_FLOP_FWD // 4 * 2    # recompute + dgrad of one stage (wgrad runs in wgrad_tc_kernel)
+            kern_flop_unit = 2 * ALG_FLOP_EVAL        # recompute + dgrad of one stage (wgrad runs in wgrad_tc_kernel)
             kern_bytes_unit = ALG_BYTES_FWDBWD / 4.0
             # DRAM bytes per agent-stage of this kernel from `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum =
             # 1.300 + 2.730 GB for a fused 4-stage launch over 189,440 agents; profiles/r01_fused_step_ncu_summary.txt)
@@ -369,31 +406,43 @@ def run_ours(args):
     hot_step(d_home, d_work, d_traits, d_t)
     torch.cuda.synchronize()
     launches_per_step = _lib.LAUNCHES
-    e2e_ms = timed(e2e_step, max(1, min(args.steps, 3)), max(1, min(args.warmup, 3)))     # same warm-up rule as the device-resident leg
     e2e_steps = max(1, min(args.steps, 3))
+    e2e_ms = timed(e2e_step, e2e_steps, max(1, min(args.warmup, 3)))     # same warm-up rule as the device-resident leg
     e2e_counted = dict(counter)
+    e2e_agent_steps = all_ranks(e2e_counted)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     pk = peaks()
-    value = world * steps_counted["agent_steps"] / (ms * 1e-3)          # every rank runs the same workload (weak scaling)
-    e2e_value = world * e2e_counted["agent_steps"] / (e2e_ms * 1e-3)
+    value = total_agent_steps / (ms * 1e-3)
+    e2e_value = e2e_agent_steps / (e2e_ms * 1e-3)
     flops_kernel = kern_units * kern_flop_unit
     achieved_tf = flops_kernel / (kern_ms * 1e-3) / 1e12
     bytes_kernel = kern_units * kern_bytes_unit
     h2d = sum(x.numel() * x.element_size() for x in (h_home, h_work, h_traits, h_t))
     d2h = (B * T * 4) if not train else 4
+    acc_per = steps_counted["accepted"] / max(1, steps_counted["solves"])
+    rej_per = steps_counted["rejected"] / max(1, steps_counted["solves"])
+    if adaptive:
+        fl_fwd, fl_fb = ALG_FLOP_FWD_DOPRI5, ALG_FLOP_FWDBWD_DOPRI5
+    else:
+        fl_fwd, fl_fb = ALG_FLOP_FWD, ALG_FLOP_FWDBWD
     out = {
         "metric": METRIC + (" fwd+bwd" if train else " fwd (inference)"), "value": value, "unit": "agent-steps/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32" if args.precision == "f32" else ("fp16 fwd / bf16 bwd operands (fp32 accumulate, fp32 state)" if train else "fp16 operands on tcgen05 (fp32 accumulate, fp32 state)"), "data": "synthetic",
-        "config": {"workload": cfg["name"], "agents_per_gpu": B, "zones": cfg["Z"], "time_points": T, "solver": cfg["method"],
-                   "agent_chunk": chunk, "precision": args.precision, "loss": (args.loss if train else None),
-                   "solver_steps": ({"accepted_per_trajectory": steps_counted["accepted"] / max(1, args.steps * ((B + chunk - 1) // chunk)),
-                                     "rejected_per_trajectory": steps_counted["rejected"] / max(1, args.steps * ((B + chunk - 1) // chunk)),
+        "higher_is_better": True, "scaling": ("strong" if strong else "weak"), "vs_baseline": None,
+        "dtype": "f32" if args.precision == "f32" else ("fp16 weights x split-fp16 (hi+lo) activations fwd / bf16 bwd operands (fp32 accumulate, fp32 state)" if (train and adaptive) else ("fp16 fwd / bf16 bwd operands (fp32 accumulate, fp32 state)" if train else "fp16 operands on tcgen05 (fp32 accumulate, fp32 state)")), "data": "synthetic",
+        # equal-work figure: simulated agent-days (whole trajectories, forward + backward) per second, independent of how
+        # many solver steps the adaptive controller needed
+        "agent_days_per_s": B_total * args.steps / (ms * 1e-3),
+        "config": {"workload": cfg["name"], "agents_total": B_total, "agents_per_gpu": B, "zones": cfg["Z"], "time_points": T,
+                   "solver": cfg["method"], "agent_chunk": chunk, "precision": args.precision, "loss": (args.loss if train else None),
+                   "solver_steps": ({"accepted_per_trajectory": acc_per, "rejected_per_trajectory": rej_per,
+                                     "fp32_accepted_per_trajectory": fp32_accepted,
+                                     "accepted_steps_vs_fp32": (acc_per / fp32_accepted if fp32_accepted else None),
+                                     "fp32_note": "same solver, drift in strict fp32 (FFMA kernels), first %d agents of rank 0" % min(2048, chunk),
                                      "rtol": model.config.rtol, "atol": model.config.atol} if adaptive else {"grid_intervals": T - 1}),
                    "l2": "trajectory rows written per step (%.0f MB) exceed L2; weights are L2-resident by design" % (chunk * T * 640 / 1e6)},
         "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": pk["tf_burst"], "unit": "TFLOP/s",
@@ -403,65 +452,99 @@ def run_ours(args):
                      if kern_traffic_unit else None, "peak_source": pk["src"],
                      "kernel": kern_name, "kernel_ms": kern_ms, "units_per_launch": kern_units,
                      "alg_flop_per_unit": kern_flop_unit, "alg_bytes_per_unit": kern_bytes_unit,
-                     "alg_flop_per_agent_step": ALG_FLOP_FWDBWD if train else ALG_FLOP_FWD,
+                     "alg_flop_per_agent_step": fl_fb if train else fl_fwd,
                      "alg_bytes_per_agent_step": ALG_BYTES_FWDBWD if train else ALG_BYTES_FWD,
+                     "step_tflops_alg": value * (fl_fb if train else fl_fwd) / 1e12,
                      "hbm_achieved_gbs": bytes_kernel / (kern_ms * 1e-3) / 1e9, "hbm_peak_gbs": pk["hbm"]},
         "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms / e2e_steps},
+                "ms_per_step": e2e_ms / e2e_steps, "agent_days_per_s": B_total * e2e_steps / (e2e_ms * 1e-3)},
         "gpu_launches": args.steps * launches_per_step,
         "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9,
         "clocks": clocks,
     }
     if not args.no_cpu_baseline and world == 1:      # the CPU leg is timed on rank 0 at N = 1 only (torchrun pins OMP threads)
-        out["cpu_baseline"] = cpu_baseline(cfg, train, budget_s=20.0)
+        out["cpu_baseline"] = reference_step_timer(cfg, train, "cpu", steps=1, warmup=0, budget_agents=args.ref_agents)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
 
-def cpu_baseline(cfg, train, budget_s=20.0, steps=1, warmup=0):
-    """The oracle port (reference's PyTorch ops + restated solver) on the host cores, bounded sample."""
+def reference_step_timer(cfg, train, device, steps=1, warmup=0, budget_agents=None, wall_budget_s=240.0):
+    """The reference-structured GAT-ODE (oracle port: the reference's PyTorch ops for the drift / encoder / decoder, the
+    restated torchdiffeq solver, the restated GATConv) on `device` ("cpu": all host cores; "cuda": eager PyTorch on one
+    B200), on a bounded slice of the same workload: the first `budget_agents` agents, the full day, the full zone graph.
+    One step = GAT zone tables + initial state + solve (+ loss backward when training).  `warmup` untimed steps, then up
+    to `steps` timed ones (fewer only if the wall budget would be exceeded -- the returned `steps_run` is the real count);
+    `seconds` is the mean timed step."""
     from oracle import models_oracle as mo
     from oracle import torchdiffeq_oracle as tdq
+    from oracle import gat_oracle as go
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    on_gpu = device != "cpu"
+    if not on_gpu:
+        torch.set_num_threads(cores)
+    dev = torch.device(device)
     adaptive = cfg["method"] == "dopri5"
-    Bs = min(cfg["B"], 10_000 if not train else 2_000)
-    Ts = cfg["T"] if (not train or adaptive) else min(cfg["T"], 25)
-    sub = dict(cfg, B=Bs, T=Ts)
-    home, work, traits, _ = make_inputs(sub)
-    t = torch.linspace(0.0, 24.0, cfg["T"])[:Ts]
+    Bs = min(cfg["B"], budget_agents or (32_768 if on_gpu else 10_000))
+    Ts = cfg["T"]
+    sub = dict(cfg, B=Bs)
+    home, work, traits, t = make_inputs(sub)
     torch.manual_seed(42)
-    m = mo.OracleModeSep(cfg["Z"])
+    m = mo.OracleGATODE(7, cfg["heads"]).to(dev)
+    ei, feats = go.synthetic_zone_graph(cfg["Z"], k=6, seed=42)
+    edges = go.symmetrise_with_self_loops(ei, cfg["Z"]).to(dev)
+    feats, home, work, traits, t = (x.to(dev) for x in (feats, home, work, traits, t))
     kw = dict(method="dopri5", rtol=1e-5, atol=1e-5) if adaptive else dict(method="rk4")
-    best, n_steps = None, Ts - 1
-    for it in range(warmup + steps):
+    n_steps = Ts - 1
+
+    def one():
+        nonlocal n_steps
+        if on_gpu:
+            torch.cuda.synchronize()
         t0 = time.perf_counter()
         if not train:
             with torch.no_grad():
-                y0 = m.initial_state(home, work, traits)
+                table, zemb = m.zone_tables(feats, edges)
+                y0 = m.initial_state(table, zemb, home, work, traits)
                 tdq.odeint(m.rhs, y0, t, **kw)
         else:
             m.zero_grad()
-            y0 = m.initial_state(home, work, traits)
+            table, zemb = m.zone_tables(feats, edges)
+            y0 = m.initial_state(table, zemb, home, work, traits)
             yp = tdq.odeint(m.rhs, y0, t, **kw)
             (yp[:, :, :128] ** 2).mean().backward()
+            del yp
+        if on_gpu:
+            torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if adaptive:
             n_steps = sum(1 for (_, _, ok) in tdq._LAST_SOLVER["solver"].step_log if ok)
-        if it >= warmup:
-            best = dt if best is None else min(best, dt)
+        return dt
+
+    wall0 = time.perf_counter()
+    for _ in range(warmup):
+        one()
+    times = []
+    for it in range(steps):
+        times.append(one())
+        spent = time.perf_counter() - wall0
+        if it + 1 < steps and spent + times[-1] > wall_budget_s:
+            break
+    mean = sum(times) / len(times)
     what = f"{n_steps} accepted dopri5 steps (rtol=atol=1e-5)" if adaptive else f"{Ts - 1} rk4 steps"
-    return {"value": Bs * n_steps / best, "unit": "agent-steps/s", "cores": cores, "kind": "port",
-            "sample": f"{Bs} agents x {what} of the same workload ({'fwd+bwd' if train else 'fwd'}), "
-                      f"torch CPU fp32, {cores} threads, best of {steps}", "seconds": best}
+    where = (f"torch eager fp32 on {torch.cuda.get_device_name(dev)}" if on_gpu else f"torch CPU fp32, {cores} threads")
+    return {"value": Bs * n_steps / mean, "unit": "agent-steps/s", "cores": (0 if on_gpu else cores), "kind": "port",
+            "device": device, "agent_days_per_s": Bs / mean,
+            "sample": f"{Bs} agents x {what} of the same workload ({'fwd+bwd' if train else 'fwd'}, {cfg['heads']}-head GAT over "
+                      f"{cfg['Z']} zones included), {where}, mean of {len(times)} timed steps after {warmup} warm-up",
+            "seconds": mean, "steps_run": len(times), "accepted_per_trajectory": (n_steps if adaptive else None)}
 
 
-def run_reference(args):
+def run_reference(args, device="cpu"):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    if "TORCHELASTIC_RUN_ID" in os.environ and os.environ.get("AB200_REF_CHILD") != "1":
+    if device == "cpu" and "TORCHELASTIC_RUN_ID" in os.environ and os.environ.get("AB200_REF_CHILD") != "1":
         # torchrun pins OMP_NUM_THREADS=1 for its workers; the CPU arm must see all host cores as it does at N=1:
         # re-run this arm in a clean child process and relay its line
         env = {k: v for k, v in os.environ.items() if k not in ("OMP_NUM_THREADS", "MKL_NUM_THREADS")}
@@ -473,20 +556,20 @@ def run_reference(args):
             d["n_gpus"] = int(os.environ.get("WORLD_SIZE", "1"))
             print(json.dumps(d))
             return
-    cfg = dict(WORKLOADS[args.workload])
-    if args.agents:
-        cfg["B"] = args.agents
-    if args.solver:
-        cfg["method"] = args.solver
-        cfg["name"] = cfg["name"].replace("96 RK4 steps", "dopri5 rtol=atol=1e-5") if args.solver == "dopri5" else \
-            cfg["name"].replace("dopri5 rtol=atol=1e-5", "96 RK4 steps")
+    cfg = _config_for(args)
     train = cfg["mode"] == "train"
     t0 = time.perf_counter()
-    cb = cpu_baseline(cfg, train, steps=max(1, min(args.steps, 3)), warmup=1 if args.warmup else 0)
-    out = {"impl": "reference", "metric": METRIC + (" fwd+bwd" if train else " fwd (inference)"), "value": cb["value"],
-           "unit": "agent-steps/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": cb["seconds"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-           "data": "synthetic", "config": {"workload": cfg["name"], "sample": cb["sample"]},
+    if device != "cpu":
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    cb = reference_step_timer(cfg, train, device, steps=max(1, args.steps), warmup=max(0, args.warmup), budget_agents=args.ref_agents)
+    out = {"impl": "reference" if device == "cpu" else "reference-gpu",
+           "metric": METRIC + (" fwd+bwd" if train else " fwd (inference)"), "value": cb["value"],
+           "unit": "agent-steps/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": cb["steps_run"], "steps_requested": args.steps,
+           "warmup": args.warmup, "ms_per_step": cb["seconds"] * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic", "agent_days_per_s": cb["agent_days_per_s"],
+           "config": {"workload": cfg["name"], "sample": cb["sample"],
+                      "same_config": "same model, zone graph, solver, tolerances and inputs as the GPU arm; a bounded slice of the agents "
+                                     "(agents are independent: per-agent cost does not depend on the slice beyond CPU cache effects)"},
            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "wall_s": time.perf_counter() - t0}
     print(json.dumps(out))
@@ -499,7 +582,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="bf16", choices=["f32", "bf16"])
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="N > 1: 'strong' shards the workload's agents over the ranks (configs[3]); 'weak' gives every rank all of them")
+    ap.add_argument("--ref-agents", type=int, default=0,
+                    help="agents in the reference arms' / cpu_baseline's slice (default 10,000 on the CPU, 32,768 on the GPU)")
     ap.add_argument("--agents", type=int, default=0, help="override agents per GPU")
     ap.add_argument("--chunk", type=int, default=378_880,
                     help="upper bound on agents per launch sequence (the batch is cut into equal parts no larger than this); "
@@ -511,7 +598,9 @@ def main():
                          "'ce' = decoder + fused cross-entropy head at 12 snap points per agent (tensor cores)")
     args = ap.parse_args()
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, "cpu")
+    elif args.impl == "reference-gpu":
+        run_reference(args, "cuda")
     else:
         run_ours(args)
 

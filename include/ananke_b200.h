@@ -152,8 +152,12 @@ size_t ab200_stage_image_bytes(const ab200_drift_desc* d);
 int ab200_stage_pack(const ab200_drift_desc* d, const float* w_flat, void* image, size_t image_bytes, ab200_stream_t stream);
 /* `a` : host array of n_a device pointers (blocked [Bp][P] fp32 each).  a_out (blocked [Bp][P]), y_out (blocked
  * [Bp][D]) and err_sumsq (device double, accumulated) may each be NULL.  operand_format: 0 = bf16 operands,
- * 1 = IEEE fp16 operands (same speed, 8x less rounding noise -- what dopri5's embedded error estimate needs at
- * rtol = atol = 1e-5; the image holds both encodings of the weights). */
+ * 1 = IEEE fp16 operands (same speed, 8x less rounding noise), 2 = fp16 weights with every ACTIVATION entering the
+ * tensor core as a two-term fp16 split hi + lo (two MMAs per K-step) and biases / time features added in fp32: the
+ * evaluation then carries no activation rounding at all, only the fixed fp16 rounding of the weights, which is what
+ * dopri5's embedded error estimate needs at rtol = atol = 1e-5 (formats 1 / 0 make it take 2.4x / 14x the steps of the
+ * fp32 reference there).  The image holds all three encodings of the weights.  A kernel whose bounded barrier wait
+ * expired adds NaN to *err_sumsq (format 2) and sets the status word (ab200_stage_status_offset). */
 int ab200_stage_forward(const ab200_drift_desc* d, const void* image, const float* y0, const float* const* a,
                         const ab200_stage_desc* s, int64_t B, float* a_out, float* y_out, double* err_sumsq,
                         int32_t operand_format, ab200_stream_t stream);

@@ -48,11 +48,11 @@ def gat_edges(x, edges, W, att_src, att_dst, bias, heads: int, F_out: int, conca
     a_d = (xw * att_dst.view(1, heads, F_out)).sum(-1)
     j, i = edges[0], edges[1]
     e = F.leaky_relu(a_s[j] + a_d[i], slope)                       # [nnz, H]
-    m = torch.full((Z, heads), -float("inf"), dtype=x.dtype).scatter_reduce(0, i.view(-1, 1).expand(-1, heads), e, "amax")
+    m = torch.full((Z, heads), -float("inf"), dtype=x.dtype, device=x.device).scatter_reduce(0, i.view(-1, 1).expand(-1, heads), e, "amax")
     w = torch.exp(e - m[i])
-    den = torch.zeros(Z, heads, dtype=x.dtype).index_add(0, i, w)
+    den = torch.zeros(Z, heads, dtype=x.dtype, device=x.device).index_add(0, i, w)
     alpha = w / den[i]
-    out = torch.zeros(Z, heads, F_out, dtype=x.dtype).index_add(0, i, alpha.unsqueeze(-1) * xw[j])
+    out = torch.zeros(Z, heads, F_out, dtype=x.dtype, device=x.device).index_add(0, i, alpha.unsqueeze(-1) * xw[j])
     out = out.reshape(Z, heads * F_out) if concat else out.mean(dim=1)
     return out + bias if bias is not None else out
 

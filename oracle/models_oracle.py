@@ -139,6 +139,48 @@ class OracleModeSep(nn.Module):
         return self.head(self.solve(y0, times_union))
 
 
+class _OracleGAT(nn.Module):
+    """PyG GATConv parameter tree (`lin.weight`, `att_src`, `att_dst`, `bias`) evaluated by oracle.gat_oracle.gat_edges."""
+
+    def __init__(self, in_channels: int, out_channels: int, heads: int):
+        super().__init__()
+        from . import gat_oracle as go
+        self.heads, self.out_channels = heads, out_channels
+        self.lin = _Holder()
+        self.lin.weight = nn.Parameter(go.glorot_(torch.empty(heads * out_channels, in_channels)))
+        self.att_src = nn.Parameter(go.glorot_(torch.empty(1, heads, out_channels)))
+        self.att_dst = nn.Parameter(go.glorot_(torch.empty(1, heads, out_channels)))
+        self.bias = nn.Parameter(torch.zeros(heads * out_channels))
+
+    def forward(self, x, edges):
+        from . import gat_oracle as go
+        return go.gat_edges(x, edges, self.lin.weight, self.att_src.view(-1), self.att_dst.view(-1), self.bias, self.heads,
+                            self.out_channels, concat=True)
+
+
+class OracleGATODE(OracleModeSep):
+    """The GAT-ODE of north_star in plain PyTorch (SURVEY.md Open Question 1, Reading A): ModeSepModel with its two learnable
+    zone lookups (`class_table[Z, E]`, `zone_embed[Z, 8]`, mode_sep/architecture/model.py:101-102) produced by graph
+    attention layers over the zone features (PyG GATConv semantics, gat_oracle.py).  Same parameter names as
+    `ananke_abm_b200.run.GATODEModel`, so state dicts are interchangeable.  Runs on whatever device its tensors are on:
+    the CPU arm and the eager-PyTorch-on-GPU arm of bench.py time this module."""
+
+    def __init__(self, num_zone_features: int, heads: int = 4, dims: Optional[ModeSepDims] = None):
+        super().__init__(1, dims)
+        del self.class_table, self.zone_embed
+        d = self.dims
+        self.table_gat = _OracleGAT(num_zone_features, d.emb_dim // heads, heads)
+        self.zone_gat = _OracleGAT(num_zone_features, d.zone_emb_dim, 1)
+
+    def zone_tables(self, zone_features, edges):
+        return self.table_gat(zone_features, edges), self.zone_gat(zone_features, edges)
+
+    def initial_state(self, class_table, zone_embed, home_idx, work_idx, traits) -> torch.Tensor:      # noqa: signature differs on purpose
+        p0 = class_table.detach()[home_idx]
+        raw = torch.cat([traits, zone_embed[home_idx], zone_embed[work_idx]], dim=-1)
+        return torch.cat([p0, torch.zeros_like(p0), self.context_encoder(raw)], dim=-1)
+
+
 class OracleLatentODE(nn.Module):
     """Same parameter tree as the reference GenerativeODE (latent_ode/architecture/model.py:132-165),
     ODE branch only (`enable_sde=False`); the h0 reparameterisation noise is an explicit argument."""
