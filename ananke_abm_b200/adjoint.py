@@ -1,15 +1,22 @@
-"""Continuous adjoint (torchdiffeq `odeint_adjoint` semantics, adjoint.py) for an arbitrary `func` on the GPU.
+"""Continuous adjoint (torchdiffeq `odeint_adjoint` semantics, adjoint.py) on the GPU.
 
 Forward under no_grad keeps only the requested output rows; backward integrates the augmented system
-[y, a_y, a_theta] from t[i] to t[i-1], re-seeding y with the saved row and adding dL/dy[i-1] to a_y -- the
+[y, a_y, a_theta...] from t[i] to t[i-1], re-seeding y with the saved row and adding dL/dy[i-1] to a_y -- the
 O(1)-in-steps memory scheme of /root/reference/src/ananke_abm/models/latent_ode/architecture/ode_components.py:50.
-Stage algebra and error norms run through the fused elementwise kernels via `odeint`'s generic path.
-Deviation (documented in DESIGN.md): the adaptive error norm is one RMS over the whole augmented vector
-instead of torchdiffeq's max over per-component RMS norms.
+
+For the two reference drift shapes (`drift.describe_drift`) the augmented dynamics are evaluated by kernels only:
+`ab200_drift_eval` for f and `ab200_drift_vjp` for (-a_y^T df/dy, -a_y^T df/dtheta); any other `func` is evaluated by
+the caller's torch code and differentiated with autograd, as torchdiffeq does.  Stage algebra and error norms run through
+the fused elementwise kernels (`odeint`'s generic path) with torchdiffeq's MIXED norm: the accepted error is the max over
+the RMS norms of the components (y, a_y and each parameter's adjoint), not one RMS over the packed vector.
 """
 from __future__ import annotations
 
 import torch
+
+
+def _pad4(n: int) -> int:
+    return (n + 3) // 4 * 4
 
 
 class _ContinuousAdjoint(torch.autograd.Function):
@@ -25,7 +32,8 @@ class _ContinuousAdjoint(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_y):
-        from .odeint import odeint
+        from .odeint import odeint, drift_eval, drift_vjp
+        from .drift import describe_drift
         func = ctx.func
         rtol, atol, method, options = ctx.cfg["adj"]
         t, y, *params = ctx.saved_tensors
@@ -33,31 +41,70 @@ class _ContinuousAdjoint(torch.autograd.Function):
         shape = y.shape[1:]
         n = int(y[0].numel())
         sizes = [int(p.numel()) for p in params]
+        # packed state: [y | a_y | a_theta_1 | a_theta_2 ...], every component starting at a multiple of 4 floats (128-bit kernels)
+        offs, off = [], 0
+        for m in [n, n] + sizes:
+            offs.append(off)
+            off += _pad4(m)
+        total = off
+        segments = [(o, m) for o, m in zip(offs, [n, n] + sizes)]
 
-        def aug(tt, z):
-            yy = z[:n].view(shape)
-            a_y = z[n:2 * n].view(shape)
-            with torch.enable_grad():
-                yy = yy.detach().requires_grad_(True)
-                f = func(tt.detach(), yy)
-                vj = torch.autograd.grad(f, (yy,) + params, -a_y, allow_unused=True, retain_graph=False)
-            vy = torch.zeros_like(yy) if vj[0] is None else vj[0]
-            vp = [torch.zeros_like(p) if v is None else v for p, v in zip(params, vj[1:])]
-            return torch.cat([f.detach().reshape(-1), vy.reshape(-1)] + [v.reshape(-1) for v in vp])
+        spec = describe_drift(func) if len(shape) == 2 and y.dtype == torch.float32 else None
+        if spec is not None:
+            sp = {id(p) for p in spec.params}
+            if shape[1] != spec.state_dim or any(id(p) not in sp for p in params):
+                spec = None      # adjoint_params outside the drift net: differentiate with autograd
 
+        def pack(parts):
+            z = torch.zeros(total, dtype=y.dtype, device=y.device)
+            for (o, m), v in zip(segments, parts):
+                z[o:o + m] = v.reshape(-1)
+            return z
+
+        if spec is not None:
+            w_flat = spec.flat_params().detach()
+            # position of every adjoint parameter inside the drift's flat parameter vector
+            where, pos = {}, 0
+            for p in spec.params:
+                where[id(p)] = pos
+                pos += p.numel()
+
+            def aug(tt, z):
+                tf = float(tt)
+                yy = z[:n].view(shape)
+                a_y = z[offs[1]:offs[1] + n].view(shape)
+                f = drift_eval(spec, w_flat, tf, yy)
+                gy, gw = drift_vjp(spec, w_flat, tf, yy, -a_y)
+                return pack([f, gy] + [gw[where[id(p)]:where[id(p)] + p.numel()] for p in params])
+        else:
+            def aug(tt, z):
+                yy = z[:n].view(shape)
+                a_y = z[offs[1]:offs[1] + n].view(shape)
+                with torch.enable_grad():
+                    yy = yy.detach().requires_grad_(True)
+                    f = func(tt.detach() if torch.is_tensor(tt) else torch.tensor(tt, dtype=y.dtype, device=y.device), yy)
+                    vj = torch.autograd.grad(f, (yy,) + params, -a_y, allow_unused=True, retain_graph=False)
+                vy = torch.zeros_like(yy) if vj[0] is None else vj[0]
+                vp = [torch.zeros_like(p) if v is None else v for p, v in zip(params, vj[1:])]
+                return pack([f.detach(), vy] + vp)
+
+        adj_options = dict(options or {})
+        for k_ in ("precision", "error_norm", "forward_operands", "fp16_forward", "group", "adjoint_mode"):
+            adj_options.pop(k_, None)      # forward-solve switches of the tensor-core path mean nothing to the augmented system
+        if method == "dopri5":
+            adj_options["segments"] = segments
+            if spec is not None:
+                adj_options["time_as_float"] = True
         with torch.no_grad():
             a_y = grad_y[-1].reshape(-1).clone()
-            a_p = torch.zeros(sum(sizes), dtype=y.dtype, device=y.device)
+            a_p = [torch.zeros(s, dtype=y.dtype, device=y.device) for s in sizes]
             for i in range(t.numel() - 1, 0, -1):
-                z = torch.cat([y[i].reshape(-1), a_y, a_p])
-                sol = odeint(aug, z, t[i - 1:i + 1].flip(0), rtol=rtol, atol=atol, method=method, options=options)
+                z = pack([y[i], a_y] + a_p)
+                sol = odeint(aug, z, t[i - 1:i + 1].flip(0), rtol=rtol, atol=atol, method=method, options=dict(adj_options))
                 z1 = sol[1]
-                a_y = z1[n:2 * n] + grad_y[i - 1].reshape(-1)
-                a_p = z1[2 * n:]
-            outs, off = [], 0
-            for p, s in zip(params, sizes):
-                outs.append(a_p[off:off + s].view_as(p))
-                off += s
+                a_y = z1[offs[1]:offs[1] + n] + grad_y[i - 1].reshape(-1)
+                a_p = [z1[o:o + m] for (o, m) in segments[2:]]
+            outs = [a.view_as(p) for a, p in zip(a_p, params)]
         return (None, a_y.view(shape), None, None, *outs)
 
 

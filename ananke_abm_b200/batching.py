@@ -240,3 +240,79 @@ def unify_and_interpolate_batch(batch: Sequence[Dict], train_on_interpolated_poi
         "purpose_groups": purpose_groups,
         "person_names": [s["person_name"] for s in batch],
     }
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the layout the reference's own (stale) test module pins: /root/reference/test/test_data_batching.py:30-81
+# ------------------------------------------------------------------------------------------------------------------
+K_INTERNAL = 10     # test_data_batching.py:39-40: dense grid length (len(gt_union) - 1) * (K_INTERNAL - 1) + 1
+
+
+def sde_collate_fn(samples: Sequence[Dict], k_internal: int = K_INTERNAL, time_match_tol: float = 1e-6) -> Dict:
+    """Collate with the key names, shapes and invariants of the `sde_collate_fn` batch that
+    /root/reference/test/test_data_batching.py checks (the function itself is no longer in the reference snapshot; the test
+    module is the specification, SURVEY.md §4 invariants 1-5):
+
+      gt_union_times [S_gt]  sorted union of every person's ground-truth times;  is_gt_union [B, S_gt]
+      grid_times [S_dense]   every union gap cut into (k_internal - 1) equal sub-intervals, endpoints shared:
+                             S_dense = (S_gt - 1) * (k_internal - 1) + 1;  is_gt_grid [S_dense] marks the union times, and
+                             grid_times[is_gt_grid] == gt_union_times exactly                                  (:33-40)
+      loc_emb_union [B, S_gt, E], purp_emb_union [B, S_gt, Ep] float32, anchor_union [B, S_gt]                   (:45-51)
+                             a person's embedding on the union axis: held FLAT across a stay (the last snap's value), linearly
+                             interpolated between origin and destination inside a travel segment                 (:53-68)
+      segments_batch         ragged list over all persons' travel segments, dicts with keys exactly
+                             {"b", "i0", "i1", "mode_id", "mode_proto"}; i0 < i1 are DENSE-grid indices of the segment's
+                             end points, which are ground-truth grid points                                      (:70-81)
+
+    `samples[b]` is a per-person dict: gt_times [S_b] (sorted), gt_loc_emb [S_b, E], gt_purp_emb [S_b, Ep], gt_anchor [S_b],
+    segments = [{"t0", "t1", "mode_id", "mode_proto"}, ...] (travel legs; t0 / t1 are ground-truth times of that person).
+    Tensorised over the union axis; person b of the input is row b of every output."""
+    if k_internal < 2:
+        raise ValueError("k_internal must be >= 2")
+    dev = samples[0]["gt_times"].device
+    B = len(samples)
+    gt_union = torch.unique(torch.cat([s["gt_times"].to(torch.float32) for s in samples]), sorted=True)
+    S = gt_union.numel()
+    K1 = k_internal - 1
+    # dense grid: exact union times at multiples of K1, equally spaced interior points in between
+    if S > 1:
+        frac = torch.arange(K1, device=dev, dtype=torch.float32) / K1                    # 0, 1/K1, ...
+        lo, hi = gt_union[:-1, None], gt_union[1:, None]
+        grid = torch.cat([(lo + (hi - lo) * frac[None, :]).reshape(-1), gt_union[-1:]])
+        grid[::K1] = gt_union                                                            # bit-exact at the union points
+    else:
+        grid = gt_union.clone()
+    is_gt_grid = torch.zeros(grid.numel(), dtype=torch.bool, device=dev)
+    is_gt_grid[::K1] = True
+    E = samples[0]["gt_loc_emb"].shape[-1]
+    Ep = samples[0]["gt_purp_emb"].shape[-1]
+    is_gt_union = torch.zeros((B, S), dtype=torch.bool, device=dev)
+    loc = torch.zeros((B, S, E), dtype=torch.float32, device=dev)
+    purp = torch.zeros((B, S, Ep), dtype=torch.float32, device=dev)
+    anchor = torch.zeros((B, S), dtype=torch.float32, device=dev)
+    segments_batch: List[Dict] = []
+    for b, s in enumerate(samples):
+        gt = s["gt_times"].to(torch.float32)
+        # last ground-truth snap at or before every union time (clamped to the person's first snap)
+        k = (torch.searchsorted(gt, gt_union + time_match_tol, right=True) - 1).clamp(0, gt.numel() - 1)
+        hit = (gt[k] - gt_union).abs() <= time_match_tol
+        is_gt_union[b] = hit
+        le, pe = s["gt_loc_emb"].to(torch.float32)[k], s["gt_purp_emb"].to(torch.float32)[k]      # flat hold
+        anchor[b] = torch.where(hit, s["gt_anchor"].to(torch.float32)[k], torch.zeros((), device=dev))
+        for seg in s["segments"]:
+            t0, t1 = float(seg["t0"]), float(seg["t1"])
+            inside = (gt_union > t0 + time_match_tol) & (gt_union < t1 - time_match_tol)
+            if bool(inside.any()):
+                k0 = int(torch.searchsorted(gt, torch.tensor(t0 + time_match_tol, device=dev), right=True) - 1)
+                k1 = int(torch.searchsorted(gt, torch.tensor(t1 - time_match_tol, device=dev), right=False))
+                w = ((gt_union - t0) / (t1 - t0)).clamp(0, 1)[:, None]
+                g0l, g1l = s["gt_loc_emb"].to(torch.float32)[k0], s["gt_loc_emb"].to(torch.float32)[k1]
+                g0p, g1p = s["gt_purp_emb"].to(torch.float32)[k0], s["gt_purp_emb"].to(torch.float32)[k1]
+                le = torch.where(inside[:, None], g0l + (g1l - g0l) * w, le)
+                pe = torch.where(inside[:, None], g0p + (g1p - g0p) * w, pe)
+            i0 = int(torch.argmin((gt_union - t0).abs())) * K1
+            i1 = int(torch.argmin((gt_union - t1).abs())) * K1
+            segments_batch.append({"b": b, "i0": i0, "i1": i1, "mode_id": seg["mode_id"], "mode_proto": seg["mode_proto"]})
+        loc[b], purp[b] = le, pe
+    return {"gt_union_times": gt_union, "grid_times": grid, "is_gt_grid": is_gt_grid, "is_gt_union": is_gt_union,
+            "loc_emb_union": loc, "purp_emb_union": purp, "anchor_union": anchor, "segments_batch": segments_batch}

@@ -19,6 +19,8 @@ size_t rk4_backward_f32_workspace(const ab200_drift_desc* d, int64_t B, int T);
 int rk4_backward_f32(const ab200_drift_desc* d, const float* w_flat, const float* t_dev, const float* y_path,
                      const float* grad_y_path, int64_t B, int T, float* grad_y0, float* grad_w_flat, void* ws, size_t ws_bytes,
                      cudaStream_t st);
+int drift_vjp_f32(const ab200_drift_desc* d, const float* w_flat, float t, const float* y, const float* g, int64_t B, float* grad_y,
+                  float* grad_w_flat, void* ws, size_t ws_bytes, cudaStream_t st);
 int rk_stage_combine(const float* y, const float* const* k, const float* coef, int n_k, float dt, float* out, int64_t n,
                      cudaStream_t st);
 int rk_combine_errnorm(const float* y0, const float* const* k, const float* csol, const float* cerr, int n_k, float dt,
@@ -194,6 +196,18 @@ int ab200_drift_eval(const ab200_drift_desc* d, const float* w_flat, float t, co
   int rc = pack_drift(d, w_flat, (float*)workspace, st);
   if (rc) return rc;
   return drift_eval_f32(d, (const float*)workspace, t, y, B, out, st);
+}
+
+size_t ab200_drift_vjp_workspace_bytes(const ab200_drift_desc* d, int64_t B) {
+  if (!desc_ok(d) || B <= 0) return 0;
+  return rk4_backward_f32_workspace(d, B, 1);
+}
+
+int ab200_drift_vjp(const ab200_drift_desc* d, const float* w_flat, float t, const float* y, const float* grad_out, int64_t B,
+                    float* grad_y, float* grad_w_flat, void* workspace, size_t workspace_bytes, ab200_stream_t stream) {
+  if (!desc_ok(d) || !w_flat || !y || !grad_out || !grad_y || !grad_w_flat || !workspace || B <= 0) return AB200_ERR_BAD_ARG;
+  if (workspace_bytes < rk4_backward_f32_workspace(d, B, 1)) return AB200_ERR_WORKSPACE;
+  return drift_vjp_f32(d, w_flat, t, y, grad_out, B, grad_y, grad_w_flat, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
 int ab200_rk_stage_combine(const float* y, const float* const* k, const float* coef_host, int32_t n_k, float dt, float* out,

@@ -94,9 +94,16 @@ struct BwdArgs {
   float period;
   int pot_a, pot_b;
   float pot_strength;
+  float t_eval;         // MODE 1: the time of the single evaluation
 };
 
-template <int P, int H, int HID, int NRES, int ACT, int POT>
+// MODE 0: discrete adjoint of the whole rk4 trajectory (above).
+// MODE 1: vector-Jacobian product of ONE drift evaluation f(t, y) = [v, net(p, v, h, t), 0]: y_path = y [B][D],
+//         gy = upstream gradient g [B][D];  gy0 = J^T g = [J_p^T g_v, g_p + J_v^T g_v, J_h^T g_v]  and the weight
+//         gradients of that evaluation -- what autograd needs to differentiate a solver step written in PyTorch ops
+//         (the reference's own training path, mode_sep/train/train.py:162, latent_ode/train/train.py:73) and what the
+//         continuous adjoint evaluates (latent_ode/architecture/ode_components.py:50).
+template <int P, int H, int HID, int NRES, int ACT, int POT, int MODE>
 __global__ void __launch_bounds__(NT, 1) rk4_bwd_f32_kernel(BwdArgs a) {
   constexpr int D = 2 * P + H;
   using MapP = TileMap<TMB, P>;
@@ -396,6 +403,36 @@ __global__ void __launch_bounds__(NT, 1) rk4_bwd_f32_kernel(BwdArgs a) {
       }
     };
 
+    if constexpr (MODE == 1) {
+      float p0[4][CP], v0[4][CP], gp[4][CP], gv[4][CP], acc_out[4][CP], xp[4][CP], xv[4][CP];
+      load_pv(a.y_path, p0, v0);
+      load_pv(a.gy, gp, gv);
+      write_stage_input(p0, v0);
+      __syncthreads();
+      mlp_forward(a.t_eval, acc_out);
+      mlp_backward(a.t_eval, gv, xp, xv);
+      if (own) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int64_t g = m0 + 4 * tm + i;
+          if (g < a.B) {
+#pragma unroll
+            for (int j = 0; j < CP; ++j) {
+              a.gy0[g * D + tn * CP + j] = xp[i][j];
+              a.gy0[g * D + P + tn * CP + j] = gp[i][j] + xv[i][j];
+            }
+          }
+        }
+      }
+      __syncthreads();
+      for (int i = tid; i < TMB * H; i += NT) {
+        const int m = i / H, j = i % H;
+        const int64_t g = m0 + m;
+        if (g < a.B) a.gy0[g * D + 2 * P + j] = sGH[j * XSB + m];
+      }
+      continue;
+    }
+
     float lp[4][CP], lv[4][CP];
     load_pv(a.gy + (size_t)(a.T - 1) * a.B * D, lp, lv);
 
@@ -641,22 +678,23 @@ size_t rk4_backward_f32_workspace(const ab200_drift_desc* d, int64_t B, int T) {
   return bwd_ws(d, B).total;
 }
 
-template <int P, int H, int HID, int NRES, int ACT, int POT>
+template <int P, int H, int HID, int NRES, int ACT, int POT, int MODE = 0>
 static int launch_bwd(const BwdArgs& args, int grid, cudaStream_t st) {
   constexpr int GR = (2 * P > HID) ? 2 * P : HID;
   constexpr int WN = (HID > 2 * P) ? HID : 2 * P;
   const size_t rows = (size_t)(2 * P + H) + (size_t)(NRES + 1) * HID + (size_t)NRES * HID + HID + HID + GR + P + H + 2;
   const size_t smem = sizeof(float) * (rows * XSB + 2 * (size_t)KC * WN);
-  auto kern = rk4_bwd_f32_kernel<P, H, HID, NRES, ACT, POT>;
+  auto kern = rk4_bwd_f32_kernel<P, H, HID, NRES, ACT, POT, MODE>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_cuda_error(e); return AB200_ERR_CUDA; }
   kern<<<grid, NT, smem, st>>>(args);
   return check_launch();
 }
 
-int rk4_backward_f32(const ab200_drift_desc* d, const float* w_flat, const float* t_dev, const float* y_path,
-                     const float* grad_y_path, int64_t B, int T, float* grad_y0, float* grad_w_flat, void* ws, size_t ws_bytes,
-                     cudaStream_t st) {
+template <int MODE>
+static int backward_f32_common(const ab200_drift_desc* d, const float* w_flat, const float* t_dev, float t_eval, const float* y_path,
+                               const float* grad_y_path, int64_t B, int T, float* grad_y0, float* grad_w_flat, void* ws, size_t ws_bytes,
+                               cudaStream_t st) {
   const BwdWs w = bwd_ws(d, B);
   if (ws_bytes < w.total) return AB200_ERR_WORKSPACE;
   char* base = (char*)ws;
@@ -674,13 +712,13 @@ int rk4_backward_f32(const ab200_drift_desc* d, const float* w_flat, const float
   if (e != cudaSuccess) { set_cuda_error(e); return AB200_ERR_CUDA; }
 
   BwdArgs a{pk, w_flat, w0d, whd, t_dev, y_path, grad_y_path, grad_y0, priv, B, T, (int)((B + TMB - 1) / TMB),
-            d->time_period, d->pot_idx_a, d->pot_idx_b, d->pot_strength};
+            d->time_period, d->pot_idx_a, d->pot_idx_b, d->pot_strength, t_eval};
   if (d->pos_dim == 64 && d->ctx_dim == 32 && d->hidden == 128 && d->n_res == 2 && d->res_act == 0 && d->potential == 0)
-    rc = launch_bwd<64, 32, 128, 2, 0, 0>(a, grid, st);
+    rc = launch_bwd<64, 32, 128, 2, 0, 0, MODE>(a, grid, st);
   else if (d->pos_dim == 16 && d->ctx_dim == 32 && d->hidden == 128 && d->n_res == 2 && d->res_act == 1 && d->potential == 1)
-    rc = launch_bwd<16, 32, 128, 2, 1, 1>(a, grid, st);
+    rc = launch_bwd<16, 32, 128, 2, 1, 1, MODE>(a, grid, st);
   else if (d->pos_dim == 16 && d->ctx_dim == 32 && d->hidden == 128 && d->n_res == 2 && d->res_act == 1 && d->potential == 0)
-    rc = launch_bwd<16, 32, 128, 2, 1, 0>(a, grid, st);
+    rc = launch_bwd<16, 32, 128, 2, 1, 0, MODE>(a, grid, st);
   else
     return AB200_ERR_UNSUPPORTED;
   if (rc) return rc;
@@ -688,6 +726,18 @@ int rk4_backward_f32(const ab200_drift_desc* d, const float* w_flat, const float
   reduce_unpack_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(priv, grid, grad_w_flat, d->pos_dim, d->ctx_dim, d->hidden,
                                                                      d->n_res);
   return check_launch();
+}
+
+int rk4_backward_f32(const ab200_drift_desc* d, const float* w_flat, const float* t_dev, const float* y_path,
+                     const float* grad_y_path, int64_t B, int T, float* grad_y0, float* grad_w_flat, void* ws, size_t ws_bytes,
+                     cudaStream_t st) {
+  return backward_f32_common<0>(d, w_flat, t_dev, 0.0f, y_path, grad_y_path, B, T, grad_y0, grad_w_flat, ws, ws_bytes, st);
+}
+
+// J^T g of one drift evaluation at (t, y): grad_y [B][D] and grad_w_flat (both OVERWRITTEN); same workspace as the rk4 adjoint
+int drift_vjp_f32(const ab200_drift_desc* d, const float* w_flat, float t, const float* y, const float* g, int64_t B, float* grad_y,
+                  float* grad_w_flat, void* ws, size_t ws_bytes, cudaStream_t st) {
+  return backward_f32_common<1>(d, w_flat, nullptr, t, y, g, B, 1, grad_y, grad_w_flat, ws, ws_bytes, st);
 }
 
 }  // namespace ab200

@@ -129,7 +129,7 @@ class _ResidualBlock(nn.Module):
 class SecondOrderDrift(nn.Module):
     """dy/dt = [v, net([p, v, h, sin, cos]) (+ potential correction), 0] with the reference's parameter tree
     under `.net`, evaluated by the fused kernels only.  `forward(t, y)` is one `ab200_drift_eval` call."""
-    _ab200_kernel_only = True     # forward() is a kernel call without autograd: odeint routes training accordingly
+    _ab200_kernel_only = True     # forward() is a kernel call (ab200_drift_eval, with ab200_drift_vjp as its autograd backward)
 
     def __init__(self, pos_dim: int, ctx_dim: int, hidden: int = 128, n_res: int = 2, res_act: str = "relu",
                  potential: Optional[Tuple[int, int, float]] = None, period: float = 24.0):
@@ -149,5 +149,5 @@ class SecondOrderDrift(nn.Module):
         return DriftSpec(desc, params)
 
     def forward(self, t, y):
-        from .odeint import drift_eval
-        return drift_eval(self.spec(), self.spec().flat_params().detach(), float(t), y)
+        from .odeint import drift_apply
+        return drift_apply(self.spec(), t, y)

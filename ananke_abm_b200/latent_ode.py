@@ -44,7 +44,7 @@ class GenerativeODEConfig:                  # latent_ode/config.py:18-71 (fields
 
 
 class ODEFunc(nn.Module):                   # model.py:19-117 -- parameter holder; `describe_drift` recognises this shape
-    _ab200_kernel_only = True     # forward() is a kernel call without autograd: odeint routes training accordingly
+    _ab200_kernel_only = True     # forward() is a kernel call (ab200_drift_eval, with ab200_drift_vjp as its autograd backward)
     def __init__(self, config, state_dim: int, position_dim: int, hidden_dim: int, num_residual_blocks: int):
         super().__init__()
         self.config, self.state_dim, self.position_dim = config, state_dim, position_dim
@@ -59,11 +59,11 @@ class ODEFunc(nn.Module):                   # model.py:19-117 -- parameter holde
 
     def forward(self, t: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
         from .drift import describe_drift
-        from .odeint import drift_eval
+        from .odeint import drift_apply
         spec = describe_drift(self)
         if spec is None:
             raise RuntimeError("drift shape not instantiated in libananke_b200.so")
-        return drift_eval(spec, spec.flat_params().detach(), float(t), y)
+        return drift_apply(spec, t, y)
 
     # torchsde interface of the reference (model.py:119-130): noise on the state only, none on the context h
     noise_type, sde_type = "diagonal", "ito"
@@ -109,8 +109,8 @@ class GenerativeODE(nn.Module):
         s0 = torch.cat([p0, torch.zeros_like(p0)], dim=-1)
         y0 = torch.cat([s0, h0], dim=-1)
         if cfg.enable_sde:
-            # model.py:192-194: sdeint(self.ode_func, y0, times, method='euler', dt=0.01).  Forward only here: sdeint
-            # refuses calls that need gradients (the reference trains through it; that backward is not built)
+            # model.py:192-194: sdeint(self.ode_func, y0, times, method='euler', dt=0.01); differentiable (the reference's
+            # default training path goes through it): every Euler-Maruyama step carries its own backward
             from .sdeint import sdeint
             path = sdeint(self.ode_func, y0, times, method="euler", dt=0.01, options={"dtype": torch.float32},
                           seed=odeint_kwargs.pop("seed", None))

@@ -45,6 +45,8 @@ class ModeSepConfig:                       # mode_sep/config.py:9-71 (fields the
 
 def _solver_options(config) -> dict:
     opt = {"precision": getattr(config, "precision", "f32")}
+    if getattr(config, "adjoint", False) and getattr(config, "adjoint_mode", None):
+        opt["adjoint_mode"] = config.adjoint_mode          # "continuous" (torchdiffeq semantics, default) | "discrete"
     if config.ode_method == "dopri5" and opt["precision"] == "bf16":
         opt["error_norm"] = getattr(config, "error_norm", "shard")
         if getattr(config, "forward_operands", None):       # "fp16x2" (default of the solver) | "fp16" | "bf16"
@@ -62,18 +64,18 @@ class ODEFunc(nn.Module):                  # model.py:30-38 -- parameter holder;
 
 
 class WrappedSDE(nn.Module):               # model.py:49-73 -- f(t, y) = [v, net([p, v, h, sin, cos]), 0]
-    _ab200_kernel_only = True     # forward() is a kernel call without autograd: odeint routes training accordingly
+    _ab200_kernel_only = True     # forward() is a kernel call (ab200_drift_eval, with ab200_drift_vjp as its autograd backward)
     def __init__(self, func: ODEFunc, emb_dim: int, context_dim: int):
         super().__init__()
         self.func, self.emb_dim, self.context_dim = func, emb_dim, context_dim
 
     def forward(self, t: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
         from .drift import describe_drift
-        from .odeint import drift_eval
+        from .odeint import drift_apply
         spec = describe_drift(self)
         if spec is None:
             raise RuntimeError("drift shape not instantiated in libananke_b200.so")
-        return drift_eval(spec, spec.flat_params().detach(), float(t), y)
+        return drift_apply(spec, t, y)
 
     # torchsde interface of the reference (model.py:75-89): drift f = forward, unit diagonal diffusion on [p, v] only
     def f(self, t: torch.Tensor, y: torch.Tensor) -> torch.Tensor:

@@ -202,6 +202,51 @@ def drift_eval(spec: DriftSpec, w_flat: torch.Tensor, t: float, y: torch.Tensor,
     return out
 
 
+def drift_vjp(spec: DriftSpec, w_flat: torch.Tensor, t: float, y: torch.Tensor, grad_out: torch.Tensor):
+    """J^T grad_out of one drift evaluation at (t, y) in strict fp32 (ab200_drift_vjp) -> (grad_y [B, D], grad_w_flat)."""
+    L = _lib.lib()
+    _require_cuda(y, "y")
+    B = y.shape[0]
+    yc, gc, wc = y.contiguous().float(), grad_out.contiguous().float(), w_flat.contiguous().float()
+    gy = torch.empty_like(yc)
+    gw = torch.empty_like(wc)
+    nbytes = L.ab200_drift_vjp_workspace_bytes(C.byref(spec.desc), B)
+    ws = torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=y.device)
+    rc = L.ab200_drift_vjp(C.byref(spec.desc), wc.data_ptr(), float(t), yc.data_ptr(), gc.data_ptr(), B, gy.data_ptr(), gw.data_ptr(),
+                           ws.data_ptr(), ws.numel(), _stream_ptr())
+    _lib.check(rc, "ab200_drift_vjp")
+    return gy, gw
+
+
+class _DriftFn(torch.autograd.Function):
+    """f(t, y) of a recognised drift on the strict-fp32 kernels WITH a backward: `ab200_drift_eval` forward,
+    `ab200_drift_vjp` backward.  This is what makes a solver written in PyTorch ops over the kernel-evaluated drift
+    differentiable (autograd through dopri5, the reference's training path) and what the continuous adjoint evaluates."""
+
+    @staticmethod
+    def forward(ctx, y, w_flat, spec: DriftSpec, t: float):
+        yd, wd = y.detach(), w_flat.detach()
+        ctx.spec, ctx.t = spec, float(t)
+        ctx.save_for_backward(yd, wd)
+        return drift_eval(spec, wd, float(t), yd)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        y, w = ctx.saved_tensors
+        gy, gw = drift_vjp(ctx.spec, w, ctx.t, y, g)
+        return gy, gw, None, None
+
+
+def drift_apply(spec: DriftSpec, t, y: torch.Tensor) -> torch.Tensor:
+    """One evaluation of a recognised drift through the kernels; differentiable (first order) w.r.t. y and the module's
+    parameters whenever autograd is recording."""
+    tf = float(t)
+    if torch.is_grad_enabled() and (y.requires_grad or any(p.requires_grad for p in spec.params)):
+        return _DriftFn.apply(y, spec.flat_params(), spec, tf)
+    return drift_eval(spec, spec.flat_params().detach(), tf, y)
+
+
 # --------------------------------------------------------------------------------------------------
 # fused elementwise stage algebra for arbitrary `func`
 # --------------------------------------------------------------------------------------------------
@@ -232,10 +277,12 @@ def _combine(y, ks, coef, dt):
     return _StageCombine.apply(float(dt), list(coef), y, *ks)
 
 
-def _rk4_generic(func, y0, t, t_host):
+def _rk4_generic(func, y0, t, t_host, time_as_float: bool = False):
     third, two_thirds = 1.0 / 3.0, 2.0 / 3.0
     sol = [y0]
     y = y0
+    if time_as_float:       # kernel-evaluated func: stage times as host scalars, computed in the state's dtype like the tensor path
+        t = t_host.to(y0.dtype)
     for i in range(t.numel() - 1):
         t0, t1 = t[i], t[i + 1]
         dt_t = t1 - t0
@@ -272,7 +319,7 @@ class _Dopri5:
     decision reads ONE float per attempted step from the device (the squared-error sum)."""
 
     def __init__(self, f: Callable, y0, rtol, atol, first_step=None, safety=0.9, ifactor=10.0, dfactor=0.2,
-                 max_num_steps=2 ** 31 - 1, dtype=torch.float64, norm=None, **unused):
+                 max_num_steps=2 ** 31 - 1, dtype=torch.float64, norm=None, time_as_float: bool = False, segments=None, **unused):
         if unused:
             warnings.warn(f"Dopri5: Unexpected arguments {unused}")
         if norm is not None:
@@ -285,8 +332,16 @@ class _Dopri5:
         self.tdtype = torch.promote_types(dtype, y0.dtype)
         self.n_accepted = self.n_rejected = 0
         self._sumsq = torch.zeros(1, dtype=torch.float32, device=y0.device)
+        self.time_as_float = bool(time_as_float)      # kernel-evaluated drifts take the time as a host scalar (no device round trip)
+        # torchdiffeq's mixed norm (misc.py `_mixed_norm`: max over the RMS norms of the tuple components) for a flat state that
+        # packs several components: `segments` = [(offset, length), ...]; None = one RMS norm over the whole state
+        self.segments = None if segments is None else [(int(o), int(n)) for o, n in segments if int(n) > 0]
+        if self.segments is not None:
+            self._sumsq = torch.zeros(len(self.segments), dtype=torch.float32, device=y0.device)
 
-    def _tt(self, v: float) -> torch.Tensor:
+    def _tt(self, v: float):
+        if self.time_as_float:
+            return float(torch.tensor(v, dtype=self.y0.dtype)) if self.y0.dtype != torch.float64 else float(v)
         return torch.tensor(v, dtype=self.y0.dtype, device=self.y0.device)
 
     def _cast(self, v: float) -> float:
@@ -296,7 +351,10 @@ class _Dopri5:
         return float(v)
 
     def _rms(self, x: torch.Tensor) -> float:
-        return float(x.float().pow(2).mean().sqrt())
+        if self.segments is None:
+            return float(x.float().pow(2).mean().sqrt())
+        flat = x.reshape(-1).float()
+        return float(torch.stack([flat[o:o + n].pow(2).mean() for o, n in self.segments]).max().sqrt())
 
     def _initial_step(self, t0: float, f0):
         y0 = self.y0
@@ -329,11 +387,23 @@ class _Dopri5:
         csol = (C.c_float * 8)(*([float(c) for c in _DP_C_SOL] + [0.0]))
         cerr = (C.c_float * 8)(*([float(c) for c in _DP_C_ERR] + [0.0]))
         self._sumsq.zero_()
-        rc = L.ab200_rk_combine_errnorm(y0.contiguous().data_ptr(), C.cast(ptrs, C.c_void_p), C.cast(csol, C.c_void_p),
-                                        C.cast(cerr, C.c_void_p), 7, float(dt), self.rtol, self.atol, None,
-                                        self._sumsq.data_ptr(), n, _stream_ptr())
-        _lib.check(rc, "ab200_rk_combine_errnorm")
-        ratio = float(torch.sqrt(self._sumsq[0] / n))
+        y0c = y0.contiguous()
+        if self.segments is None:
+            rc = L.ab200_rk_combine_errnorm(y0c.data_ptr(), C.cast(ptrs, C.c_void_p), C.cast(csol, C.c_void_p),
+                                            C.cast(cerr, C.c_void_p), 7, float(dt), self.rtol, self.atol, None,
+                                            self._sumsq.data_ptr(), n, _stream_ptr())
+            _lib.check(rc, "ab200_rk_combine_errnorm")
+            ratio = float(torch.sqrt(self._sumsq[0] / n))
+        else:
+            # one error-norm pass per component of the packed state; the ratio is the max of the per-component RMS values
+            for i, (o, m) in enumerate(self.segments):
+                sp = (C.c_void_p * 8)(*([k.data_ptr() + 4 * o for k in kc] + [0]))
+                rc = L.ab200_rk_combine_errnorm(y0c.data_ptr() + 4 * o, C.cast(sp, C.c_void_p), C.cast(csol, C.c_void_p),
+                                                C.cast(cerr, C.c_void_p), 7, float(dt), self.rtol, self.atol, None,
+                                                self._sumsq.data_ptr() + 4 * i, m, _stream_ptr())
+                _lib.check(rc, "ab200_rk_combine_errnorm")
+            cnt = torch.tensor([float(m) for _, m in self.segments], dtype=torch.float32, device=y0.device)
+            ratio = float(torch.sqrt((self._sumsq / cnt).max()))
         return y1, f1, ratio, ks
 
     def _next_dt(self, dt: float, ratio: float) -> float:
@@ -417,7 +487,8 @@ def odeint(func, y0, t, *, rtol: float = 1e-7, atol: float = 1e-9, method: Optio
     spec = describe_drift(func) if (y0.dim() == 2 and not decreasing) else None
 
     if method == "rk4":
-        for k in ("dtype", "norm"):
+        time_as_float = bool(options.pop("time_as_float", False))
+        for k in ("dtype", "norm", "segments", "adjoint_mode"):
             options.pop(k, None)
         if options:
             warnings.warn(f"rk4: Unexpected arguments {options}")
@@ -427,23 +498,15 @@ def odeint(func, y0, t, *, rtol: float = 1e-7, atol: float = 1e-9, method: Optio
             if precision == _lib.PREC_BF16 and needs_grad and spec.tc_stage_supported():
                 return _StageRK4TC.apply(y0, t, w_flat, spec, t_host)
             return _FusedRK4.apply(y0, t, w_flat, spec, precision, t_host)
+        if y0.dtype != torch.float32:
+            raise _lib.Ab200Error(f"rk4: the fused stage-combine kernels are fp32, got y0 of {y0.dtype} (cast the state)")
         f = _wrap_func(func, y0, decreasing)
         tt = -t if decreasing else t
         th = -t_host if decreasing else t_host
-        return _rk4_generic(f, y0, tt.to(y0.dtype), th)
+        return _rk4_generic(f, y0, tt.to(y0.dtype), th, time_as_float)
     if method == "dopri5":
         # Modules whose forward() is a bare kernel call (this package's mirrors) cannot be differentiated by autograd: a
         # training call on them takes the tensor-core stage path (the only differentiable dopri5 for them) or fails loudly.
-        kernel_only = bool(getattr(func, "_ab200_kernel_only", False))
-        wants_grad = spec is not None and torch.is_grad_enabled() and (y0.requires_grad or any(p.requires_grad for p in spec.params))
-        if kernel_only and wants_grad and precision != _lib.PREC_BF16:
-            if spec.tc_stage_supported():
-                warnings.warn("dopri5 training on a kernel-evaluated drift runs on the tensor-core stage path "
-                              "(options={'precision': 'bf16'}); the strict-fp32 dopri5 path is forward-only")
-                precision = _lib.PREC_BF16
-            else:
-                raise _lib.Ab200Error("dopri5 training needs the tensor-core stage path, which is instantiated for the mode_sep "
-                                      "drift shape only; use method='rk4' (fused fp32 adjoint) or the reference's torch module")
         if (spec is not None and y0.shape[1] == spec.state_dim and precision == _lib.PREC_BF16 and spec.tc_stage_supported()
                 and y0.dtype == torch.float32):
             opts = {}
@@ -460,10 +523,15 @@ def odeint(func, y0, t, *, rtol: float = 1e-7, atol: float = 1e-9, method: Optio
                 return _StageDopri5TC.apply(y0, t, w_flat, spec, t_host, float(rtol), float(atol), opts)
             with torch.no_grad():
                 return _StageDopri5TC.apply(y0, t, w_flat.detach(), spec, t_host, float(rtol), float(atol), opts)
-        if spec is not None and y0.shape[1] == spec.state_dim and not torch.is_grad_enabled():
-            w_flat = spec.flat_params().detach()
-            f = lambda tt, yy: drift_eval(spec, w_flat, float(tt), yy, _lib.PREC_F32)   # noqa: E731
+        if spec is not None and y0.shape[1] == spec.state_dim and y0.dtype == torch.float32:
+            # strict fp32: every drift evaluation is ab200_drift_eval; when autograd is recording, each evaluation carries
+            # ab200_drift_vjp as its backward, so `loss.backward()` through the solver ops (the reference's training path,
+            # latent_ode/train/train.py:73) runs on kernels for both reference drift shapes
+            f = lambda tt, yy: drift_apply(spec, tt, yy)   # noqa: E731
+            options["time_as_float"] = True
         else:
+            if y0.dtype != torch.float32:
+                raise _lib.Ab200Error(f"dopri5: the fused stage-combine kernels are fp32, got y0 of {y0.dtype} (cast the state)")
             f = _wrap_func(func, y0, decreasing)
         th = -t_host if decreasing else t_host
         solver = _Dopri5(f, y0, rtol, atol, **options)
@@ -473,35 +541,44 @@ def odeint(func, y0, t, *, rtol: float = 1e-7, atol: float = 1e-9, method: Optio
 
 
 def _wrap_func(func, y0, decreasing: bool):
+    def conv(tt, yy):      # torchdiffeq casts t to the state's dtype before every user call; host scalars pass through
+        return tt.to(yy.dtype) if torch.is_tensor(tt) else tt
     if decreasing:
-        return lambda tt, yy: -func((-tt).to(yy.dtype), yy)
-    return lambda tt, yy: func(tt.to(yy.dtype), yy)
+        return lambda tt, yy: -func(conv(-tt, yy), yy)
+    return lambda tt, yy: func(conv(tt, yy), yy)
 
 
 def odeint_adjoint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, event_fn=None, adjoint_rtol=None,
                    adjoint_atol=None, adjoint_method=None, adjoint_options=None, adjoint_params=None):
-    """Drop-in for `torchdiffeq.odeint_adjoint`.
+    """Drop-in for `torchdiffeq.odeint_adjoint` (the call at latent_ode/architecture/ode_components.py:50).
 
-    For the recognised drift nets on a fixed grid the backward pass is the fused discrete adjoint
-    (`ab200_rk4_backward`): O(T) saved rows, gradients equal to autograd through the solver to round-off, which is
-    what the reference's live training path computes.  Other cases integrate the augmented system backwards
-    (tdq adjoint.py), re-seeding y from the saved forward rows.
+    Default = torchdiffeq's semantics: forward solve under no_grad (any `options['precision']`), backward by integrating the
+    augmented system [y, a_y, a_theta] from t[i] to t[i-1] with adjoint_rtol / adjoint_atol / adjoint_method and the mixed
+    error norm, re-seeding y from the saved rows (adjoint.py).  For the two reference drift shapes the augmented dynamics run
+    on kernels (`ab200_drift_eval` + `ab200_drift_vjp`, strict fp32).
+
+    Explicit opt-in `options={'adjoint_mode': 'discrete'}`: the discrete adjoint of the accepted steps (what autograd through
+    `odeint` computes, i.e. the gradient of the reference's LIVE training paths), on the fused fp32 rk4 adjoint or the tensor-core
+    stage path according to `options['precision']`.  It ignores adjoint_* by construction, so passing any of them together
+    with this mode is an error rather than a silent override.
     """
+    if event_fn is not None:
+        raise NotImplementedError("event handling is outside the reference's path")
     if adjoint_params is None and not isinstance(func, torch.nn.Module):
         raise ValueError("func must be an instance of nn.Module to specify the adjoint parameters; alternatively they "
                          "can be specified explicitly via the `adjoint_params` argument.")
     method = "dopri5" if method is None else method
-    spec = describe_drift(func) if y0.dim() == 2 else None
-    if method == "rk4" and spec is not None:
-        return odeint(func, y0, t, rtol=rtol, atol=atol, method=method, options=options)
-    if method == "dopri5" and spec is not None and spec.tc_stage_supported() and (
-            getattr(func, "_ab200_kernel_only", False) or (options or {}).get("precision", _DEFAULT_PRECISION["value"]) == "bf16"):
-        # discrete adjoint of the accepted steps on the tensor-core stage kernels: O(steps) saved state, gradients equal to
-        # the continuous adjoint up to the solver tolerance (documented deviation, DESIGN.md §8)
-        opt = dict(options or {})
-        opt["precision"] = "bf16"
+    opt = dict(options or {})
+    mode = opt.pop("adjoint_mode", "continuous")
+    if mode == "discrete":
+        given = [k for k, v in (("adjoint_rtol", adjoint_rtol), ("adjoint_atol", adjoint_atol), ("adjoint_method", adjoint_method),
+                                ("adjoint_options", adjoint_options), ("adjoint_params", adjoint_params)) if v is not None]
+        if given:
+            raise ValueError(f"adjoint_mode='discrete' differentiates the forward steps themselves: {given} would be ignored")
         return odeint(func, y0, t, rtol=rtol, atol=atol, method=method, options=opt)
+    if mode != "continuous":
+        raise ValueError(f"unknown adjoint_mode {mode!r} (choose 'continuous' or 'discrete')")
     from .adjoint import continuous_adjoint
-    return continuous_adjoint(func, y0, t, rtol=rtol, atol=atol, method=method, options=options,
+    return continuous_adjoint(func, y0, t, rtol=rtol, atol=atol, method=method, options=opt,
                               adjoint_rtol=adjoint_rtol, adjoint_atol=adjoint_atol, adjoint_method=adjoint_method,
                               adjoint_options=adjoint_options, adjoint_params=adjoint_params)

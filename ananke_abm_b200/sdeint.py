@@ -32,6 +32,69 @@ def _drift_module(sde):
     return None
 
 
+class _EulerMaruyamaStep(torch.autograd.Function):
+    """y_next = y + f h + g sqrt(h) xi  as ONE kernel pass (ab200_sde_euler_step, xi = counter-based Philox noise of (seed, step))
+    with its backward: d/dy = 1, d/df = h, d/dg = sqrt(h) xi.  The drift evaluation feeding `f` carries its own backward
+    (ab200_drift_vjp), so autograd through the whole Euler-Maruyama loop -- the reference's default latent_ode training path,
+    latent_ode/train/train.py:57-74 with enable_sde=True -- runs on kernels."""
+
+    @staticmethod
+    def forward(ctx, y, f, g, h: float, seed: int, step: int):
+        L = _lib.lib()
+        B, D = y.shape
+        yc, fc, gc = y.contiguous().float(), f.contiguous().float(), g.contiguous().float()
+        out = torch.empty_like(yc)
+        need_xi = ctx.needs_input_grad[2]
+        xi = torch.empty_like(yc) if need_xi else None
+        rc = L.ab200_sde_euler_step(yc.data_ptr(), fc.data_ptr(), gc.data_ptr(), 1, B, D, float(h), int(seed), int(step), out.data_ptr(),
+                                    None if xi is None else xi.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "ab200_sde_euler_step")
+        ctx.h = float(h)
+        if need_xi:
+            ctx.save_for_backward(xi)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, go):
+        gg = None
+        if ctx.needs_input_grad[2]:
+            (xi,) = ctx.saved_tensors
+            gg = go * (xi * (ctx.h ** 0.5))
+        return go, go * ctx.h, gg, None, None, None
+
+
+def _integrate_with_grad(sde, y0, ts, dt: float, seed: int):
+    """the same scheme as `_integrate`, recorded by autograd (training through the sampler)"""
+    from .odeint import drift_apply
+    t_list = [float(v) for v in ts.tolist()]
+    dev = y0.device
+    mod = _drift_module(sde)
+    spec = describe_drift(mod) if mod is not None else None
+    rows = [y0]
+    curr_y, prev_y = y0.float(), None
+    curr_t = prev_t = t_list[0]
+    step = 0
+    for out_t in t_list[1:]:
+        while curr_t < out_t:
+            next_t = min(curr_t + dt, t_list[-1])
+            h = float(torch.tensor(next_t - curr_t, dtype=torch.float32))
+            tt = torch.tensor(curr_t, dtype=torch.float32, device=dev)
+            f = drift_apply(spec, curr_t, curr_y) if spec is not None else sde.f(tt, curr_y).float()
+            g = sde.g(tt, curr_y).float()
+            if g.shape != curr_y.shape:
+                raise ValueError("sdeint: diagonal noise expected (g(t, y) must have the shape of y)")
+            prev_t, curr_t = curr_t, next_t
+            prev_y, curr_y = curr_y, _EulerMaruyamaStep.apply(curr_y, f, g, h, seed, step)
+            step += 1
+        if prev_y is None or curr_t == out_t:
+            rows.append(curr_y)
+        else:
+            w = float(torch.tensor((out_t - prev_t) / (curr_t - prev_t), dtype=torch.float32))
+            rows.append(torch.lerp(prev_y, curr_y, w))
+    return torch.stack(rows, dim=0)
+
+
 @torch.no_grad()
 def _integrate(sde, y0, ts, dt: float, seed: int, return_noise: bool = False):
     from .odeint import drift_eval
@@ -93,10 +156,9 @@ def sdeint(sde, y0: torch.Tensor, ts: torch.Tensor, bm=None, method: Optional[st
     if ts.dim() != 1 or ts.numel() < 1 or bool((ts[1:] <= ts[:-1]).any()):
         raise ValueError("ts must be one-dimensional and strictly increasing")
     params = list(sde.parameters()) if isinstance(sde, torch.nn.Module) else []
-    if torch.is_grad_enabled() and (y0.requires_grad or any(p.requires_grad for p in params)):
-        # the reference's latent_ode trains THROUGH sdeint; that backward pass is not built
-        raise _lib.Ab200Error("sdeint is forward-only here: wrap the call in torch.no_grad() (sampling / inference), "
-                              "or train on the ODE branch (enable_sde=False)")
     if seed is None:
         seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    if torch.is_grad_enabled() and (y0.requires_grad or any(p.requires_grad for p in params)):
+        # the reference's latent_ode trains THROUGH sdeint (latent_ode/train/train.py:57-74): same steps, recorded by autograd
+        return _integrate_with_grad(sde, y0, ts.detach().cpu(), float(dt), int(seed))
     return _integrate(sde, y0.detach(), ts.detach().cpu(), float(dt), int(seed))

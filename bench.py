@@ -128,6 +128,7 @@ def build_model(cfg, precision, device):
     mc.precision = precision
     mc.ode_method = cfg["method"]            # rtol = atol = 1e-5 (mode_sep/config.py:27-28) apply to dopri5 only
     mc.adjoint = bool(cfg.get("adjoint", False))
+    mc.adjoint_mode = "discrete"             # c5: the odeint_adjoint seam with the explicit discrete-adjoint opt-in (tensor-core stage path)
     mc.error_norm = "global"                 # N > 1: one RMS error norm over all ranks' agents, as a single process would use
     model = ab.GATODEModel(7, mc, heads=cfg["heads"]).to(device)
     ei, feats = synthetic_zone_graph(cfg["Z"], k=6, seed=42)

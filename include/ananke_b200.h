@@ -101,6 +101,17 @@ int ab200_drift_eval(const ab200_drift_desc* d, const float* w_flat, float t, co
                      float* out, void* workspace, size_t workspace_bytes, int32_t precision,
                      ab200_stream_t stream);
 
+/* Vector-Jacobian product of ONE drift evaluation f(t, y) = [v, net(p, v, h, t) (+ potential term), 0] in strict fp32:
+ *   grad_y [B][D]  = J_y^T grad_out = [J_p^T g_v, g_p + J_v^T g_v, J_h^T g_v]     (OVERWRITTEN)
+ *   grad_w_flat    = sum over agents of d(net)/dw ^T g_v, ab200_drift_param_count order     (OVERWRITTEN)
+ * This is the backward of one `func(t, y)` call: it makes a solver written in PyTorch ops over the kernel-evaluated
+ * drift differentiable (the reference trains by autograd through the solver: mode_sep/train/train.py:162,
+ * latent_ode/train/train.py:73 -- dopri5 there), and it is the a^T df/dy, a^T df/dtheta evaluation of the continuous adjoint
+ * (torchdiffeq odeint_adjoint, the call at latent_ode/architecture/ode_components.py:50).  Same shapes as ab200_rk4_backward. */
+size_t ab200_drift_vjp_workspace_bytes(const ab200_drift_desc* d, int64_t B);
+int ab200_drift_vjp(const ab200_drift_desc* d, const float* w_flat, float t, const float* y, const float* grad_out, int64_t B,
+                    float* grad_y, float* grad_w_flat, void* workspace, size_t workspace_bytes, ab200_stream_t stream);
+
 /* ---- generic-func path: fused Runge-Kutta stage combine (+ error norm) ------------------------
  * For an arbitrary `func` evaluated by the caller.  out[i] = y[i] + dt * sum_j coef[j] * k_j[i]
  * (tdq: rk_common.py `_runge_kutta_step`: yi = y0 + sum(k[..., :i+1] * (beta_i * dt))).

@@ -54,6 +54,7 @@ class LatentDims:            # latent_ode/config.py:21-35,57 ; feature dims from
     mode_feature_dim: int = 4
     num_residual_blocks: int = 2
     correction_strength: float = 1.0
+    use_second_order_sde: bool = True       # latent_ode/config.py: the only branch restated (and the reference default)
     ode_method: str = "dopri5"
     num_modes: int = 5
     num_purposes: int = 6
@@ -85,6 +86,62 @@ class _Holder(nn.Module):
     pass
 
 
+class OracleWrappedSDE(nn.Module):
+    """The reference's `WrappedSDE(func=ODEFunc(...), emb_dim, context_dim)` (mode_sep/architecture/model.py:49-73): same
+    attribute structure (`.func.net`, `.emb_dim`, `.context_dim`) and the same eager forward, so that whatever consumes the
+    solver seam sees what it would see from the unmodified reference class.  `calls` counts eager evaluations (tests use it to
+    prove that a drop-in solver evaluated the drift on its own kernels instead)."""
+
+    def __init__(self, net: nn.Sequential, emb_dim: int, context_dim: int):
+        super().__init__()
+        self.func = _Holder()
+        self.func.net = net
+        self.emb_dim, self.context_dim = emb_dim, context_dim
+        self.calls = 0
+
+    def forward(self, t: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        self.calls += 1
+        E, H = self.emb_dim, self.context_dim
+        p, v, h = torch.split(y, [E, E, H], dim=-1)
+        s = torch.sin(t * 2 * torch.pi / 24.0).expand(y.shape[0])
+        c = torch.cos(t * 2 * torch.pi / 24.0).expand(y.shape[0])
+        a = self.func.net(torch.cat([p, v, h, torch.stack([s, c], dim=-1)], dim=-1))
+        return torch.cat([v, a, torch.zeros_like(h)], dim=-1)
+
+
+class OracleLatentFunc(nn.Module):
+    """The reference's latent `ODEFunc(config, state_dim, position_dim, ...)`, second-order branch
+    (latent_ode/architecture/model.py:19-117): `.net`, `.config`, `.state_dim`, `.position_dim` and the eager forward with the
+    potential-gradient correction in closed form (see OracleLatentODE.rhs)."""
+    IS_MOVING_DIM = 0
+    IS_STATIONARY_DIM = 0
+
+    def __init__(self, dims, net: nn.Sequential, position_dim: int):
+        super().__init__()
+        self.config = dims
+        self.net = net
+        self.position_dim, self.state_dim = position_dim, 2 * position_dim
+        self.calls = 0
+
+    def forward(self, t: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
+        self.calls += 1
+        d, P = self.config, self.position_dim
+        p, v, h = torch.split(y, [P, P, d.hidden_dim], dim=-1)
+        s = torch.sin(t * 2 * torch.pi / 24).expand(y.shape[0])
+        c = torch.cos(t * 2 * torch.pi / 24).expand(y.shape[0])
+        dv = self.net(torch.cat([p, v, h, torch.stack([s, c], dim=-1)], dim=-1))
+        i_purp = d.zone_embed_dim
+        i_mode = d.zone_embed_dim + d.purpose_feature_dim
+        a = torch.sigmoid(p[:, i_mode])
+        b = torch.sigmoid(p[:, i_purp])
+        r = 2.0 * (a + b - 1.0)
+        corr = torch.zeros_like(dv)
+        corr[:, i_mode] = -r * a * (1 - a)
+        corr[:, i_purp] = -r * b * (1 - b)
+        dv = dv + d.correction_strength * corr
+        return torch.cat([v, dv, torch.zeros_like(h)], dim=-1)
+
+
 class OracleModeSep(nn.Module):
     """Same parameter tree as the reference ModeSepModel (mode_sep/architecture/model.py:92-136)."""
 
@@ -98,19 +155,12 @@ class OracleModeSep(nn.Module):
         self.zone_embed = nn.Embedding(Z, d.zone_emb_dim)
         self.context_encoder = nn.Sequential(nn.Linear(2 + 2 * d.zone_emb_dim, d.hidden_dim), nn.ReLU(),
                                              nn.Linear(d.hidden_dim, H))
-        self.odefunc = _Holder()
-        self.odefunc.func = _Holder()
-        self.odefunc.func.net = _drift_net(2 * E + H + 2, d.hidden_dim, d.num_res_blocks, E, "relu")
+        self.odefunc = OracleWrappedSDE(_drift_net(2 * E + H + 2, d.hidden_dim, d.num_res_blocks, E, "relu"), E, H)
         self.decoder = nn.Sequential(nn.Linear(E, d.hidden_dim), nn.ReLU(), nn.Linear(d.hidden_dim, E))
 
     # ---- WrappedSDE.forward (mode_sep/architecture/model.py:56-73)
     def rhs(self, t: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
-        E, H = self.dims.emb_dim, self.dims.context_dim
-        p, v, h = torch.split(y, [E, E, H], dim=-1)
-        s = torch.sin(t * 2 * torch.pi / 24.0).expand(y.shape[0])
-        c = torch.cos(t * 2 * torch.pi / 24.0).expand(y.shape[0])
-        a = self.odefunc.func.net(torch.cat([p, v, h, torch.stack([s, c], dim=-1)], dim=-1))
-        return torch.cat([v, a, torch.zeros_like(h)], dim=-1)
+        return self.odefunc(t, y)
 
     # ---- ModeSepModel.forward initial state (model.py:150-155)
     def initial_state(self, home_idx, work_idx, traits) -> torch.Tensor:
@@ -131,7 +181,8 @@ class OracleModeSep(nn.Module):
         return pred, logits, v_t
 
     def solve(self, y0, times):
-        return tdq.odeint(self.rhs, y0, times, method=self.dims.ode_method, rtol=self.dims.rtol,
+        # the reference's call shape (mode_sep/architecture/model.py:184-191): the drift MODULE goes through the solver seam
+        return tdq.odeint(self.odefunc, y0, times, method=self.dims.ode_method, rtol=self.dims.rtol,
                           atol=self.dims.atol)
 
     def forward(self, times_union, home_idx, work_idx, person_traits_raw):
@@ -195,9 +246,8 @@ class OracleLatentODE(nn.Module):
                                      nn.Linear(d.encoder_hidden_dim, 2 * d.hidden_dim))
         self.position_dim = d.zone_embed_dim + d.purpose_feature_dim + d.mode_feature_dim
         self.state_dim = 2 * self.position_dim
-        self.ode_func = _Holder()
-        self.ode_func.net = _drift_net(self.state_dim + d.hidden_dim + 2, d.ode_hidden_dim,
-                                       d.num_residual_blocks, self.position_dim, "tanh")
+        self.ode_func = OracleLatentFunc(d, _drift_net(self.state_dim + d.hidden_dim + 2, d.ode_hidden_dim,
+                                                       d.num_residual_blocks, self.position_dim, "tanh"), self.position_dim)
         self.decoder_loc = nn.Linear(d.zone_embed_dim, d.zone_embed_dim)
         self.decoder_purpose = nn.Linear(d.purpose_feature_dim, d.num_purposes)
         self.decoder_mode = nn.Linear(d.mode_feature_dim, d.num_modes)
@@ -209,21 +259,7 @@ class OracleLatentODE(nn.Module):
     # applied only when any potential term is > 0 (the reference's `torch.any(potential > 0)` branch,
     # which is a no-op otherwise because the gradient is then exactly zero too).
     def rhs(self, t: torch.Tensor, y: torch.Tensor) -> torch.Tensor:
-        d, P = self.dims, self.position_dim
-        p, v, h = torch.split(y, [P, P, d.hidden_dim], dim=-1)
-        s = torch.sin(t * 2 * torch.pi / 24).expand(y.shape[0])
-        c = torch.cos(t * 2 * torch.pi / 24).expand(y.shape[0])
-        dv = self.ode_func.net(torch.cat([p, v, h, torch.stack([s, c], dim=-1)], dim=-1))
-        i_purp = d.zone_embed_dim
-        i_mode = d.zone_embed_dim + d.purpose_feature_dim
-        a = torch.sigmoid(p[:, i_mode])
-        b = torch.sigmoid(p[:, i_purp])
-        r = 2.0 * (a + b - 1.0)
-        corr = torch.zeros_like(dv)
-        corr[:, i_mode] = -r * a * (1 - a)
-        corr[:, i_purp] = -r * b * (1 - b)
-        dv = dv + d.correction_strength * corr
-        return torch.cat([v, dv, torch.zeros_like(h)], dim=-1)
+        return self.ode_func(t, y)
 
     def initial_state(self, person_features, home_zone_features, work_zone_features, purp0, mode0, eps):
         d = self.dims
@@ -236,7 +272,8 @@ class OracleLatentODE(nn.Module):
         return torch.cat([p0, torch.zeros_like(p0), h0], dim=-1), mu, logvar
 
     def solve(self, y0, times, rtol=1e-7, atol=1e-9):
-        return tdq.odeint(self.rhs, y0, times, method=self.dims.ode_method, rtol=rtol, atol=atol,
+        # the reference's call shape (latent_ode/architecture/model.py:192,196)
+        return tdq.odeint(self.ode_func, y0, times, method=self.dims.ode_method, rtol=rtol, atol=atol,
                           options={"dtype": torch.float32})
 
     def head(self, y_path, all_zone_features):

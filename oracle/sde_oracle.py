@@ -55,15 +55,16 @@ def normals(B: int, D: int, seed: int, step: int) -> np.ndarray:
     return np.stack([z0, z1, z2, z3], axis=-1).reshape(B, D)
 
 
-def sdeint_euler(sde, y0: torch.Tensor, ts: torch.Tensor, dt: float, seed: int) -> torch.Tensor:
-    """[len(ts), B, D]; `sde.f(t, y)`, `sde.g(t, y)` (diagonal noise) are the reference's own modules on the CPU."""
+def sdeint_euler(sde, y0: torch.Tensor, ts: torch.Tensor, dt: float, seed: int, with_grad: bool = False) -> torch.Tensor:
+    """[len(ts), B, D]; `sde.f(t, y)`, `sde.g(t, y)` (diagonal noise) are the reference's own modules on the CPU.
+    `with_grad`: record the loop with autograd (the reference trains through torchsde's solver ops)."""
     B, D = y0.shape
     t_list = [float(v) for v in ts.tolist()]
     out = [y0.clone()]
     curr_t, curr_y = t_list[0], y0.clone()
     prev_t, prev_y = curr_t, curr_y
     step = 0
-    with torch.no_grad():
+    with torch.set_grad_enabled(bool(with_grad)):
         for out_t in t_list[1:]:
             while curr_t < out_t:
                 next_t = min(curr_t + dt, t_list[-1])

@@ -230,11 +230,11 @@ class Dopri5Solver:
         self.max_step = torch.as_tensor(max_step, dtype=dtype, device=dev)
         self.max_num_steps = int(max_num_steps)
         yd = y0.dtype
-        self.alpha = [torch.tensor(a, dtype=torch.float64).to(yd) for a in DP_ALPHA]
-        self.beta = [torch.tensor(b, dtype=torch.float64).to(yd) for b in DP_BETA]
-        self.c_sol = torch.tensor(DP_C_SOL, dtype=torch.float64).to(yd)
-        self.c_error = torch.tensor(DP_C_ERROR, dtype=torch.float64).to(yd)
-        self.mid = torch.tensor(DP_C_MID, dtype=torch.float64).to(yd)
+        self.alpha = [torch.tensor(a, dtype=torch.float64).to(yd).to(dev) for a in DP_ALPHA]
+        self.beta = [torch.tensor(b, dtype=torch.float64).to(yd).to(dev) for b in DP_BETA]
+        self.c_sol = torch.tensor(DP_C_SOL, dtype=torch.float64).to(yd).to(dev)
+        self.c_error = torch.tensor(DP_C_ERROR, dtype=torch.float64).to(yd).to(dev)
+        self.mid = torch.tensor(DP_C_MID, dtype=torch.float64).to(yd).to(dev)
         # statistics for tests / bench (not part of the package)
         self.n_accepted = 0
         self.n_rejected = 0

@@ -86,3 +86,70 @@ def test_unify_and_interpolate_batch_matches_reference_fixture(golden_latent):
     # (/root/reference/test/test_data_batching.py:30-81): one shared strictly increasing grid, [B, T] dense tensors
     t = batch["t_unified"]
     assert (t[1:] > t[:-1]).all() and batch["y_loc_dense"].shape == (2, t.numel()) and batch["loss_mask"].shape == (2, t.numel())
+
+
+# ---- the reference's own test module, restated assertion for assertion on the same two persons ---------------------------------
+# /root/reference/test/test_data_batching.py:30-81 pins the layout of the `sde_collate_fn` batch (invariants 1-5).
+# The per-person inputs are the two persons of the reference's test CSVs (test/test_periods_small.csv, test_snaps_small.csv) as
+# frozen in tests/golden/mode_sep_fixture.npz: snap times, zone ids and stay intervals; a travel leg joins consecutive stays.
+def _stale_test_samples(g):
+    table = torch.eye(8, dtype=torch.float32)[:, :6] + 0.1                 # any fixed zone -> embedding map
+    samples = []
+    for i in range(2):
+        times = torch.from_numpy(g[f"p{i}_times_snap"]).float()
+        loc = torch.from_numpy(g[f"p{i}_loc_ids"]).long()
+        stays = [(float(a), float(b), int(c)) for a, b, c in g[f"p{i}_stay_segments"]]
+        segs = [{"t0": stays[j][1], "t1": stays[j + 1][0], "mode_id": 1 + i, "mode_proto": torch.full((4,), float(1 + i))}
+                for j in range(len(stays) - 1)]
+        samples.append({"gt_times": times, "gt_loc_emb": table[loc], "gt_purp_emb": table[loc][:, :3].contiguous(),
+                        "gt_anchor": torch.ones(times.numel()), "segments": segs})
+    return samples
+
+
+def test_stale_reference_test_grid_creation(golden_mode_sep):                 # test_data_batching.py:30-40
+    batch = batching.sde_collate_fn(_stale_test_samples(golden_mode_sep))
+    gt_union = batch["gt_union_times"]
+    assert torch.all(batch["grid_times"][1:] > batch["grid_times"][:-1])
+    assert batch["is_gt_grid"].sum() == len(gt_union)
+    assert torch.all(batch["grid_times"][batch["is_gt_grid"]] == gt_union)
+    assert len(batch["grid_times"]) == (len(gt_union) - 1) * (batching.K_INTERNAL - 1) + 1
+    assert len(gt_union) == 11 and len(batch["grid_times"]) == 91        # the fixtures' 11 snap times -> 91 points
+
+
+def test_stale_reference_test_state_interpolation_shapes(golden_mode_sep):   # test_data_batching.py:42-51
+    batch = batching.sde_collate_fn(_stale_test_samples(golden_mode_sep))
+    b, s_gt = batch["is_gt_union"].shape
+    assert b == 2
+    assert batch["loc_emb_union"].shape[:2] == (b, s_gt)
+    assert batch["purp_emb_union"].shape[:2] == (b, s_gt)
+    assert batch["anchor_union"].shape == (b, s_gt)
+    assert batch["loc_emb_union"].dtype == torch.float32
+
+
+def test_stale_reference_test_flat_stays(golden_mode_sep):                   # test_data_batching.py:53-68
+    samples = _stale_test_samples(golden_mode_sep)
+    batch = batching.sde_collate_fn(samples)
+    gt_union = batch["gt_union_times"]
+    p1 = samples[0]
+    start_time = p1["segments"][0]["t0"]                                      # first travel
+    stay_start_time, stay_end_time = p1["gt_times"][0], torch.tensor(start_time)
+    start_idx = torch.searchsorted(gt_union, stay_start_time).item()
+    end_idx = torch.searchsorted(gt_union, stay_end_time).item()
+    assert end_idx > start_idx
+    for j in range(start_idx, end_idx + 1):
+        assert torch.allclose(batch["loc_emb_union"][0, j], p1["gt_loc_emb"][0], atol=1e-6)
+    # and inside the travel leg the embedding moves from origin to destination
+    k = int(torch.searchsorted(gt_union, torch.tensor(p1["segments"][0]["t1"])))
+    assert torch.allclose(batch["loc_emb_union"][0, k], p1["gt_loc_emb"][2], atol=1e-6)
+
+
+def test_stale_reference_test_ragged_segments(golden_mode_sep):             # test_data_batching.py:70-81
+    samples = _stale_test_samples(golden_mode_sep)
+    batch = batching.sde_collate_fn(samples)
+    assert isinstance(batch["segments_batch"], list)
+    assert len(batch["segments_batch"]) == len(samples[0]["segments"]) + len(samples[1]["segments"]) == 4
+    for seg in batch["segments_batch"]:
+        assert set(seg.keys()) == {"b", "i0", "i1", "mode_id", "mode_proto"}
+        assert batch["is_gt_grid"][seg["i0"]] and batch["is_gt_grid"][seg["i1"]]
+        assert seg["i0"] < seg["i1"]
+    assert [s["b"] for s in batch["segments_batch"]] == [0, 0, 1, 1]

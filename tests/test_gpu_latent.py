@@ -49,9 +49,9 @@ def test_generative_ode_forward_matches_golden(golden_latent):
     assert abs(st.n_accepted - int(g["n_accepted"])) <= max(3, int(g["n_accepted"]) // 10)
 
 
-def test_generative_ode_sde_branch_samples_but_refuses_training():
-    """enable_sde=True (the reference default): forward-only Euler-Maruyama sampling; a call that needs gradients fails
-    loudly instead of silently training without the SDE."""
+def test_generative_ode_sde_branch_samples_and_trains():
+    """enable_sde=True (the reference default, latent_ode/config.py:60): Euler-Maruyama sampling, reproducible per seed; a
+    call that needs gradients back-propagates through the sampler (latent_ode/train/train.py:57-74) on kernels."""
     import ananke_abm_b200 as ab
     dev = _cuda()
     cfg = ab.GenerativeODEConfig(enable_sde=True)
@@ -59,13 +59,17 @@ def test_generative_ode_sde_branch_samples_but_refuses_training():
     z = torch.zeros(2, 7, device=dev)
     args = (torch.zeros(2, 8, device=dev), z, z, torch.zeros(2, 4, device=dev), torch.zeros(2, 4, device=dev),
             torch.linspace(0, 0.1, 3, device=dev), torch.zeros(8, 7, device=dev))
-    with pytest.raises(ab.Ab200Error):
-        m(*args)
+    outs = m(*args, eps=torch.zeros(2, cfg.hidden_dim, device=dev), seed=5)
+    (outs[0].square().mean() + outs[2].square().mean()).backward()
+    gr = [p.grad for p in m.ode_func.parameters()]
+    assert all(g_ is not None and torch.isfinite(g_).all() for g_ in gr) and any(float(g_.abs().max()) > 0 for g_ in gr)
+    assert m.zone_feature_encoder.weight.grad is not None
     with torch.no_grad():
         out_a = m(*args, eps=torch.zeros(2, cfg.hidden_dim, device=dev), seed=5)
         out_b = m(*args, eps=torch.zeros(2, cfg.hidden_dim, device=dev), seed=5)
         out_c = m(*args, eps=torch.zeros(2, cfg.hidden_dim, device=dev), seed=6)
     assert out_a[0].shape == (2, 3, 8) and torch.isfinite(out_a[1]).all()
+    assert float((outs[1].detach() - out_a[1]).abs().max()) < 1e-6        # the recorded loop takes the same steps
     assert torch.equal(out_a[1], out_b[1]) and not torch.equal(out_a[1], out_c[1])      # reproducible per seed
 
 

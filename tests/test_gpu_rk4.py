@@ -314,8 +314,8 @@ def test_combine_errnorm_kernel_bitexact_solution_and_norm(n, offset):
 
 
 def test_adjoint_seam_equals_odeint_on_the_stage_path():
-    """config.adjoint routes GATODEModel.integrate through odeint_adjoint (configs[4]); for the recognised drift both
-    seams run the same discrete adjoint, so outputs and gradients are identical."""
+    """config.adjoint routes GATODEModel.integrate through odeint_adjoint (configs[4]); with the explicit
+    adjoint_mode='discrete' opt-in both seams run the same discrete adjoint, so outputs and gradients are identical."""
     import ananke_abm_b200 as ab
     from ananke_abm_b200.graph import synthetic_zone_graph
     dev = _cuda()
@@ -324,6 +324,7 @@ def test_adjoint_seam_equals_odeint_on_the_stage_path():
         torch.manual_seed(7)
         mc = ab.ModeSepConfig()
         mc.precision, mc.ode_method, mc.adjoint = "bf16", "dopri5", adjoint
+        mc.adjoint_mode = "discrete"
         model = ab.GATODEModel(7, mc, heads=4).to(dev)
         ei, feats = synthetic_zone_graph(64, k=6, seed=1)
         csr = ab.build_zone_csr(ei, 64).to(dev)

@@ -69,8 +69,21 @@ def test_sdeint_mode_sep_drift_matches_oracle_euler_maruyama(B):
     with torch.no_grad():
         solo = ab.sdeint(_ScaledSDE(m.odefunc, 0.05), y0[:1].to(dev), ts.to(dev), method="euler", dt=0.01, seed=99)
     assert float((solo[:, 0] - out[:, 0]).abs().max()) < 1e-6
-    with pytest.raises(ab.Ab200Error):
-        ab.sdeint(_ScaledSDE(m.odefunc, 0.05), y0.to(dev).requires_grad_(True), ts.to(dev), method="euler", dt=0.01)
+    # training through the sampler (the reference's default latent_ode path, latent_ode/train/train.py:57-74): same values as
+    # the no-grad call, gradients == autograd through the oracle's Euler-Maruyama loop with the same noise
+    for p in m.parameters():
+        p.grad = None
+    yg = y0.to(dev).requires_grad_(True)
+    og = ab.sdeint(_ScaledSDE(m.odefunc, 0.05), yg, ts.to(dev), method="euler", dt=0.01, seed=99)
+    assert float((og.detach() - out).abs().max()) < 1e-6
+    og[:, :, :128].square().mean().backward()
+    om.zero_grad()
+    yr = y0.clone().requires_grad_(True)
+    rg = so.sdeint_euler(OracleSDE(), yr, ts, dt=0.01, seed=99, with_grad=True)
+    rg[:, :, :128].square().mean().backward()
+    assert float((yg.grad.cpu() - yr.grad).abs().max()) < 2e-5 * float(yr.grad.abs().max())
+    for (n_, p), (_, q) in zip(m.odefunc.func.net.named_parameters(), om.odefunc.func.net.named_parameters()):
+        assert float((p.grad.cpu() - q.grad).abs().max()) < 5e-5 * float(q.grad.abs().max()) + 1e-9, n_
 
 
 def test_mode_sep_model_sde_config_switch():

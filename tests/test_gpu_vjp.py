@@ -1,0 +1,256 @@
+"""Strict-fp32 differentiation of the kernel-evaluated drifts, through the C ABI (`ab200_drift_vjp`), against the CPU oracle:
+
+  * the vector-Jacobian product of one evaluation == torch.autograd.grad of the reference-structured module's forward
+    (mode_sep WrappedSDE: mode_sep/architecture/model.py:56-73; latent ODEFunc with the potential term:
+    latent_ode/architecture/model.py:77-117)
+  * dopri5 TRAINING in strict fp32 == autograd through the oracle solver (the reference's live training path,
+    latent_ode/train/train.py:57-74, mode_sep/train/train.py:161-164), for both drift shapes
+  * the continuous adjoint (`odeint_adjoint`, latent_ode/architecture/ode_components.py:29-50) == oracle.odeint_adjoint, on a
+    recognised drift (kernels) and on a generic nn.Module shaped like the orphan ODEBlock's ODEFunc (autograd)
+  * drop-in: the solver seam swapped under REFERENCE-STRUCTURED modules evaluates their drift on kernels (their own eager
+    forward is never called) and reproduces the golden vectors of the unmodified reference.
+"""
+import importlib
+
+import numpy as np
+import pytest
+import torch
+from torch import nn
+
+pytestmark = pytest.mark.gpu
+
+from oracle import models_oracle as mo
+from oracle import torchdiffeq_oracle as tdq
+
+
+def _cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+def _rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def _mode_sep_pair(dev, Z=8, seed=0):
+    import ananke_abm_b200 as ab
+    torch.manual_seed(seed)
+    oracle = mo.OracleModeSep(Z)
+    model = ab.ModeSepModel(Z, ab.ModeSepConfig())
+    model.load_state_dict(oracle.state_dict())
+    return oracle, model.to(dev)
+
+
+def _latent_pair(dev, seed=0):
+    import ananke_abm_b200 as ab
+    torch.manual_seed(seed)
+    oracle = mo.OracleLatentODE(8, 7)
+    model = ab.GenerativeODE(8, 7, ab.GenerativeODEConfig())
+    model.load_state_dict(oracle.state_dict())
+    return oracle, model.to(dev)
+
+
+@pytest.mark.parametrize("shape", ["mode_sep", "latent"])
+@pytest.mark.parametrize("B", [1, 33, 500])
+def test_drift_vjp_matches_autograd(shape, B):
+    import ananke_abm_b200 as ab
+    oi = importlib.import_module("ananke_abm_b200.odeint")
+    dev = _cuda()
+    if shape == "mode_sep":
+        oracle, model = _mode_sep_pair(dev)
+        fo, fm, D = oracle.odefunc, model.odefunc, 160
+    else:
+        oracle, model = _latent_pair(dev)
+        fo, fm, D = oracle.ode_func, model.ode_func, 64
+    g = torch.Generator().manual_seed(B)
+    y = (0.5 * torch.randn(B, D, generator=g)).requires_grad_(True)
+    up = torch.randn(B, D, generator=g)
+    t = torch.tensor(7.3)
+    params = list(fo.parameters())
+    f = fo(t, y)
+    ref = torch.autograd.grad(f, [y] + params, up)
+    spec = ab.describe_drift(fm)
+    assert spec is not None
+    gy, gw = oi.drift_vjp(spec, spec.flat_params().detach(), 7.3, y.detach().to(dev), up.to(dev))
+    torch.cuda.synchronize()
+    assert _rel(gy.cpu(), ref[0]) < 1e-5, _rel(gy.cpu(), ref[0])
+    off = 0
+    for p, r in zip(spec.params, ref[1:]):
+        got = gw[off:off + p.numel()].view_as(p).cpu()
+        off += p.numel()
+        assert _rel(got, r) < 5e-5, (tuple(p.shape), _rel(got, r))
+    # the module's forward is differentiable through the same kernels
+    yd = y.detach().to(dev).requires_grad_(True)
+    out = fm(torch.tensor(7.3, device=dev), yd)
+    assert _rel(out.detach().cpu(), f.detach()) < 1e-5
+    out.backward(up.to(dev))
+    assert _rel(yd.grad.cpu(), ref[0]) < 1e-5
+
+
+def test_f32_dopri5_training_mode_sep_vs_oracle():
+    """default precision (strict fp32): dopri5 forward + backward on kernels == autograd through the oracle solver at the
+    reference's rtol = atol = 1e-5, same accepted steps"""
+    import ananke_abm_b200 as ab
+    oi = importlib.import_module("ananke_abm_b200.odeint")
+    dev = _cuda()
+    oracle, model = _mode_sep_pair(dev)
+    B, T = 96, 5
+    g = torch.Generator().manual_seed(1)
+    home, work, traits = torch.randint(0, 8, (B,), generator=g), torch.randint(0, 8, (B,), generator=g), torch.rand(B, 2, generator=g)
+    t = torch.linspace(0.0, 6.0, T)
+    y0r = oracle.initial_state(home, work, traits).detach().requires_grad_(True)
+    ref = tdq.odeint(oracle.odefunc, y0r, t, method="dopri5", rtol=1e-5, atol=1e-5)
+    n_ref = sum(1 for (_, _, ok) in tdq._LAST_SOLVER["solver"].step_log if ok)
+    (ref[:, :, :128] ** 2).mean().backward()
+    y0 = model.initial_state(home.to(dev), work.to(dev), traits.to(dev)).detach().requires_grad_(True)
+    out = ab.odeint(model.odefunc, y0, t.to(dev), method="dopri5", rtol=1e-5, atol=1e-5)
+    n_acc = oi._LAST["solver"].n_accepted
+    (out[:, :, :128] ** 2).mean().backward()
+    torch.cuda.synchronize()
+    assert n_acc == n_ref, (n_acc, n_ref)
+    assert _rel(out.detach().cpu(), ref.detach()) < 1e-5
+    assert _rel(y0.grad.cpu(), y0r.grad) < 1e-4, _rel(y0.grad.cpu(), y0r.grad)
+    for (n, p), (_, q) in zip(model.odefunc.func.net.named_parameters(), oracle.odefunc.func.net.named_parameters()):
+        assert _rel(p.grad.cpu(), q.grad) < 2e-4, (n, _rel(p.grad.cpu(), q.grad))
+
+
+def test_generative_ode_training_step_matches_golden_gradients(golden_latent):
+    """GenerativeODE (ODE branch) training step through dopri5 with torchdiffeq's default tolerances, as
+    latent_ode/train/train.py:57-74 runs it: loss and EVERY parameter gradient against the vectors minted from the unmodified
+    reference (tests/golden/make_golden.py: loss = mean-squares of loc_logits, loc_embed, purpose and mode logits).  Every drift
+    evaluation and its backward (incl. the second derivative of the potential term) run on kernels.  The solver is round-off
+    limited at rtol=1e-7 / atol=1e-9 in fp32, so the CPU reference and the GPU take slightly different step sequences."""
+    import ananke_abm_b200 as ab
+    dev = _cuda()
+    g = golden_latent
+    m = ab.GenerativeODE(g["batch_person_features"].shape[-1], g["batch_all_zone_features"].shape[-1], ab.GenerativeODEConfig())
+    m.load_state_dict({k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd_")}, strict=True)
+    m = m.to(dev)
+    t = lambda k: torch.from_numpy(g[k]).to(dev)   # noqa: E731
+    outs = m(t("batch_person_features"), t("batch_home_zone_features"), t("batch_work_zone_features"),
+             t("batch_y_purp_feat_dense")[:, 0], t("batch_y_mode_feat_dense")[:, 0], t("batch_t_unified"), t("batch_all_zone_features"),
+             eps=t("eps"))
+    loss = outs[0].pow(2).mean() + outs[2].pow(2).mean() + outs[3].pow(2).mean() + outs[1].pow(2).mean()
+    loss.backward()
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(g["loss"])) < 2e-4 * abs(float(g["loss"]))
+    worst = 0.0
+    for name, p in m.named_parameters():
+        ref = torch.from_numpy(g["grad_" + name])
+        assert p.grad is not None, name
+        e = _rel(p.grad.cpu(), ref)
+        worst = max(worst, e)
+        assert e < 5e-3, (name, e)
+    print(f"latent training step vs the unmodified reference: worst parameter-gradient error {worst:.2e}")
+
+
+def test_continuous_adjoint_on_kernels_vs_oracle():
+    """odeint_adjoint (default = torchdiffeq semantics) on the recognised mode_sep drift: forward under no_grad, augmented system
+    integrated backwards with the mixed error norm; f and both vector-Jacobian products evaluated by kernels"""
+    import ananke_abm_b200 as ab
+    dev = _cuda()
+    oracle, model = _mode_sep_pair(dev)
+    B, T = 40, 4
+    g = torch.Generator().manual_seed(4)
+    home, work, traits = torch.randint(0, 8, (B,), generator=g), torch.randint(0, 8, (B,), generator=g), torch.rand(B, 2, generator=g)
+    t = torch.linspace(0.0, 3.0, T)
+    wgt = torch.linspace(0.5, 1.5, T)[:, None, None]
+    y0r = oracle.initial_state(home, work, traits).detach().requires_grad_(True)
+    ref = tdq.odeint_adjoint(oracle.odefunc, y0r, t, method="dopri5", rtol=1e-6, atol=1e-6)
+    ((ref[:, :, :128] * wgt) ** 2).mean().backward()
+    calls_before = oracle.odefunc.calls
+    y0 = model.initial_state(home.to(dev), work.to(dev), traits.to(dev)).detach().requires_grad_(True)
+    out = ab.odeint_adjoint(model.odefunc, y0, t.to(dev), method="dopri5", rtol=1e-6, atol=1e-6)
+    ((out[:, :, :128] * wgt.to(dev)) ** 2).mean().backward()
+    torch.cuda.synchronize()
+    assert calls_before > 0
+    assert _rel(out.detach().cpu(), ref.detach()) < 1e-5
+    assert _rel(y0.grad.cpu(), y0r.grad) < 2e-4, _rel(y0.grad.cpu(), y0r.grad)
+    for (n, p), (_, q) in zip(model.odefunc.func.net.named_parameters(), oracle.odefunc.func.net.named_parameters()):
+        assert _rel(p.grad.cpu(), q.grad) < 5e-4, (n, _rel(p.grad.cpu(), q.grad))
+
+
+class _BlockFunc(nn.Module):
+    """the orphan ODEBlock's ODEFunc (latent_ode/architecture/ode_components.py:6-26): dx/dt = net([x, Linear(t)]) + alpha (h0 - x)"""
+
+    def __init__(self, dim=12, hid=32, alpha=0.3):
+        super().__init__()
+        self.time_embedding = nn.Linear(1, 4)
+        self.net = nn.Sequential(nn.Linear(dim + 4, hid), nn.Tanh(), nn.Linear(hid, dim))
+        self.alpha = alpha
+        self.h0 = None
+
+    def forward(self, t, x):
+        te = self.time_embedding(t.reshape(1, 1).to(x.dtype)).expand(x.shape[0], -1)
+        return self.net(torch.cat([x, te], dim=-1)) + self.alpha * (self.h0 - x)
+
+
+@pytest.mark.parametrize("method", ["dopri5", "rk4"])
+def test_continuous_adjoint_generic_func_vs_oracle(method):
+    """any nn.Module through odeint_adjoint (call shape of ode_components.py:50: rtol = atol = 1e-5, dopri5): func by the caller's
+    torch code, stage algebra / error norms by the fused kernels, mixed norm over (y, a_y, each parameter's adjoint)"""
+    import ananke_abm_b200 as ab
+    dev = _cuda()
+    torch.manual_seed(3)
+    fr = _BlockFunc()
+    fg = _BlockFunc().to(dev)
+    fg.load_state_dict(fr.state_dict())
+    x0 = torch.randn(17, 12, generator=torch.Generator().manual_seed(5))
+    fr.h0, fg.h0 = x0.clone(), x0.clone().to(dev)
+    t = torch.linspace(0.0, 2.0, 6)
+    xr = x0.clone().requires_grad_(True)
+    ref = tdq.odeint_adjoint(fr, xr, t, method=method, rtol=1e-5, atol=1e-5)
+    ref.square().mean().backward()
+    xg = x0.clone().to(dev).requires_grad_(True)
+    out = ab.odeint_adjoint(fg, xg, t.to(dev), method=method, rtol=1e-5, atol=1e-5)
+    out.square().mean().backward()
+    assert _rel(out.detach().cpu(), ref.detach()) < 2e-5
+    assert _rel(xg.grad.cpu(), xr.grad) < 2e-4, _rel(xg.grad.cpu(), xr.grad)
+    for (n, p), (_, q) in zip(fg.named_parameters(), fr.named_parameters()):
+        assert _rel(p.grad.cpu(), q.grad) < 5e-4, (n, _rel(p.grad.cpu(), q.grad))
+
+
+def test_drop_in_solver_seam_under_reference_structured_modules(golden_mode_sep, golden_latent, monkeypatch):
+    """INTEGRATION.md's claim on the GPU box: with this package's `odeint` standing where `torchdiffeq.odeint` stood, modules
+    with the REFERENCE's structure and call shapes (oracle.OracleModeSep / OracleLatentODE: `odeint(self.odefunc, y0, t,
+    method=..., rtol=, atol=)`) run their unmodified forward on CUDA, the drift is recognised (`describe_drift`) and evaluated
+    by kernels -- the module's own eager forward is never called -- and the outputs reproduce the golden vectors minted from
+    the unmodified reference."""
+    import ananke_abm_b200 as ab
+    oi = importlib.import_module("ananke_abm_b200.odeint")
+    dev = _cuda()
+    monkeypatch.setattr(mo, "tdq", oi)          # == sys.modules["torchdiffeq"] = ananke_abm_b200.odeint for the reference files
+    g = golden_mode_sep
+    m = mo.OracleModeSep(8)
+    m.load_state_dict({k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd_")}, strict=True)
+    m = m.to(dev)
+    assert ab.describe_drift(m.odefunc) is not None
+    tt = lambda k: torch.from_numpy(g[k]).to(dev)   # noqa: E731
+    with torch.no_grad():
+        pred_emb, logits, v_t = m(tt("times_union"), tt("home_idx"), tt("work_idx"), tt("traits"))
+    assert m.odefunc.calls == 0                 # not the generic path: the drift ran in libananke_b200.so
+    assert _rel(pred_emb.cpu(), torch.from_numpy(g["pred_emb"])) < 1e-5
+    assert _rel(v_t.cpu(), torch.from_numpy(g["v_t"])) < 1e-5
+    assert np.array_equal(logits.argmax(-1).cpu().numpy(), g["logits"].argmax(-1))
+    # training through the swapped seam: gradients of the fixture's training step
+    m.zero_grad()
+    pred_emb, logits, v_t = m(tt("times_union"), tt("home_idx"), tt("work_idx"), tt("traits"))
+    (pred_emb.square().mean() + v_t.square().mean()).backward()
+    assert m.odefunc.calls == 0
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.odefunc.parameters())
+
+    gl = golden_latent
+    ml = mo.OracleLatentODE(gl["batch_person_features"].shape[-1], gl["batch_all_zone_features"].shape[-1])
+    ml.load_state_dict({k[3:]: torch.from_numpy(gl[k]) for k in gl.files if k.startswith("sd_")}, strict=True)
+    ml = ml.to(dev)
+    assert ab.describe_drift(ml.ode_func) is not None
+    tl = lambda k: torch.from_numpy(gl[k]).to(dev)   # noqa: E731
+    with torch.no_grad():
+        outs = ml(tl("batch_person_features"), tl("batch_home_zone_features"), tl("batch_work_zone_features"),
+                  tl("batch_y_purp_feat_dense")[:, 0], tl("batch_y_mode_feat_dense")[:, 0], tl("batch_t_unified"),
+                  tl("batch_all_zone_features"), tl("eps"))
+    assert ml.ode_func.calls == 0
+    assert _rel(outs[0].cpu(), torch.from_numpy(gl["loc_logits"])) < 2e-4
+    assert np.array_equal(outs[0].argmax(-1).cpu().numpy(), gl["loc_logits"].argmax(-1))
