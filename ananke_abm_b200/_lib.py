@@ -87,6 +87,7 @@ SIGNATURES = {
     "ab200_stage_status_offset": (C.c_int, [_dp, _vp, _vp]),
     "ab200_pv_combine": (C.c_int, [_dp, _vp, _vp, _i32, _f32, _vp, _vp, _i64, _vp, _vp]),
     "ab200_pv_combine_rowmajor": (C.c_int, [_dp, _vp, _vp, _i32, _f32, _vp, _vp, _i64, _vp, _vp]),
+    "ab200_pv_combine_rowmajor_multi": (C.c_int, [_dp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _i64, _vp, _vp]),
     "ab200_pv_combine_backward": (C.c_int, [_dp, _vp, _i32, _f32, _vp, _vp, _i64, _vp, _vp, _i32, _vp]),
     "ab200_debug_umma_probe": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
 }

@@ -73,6 +73,8 @@ int pv_combine(const ab200_drift_desc* d, const float* y0, const float* const* a
                const float* cva, int64_t B, float* out, cudaStream_t st);
 int pv_combine_rowmajor(const ab200_drift_desc* d, const float* y0, const float* const* a_ptrs, int n_a, float cpv, const float* cpa,
                         const float* cva, int64_t B, float* out_rowmajor, cudaStream_t st);
+int pv_combine_rowmajor_multi(const ab200_drift_desc* d, const float* y0, const float* const* a_ptrs, int n_a, int n_rows, const float* cpv,
+                              const float* cpa, const float* cva, int64_t B, float* const* out_rowmajor, cudaStream_t st);
 int pv_combine_bwd(const ab200_drift_desc* d, const float* g, int n_a, float cpv, const float* cpa, const float* cva, int64_t B,
                    float* G_y0, float* const* G_a, int accumulate, cudaStream_t st);
 
@@ -359,6 +361,16 @@ int ab200_pv_combine_rowmajor(const ab200_drift_desc* d, const float* y0, const 
                               const float* cpa_host, const float* cva_host, int64_t B, float* out_rowmajor, ab200_stream_t stream) {
   if (!desc_ok(d) || !y0 || !out_rowmajor || B <= 0 || (n_a > 0 && (!a || !cpa_host || !cva_host))) return AB200_ERR_BAD_ARG;
   return pv_combine_rowmajor(d, y0, a, n_a, cpv, cpa_host, cva_host, B, out_rowmajor, (cudaStream_t)stream);
+}
+
+int ab200_pv_combine_rowmajor_multi(const ab200_drift_desc* d, const float* y0, const float* const* a, int32_t n_a, int32_t n_rows,
+                                    const float* cpv_host, const float* cpa_host, const float* cva_host, int64_t B,
+                                    float* const* out_rowmajor, ab200_stream_t stream) {
+  if (!desc_ok(d) || !y0 || !out_rowmajor || !cpv_host || B <= 0 || n_rows < 1 || (n_a > 0 && (!a || !cpa_host || !cva_host)))
+    return AB200_ERR_BAD_ARG;
+  for (int i = 0; i < n_rows; ++i)
+    if (!out_rowmajor[i]) return AB200_ERR_BAD_ARG;
+  return pv_combine_rowmajor_multi(d, y0, a, n_a, n_rows, cpv_host, cpa_host, cva_host, B, out_rowmajor, (cudaStream_t)stream);
 }
 
 int ab200_pv_combine_backward(const ab200_drift_desc* d, const float* g, int32_t n_a, float cpv, const float* cpa_host,

@@ -141,7 +141,9 @@ __global__ void __launch_bounds__(THREADS, 1) stage_bwd_tc_kernel(const __grid_c
   auto blob_at = [&](size_t off) -> uint8_t* { return no_spill ? nullptr : a.spill + off; };
 
 #pragma unroll 1
-  for (int tile = blockIdx.x * NSLOT + c.slot; tile < a.ntiles; tile += gridDim.x * NSLOT) {
+  for (int it = 0;; ++it) {
+    const int tile = slot_tile(it, a.ntiles, c.slot);
+    if (tile < 0) break;
     const bool valid = (int64_t)tile * TM + c.row < a.B && !no_gx;      // padding rows: zeros in, nothing stored
 #pragma unroll 1
    for (int si = 0; si < a.n_stage; ++si) {                   // all stages of the step for this tile: later stages' gx come from L2
@@ -389,8 +391,7 @@ int stage_bwd_tc_multi(const ab200_drift_desc* d, const uint8_t* image, const fl
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int need = (k.ntiles + NSLOT - 1) / NSLOT;
-  const int grid = need < sms ? need : sms;
+  const int grid = k.ntiles < sms ? k.ntiles : sms;      // a partial wave uses one slot per CTA first (slot_tile)
   cudaError_t e = cudaFuncSetAttribute(stage_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W_BYTES);
   if (e != cudaSuccess) { set_cuda_error(e); return AB200_ERR_CUDA; }
   stage_bwd_tc_kernel<<<grid, THREADS, W_BYTES, st>>>(k);

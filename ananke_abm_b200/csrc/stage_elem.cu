@@ -339,6 +339,66 @@ __global__ void __launch_bounds__(256) pv_combine_rowmajor_kernel(const __grid_c
   }
 }
 
+// Several ROW-MAJOR dense-output rows of the SAME step in one pass: y0 and the accelerations are read once, every row is
+// its own linear combination (tdq interp.py `_interp_evaluate` expanded over the stage derivatives) -- a dopri5 step at
+// rtol = atol = 1e-5 contains ~3 of the 97 requested rows, each of which re-read 2.4 KB per agent when launched alone.
+constexpr int RM_MAX_ROWS = 4;
+struct RowMajorMultiArgs {
+  const float* y0;
+  const float* a[EL_MAX_A];
+  float* out[RM_MAX_ROWS];
+  float cpv[RM_MAX_ROWS], cpa[RM_MAX_ROWS][EL_MAX_A], cva[RM_MAX_ROWS][EL_MAX_A];
+  int n_a, n_rows, P, H;
+};
+__global__ void __launch_bounds__(256) pv_combine_rowmajor_multi_kernel(const __grid_constant__ RowMajorMultiArgs a, int64_t B) {
+  extern __shared__ float4 tile_s[];     // [n_rows][TR_ROWS][F4 + 1]
+  const int P4 = a.P / 4, H4 = a.H / 4, F4 = 2 * P4 + H4, ld = F4 + 1;
+  const int64_t row0 = (int64_t)blockIdx.x * TR_ROWS;
+  const int n_work = TR_ROWS * (P4 + H4);
+  for (int i = threadIdx.x; i < n_work; i += blockDim.x) {
+    const int grp = i / TR_ROWS, r = i % TR_ROWS;
+    const int64_t g = row0 + r;
+    if (g >= B) continue;
+    const int tile = (int)(g / EL_TM), row = (int)(g % EL_TM);
+    const float4* y4 = reinterpret_cast<const float4*>(a.y0) + (size_t)tile * F4 * EL_TM + row;
+    if (grp >= P4) {
+      const int f = 2 * P4 + (grp - P4);
+      const float4 hv = y4[(size_t)f * EL_TM];
+      for (int q = 0; q < a.n_rows; ++q) tile_s[(q * TR_ROWS + r) * ld + f] = hv;
+      continue;
+    }
+    const float4 p0 = y4[(size_t)grp * EL_TM], v0 = y4[(size_t)(P4 + grp) * EL_TM];
+    float4 x[EL_MAX_A];
+#pragma unroll
+    for (int s = 0; s < EL_MAX_A; ++s)
+      if (s < a.n_a) x[s] = reinterpret_cast<const float4*>(a.a[s])[((size_t)tile * P4 + grp) * EL_TM + row];
+#pragma unroll 1
+    for (int q = 0; q < a.n_rows; ++q) {
+      const float c = a.cpv[q];
+      float4 p = make_float4(p0.x + c * v0.x, p0.y + c * v0.y, p0.z + c * v0.z, p0.w + c * v0.w), v = v0;
+#pragma unroll
+      for (int s = 0; s < EL_MAX_A; ++s) {
+        if (s < a.n_a) {
+          const float cp = a.cpa[q][s], cv = a.cva[q][s];
+          p.x += cp * x[s].x; p.y += cp * x[s].y; p.z += cp * x[s].z; p.w += cp * x[s].w;
+          v.x += cv * x[s].x; v.y += cv * x[s].y; v.z += cv * x[s].z; v.w += cv * x[s].w;
+        }
+      }
+      tile_s[(q * TR_ROWS + r) * ld + grp] = p;
+      tile_s[(q * TR_ROWS + r) * ld + P4 + grp] = v;
+    }
+  }
+  __syncthreads();
+  for (int q = 0; q < a.n_rows; ++q) {
+    float4* o = reinterpret_cast<float4*>(a.out[q]);
+    for (int i = threadIdx.x; i < TR_ROWS * F4; i += blockDim.x) {
+      const int r = i / F4, c = i % F4;
+      const int64_t g = row0 + r;
+      if (g < B) o[g * F4 + c] = tile_s[(q * TR_ROWS + r) * ld + c];
+    }
+  }
+}
+
 static int launch_cfg(int64_t n) {
   int64_t blocks = (n + 255) / 256;
   const int64_t cap = 148 * 16;
@@ -367,6 +427,33 @@ int pv_combine_rowmajor(const ab200_drift_desc* d, const float* y0, const float*
   const size_t smem = (size_t)TR_ROWS * (F4 + 1) * sizeof(float4);
   pv_combine_rowmajor_kernel<<<(int)((B + TR_ROWS - 1) / TR_ROWS), 256, smem, st>>>(k, B);
   return check_launch();
+}
+
+// n_rows row-major outputs out[q] = combination q (cpv[q], cpa[q * 8 + j], cva[q * 8 + j]) of the same (y0, a[]); any n_rows >= 1
+int pv_combine_rowmajor_multi(const ab200_drift_desc* d, const float* y0, const float* const* a_ptrs, int n_a, int n_rows, const float* cpv,
+                              const float* cpa, const float* cva, int64_t B, float* const* out_rowmajor, cudaStream_t st) {
+  if (n_a < 0 || n_a > EL_MAX_A || n_rows < 1 || d->pos_dim % 4 || d->ctx_dim % 4) return AB200_ERR_BAD_ARG;
+  const int F4 = (2 * d->pos_dim + d->ctx_dim) / 4;
+  for (int r0 = 0; r0 < n_rows; r0 += RM_MAX_ROWS) {
+    RowMajorMultiArgs k{};
+    k.y0 = y0; k.n_a = n_a; k.P = d->pos_dim; k.H = d->ctx_dim;
+    k.n_rows = (n_rows - r0 < RM_MAX_ROWS) ? n_rows - r0 : RM_MAX_ROWS;
+    for (int i = 0; i < n_a; ++i) k.a[i] = a_ptrs[i];
+    for (int q = 0; q < k.n_rows; ++q) {
+      k.out[q] = out_rowmajor[r0 + q];
+      k.cpv[q] = cpv[r0 + q];
+      for (int i = 0; i < n_a; ++i) { k.cpa[q][i] = cpa[(r0 + q) * EL_MAX_A + i]; k.cva[q][i] = cva[(r0 + q) * EL_MAX_A + i]; }
+    }
+    const size_t smem = (size_t)k.n_rows * TR_ROWS * (F4 + 1) * sizeof(float4);
+    if (smem > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(pv_combine_rowmajor_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) { set_cuda_error(e); return AB200_ERR_CUDA; }
+    }
+    pv_combine_rowmajor_multi_kernel<<<(int)((B + TR_ROWS - 1) / TR_ROWS), 256, smem, st>>>(k, B);
+    const int rc = check_launch();
+    if (rc) return rc;
+  }
+  return AB200_OK;
 }
 
 int pv_combine_bwd(const ab200_drift_desc* d, const float* g, int n_a, float cpv, const float* cpa, const float* cva, int64_t B,

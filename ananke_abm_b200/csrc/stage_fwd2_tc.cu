@@ -216,19 +216,10 @@ __global__ void __launch_bounds__(THREADS, 1) stage_fwd2_tc_kernel(const __grid_
   uint8_t* htile = smem + f2::OFF_HT + (uint32_t)c.slot * f2::SZ_HT;
   double err_local = 0.0;
 
-  // tile -> (CTA, slot): full waves fill both slots of every CTA; the tiles of a last, partial wave are spread over the
-  // first slots of as many CTAs as possible (a slot that runs alone is faster than two that share the tensor pipe)
-  const int per_wave = gridDim.x * NSLOT;
-  const int full = a.ntiles / per_wave * per_wave;
 #pragma unroll 1
   for (int it = 0;; ++it) {
-    int tile = it * per_wave + blockIdx.x * NSLOT + c.slot;
-    if (tile >= full) {
-      if (it * per_wave != full) break;
-      // partial wave: slot 0 of CTA b takes tile full + b, slot 1 takes full + gridDim.x + b
-      tile = full + c.slot * gridDim.x + blockIdx.x;
-      if (tile >= a.ntiles) break;
-    }
+    const int tile = slot_tile(it, a.ntiles, c.slot);
+    if (tile < 0) break;
     const bool valid = (int64_t)tile * TM + c.row < a.B;      // padding rows hold zeros and are never stored to
     STAGE_TRACE(c, 9);
     // context h -> this slot's shared-memory operand tile, once per tile (canonical K-major: 8-row x 16-byte cores)

@@ -137,7 +137,9 @@ __global__ void __launch_bounds__(THREADS, 1) stage_fwd_tc_kernel(const __grid_c
   double err_local = 0.0;
 
 #pragma unroll 1
-  for (int tile = blockIdx.x * NSLOT + c.slot; tile < a.ntiles; tile += gridDim.x * NSLOT) {
+  for (int it = 0;; ++it) {
+    const int tile = slot_tile(it, a.ntiles, c.slot);
+    if (tile < 0) break;
     const bool valid = (int64_t)tile * TM + c.row < a.B;      // padding rows hold zeros and are never stored to
     STAGE_TRACE(c, 9);
     // context h -> HB once per tile (constant along the step)
@@ -364,8 +366,7 @@ int stage_fwd_tc_multi(const ab200_drift_desc* d, const uint8_t* image, const fl
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int need = (k.ntiles + NSLOT - 1) / NSLOT;
-  const int grid = need < sms ? need : sms;
+  const int grid = k.ntiles < sms ? k.ntiles : sms;      // a partial wave uses one slot per CTA first (slot_tile)
   auto kern = half_ops ? stage_fwd_tc_kernel<true> : stage_fwd_tc_kernel<false>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)W_BYTES);
   if (e != cudaSuccess) { set_cuda_error(e); return AB200_ERR_CUDA; }

@@ -321,6 +321,20 @@ __device__ __forceinline__ SlotCtx stage_setup(uint8_t* smem, const uint8_t* wim
   return c;
 }
 
+// Tile of iteration `it` for this (CTA, slot), or -1 when the slot is done.  Full waves fill both slots of every CTA; the tiles
+// of a last, partial wave are spread over the FIRST slots of as many CTAs as possible before any second slot is used (a slot
+// that runs alone is faster than two that share the tensor pipe and the SM's load/store path): matters when a rank owns few
+// tiles, e.g. 1M agents sharded over 8 GPUs = 977 tiles on 296 slots.  Launch with grid = min(ntiles, #SMs).
+__device__ __forceinline__ int slot_tile(int it, int ntiles, int slot) {
+  const int per_wave = (int)gridDim.x * NSLOT;
+  const int full = ntiles / per_wave * per_wave;
+  int tile = it * per_wave + (int)blockIdx.x * NSLOT + slot;
+  if (tile < full) return tile;
+  if (it * per_wave != full) return -1;
+  tile = full + slot * (int)gridDim.x + (int)blockIdx.x;
+  return tile < ntiles ? tile : -1;
+}
+
 __device__ __forceinline__ void stage_teardown(uint32_t tmem_base) {
   tc_fence_before();
   __syncthreads();

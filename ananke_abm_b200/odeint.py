@@ -351,6 +351,7 @@ class _Dopri5:
         return float(v)
 
     def _rms(self, x: torch.Tensor) -> float:
+        x = x.detach()
         if self.segments is None:
             return float(x.float().pow(2).mean().sqrt())
         flat = x.reshape(-1).float()

@@ -226,6 +226,23 @@ class TcEngine:
                                               C.cast(cpa, C.c_void_p), C.cast(cva, C.c_void_p), B, out_rowmajor.data_ptr(), _stream())
         _lib.check(rc, "ab200_pv_combine_rowmajor")
 
+    def combine_rowmajor_multi(self, y0, a: Sequence[torch.Tensor], combos: Sequence[Combo], B: int, outs: Sequence[torch.Tensor]) -> None:
+        """several dense-output rows of the same step in ONE pass (y0 and the accelerations are read once)"""
+        n, nr = len(a), len(combos)
+        cpv = (C.c_float * nr)(*[float(c.cpv) for c in combos])
+        cpa = (C.c_float * (nr * 8))()
+        cva = (C.c_float * (nr * 8))()
+        for q, c in enumerate(combos):
+            for j in range(n):
+                cpa[q * 8 + j] = float(c.cpa[j])
+                cva[q * 8 + j] = float(c.cva[j])
+        op = (C.c_void_p * nr)(*[o.data_ptr() for o in outs])
+        assert all(o.is_contiguous() for o in outs)
+        rc = self.L.ab200_pv_combine_rowmajor_multi(C.byref(self.desc), y0.data_ptr(), C.cast(_ptr_array(a), C.c_void_p), n, nr,
+                                                    C.cast(cpv, C.c_void_p), C.cast(cpa, C.c_void_p), C.cast(cva, C.c_void_p), B,
+                                                    C.cast(op, C.c_void_p), _stream())
+        _lib.check(rc, "ab200_pv_combine_rowmajor_multi")
+
     # ---- backward -----------------------------------------------------------------------------------
     def backward_begin(self, B: int, stages_per_flush: int) -> None:
         self.ntiles = (B + TM - 1) // TM
@@ -609,10 +626,11 @@ def dopri5_forward(eng: TcEngine, y0: torch.Tensor, t_host: Sequence[float], rto
             stats.n_accepted += 1
             outs = []
             while k < T and ts[k] <= tb:
-                x = (ts[k] - ta) / (tb - ta)
-                eng.combine_rowmajor(y_cur, A, DOPRI5.combo(dopri5_interp_weights(x), dt), B, y_path[k])
-                outs.append((k, x))
+                outs.append((k, (ts[k] - ta) / (tb - ta)))
                 k += 1
+            if outs:       # every requested time inside (t, t + dt]: one pass over (y, a_1..a_7) for all of them
+                eng.combine_rowmajor_multi(y_cur, A, [DOPRI5.combo(dopri5_interp_weights(x), dt) for _, x in outs], B,
+                                           [y_path[kk] for kk, _ in outs])
             if save_steps:
                 steps.append(_Dopri5Step(y_cur, A, ta, dt, outs))
                 y_cur, y_next = y_next, blocked_empty(B, D, dev)

@@ -149,22 +149,20 @@ def labels_from_path(model, y_path, class_table, t_chunk=8):
 
 
 class _TrajectoryLoss(torch.autograd.Function):
-    """The bench's stand-in loss  mean(y_path[:, :, :K]^2)  as ONE reduction pass forward and ONE scaled copy backward
-    (the plain torch expression costs ~8 full passes over the 12 GB trajectory; the loss is harness, not hot path)."""
+    """The bench's stand-in loss  mean(y_path^2)  as ONE reduction pass forward and ONE scalar-scaled copy backward (the plain
+    torch expression costs ~8 full passes over the 20 GB trajectory of a chunk; the loss is harness, not hot path).  The
+    reference arms compute the same quantity with plain torch ops."""
 
     @staticmethod
-    def forward(ctx, y_path, K):
-        n = y_path.shape[0] * y_path.shape[1] * K
+    def forward(ctx, y_path):
         ctx.save_for_backward(y_path)
-        ctx.K, ctx.n = K, n
-        return torch.linalg.vector_norm(y_path[:, :, :K]).pow(2) / n
+        ctx.n = y_path.numel()
+        return torch.linalg.vector_norm(y_path).pow(2) / ctx.n
 
     @staticmethod
     def backward(ctx, go):
         (y_path,) = ctx.saved_tensors
-        scale = torch.zeros(y_path.shape[-1], dtype=y_path.dtype, device=y_path.device)
-        scale[:ctx.K] = 2.0 / ctx.n
-        return y_path * (scale * go), None
+        return y_path * (go * (2.0 / ctx.n))
 
 
 def _config_for(args):
@@ -265,7 +263,7 @@ def run_ours(args):
                 rows = ab.head_ce_rows(pred_emb, table, snap_target[:, s:s + chunk], model.config.softmax_tau)
                 loss = rows.sum() / (snap_idx.numel() * B_total)
             else:
-                loss = _TrajectoryLoss.apply(y_path, 128) * ((min(B, s + chunk) - s) / B_total)
+                loss = _TrajectoryLoss.apply(y_path) * ((min(B, s + chunk) - s) / B_total)
             loss.backward()
             total = loss.detach() if total is None else total + loss.detach()
             del y_path, loss
@@ -513,7 +511,7 @@ def reference_step_timer(cfg, train, device, steps=1, warmup=0, budget_agents=No
             table, zemb = m.zone_tables(feats, edges)
             y0 = m.initial_state(table, zemb, home, work, traits)
             yp = tdq.odeint(m.rhs, y0, t, **kw)
-            (yp[:, :, :128] ** 2).mean().backward()
+            (yp ** 2).mean().backward()
             del yp
         if on_gpu:
             torch.cuda.synchronize()

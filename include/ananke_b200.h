@@ -243,6 +243,11 @@ int ab200_pv_combine(const ab200_drift_desc* d, const float* y0, const float* co
 /* ab200_pv_combine whose result is the reference's ROW-MAJOR [B][D] trajectory row (blocked inputs, transposed on chip) */
 int ab200_pv_combine_rowmajor(const ab200_drift_desc* d, const float* y0, const float* const* a, int32_t n_a, float cpv,
                               const float* cpa_host, const float* cva_host, int64_t B, float* out_rowmajor, ab200_stream_t stream);
+/* n_rows row-major outputs of the SAME (y0, a[]) in one pass (the dense-output rows that fall inside one dopri5 step: y0 and
+ * the accelerations are read once): out_rowmajor[q] = combination (cpv[q], cpa[q * 8 + j], cva[q * 8 + j], j < n_a). */
+int ab200_pv_combine_rowmajor_multi(const ab200_drift_desc* d, const float* y0, const float* const* a, int32_t n_a, int32_t n_rows,
+                                    const float* cpv_host, const float* cpa_host, const float* cva_host, int64_t B,
+                                    float* const* out_rowmajor, ab200_stream_t stream);
 int ab200_pv_combine_backward(const ab200_drift_desc* d, const float* g, int32_t n_a, float cpv, const float* cpa_host,
                               const float* cva_host, int64_t B, float* G_y0, float* const* G_a, int32_t accumulate,
                               ab200_stream_t stream);

@@ -21,7 +21,7 @@ for it in range(reps):
     table, zemb = model.zone_tables(zfeat, csr)
     y0 = model.initial_state(table, zemb, home, work, traits)
     y_path = model.integrate(y0, t)
-    loss = bench._TrajectoryLoss.apply(y_path, 128)
+    loss = bench._TrajectoryLoss.apply(y_path)
     loss.backward()
     torch.cuda.synchronize()
     st = oi._LAST["solver"]
