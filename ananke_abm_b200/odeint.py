@@ -481,6 +481,12 @@ def odeint(func, y0, t, *, rtol: float = 1e-7, atol: float = 1e-9, method: Optio
     t_host = _check_t(t)
     t = t.to(y0.device)
     if y0.numel() == 0:      # empty batch (a rank with no agents): torchdiffeq returns the stacked, still empty, state
+        if options.get("error_norm") == "global":
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size(options.get("group")) > 1:
+                # the other ranks all-reduce the error norm once per attempt: a rank that returns here would leave them waiting
+                raise _lib.Ab200Error("error_norm='global' needs at least one agent on every rank (and the same number of solves "
+                                      "per rank): an empty shard cannot take part in the per-attempt all-reduce")
         return y0.unsqueeze(0).repeat(t_host.numel(), *([1] * y0.dim()))
     precision = _lib.PRECISIONS[options.pop("precision", _DEFAULT_PRECISION["value"])]
 

@@ -15,6 +15,7 @@ which is what the reference's training loops compute (mode_sep/train/train.py:16
 from __future__ import annotations
 
 import ctypes as C
+import math
 from dataclasses import dataclass
 from typing import List, Optional, Sequence
 
@@ -617,7 +618,7 @@ def dopri5_forward(eng: TcEngine, y0: torch.Tensor, t_host: Sequence[float], rto
         stats.n_evals += 6
         if use_global:
             dist.all_reduce(sumsq, group=group)
-        ratio = float(torch.sqrt(sumsq[0] / n_elems))
+        ratio = math.sqrt(float(sumsq.item()) / n_elems)      # ONE device->host read per attempt (NaN stays NaN)
         if ratio != ratio:
             eng.check_status()       # a kernel whose bounded barrier wait expired poisons the norm: report that, not an overflow
             raise _lib.Ab200Error("dopri5: non-finite error estimate (state or drift overflowed)")
