@@ -272,6 +272,87 @@ int ab200_stage_forward_fused(const ab200_drift_desc* d, const void* image, cons
                             (cudaStream_t)stream);
 }
 
+// ---- Dormand-Prince 5(4) tableau (tdq dopri5.py) and the (p0, v0, a_j) form of its linear combinations (second-order drift:
+// k_j = (v_in_j, a_j), see stage.py Tableau.combo) ---------------------------------------------------------------------
+namespace {
+const double DP_C[7] = {0.0, 1.0 / 5, 3.0 / 10, 4.0 / 5, 8.0 / 9, 1.0, 1.0};
+const double DP_BETA[7][6] = {
+    {0, 0, 0, 0, 0, 0},
+    {1.0 / 5, 0, 0, 0, 0, 0},
+    {3.0 / 40, 9.0 / 40, 0, 0, 0, 0},
+    {44.0 / 45, -56.0 / 15, 32.0 / 9, 0, 0, 0},
+    {19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729, 0, 0},
+    {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656, 0},
+    {35.0 / 384, 0.0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84}};
+const double DP_SOL[7] = {35.0 / 384, 0.0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84, 0.0};
+const double DP_ERR[7] = {35.0 / 384 - 1951.0 / 21600, 0.0, 500.0 / 1113 - 22642.0 / 50085, 125.0 / 192 - 451.0 / 720,
+                          -2187.0 / 6784 + 12231.0 / 42400, 11.0 / 84 - 649.0 / 6300, -1.0 / 60.0};
+const double DP_MID[7] = {6025192743.0 / 30085553152.0 / 2, 0.0, 51252292925.0 / 65400821598.0 / 2, -2691868925.0 / 45128329728.0 / 2,
+                          187940372067.0 / 1594534317056.0 / 2, -1776094331.0 / 19743644256.0 / 2, 11237099.0 / 235043384.0 / 2};
+// y0 + dt sum_j w_j k_j over (p0, v0, a_1..a_n):  p = p0 + cpv v0 + sum cpa[l] a_l,  v = v0 + sum cva[l] a_l
+void dp_combo(const double* w, int n, double dt, float* cpv, float* cpa, float* cva) {
+  double sw = 0.0;
+  for (int j = 0; j < n; ++j) sw += w[j];
+  *cpv = (float)(dt * sw);
+  for (int l = 0; l < n; ++l) {
+    double acc = 0.0;
+    for (int j = l + 1; j < n; ++j) acc += w[j] * (dt * DP_BETA[j][l]);     // k_j.p = v_in_j = v0 + dt sum_l beta[j][l] a_l
+    cpa[l] = (float)(dt * acc);
+    cva[l] = (float)(dt * w[l]);
+  }
+}
+}  // namespace
+
+int ab200_dopri5_attempt(const ab200_drift_desc* d, const void* image, const float* y0, float* const* a, double t0, double dt,
+                         int64_t B, float* y_out, double* err_sumsq, float rtol, float atol, int32_t operand_format,
+                         ab200_stream_t stream) {
+  if (!d || !image || !y0 || !a || !y_out || B <= 0 || operand_format < 0 || operand_format > 2) return AB200_ERR_BAD_ARG;
+  if (!stage_shape_ok(d)) return AB200_ERR_UNSUPPORTED;
+  for (int i = 0; i < 7; ++i)
+    if (!a[i]) return AB200_ERR_BAD_ARG;
+  ab200_stage_desc st[6];
+  memset(st, 0, sizeof(st));
+  float* outs[6];
+  const float* ins[AB200_STAGE_MAX_A];
+  for (int i = 0; i < 7; ++i) ins[i] = a[i];
+  for (int i = 1; i <= 6; ++i) {
+    ab200_stage_desc& s = st[i - 1];
+    s.n_a = i;
+    dp_combo(DP_BETA[i], i, dt, &s.in_cpv, s.in_cpa, s.in_cva);
+    s.t = (float)(i == 6 ? t0 + dt : t0 + DP_C[i] * dt);
+    outs[i - 1] = a[i];
+  }
+  ab200_stage_desc& last = st[5];
+  dp_combo(DP_SOL, 7, dt, &last.out_cpv, last.out_cpa, last.out_cva);
+  float unused;
+  dp_combo(DP_ERR, 7, dt, &unused, last.err_pa, last.err_va);
+  last.rtol = rtol;
+  last.atol = atol;
+  if (operand_format == 2)
+    return stage_fwd2_tc_multi(d, (const uint8_t*)image, y0, ins, st, 6, outs, B, y_out, err_sumsq, (cudaStream_t)stream);
+  return stage_fwd_tc_multi(d, (const uint8_t*)image, y0, ins, st, 6, outs, B, y_out, err_sumsq, operand_format, (cudaStream_t)stream);
+}
+
+int ab200_dopri5_dense_rows(const ab200_drift_desc* d, const float* y0, const float* const* a, double dt, int32_t n_rows,
+                            const double* x_host, int64_t B, float* const* out_rowmajor, ab200_stream_t stream) {
+  if (!desc_ok(d) || !y0 || !a || !x_host || !out_rowmajor || B <= 0 || n_rows < 1 || n_rows > 256) return AB200_ERR_BAD_ARG;
+  float cpv[256], cpa[256 * 8], cva[256 * 8];
+  for (int q = 0; q < n_rows; ++q) {
+    const double x = x_host[q];
+    double w[7];
+    for (int j = 0; j < 7; ++j) {       // interp.py: y(t0 + x dt) = y0 + dt sum_j W_j(x) k_j
+      const double e1 = (j == 0), e7 = (j == 6), cs = DP_SOL[j], cm = DP_MID[j];
+      const double c2 = e7 - 4 * e1 - 5 * cs + 16 * cm;
+      const double c3 = 5 * e1 - 3 * e7 + 14 * cs - 32 * cm;
+      const double c4 = 2 * (e7 - e1) - 8 * cs + 16 * cm;
+      w[j] = x * e1 + x * x * c2 + x * x * x * c3 + x * x * x * x * c4;
+    }
+    dp_combo(w, 7, dt, &cpv[q], &cpa[q * 8], &cva[q * 8]);
+    cpa[q * 8 + 7] = cva[q * 8 + 7] = 0.f;
+  }
+  return pv_combine_rowmajor_multi(d, y0, a, 7, n_rows, cpv, cpa, cva, B, out_rowmajor, (cudaStream_t)stream);
+}
+
 size_t ab200_stage_spill_bytes(const ab200_drift_desc* d, int32_t nblobs) {
   return (stage_shape_ok(d) && nblobs > 0) ? wgrad_spill_bytes(nblobs) : 0;
 }

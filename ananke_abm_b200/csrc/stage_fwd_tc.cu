@@ -226,11 +226,12 @@ __global__ void __launch_bounds__(THREADS, 1) stage_fwd_tc_kernel(const __grid_c
         tmem_ld16(c.tmem + c.lane_sel + C_ACC + (uint32_t)(c.hf * 32 + qd * 16), r);
         tmem_ld_wait();
         const int fq = f0 + qd * 4;
-        if (sp.a_out != nullptr && valid) {
+        if (sp.a_out != nullptr) {      // padding rows of the last tile are written as zeros: output buffers need no initialisation
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            *blk4(sp.a_out, tile, AF4, fq + j, c.row) = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                                                     __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+            *blk4(sp.a_out, tile, AF4, fq + j, c.row) = valid ? make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                                            __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]))
+                                                              : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         if (want_y) {
           float po[16], vo[16], ep[16], ev[16];
@@ -266,13 +267,15 @@ __global__ void __launch_bounds__(THREADS, 1) stage_fwd_tc_kernel(const __grid_c
               }
             }
           }
-          if (valid) {
+          {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              *blk4(sp.y_out, tile, YF4, fq + j, c.row) = make_float4(po[4 * j], po[4 * j + 1], po[4 * j + 2], po[4 * j + 3]);
-              *blk4(sp.y_out, tile, YF4, AF4 + fq + j, c.row) = make_float4(vo[4 * j], vo[4 * j + 1], vo[4 * j + 2], vo[4 * j + 3]);
+              *blk4(sp.y_out, tile, YF4, fq + j, c.row) =
+                  valid ? make_float4(po[4 * j], po[4 * j + 1], po[4 * j + 2], po[4 * j + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+              *blk4(sp.y_out, tile, YF4, AF4 + fq + j, c.row) =
+                  valid ? make_float4(vo[4 * j], vo[4 * j + 1], vo[4 * j + 2], vo[4 * j + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            if (want_err) {
+            if (valid && want_err) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) {       // y0 again (L1/L2 hit): keeping it live through the source loop costs 32 registers
                 const float4 p0 = ldro(blk4(a.y0, tile, YF4, fq + j, c.row));
@@ -290,11 +293,11 @@ __global__ void __launch_bounds__(THREADS, 1) stage_fwd_tc_kernel(const __grid_c
           }
         }
       }
-      if (want_y) {
-        if (valid) {   // context h rides along unchanged (dh/dt = 0)
+      if (want_y) {   // context h rides along unchanged (dh/dt = 0); padding rows: zeros
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            *blk4(sp.y_out, tile, YF4, 2 * AF4 + c.hf * 4 + j, c.row) = ldro(blk4(a.y0, tile, YF4, 2 * AF4 + c.hf * 4 + j, c.row));
+        for (int j = 0; j < 4; ++j) {
+          const float4 hv = ldro(blk4(a.y0, tile, YF4, 2 * AF4 + c.hf * 4 + j, c.row));
+          *blk4(sp.y_out, tile, YF4, 2 * AF4 + c.hf * 4 + j, c.row) = valid ? hv : make_float4(0.f, 0.f, 0.f, 0.f);
         }
       }
     }

@@ -19,6 +19,7 @@ import math
 from dataclasses import dataclass
 from typing import List, Optional, Sequence
 
+import numpy as np
 import torch
 
 from . import _lib
@@ -227,6 +228,24 @@ class TcEngine:
                                               C.cast(cpa, C.c_void_p), C.cast(cva, C.c_void_p), B, out_rowmajor.data_ptr(), _stream())
         _lib.check(rc, "ab200_pv_combine_rowmajor")
 
+    def dopri5_attempt(self, y0, A: Sequence[torch.Tensor], t0: float, dt: float, B: int, y_out, err_sumsq, rtol: float, atol: float) -> None:
+        """one attempted Dormand-Prince step in ONE call: stages 2..7 fused, descriptors built in C (ab200_dopri5_attempt)"""
+        ptrs = (C.c_void_p * 7)(*[t.data_ptr() for t in A[:7]])
+        rc = self.L.ab200_dopri5_attempt(C.byref(self.desc), self.image.data_ptr(), y0.data_ptr(), C.cast(ptrs, C.c_void_p), float(t0),
+                                         float(dt), B, y_out.data_ptr(), err_sumsq.data_ptr(), float(rtol), float(atol), self.fwd_format,
+                                         _stream())
+        _lib.check(rc, "ab200_dopri5_attempt")
+
+    def dopri5_dense_rows(self, y0, A: Sequence[torch.Tensor], dt: float, xs: Sequence[float], B: int, outs: Sequence[torch.Tensor]) -> None:
+        """dense-output rows of an accepted step at relative positions xs, one pass (ab200_dopri5_dense_rows)"""
+        n = len(xs)
+        ptrs = (C.c_void_p * 7)(*[t.data_ptr() for t in A[:7]])
+        xa = (C.c_double * n)(*[float(x) for x in xs])
+        op = (C.c_void_p * n)(*[o.data_ptr() for o in outs])
+        rc = self.L.ab200_dopri5_dense_rows(C.byref(self.desc), y0.data_ptr(), C.cast(ptrs, C.c_void_p), float(dt), n,
+                                            C.cast(xa, C.c_void_p), B, C.cast(op, C.c_void_p), _stream())
+        _lib.check(rc, "ab200_dopri5_dense_rows")
+
     def combine_rowmajor_multi(self, y0, a: Sequence[torch.Tensor], combos: Sequence[Combo], B: int, outs: Sequence[torch.Tensor]) -> None:
         """several dense-output rows of the same step in ONE pass (y0 and the accelerations are read once)"""
         n, nr = len(a), len(combos)
@@ -414,12 +433,9 @@ def blocked_zeros(B: int, F: int, device) -> torch.Tensor:
 
 
 def blocked_empty(B: int, F: int, device) -> torch.Tensor:
-    """Like `blocked_zeros` but only the padding rows of the last tile are zeroed (the kernels overwrite every real row)."""
-    Bp = padded_rows(B)
-    buf = torch.empty(Bp * F, dtype=torch.float32, device=device)
-    if Bp != B:
-        buf.view(Bp // TM, F // 4, TM, 4)[-1, :, B % TM:, :] = 0.0
-    return buf
+    """An uninitialised tile-blocked [Bp, F] buffer for kernel OUTPUTS (ab200_stage_forward* write every row of a_out / y_out,
+    zeros in the padding rows of the last tile)."""
+    return torch.empty(padded_rows(B) * F, dtype=torch.float32, device=device)
 
 
 def rows_block(src: torch.Tensor, dst: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
@@ -539,7 +555,7 @@ class Dopri5Stats:
 
 def _cast_time(v: float, time_dtype) -> float:
     if time_dtype == torch.float32:
-        return float(torch.tensor(v, dtype=torch.float32))
+        return float(np.float32(v))
     return float(v)
 
 
@@ -603,19 +619,35 @@ def dopri5_forward(eng: TcEngine, y0: torch.Tensor, t_host: Sequence[float], rto
     t0 = t1 = ts[0]
     k = 1
     n_steps = 0
-    c_sol, c_err = DOPRI5.b, DOPRI5.b_err
+    # The error norm is read on the host after every attempt; whatever the host does between that read and the next launch is
+    # GPU idle time.  So: the attempt's ~300 tableau coefficients are assembled in C (ab200_dopri5_attempt), the squared-error
+    # sums come from a pre-zeroed pool (no memset launch per attempt), the buffers of the next accepted step are one allocation,
+    # and the dense-output rows of an accepted step are launched AFTER the next attempt (their host work overlaps its execution).
+    pool_n = 256
+    pool = torch.zeros(pool_n, dtype=torch.float64, device=dev)
+    pending = None                              # (y, A, dt, outs) of the last accepted step whose dense rows are not launched yet
+
+    def flush_rows():
+        nonlocal pending
+        if pending is not None:
+            yb_, A_, dt_, outs_ = pending
+            eng.dopri5_dense_rows(yb_, A_, dt_, [x for _, x in outs_], B, [y_path[kk] for kk, _ in outs_])
+            pending = None
+
+    Bp = padded_rows(B)
     while k < T:
         # ---- one attempted step from t1 with size dt
         assert n_steps < max_num_steps, "max_num_steps exceeded ({}>={})".format(n_steps, max_num_steps)
         assert _cast_time(t1 + dt, time_dtype) > t1, "underflow in dt {}".format(dt)
         ta = t1
         tb = _cast_time(ta + dt, time_dtype)
-        stages = [(i, DOPRI5.stage_input(i, dt), _cast_time(ta + DOPRI5.c[i] * dt, time_dtype), A[i]) for i in range(1, 6)]
-        stages.append((6, DOPRI5.stage_input(6, dt), tb, A[6]))
-        sumsq.zero_()
-        eng.stage_forward_fused(y_cur, A, stages, B, y_out=y_next, cout=DOPRI5.combo(c_sol, dt), err_sumsq=sumsq,
-                                cerr=DOPRI5.combo(c_err, dt), rtol=rtol, atol=atol)
+        slot = n_steps % pool_n
+        if slot == 0 and n_steps > 0:
+            pool.zero_()
+        sumsq = pool[slot:slot + 1]
+        eng.dopri5_attempt(y_cur, A, ta, dt, B, y_next, sumsq, rtol, atol)
         stats.n_evals += 6
+        flush_rows()
         if use_global:
             dist.all_reduce(sumsq, group=group)
         ratio = math.sqrt(float(sumsq.item()) / n_elems)      # ONE device->host read per attempt (NaN stays NaN)
@@ -629,14 +661,16 @@ def dopri5_forward(eng: TcEngine, y0: torch.Tensor, t_host: Sequence[float], rto
             while k < T and ts[k] <= tb:
                 outs.append((k, (ts[k] - ta) / (tb - ta)))
                 k += 1
-            if outs:       # every requested time inside (t, t + dt]: one pass over (y, a_1..a_7) for all of them
-                eng.combine_rowmajor_multi(y_cur, A, [DOPRI5.combo(dopri5_interp_weights(x), dt) for _, x in outs], B,
-                                           [y_path[kk] for kk, _ in outs])
             if save_steps:
+                if outs:
+                    pending = (y_cur, A, dt, outs)
                 steps.append(_Dopri5Step(y_cur, A, ta, dt, outs))
-                y_cur, y_next = y_next, blocked_empty(B, D, dev)
-                A = [A[6]] + [blocked_empty(B, P, dev) for _ in range(6)]
+                buf = torch.empty(Bp * (D + 6 * P), dtype=torch.float32, device=dev)     # y_next + a_2..a_7 of the next step
+                y_cur, y_next = y_next, buf[:Bp * D]
+                A = [A[6]] + [buf[Bp * (D + i * P):Bp * (D + (i + 1) * P)] for i in range(6)]
             else:
+                if outs:       # buffers are recycled by the next attempt: every requested time inside (t, t + dt] now
+                    eng.dopri5_dense_rows(y_cur, A, dt, [x for _, x in outs], B, [y_path[kk] for kk, _ in outs])
                 y_cur, y_next = y_next, y_cur
                 A[0], A[6] = A[6], A[0]
             t0, t1 = ta, tb
@@ -648,6 +682,7 @@ def dopri5_forward(eng: TcEngine, y0: torch.Tensor, t_host: Sequence[float], rto
         else:
             dfac = 1.0 if ratio < 1.0 else dfactor
             dt = _cast_time(dt * min(ifactor, max(safety / ratio ** 0.2, dfac)), time_dtype)
+    flush_rows()
     eng.fwd_format = prev_fmt
     eng.check_status()
     return y_path, (steps if save_steps else None), stats

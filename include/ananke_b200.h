@@ -151,7 +151,8 @@ typedef struct ab200_stage_desc {
  * of ab200_pv_combine*): "tile-blocked".  Rows are padded to Bp = ceil(B / 128) * 128; inside a 128-agent tile the
  * float4 with features 4 f4 .. 4 f4 + 3 of agent r is float4 number (tile * F/4 + f4) * 128 + r of the buffer, so a warp
  * whose lanes own consecutive agents (= consecutive tensor-memory lanes) touches one contiguous 512-byte segment per
- * access.  Padding rows must hold zeros (ab200_rows_block writes them; the kernels never store to them).
+ * access.  Padding rows of INPUT buffers must hold zeros (ab200_rows_block writes them; ab200_stage_forward* write zeros to
+ * the padding rows of a_out / y_out, so output buffers may be uninitialised; no other kernel stores to padding rows).
  * ab200_rows_block / ab200_rows_unblock convert from / to the reference's row-major [B][F] tensors
  * (accumulate = 1: blocked += row-major). */
 int ab200_rows_block(const float* src_rowmajor, float* dst_blocked, int64_t B, int32_t F, int32_t accumulate,
@@ -179,6 +180,21 @@ int ab200_stage_forward(const ab200_drift_desc* d, const void* image, const floa
 int ab200_stage_forward_fused(const ab200_drift_desc* d, const void* image, const float* y0, const float* const* a,
                               const ab200_stage_desc* stages, int32_t n_stage, float* const* a_out, int64_t B,
                               float* y_out, double* err_sumsq, int32_t operand_format, ab200_stream_t stream);
+
+/* One attempted Dormand-Prince 5(4) step (tdq dopri5.py tableau, rk_common.py `_runge_kutta_step`) = ab200_stage_forward_fused over
+ * stages 2..7 with every stage descriptor built HERE from (t0, dt): a[0] holds the acceleration of the step's first stage (k_1,
+ * the previous step's FSAL evaluation), a[1..6] receive a_2..a_7; y_out = the 5th-order solution, *err_sumsq += the squared
+ * error-ratio sum of the embedded 4th-order estimate.  Exists because an adaptive solver reads the error norm on the host after
+ * every attempt: the time between that read and the next launch is GPU idle time, and assembling ~300 tableau coefficients in
+ * the caller's interpreter costs more than a forward launch over a 100k-agent shard takes. */
+int ab200_dopri5_attempt(const ab200_drift_desc* d, const void* image, const float* y0, float* const* a, double t0, double dt,
+                         int64_t B, float* y_out, double* err_sumsq, float rtol, float atol, int32_t operand_format,
+                         ab200_stream_t stream);
+/* The dense-output rows of an accepted dopri5 step at relative positions x[q] = (t_q - t0) / dt in (0, 1] (tdq interp.py
+ * `_interp_fit` / `_interp_evaluate`: the quartic through y0, y1, y_mid, f0, f1, expanded over the seven stage derivatives):
+ * out_rowmajor[q] (row-major [B][D]) for q < n_rows, all in one pass over (y0, a[0..6]). */
+int ab200_dopri5_dense_rows(const ab200_drift_desc* d, const float* y0, const float* const* a, double dt, int32_t n_rows,
+                            const double* x_host, int64_t B, float* const* out_rowmajor, ab200_stream_t stream);
 
 /* Vector-Jacobian product of one stage = what autograd does for the ops of one `func` call inside the solver
  * (mode_sep/train/train.py:162).  The upstream gradient is assembled in the kernel as
