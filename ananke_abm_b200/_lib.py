@@ -51,6 +51,10 @@ SIGNATURES = {
     "ab200_drift_eval": (C.c_int, [_dp, _vp, _f32, _vp, _i64, _vp, _vp, _sz, _i32, _vp]),
     "ab200_drift_vjp_workspace_bytes": (_sz, [_dp, _i64]),
     "ab200_drift_vjp": (C.c_int, [_dp, _vp, _f32, _vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "ab200_emb_losses_forward": (C.c_int, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32,
+                                           _f32, _f32, _f32, _f32, _vp, _vp]),
+    "ab200_emb_losses_backward": (C.c_int, [_vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32,
+                                            _f32, _f32, _f32, _f32, _vp, _vp, _vp, _vp, _vp]),
     "ab200_rk_stage_combine": (C.c_int, [_vp, _vp, _vp, _i32, _f32, _vp, _i64, _vp]),
     "ab200_rk_combine_errnorm": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _f32, _f32, _f32, _vp, _vp, _i64, _vp]),
     "ab200_head_workspace_bytes": (_sz, [_i32, _i32]),

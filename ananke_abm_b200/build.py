@@ -12,7 +12,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libananke_b200.so"
 SOURCES = ["capi.cu", "rk4_f32.cu", "rk4_bwd_f32.cu", "rk_combine.cu", "umma_probe.cu", "rk4_tc.cu", "gat.cu",
-           "stage_fwd_tc.cu", "stage_fwd2_tc.cu", "stage_bwd_tc.cu", "wgrad_tc.cu", "stage_elem.cu", "head_tc.cu", "head_bwd_tc.cu", "optim.cu", "sde_em.cu"]
+           "stage_fwd_tc.cu", "stage_fwd2_tc.cu", "stage_bwd_tc.cu", "wgrad_tc.cu", "stage_elem.cu", "head_tc.cu", "head_bwd_tc.cu", "optim.cu", "sde_em.cu", "emb_losses.cu"]
 OPTIONAL = []
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -6,9 +6,10 @@ Mirrors /root/reference/src/ananke_abm/models/latent_ode/architecture/model.py:9
 latent_ode/config.py:18-71.  Same `state_dict` keys, so checkpoints are interchangeable.  The encoder / decoders /
 einsum head are host-side PyTorch plumbing; every drift evaluation and all solver algebra inside `odeint` run in
 libananke_b200.so (`ab200_drift_eval` with the closed-form correction term, `ab200_rk_combine_errnorm`).
-The SDE branch (`enable_sde=True`, the reference default) runs forward-only (Euler-Maruyama sampling, `sdeint.py`); training
-runs the ODE
-branch and raises if asked for the SDE.  `zone_embed` may be a `gnn_embed.GATEmbed`: the slot a GAT fills (:171-173).
+Training back-propagates through dopri5 on kernels (every drift evaluation carries `ab200_drift_vjp` as its backward); the SDE
+branch (`enable_sde=True`, the reference default) samples with Euler-Maruyama (`sdeint.py`) and trains through the sampler the
+same way.  `calculate_composite_loss` is the 8-term loss of latent_ode/architecture/loss.py.  `zone_embed` may be a
+`gnn_embed.GATEmbed`: the slot a GAT fills (:171-173).
 """
 from __future__ import annotations
 
@@ -41,6 +42,15 @@ class GenerativeODEConfig:                  # latent_ode/config.py:18-71 (fields
     sde_noise_strength: float = 0.1
     num_modes: int = 5
     purpose_groups: tuple = field(default_factory=lambda: PURPOSE_GROUPS)
+    # loss weights (latent_ode/config.py:38-48), read by `calculate_composite_loss`
+    kl_weight: float = 0.5
+    loss_weight_classification: float = 1.0
+    loss_weight_embedding: float = 0.5
+    loss_weight_distance: float = 2.0
+    loss_weight_purpose_class: float = 0.75
+    loss_weight_mode_class: float = 1.0
+    loss_weight_purpose_mse: float = 0.5
+    loss_weight_mode_mse: float = 0.5
 
 
 class ODEFunc(nn.Module):                   # model.py:19-117 -- parameter holder; `describe_drift` recognises this shape
@@ -123,3 +133,52 @@ class GenerativeODE(nn.Module):
         loc_logits = torch.einsum("bsd,zd->bsz", self.decoder_loc(loc_embed), cand)
         return (loc_logits, loc_embed, self.decoder_purpose(purp_feat), self.decoder_mode(mode_feat), purp_feat, mode_feat,
                 h0_mu, h0_log_var)
+
+
+def calculate_composite_loss(batch, model_outputs, model, distance_matrix, config):
+    """The latent model's 8-term training loss with the reference's signature and return tuple
+    (latent_ode/architecture/loss.py:7-100; called at latent_ode/train/train.py:67-70):
+
+        (total, classification, embedding, distance, purpose_class, purpose_mse, mode_class, mode_mse, kl)
+
+    `batch` is the collate dict of `unify_and_interpolate_batch`, `model_outputs` the 8-tuple of `GenerativeODE.forward`.
+    Every term is a masked mean over the [B, T] grid weighted by `loss_mask`; the targets of the embedding term are the zone
+    embeddings of the previous / next REAL observation blended by elapsed time.  All inputs are [B, T, <= 8]-sized at the
+    reference's scale (B = 2, Z = 8): this is host-side glue in PyTorch ops on the tensors' device, term for term the
+    reference's arithmetic; the ODE solve that produces `model_outputs` is what runs in the CUDA library."""
+    import torch.nn.functional as F
+    (loc_logits, loc_embed, purp_logits, mode_logits, purp_feat, mode_feat, mu, log_var) = model_outputs
+    t = batch["t_unified"]
+    y_loc, y_purp, y_mode = batch["y_loc_dense"], batch["y_purp_dense"], batch["y_mode_dense"]
+    mask = batch["loss_mask"]
+    msum = mask.sum()
+    B = loc_logits.shape[0]
+
+    def masked_ce(logits, target):
+        ce = F.cross_entropy(logits.reshape(-1, logits.shape[-1]), target.reshape(-1), ignore_index=-1, reduction="none")
+        return (ce * mask.reshape(-1)).sum() / msum
+
+    def masked_mse(pred, target):
+        return (F.mse_loss(pred, target, reduction="none").mean(dim=-1) * mask).sum() / msum
+
+    loss_classification = masked_ce(loc_logits, y_loc)
+    cand = model.zone_feature_encoder(batch["all_zone_features"])
+    prev_ids = torch.gather(y_loc, 1, batch["prev_real_indices"])
+    next_ids = torch.gather(y_loc, 1, batch["next_real_indices"])
+    prev_e, next_e = cand[prev_ids.clamp(min=0)], cand[next_ids.clamp(min=0)]
+    t_prev, t_next = t[batch["prev_real_indices"]], t[batch["next_real_indices"]]
+    w_next = torch.clamp((t.unsqueeze(0) - t_prev) / (t_next - t_prev + 1e-8), 0, 1).unsqueeze(-1)
+    loss_embedding = masked_mse(loc_embed, (1 - w_next) * prev_e + w_next * next_e)
+    pred_ids = torch.argmax(loc_logits, dim=2)
+    loss_distance = (distance_matrix[pred_ids, y_loc.clamp(min=0)] * mask).sum() / msum
+    loss_purpose_class = masked_ce(purp_logits, y_purp)
+    loss_purpose_mse = masked_mse(purp_feat, batch["y_purp_feat_dense"])
+    loss_mode_class = masked_ce(mode_logits, y_mode)
+    loss_mode_mse = masked_mse(mode_feat, batch["y_mode_feat_dense"])
+    kl = -0.5 * torch.sum(1 + log_var - mu.pow(2) - log_var.exp()) / B
+    total = (config.loss_weight_classification * loss_classification + config.loss_weight_embedding * loss_embedding
+             + config.loss_weight_distance * loss_distance + config.loss_weight_purpose_class * loss_purpose_class
+             + config.loss_weight_mode_class * loss_mode_class + config.loss_weight_purpose_mse * loss_purpose_mse
+             + config.loss_weight_mode_mse * loss_mode_mse + config.kl_weight * kl)
+    return (total, loss_classification, loss_embedding, loss_distance, loss_purpose_class, loss_purpose_mse, loss_mode_class,
+            loss_mode_mse, kl)

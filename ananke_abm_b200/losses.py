@@ -131,3 +131,105 @@ def ce_and_expected_distance_at_snaps_fused(pred_emb: torch.Tensor, class_table:
         return z, z.clone()
     ce, ed = head_loss_rows(pred_emb[mask], class_table, y_union[mask], tau, dist_mat)
     return ce.mean(), ed.mean()
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# embedding-space terms (mse, travel margin / monotonicity, velocity regularisers) and the whole mode_sep objective
+# --------------------------------------------------------------------------------------------------------------------
+def _strided_rows(x: torch.Tensor):
+    """[B, T, E] fp32 with unit inner stride and 16-byte aligned rows -> (tensor, stride_b, stride_t); copies otherwise"""
+    if x.dtype != torch.float32 or x.stride(-1) != 1 or x.stride(0) % 4 or x.stride(1) % 4 or x.data_ptr() % 16:
+        x = x.float().contiguous()
+    return x, int(x.stride(0)), int(x.stride(1))
+
+
+class _EmbLosses(torch.autograd.Function):
+    """-> the six embedding-space loss terms of the mode_sep objective as 0-dim tensors, from ONE pass over (pred_emb, v_t):
+    [mse at snaps, mse inside stays, travel margin, travel monotonicity, stay velocity, move velocity]
+    (`ab200_emb_losses_forward` / `_backward`; masked means with the reference's "0 when the mask is empty" rule)."""
+
+    @staticmethod
+    def forward(ctx, pred_emb, v_t, class_table, y_union, is_gt, y_stay, stay_non_gt, travel_mask, prev_idx, dest_idx, gt_interior,
+                m_travel: float, epsilon_mono: float, v_min: float, v_max: float):
+        L = _lib.lib()
+        if not pred_emb.is_cuda:
+            raise _lib.Ab200Error("pred_emb must be a CUDA tensor: ananke_abm_b200 has no CPU path")
+        B, T, E = pred_emb.shape
+        Z = class_table.shape[0]
+        emb, esb, est = _strided_rows(pred_emb.detach())
+        vt, vsb, vst = _strided_rows(v_t.detach())
+        table = class_table.detach().contiguous().float()
+        idx = [t.contiguous().to(torch.int64) for t in (y_union, y_stay, prev_idx, dest_idx)]
+        msk = [t.contiguous().to(torch.bool) for t in (is_gt, stay_non_gt, travel_mask, gt_interior)]
+        sums = torch.zeros(12, dtype=torch.float64, device=pred_emb.device)
+        par = (float(m_travel), float(epsilon_mono), float(v_min), float(v_max))
+        rc = L.ab200_emb_losses_forward(emb.data_ptr(), esb, est, vt.data_ptr(), vsb, vst, table.data_ptr(), idx[0].data_ptr(),
+                                        msk[0].data_ptr(), idx[1].data_ptr(), msk[1].data_ptr(), msk[2].data_ptr(), idx[2].data_ptr(),
+                                        idx[3].data_ptr(), msk[3].data_ptr(), B, T, E, Z, *par, sums.data_ptr(),
+                                        torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "ab200_emb_losses_forward")
+        cnt = torch.stack([sums[1], sums[3], sums[5], sums[8], sums[3], sums[11]])
+        num = torch.stack([sums[0], sums[2], sums[4], 0.5 * (sums[6] + sums[7]), sums[9], sums[10]])
+        terms = torch.where(cnt > 0, num / cnt.clamp_min(1.0), torch.zeros_like(num)).float()
+        ctx.save_for_backward(emb, vt, table, *idx, *msk, cnt)
+        ctx.par, ctx.strides, ctx.shape = par, (esb, est, vsb, vst), (B, T, E, Z)
+        return tuple(terms.unbind(0))
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, *g):
+        L = _lib.lib()
+        emb, vt, table, y_union, y_stay, prev_idx, dest_idx, is_gt, stay_non_gt, travel_mask, gt_interior, cnt = ctx.saved_tensors
+        B, T, E, Z = ctx.shape
+        esb, est, vsb, vst = ctx.strides
+        gs = torch.stack([x.reshape(()).double() for x in g])
+        scale = torch.tensor([1.0, 1.0, 1.0, 0.5, 1.0, 1.0], dtype=torch.float64, device=emb.device)
+        coef = torch.where(cnt > 0, gs * scale / cnt.clamp_min(1.0), torch.zeros_like(gs)).float().contiguous()
+        d_emb = torch.empty((B, T, E), dtype=torch.float32, device=emb.device)
+        d_v = torch.empty((B, T, E), dtype=torch.float32, device=emb.device)
+        d_table = torch.zeros((Z, E), dtype=torch.float32, device=emb.device)
+        rc = L.ab200_emb_losses_backward(emb.data_ptr(), esb, est, vt.data_ptr(), vsb, vst, table.data_ptr(), y_union.data_ptr(),
+                                         is_gt.data_ptr(), y_stay.data_ptr(), stay_non_gt.data_ptr(), travel_mask.data_ptr(),
+                                         prev_idx.data_ptr(), dest_idx.data_ptr(), gt_interior.data_ptr(), B, T, E, Z, *ctx.par,
+                                         coef.data_ptr(), d_emb.data_ptr(), d_v.data_ptr(), d_table.data_ptr(),
+                                         torch.cuda.current_stream().cuda_stream)
+        _lib.check(rc, "ab200_emb_losses_backward")
+        return (d_emb, d_v, d_table) + (None,) * 12
+
+
+def emb_loss_terms(pred_emb, v_t, class_table, y_union, is_gt, y_stay, stay_non_gt, travel_mask, prev_idx, dest_idx, gt_interior,
+                   m_travel: float = 0.10, epsilon_mono: float = 0.01, v_min_move: float = 0.2, v_max_move: float = 1.0):
+    """The reference's `mse_at_snaps` (at snaps and, second value, at the non-snap stay points), `travel_margin_loss`,
+    `travel_monotonicity_loss` (mode_sep/architecture/losses.py:24-31, 56-115) and the two velocity regularisers of the
+    training loop (mode_sep/train/train.py:137-153) in one fused pass; same values, same "0 when the mask is empty" rule."""
+    names = ("mse", "stay_mse", "travel_margin", "travel_mono", "stay_vel", "move_vel")
+    vals = _EmbLosses.apply(pred_emb, v_t, class_table, y_union, is_gt, y_stay, stay_non_gt, travel_mask, prev_idx, dest_idx,
+                            gt_interior, m_travel, epsilon_mono, v_min_move, v_max_move)
+    return dict(zip(names, vals))
+
+
+def mode_sep_total_loss(config, pred_emb, v_t, class_table, union, y_union, dist_mat):
+    """The COMPLETE training objective of the reference's mode_sep loop (mode_sep/train/train.py:111-159), from the head's
+    inputs instead of the `[B, T, Z]` logits:
+
+        total_loss(...)                              losses.py:118-158   w_ce ce + w_mse mse + w_dist dist + travel terms
+      + w_stay_aux (ce + mse + dist at stay_non_gt)  train.py:121-135
+      + w_stay_vel_core stay_vel + w_move_vel_hinge move_vel          train.py:137-159
+
+    `union` is the `UnionBatch` of `build_union_batch`, `y_union [B, T]` the zone id at snaps (-1 elsewhere, train.py:102-108).
+    Cross entropy and expected distance come from the fused tensor-core head (two masked row sets), every embedding-space
+    term from the fused pass above.  -> (total, parts) with `parts` a dict of 0-dim tensors (no host sync)."""
+    tau = config.softmax_tau
+    ce, dist = ce_and_expected_distance_at_snaps_fused(pred_emb, class_table, y_union, dist_mat, union.is_gt_union, tau)
+    aux_ce, aux_dist = ce_and_expected_distance_at_snaps_fused(pred_emb, class_table, union.stay_loc_ids, dist_mat,
+                                                               union.stay_non_gt_mask, tau)
+    e = emb_loss_terms(pred_emb, v_t, class_table, y_union, union.is_gt_union, union.stay_loc_ids, union.stay_non_gt_mask,
+                       union.travel_mask, union.prev_zone_idx, union.dest_zone_idx, union.gt_interior_mask,
+                       config.m_travel, config.epsilon_mono, config.v_min_move, config.v_max_move)
+    base = (config.w_ce * ce + config.w_mse * e["mse"] + config.w_dist * dist + config.w_travel_margin * e["travel_margin"]
+            + config.w_travel_mono * e["travel_mono"])
+    aux = config.w_stay_aux * (aux_ce + e["stay_mse"] + aux_dist)
+    total = base + aux + config.w_stay_vel_core * e["stay_vel"] + config.w_move_vel_hinge * e["move_vel"]
+    parts = {"ce": ce, "mse": e["mse"], "dist": dist, "travel_margin": e["travel_margin"], "travel_mono": e["travel_mono"],
+             "stay_aux": aux, "stay_vel": e["stay_vel"], "move_vel": e["move_vel"], "base": base}
+    return total, parts

@@ -39,6 +39,22 @@ class ModeSepConfig:                       # mode_sep/config.py:9-71 (fields the
     sde_method: str = "euler"              # config.py:34-35
     sde_dt: float = 0.01
     softmax_tau: float = 0.2
+    # loss weights and thresholds (config.py:38-53), read by losses.mode_sep_total_loss
+    w_ce: float = 1.0
+    w_mse: float = 0.5
+    w_dist: float = 0.5
+    w_stay_aux: float = 0.9
+    w_stay_vel_core: float = 5.0
+    w_move_vel_hinge: float = 1.0
+    v_min_move: float = 0.2
+    v_max_move: float = 1.0
+    w_travel_margin: float = 1.0
+    w_travel_mono: float = 0.5
+    m_travel: float = 0.10
+    epsilon_mono: float = 0.01
+    lr: float = 1e-3
+    weight_decay: float = 0.0
+    grad_clip: float = 1.0
     precision: str = "f32"                 # ananke_b200 extension: 'f32' | 'bf16' (tensor-core drift GEMMs)
     error_norm: str = "shard"              # dopri5 across ranks: 'global' = one RMS norm over all shards (single-process parity)
 
@@ -143,6 +159,15 @@ class ModeSepModel(nn.Module):
         emb_norm = pred_emb / (pred_emb.norm(dim=-1, keepdim=True) + 1e-8)
         logits = torch.einsum("bte,ze->btz", emb_norm, table_norm) / self.config.softmax_tau
         return pred_emb, logits, v_t
+
+    def training_loss(self, times_union, home_idx, work_idx, person_traits_raw, union, y_union, dist_mat):
+        """One training forward of mode_sep/train/train.py:94-159 WITHOUT the `[B, T, Z]` logits: solve -> decoder -> the complete
+        objective (`losses.mode_sep_total_loss`).  `union` = the `UnionBatch`, `y_union [B, T]` = zone id at snaps (-1 elsewhere).
+        -> (total, parts)."""
+        from .losses import mode_sep_total_loss
+        E = self.config.emb_dim
+        yb = self.integrate(self.initial_state(home_idx, work_idx, person_traits_raw), times_union).permute(1, 0, 2)
+        return mode_sep_total_loss(self.config, self.decoder(yb[:, :, :E]), yb[:, :, E:2 * E], self.class_table, union, y_union, dist_mat)
 
     def forward(self, times_union, home_idx, work_idx, person_traits_raw) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         y0 = self.initial_state(home_idx, work_idx, person_traits_raw)

@@ -57,6 +57,18 @@ class GATODEModel(nn.Module):
         emb_norm = pred_emb / (pred_emb.norm(dim=-1, keepdim=True) + 1e-8)
         return pred_emb, torch.einsum("bte,ze->btz", emb_norm, table_norm) / self.config.softmax_tau, v_t
 
+    def training_loss(self, times_union, home_idx, work_idx, person_traits_raw, zone_features, graph: ZoneCSR, union, y_union, dist_mat):
+        """One training forward WITHOUT the `[B, T, Z]` logits: zone tables -> initial state -> solve -> decoder -> the complete
+        mode_sep objective (`losses.mode_sep_total_loss`: fused tensor-core head for cross entropy / expected distance, fused
+        pass for the embedding-space terms).  -> (total, parts); call `.backward()` on `total`
+        (mode_sep/train/train.py:94-162 with the GAT tables in place of the learnable lookups)."""
+        from .losses import mode_sep_total_loss
+        E = self.config.emb_dim
+        class_table, zone_embed = self.zone_tables(zone_features, graph)
+        y0 = self.initial_state(class_table, zone_embed, home_idx, work_idx, person_traits_raw)
+        yb = self.integrate(y0, times_union).permute(1, 0, 2)
+        return mode_sep_total_loss(self.config, self.decoder(yb[:, :, :E]), yb[:, :, E:2 * E], class_table, union, y_union, dist_mat)
+
     def forward(self, times_union, home_idx, work_idx, person_traits_raw, zone_features, graph: ZoneCSR):
         class_table, zone_embed = self.zone_tables(zone_features, graph)
         y0 = self.initial_state(class_table, zone_embed, home_idx, work_idx, person_traits_raw)

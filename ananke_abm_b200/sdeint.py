@@ -8,8 +8,9 @@ Fixed-step Euler-Maruyama for diagonal Ito noise: the drift `sde.f` of the recog
 state, counter-based Philox noise generated in the kernel).  Stepping follows torchsde's fixed-step solvers: grid
 t0 + k*dt clipped at ts[-1], requested times read off by linear interpolation between the surrounding grid points.
 
-Forward (sampling / inference) only: back-propagation through the 2,400 steps per day is not implemented and a call
-that needs gradients fails loudly.  The noise is this package's own specification (csrc/sde_em.cu) -- torchsde's
+A call that needs gradients records the same steps with autograd (`_EulerMaruyamaStep`: the step kernel forward, d/dy = 1,
+d/df = h, d/dg = sqrt(h) xi backward; the drift evaluation carries `ab200_drift_vjp`): the reference's default latent_ode
+training path (latent_ode/train/train.py:57-74 with enable_sde=True).  The noise is this package's own specification (csrc/sde_em.cu) -- torchsde's
 Brownian interval is not reproducible -- seeded by `seed=` (or drawn from torch's generator when omitted).
 """
 from __future__ import annotations

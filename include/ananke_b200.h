@@ -112,6 +112,29 @@ size_t ab200_drift_vjp_workspace_bytes(const ab200_drift_desc* d, int64_t B);
 int ab200_drift_vjp(const ab200_drift_desc* d, const float* w_flat, float t, const float* y, const float* grad_out, int64_t B,
                     float* grad_y, float* grad_w_flat, void* workspace, size_t workspace_bytes, ab200_stream_t stream);
 
+/* Embedding-space terms of the mode_sep training loss in one pass over pred_emb / v_t [B][T][E] (E = 64; element (b, t, e) at
+ * ptr[b * stride_b + t * stride_t + e], strides in floats, multiples of 4):
+ *   sums12[0] = sum over is_gt rows of |pred_emb - class_table[y_union]|^2,      [1] = number of is_gt rows      (mse_at_snaps,
+ *   sums12[2], [3] = the same over stay_non_gt rows against y_stay                mode_sep/architecture/losses.py:24-31; train.py:126-135)
+ *   sums12[4] = sum over travel rows of (m_travel - (d_prev - d_dest))+,          [5] = number of travel rows    (losses.py:56-73)
+ *   sums12[6], [7] = sums of the two monotonicity hinges over pairs (t, t+1) of one travel segment, [8] = pairs  (losses.py:76-115)
+ *   sums12[9] = sum over stay_non_gt rows of |v|^2 ;  sums12[10] = sum over gt_interior rows of (v_min - |v|)+^2 + (|v| - v_max)+^2,
+ *   sums12[11] = number of gt_interior rows                                                          (mode_sep/train/train.py:137-153)
+ * accumulated into 12 device doubles (zeroed by the caller).  The backward takes coef6 (device) = d total / d of the six sums
+ * {mse_gt, mse_stay, margin, each monotonicity hinge, stay_vel, move_vel} and OVERWRITES grad_pred_emb / grad_v ([B][T][E]
+ * contiguous) and ACCUMULATES into grad_class_table [Z][E].  Masks are bytes (torch.bool), indices int64 (-1 = none). */
+int ab200_emb_losses_forward(const float* pred_emb, int64_t emb_stride_b, int64_t emb_stride_t, const float* v_t, int64_t v_stride_b,
+                             int64_t v_stride_t, const float* class_table, const int64_t* y_union, const uint8_t* is_gt,
+                             const int64_t* y_stay, const uint8_t* stay_non_gt, const uint8_t* travel_mask, const int64_t* prev_idx,
+                             const int64_t* dest_idx, const uint8_t* gt_interior, int64_t B, int32_t T, int32_t E, int32_t Z,
+                             float m_travel, float epsilon_mono, float v_min_move, float v_max_move, double* sums12, void* stream);
+int ab200_emb_losses_backward(const float* pred_emb, int64_t emb_stride_b, int64_t emb_stride_t, const float* v_t, int64_t v_stride_b,
+                              int64_t v_stride_t, const float* class_table, const int64_t* y_union, const uint8_t* is_gt,
+                              const int64_t* y_stay, const uint8_t* stay_non_gt, const uint8_t* travel_mask, const int64_t* prev_idx,
+                              const int64_t* dest_idx, const uint8_t* gt_interior, int64_t B, int32_t T, int32_t E, int32_t Z,
+                              float m_travel, float epsilon_mono, float v_min_move, float v_max_move, const float* coef6,
+                              float* grad_pred_emb, float* grad_v, float* grad_class_table, void* stream);
+
 /* ---- generic-func path: fused Runge-Kutta stage combine (+ error norm) ------------------------
  * For an arbitrary `func` evaluated by the caller.  out[i] = y[i] + dt * sum_j coef[j] * k_j[i]
  * (tdq: rk_common.py `_runge_kutta_step`: yi = y0 + sum(k[..., :i+1] * (beta_i * dt))).

@@ -213,6 +213,40 @@ def latent_fixture():
                                                                       solver.n_rejected, loss.item()))
 
 
+def latent_loss_fixture():
+    """The reference's own `calculate_composite_loss` (latent_ode/architecture/loss.py:7-100, unmodified) on the frozen latent
+    fixture: the model outputs of latent_ode_fixture.npz as leaves -> the nine returned values and the gradients with respect to
+    every model output and to the zone encoder -> latent_loss_fixture.npz."""
+    from ananke_abm.models.latent_ode.config import GenerativeODEConfig
+    from ananke_abm.models.latent_ode.data_process.data import DataProcessor
+    from ananke_abm.models.latent_ode.architecture.model import GenerativeODE
+    from ananke_abm.models.latent_ode.architecture.loss import calculate_composite_loss
+    g = np.load(HERE / "latent_ode_fixture.npz", allow_pickle=False)
+    cfg = GenerativeODEConfig()
+    cfg.enable_sde = False
+    proc = DataProcessor(torch.device("cpu"), cfg)
+    model = GenerativeODE(person_feat_dim=g["batch_person_features"].shape[-1], num_zone_features=g["batch_all_zone_features"].shape[-1],
+                          config=cfg)
+    model.load_state_dict({k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd_")})
+    names = ["loc_logits", "loc_embed", "purp_logits", "mode_logits", "purp_feat", "mode_feat", "h0_mu", "h0_log_var"]
+    outs = [torch.from_numpy(g[n]).clone().requires_grad_(True) for n in names]
+    batch = {k[6:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("batch_") and g[k].dtype.kind in "fiub" and g[k].ndim > 0}
+    vals = calculate_composite_loss(batch, tuple(outs), model, proc.distance_matrix, cfg)
+    vals[0].backward()
+    out = {"distance_matrix": _np(proc.distance_matrix)}
+    for n, v in zip(["total", "classification", "embedding", "distance", "purpose_class", "purpose_mse", "mode_class", "mode_mse", "kl"], vals):
+        out["loss_" + n] = np.float64(v.item())
+    for n, o in zip(names, outs):
+        out["grad_" + n] = _np(o.grad) if o.grad is not None else np.zeros(tuple(o.shape), np.float32)
+    out["grad_zone_feature_encoder.weight"] = _np(model.zone_feature_encoder.weight.grad)
+    out["grad_zone_feature_encoder.bias"] = _np(model.zone_feature_encoder.bias.grad)
+    for k in ("loss_weight_classification", "loss_weight_embedding", "loss_weight_distance", "loss_weight_purpose_class",
+              "loss_weight_mode_class", "loss_weight_purpose_mse", "loss_weight_mode_mse", "kl_weight"):
+        out["cfg_" + k] = np.float64(getattr(cfg, k))
+    np.savez_compressed(HERE / "latent_loss_fixture.npz", **out)
+    print("latent loss fixture written", {k: float(v) for k, v in out.items() if k.startswith("loss_")})
+
+
 def rhs_fixture():
     from ananke_abm.models.mode_sep.config import ModeSepConfig
     from ananke_abm.models.mode_sep.architecture.model import ModeSepModel
@@ -271,6 +305,9 @@ def loss_terms_fixture():
 
 if __name__ == "__main__":
     assert REF.exists(), "the reference tree is only present in the authoring container"
+    if len(sys.argv) > 1 and sys.argv[1] == "latent_loss":  # only the latent composite loss (reads the frozen latent fixture)
+        latent_loss_fixture()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "losses":       # only the loss terms (reads the frozen mode_sep fixture)
         loss_terms_fixture()
         sys.exit(0)
@@ -278,3 +315,4 @@ if __name__ == "__main__":
     latent_fixture()
     rhs_fixture()
     loss_terms_fixture()
+    latent_loss_fixture()

@@ -153,3 +153,30 @@ def test_stale_reference_test_ragged_segments(golden_mode_sep):             # te
         assert batch["is_gt_grid"][seg["i0"]] and batch["is_gt_grid"][seg["i1"]]
         assert seg["i0"] < seg["i1"]
     assert [s["b"] for s in batch["segments_batch"]] == [0, 0, 1, 1]
+
+
+def test_latent_composite_loss_matches_the_unmodified_reference():
+    """`calculate_composite_loss` (latent_ode/architecture/loss.py:7-100) on the frozen model outputs of the latent fixture: the
+    nine returned values and the gradients w.r.t. every model output and the zone encoder equal the vectors the UNMODIFIED
+    reference function produced (tests/golden/make_golden.py latent_loss_fixture)."""
+    from pathlib import Path
+    from ananke_abm_b200 import latent_ode as lo
+    GOLDEN = Path(__file__).resolve().parent / "golden"
+    g = np.load(GOLDEN / "latent_ode_fixture.npz", allow_pickle=False)
+    gl = np.load(GOLDEN / "latent_loss_fixture.npz", allow_pickle=False)
+    cfg = lo.GenerativeODEConfig()
+    model = lo.GenerativeODE(g["batch_person_features"].shape[-1], g["batch_all_zone_features"].shape[-1], cfg)
+    model.load_state_dict({k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd_")})
+    names = ["loc_logits", "loc_embed", "purp_logits", "mode_logits", "purp_feat", "mode_feat", "h0_mu", "h0_log_var"]
+    outs = [torch.from_numpy(g[n]).clone().requires_grad_(True) for n in names]
+    batch = {k[6:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("batch_") and g[k].dtype.kind in "fiub" and g[k].ndim > 0}
+    vals = lo.calculate_composite_loss(batch, tuple(outs), model, torch.from_numpy(gl["distance_matrix"]), cfg)
+    labels = ["total", "classification", "embedding", "distance", "purpose_class", "purpose_mse", "mode_class", "mode_mse", "kl"]
+    for n, v in zip(labels, vals):
+        assert abs(float(v) - float(gl["loss_" + n])) <= 1e-6 * max(1.0, abs(float(gl["loss_" + n]))), n
+    vals[0].backward()
+    for n, o in zip(names, outs):
+        ref = torch.from_numpy(gl["grad_" + n])
+        got = o.grad if o.grad is not None else torch.zeros_like(ref)
+        assert torch.allclose(got, ref, rtol=1e-5, atol=1e-7), n
+    assert torch.allclose(model.zone_feature_encoder.weight.grad, torch.from_numpy(gl["grad_zone_feature_encoder.weight"]), rtol=1e-5, atol=1e-6)

@@ -181,3 +181,125 @@ def test_fused_losses_match_the_unmodified_reference_on_the_fixture():
         assert abs(float(ce) - float(lt[ce_key])) < 1e-5 * abs(float(lt[ce_key])), (ce_key, float(ce), float(lt[ce_key]))
         assert abs(float(ed) - float(lt[d_key])) < 2e-5 * abs(float(lt[d_key])), (d_key, float(ed), float(lt[d_key]))
         assert abs(float(ab.ce_at_snaps_fused(pred_emb, table, y, mask, 0.2)) - float(lt[ce_key])) < 1e-5 * abs(float(lt[ce_key]))
+
+
+# ---- embedding-space terms (mse, travel margin / monotonicity, velocity regularisers) and the whole objective ---------------------
+def _ref_emb_terms(pred, v, table, y_union, is_gt, y_stay, m_stay, travel, prev, dest, m_move, m_travel=0.10, eps=0.01, vmin=0.2, vmax=1.0):
+    """the reference's own expressions (mode_sep/architecture/losses.py:24-31, 46-115; mode_sep/train/train.py:137-153)"""
+    z = pred.new_zeros(())
+
+    def mse(y, mask):
+        return (pred - table[y.clamp(min=0)]).pow(2).sum(-1)[mask].mean() if mask.any() else z
+
+    def d2c(idx):
+        return (pred - table[idx.clamp_min(0)]).pow(2).sum(-1).sqrt()
+    out = {"mse": mse(y_union, is_gt), "stay_mse": mse(y_stay, m_stay), "travel_margin": z, "travel_mono": z}
+    if travel.any():
+        dp, dd = d2c(prev), d2c(dest)
+        out["travel_margin"] = (m_travel - (dp - dd))[travel].clamp(min=0.0).mean()
+        pair = travel[:, :-1] & travel[:, 1:] & (prev[:, :-1] == prev[:, 1:]) & (dest[:, :-1] == dest[:, 1:])
+        if pair.any():
+            away = (dp[:, :-1][pair] - dp[:, 1:][pair] + eps).clamp(min=0.0)
+            toward = (dd[:, 1:][pair] - dd[:, :-1][pair] + eps).clamp(min=0.0)
+            out["travel_mono"] = (away.mean() + toward.mean()) * 0.5
+    v_abs = v.norm(dim=-1)
+    out["stay_vel"] = (v_abs[m_stay] ** 2).mean() if m_stay.any() else z
+    if m_move.any():
+        vm = v_abs[m_move]
+        out["move_vel"] = ((vmin - vm).clamp(min=0.0) ** 2 + (vm - vmax).clamp(min=0.0) ** 2).mean()
+    else:
+        out["move_vel"] = z
+    return out
+
+
+def _random_union(B, T, Z, g, dev):
+    """random stay / travel structure per agent with the UnionBatch field semantics (batching.py:15-28)"""
+    is_gt = torch.zeros(B, T, dtype=torch.bool)
+    stay = torch.zeros(B, T, dtype=torch.bool)
+    travel = torch.zeros(B, T, dtype=torch.bool)
+    y_union = torch.full((B, T), -1, dtype=torch.long)
+    y_stay = torch.full((B, T), -1, dtype=torch.long)
+    prev = torch.full((B, T), -1, dtype=torch.long)
+    dest = torch.full((B, T), -1, dtype=torch.long)
+    for b in range(B):
+        t, zone = 0, int(torch.randint(0, Z, (1,), generator=g))
+        while t < T:
+            n = int(torch.randint(1, 6, (1,), generator=g))
+            if int(torch.randint(0, 2, (1,), generator=g)):          # a stay: snaps at both ends
+                seg = slice(t, min(T, t + n))
+                stay[b, seg] = True
+                y_stay[b, seg] = zone
+                is_gt[b, t] = True
+                y_union[b, t] = zone
+            else:                                                      # a travel leg to a new zone
+                nz = int(torch.randint(0, Z, (1,), generator=g))
+                seg = slice(t, min(T, t + n))
+                travel[b, seg] = True
+                prev[b, seg], dest[b, seg] = zone, nz
+                zone = nz
+            t += n
+    stay_non_gt = stay & ~is_gt
+    gt_idx = is_gt.clone()
+    first = is_gt.float().cumsum(1) == 1
+    last = is_gt.flip(1).float().cumsum(1).flip(1) == 1
+    gt_interior = is_gt & ~(first & is_gt) & ~(last & is_gt)
+    del gt_idx
+    return [x.to(dev) for x in (y_union, is_gt, y_stay, stay_non_gt, travel, prev, dest, gt_interior)]
+
+
+@pytest.mark.parametrize("B,T,Z", [(1, 1, 8), (3, 7, 8), (130, 29, 500), (257, 97, 10_000)])
+def test_emb_loss_terms_match_the_reference_expressions(B, T, Z):
+    import ananke_abm_b200 as ab
+    dev = _cuda()
+    g = torch.Generator().manual_seed(B * 1000 + T)
+    table = (0.3 * torch.randn(Z, 64, generator=g)).to(dev).requires_grad_(True)
+    y_path = (0.3 * torch.randn(T, B, 160, generator=g)).to(dev).requires_grad_(True)      # the solver's layout: v_t is a strided view
+    yb = y_path.permute(1, 0, 2)
+    v_t = yb[:, :, 64:128]
+    pred = (yb[:, :, :64] * 1.0 + 0.1).contiguous()
+    pred.retain_grad()
+    fields = _random_union(B, T, Z, g, dev)
+    terms = ab.emb_loss_terms(pred, v_t, table, *fields)
+    w = {"mse": 0.7, "stay_mse": 1.3, "travel_margin": 2.1, "travel_mono": 0.9, "stay_vel": 5.0, "move_vel": 1.1}
+    sum(w[k] * terms[k] for k in w).backward()
+    p2, v2, t2 = pred.detach().double().requires_grad_(True), v_t.detach().double().requires_grad_(True), table.detach().double().requires_grad_(True)
+    ref = _ref_emb_terms(p2, v2, t2, *fields)
+    sum(w[k] * ref[k] for k in w).backward()
+    for k in w:
+        assert abs(float(terms[k]) - float(ref[k])) <= 2e-6 * max(abs(float(ref[k])), 1e-3), (k, float(terms[k]), float(ref[k]))
+
+    def rel(a, b):
+        return float((a.double() - b).abs().max() / b.abs().max().clamp_min(1e-12))
+    assert rel(pred.grad, p2.grad) < 1e-5
+    assert rel(y_path.grad.permute(1, 0, 2)[:, :, 64:128], v2.grad) < 1e-5
+    assert rel(table.grad, t2.grad) < 2e-5
+
+
+def test_mode_sep_full_objective_fused_matches_the_unmodified_reference(golden_mode_sep):
+    """The COMPLETE training objective of mode_sep/train/train.py:111-159 through `mode_sep_total_loss` (fused head for cross
+    entropy / expected distance, fused pass for every embedding-space term, no [B, T, Z] logits): the loss and EVERY parameter
+    gradient equal the vectors minted from the unmodified reference's training step (tests/golden/make_golden.py)."""
+    from types import SimpleNamespace
+    import ananke_abm_b200 as ab
+    dev = _cuda()
+    g = golden_mode_sep
+    cfg = ab.ModeSepConfig()
+    m = ab.ModeSepModel(8, cfg)
+    m.load_state_dict({k[3:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd_")}, strict=True)
+    m = m.to(dev)
+    tt = lambda k: torch.from_numpy(g[k]).to(dev)   # noqa: E731
+    union = SimpleNamespace(**{f: tt("ub_" + f) for f in ("is_gt_union", "stay_loc_ids", "stay_non_gt_mask", "travel_mask",
+                                                          "prev_zone_idx", "dest_zone_idx", "gt_interior_mask")})
+    y0 = m.initial_state(tt("home_idx"), tt("work_idx"), tt("traits"))
+    y_path = m.integrate(y0, tt("times_union"))
+    yb = y_path.permute(1, 0, 2)
+    pred_emb = m.decoder(yb[:, :, :64])
+    total, parts = ab.mode_sep_total_loss(cfg, pred_emb, yb[:, :, 64:128], m.class_table, union, tt("y_union"), tt("dist_mat"))
+    assert abs(float(total) - float(g["loss_total"])) < 2e-5 * abs(float(g["loss_total"]))
+    assert abs(float(parts["base"]) - float(g["loss_base"])) < 2e-5 * abs(float(g["loss_base"]))
+    total.backward()
+    for name, p in m.named_parameters():
+        ref = torch.from_numpy(g["grad_" + name])
+        got = p.grad.cpu() if p.grad is not None else torch.zeros_like(ref)
+        scale = ref.abs().max().clamp_min(1e-12)
+        assert float((got - ref).abs().max() / scale) < 1e-4, (name, float((got - ref).abs().max() / scale))
