@@ -379,8 +379,8 @@ def run_ours(args):
             kern_flop_unit = 2 * ALG_FLOP_EVAL        # recompute + dgrad of one stage (wgrad runs in wgrad_tc_kernel)
             kern_bytes_unit = ALG_BYTES_FWDBWD / 4.0
             # DRAM bytes per agent-stage of this kernel from `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum =
-            # 1.300 + 2.730 GB for a fused 4-stage launch over 189,440 agents; profiles/r01_fused_step_ncu_summary.txt)
-            kern_traffic_unit = (1.299641e9 + 2.729880e9) / (189440 * 4)
+            # 5.746 + 7.312 GB for the fused 6-stage launch over 333,440 agents; profiles/r02_stage_kernels_ncu_summary.txt)
+            kern_traffic_unit = (5.745611e9 + 7.312489e9) / (333440 * 6)
             del eng, yb, A, Gb, GX
         else:
             prec = {"f32": 0, "bf16": 1}[args.precision]
@@ -447,8 +447,11 @@ def run_ours(args):
         "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": pk["tf_burst"], "unit": "TFLOP/s",
                      "frac": achieved_tf / pk["tf_burst"],
                      "traffic": (kern_traffic_unit * kern_units if kern_traffic_unit else None),
-                     "traffic_note": "DRAM bytes per launch scaled from one ncu --set full capture (profiles/r01_fused_step_ncu_summary.txt)"
-                     if kern_traffic_unit else None, "peak_source": pk["src"],
+                     "traffic_note": "DRAM bytes per launch scaled from one ncu --set full capture (profiles/r02_stage_kernels_ncu_summary.txt)"
+                     if kern_traffic_unit else None,
+                     "dram_achieved_gbs": (kern_traffic_unit * kern_units / (kern_ms * 1e-3) / 1e9 if kern_traffic_unit else None),
+                     "dram_frac_of_hbm_peak": (kern_traffic_unit * kern_units / (kern_ms * 1e-3) / 1e9 / pk["hbm"] if kern_traffic_unit else None),
+                     "peak_source": pk["src"],
                      "kernel": kern_name, "kernel_ms": kern_ms, "units_per_launch": kern_units,
                      "alg_flop_per_unit": kern_flop_unit, "alg_bytes_per_unit": kern_bytes_unit,
                      "alg_flop_per_agent_step": fl_fb if train else fl_fwd,
