@@ -51,14 +51,16 @@ __device__ __forceinline__ bool pair_ok(const EmbLossArgs& a, int64_t r, int t) 
 }
 
 template <bool BWD>
-__global__ void __launch_bounds__(256) emb_losses_kernel(const __grid_constant__ EmbLossArgs a) {
+__global__ void __launch_bounds__(256, 4) emb_losses_kernel(const __grid_constant__ EmbLossArgs a) {
   const int lane = threadIdx.x & 31, sub = lane % EL_LANES, which = lane / EL_LANES;
   const uint32_t rmask = 0xFFFFu << (which * EL_LANES);
   const int64_t n_rows = a.B * (int64_t)a.T;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  double s_loc[N_SUMS];
+  // per-thread partial sums in fp32 (a thread sees a few hundred rows at most; the cross-thread reduction is in double): the kernel
+  // is latency-bound on its gathers, so registers are occupancy (64 per thread = 32 warps per SM)
+  float s_loc[N_SUMS];
 #pragma unroll
-  for (int i = 0; i < N_SUMS; ++i) s_loc[i] = 0.0;
+  for (int i = 0; i < N_SUMS; ++i) s_loc[i] = 0.0f;
   float c_mse_gt = 0.f, c_mse_stay = 0.f, c_margin = 0.f, c_mono = 0.f, c_stayvel = 0.f, c_movevel = 0.f;
   if (BWD) {
     c_mse_gt = a.coef[0]; c_mse_stay = a.coef[1]; c_margin = a.coef[2]; c_mono = a.coef[3]; c_stayvel = a.coef[4]; c_movevel = a.coef[5];
@@ -80,8 +82,8 @@ __global__ void __launch_bounds__(256) emb_losses_kernel(const __grid_constant__
       const int64_t y = clamp_idx(gt ? a.y_gt[r] : a.y_stay[r], a.Z);
       const float4 d = sub4(e, ld4(a.table + y * EL_E + 4 * sub));
       const float d2 = row_sum(dot4(d, d), rmask);
-      if (gt) { s_loc[SUM_MSE_GT] += d2; s_loc[N_GT] += 1.0; }
-      else { s_loc[SUM_MSE_STAY] += d2; s_loc[N_STAY] += 1.0; }
+      if (gt) { s_loc[SUM_MSE_GT] += d2; s_loc[N_GT] += 1.0f; }
+      else { s_loc[SUM_MSE_STAY] += d2; s_loc[N_STAY] += 1.0f; }
       if (BWD) {
         const float c = 2.0f * (gt ? c_mse_gt : c_mse_stay);
         axpy4(ge, c, d);
@@ -91,7 +93,7 @@ __global__ void __launch_bounds__(256) emb_losses_kernel(const __grid_constant__
       if (gt && stay) {      // cannot happen with the reference's masks (stay_non_gt excludes snaps); kept exact anyway
         const int64_t y2 = clamp_idx(a.y_stay[r], a.Z);
         const float4 d_ = sub4(e, ld4(a.table + y2 * EL_E + 4 * sub));
-        s_loc[SUM_MSE_STAY] += row_sum(dot4(d_, d_), rmask); s_loc[N_STAY] += 1.0;
+        s_loc[SUM_MSE_STAY] += row_sum(dot4(d_, d_), rmask); s_loc[N_STAY] += 1.0f;
         if (BWD) {
           axpy4(ge, 2.0f * c_mse_stay, d_);
           float* q = a.d_table + y2 * EL_E + 4 * sub;
@@ -108,7 +110,7 @@ __global__ void __launch_bounds__(256) emb_losses_kernel(const __grid_constant__
       const float4 dp4 = sub4(e, tp), dd4 = sub4(e, td);
       const float dp = sqrtf(row_sum(dot4(dp4, dp4), rmask)), dd = sqrtf(row_sum(dot4(dd4, dd4), rmask));
       const float hinge = a.m_margin - (dp - dd);
-      s_loc[N_TRAVEL] += 1.0;
+      s_loc[N_TRAVEL] += 1.0f;
       if (hinge > 0.f) s_loc[SUM_MARGIN] += hinge;
       float g_dp = 0.f, g_dd = 0.f;                       // d total / d d_prev(t), d d_dest(t)
       if (BWD && hinge > 0.f) { g_dp -= c_margin; g_dd += c_margin; }
@@ -118,7 +120,7 @@ __global__ void __launch_bounds__(256) emb_losses_kernel(const __grid_constant__
         const float4 a4 = sub4(en, tp), b4 = sub4(en, td);
         const float dpn = sqrtf(row_sum(dot4(a4, a4), rmask)), ddn = sqrtf(row_sum(dot4(b4, b4), rmask));
         const float away = dp - dpn + a.eps_mono, toward = ddn - dd + a.eps_mono;
-        s_loc[N_PAIR] += 1.0;
+        s_loc[N_PAIR] += 1.0f;
         if (away > 0.f) { s_loc[SUM_AWAY] += away; if (BWD) g_dp += c_mono; }
         if (toward > 0.f) { s_loc[SUM_TOWARD] += toward; if (BWD) g_dd -= c_mono; }
       }
@@ -157,7 +159,7 @@ __global__ void __launch_bounds__(256) emb_losses_kernel(const __grid_constant__
         const float vm = sqrtf(v2);
         const float lo = fmaxf(a.v_min - vm, 0.f), hi = fmaxf(vm - a.v_max, 0.f);
         s_loc[SUM_MOVEVEL] += lo * lo + hi * hi;
-        s_loc[N_MOVE] += 1.0;
+        s_loc[N_MOVE] += 1.0f;
         if (BWD && vm > 0.f) axpy4(gv, c_movevel * 2.0f * (hi - lo) / vm, vv);
       }
     }
@@ -172,7 +174,7 @@ __global__ void __launch_bounds__(256) emb_losses_kernel(const __grid_constant__
     __shared__ double red[8][N_SUMS];
 #pragma unroll
     for (int i = 0; i < N_SUMS; ++i) {
-      double x = sub == 0 ? s_loc[i] : 0.0;
+      double x = sub == 0 ? (double)s_loc[i] : 0.0;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
       if (lane == 0) red[threadIdx.x >> 5][i] = x;

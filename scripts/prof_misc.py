@@ -45,5 +45,24 @@ for it in range(int(sys.argv[2]) if len(sys.argv) > 2 else 2):
     y0 = model.initial_state(table, zemb, home, work, traits)
     yp = model.integrate(y0, torch.tensor([0.0, 0.25, 0.5], device=dev))
     yp[:, :, :128].square().mean().backward()
+    # 5. the fused embedding-space loss terms (forward + backward) on a [B, 16, 64] slab with random stay / travel structure
+    T2 = 16
+    emb = (0.3 * torch.randn(B, T2, 64, device=dev)).requires_grad_(True)
+    vel = (0.3 * torch.randn(B, T2, 64, device=dev)).requires_grad_(True)
+    tab = table.detach().clone().requires_grad_(True)
+    r = torch.rand(B, T2, device=dev)
+    is_gt, stay, trav = r < 0.12, (r >= 0.12) & (r < 0.6), r >= 0.6
+    zid = torch.randint(0, Z, (B, T2), device=dev)
+    y_gt = torch.where(is_gt, zid, torch.full_like(zid, -1))
+    y_st = torch.where(stay, zid, torch.full_like(zid, -1))
+    prev = torch.where(trav, zid, torch.full_like(zid, -1))
+    dest = torch.where(trav, (zid * 7 + 3) % Z, torch.full_like(zid, -1))
+    terms = ab.emb_loss_terms(emb, vel, tab, y_gt, is_gt, y_st, stay, trav, prev, dest, is_gt)
+    sum(terms.values()).backward()
+    # 6. strict-fp32 drift evaluation and its vector-Jacobian product (FFMA kernels behind autograd-through-dopri5 / the adjoint)
+    spec = ab.describe_drift(model.odefunc)
+    yv = torch.randn(min(B, 65_536), 160, device=dev)
+    fv = oi.drift_eval(spec, spec.flat_params().detach(), 3.0, yv)
+    gyv, gwv = oi.drift_vjp(spec, spec.flat_params().detach(), 3.0, yv, fv)
     torch.cuda.synchronize()
 print("ok", int(labels.sum()) >= 0)
