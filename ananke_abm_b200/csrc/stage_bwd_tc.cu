@@ -41,6 +41,7 @@ struct BwdStageParams {       // one stage of a fused (latest-first) sequence
   float dp[MAX_A], dv[MAX_A]; // and coefficients (that stage's in.cpa / in.cva entry for a_out)
   float* gx_out;              // blocked [Bp][160]: [g_p, g_v, g_h] of this stage (written)
   int blob0;                  // blob index of tile 0 for this stage
+  const uint8_t* x1_in;       // X blobs of this stage written by the forward launch ([ntiles][X1_BYTES]) or null: rebuild from y0 / a_j
 };
 
 struct StageBwdArgs {
@@ -152,6 +153,30 @@ __global__ void __launch_bounds__(THREADS, 1) stage_bwd_tc_kernel(const __grid_c
     STAGE_TRACE(c, 9);
 
     // ---- stage input -> ACT / HB / TB and the X blob (features: p 0..63, v 64..127, h 128..159, sin, cos, 1)
+    if (sp.x1_in != nullptr) {
+      // The forward launch of this step already wrote the stage input as the bf16 X blob (the very operand image the recompute
+      // and the weight-gradient kernel need): 10 independent 16-byte loads per thread instead of y0 plus up to six a_j
+      // (1.5 KB -> 0.35 KB per agent-stage), and nothing to spill.
+      const uint8_t* xin = sp.x1_in + (size_t)tile * wg::X1_BYTES + (size_t)c.row * 16;
+      uint4 pg[4], vg[4], hg[2];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        pg[q] = __ldg(reinterpret_cast<const uint4*>(xin + (size_t)(c.hf * 4 + q) * wg::FG_BYTES));
+        vg[q] = __ldg(reinterpret_cast<const uint4*>(xin + (size_t)(P / 8 + c.hf * 4 + q) * wg::FG_BYTES));
+      }
+#pragma unroll
+      for (int q = 0; q < 2; ++q) hg[q] = __ldg(reinterpret_cast<const uint4*>(xin + (size_t)(2 * P / 8 + c.hf * 2 + q) * wg::FG_BYTES));
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        const uint32_t op[8] = {pg[2 * ch].x, pg[2 * ch].y, pg[2 * ch].z, pg[2 * ch].w, pg[2 * ch + 1].x, pg[2 * ch + 1].y, pg[2 * ch + 1].z, pg[2 * ch + 1].w};
+        const uint32_t ov[8] = {vg[2 * ch].x, vg[2 * ch].y, vg[2 * ch].z, vg[2 * ch].w, vg[2 * ch + 1].x, vg[2 * ch + 1].y, vg[2 * ch + 1].z, vg[2 * ch + 1].w};
+        tmem_st8(c.tmem + c.lane_sel + C_ACT + (uint32_t)((c.hf * 8 + ch * 4) * 2), op);
+        tmem_st8(c.tmem + c.lane_sel + C_ACT + (uint32_t)(P / 2 + (c.hf * 8 + ch * 4) * 2), ov);
+      }
+      const uint32_t oh[8] = {hg[0].x, hg[0].y, hg[0].z, hg[0].w, hg[1].x, hg[1].y, hg[1].z, hg[1].w};
+      tmem_st8(c.tmem + c.lane_sel + C_HB + (uint32_t)(c.hf * 8), oh);
+      write_time_block(c, sp.t, a.period);
+    } else {
     uint8_t* xb = blob_at(S.x1(blob));
     {   // both 16-dim halves together: one batch of independent 128-bit loads per source (n_a + 1 round trips, not 2x that)
       const int f0 = c.hf * 8;
@@ -208,6 +233,7 @@ __global__ void __launch_bounds__(THREADS, 1) stage_bwd_tc_kernel(const __grid_c
       time_features(sp.t, a.period, s, co);
       const uint32_t o[8] = {pack_bf16(s, co), pack_bf16(1.0f, 0.0f), 0u, 0u, 0u, 0u, 0u, 0u};
       spill_groups<2>(xb, (2 * P + H) / 8, c.row, o);
+    }
     }
 
     STAGE_TRACE(c, 10);
@@ -348,7 +374,7 @@ static_assert(sizeof(StageBwdHost) == sizeof(ab200_stage_desc), "stage descripto
 int stage_bwd_tc_multi(const ab200_drift_desc* d, const uint8_t* image, const float* y0, const float* const* a_ptrs,
                        const void* descs_v, int n_stage, const float* const* g_base, float* const* gx_out, const int32_t* n_g,
                        const int32_t* gx_src, const float* const* gx_ext, const float* dp, const float* dv, int64_t B, void* spill,
-                       int blob0, int nblobs, float* g_bout, cudaStream_t st) {
+                       int blob0, int nblobs, float* g_bout, const void* const* x1_in, cudaStream_t st) {
   const StageBwdHost* hs = reinterpret_cast<const StageBwdHost*>(descs_v);
   if (n_stage < 1 || n_stage > MAX_A) return AB200_ERR_BAD_ARG;
   StageBwdArgs k{};
@@ -377,6 +403,7 @@ int stage_bwd_tc_multi(const ab200_drift_desc* d, const uint8_t* image, const fl
     }
     sp.gx_out = gx_out[s];
     sp.blob0 = blob0 + s * k.ntiles;
+    sp.x1_in = x1_in ? (const uint8_t*)x1_in[s] : nullptr;
   }
   if (blob0 < 0 || blob0 + n_stage * k.ntiles > nblobs) return AB200_ERR_BAD_ARG;
   for (int i = 0; i < MAX_A; ++i) k.a[i] = (i < max_a) ? a_ptrs[i] : nullptr;
@@ -408,7 +435,7 @@ int stage_bwd_tc(const ab200_drift_desc* d, const uint8_t* image, const float* y
   int32_t src[MAX_A];
   float dpa[MAX_A], dva[MAX_A];
   for (int l = 0; l < MAX_A; ++l) { src[l] = -1 - l; dpa[l] = l < n_g ? dp[l] : 0.f; dva[l] = l < n_g ? dv[l] : 0.f; }
-  return stage_bwd_tc_multi(d, image, y0, a_ptrs, desc_v, 1, gb, go, ng, src, gx_ptrs, dpa, dva, B, spill, blob0, nblobs, g_bout, st);
+  return stage_bwd_tc_multi(d, image, y0, a_ptrs, desc_v, 1, gb, go, ng, src, gx_ptrs, dpa, dva, B, spill, blob0, nblobs, g_bout, nullptr, st);
 }
 
 }  // namespace ab200

@@ -18,6 +18,7 @@
 // The context h (constant along a trajectory: dh/dt = 0) enters layer 1 as a hi and a lo fp16 tile from shared memory.
 #include <cuda_fp16.h>
 #include "stage_tc.cuh"
+#include "wgrad_layout.cuh"
 
 namespace ab200 {
 using namespace stc;
@@ -187,6 +188,7 @@ struct Stage2Params {         // one stage of a fused sequence (same meaning as 
   Combo out;
   Combo err;
   int want_err;
+  uint8_t* x1_out;            // or null: this stage's input as the bf16 X blob of the backward pass ([ntiles][X1_BYTES], wgrad_layout.cuh)
 };
 
 struct StageFwd2Args {
@@ -264,6 +266,34 @@ __global__ void __launch_bounds__(THREADS, 1) stage_fwd2_tc_kernel(const __grid_
           for (int j = 0; j < 8; ++j) {
             pin[4 * j] += cp * x[j].x; pin[4 * j + 1] += cp * x[j].y; pin[4 * j + 2] += cp * x[j].z; pin[4 * j + 3] += cp * x[j].w;
             vin[4 * j] += cv * x[j].x; vin[4 * j + 1] += cv * x[j].y; vin[4 * j + 2] += cv * x[j].z; vin[4 * j + 3] += cv * x[j].w;
+          }
+        }
+        if (sp.x1_out != nullptr) {
+          // The backward pass needs exactly this stage input as a bf16 operand image (recompute A operand, weight-gradient B
+          // operand): written here it costs 352 B per agent-stage of a launch that uses 12 % of the DRAM bandwidth, and saves the
+          // backward kernel -- which is bound by its HBM traffic -- re-reading y0 and up to six a_j (1.5 KB) and spilling the blob.
+          uint8_t* xb = sp.x1_out + (size_t)tile * wg::X1_BYTES + (size_t)c.row * 16;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {      // feature groups of 8: p groups 4 hf + q, v groups 8 + 4 hf + q
+            const uint4 gp = make_uint4(pack_bf16(pin[8 * q], pin[8 * q + 1]), pack_bf16(pin[8 * q + 2], pin[8 * q + 3]),
+                                        pack_bf16(pin[8 * q + 4], pin[8 * q + 5]), pack_bf16(pin[8 * q + 6], pin[8 * q + 7]));
+            const uint4 gv = make_uint4(pack_bf16(vin[8 * q], vin[8 * q + 1]), pack_bf16(vin[8 * q + 2], vin[8 * q + 3]),
+                                        pack_bf16(vin[8 * q + 4], vin[8 * q + 5]), pack_bf16(vin[8 * q + 6], vin[8 * q + 7]));
+            __stcs(reinterpret_cast<uint4*>(xb + (size_t)(c.hf * 4 + q) * wg::FG_BYTES), gp);
+            __stcs(reinterpret_cast<uint4*>(xb + (size_t)(P / 8 + c.hf * 4 + q) * wg::FG_BYTES), gv);
+          }
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {      // h groups 16 + 2 hf + q (16 context dims per thread)
+            const float4 x0 = ldro(blk4(a.y0, tile, YF4, 2 * AF4 + c.hf * 4 + 2 * q, c.row));
+            const float4 x1 = ldro(blk4(a.y0, tile, YF4, 2 * AF4 + c.hf * 4 + 2 * q + 1, c.row));
+            __stcs(reinterpret_cast<uint4*>(xb + (size_t)(2 * P / 8 + c.hf * 2 + q) * wg::FG_BYTES),
+                   make_uint4(pack_bf16(x0.x, x0.y), pack_bf16(x0.z, x0.w), pack_bf16(x1.x, x1.y), pack_bf16(x1.z, x1.w)));
+          }
+          if (c.hf == 0) {                   // groups 20, 21: [sin, cos, 1, 0 ...], zeros
+            float sn, co;
+            time_features(sp.t, a.period, sn, co);
+            __stcs(reinterpret_cast<uint4*>(xb + (size_t)((2 * P + H) / 8) * wg::FG_BYTES), make_uint4(pack_bf16(sn, co), pack_bf16(1.0f, 0.0f), 0u, 0u));
+            __stcs(reinterpret_cast<uint4*>(xb + (size_t)((2 * P + H) / 8 + 1) * wg::FG_BYTES), make_uint4(0u, 0u, 0u, 0u));
           }
         }
         // p features 32 hf .. -> columns 32 hf .. ; v features 64 + 32 hf .. -> columns 64 + 32 hf ..
@@ -415,7 +445,7 @@ struct StageFwd2Host {   // mirrors ab200_stage_desc in the public header
 static_assert(sizeof(StageFwd2Host) == sizeof(ab200_stage_desc), "stage descriptor layout");
 
 int stage_fwd2_tc_multi(const ab200_drift_desc* d, const uint8_t* image, const float* y0, const float* const* a_ptrs, const void* descs_v,
-                        int n_stage, float* const* a_outs, int64_t B, float* y_out, double* err_sumsq, cudaStream_t st) {
+                        int n_stage, float* const* a_outs, int64_t B, float* y_out, double* err_sumsq, void* const* x1_outs, cudaStream_t st) {
   const StageFwd2Host* hs = reinterpret_cast<const StageFwd2Host*>(descs_v);
   if (n_stage < 1 || n_stage > MAX_A) return AB200_ERR_BAD_ARG;
   StageFwd2Args k{};
@@ -440,6 +470,7 @@ int stage_fwd2_tc_multi(const ab200_drift_desc* d, const uint8_t* image, const f
     sp.a_out = a_outs ? a_outs[s] : nullptr;
     sp.y_out = (s == n_stage - 1) ? y_out : nullptr;
     sp.want_err = (s == n_stage - 1 && err_sumsq != nullptr) ? 1 : 0;
+    sp.x1_out = x1_outs ? (uint8_t*)x1_outs[s] : nullptr;
   }
   for (int i = 0; i < MAX_A; ++i) k.a[i] = (i < max_a) ? a_ptrs[i] : nullptr;
   k.n_stage = n_stage;

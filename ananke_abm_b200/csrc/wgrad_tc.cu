@@ -33,6 +33,10 @@ struct WgradArgs {
   int nblobs;          // capacity of the spill buffer (layout stride)
   int used;            // blobs actually filled
   int* status;
+  // X blobs (pair 0's B operand) written by the FORWARD launch of the step instead of the backward kernel: one base pointer per ring
+  // position (= blob / ntiles, the stage's place in the backward launch), tile-indexed; null = the spill buffer's own x1 region
+  const uint8_t* x1_ext[8];
+  int ntiles;
 };
 
 struct PairDesc { size_t a_off, b_off; uint32_t a_bytes, b_bytes; int N; bool bias; int part_off, part_ld; };
@@ -94,7 +98,12 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
             uint8_t* dst = smem + slot * WG_SLOT;
             mbar_arrive_expect_tx(&full[slot], d.a_bytes + d.b_bytes);
             bulk_g2s(dst, a.spill + d.a_off, d.a_bytes, &full[slot]);
-            bulk_g2s(dst + HID_BYTES, a.spill + d.b_off, d.b_bytes, &full[slot]);
+            const uint8_t* bsrc = a.spill + d.b_off;
+            if (pair == 0 && a.ntiles > 0) {
+              const int pos = b / a.ntiles;
+              if (pos < 8 && a.x1_ext[pos] != nullptr) bsrc = a.x1_ext[pos] + (size_t)(b - pos * a.ntiles) * X1_BYTES;
+            }
+            bulk_g2s(dst + HID_BYTES, bsrc, d.b_bytes, &full[slot]);
           }
         }
       }
@@ -225,10 +234,15 @@ int wgrad_num_ctas() {
 size_t wgrad_partial_bytes() { return ((size_t)wgrad_num_ctas() * PART_TOTAL + 64) * sizeof(float) + 256; }
 
 // partial buffer: [ncta][PART_TOTAL] floats, then g_bout[64], then a status word
-int wgrad_tc(const void* spill, int nblobs, int used, void* partial, cudaStream_t st) {
+int wgrad_tc(const void* spill, int nblobs, int used, void* partial, const void* const* x1_ext, int n_x1, int ntiles, cudaStream_t st) {
   if (used <= 0) return AB200_OK;
   const int ncta = wgrad_num_ctas();
-  WgradArgs k{(const uint8_t*)spill, (float*)partial, nblobs, used, reinterpret_cast<int*>((float*)partial + (size_t)ncta * PART_TOTAL + 64)};
+  WgradArgs k{(const uint8_t*)spill, (float*)partial, nblobs, used, reinterpret_cast<int*>((float*)partial + (size_t)ncta * PART_TOTAL + 64), {}, 0};
+  if (x1_ext != nullptr && n_x1 > 0 && ntiles > 0) {
+    if (n_x1 > 8) return AB200_ERR_BAD_ARG;
+    for (int i = 0; i < n_x1; ++i) k.x1_ext[i] = (const uint8_t*)x1_ext[i];
+    k.ntiles = ntiles;
+  }
   cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM);
   if (e != cudaSuccess) { set_cuda_error(e); return AB200_ERR_CUDA; }
   wgrad_tc_kernel<<<ncta, WG_THREADS, WG_SMEM, st>>>(k);

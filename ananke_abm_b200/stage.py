@@ -228,13 +228,18 @@ class TcEngine:
                                               C.cast(cpa, C.c_void_p), C.cast(cva, C.c_void_p), B, out_rowmajor.data_ptr(), _stream())
         _lib.check(rc, "ab200_pv_combine_rowmajor")
 
-    def dopri5_attempt(self, y0, A: Sequence[torch.Tensor], t0: float, dt: float, B: int, y_out, err_sumsq, rtol: float, atol: float) -> None:
-        """one attempted Dormand-Prince step in ONE call: stages 2..7 fused, descriptors built in C (ab200_dopri5_attempt)"""
+    def dopri5_attempt(self, y0, A: Sequence[torch.Tensor], t0: float, dt: float, B: int, y_out, err_sumsq, rtol: float, atol: float,
+                       x_blobs=None) -> None:
+        """one attempted Dormand-Prince step in ONE call: stages 2..7 fused, descriptors built in C (ab200_dopri5_attempt);
+        `x_blobs` (6 * xblob_bytes(B) bytes, split-activation format only) receives the stage inputs as backward operand images"""
         ptrs = (C.c_void_p * 7)(*[t.data_ptr() for t in A[:7]])
         rc = self.L.ab200_dopri5_attempt(C.byref(self.desc), self.image.data_ptr(), y0.data_ptr(), C.cast(ptrs, C.c_void_p), float(t0),
                                          float(dt), B, y_out.data_ptr(), err_sumsq.data_ptr(), float(rtol), float(atol), self.fwd_format,
-                                         _stream())
+                                         None if x_blobs is None else x_blobs.data_ptr(), _stream())
         _lib.check(rc, "ab200_dopri5_attempt")
+
+    def xblob_bytes(self, B: int) -> int:
+        return int(self.L.ab200_stage_xblob_bytes(C.byref(self.desc), B))
 
     def dopri5_dense_rows(self, y0, A: Sequence[torch.Tensor], dt: float, xs: Sequence[float], B: int, outs: Sequence[torch.Tensor]) -> None:
         """dense-output rows of an accepted step at relative positions xs, one pass (ab200_dopri5_dense_rows)"""
@@ -272,6 +277,7 @@ class TcEngine:
         npart = self.L.ab200_wgrad_partial_bytes(C.byref(self.desc))
         self.partial = torch.zeros(int(npart), dtype=torch.uint8, device=self.dev)
         self.used = 0
+        self.x_ring = []          # per filled run of ntiles blobs: device pointer of a forward-saved X blob, or None
 
     def combine_backward(self, g, c: Combo, B: int, G_y0, G_a: Sequence[torch.Tensor], accumulate: bool) -> None:
         n = len(G_a)
@@ -303,6 +309,7 @@ class TcEngine:
                                          self.partial.data_ptr(), _stream())
         _lib.check(rc, "ab200_stage_backward")
         self.used += self.ntiles
+        self.x_ring.append(None)
 
     def combine_backward_multi(self, sources: Sequence, B: int, G_y0, G_a: Sequence[torch.Tensor], accumulate: bool) -> None:
         """`sources` = [(g blocked tensor, Combo), ...]: all folded into G_y0 / G_a in passes of up to 4 sources."""
@@ -332,11 +339,14 @@ class TcEngine:
                                          C.cast(dpa, C.c_void_p), C.cast(dva, C.c_void_p), B, out.data_ptr(), _stream())
         _lib.check(rc, "ab200_stage_upstream")
 
-    def stage_backward_fused(self, y0, a_bufs: Sequence[torch.Tensor], stages: Sequence, B: int) -> None:
+    def stage_backward_fused(self, y0, a_bufs: Sequence[torch.Tensor], stages: Sequence, B: int, x_blobs: Optional[Sequence] = None) -> None:
         """The backward stages of one step in ONE launch.  `stages` (latest stage first) =
         [(n_a, Combo in, t, g_base tensor or None, [(src, dp, dv), ...], gx_out tensor)], where `src` is the position of an
-        earlier entry of `stages` whose gx_out feeds this stage's upstream gradient."""
+        earlier entry of `stages` whose gx_out feeds this stage's upstream gradient.  `x_blobs[i]`: device pointer of the
+        forward-saved input blob of entry i (`dopri5_attempt`), or None to rebuild it from (y0, a_j)."""
         n = len(stages)
+        xs = list(x_blobs) if x_blobs is not None else [None] * n
+        assert len(xs) == n
         if self.used + n * self.ntiles > self.nblobs:
             self.flush()
         descs = (StageDesc * n)()
@@ -365,9 +375,11 @@ class TcEngine:
                                                C.cast(descs, C.c_void_p), n, C.cast(g_base, C.c_void_p), C.cast(gx_out, C.c_void_p),
                                                C.cast(n_g, C.c_void_p), C.cast(src, C.c_void_p), None, C.cast(dp, C.c_void_p),
                                                C.cast(dv, C.c_void_p), B, self.spill.data_ptr(), self.spill.numel(), self.used,
-                                               self.nblobs, self.partial.data_ptr(), _stream())
+                                               self.nblobs, self.partial.data_ptr(),
+                                               C.cast((C.c_void_p * n)(*xs), C.c_void_p) if any(x is not None for x in xs) else None, _stream())
         _lib.check(rc, "ab200_stage_backward_fused")
         self.used += n * self.ntiles
+        self.x_ring.extend(xs)
 
     def adjoint_gather_upstream(self, base, gx: Sequence[torch.Tensor], cpv: Sequence[float], B: int, out, g_base,
                                 dp: Sequence[float], dv: Sequence[float], g_a_out) -> None:
@@ -390,10 +402,13 @@ class TcEngine:
 
     def flush(self) -> None:
         if self.used:
+            nx = len(self.x_ring) if any(x is not None for x in self.x_ring) else 0
             rc = self.L.ab200_wgrad_accumulate(C.byref(self.desc), self.spill.data_ptr(), self.nblobs, self.used,
-                                               self.partial.data_ptr(), _stream())
+                                               self.partial.data_ptr(),
+                                               C.cast((C.c_void_p * nx)(*self.x_ring), C.c_void_p) if nx else None, nx, self.ntiles, _stream())
             _lib.check(rc, "ab200_wgrad_accumulate")
             self.used = 0
+            self.x_ring = []
 
     def backward_end(self) -> torch.Tensor:
         self.flush()
@@ -489,9 +504,10 @@ def rk4_forward(eng: TcEngine, y0: torch.Tensor, t_host: Sequence[float], save_s
 
 
 def stages_backward(eng: TcEngine, tab: Tableau, B: int, yn, A: Sequence[torch.Tensor], stage_times: Sequence[float], dt: float,
-                    G_a_base: Sequence[Optional[torch.Tensor]], gx: Sequence[torch.Tensor], first: int, last: int):
+                    G_a_base: Sequence[Optional[torch.Tensor]], gx: Sequence[torch.Tensor], first: int, last: int, x_blobs=None):
     """Backward of stages last..first of ONE explicit Runge-Kutta step in a single fused launch (latest stage first).
-    Returns the stage input combinations (their cpv feed `adjoint_gather`)."""
+    Returns the stage input combinations (their cpv feed `adjoint_gather`).  `x_blobs`: the step's forward-saved stage-input
+    blobs (uint8 tensor, stage i >= 1 at offset (i - 1) * xblob_bytes) or None."""
     combos = [tab.stage_input(i, dt) for i in range(last + 1)]
     order = list(range(last, first - 1, -1))
     pos = {i: k for k, i in enumerate(order)}
@@ -499,7 +515,11 @@ def stages_backward(eng: TcEngine, tab: Tableau, B: int, yn, A: Sequence[torch.T
     for i in order:
         later = [l for l in range(i + 1, last + 1) if combos[l].cpa[i] != 0.0 or combos[l].cva[i] != 0.0]
         stages.append((i, combos[i], stage_times[i], G_a_base[i], [(pos[l], combos[l].cpa[i], combos[l].cva[i]) for l in later], gx[i]))
-    eng.stage_backward_fused(yn, list(A), stages, B)
+    xs = None
+    if x_blobs is not None:
+        per = eng.xblob_bytes(B)
+        xs = [x_blobs.data_ptr() + (i - 1) * per if i >= 1 else None for i in order]
+    eng.stage_backward_fused(yn, list(A), stages, B, xs)
     return combos
 
 
@@ -546,6 +566,7 @@ class _Dopri5Step:
     t0: float
     dt: float
     outputs: List                    # [(row index k into y_path, x = (t_k - t0) / dt)]
+    x: Optional[torch.Tensor] = None # inputs of stages 2..7 as bf16 operand images (written by the forward attempt), or None
 
 
 class Dopri5Stats:
@@ -635,6 +656,11 @@ def dopri5_forward(eng: TcEngine, y0: torch.Tensor, t_host: Sequence[float], rto
             pending = None
 
     Bp = padded_rows(B)
+    # A training forward in the split-activation format also keeps every stage INPUT of the accepted steps as the bf16 operand
+    # image of the backward kernels (352 B per agent-stage): the backward pass is bound by its HBM traffic, and loading that
+    # image replaces re-reading y0 and up to six a_j (1.5 KB) and spilling it for the weight-gradient kernel.
+    xb_floats = eng.xblob_bytes(B) * 6 // 4 if (save_steps and eng.fwd_format == 2) else 0
+    x_cur = torch.empty(xb_floats, dtype=torch.float32, device=dev) if xb_floats else None
     while k < T:
         # ---- one attempted step from t1 with size dt
         assert n_steps < max_num_steps, "max_num_steps exceeded ({}>={})".format(n_steps, max_num_steps)
@@ -645,7 +671,7 @@ def dopri5_forward(eng: TcEngine, y0: torch.Tensor, t_host: Sequence[float], rto
         if slot == 0 and n_steps > 0:
             pool.zero_()
         sumsq = pool[slot:slot + 1]
-        eng.dopri5_attempt(y_cur, A, ta, dt, B, y_next, sumsq, rtol, atol)
+        eng.dopri5_attempt(y_cur, A, ta, dt, B, y_next, sumsq, rtol, atol, x_cur)
         stats.n_evals += 6
         flush_rows()
         if use_global:
@@ -664,10 +690,12 @@ def dopri5_forward(eng: TcEngine, y0: torch.Tensor, t_host: Sequence[float], rto
             if save_steps:
                 if outs:
                     pending = (y_cur, A, dt, outs)
-                steps.append(_Dopri5Step(y_cur, A, ta, dt, outs))
-                buf = torch.empty(Bp * (D + 6 * P), dtype=torch.float32, device=dev)     # y_next + a_2..a_7 of the next step
+                steps.append(_Dopri5Step(y_cur, A, ta, dt, outs, x_cur))
+                n_state = Bp * (D + 6 * P)
+                buf = torch.empty(n_state + xb_floats, dtype=torch.float32, device=dev)  # y_next + a_2..a_7 (+ X blobs) of the next step
                 y_cur, y_next = y_next, buf[:Bp * D]
                 A = [A[6]] + [buf[Bp * (D + i * P):Bp * (D + (i + 1) * P)] for i in range(6)]
+                x_cur = buf[n_state:] if xb_floats else None
             else:
                 if outs:       # buffers are recycled by the next attempt: every requested time inside (t, t + dt] now
                     eng.dopri5_dense_rows(y_cur, A, dt, [x for _, x in outs], B, [y_path[kk] for kk, _ in outs])
@@ -722,7 +750,7 @@ def dopri5_backward(eng: TcEngine, steps: List[_Dopri5Step], grad_y_path: torch.
         first = 0 if si == 0 else 1                                # k_1 of a later step belongs to the previous step
         combos = [DOPRI5.stage_input(i, dt) for i in range(7)]
         times = [st.t0 + DOPRI5.c[i] * dt for i in range(7)]
-        stages_backward(eng, DOPRI5, B, st.yb, st.A, times, dt, G_a, gx, first, last)
+        stages_backward(eng, DOPRI5, B, st.yb, st.A, times, dt, G_a, gx, first, last, st.x)
         used = list(range(first, last + 1))
         if first == 1:      # one pass: dL/dy0 of the step and the gradient handed to the previous step's FSAL evaluation
             lam_a = lam_a_buf[si % 2]

@@ -309,3 +309,35 @@ def test_full_chunk_properties_dopri5():
     assert float(gy0.abs().max()) == 0.0 and float(gw0.abs().max()) == 0.0
     assert bool(torch.isfinite(gy1).all()) and bool(torch.isfinite(gw1).all())
     assert _rel(gy2, 4.0 * gy1) < 1e-5 and _rms(gw2, 4.0 * gw1) < 1e-3
+
+
+@pytest.mark.parametrize("B", [129, 1000])
+def test_forward_saved_stage_inputs_equal_rebuilt_ones(B):
+    """The split-activation forward writes every stage input of an accepted step as the bf16 operand image of the backward
+    kernels (ab200_dopri5_attempt `x_blobs`); the backward pass that LOADS those images and the one that REBUILDS them from
+    (y0, a_j) must see the same bf16 numbers: dL/dy0 bit-identical, dL/dW equal up to the order of the atomic partial sums."""
+    import ananke_abm_b200 as ab
+    from ananke_abm_b200 import stage
+    dev = _cuda()
+    _, model = _pair()
+    model = model.to(dev)
+    home, work, traits = _agents(B, 8)
+    y0 = model.initial_state(home.to(dev), work.to(dev), traits.to(dev)).detach()
+    spec = ab.describe_drift(model.odefunc)
+    eng = stage.TcEngine(spec, spec.flat_params().detach())
+    t = [0.0, 1.5, 3.0, 6.0]
+    y_path, steps, _ = stage.dopri5_forward(eng, y0, t, 1e-4, 1e-4, save_steps=True)
+    assert all(s.x is not None for s in steps) and len(steps) >= 2
+    g = torch.randn(y_path.shape, device=dev, generator=torch.Generator(device=dev).manual_seed(5))
+    gy_a, gw_a = stage.dopri5_backward(eng, steps, g)
+    for s in steps:
+        s.x = None
+    gy_b, gw_b = stage.dopri5_backward(eng, steps, g)
+    torch.cuda.synchronize()
+    assert torch.equal(gy_a, gy_b)
+    assert _rel(gw_a, gw_b) < 1e-5, _rel(gw_a, gw_b)
+    # a single-term forward format has no blobs to offer and still trains
+    y_path1, steps1, _ = stage.dopri5_forward(eng, y0, t, 1e-4, 1e-4, save_steps=True, forward_operands="fp16")
+    assert all(s.x is None for s in steps1)
+    gy_c, _ = stage.dopri5_backward(eng, steps1, g)
+    assert torch.isfinite(gy_c).all()
