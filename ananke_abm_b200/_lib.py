@@ -77,19 +77,19 @@ SIGNATURES = {
     "ab200_stage_pack": (C.c_int, [_dp, _vp, _vp, _sz, _vp]),
     "ab200_stage_forward": (C.c_int, [_dp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i32, _vp]),
     "ab200_stage_forward_fused": (C.c_int, [_dp, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _vp, _vp, _i32, _vp]),
-    "ab200_dopri5_attempt": (C.c_int, [_dp, _vp, _vp, _vp, C.c_double, C.c_double, _i64, _vp, _vp, _f32, _f32, _i32, _vp, _vp]),
-    "ab200_stage_xblob_bytes": (_sz, [_dp, _i64]),
+    "ab200_dopri5_attempt": (C.c_int, [_dp, _vp, _vp, _vp, C.c_double, C.c_double, _i64, _vp, _vp, _f32, _f32, _i32, _vp, _i32, _vp]),
+    "ab200_stage_xblob_bytes": (_sz, [_dp, _i64, _i32]),
     "ab200_dopri5_dense_rows": (C.c_int, [_dp, _vp, _vp, C.c_double, _i32, _vp, _i64, _vp, _vp]),
     "ab200_stage_spill_bytes": (_sz, [_dp, _i32]),
     "ab200_wgrad_partial_bytes": (_sz, [_dp]),
     "ab200_stage_backward": (C.c_int, [_dp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _sz, _i32, _i32, _vp, _vp]),
     "ab200_stage_backward_fused": (C.c_int, [_dp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _sz, _i32, _i32,
-                                             _vp, _vp, _vp]),
+                                             _vp, _vp, _i32, _vp]),
     "ab200_adjoint_gather": (C.c_int, [_dp, _vp, _vp, _i32, _vp, _i64, _vp, _vp]),
     "ab200_adjoint_gather_upstream": (C.c_int, [_dp, _vp, _vp, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ab200_pv_combine_backward_multi": (C.c_int, [_dp, _vp, _i32, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _i32, _vp]),
     "ab200_stage_upstream": (C.c_int, [_dp, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _vp]),
-    "ab200_wgrad_accumulate": (C.c_int, [_dp, _vp, _i32, _i32, _vp, _vp, _i32, _i32, _vp]),
+    "ab200_wgrad_accumulate": (C.c_int, [_dp, _vp, _i32, _i32, _vp, _vp, _i32, _i32, _i32, _vp]),
     "ab200_wgrad_finalize": (C.c_int, [_dp, _vp, _vp, _vp]),
     "ab200_stage_status_offset": (C.c_int, [_dp, _vp, _vp]),
     "ab200_pv_combine": (C.c_int, [_dp, _vp, _vp, _i32, _f32, _vp, _vp, _i64, _vp, _vp]),

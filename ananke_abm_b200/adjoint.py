@@ -89,7 +89,7 @@ class _ContinuousAdjoint(torch.autograd.Function):
                 return pack([f.detach(), vy] + vp)
 
         adj_options = dict(options or {})
-        for k_ in ("precision", "error_norm", "forward_operands", "fp16_forward", "group", "adjoint_mode"):
+        for k_ in ("precision", "error_norm", "forward_operands", "fp16_forward", "group", "adjoint_mode", "saved_operands"):
             adj_options.pop(k_, None)      # forward-solve switches of the tensor-core path mean nothing to the augmented system
         if method == "dopri5":
             adj_options["segments"] = segments

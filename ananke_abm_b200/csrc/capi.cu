@@ -1,6 +1,7 @@
 // extern "C" surface of libananke_b200.so -- see include/ananke_b200.h for the contract of each symbol.
 #include <string.h>
 #include "common.cuh"
+#include "wgrad_layout.cuh"
 
 namespace ab200 {
 static thread_local char g_cuda_err[256] = "";
@@ -49,7 +50,8 @@ int stage_fwd_tc(const ab200_drift_desc* d, const uint8_t* image, const float* y
 int stage_fwd_tc_multi(const ab200_drift_desc* d, const uint8_t* image, const float* y0, const float* const* a_ptrs, const void* descs_v,
                        int n_stage, float* const* a_outs, int64_t B, float* y_out, double* err_sumsq, int half_ops, cudaStream_t st);
 int stage_fwd2_tc_multi(const ab200_drift_desc* d, const uint8_t* image, const float* y0, const float* const* a_ptrs, const void* descs_v,
-                        int n_stage, float* const* a_outs, int64_t B, float* y_out, double* err_sumsq, void* const* x1_outs, cudaStream_t st);
+                        int n_stage, float* const* a_outs, int64_t B, float* y_out, double* err_sumsq, void* const* x1_outs, int save_level,
+                        cudaStream_t st);
 int stage_bwd_tc(const ab200_drift_desc* d, const uint8_t* image, const float* y0, const float* const* a_ptrs, const void* desc_v,
                  int64_t B, const float* g_base, const float* const* gx_ptrs, int n_g, const float* dp, const float* dv, float* gx_out,
                  void* spill, int blob0, int nblobs, float* g_bout, cudaStream_t st);
@@ -60,14 +62,15 @@ int ga_assemble(const ab200_drift_desc* d, const float* base, const float* const
 int stage_bwd_tc_multi(const ab200_drift_desc* d, const uint8_t* image, const float* y0, const float* const* a_ptrs,
                        const void* descs_v, int n_stage, const float* const* g_base, float* const* gx_out, const int32_t* n_g,
                        const int32_t* gx_src, const float* const* gx_ext, const float* dp, const float* dv, int64_t B, void* spill,
-                       int blob0, int nblobs, float* g_bout, const void* const* x1_in, cudaStream_t st);
+                       int blob0, int nblobs, float* g_bout, const void* const* x1_in, int save_level, cudaStream_t st);
 int adjoint_gather(const ab200_drift_desc* d, const float* base, const float* const* gx, int n, const float* cpv, int64_t B, float* out,
                    const float* ga_base, const float* dp, const float* dv, float* ga_out, cudaStream_t st);
 size_t wgrad_spill_bytes(int nblobs);
 size_t wgrad_partial_bytes();
 int wgrad_num_ctas();
 float* wgrad_bout_ptr(void* partial);
-int wgrad_tc(const void* spill, int nblobs, int used, void* partial, const void* const* x1_ext, int n_x1, int ntiles, cudaStream_t st);
+int wgrad_tc(const void* spill, int nblobs, int used, void* partial, const void* const* x1_ext, int n_x1, int ntiles, int save_level,
+             cudaStream_t st);
 int wgrad_finalize(const void* partial, float* grad_w_flat, cudaStream_t st);
 int pv_combine(const ab200_drift_desc* d, const float* y0, const float* const* a_ptrs, int n_a, float cpv, const float* cpa,
                const float* cva, int64_t B, float* out, cudaStream_t st);
@@ -255,7 +258,7 @@ int ab200_stage_forward(const ab200_drift_desc* d, const void* image, const floa
   if ((err_sumsq && !y_out) || operand_format < 0 || operand_format > 2) return AB200_ERR_BAD_ARG;
   if (operand_format == 2) {
     float* outs[1] = {a_out};
-    return stage_fwd2_tc_multi(d, (const uint8_t*)image, y0, a, s, 1, outs, B, y_out, err_sumsq, nullptr, (cudaStream_t)stream);
+    return stage_fwd2_tc_multi(d, (const uint8_t*)image, y0, a, s, 1, outs, B, y_out, err_sumsq, nullptr, 0, (cudaStream_t)stream);
   }
   return stage_fwd_tc(d, (const uint8_t*)image, y0, a, s, B, a_out, y_out, err_sumsq, operand_format, (cudaStream_t)stream);
 }
@@ -267,14 +270,14 @@ int ab200_stage_forward_fused(const ab200_drift_desc* d, const void* image, cons
   if (!stage_shape_ok(d)) return AB200_ERR_UNSUPPORTED;
   if ((err_sumsq && !y_out) || operand_format < 0 || operand_format > 2) return AB200_ERR_BAD_ARG;
   if (operand_format == 2)
-    return stage_fwd2_tc_multi(d, (const uint8_t*)image, y0, a, stages, n_stage, a_out, B, y_out, err_sumsq, nullptr, (cudaStream_t)stream);
+    return stage_fwd2_tc_multi(d, (const uint8_t*)image, y0, a, stages, n_stage, a_out, B, y_out, err_sumsq, nullptr, 0, (cudaStream_t)stream);
   return stage_fwd_tc_multi(d, (const uint8_t*)image, y0, a, stages, n_stage, a_out, B, y_out, err_sumsq, operand_format,
                             (cudaStream_t)stream);
 }
 
-size_t ab200_stage_xblob_bytes(const ab200_drift_desc* d, int64_t B) {
-  if (!stage_shape_ok(d) || B <= 0) return 0;
-  return (size_t)((B + 127) / 128) * 45056;      // wg::X1_BYTES per 128-agent tile
+size_t ab200_stage_xblob_bytes(const ab200_drift_desc* d, int64_t B, int32_t save_level) {
+  if (!stage_shape_ok(d) || B <= 0 || save_level < 1 || save_level > 2) return 0;
+  return wg::FwdSaveLayout{(int)((B + 127) / 128)}.total(save_level);
 }
 
 // ---- Dormand-Prince 5(4) tableau (tdq dopri5.py) and the (p0, v0, a_j) form of its linear combinations (second-order drift:
@@ -310,7 +313,7 @@ void dp_combo(const double* w, int n, double dt, float* cpv, float* cpa, float* 
 
 int ab200_dopri5_attempt(const ab200_drift_desc* d, const void* image, const float* y0, float* const* a, double t0, double dt,
                          int64_t B, float* y_out, double* err_sumsq, float rtol, float atol, int32_t operand_format, void* x_blobs,
-                         ab200_stream_t stream) {
+                         int32_t save_level, ab200_stream_t stream) {
   if (!d || !image || !y0 || !a || !y_out || B <= 0 || operand_format < 0 || operand_format > 2) return AB200_ERR_BAD_ARG;
   if (!stage_shape_ok(d)) return AB200_ERR_UNSUPPORTED;
   for (int i = 0; i < 7; ++i)
@@ -333,12 +336,13 @@ int ab200_dopri5_attempt(const ab200_drift_desc* d, const void* image, const flo
   dp_combo(DP_ERR, 7, dt, &unused, last.err_pa, last.err_va);
   last.rtol = rtol;
   last.atol = atol;
-  if (x_blobs != nullptr && operand_format != 2) return AB200_ERR_UNSUPPORTED;
+  if (x_blobs != nullptr && (operand_format != 2 || save_level < 1 || save_level > 2)) return AB200_ERR_UNSUPPORTED;
   if (operand_format == 2) {
     void* xo[6];
-    const size_t per_stage = ab200_stage_xblob_bytes(d, B);
+    const size_t per_stage = ab200_stage_xblob_bytes(d, B, save_level);
     for (int i = 0; i < 6; ++i) xo[i] = x_blobs ? (uint8_t*)x_blobs + (size_t)i * per_stage : nullptr;
-    return stage_fwd2_tc_multi(d, (const uint8_t*)image, y0, ins, st, 6, outs, B, y_out, err_sumsq, x_blobs ? xo : nullptr, (cudaStream_t)stream);
+    return stage_fwd2_tc_multi(d, (const uint8_t*)image, y0, ins, st, 6, outs, B, y_out, err_sumsq, x_blobs ? xo : nullptr,
+                               x_blobs ? save_level : 0, (cudaStream_t)stream);
   }
   return stage_fwd_tc_multi(d, (const uint8_t*)image, y0, ins, st, 6, outs, B, y_out, err_sumsq, operand_format, (cudaStream_t)stream);
 }
@@ -385,14 +389,14 @@ int ab200_stage_backward_fused(const ab200_drift_desc* d, const void* image, con
                                const ab200_stage_desc* stages, int32_t n_stage, const float* const* g_base, float* const* gx_out,
                                const int32_t* n_g, const int32_t* gx_src, const float* const* gx_ext, const float* dp_host,
                                const float* dv_host, int64_t B, void* spill, size_t spill_bytes, int32_t blob0, int32_t nblobs,
-                               void* partial, const void* const* x_blobs, ab200_stream_t stream) {
+                               void* partial, const void* const* x_blobs, int32_t save_level, ab200_stream_t stream) {
   if (!d || !image || !y0 || !a || !stages || !g_base || !gx_out || !n_g || !gx_src || !dp_host || !dv_host || !spill || !partial ||
       B <= 0 || n_stage < 1 || n_stage > AB200_STAGE_MAX_A)
     return AB200_ERR_BAD_ARG;
   if (!stage_shape_ok(d)) return AB200_ERR_UNSUPPORTED;
   if (nblobs <= 0 || spill_bytes < wgrad_spill_bytes(nblobs)) return AB200_ERR_WORKSPACE;
   return stage_bwd_tc_multi(d, (const uint8_t*)image, y0, a, stages, n_stage, g_base, gx_out, n_g, gx_src, gx_ext, dp_host, dv_host, B,
-                            spill, blob0, nblobs, wgrad_bout_ptr(partial), x_blobs, (cudaStream_t)stream);
+                            spill, blob0, nblobs, wgrad_bout_ptr(partial), x_blobs, x_blobs ? save_level : 0, (cudaStream_t)stream);
 }
 
 int ab200_pv_combine_backward_multi(const ab200_drift_desc* d, const float* const* g, int32_t n_src, const float* cpv_host,
@@ -423,11 +427,11 @@ int ab200_adjoint_gather_upstream(const ab200_drift_desc* d, const float* base, 
 }
 
 int ab200_wgrad_accumulate(const ab200_drift_desc* d, const void* spill, int32_t nblobs, int32_t used, void* partial,
-                           const void* const* x_blobs, int32_t n_x_blobs, int32_t ntiles, ab200_stream_t stream) {
+                           const void* const* x_blobs, int32_t n_x_blobs, int32_t ntiles, int32_t save_level, ab200_stream_t stream) {
   if (!d || !spill || !partial || nblobs <= 0 || used < 0 || used > nblobs || n_x_blobs < 0 || (n_x_blobs > 0 && (!x_blobs || ntiles <= 0)))
     return AB200_ERR_BAD_ARG;
   if (!stage_shape_ok(d)) return AB200_ERR_UNSUPPORTED;
-  return wgrad_tc(spill, nblobs, used, partial, x_blobs, n_x_blobs, ntiles, (cudaStream_t)stream);
+  return wgrad_tc(spill, nblobs, used, partial, x_blobs, n_x_blobs, ntiles, save_level, (cudaStream_t)stream);
 }
 
 int ab200_wgrad_finalize(const ab200_drift_desc* d, const void* partial, float* grad_w_flat, ab200_stream_t stream) {

@@ -41,7 +41,8 @@ struct BwdStageParams {       // one stage of a fused (latest-first) sequence
   float dp[MAX_A], dv[MAX_A]; // and coefficients (that stage's in.cpa / in.cva entry for a_out)
   float* gx_out;              // blocked [Bp][160]: [g_p, g_v, g_h] of this stage (written)
   int blob0;                  // blob index of tile 0 for this stage
-  const uint8_t* x1_in;       // X blobs of this stage written by the forward launch ([ntiles][X1_BYTES]) or null: rebuild from y0 / a_j
+  const uint8_t* x1_in;       // what the forward launch saved for this stage (wg::FwdSaveLayout) or null: rebuild the input from y0 / a_j
+  int saved_acts;             // 1: x1_in also holds the hidden activations and the ReLU masks -> nothing is recomputed or re-spilled
 };
 
 struct StageBwdArgs {
@@ -152,6 +153,16 @@ __global__ void __launch_bounds__(THREADS, 1) stage_bwd_tc_kernel(const __grid_c
     const int blob = sp.blob0 + tile;
     STAGE_TRACE(c, 9);
 
+    uint32_t z[32];
+    uint32_t m_z0[2], m_u0[2], m_z1[2], m_u1[2], m_z2[2];
+    if (sp.saved_acts) {
+      // The training forward saved every layer input of this evaluation as blobs and the ReLU masks as bits: the recompute
+      // half of this kernel (stage input, five GEMMs, five epilogues, 1.6 KB of spills per agent) reduces to loading 40 bytes.
+      const uint2* mp = reinterpret_cast<const uint2*>(sp.x1_in + wg::FwdSaveLayout{a.ntiles}.mask(tile)) + (c.hf * TM + c.row);
+      const uint2 q0 = __ldg(mp), q1 = __ldg(mp + 256), q2 = __ldg(mp + 512), q3 = __ldg(mp + 768), q4 = __ldg(mp + 1024);
+      m_z0[0] = q0.x; m_z0[1] = q0.y; m_u0[0] = q1.x; m_u0[1] = q1.y; m_z1[0] = q2.x; m_z1[1] = q2.y;
+      m_u1[0] = q3.x; m_u1[1] = q3.y; m_z2[0] = q4.x; m_z2[1] = q4.y;
+    } else {
     // ---- stage input -> ACT / HB / TB and the X blob (features: p 0..63, v 64..127, h 128..159, sin, cos, 1)
     if (sp.x1_in != nullptr) {
       // The forward launch of this step already wrote the stage input as the bf16 X blob (the very operand image the recompute
@@ -238,8 +249,6 @@ __global__ void __launch_bounds__(THREADS, 1) stage_bwd_tc_kernel(const __grid_c
 
     STAGE_TRACE(c, 10);
     // ---- forward recompute (hidden layers only), masks + blobs
-    uint32_t z[32];
-    uint32_t m_z0[2], m_u0[2], m_z1[2], m_u1[2], m_z2[2];
     run_layer<false, (2 * P + H) / 16, true, HID, HID, true>(c, C_ACT, OFF_W1);
     bwd_fwd_epi<false, true>(c, z, m_z0, blob_at(S.act(0, blob)));
     run_layer<false, HID / 16, true, HID, HID, true>(c, C_ACT, off_hh(0));
@@ -250,6 +259,7 @@ __global__ void __launch_bounds__(THREADS, 1) stage_bwd_tc_kernel(const __grid_c
     bwd_fwd_epi<false, false>(c, z, m_u1, blob_at(S.act(3, blob)));
     run_layer<false, HID / 16, true, HID, HID, true>(c, C_ACT, off_hh(3));
     bwd_fwd_epi<true, false, false>(c, z, m_z2, blob_at(S.act(4, blob)));
+    }
 
     STAGE_TRACE(c, 12);
     // ---- upstream gradient of the output layer -> ACT (K = 64) + gO blob + bias column sums
@@ -374,7 +384,7 @@ static_assert(sizeof(StageBwdHost) == sizeof(ab200_stage_desc), "stage descripto
 int stage_bwd_tc_multi(const ab200_drift_desc* d, const uint8_t* image, const float* y0, const float* const* a_ptrs,
                        const void* descs_v, int n_stage, const float* const* g_base, float* const* gx_out, const int32_t* n_g,
                        const int32_t* gx_src, const float* const* gx_ext, const float* dp, const float* dv, int64_t B, void* spill,
-                       int blob0, int nblobs, float* g_bout, const void* const* x1_in, cudaStream_t st) {
+                       int blob0, int nblobs, float* g_bout, const void* const* x1_in, int save_level, cudaStream_t st) {
   const StageBwdHost* hs = reinterpret_cast<const StageBwdHost*>(descs_v);
   if (n_stage < 1 || n_stage > MAX_A) return AB200_ERR_BAD_ARG;
   StageBwdArgs k{};
@@ -404,6 +414,7 @@ int stage_bwd_tc_multi(const ab200_drift_desc* d, const uint8_t* image, const fl
     sp.gx_out = gx_out[s];
     sp.blob0 = blob0 + s * k.ntiles;
     sp.x1_in = x1_in ? (const uint8_t*)x1_in[s] : nullptr;
+    sp.saved_acts = (sp.x1_in != nullptr && save_level >= 2) ? 1 : 0;
   }
   if (blob0 < 0 || blob0 + n_stage * k.ntiles > nblobs) return AB200_ERR_BAD_ARG;
   for (int i = 0; i < MAX_A; ++i) k.a[i] = (i < max_a) ? a_ptrs[i] : nullptr;
@@ -435,7 +446,7 @@ int stage_bwd_tc(const ab200_drift_desc* d, const uint8_t* image, const float* y
   int32_t src[MAX_A];
   float dpa[MAX_A], dva[MAX_A];
   for (int l = 0; l < MAX_A; ++l) { src[l] = -1 - l; dpa[l] = l < n_g ? dp[l] : 0.f; dva[l] = l < n_g ? dv[l] : 0.f; }
-  return stage_bwd_tc_multi(d, image, y0, a_ptrs, desc_v, 1, gb, go, ng, src, gx_ptrs, dpa, dva, B, spill, blob0, nblobs, g_bout, nullptr, st);
+  return stage_bwd_tc_multi(d, image, y0, a_ptrs, desc_v, 1, gb, go, ng, src, gx_ptrs, dpa, dva, B, spill, blob0, nblobs, g_bout, nullptr, 0, st);
 }
 
 }  // namespace ab200

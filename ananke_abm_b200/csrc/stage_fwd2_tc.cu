@@ -143,8 +143,14 @@ __device__ __forceinline__ void run_layer2(SlotCtx& c, uint32_t a_reg, uint32_t 
 
 // Hidden-layer epilogue on this thread's 64 columns (hf * 64 ..) of region `reg`, in place:
 //   x = acc + bias [+ z] ;  x = relu(x) ;  [z = x] ;  columns <- (hi pairs | lo pairs) per 16-feature group
-template <bool RES, bool KEEP>
-__device__ __forceinline__ void epi2(const SlotCtx& c, uint32_t reg, const float* __restrict__ bias, float (&z)[64]) {
+// SAVE: the activation also goes out as the bf16 blob of the weight-gradient kernel (`blob` = this tile's blob + row * 16) and
+// its ReLU mask as two words (`mask_out`, the bit layout of stage_bwd_tc.cu): the backward pass then has nothing to recompute.
+// (The fp16 hi words that are already at hand cannot be used: tcgen05.mma kind::f16 with an fp16 A next to a bf16 B operand is
+// an illegal instruction on sm_100a -- tried, profiles/r02_stage_source_stalls.txt.)
+template <bool RES, bool KEEP, bool SAVE>
+__device__ __forceinline__ void epi2(const SlotCtx& c, uint32_t reg, const float* __restrict__ bias, float (&z)[64], uint8_t* blob,
+                                     uint2* mask_out) {
+  uint32_t mw[2] = {0u, 0u};
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const int col = c.hf * 64 + q * 16;
@@ -152,6 +158,8 @@ __device__ __forceinline__ void epi2(const SlotCtx& c, uint32_t reg, const float
     tmem_ld16(c.tmem + c.lane_sel + reg + (uint32_t)col, r);
     tmem_ld_wait();
     uint32_t o[16];
+    uint32_t w[8];
+    uint32_t m = 0u;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float2 b2 = *reinterpret_cast<const float2*>(bias + col + 2 * j);      // same address for the whole warp: broadcast
@@ -162,13 +170,24 @@ __device__ __forceinline__ void epi2(const SlotCtx& c, uint32_t reg, const float
       const uint32_t hi = pack2<true>(x0, x1);
       o[j] = hi;
       o[8 + j] = pack2<true>(x0 - un_lo<true>(hi), x1 - un_hi<true>(hi));
+      if (SAVE) {      // post-ReLU halves are >= +0: adding 0x7FFF sets bit 15 / 31 iff the low / high half is non-zero (no carry across)
+        w[j] = pack_bf16(x0, x1);
+        m |= ((w[j] + 0x7FFF7FFFu) >> ((q & 1) * 8 + j)) & (0x80008000u >> ((q & 1) * 8 + j));
+      }
     }
     tmem_st16(c.tmem + c.lane_sel + reg + (uint32_t)col, o);
+    if (SAVE) mw[q >> 1] |= m;
+    if (SAVE && blob != nullptr) {
+      __stcs(reinterpret_cast<uint4*>(blob + (size_t)(c.hf * 8 + q * 2) * wg::FG_BYTES), make_uint4(w[0], w[1], w[2], w[3]));
+      __stcs(reinterpret_cast<uint4*>(blob + (size_t)(c.hf * 8 + q * 2 + 1) * wg::FG_BYTES), make_uint4(w[4], w[5], w[6], w[7]));
+    }
   }
+  if (SAVE && mask_out != nullptr) __stcs(mask_out, make_uint2(mw[0], mw[1]));
 }
 
-// 16 features -> (8 hi columns | 8 lo columns) at tensor-memory column `col` of this thread's lane
-__device__ __forceinline__ void st_split16(const SlotCtx& c, uint32_t col, const float* x) {
+// 16 features -> (8 hi columns | 8 lo columns) at tensor-memory column `col` of this thread's lane; `xg` != null: they also go
+// out as two feature groups of the bf16 X blob (xg = address of the first group for this row)
+__device__ __forceinline__ void st_split16(const SlotCtx& c, uint32_t col, const float* x, uint8_t* xg = nullptr) {
   uint32_t o[16];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -177,6 +196,11 @@ __device__ __forceinline__ void st_split16(const SlotCtx& c, uint32_t col, const
     o[8 + j] = pack2<true>(x[2 * j] - un_lo<true>(hi), x[2 * j + 1] - un_hi<true>(hi));
   }
   tmem_st16(c.tmem + c.lane_sel + col, o);
+  if (xg != nullptr) {
+    __stcs(reinterpret_cast<uint4*>(xg), make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7])));
+    __stcs(reinterpret_cast<uint4*>(xg + wg::FG_BYTES),
+           make_uint4(pack_bf16(x[8], x[9]), pack_bf16(x[10], x[11]), pack_bf16(x[12], x[13]), pack_bf16(x[14], x[15])));
+  }
 }
 
 struct Stage2Params {         // one stage of a fused sequence (same meaning as StageParams in stage_fwd_tc.cu)
@@ -188,7 +212,8 @@ struct Stage2Params {         // one stage of a fused sequence (same meaning as 
   Combo out;
   Combo err;
   int want_err;
-  uint8_t* x1_out;            // or null: this stage's input as the bf16 X blob of the backward pass ([ntiles][X1_BYTES], wgrad_layout.cuh)
+  uint8_t* x1_out;            // or null: what this stage saves for the backward pass (wg::FwdSaveLayout: X blob; + activations and masks
+                              // when the launch runs the SAVE_ACTS kernel)
 };
 
 struct StageFwd2Args {
@@ -205,6 +230,7 @@ struct StageFwd2Args {
   int* status;
 };
 
+template <bool SAVE_ACTS>
 __global__ void __launch_bounds__(THREADS, 1) stage_fwd2_tc_kernel(const __grid_constant__ StageFwd2Args a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bars[NSLOT + 1];
@@ -268,39 +294,32 @@ __global__ void __launch_bounds__(THREADS, 1) stage_fwd2_tc_kernel(const __grid_
             vin[4 * j] += cv * x[j].x; vin[4 * j + 1] += cv * x[j].y; vin[4 * j + 2] += cv * x[j].z; vin[4 * j + 3] += cv * x[j].w;
           }
         }
-        if (sp.x1_out != nullptr) {
-          // The backward pass needs exactly this stage input as a bf16 operand image (recompute A operand, weight-gradient B
-          // operand): written here it costs 352 B per agent-stage of a launch that uses 12 % of the DRAM bandwidth, and saves the
-          // backward kernel -- which is bound by its HBM traffic -- re-reading y0 and up to six a_j (1.5 KB) and spilling the blob.
-          uint8_t* xb = sp.x1_out + (size_t)tile * wg::X1_BYTES + (size_t)c.row * 16;
+        // p features 32 hf .. -> columns 32 hf .. ; v features 64 + 32 hf .. -> columns 64 + 32 hf ..
+        // The backward pass needs exactly this stage input as a bf16 operand image (weight-gradient B operand; at save level 1 also
+        // the recompute A operand): written here it costs 352 B per agent-stage of a launch that uses little of the DRAM bandwidth,
+        // and saves the backward kernel re-reading y0 and up to six a_j (1.5 KB) and spilling the blob.
+        // Feature groups: p 4 hf + {0..3}, v 8 + 4 hf + {0..3}, h 16 + 2 hf + {0, 1}, [sin, cos, 1, 0..] 20, zeros 21.
+        uint8_t* xb = (sp.x1_out != nullptr && !(c.flags & 64)) ? sp.x1_out + (size_t)tile * wg::X1_BYTES + (size_t)c.row * 16 : nullptr;
+        auto grp = [&](int g) -> uint8_t* { return xb ? xb + (size_t)g * wg::FG_BYTES : nullptr; };
+        st_split16(c, f2::RX + (uint32_t)(c.hf * 32), pin, grp(c.hf * 4));
+        st_split16(c, f2::RX + (uint32_t)(c.hf * 32 + 16), pin + 16, grp(c.hf * 4 + 2));
+        st_split16(c, f2::RX + (uint32_t)(P + c.hf * 32), vin, grp(P / 8 + c.hf * 4));
+        st_split16(c, f2::RX + (uint32_t)(P + c.hf * 32 + 16), vin + 16, grp(P / 8 + c.hf * 4 + 2));
+        if (xb != nullptr) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {      // feature groups of 8: p groups 4 hf + q, v groups 8 + 4 hf + q
-            const uint4 gp = make_uint4(pack_bf16(pin[8 * q], pin[8 * q + 1]), pack_bf16(pin[8 * q + 2], pin[8 * q + 3]),
-                                        pack_bf16(pin[8 * q + 4], pin[8 * q + 5]), pack_bf16(pin[8 * q + 6], pin[8 * q + 7]));
-            const uint4 gv = make_uint4(pack_bf16(vin[8 * q], vin[8 * q + 1]), pack_bf16(vin[8 * q + 2], vin[8 * q + 3]),
-                                        pack_bf16(vin[8 * q + 4], vin[8 * q + 5]), pack_bf16(vin[8 * q + 6], vin[8 * q + 7]));
-            __stcs(reinterpret_cast<uint4*>(xb + (size_t)(c.hf * 4 + q) * wg::FG_BYTES), gp);
-            __stcs(reinterpret_cast<uint4*>(xb + (size_t)(P / 8 + c.hf * 4 + q) * wg::FG_BYTES), gv);
-          }
-#pragma unroll
-          for (int q = 0; q < 2; ++q) {      // h groups 16 + 2 hf + q (16 context dims per thread)
+          for (int q = 0; q < 2; ++q) {      // h groups 16 + 2 hf + q (16 context dims per thread; L1 / L2 hits)
             const float4 x0 = ldro(blk4(a.y0, tile, YF4, 2 * AF4 + c.hf * 4 + 2 * q, c.row));
             const float4 x1 = ldro(blk4(a.y0, tile, YF4, 2 * AF4 + c.hf * 4 + 2 * q + 1, c.row));
-            __stcs(reinterpret_cast<uint4*>(xb + (size_t)(2 * P / 8 + c.hf * 2 + q) * wg::FG_BYTES),
+            __stcs(reinterpret_cast<uint4*>(grp(2 * P / 8 + c.hf * 2 + q)),
                    make_uint4(pack_bf16(x0.x, x0.y), pack_bf16(x0.z, x0.w), pack_bf16(x1.x, x1.y), pack_bf16(x1.z, x1.w)));
           }
-          if (c.hf == 0) {                   // groups 20, 21: [sin, cos, 1, 0 ...], zeros
+          if (c.hf == 0) {
             float sn, co;
             time_features(sp.t, a.period, sn, co);
-            __stcs(reinterpret_cast<uint4*>(xb + (size_t)((2 * P + H) / 8) * wg::FG_BYTES), make_uint4(pack_bf16(sn, co), pack_bf16(1.0f, 0.0f), 0u, 0u));
-            __stcs(reinterpret_cast<uint4*>(xb + (size_t)((2 * P + H) / 8 + 1) * wg::FG_BYTES), make_uint4(0u, 0u, 0u, 0u));
+            __stcs(reinterpret_cast<uint4*>(grp((2 * P + H) / 8)), make_uint4(pack_bf16(sn, co), pack_bf16(1.0f, 0.0f), 0u, 0u));
+            __stcs(reinterpret_cast<uint4*>(grp((2 * P + H) / 8 + 1)), make_uint4(0u, 0u, 0u, 0u));
           }
         }
-        // p features 32 hf .. -> columns 32 hf .. ; v features 64 + 32 hf .. -> columns 64 + 32 hf ..
-        st_split16(c, f2::RX + (uint32_t)(c.hf * 32), pin);
-        st_split16(c, f2::RX + (uint32_t)(c.hf * 32 + 16), pin + 16);
-        st_split16(c, f2::RX + (uint32_t)(P + c.hf * 32), vin);
-        st_split16(c, f2::RX + (uint32_t)(P + c.hf * 32 + 16), vin + 16);
       }
       if (c.stid < HID) {
         float s, co;
@@ -311,16 +330,22 @@ __global__ void __launch_bounds__(THREADS, 1) stage_fwd2_tc_kernel(const __grid_
 
       // ---- drift net (regions alternate: X -> Y -> X -> Y -> X -> Y -> X)
       float z[64];
+      const wg::FwdSaveLayout FS{a.ntiles};      // SAVE_ACTS launches save every stage (the host checks x1_out != null)
+      const bool no_store = (c.flags & 64) != 0;      // timing experiment only (results invalid): everything but the stores
+      auto act_blob = [&](int l) -> uint8_t* { return (SAVE_ACTS && !no_store) ? sp.x1_out + FS.act(l, tile) + (size_t)c.row * 16 : nullptr; };
+      auto mask_at = [&](int l) -> uint2* {
+        return (SAVE_ACTS && !no_store) ? reinterpret_cast<uint2*>(sp.x1_out + FS.mask(tile)) + (l * 2 * TM + c.hf * TM + c.row) : nullptr;
+      };
       run_layer2<2 * P / 16, true, HID, HID>(c, f2::RX, f2::RY, f2::OFF_W1);
-      epi2<false, true>(c, f2::RY, ct, z);
+      epi2<false, true, SAVE_ACTS>(c, f2::RY, ct, z, act_blob(0), mask_at(0));
       run_layer2<HID / 16, false, HID, HID>(c, f2::RY, f2::RX, f2::off_hh(0));
-      epi2<false, false>(c, f2::RX, tab + f2::T_BHH, z);
+      epi2<false, false, SAVE_ACTS>(c, f2::RX, tab + f2::T_BHH, z, act_blob(1), mask_at(1));
       run_layer2<HID / 16, false, HID, HID>(c, f2::RX, f2::RY, f2::off_hh(1));
-      epi2<true, true>(c, f2::RY, tab + f2::T_BHH + HID, z);
+      epi2<true, true, SAVE_ACTS>(c, f2::RY, tab + f2::T_BHH + HID, z, act_blob(2), mask_at(2));
       run_layer2<HID / 16, false, HID, HID>(c, f2::RY, f2::RX, f2::off_hh(2));
-      epi2<false, false>(c, f2::RX, tab + f2::T_BHH + 2 * HID, z);
+      epi2<false, false, SAVE_ACTS>(c, f2::RX, tab + f2::T_BHH + 2 * HID, z, act_blob(3), mask_at(3));
       run_layer2<HID / 16, false, HID, HID>(c, f2::RX, f2::RY, f2::off_hh(3));
-      epi2<true, false>(c, f2::RY, tab + f2::T_BHH + 3 * HID, z);
+      epi2<true, false, SAVE_ACTS>(c, f2::RY, tab + f2::T_BHH + 3 * HID, z, act_blob(4), mask_at(4));
       run_layer2<HID / 16, false, P, P>(c, f2::RY, f2::RX, f2::OFF_WO);
 
       // ---- output epilogue: this thread's 32 acceleration dims (float4 groups hf*8 ..)
@@ -445,7 +470,8 @@ struct StageFwd2Host {   // mirrors ab200_stage_desc in the public header
 static_assert(sizeof(StageFwd2Host) == sizeof(ab200_stage_desc), "stage descriptor layout");
 
 int stage_fwd2_tc_multi(const ab200_drift_desc* d, const uint8_t* image, const float* y0, const float* const* a_ptrs, const void* descs_v,
-                        int n_stage, float* const* a_outs, int64_t B, float* y_out, double* err_sumsq, void* const* x1_outs, cudaStream_t st) {
+                        int n_stage, float* const* a_outs, int64_t B, float* y_out, double* err_sumsq, void* const* x1_outs, int save_level,
+                        cudaStream_t st) {
   const StageFwd2Host* hs = reinterpret_cast<const StageFwd2Host*>(descs_v);
   if (n_stage < 1 || n_stage > MAX_A) return AB200_ERR_BAD_ARG;
   StageFwd2Args k{};
@@ -471,6 +497,7 @@ int stage_fwd2_tc_multi(const ab200_drift_desc* d, const uint8_t* image, const f
     sp.y_out = (s == n_stage - 1) ? y_out : nullptr;
     sp.want_err = (s == n_stage - 1 && err_sumsq != nullptr) ? 1 : 0;
     sp.x1_out = x1_outs ? (uint8_t*)x1_outs[s] : nullptr;
+    if (save_level >= 2 && sp.x1_out == nullptr) return AB200_ERR_BAD_ARG;      // the activation-saving kernel saves every stage
   }
   for (int i = 0; i < MAX_A; ++i) k.a[i] = (i < max_a) ? a_ptrs[i] : nullptr;
   k.n_stage = n_stage;
@@ -486,9 +513,10 @@ int stage_fwd2_tc_multi(const ab200_drift_desc* d, const uint8_t* image, const f
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = k.ntiles < sms ? k.ntiles : sms;      // a partial wave uses one slot per CTA first
-  cudaError_t e = cudaFuncSetAttribute(stage_fwd2_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f2::SMEM_BYTES);
+  auto kern = save_level >= 2 ? stage_fwd2_tc_kernel<true> : stage_fwd2_tc_kernel<false>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f2::SMEM_BYTES);
   if (e != cudaSuccess) { set_cuda_error(e); return AB200_ERR_CUDA; }
-  stage_fwd2_tc_kernel<<<grid, THREADS, f2::SMEM_BYTES, st>>>(k);
+  kern<<<grid, THREADS, f2::SMEM_BYTES, st>>>(k);
   return check_launch();
 }
 

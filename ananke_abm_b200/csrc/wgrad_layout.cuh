@@ -31,6 +31,22 @@ struct SpillLayout {
   __host__ __device__ size_t total() const { return (size_t)nblobs * BYTES_PER_BLOB_SET; }
 };
 
+// What a TRAINING forward launch (stage_fwd2_tc.cu) can save per stage for the backward pass, so that the backward kernel does not
+// recompute the net and the weight-gradient kernel reads the layer inputs from here:
+//   level 1: the stage input X blob;   level 2: + the five hidden activation blobs (z0,u0,z1,u1,z2) + the ReLU masks
+// (two words per thread and layer, the bit layout of stage_bwd_tc.cu's bwd_fwd_epi: [layer][hf * 128 + row] uint2).
+// A level-1 buffer is the prefix of a level-2 buffer.
+constexpr uint32_t MASK_BYTES = 5 * 256 * 8;                 // 10,240 per tile
+struct FwdSaveLayout {
+  int ntiles;
+  __host__ __device__ size_t x1(int tile) const { return (size_t)tile * X1_BYTES; }
+  __host__ __device__ size_t act(int i, int tile) const { return (size_t)ntiles * X1_BYTES + ((size_t)i * ntiles + tile) * HID_BYTES; }
+  __host__ __device__ size_t mask(int tile) const { return (size_t)ntiles * (X1_BYTES + 5 * HID_BYTES) + (size_t)tile * MASK_BYTES; }
+  __host__ __device__ size_t total(int level) const {
+    return level >= 2 ? (size_t)ntiles * (X1_BYTES + 5 * HID_BYTES + MASK_BYTES) : (size_t)ntiles * X1_BYTES;
+  }
+};
+
 // per-CTA fp32 partial weight gradients: pair 0 [128][176] | pairs 1..4 [128][128] + bias block [128][16] | pair 5 [128 in][64 out]
 constexpr int PART_W1 = 0, PART_W1_N = 176;
 constexpr int PART_HH = 128 * 176, PART_HH_N = 144, PART_HH_SZ = 128 * 144;

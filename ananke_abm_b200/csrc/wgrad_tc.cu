@@ -37,6 +37,7 @@ struct WgradArgs {
   // position (= blob / ntiles, the stage's place in the backward launch), tile-indexed; null = the spill buffer's own x1 region
   const uint8_t* x1_ext[8];
   int ntiles;
+  int save_level;      // 2: those buffers (wg::FwdSaveLayout) also hold the hidden activation blobs: every layer INPUT comes from them
 };
 
 struct PairDesc { size_t a_off, b_off; uint32_t a_bytes, b_bytes; int N; bool bias; int part_off, part_ld; };
@@ -97,12 +98,21 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tc_kernel(const __grid_co
             const PairDesc d = pair_desc(S, pair, b);
             uint8_t* dst = smem + slot * WG_SLOT;
             mbar_arrive_expect_tx(&full[slot], d.a_bytes + d.b_bytes);
-            bulk_g2s(dst, a.spill + d.a_off, d.a_bytes, &full[slot]);
+            const uint8_t* asrc = a.spill + d.a_off;
             const uint8_t* bsrc = a.spill + d.b_off;
-            if (pair == 0 && a.ntiles > 0) {
-              const int pos = b / a.ntiles;
-              if (pos < 8 && a.x1_ext[pos] != nullptr) bsrc = a.x1_ext[pos] + (size_t)(b - pos * a.ntiles) * X1_BYTES;
+            if (a.ntiles > 0) {      // layer inputs saved by the forward launch (pair 0: X; pairs 1..4: B = act(pair - 1); pair 5: A = act(4))
+              const int pos = b / a.ntiles, tile = b - pos * a.ntiles;
+              const uint8_t* ext = pos < 8 ? a.x1_ext[pos] : nullptr;
+              if (ext != nullptr) {
+                const FwdSaveLayout FS{a.ntiles};
+                if (pair == 0) bsrc = ext + FS.x1(tile);
+                else if (a.save_level >= 2) {
+                  if (pair <= 4) bsrc = ext + FS.act(pair - 1, tile);
+                  else asrc = ext + FS.act(4, tile);
+                }
+              }
             }
+            bulk_g2s(dst, asrc, d.a_bytes, &full[slot]);
             bulk_g2s(dst + HID_BYTES, bsrc, d.b_bytes, &full[slot]);
           }
         }
@@ -234,14 +244,16 @@ int wgrad_num_ctas() {
 size_t wgrad_partial_bytes() { return ((size_t)wgrad_num_ctas() * PART_TOTAL + 64) * sizeof(float) + 256; }
 
 // partial buffer: [ncta][PART_TOTAL] floats, then g_bout[64], then a status word
-int wgrad_tc(const void* spill, int nblobs, int used, void* partial, const void* const* x1_ext, int n_x1, int ntiles, cudaStream_t st) {
+int wgrad_tc(const void* spill, int nblobs, int used, void* partial, const void* const* x1_ext, int n_x1, int ntiles, int save_level,
+             cudaStream_t st) {
   if (used <= 0) return AB200_OK;
   const int ncta = wgrad_num_ctas();
-  WgradArgs k{(const uint8_t*)spill, (float*)partial, nblobs, used, reinterpret_cast<int*>((float*)partial + (size_t)ncta * PART_TOTAL + 64), {}, 0};
+  WgradArgs k{(const uint8_t*)spill, (float*)partial, nblobs, used, reinterpret_cast<int*>((float*)partial + (size_t)ncta * PART_TOTAL + 64), {}, 0, 0};
   if (x1_ext != nullptr && n_x1 > 0 && ntiles > 0) {
     if (n_x1 > 8) return AB200_ERR_BAD_ARG;
     for (int i = 0; i < n_x1; ++i) k.x1_ext[i] = (const uint8_t*)x1_ext[i];
     k.ntiles = ntiles;
+    k.save_level = save_level;
   }
   cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM);
   if (e != cudaSuccess) { set_cuda_error(e); return AB200_ERR_CUDA; }

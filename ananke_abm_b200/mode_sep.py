@@ -67,6 +67,8 @@ def _solver_options(config) -> dict:
         opt["error_norm"] = getattr(config, "error_norm", "shard")
         if getattr(config, "forward_operands", None):       # "fp16x2" (default of the solver) | "fp16" | "bf16"
             opt["forward_operands"] = config.forward_operands
+        if getattr(config, "saved_operands", None):         # "all" (default of the solver) | "inputs" | "none": memory vs backward traffic
+            opt["saved_operands"] = config.saved_operands
     return opt
 
 

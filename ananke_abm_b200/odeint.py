@@ -517,7 +517,7 @@ def odeint(func, y0, t, *, rtol: float = 1e-7, atol: float = 1e-9, method: Optio
         if (spec is not None and y0.shape[1] == spec.state_dim and precision == _lib.PREC_BF16 and spec.tc_stage_supported()
                 and y0.dtype == torch.float32):
             opts = {}
-            for k_ in ("first_step", "safety", "ifactor", "dfactor", "max_num_steps", "fp16_forward", "forward_operands", "error_norm", "group"):
+            for k_ in ("first_step", "safety", "ifactor", "dfactor", "max_num_steps", "fp16_forward", "forward_operands", "error_norm", "group", "saved_operands"):
                 if k_ in options:
                     opts[k_] = options.pop(k_)
             opts["time_dtype"] = torch.promote_types(options.pop("dtype", torch.float64), torch.float32)

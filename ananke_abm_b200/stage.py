@@ -27,6 +27,7 @@ from .drift import DriftSpec
 
 MAX_A = 7
 TM = 128
+SAVE_LEVELS = {"none": 0, "inputs": 1, "all": 2}
 FWD_FORMATS = {"bf16": 0, "fp16": 1, "fp16x2": 2}
 
 
@@ -229,17 +230,18 @@ class TcEngine:
         _lib.check(rc, "ab200_pv_combine_rowmajor")
 
     def dopri5_attempt(self, y0, A: Sequence[torch.Tensor], t0: float, dt: float, B: int, y_out, err_sumsq, rtol: float, atol: float,
-                       x_blobs=None) -> None:
+                       x_blobs=None, save_level: int = 0) -> None:
         """one attempted Dormand-Prince step in ONE call: stages 2..7 fused, descriptors built in C (ab200_dopri5_attempt);
-        `x_blobs` (6 * xblob_bytes(B) bytes, split-activation format only) receives the stage inputs as backward operand images"""
+        `x_blobs` (6 * xblob_bytes(B, save_level) bytes, split-activation format only) receives what the backward pass would
+        otherwise recompute (level 1: stage inputs; level 2: + hidden activations and ReLU masks) as its operand images"""
         ptrs = (C.c_void_p * 7)(*[t.data_ptr() for t in A[:7]])
         rc = self.L.ab200_dopri5_attempt(C.byref(self.desc), self.image.data_ptr(), y0.data_ptr(), C.cast(ptrs, C.c_void_p), float(t0),
                                          float(dt), B, y_out.data_ptr(), err_sumsq.data_ptr(), float(rtol), float(atol), self.fwd_format,
-                                         None if x_blobs is None else x_blobs.data_ptr(), _stream())
+                                         None if x_blobs is None else x_blobs.data_ptr(), int(save_level), _stream())
         _lib.check(rc, "ab200_dopri5_attempt")
 
-    def xblob_bytes(self, B: int) -> int:
-        return int(self.L.ab200_stage_xblob_bytes(C.byref(self.desc), B))
+    def xblob_bytes(self, B: int, save_level: int) -> int:
+        return int(self.L.ab200_stage_xblob_bytes(C.byref(self.desc), B, int(save_level)))
 
     def dopri5_dense_rows(self, y0, A: Sequence[torch.Tensor], dt: float, xs: Sequence[float], B: int, outs: Sequence[torch.Tensor]) -> None:
         """dense-output rows of an accepted step at relative positions xs, one pass (ab200_dopri5_dense_rows)"""
@@ -277,7 +279,8 @@ class TcEngine:
         npart = self.L.ab200_wgrad_partial_bytes(C.byref(self.desc))
         self.partial = torch.zeros(int(npart), dtype=torch.uint8, device=self.dev)
         self.used = 0
-        self.x_ring = []          # per filled run of ntiles blobs: device pointer of a forward-saved X blob, or None
+        self.x_ring = []          # per filled run of ntiles blobs: device pointer of a forward-saved buffer, or None
+        self.x_level = 0          # save level of those buffers (one level per backward pass)
 
     def combine_backward(self, g, c: Combo, B: int, G_y0, G_a: Sequence[torch.Tensor], accumulate: bool) -> None:
         n = len(G_a)
@@ -339,14 +342,18 @@ class TcEngine:
                                          C.cast(dpa, C.c_void_p), C.cast(dva, C.c_void_p), B, out.data_ptr(), _stream())
         _lib.check(rc, "ab200_stage_upstream")
 
-    def stage_backward_fused(self, y0, a_bufs: Sequence[torch.Tensor], stages: Sequence, B: int, x_blobs: Optional[Sequence] = None) -> None:
+    def stage_backward_fused(self, y0, a_bufs: Sequence[torch.Tensor], stages: Sequence, B: int, x_blobs: Optional[Sequence] = None,
+                             save_level: int = 0) -> None:
         """The backward stages of one step in ONE launch.  `stages` (latest stage first) =
         [(n_a, Combo in, t, g_base tensor or None, [(src, dp, dv), ...], gx_out tensor)], where `src` is the position of an
         earlier entry of `stages` whose gx_out feeds this stage's upstream gradient.  `x_blobs[i]`: device pointer of the
-        forward-saved input blob of entry i (`dopri5_attempt`), or None to rebuild it from (y0, a_j)."""
+        forward-saved buffer of entry i (`dopri5_attempt`, same `save_level`), or None to rebuild / recompute from (y0, a_j)."""
         n = len(stages)
         xs = list(x_blobs) if x_blobs is not None else [None] * n
         assert len(xs) == n
+        if any(x is not None for x in xs):
+            assert self.x_level in (0, save_level), "one save level per backward pass"
+            self.x_level = save_level
         if self.used + n * self.ntiles > self.nblobs:
             self.flush()
         descs = (StageDesc * n)()
@@ -376,7 +383,8 @@ class TcEngine:
                                                C.cast(n_g, C.c_void_p), C.cast(src, C.c_void_p), None, C.cast(dp, C.c_void_p),
                                                C.cast(dv, C.c_void_p), B, self.spill.data_ptr(), self.spill.numel(), self.used,
                                                self.nblobs, self.partial.data_ptr(),
-                                               C.cast((C.c_void_p * n)(*xs), C.c_void_p) if any(x is not None for x in xs) else None, _stream())
+                                               C.cast((C.c_void_p * n)(*xs), C.c_void_p) if any(x is not None for x in xs) else None,
+                                               int(save_level), _stream())
         _lib.check(rc, "ab200_stage_backward_fused")
         self.used += n * self.ntiles
         self.x_ring.extend(xs)
@@ -405,7 +413,8 @@ class TcEngine:
             nx = len(self.x_ring) if any(x is not None for x in self.x_ring) else 0
             rc = self.L.ab200_wgrad_accumulate(C.byref(self.desc), self.spill.data_ptr(), self.nblobs, self.used,
                                                self.partial.data_ptr(),
-                                               C.cast((C.c_void_p * nx)(*self.x_ring), C.c_void_p) if nx else None, nx, self.ntiles, _stream())
+                                               C.cast((C.c_void_p * nx)(*self.x_ring), C.c_void_p) if nx else None, nx, self.ntiles,
+                                               self.x_level, _stream())
             _lib.check(rc, "ab200_wgrad_accumulate")
             self.used = 0
             self.x_ring = []
@@ -504,10 +513,11 @@ def rk4_forward(eng: TcEngine, y0: torch.Tensor, t_host: Sequence[float], save_s
 
 
 def stages_backward(eng: TcEngine, tab: Tableau, B: int, yn, A: Sequence[torch.Tensor], stage_times: Sequence[float], dt: float,
-                    G_a_base: Sequence[Optional[torch.Tensor]], gx: Sequence[torch.Tensor], first: int, last: int, x_blobs=None):
+                    G_a_base: Sequence[Optional[torch.Tensor]], gx: Sequence[torch.Tensor], first: int, last: int, x_blobs=None,
+                    save_level: int = 0):
     """Backward of stages last..first of ONE explicit Runge-Kutta step in a single fused launch (latest stage first).
-    Returns the stage input combinations (their cpv feed `adjoint_gather`).  `x_blobs`: the step's forward-saved stage-input
-    blobs (uint8 tensor, stage i >= 1 at offset (i - 1) * xblob_bytes) or None."""
+    Returns the stage input combinations (their cpv feed `adjoint_gather`).  `x_blobs`: what the step's forward attempt saved
+    (tensor, stage i >= 1 at byte offset (i - 1) * xblob_bytes(B, save_level)) or None."""
     combos = [tab.stage_input(i, dt) for i in range(last + 1)]
     order = list(range(last, first - 1, -1))
     pos = {i: k for k, i in enumerate(order)}
@@ -517,9 +527,9 @@ def stages_backward(eng: TcEngine, tab: Tableau, B: int, yn, A: Sequence[torch.T
         stages.append((i, combos[i], stage_times[i], G_a_base[i], [(pos[l], combos[l].cpa[i], combos[l].cva[i]) for l in later], gx[i]))
     xs = None
     if x_blobs is not None:
-        per = eng.xblob_bytes(B)
+        per = eng.xblob_bytes(B, save_level)
         xs = [x_blobs.data_ptr() + (i - 1) * per if i >= 1 else None for i in order]
-    eng.stage_backward_fused(yn, list(A), stages, B, xs)
+    eng.stage_backward_fused(yn, list(A), stages, B, xs, save_level)
     return combos
 
 
@@ -566,7 +576,8 @@ class _Dopri5Step:
     t0: float
     dt: float
     outputs: List                    # [(row index k into y_path, x = (t_k - t0) / dt)]
-    x: Optional[torch.Tensor] = None # inputs of stages 2..7 as bf16 operand images (written by the forward attempt), or None
+    x: Optional[torch.Tensor] = None # what the forward attempt saved for the backward pass of stages 2..7 (operand images), or None
+    save_level: int = 0              # 1: stage inputs; 2: + hidden activations and ReLU masks
 
 
 class Dopri5Stats:
@@ -583,12 +594,16 @@ def _cast_time(v: float, time_dtype) -> float:
 def dopri5_forward(eng: TcEngine, y0: torch.Tensor, t_host: Sequence[float], rtol: float, atol: float, *, first_step=None,
                    safety: float = 0.9, ifactor: float = 10.0, dfactor: float = 0.2, max_num_steps: int = 2 ** 31 - 1,
                    time_dtype=torch.float64, save_steps: bool = False, stats: Optional[Dopri5Stats] = None, fp16_forward=None,
-                   forward_operands="fp16x2", error_norm: str = "shard", group=None):
+                   forward_operands="fp16x2", error_norm: str = "shard", group=None, saved_operands: str = "all"):
     """y0 row-major [B, D] -> y_path [T, B, D] (dense output at the requested times), and the accepted steps when
     `save_steps`.  One host read of the squared-error sum per attempted step decides accept / reject.
     error_norm="global": when agents are sharded over ranks, the squared-error sum and the element count are all-reduced
     (2 doubles per attempt) so that every rank takes the step sequence a single process would take on the whole batch --
-    torchdiffeq's RMS norm runs over ALL agents; "shard" uses the local agents only."""
+    torchdiffeq's RMS norm runs over ALL agents; "shard" uses the local agents only.
+    saved_operands (training forward in the split-activation format): what an accepted attempt keeps for the backward pass
+    besides (y, a_j): "all" = stage inputs, hidden activations and ReLU masks as the backward kernels' operand images (1,712 B per
+    agent-evaluation; the backward kernel recomputes nothing and (y, a_j) of the step are NOT kept), "inputs" = stage inputs only
+    (352 B), "none" = nothing (the backward pass rebuilds and recomputes from (y, a_j))."""
     import torch.distributed as dist
     use_global = error_norm == "global" and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
     n_elems = torch.tensor([float(y0.shape[0] * y0.shape[1])], dtype=torch.float64, device=y0.device)
@@ -659,8 +674,15 @@ def dopri5_forward(eng: TcEngine, y0: torch.Tensor, t_host: Sequence[float], rto
     # A training forward in the split-activation format also keeps every stage INPUT of the accepted steps as the bf16 operand
     # image of the backward kernels (352 B per agent-stage): the backward pass is bound by its HBM traffic, and loading that
     # image replaces re-reading y0 and up to six a_j (1.5 KB) and spilling it for the weight-gradient kernel.
-    xb_floats = eng.xblob_bytes(B) * 6 // 4 if (save_steps and eng.fwd_format == 2) else 0
+    save_level = SAVE_LEVELS[saved_operands] if (save_steps and eng.fwd_format == 2) else 0
+    xb_floats = eng.xblob_bytes(B, save_level) * 6 // 4 if save_level else 0
     x_cur = torch.empty(xb_floats, dtype=torch.float32, device=dev) if xb_floats else None
+    # level 2: the backward pass never reads (y, a_j) of a step (only y of the very first one, which lives outside the sets), so
+    # the attempts rotate through THREE buffer sets: the dense-output rows of step n are launched after attempt n + 1 and read
+    # y / a_1 = a_7 of step n - 1 and a_2..a_7 of step n; set (n mod 3) is next written by attempt n + 3.
+    sets, ci = None, 0
+    if save_level == 2:
+        sets = [(y_next, A[1:])] + [(blocked_zeros(B, D, dev), [blocked_zeros(B, P, dev) for _ in range(6)]) for _ in range(2)]
     while k < T:
         # ---- one attempted step from t1 with size dt
         assert n_steps < max_num_steps, "max_num_steps exceeded ({}>={})".format(n_steps, max_num_steps)
@@ -671,7 +693,7 @@ def dopri5_forward(eng: TcEngine, y0: torch.Tensor, t_host: Sequence[float], rto
         if slot == 0 and n_steps > 0:
             pool.zero_()
         sumsq = pool[slot:slot + 1]
-        eng.dopri5_attempt(y_cur, A, ta, dt, B, y_next, sumsq, rtol, atol, x_cur)
+        eng.dopri5_attempt(y_cur, A, ta, dt, B, y_next, sumsq, rtol, atol, x_cur, save_level)
         stats.n_evals += 6
         flush_rows()
         if use_global:
@@ -690,12 +712,18 @@ def dopri5_forward(eng: TcEngine, y0: torch.Tensor, t_host: Sequence[float], rto
             if save_steps:
                 if outs:
                     pending = (y_cur, A, dt, outs)
-                steps.append(_Dopri5Step(y_cur, A, ta, dt, outs, x_cur))
-                n_state = Bp * (D + 6 * P)
-                buf = torch.empty(n_state + xb_floats, dtype=torch.float32, device=dev)  # y_next + a_2..a_7 (+ X blobs) of the next step
-                y_cur, y_next = y_next, buf[:Bp * D]
-                A = [A[6]] + [buf[Bp * (D + i * P):Bp * (D + (i + 1) * P)] for i in range(6)]
-                x_cur = buf[n_state:] if xb_floats else None
+                steps.append(_Dopri5Step(y_cur, A, ta, dt, outs, x_cur, save_level))
+                if save_level == 2:
+                    ci = (ci + 1) % 3
+                    y_cur, y_next = y_next, sets[ci][0]
+                    A = [A[6]] + sets[ci][1]
+                    x_cur = torch.empty(xb_floats, dtype=torch.float32, device=dev)
+                else:
+                    n_state = Bp * (D + 6 * P)
+                    buf = torch.empty(n_state + xb_floats, dtype=torch.float32, device=dev)  # y_next + a_2..a_7 (+ X blobs) of the next step
+                    y_cur, y_next = y_next, buf[:Bp * D]
+                    A = [A[6]] + [buf[Bp * (D + i * P):Bp * (D + (i + 1) * P)] for i in range(6)]
+                    x_cur = buf[n_state:] if xb_floats else None
             else:
                 if outs:       # buffers are recycled by the next attempt: every requested time inside (t, t + dt] now
                     eng.dopri5_dense_rows(y_cur, A, dt, [x for _, x in outs], B, [y_path[kk] for kk, _ in outs])
@@ -750,7 +778,7 @@ def dopri5_backward(eng: TcEngine, steps: List[_Dopri5Step], grad_y_path: torch.
         first = 0 if si == 0 else 1                                # k_1 of a later step belongs to the previous step
         combos = [DOPRI5.stage_input(i, dt) for i in range(7)]
         times = [st.t0 + DOPRI5.c[i] * dt for i in range(7)]
-        stages_backward(eng, DOPRI5, B, st.yb, st.A, times, dt, G_a, gx, first, last, st.x)
+        stages_backward(eng, DOPRI5, B, st.yb, st.A, times, dt, G_a, gx, first, last, st.x, st.save_level)
         used = list(range(first, last + 1))
         if first == 1:      # one pass: dL/dy0 of the step and the gradient handed to the previous step's FSAL evaluation
             lam_a = lam_a_buf[si % 2]

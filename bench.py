@@ -119,7 +119,7 @@ def make_inputs(cfg, seed=42, device="cpu"):
     return home, work, traits, t
 
 
-def build_model(cfg, precision, device):
+def build_model(cfg, precision, device, saved_operands="all"):
     """GAT-ODE: zone tables from the graph-attention layers, drift net + fused solver, random init (seed 42)."""
     import ananke_abm_b200 as ab
     from ananke_abm_b200.graph import synthetic_zone_graph
@@ -130,6 +130,7 @@ def build_model(cfg, precision, device):
     mc.adjoint = bool(cfg.get("adjoint", False))
     mc.adjoint_mode = "discrete"             # c5: the odeint_adjoint seam with the explicit discrete-adjoint opt-in (tensor-core stage path)
     mc.error_norm = "global"                 # N > 1: one RMS error norm over all ranks' agents, as a single process would use
+    mc.saved_operands = saved_operands
     model = ab.GATODEModel(7, mc, heads=cfg["heads"]).to(device)
     ei, feats = synthetic_zone_graph(cfg["Z"], k=6, seed=42)
     csr = ab.build_zone_csr(ei, cfg["Z"]).to(device)
@@ -162,7 +163,7 @@ class _TrajectoryLoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, go):
         (y_path,) = ctx.saved_tensors
-        return y_path * (go * (2.0 / ctx.n))
+        return y_path * (float(go) * (2.0 / ctx.n))      # host scalar: the vectorised kernel (a 0-dim CUDA operand takes the strided one)
 
 
 def _config_for(args):
@@ -212,7 +213,7 @@ def run_ours(args):
     # badly utilised tail chunk; the saved steps of ONE chunk live in HBM (peak_mem_gb in the JSON line)
     n_parts = max(1, -(-B // args.chunk))
     chunk = min(B, -(-(-(-B // n_parts)) // 128) * 128)
-    model, zfeat, csr = build_model(cfg, args.precision, dev)
+    model, zfeat, csr = build_model(cfg, args.precision, dev, args.saved_operands)
     pin = lambda x: x.pin_memory()   # noqa: E731
     h_home, h_work, h_traits, h_t = pin(home), pin(work), pin(traits), pin(t)
     d_home, d_work, d_traits, d_t = (x.to(dev) for x in (home, work, traits, t))
@@ -437,7 +438,8 @@ def run_ours(args):
         # many solver steps the adaptive controller needed
         "agent_days_per_s": B_total * args.steps / (ms * 1e-3),
         "config": {"workload": cfg["name"], "agents_total": B_total, "agents_per_gpu": B, "zones": cfg["Z"], "time_points": T,
-                   "solver": cfg["method"], "agent_chunk": chunk, "precision": args.precision, "loss": (args.loss if train else None),
+                   "solver": cfg["method"], "agent_chunk": chunk, "saved_operands": (args.saved_operands if (train and cfg["method"] == "dopri5" and args.precision == "bf16") else None),
+                   "precision": args.precision, "loss": (args.loss if train else None),
                    "solver_steps": ({"accepted_per_trajectory": acc_per, "rejected_per_trajectory": rej_per,
                                      "fp32_accepted_per_trajectory": fp32_accepted,
                                      "accepted_steps_vs_fp32": (acc_per / fp32_accepted if fp32_accepted else None),
@@ -590,9 +592,14 @@ def main():
     ap.add_argument("--ref-agents", type=int, default=0,
                     help="agents in the reference arms' / cpu_baseline's slice (default 10,000 on the CPU, 32,768 on the GPU)")
     ap.add_argument("--agents", type=int, default=0, help="override agents per GPU")
-    ap.add_argument("--chunk", type=int, default=378_880,
+    ap.add_argument("--chunk", type=int, default=265_216,
                     help="upper bound on agents per launch sequence (the batch is cut into equal parts no larger than this); "
-                         "378,880 = 10 x (148 SMs x 2 slots x 128 agents); dopri5 training keeps ~0.33 MB per agent of the chunk")
+                         "265,216 = 7 x (148 SMs x 2 slots x 128 agents); dopri5 training with --saved-operands all keeps ~0.44 MB "
+                         "per agent of the chunk (30 accepted steps x 10.3 KB + the 97-row trajectory and its gradient)")
+    ap.add_argument("--saved-operands", default="all", choices=["all", "inputs", "none"],
+                    help="dopri5 training: what an accepted attempt's forward launch keeps for the backward pass as operand images "
+                         "(all: stage inputs + hidden activations + ReLU masks, the backward kernel recomputes nothing; inputs: "
+                         "stage inputs only; none: the backward pass rebuilds everything from (y, a_j))")
     ap.add_argument("--solver", default="", choices=["", "rk4", "dopri5"], help="override the workload's solver")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--loss", default="traj", choices=["traj", "ce"],

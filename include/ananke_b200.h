@@ -212,12 +212,16 @@ int ab200_stage_forward_fused(const ab200_drift_desc* d, const void* image, cons
  * the caller's interpreter costs more than a forward launch over a 100k-agent shard takes. */
 int ab200_dopri5_attempt(const ab200_drift_desc* d, const void* image, const float* y0, float* const* a, double t0, double dt,
                          int64_t B, float* y_out, double* err_sumsq, float rtol, float atol, int32_t operand_format, void* x_blobs,
-                         ab200_stream_t stream);
-/* `x_blobs` (operand_format 2 only; NULL = not wanted): 6 * ab200_stage_xblob_bytes(d, B) bytes that receive the input of each
- * of the six evaluations of the attempt as the bf16 operand image the backward kernels consume (stage i -> x_blobs + (i - 1) *
- * ab200_stage_xblob_bytes).  A training step keeps it with the step's a_j and hands it to ab200_stage_backward_fused /
- * ab200_wgrad_accumulate, which then neither rebuild the stage inputs from (y0, a_j) nor spill them. */
-size_t ab200_stage_xblob_bytes(const ab200_drift_desc* d, int64_t B);
+                         int32_t save_level, ab200_stream_t stream);
+/* `x_blobs` (operand_format 2 only; NULL = not wanted): 6 * ab200_stage_xblob_bytes(d, B, save_level) bytes that receive, for each
+ * of the six evaluations of the attempt (stage i -> x_blobs + (i - 1) * ab200_stage_xblob_bytes), what the backward pass would
+ * otherwise recompute, as the bf16 operand images its kernels consume:
+ *   save_level 1: the stage input (352 B per agent-stage);
+ *   save_level 2: + the five hidden activations and their ReLU masks (1,712 B per agent-stage).
+ * A training step keeps the buffer of an ACCEPTED attempt and hands it to ab200_stage_backward_fused / ab200_wgrad_accumulate
+ * with the same save_level: at level 1 the backward kernel loads the stage input instead of rebuilding it from (y0, a_j); at
+ * level 2 it recomputes nothing (no stage input, no forward GEMMs, no activation spills) and reads neither y0 nor a. */
+size_t ab200_stage_xblob_bytes(const ab200_drift_desc* d, int64_t B, int32_t save_level);
 /* The dense-output rows of an accepted dopri5 step at relative positions x[q] = (t_q - t0) / dt in (0, 1] (tdq interp.py
  * `_interp_fit` / `_interp_evaluate`: the quartic through y0, y1, y_mid, f0, f1, expanded over the seven stage derivatives):
  * out_rowmajor[q] (row-major [B][D]) for q < n_rows, all in one pass over (y0, a[0..6]). */
@@ -254,10 +258,11 @@ int ab200_stage_backward_fused(const ab200_drift_desc* d, const void* image, con
                                const ab200_stage_desc* stages, int32_t n_stage, const float* const* g_base,
                                float* const* gx_out, const int32_t* n_g, const int32_t* gx_src, const float* const* gx_ext,
                                const float* dp_host, const float* dv_host, int64_t B, void* spill, size_t spill_bytes,
-                               int32_t blob0, int32_t nblobs, void* partial, const void* const* x_blobs, ab200_stream_t stream);
-/* x_blobs: NULL, or a host array of n_stage device pointers; entry s non-NULL = the forward-saved input blob of that stage
- * (ab200_dopri5_attempt): it is loaded instead of rebuilt, and the X part of that stage's spill blobs is NOT written (pass the
- * same pointers to ab200_wgrad_accumulate). */
+                               int32_t blob0, int32_t nblobs, void* partial, const void* const* x_blobs, int32_t save_level,
+                               ab200_stream_t stream);
+/* x_blobs: NULL, or a host array of n_stage device pointers; entry s non-NULL = what the forward launch saved for that stage
+ * (ab200_dopri5_attempt, same save_level): it is loaded instead of rebuilt / recomputed, and the corresponding parts of that
+ * stage's spill blobs are NOT written (pass the same pointers and level to ab200_wgrad_accumulate). */
 /* ab200_adjoint_gather and ab200_stage_upstream over the same gx list in ONE pass (each gx is read once):
  *     out = base + sum_l [...]  and  g_a_out = g_base + sum_l dp[l] gx[l].p + dv[l] gx[l].v   (dp/dv may be 0 for some l). */
 int ab200_adjoint_gather_upstream(const ab200_drift_desc* d, const float* base, const float* const* gx, int32_t n,
@@ -276,9 +281,10 @@ int ab200_pv_combine_backward_multi(const ab200_drift_desc* d, const float* cons
 int ab200_stage_upstream(const ab200_drift_desc* d, const float* g_base, const float* const* gx, int32_t n_g,
                          const float* dp_host, const float* dv_host, int64_t B, float* g_a_out, ab200_stream_t stream);
 int ab200_wgrad_accumulate(const ab200_drift_desc* d, const void* spill, int32_t nblobs, int32_t used, void* partial,
-                           const void* const* x_blobs, int32_t n_x_blobs, int32_t ntiles, ab200_stream_t stream);
-/* x_blobs (n_x_blobs <= 8 host entries, one per run of `ntiles` consecutive blobs; NULL entry / n_x_blobs 0 = read the X part
- * from `spill`): forward-saved input blobs of the stages whose blobs occupy [k * ntiles, (k + 1) * ntiles). */
+                           const void* const* x_blobs, int32_t n_x_blobs, int32_t ntiles, int32_t save_level,
+                           ab200_stream_t stream);
+/* x_blobs (n_x_blobs <= 8 host entries, one per run of `ntiles` consecutive blobs; NULL entry / n_x_blobs 0 = read the layer
+ * inputs from `spill`): forward-saved buffers of the stages whose blobs occupy [k * ntiles, (k + 1) * ntiles). */
 int ab200_wgrad_finalize(const ab200_drift_desc* d, const void* partial, float* grad_w_flat, ab200_stream_t stream);
 /* 1 if any tensor-core kernel that used `image` / `partial` hit its bounded mbarrier wait (a bug, never expected) */
 int ab200_stage_status_offset(const ab200_drift_desc* d, int64_t* image_status_byte, int64_t* partial_status_byte);

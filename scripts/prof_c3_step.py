@@ -1,5 +1,5 @@
 """One configs[2] training step (GAT zone tables -> initial state -> dopri5 rtol=atol=1e-5 forward -> trajectory loss -> discrete
-adjoint) over ONE chunk of agents, for ncu launch lists / captures.  usage: python scripts/prof_c3_step.py [B] [reps]"""
+adjoint) over ONE chunk of agents, for ncu launch lists / captures.  usage: python scripts/prof_c3_step.py [B] [reps] [all|inputs|none]"""
 import sys, time, torch
 sys.path.insert(0, '.')
 import bench
@@ -8,12 +8,20 @@ import importlib
 oi = importlib.import_module("ananke_abm_b200.odeint")
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 333440
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+saved = sys.argv[3] if len(sys.argv) > 3 else "all"
+kineto = len(sys.argv) > 4 and sys.argv[4] == "kineto"      # per-kernel durations of the LAST repetition through CUPTI (warm caches, unlike ncu)
 dev = torch.device('cuda:0')
 cfg = dict(bench.WORKLOADS["c3"], B=B)
 model, zfeat, csr = bench.build_model(cfg, "bf16", dev)
+model.config.saved_operands = saved
 home, work, traits, t = (x.to(dev) for x in bench.make_inputs(cfg, seed=42))
 params = list(model.parameters())
+prof = None
 for it in range(reps):
+    if kineto and it == reps - 1:
+        from torch.profiler import profile, ProfilerActivity
+        prof = profile(activities=[ProfilerActivity.CUDA])
+        prof.__enter__()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for p in params:
@@ -25,6 +33,13 @@ for it in range(reps):
     loss.backward()
     torch.cuda.synchronize()
     st = oi._LAST["solver"]
-    print(f"rep {it}: {1e3 * (time.perf_counter() - t0):.1f} ms, accepted {st.n_accepted} rejected {st.n_rejected}, loss {float(loss):.6g}")
+    print(f"rep {it} [{saved}]: {1e3 * (time.perf_counter() - t0):.1f} ms, peak {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB, accepted {st.n_accepted} rejected {st.n_rejected}, loss {float(loss):.6g}")
     del y_path, loss
+if prof is not None:
+    prof.__exit__(None, None, None)
+    rows = sorted(((e.key, e.count, e.device_time_total) for e in prof.key_averages() if e.device_time_total > 0), key=lambda r: -r[2])
+    tot = sum(r[2] for r in rows)
+    print(f"kernel time of the last repetition: {tot / 1e3:.1f} ms")
+    for k, n, us in rows[:16]:
+        print(f"  {100 * us / tot:5.1f} %  {us / 1e3:8.2f} ms  {n:4d} x {us / n:8.1f} us  {k[:90]}")
 print("ok")

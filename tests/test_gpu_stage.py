@@ -312,10 +312,12 @@ def test_full_chunk_properties_dopri5():
 
 
 @pytest.mark.parametrize("B", [129, 1000])
-def test_forward_saved_stage_inputs_equal_rebuilt_ones(B):
-    """The split-activation forward writes every stage input of an accepted step as the bf16 operand image of the backward
-    kernels (ab200_dopri5_attempt `x_blobs`); the backward pass that LOADS those images and the one that REBUILDS them from
-    (y0, a_j) must see the same bf16 numbers: dL/dy0 bit-identical, dL/dW equal up to the order of the atomic partial sums."""
+def test_forward_saved_operands_vs_recomputed_ones(B):
+    """A training forward in the split-activation format saves, per evaluation of an accepted step, what the backward pass would
+    recompute (ab200_dopri5_attempt `x_blobs` / `save_level`).  "inputs": the stage input as a bf16 operand image -- the same bf16
+    numbers the backward kernel rebuilds from (y0, a_j): dL/dy0 bit-identical, dL/dW equal up to the order of the atomic partial
+    sums.  "all": also the hidden activations and ReLU masks, taken from the fp32-class forward instead of a bf16 recompute: the
+    gradients agree to bf16 accuracy."""
     import ananke_abm_b200 as ab
     from ananke_abm_b200 import stage
     dev = _cuda()
@@ -326,17 +328,23 @@ def test_forward_saved_stage_inputs_equal_rebuilt_ones(B):
     spec = ab.describe_drift(model.odefunc)
     eng = stage.TcEngine(spec, spec.flat_params().detach())
     t = [0.0, 1.5, 3.0, 6.0]
-    y_path, steps, _ = stage.dopri5_forward(eng, y0, t, 1e-4, 1e-4, save_steps=True)
-    assert all(s.x is not None for s in steps) and len(steps) >= 2
-    g = torch.randn(y_path.shape, device=dev, generator=torch.Generator(device=dev).manual_seed(5))
-    gy_a, gw_a = stage.dopri5_backward(eng, steps, g)
-    for s in steps:
-        s.x = None
-    gy_b, gw_b = stage.dopri5_backward(eng, steps, g)
-    torch.cuda.synchronize()
-    assert torch.equal(gy_a, gy_b)
-    assert _rel(gw_a, gw_b) < 1e-5, _rel(gw_a, gw_b)
-    # a single-term forward format has no blobs to offer and still trains
+    res = {}
+    for mode in ("none", "inputs", "all"):
+        y_path, steps, _ = stage.dopri5_forward(eng, y0, t, 1e-4, 1e-4, save_steps=True, saved_operands=mode)
+        assert len(steps) >= 2 and all((s.x is None) == (mode == "none") for s in steps)
+        g = torch.randn(y_path.shape, device=dev, generator=torch.Generator(device=dev).manual_seed(5))
+        gy, gw = stage.dopri5_backward(eng, steps, g)
+        torch.cuda.synchronize()
+        res[mode] = (y_path, gy, gw)
+    assert torch.equal(res["none"][0], res["inputs"][0]) and torch.equal(res["none"][0], res["all"][0])
+    assert torch.equal(res["none"][1], res["inputs"][1])
+    assert _rel(res["inputs"][2], res["none"][2]) < 1e-5
+    e_y, e_w = _rms(res["all"][1], res["none"][1]), _rms(res["all"][2], res["none"][2])
+    print(f"saved activations vs bf16 recompute: dL/dy0 rms {e_y:.2e}, dL/dW rms {e_w:.2e}")
+    # two approximations of the same gradient, each ~2e-2 (dL/dy0) / ~5e-3 (dL/dW) rms from the fp32 oracle
+    # (tests/test_gpu_dopri5_parity.py pins the default "all" against the oracle); measured here 1.8e-2 / 2.1e-2
+    assert e_y < 4e-2 and e_w < 4e-2, (e_y, e_w)
+    # a single-term forward format has nothing to offer and still trains
     y_path1, steps1, _ = stage.dopri5_forward(eng, y0, t, 1e-4, 1e-4, save_steps=True, forward_operands="fp16")
     assert all(s.x is None for s in steps1)
     gy_c, _ = stage.dopri5_backward(eng, steps1, g)
