@@ -119,6 +119,25 @@ def make_inputs(cfg, seed=42, device="cpu"):
     return home, work, traits, t
 
 
+def chunk_bounds(B, max_chunk, slots, tile=128):
+    """[(start, end)] covering B agents in ceil(B / max_chunk) parts whose sizes are whole waves of `slots` tiles (the last part
+    takes the remainder)"""
+    n_parts = max(1, -(-B // max_chunk))
+    tiles = -(-B // tile)
+    waves = -(-tiles // slots)
+    if n_parts == 1 or waves < n_parts:
+        per = -(-(-(-B // n_parts)) // tile) * tile
+        return [(s, min(B, s + per)) for s in range(0, B, per)]
+    out, s = [], 0
+    for i in range(n_parts):
+        w = waves // n_parts + (1 if i < waves % n_parts else 0)
+        e = B if i == n_parts - 1 else min(B, s + w * slots * tile)
+        if e > s:
+            out.append((s, e))
+        s = e
+    return out
+
+
 def build_model(cfg, precision, device, saved_operands="all"):
     """GAT-ODE: zone tables from the graph-attention layers, drift net + fused solver, random init (seed 42)."""
     import ananke_abm_b200 as ab
@@ -209,10 +228,11 @@ def run_ours(args):
         lo, hi = 0, cfg["B"]
         home, work, traits, t = make_inputs(cfg, seed=42 + rank)
     B = hi - lo
-    # agents are processed in equal chunks of at most --chunk agents (whole 128-agent tiles): equal parts avoid a small,
-    # badly utilised tail chunk; the saved steps of ONE chunk live in HBM (peak_mem_gb in the JSON line)
-    n_parts = max(1, -(-B // args.chunk))
-    chunk = min(B, -(-(-(-B // n_parts)) // 128) * 128)
+    # agents are processed in chunks of at most --chunk agents, cut at whole WAVES of the stage kernels (#SMs x 2 slots x 128
+    # agents): 1 M agents = 7,813 tiles = 26.4 waves run as 7 + 7 + 7 + 6 waves (four equal parts would each pay a partial wave);
+    # the saved steps of ONE chunk live in HBM (peak_mem_gb in the JSON line)
+    bounds = chunk_bounds(B, args.chunk, 2 * torch.cuda.get_device_properties(dev).multi_processor_count)
+    chunk = max(e - s for s, e in bounds)
     model, zfeat, csr = build_model(cfg, args.precision, dev, args.saved_operands)
     pin = lambda x: x.pin_memory()   # noqa: E731
     h_home, h_work, h_traits, h_t = pin(home), pin(work), pin(traits), pin(t)
@@ -242,8 +262,8 @@ def run_ours(args):
             with torch.no_grad():
                 acc = None
                 table, zemb = model.zone_tables(zfeat, csr)
-                for s in range(0, B, chunk):
-                    y0 = model.initial_state(table, zemb, hm[s:s + chunk], wk[s:s + chunk], tr[s:s + chunk])
+                for s, e in bounds:
+                    y0 = model.initial_state(table, zemb, hm[s:e], wk[s:e], tr[s:e])
                     y_path = model.integrate(y0, tt)
                     count(y0.shape[0])
                     acc = y_path[-1, :1, :1]
@@ -252,19 +272,19 @@ def run_ours(args):
         for p in params:
             p.grad = None
         total = None
-        for s in range(0, B, chunk):
+        for s, e in bounds:
             table, zemb = model.zone_tables(zfeat, csr)
-            y0 = model.initial_state(table, zemb, hm[s:s + chunk], wk[s:s + chunk], tr[s:s + chunk])
+            y0 = model.initial_state(table, zemb, hm[s:e], wk[s:e], tr[s:e])
             y_path = model.integrate(y0, tt)
             count(y0.shape[0])
             if args.loss == "ce":
                 # the reference's training loss at the ground-truth snaps (ce_at_snaps, losses.py:14-22): decoder + fused
                 # cross-entropy head at 12 of the 97 grid points (~12 GT snaps per agent-day)
                 pred_emb = model.decoder(y_path[snap_idx, :, :model.config.emb_dim])
-                rows = ab.head_ce_rows(pred_emb, table, snap_target[:, s:s + chunk], model.config.softmax_tau)
+                rows = ab.head_ce_rows(pred_emb, table, snap_target[:, s:e], model.config.softmax_tau)
                 loss = rows.sum() / (snap_idx.numel() * B_total)
             else:
-                loss = _TrajectoryLoss.apply(y_path) * ((min(B, s + chunk) - s) / B_total)
+                loss = _TrajectoryLoss.apply(y_path) * ((e - s) / B_total)
             loss.backward()
             total = loss.detach() if total is None else total + loss.detach()
             del y_path, loss
@@ -279,8 +299,8 @@ def run_ours(args):
             with torch.no_grad():
                 outs = []
                 table, zemb = model.zone_tables(zfeat, csr)
-                for s in range(0, B, chunk):
-                    y0 = model.initial_state(table, zemb, hm[s:s + chunk], wk[s:s + chunk], tr[s:s + chunk])
+                for s, e in bounds:
+                    y0 = model.initial_state(table, zemb, hm[s:e], wk[s:e], tr[s:e])
                     y_path = model.integrate(y0, tt)
                     count(y0.shape[0])
                     outs.append(labels_from_path(model, y_path, table).to(torch.int32))
@@ -438,7 +458,7 @@ def run_ours(args):
         # many solver steps the adaptive controller needed
         "agent_days_per_s": B_total * args.steps / (ms * 1e-3),
         "config": {"workload": cfg["name"], "agents_total": B_total, "agents_per_gpu": B, "zones": cfg["Z"], "time_points": T,
-                   "solver": cfg["method"], "agent_chunk": chunk, "saved_operands": (args.saved_operands if (train and cfg["method"] == "dopri5" and args.precision == "bf16") else None),
+                   "solver": cfg["method"], "agent_chunk": chunk, "agent_chunks": [e - s for s, e in bounds], "saved_operands": (args.saved_operands if (train and cfg["method"] == "dopri5" and args.precision == "bf16") else None),
                    "precision": args.precision, "loss": (args.loss if train else None),
                    "solver_steps": ({"accepted_per_trajectory": acc_per, "rejected_per_trajectory": rej_per,
                                      "fp32_accepted_per_trajectory": fp32_accepted,
