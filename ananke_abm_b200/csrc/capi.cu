@@ -56,13 +56,14 @@ int stage_bwd_tc(const ab200_drift_desc* d, const uint8_t* image, const float* y
                  int64_t B, const float* g_base, const float* const* gx_ptrs, int n_g, const float* dp, const float* dv, float* gx_out,
                  void* spill, int blob0, int nblobs, float* g_bout, cudaStream_t st);
 int pv_combine_bwd_multi(const ab200_drift_desc* d, const float* const* g, int n_src, const float* cpv, const float* cpa, const float* cva,
-                         int n_a, int64_t B, float* G_y0, float* const* G_a, int accumulate, cudaStream_t st);
+                         int n_a, int64_t B, float* G_y0, float* const* G_a, int accumulate, int rowmajor_mask, cudaStream_t st);
 int ga_assemble(const ab200_drift_desc* d, const float* base, const float* const* gx, int n, const float* dp, const float* dv,
                 int64_t B, float* out, cudaStream_t st);
 int stage_bwd_tc_multi(const ab200_drift_desc* d, const uint8_t* image, const float* y0, const float* const* a_ptrs,
                        const void* descs_v, int n_stage, const float* const* g_base, float* const* gx_out, const int32_t* n_g,
                        const int32_t* gx_src, const float* const* gx_ext, const float* dp, const float* dv, int64_t B, void* spill,
-                       int blob0, int nblobs, float* g_bout, const void* const* x1_in, int save_level, cudaStream_t st);
+                       int blob0, int nblobs, float* g_bout, const void* const* x1_in, int save_level, float* y0_acc,
+                       float* const* ga_out, cudaStream_t st);
 int adjoint_gather(const ab200_drift_desc* d, const float* base, const float* const* gx, int n, const float* cpv, int64_t B, float* out,
                    const float* ga_base, const float* dp, const float* dv, float* ga_out, cudaStream_t st);
 size_t wgrad_spill_bytes(int nblobs);
@@ -389,21 +390,23 @@ int ab200_stage_backward_fused(const ab200_drift_desc* d, const void* image, con
                                const ab200_stage_desc* stages, int32_t n_stage, const float* const* g_base, float* const* gx_out,
                                const int32_t* n_g, const int32_t* gx_src, const float* const* gx_ext, const float* dp_host,
                                const float* dv_host, int64_t B, void* spill, size_t spill_bytes, int32_t blob0, int32_t nblobs,
-                               void* partial, const void* const* x_blobs, int32_t save_level, ab200_stream_t stream) {
+                               void* partial, const void* const* x_blobs, int32_t save_level, float* y0_accum,
+                               float* const* upstream_out, ab200_stream_t stream) {
   if (!d || !image || !y0 || !a || !stages || !g_base || !gx_out || !n_g || !gx_src || !dp_host || !dv_host || !spill || !partial ||
-      B <= 0 || n_stage < 1 || n_stage > AB200_STAGE_MAX_A)
+      B <= 0 || n_stage < 1 || n_stage > AB200_STAGE_MAX_A + 1)
     return AB200_ERR_BAD_ARG;
   if (!stage_shape_ok(d)) return AB200_ERR_UNSUPPORTED;
   if (nblobs <= 0 || spill_bytes < wgrad_spill_bytes(nblobs)) return AB200_ERR_WORKSPACE;
   return stage_bwd_tc_multi(d, (const uint8_t*)image, y0, a, stages, n_stage, g_base, gx_out, n_g, gx_src, gx_ext, dp_host, dv_host, B,
-                            spill, blob0, nblobs, wgrad_bout_ptr(partial), x_blobs, x_blobs ? save_level : 0, (cudaStream_t)stream);
+                            spill, blob0, nblobs, wgrad_bout_ptr(partial), x_blobs, x_blobs ? save_level : 0, y0_accum, upstream_out,
+                            (cudaStream_t)stream);
 }
 
 int ab200_pv_combine_backward_multi(const ab200_drift_desc* d, const float* const* g, int32_t n_src, const float* cpv_host,
                                     const float* cpa_host, const float* cva_host, int32_t n_a, int64_t B, float* G_y0,
-                                    float* const* G_a, int32_t accumulate, ab200_stream_t stream) {
+                                    float* const* G_a, int32_t accumulate, int32_t rowmajor_mask, ab200_stream_t stream) {
   if (!desc_ok(d) || !g || !cpv_host || !G_y0 || B <= 0 || (n_a > 0 && (!G_a || !cpa_host || !cva_host))) return AB200_ERR_BAD_ARG;
-  return pv_combine_bwd_multi(d, g, n_src, cpv_host, cpa_host, cva_host, n_a, B, G_y0, G_a, accumulate, (cudaStream_t)stream);
+  return pv_combine_bwd_multi(d, g, n_src, cpv_host, cpa_host, cva_host, n_a, B, G_y0, G_a, accumulate, rowmajor_mask, (cudaStream_t)stream);
 }
 
 int ab200_stage_upstream(const ab200_drift_desc* d, const float* g_base, const float* const* gx, int32_t n_g, const float* dp_host,

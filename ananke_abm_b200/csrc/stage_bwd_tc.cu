@@ -43,6 +43,14 @@ struct BwdStageParams {       // one stage of a fused (latest-first) sequence
   int blob0;                  // blob index of tile 0 for this stage
   const uint8_t* x1_in;       // what the forward launch saved for this stage (wg::FwdSaveLayout) or null: rebuild the input from y0 / a_j
   int saved_acts;             // 1: x1_in also holds the hidden activations and the ReLU masks -> nothing is recomputed or re-spilled
+  // GATHER entry (gx_out == null; last of a launch; no GEMMs, no blobs): from the p / v / h parts of its sources' gx it writes
+  //   ga_out (if non-null, fp32 blocked [Bp][64]) = g_base + sum_l dp[l] gx_l.p + dv[l] gx_l.v     (the gradient handed to the FSAL
+  //                                                                                                evaluation of the previous step)
+  //   y0_acc (StageBwdArgs, if non-null)         += sum_l [gx_l.p ; cpv_src[l] gx_l.p + gx_l.v ; gx_l.h]     (dL/dy0 of the step)
+  // The sources were written by this same thread moments ago, so they are read from L2, not from DRAM.
+  int gather;
+  float* ga_out;
+  float cpv_src[MAX_A];
 };
 
 struct StageBwdArgs {
@@ -50,10 +58,11 @@ struct StageBwdArgs {
   const float* y0;            // blocked [Bp][160]
   const float* a[MAX_A];      // blocked [Bp][64]
   int n_stage;
-  BwdStageParams st[MAX_A];
+  BwdStageParams st[MAX_A + 1];
   float period;
   uint8_t* spill;             // blob buffer (SpillLayout)
   float* g_bout;              // [64] atomically accumulated column sums of dL/da_out (bias gradient of the output layer)
+  float* y0_acc;              // or null: blocked [Bp][160], updated in place by the gather entry
   int64_t B;
   int ntiles;
   int nblobs;                 // blobs the spill buffer was sized for
@@ -130,6 +139,37 @@ __device__ __forceinline__ void bwd_bwd_epi(const SlotCtx& c, uint32_t (&gs)[32]
   }
 }
 
+// dL/da_out of a stage for this thread's 32 columns: g_base + sum_l dp[l] gx_l.p + dv[l] gx_l.v
+__device__ __forceinline__ void upstream_gather(const BwdStageParams& sp, int tile, const SlotCtx& c, float (&gv)[32]) {
+  // all loads of one source are issued before any is consumed: a later stage's gx usually comes from L2, and a
+  // load -> FMA -> load chain per float4 (as a naive loop nest gives) exposes that latency 8 x n_g times per tile
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (sp.g_base != nullptr) x = ldro(blk4(sp.g_base, tile, AF4, c.hf * 8 + j, c.row));     // padding rows are zero
+    gv[4 * j] = x.x; gv[4 * j + 1] = x.y; gv[4 * j + 2] = x.z; gv[4 * j + 3] = x.w;
+  }
+#pragma unroll 1
+  for (int s = 0; s < sp.n_g; ++s) {
+    const float dp = sp.dp[s], dv = sp.dv[s];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      float4 gp[4], gq[4];     // coherent loads: an earlier stage of THIS launch (same thread) may have written these
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        gp[j] = *blk4(sp.gx[s], tile, YF4, c.hf * 8 + half * 4 + j, c.row);
+        gq[j] = *blk4(sp.gx[s], tile, YF4, AF4 + c.hf * 8 + half * 4 + j, c.row);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int b = (half * 4 + j) * 4;
+        gv[b] += dp * gp[j].x + dv * gq[j].x; gv[b + 1] += dp * gp[j].y + dv * gq[j].y;
+        gv[b + 2] += dp * gp[j].z + dv * gq[j].z; gv[b + 3] += dp * gp[j].w + dv * gq[j].w;
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(THREADS, 1) stage_bwd_tc_kernel(const __grid_constant__ StageBwdArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bars[NSLOT + 1];
@@ -152,6 +192,71 @@ __global__ void __launch_bounds__(THREADS, 1) stage_bwd_tc_kernel(const __grid_c
     const BwdStageParams& sp = a.st[si];
     const int blob = sp.blob0 + tile;
     STAGE_TRACE(c, 9);
+    if (sp.gather) {
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {      // 16 of this thread's 32 columns of p and of v per pass (register budget)
+        const int f0 = c.hf * 8 + half * 4;
+        float xa[16], xp[16], xv[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float4 b = make_float4(0.f, 0.f, 0.f, 0.f), p = b, v = b;
+          if (sp.g_base != nullptr && sp.ga_out != nullptr) b = ldro(blk4(sp.g_base, tile, AF4, f0 + j, c.row));
+          if (a.y0_acc != nullptr) { p = *blk4(a.y0_acc, tile, YF4, f0 + j, c.row); v = *blk4(a.y0_acc, tile, YF4, AF4 + f0 + j, c.row); }
+          xa[4 * j] = b.x; xa[4 * j + 1] = b.y; xa[4 * j + 2] = b.z; xa[4 * j + 3] = b.w;
+          xp[4 * j] = p.x; xp[4 * j + 1] = p.y; xp[4 * j + 2] = p.z; xp[4 * j + 3] = p.w;
+          xv[4 * j] = v.x; xv[4 * j + 1] = v.y; xv[4 * j + 2] = v.z; xv[4 * j + 3] = v.w;
+        }
+#pragma unroll 1
+        for (int s = 0; s < sp.n_g; ++s) {
+          const float dp = sp.dp[s], dv = sp.dv[s], cs = sp.cpv_src[s];
+          float4 gp[4], gq[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            gp[j] = *blk4(sp.gx[s], tile, YF4, f0 + j, c.row);
+            gq[j] = *blk4(sp.gx[s], tile, YF4, AF4 + f0 + j, c.row);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float pe[4] = {gp[j].x, gp[j].y, gp[j].z, gp[j].w}, ve[4] = {gq[j].x, gq[j].y, gq[j].z, gq[j].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              xa[4 * j + e] += dp * pe[e] + dv * ve[e];
+              xp[4 * j + e] += pe[e];
+              xv[4 * j + e] += cs * pe[e] + ve[e];
+            }
+          }
+        }
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (sp.ga_out != nullptr)
+              *blk4(sp.ga_out, tile, AF4, f0 + j, c.row) = make_float4(xa[4 * j], xa[4 * j + 1], xa[4 * j + 2], xa[4 * j + 3]);
+            if (a.y0_acc != nullptr) {
+              *blk4(a.y0_acc, tile, YF4, f0 + j, c.row) = make_float4(xp[4 * j], xp[4 * j + 1], xp[4 * j + 2], xp[4 * j + 3]);
+              *blk4(a.y0_acc, tile, YF4, AF4 + f0 + j, c.row) = make_float4(xv[4 * j], xv[4 * j + 1], xv[4 * j + 2], xv[4 * j + 3]);
+            }
+          }
+        }
+      }
+      if (a.y0_acc != nullptr) {      // context part: 16 of 32 columns per thread
+        float4 xh[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) xh[j] = *blk4(a.y0_acc, tile, YF4, 2 * AF4 + c.hf * 4 + j, c.row);
+#pragma unroll 1
+        for (int s = 0; s < sp.n_g; ++s) {
+          float4 g[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) g[j] = *blk4(sp.gx[s], tile, YF4, 2 * AF4 + c.hf * 4 + j, c.row);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { xh[j].x += g[j].x; xh[j].y += g[j].y; xh[j].z += g[j].z; xh[j].w += g[j].w; }
+        }
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) *blk4(a.y0_acc, tile, YF4, 2 * AF4 + c.hf * 4 + j, c.row) = xh[j];
+        }
+      }
+      continue;
+    }
 
     uint32_t z[32];
     uint32_t m_z0[2], m_u0[2], m_z1[2], m_u1[2], m_z2[2];
@@ -266,33 +371,7 @@ __global__ void __launch_bounds__(THREADS, 1) stage_bwd_tc_kernel(const __grid_c
     {
       uint32_t o[16];
       float gv[32];
-      // all loads of one source are issued before any is consumed: a later stage's gx usually comes from L2, and a
-      // load -> FMA -> load chain per float4 (as a naive loop nest gives) exposes that latency 8 x n_g times per tile
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (sp.g_base != nullptr) x = ldro(blk4(sp.g_base, tile, AF4, c.hf * 8 + j, c.row));     // padding rows are zero
-        gv[4 * j] = x.x; gv[4 * j + 1] = x.y; gv[4 * j + 2] = x.z; gv[4 * j + 3] = x.w;
-      }
-#pragma unroll 1
-      for (int s = 0; s < sp.n_g; ++s) {
-        const float dp = sp.dp[s], dv = sp.dv[s];
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          float4 gp[4], gq[4];     // coherent loads: an earlier stage of THIS launch (same thread) may have written these
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            gp[j] = *blk4(sp.gx[s], tile, YF4, c.hf * 8 + half * 4 + j, c.row);
-            gq[j] = *blk4(sp.gx[s], tile, YF4, AF4 + c.hf * 8 + half * 4 + j, c.row);
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int b = (half * 4 + j) * 4;
-            gv[b] += dp * gp[j].x + dv * gq[j].x; gv[b + 1] += dp * gp[j].y + dv * gq[j].y;
-            gv[b + 2] += dp * gp[j].z + dv * gq[j].z; gv[b + 3] += dp * gp[j].w + dv * gq[j].w;
-          }
-        }
-      }
+      upstream_gather(sp, tile, c, gv);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         o[2 * j] = pack_bf16(gv[4 * j], gv[4 * j + 1]);
@@ -384,9 +463,10 @@ static_assert(sizeof(StageBwdHost) == sizeof(ab200_stage_desc), "stage descripto
 int stage_bwd_tc_multi(const ab200_drift_desc* d, const uint8_t* image, const float* y0, const float* const* a_ptrs,
                        const void* descs_v, int n_stage, const float* const* g_base, float* const* gx_out, const int32_t* n_g,
                        const int32_t* gx_src, const float* const* gx_ext, const float* dp, const float* dv, int64_t B, void* spill,
-                       int blob0, int nblobs, float* g_bout, const void* const* x1_in, int save_level, cudaStream_t st) {
+                       int blob0, int nblobs, float* g_bout, const void* const* x1_in, int save_level, float* y0_acc,
+                       float* const* ga_out, cudaStream_t st) {
   const StageBwdHost* hs = reinterpret_cast<const StageBwdHost*>(descs_v);
-  if (n_stage < 1 || n_stage > MAX_A) return AB200_ERR_BAD_ARG;
+  if (n_stage < 1 || n_stage > MAX_A + 1) return AB200_ERR_BAD_ARG;
   StageBwdArgs k{};
   k.wimg = image;
   k.y0 = y0;
@@ -394,7 +474,11 @@ int stage_bwd_tc_multi(const ab200_drift_desc* d, const uint8_t* image, const fl
   int max_a = 0;
   for (int s = 0; s < n_stage; ++s) {
     const StageBwdHost& h = hs[s];
-    if (h.n_a < 0 || h.n_a > MAX_A || n_g[s] < 0 || n_g[s] > MAX_A || !gx_out[s]) return AB200_ERR_BAD_ARG;
+    const bool gather = gx_out[s] == nullptr;      // the gather entry comes last and writes no blobs
+    float* ga = (gather && ga_out != nullptr) ? ga_out[s] : nullptr;
+    if (gather && (s != n_stage - 1 || s == 0 || (ga == nullptr && y0_acc == nullptr))) return AB200_ERR_BAD_ARG;
+    if (!gather && s >= MAX_A) return AB200_ERR_BAD_ARG;
+    if (h.n_a < 0 || h.n_a > MAX_A || n_g[s] < 0 || n_g[s] > MAX_A) return AB200_ERR_BAD_ARG;
     if (n_g[s] == 0 && !g_base[s]) return AB200_ERR_BAD_ARG;
     max_a = h.n_a > max_a ? h.n_a : max_a;
     BwdStageParams& sp = k.st[s];
@@ -407,21 +491,28 @@ int stage_bwd_tc_multi(const ab200_drift_desc* d, const uint8_t* image, const fl
     for (int l = 0; l < n_g[s]; ++l) {
       const int src = gx_src[s * MAX_A + l];
       if (src >= s) return AB200_ERR_BAD_ARG;                      // only stages processed earlier in this sequence
+      if (gather && src < 0) return AB200_ERR_BAD_ARG;            // a gather entry folds stages of its own launch
       sp.gx[l] = src >= 0 ? gx_out[src] : gx_ext[-1 - src];
+      sp.cpv_src[l] = src >= 0 ? hs[src].in_cpv : 0.f;
       sp.dp[l] = dp[s * MAX_A + l];
       sp.dv[l] = dv[s * MAX_A + l];
     }
     sp.gx_out = gx_out[s];
+    sp.gather = gather ? 1 : 0;
+    sp.ga_out = ga;
     sp.blob0 = blob0 + s * k.ntiles;
     sp.x1_in = x1_in ? (const uint8_t*)x1_in[s] : nullptr;
     sp.saved_acts = (sp.x1_in != nullptr && save_level >= 2) ? 1 : 0;
   }
-  if (blob0 < 0 || blob0 + n_stage * k.ntiles > nblobs) return AB200_ERR_BAD_ARG;
+  const int n_real = n_stage - (gx_out[n_stage - 1] == nullptr ? 1 : 0);
+  if (y0_acc != nullptr && n_real == n_stage) return AB200_ERR_BAD_ARG;      // y0_accum is the gather entry's job
+  if (blob0 < 0 || blob0 + n_real * k.ntiles > nblobs) return AB200_ERR_BAD_ARG;
   for (int i = 0; i < MAX_A; ++i) k.a[i] = (i < max_a) ? a_ptrs[i] : nullptr;
   k.n_stage = n_stage;
   k.period = d->time_period;
   k.spill = (uint8_t*)spill;
   k.g_bout = g_bout;
+  k.y0_acc = y0_acc;
   k.B = B;
   k.nblobs = nblobs;
   k.flags = stage_flags();
@@ -446,7 +537,7 @@ int stage_bwd_tc(const ab200_drift_desc* d, const uint8_t* image, const float* y
   int32_t src[MAX_A];
   float dpa[MAX_A], dva[MAX_A];
   for (int l = 0; l < MAX_A; ++l) { src[l] = -1 - l; dpa[l] = l < n_g ? dp[l] : 0.f; dva[l] = l < n_g ? dv[l] : 0.f; }
-  return stage_bwd_tc_multi(d, image, y0, a_ptrs, desc_v, 1, gb, go, ng, src, gx_ptrs, dpa, dva, B, spill, blob0, nblobs, g_bout, nullptr, 0, st);
+  return stage_bwd_tc_multi(d, image, y0, a_ptrs, desc_v, 1, gb, go, ng, src, gx_ptrs, dpa, dva, B, spill, blob0, nblobs, g_bout, nullptr, 0, nullptr, nullptr, st);
 }
 
 }  // namespace ab200

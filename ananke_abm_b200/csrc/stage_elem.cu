@@ -107,14 +107,24 @@ __global__ void __launch_bounds__(256) pv_combine_bwd_kernel(const __grid_consta
 //   G_y0.p (+)= sum_i g_i.p ; G_y0.v (+)= sum_i cpv_i g_i.p + g_i.v ; G_y0.h (+)= sum_i g_i.h ; G_a[j] (+)= sum_i cpa_i[j] g_i.p + cva_i[j] g_i.v
 // (the end state of a dopri5 step and every dense-output row inside it; one read-modify-write of the accumulators
 // instead of one per output)
-constexpr int EL_MAX_SRC = 4;
+constexpr int EL_MAX_SRC = 6;
 struct MultiBwdArgs {
   const float* g[EL_MAX_SRC];
   float cpv[EL_MAX_SRC], cpa[EL_MAX_SRC][EL_MAX_A], cva[EL_MAX_SRC][EL_MAX_A];
   float* G_y0;
   float* G_a[EL_MAX_A];
   int n_src, n_a, accumulate, ntiles, P, H;
+  int rowmajor_mask;      // bit s: source s is a ROW-MAJOR [B][D] row of the caller's gradient tensor (read in place: no transposed copy)
+  int64_t B;
 };
+// float4 `f4` (of Y4 per agent) of agent (tile, row) from a blocked or a row-major source; row-major rows beyond B read as zero
+__device__ __forceinline__ float4 src_f4(const float* g, bool rowmajor, int tile, int row, int f4, int Y4, int64_t B) {
+  if (!rowmajor) return (reinterpret_cast<const float4*>(g) + (size_t)tile * Y4 * EL_TM + row)[(size_t)f4 * EL_TM];
+  const int64_t agent = (int64_t)tile * EL_TM + row;
+  if (agent >= B) return make_float4(0.f, 0.f, 0.f, 0.f);
+  return __ldcs(reinterpret_cast<const float4*>(g) + agent * Y4 + f4);      // 16 B of a 640-byte row per lane: the neighbouring lanes of
+                                                                            // the other feature groups pick the rest of the sector up from L2
+}
 __global__ void __launch_bounds__(256) pv_combine_bwd_multi_kernel(const __grid_constant__ MultiBwdArgs a) {
   const int P4 = a.P / 4, H4 = a.H / 4, Y4 = 2 * P4 + H4;
   const int64_t n = (int64_t)a.ntiles * (P4 + H4) * EL_TM;
@@ -130,7 +140,7 @@ __global__ void __launch_bounds__(256) pv_combine_bwd_multi_kernel(const __grid_
 #pragma unroll
       for (int s = 0; s < EL_MAX_SRC; ++s)
         if (s < a.n_src) {
-          const float4 g = (reinterpret_cast<const float4*>(a.g[s]) + t0)[f];
+          const float4 g = src_f4(a.g[s], (a.rowmajor_mask >> s) & 1, tile, row, 2 * P4 + (grp - P4), Y4, a.B);
           x.x += g.x; x.y += g.y; x.z += g.z; x.w += g.w;
         }
       o4[f] = x;
@@ -141,9 +151,9 @@ __global__ void __launch_bounds__(256) pv_combine_bwd_multi_kernel(const __grid_
 #pragma unroll
     for (int s = 0; s < EL_MAX_SRC; ++s)
       if (s < a.n_src) {
-        const float4* g4 = reinterpret_cast<const float4*>(a.g[s]) + t0;
-        gp[s] = g4[fp];
-        gv[s] = g4[fv];
+        const bool rm = (a.rowmajor_mask >> s) & 1;
+        gp[s] = src_f4(a.g[s], rm, tile, row, grp, Y4, a.B);
+        gv[s] = src_f4(a.g[s], rm, tile, row, P4 + grp, Y4, a.B);
       }
     float4 xp = acc ? o4[fp] : make_float4(0.f, 0.f, 0.f, 0.f), xv = acc ? o4[fv] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -480,10 +490,11 @@ int adjoint_gather(const ab200_drift_desc* d, const float* base, const float* co
 }
 
 int pv_combine_bwd_multi(const ab200_drift_desc* d, const float* const* g, int n_src, const float* cpv, const float* cpa, const float* cva,
-                         int n_a, int64_t B, float* G_y0, float* const* G_a, int accumulate, cudaStream_t st) {
+                         int n_a, int64_t B, float* G_y0, float* const* G_a, int accumulate, int rowmajor_mask, cudaStream_t st) {
   if (n_src < 1 || n_src > EL_MAX_SRC || n_a < 0 || n_a > EL_MAX_A || d->pos_dim % 4 || d->ctx_dim % 4) return AB200_ERR_BAD_ARG;
   MultiBwdArgs k{};
   k.G_y0 = G_y0; k.n_src = n_src; k.n_a = n_a; k.accumulate = accumulate; k.P = d->pos_dim; k.H = d->ctx_dim;
+  k.rowmajor_mask = rowmajor_mask; k.B = B;
   k.ntiles = (int)((B + EL_TM - 1) / EL_TM);
   for (int s = 0; s < n_src; ++s) {
     k.g[s] = g[s];

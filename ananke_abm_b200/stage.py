@@ -315,11 +315,17 @@ class TcEngine:
         self.x_ring.append(None)
 
     def combine_backward_multi(self, sources: Sequence, B: int, G_y0, G_a: Sequence[torch.Tensor], accumulate: bool) -> None:
-        """`sources` = [(g blocked tensor, Combo), ...]: all folded into G_y0 / G_a in passes of up to 4 sources."""
+        """`sources` = [(g, Combo), ...]: all folded into G_y0 / G_a in passes of up to 6 sources.  g is a blocked tensor, or a
+        contiguous ROW-MAJOR [B, D] row of the caller's gradient tensor (2-D: read in place, no transposed copy)."""
         n_a = len(G_a)
-        for s0 in range(0, len(sources), 4):
-            grp = sources[s0:s0 + 4]
+        for s0 in range(0, len(sources), 6):
+            grp = sources[s0:s0 + 6]
             n = len(grp)
+            rm_mask = 0
+            for i, (g, _) in enumerate(grp):
+                if g.dim() == 2:
+                    assert g.is_contiguous() and g.shape == (B, self.D) and g.dtype == torch.float32
+                    rm_mask |= 1 << i
             gp = (C.c_void_p * n)(*[g.data_ptr() for g, _ in grp])
             cpv = (C.c_float * n)(*[float(c.cpv) for _, c in grp])
             cpa = (C.c_float * (n * 8))()
@@ -330,7 +336,8 @@ class TcEngine:
                     cva[i * 8 + j] = float(c.cva[j])
             rc = self.L.ab200_pv_combine_backward_multi(C.byref(self.desc), C.cast(gp, C.c_void_p), n, C.cast(cpv, C.c_void_p),
                                                         C.cast(cpa, C.c_void_p), C.cast(cva, C.c_void_p), n_a, B, G_y0.data_ptr(),
-                                                        C.cast(_ptr_array(G_a), C.c_void_p), 1 if (accumulate or s0 > 0) else 0, _stream())
+                                                        C.cast(_ptr_array(G_a), C.c_void_p), 1 if (accumulate or s0 > 0) else 0, rm_mask,
+                                                        _stream())
             _lib.check(rc, "ab200_pv_combine_backward_multi")
 
     def stage_upstream(self, g_base, gx: Sequence[torch.Tensor], dp: Sequence[float], dv: Sequence[float], B: int, out) -> None:
@@ -343,22 +350,33 @@ class TcEngine:
         _lib.check(rc, "ab200_stage_upstream")
 
     def stage_backward_fused(self, y0, a_bufs: Sequence[torch.Tensor], stages: Sequence, B: int, x_blobs: Optional[Sequence] = None,
-                             save_level: int = 0) -> None:
+                             save_level: int = 0, y0_accum=None, upstream=None) -> None:
         """The backward stages of one step in ONE launch.  `stages` (latest stage first) =
         [(n_a, Combo in, t, g_base tensor or None, [(src, dp, dv), ...], gx_out tensor)], where `src` is the position of an
         earlier entry of `stages` whose gx_out feeds this stage's upstream gradient.  `x_blobs[i]`: device pointer of the
-        forward-saved buffer of entry i (`dopri5_attempt`, same `save_level`), or None to rebuild / recompute from (y0, a_j)."""
+        forward-saved buffer of entry i (`dopri5_attempt`, same `save_level`), or None to rebuild / recompute from (y0, a_j).
+        `y0_accum` (blocked [Bp, D], initialised with the step-level dL/dy0) and / or `upstream` = (g_base, [(dp, dv)] per entry
+        of `stages`, out) add one GATHER entry to the launch: it folds every stage's gx into dL/dy0 (in place, no `adjoint_gather`
+        pass) and writes g_base + sum dp gx.p + dv gx.v to `out` (the gradient of the previous step's FSAL evaluation)."""
+        n_real = len(stages)
+        if upstream is not None or y0_accum is not None:
+            coef = upstream[1] if upstream is not None else [(0.0, 0.0)] * n_real
+            stages = list(stages) + [(0, Combo(0.0, [], []), 0.0, upstream[0] if upstream is not None else None,
+                                      [(i, dp_, dv_) for i, (dp_, dv_) in enumerate(coef)], None)]
         n = len(stages)
-        xs = list(x_blobs) if x_blobs is not None else [None] * n
+        xs = (list(x_blobs) if x_blobs is not None else [None] * n_real) + [None] * (n - n_real)
         assert len(xs) == n
         if any(x is not None for x in xs):
             assert self.x_level in (0, save_level), "one save level per backward pass"
             self.x_level = save_level
-        if self.used + n * self.ntiles > self.nblobs:
+        if self.used + n_real * self.ntiles > self.nblobs:
             self.flush()
         descs = (StageDesc * n)()
         g_base = (C.c_void_p * n)()
         gx_out = (C.c_void_p * n)()
+        up_out = (C.c_void_p * n)()
+        if upstream is not None:
+            up_out[n - 1] = upstream[2].data_ptr()
         n_g = (C.c_int32 * n)()
         src = (C.c_int32 * (n * MAX_A))()
         dp = (C.c_float * (n * MAX_A))()
@@ -371,7 +389,7 @@ class TcEngine:
             _fill(s.in_cva, cin.cva[:n_a])
             s.t = float(t)
             g_base[i] = None if gb is None else gb.data_ptr()
-            gx_out[i] = gout.data_ptr()
+            gx_out[i] = None if gout is None else gout.data_ptr()
             n_g[i] = len(sources)
             for l, (sidx, a_, b_) in enumerate(sources):
                 src[i * MAX_A + l] = sidx
@@ -384,10 +402,11 @@ class TcEngine:
                                                C.cast(dv, C.c_void_p), B, self.spill.data_ptr(), self.spill.numel(), self.used,
                                                self.nblobs, self.partial.data_ptr(),
                                                C.cast((C.c_void_p * n)(*xs), C.c_void_p) if any(x is not None for x in xs) else None,
-                                               int(save_level), _stream())
+                                               int(save_level), None if y0_accum is None else y0_accum.data_ptr(),
+                                               C.cast(up_out, C.c_void_p) if upstream is not None else None, _stream())
         _lib.check(rc, "ab200_stage_backward_fused")
-        self.used += n * self.ntiles
-        self.x_ring.extend(xs)
+        self.used += n_real * self.ntiles
+        self.x_ring.extend(xs[:n_real])
 
     def adjoint_gather_upstream(self, base, gx: Sequence[torch.Tensor], cpv: Sequence[float], B: int, out, g_base,
                                 dp: Sequence[float], dv: Sequence[float], g_a_out) -> None:
@@ -514,10 +533,12 @@ def rk4_forward(eng: TcEngine, y0: torch.Tensor, t_host: Sequence[float], save_s
 
 def stages_backward(eng: TcEngine, tab: Tableau, B: int, yn, A: Sequence[torch.Tensor], stage_times: Sequence[float], dt: float,
                     G_a_base: Sequence[Optional[torch.Tensor]], gx: Sequence[torch.Tensor], first: int, last: int, x_blobs=None,
-                    save_level: int = 0):
+                    save_level: int = 0, y0_accum=None, fsal_out=None):
     """Backward of stages last..first of ONE explicit Runge-Kutta step in a single fused launch (latest stage first).
     Returns the stage input combinations (their cpv feed `adjoint_gather`).  `x_blobs`: what the step's forward attempt saved
-    (tensor, stage i >= 1 at byte offset (i - 1) * xblob_bytes(B, save_level)) or None."""
+    (tensor, stage i >= 1 at byte offset (i - 1) * xblob_bytes(B, save_level)) or None.  `y0_accum`: see `stage_backward_fused`.
+    `fsal_out` (first >= 1): receives dL/da_1 = G_a_base[0] + the contributions of stages first..last -- the gradient w.r.t. the
+    evaluation this step took over from the previous one (FSAL)."""
     combos = [tab.stage_input(i, dt) for i in range(last + 1)]
     order = list(range(last, first - 1, -1))
     pos = {i: k for k, i in enumerate(order)}
@@ -529,7 +550,11 @@ def stages_backward(eng: TcEngine, tab: Tableau, B: int, yn, A: Sequence[torch.T
     if x_blobs is not None:
         per = eng.xblob_bytes(B, save_level)
         xs = [x_blobs.data_ptr() + (i - 1) * per if i >= 1 else None for i in order]
-    eng.stage_backward_fused(yn, list(A), stages, B, xs, save_level)
+    upstream = None
+    if fsal_out is not None:
+        assert first >= 1
+        upstream = (G_a_base[0], [(combos[l].cpa[0], combos[l].cva[0]) for l in order], fsal_out)
+    eng.stage_backward_fused(yn, list(A), stages, B, xs, save_level, y0_accum, upstream)
     return combos
 
 
@@ -754,23 +779,20 @@ def dopri5_backward(eng: TcEngine, steps: List[_Dopri5Step], grad_y_path: torch.
     P = eng.P
     eng.backward_begin(B, stages_per_flush=7)
     lam = blocked_zeros(B, D, dev)          # dL/dy at the end of the step being processed
-    lam_prev = blocked_zeros(B, D, dev)
     lam_a = None                            # dL/da_7 handed over by the following step (None: nothing depends on it)
     lam_a_buf = [blocked_zeros(B, P, dev) for _ in range(2)]
     G_y0 = blocked_zeros(B, D, dev)
     G_a = [blocked_zeros(B, P, dev) for _ in range(7)]
     gx = [blocked_zeros(B, D, dev) for _ in range(7)]
-    g_blk = [blocked_zeros(B, D, dev)]
+    grad_rows = grad_y_path if (grad_y_path.is_contiguous() and grad_y_path.dtype == torch.float32) else grad_y_path.contiguous().float()
     for si in range(len(steps) - 1, -1, -1):
         st = steps[si]
         dt = st.dt
-        # step-level gradients: the end state y1 = y0 + dt sum c_sol k, and every dense-output row inside the step
+        # step-level gradients: the end state y1 = y0 + dt sum c_sol k, and every dense-output row inside the step (the rows of
+        # dL/dy_path are read in place, row-major)
         sources = [(lam, DOPRI5.combo(DOPRI5.b, dt))]
-        for n_o, (k, x) in enumerate(st.outputs):
-            if n_o >= len(g_blk):
-                g_blk.append(blocked_zeros(B, D, dev))
-            rows_block(grad_y_path[k], g_blk[n_o])
-            sources.append((g_blk[n_o], DOPRI5.combo(dopri5_interp_weights(x), dt)))
+        for (k, x) in st.outputs:
+            sources.append((grad_rows[k], DOPRI5.combo(dopri5_interp_weights(x), dt)))
         eng.combine_backward_multi(sources, B, G_y0, G_a, accumulate=False)
         if lam_a is not None:
             G_a[6].add_(lam_a)
@@ -778,16 +800,14 @@ def dopri5_backward(eng: TcEngine, steps: List[_Dopri5Step], grad_y_path: torch.
         first = 0 if si == 0 else 1                                # k_1 of a later step belongs to the previous step
         combos = [DOPRI5.stage_input(i, dt) for i in range(7)]
         times = [st.t0 + DOPRI5.c[i] * dt for i in range(7)]
-        stages_backward(eng, DOPRI5, B, st.yb, st.A, times, dt, G_a, gx, first, last, st.x, st.save_level)
-        used = list(range(first, last + 1))
-        if first == 1:      # one pass: dL/dy0 of the step and the gradient handed to the previous step's FSAL evaluation
-            lam_a = lam_a_buf[si % 2]
-            eng.adjoint_gather_upstream(G_y0, [gx[i] for i in used], [combos[i].cpv for i in used], B, lam_prev, G_a[0],
-                                        [combos[i].cpa[0] for i in used], [combos[i].cva[0] for i in used], lam_a)
-        else:
-            eng.adjoint_gather(G_y0, [gx[i] for i in used], [combos[i].cpv for i in used], B, lam_prev)
+        # the stage kernel adds every stage's contribution to dL/dy0 into G_y0 itself and, as one more entry of the same launch,
+        # assembles the gradient handed to the previous step's FSAL evaluation: no gather pass over the six gx buffers
+        lam_a_next = lam_a_buf[si % 2] if first == 1 else None
+        stages_backward(eng, DOPRI5, B, st.yb, st.A, times, dt, G_a, gx, first, last, st.x, st.save_level, y0_accum=G_y0,
+                        fsal_out=lam_a_next)
+        lam_a = lam_a_next
         eng.flush()
-        lam, lam_prev = lam_prev, lam
+        lam, G_y0 = G_y0, lam
     rows_block(grad_y_path[0], lam, accumulate=True)
     gw = eng.backward_end()
     return rows_unblock(lam, B, D), gw

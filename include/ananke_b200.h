@@ -259,7 +259,14 @@ int ab200_stage_backward_fused(const ab200_drift_desc* d, const void* image, con
                                float* const* gx_out, const int32_t* n_g, const int32_t* gx_src, const float* const* gx_ext,
                                const float* dp_host, const float* dv_host, int64_t B, void* spill, size_t spill_bytes,
                                int32_t blob0, int32_t nblobs, void* partial, const void* const* x_blobs, int32_t save_level,
-                               ab200_stream_t stream);
+                               float* y0_accum, float* const* upstream_out, ab200_stream_t stream);
+/* GATHER entry: when gx_out[n_stage - 1] is NULL the last entry (allowed on top of AB200_STAGE_MAX_A stages) runs no network
+ * backward and writes no blobs (it does not count towards blob indices); from the gx of its sources -- entries of this call --
+ *   upstream_out[n_stage - 1] (if upstream_out and that entry are non-NULL; fp32 blocked [Bp][P])
+ *        = g_base + sum_l dp[l] gx_l.p + dv[l] gx_l.v        (e.g. the gradient handed to the FSAL evaluation of the previous step)
+ *   y0_accum (if non-NULL; blocked [Bp][D], initialised by the caller with the step-level dL/dy0), in place
+ *       += sum_l [gx_l.p ; in_cpv_l gx_l.p + gx_l.v ; gx_l.h]                   (what ab200_adjoint_gather does in a pass of its own)
+ * while those gx tiles are still in L2.  y0_accum / upstream_out are ignored (must be NULL) without a gather entry. */
 /* x_blobs: NULL, or a host array of n_stage device pointers; entry s non-NULL = what the forward launch saved for that stage
  * (ab200_dopri5_attempt, same save_level): it is loaded instead of rebuilt / recomputed, and the corresponding parts of that
  * stage's spill blobs are NOT written (pass the same pointers and level to ab200_wgrad_accumulate). */
@@ -268,12 +275,13 @@ int ab200_stage_backward_fused(const ab200_drift_desc* d, const void* image, con
 int ab200_adjoint_gather_upstream(const ab200_drift_desc* d, const float* base, const float* const* gx, int32_t n,
                                   const float* cpv_host, int64_t B, float* out, const float* g_base, const float* dp_host,
                                   const float* dv_host, float* g_a_out, ab200_stream_t stream);
-/* ab200_pv_combine_backward for up to 4 linear outputs of the same step in ONE pass (source i: gradient g[i], blocked
- * [Bp][D], and its combination cpv[i], cpa[i * 8 + j], cva[i * 8 + j], j < n_a): the accumulators are written once
- * instead of once per output (a dopri5 step's end state plus the dense-output rows that fall inside it). */
+/* ab200_pv_combine_backward for up to 6 linear outputs of the same step in ONE pass (source i: gradient g[i] and its
+ * combination cpv[i], cpa[i * 8 + j], cva[i * 8 + j], j < n_a): the accumulators are written once instead of once per output
+ * (a dopri5 step's end state plus the dense-output rows that fall inside it).  Source i is blocked [Bp][D], or -- bit i of
+ * rowmajor_mask set -- a ROW-MAJOR [B][D] row of the caller's own gradient tensor (dL/dy_path[k]), read in place. */
 int ab200_pv_combine_backward_multi(const ab200_drift_desc* d, const float* const* g, int32_t n_src, const float* cpv_host,
                                     const float* cpa_host, const float* cva_host, int32_t n_a, int64_t B, float* G_y0,
-                                    float* const* G_a, int32_t accumulate, ab200_stream_t stream);
+                                    float* const* G_a, int32_t accumulate, int32_t rowmajor_mask, ab200_stream_t stream);
 /* The upstream gradient of a stage written out as a buffer instead of being consumed by ab200_stage_backward:
  *     g_a_out (blocked [Bp][P]) = g_base + sum_l dp[l] gx[l].p + dv[l] gx[l].v
  * dopri5's first stage of a step IS the last (FSAL) evaluation of the previous step (tdq rk_common.py _adaptive_step:
