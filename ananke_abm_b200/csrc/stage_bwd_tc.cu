@@ -73,7 +73,6 @@ struct StageBwdArgs {
 // store packed pairs as feature groups of a blob: NG groups starting at fg0, row = agent
 template <int NG>
 __device__ __forceinline__ void spill_groups(uint8_t* blob, int fg0, int row, const uint32_t* o) {
-#pragma unroll
   if (blob == nullptr) return;     // AB200_STAGE_FLAGS bit 16: timing experiment without the blob spill
 #pragma unroll
   for (int q = 0; q < NG; ++q)

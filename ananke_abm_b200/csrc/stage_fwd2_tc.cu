@@ -114,9 +114,9 @@ static __device__ __noinline__ void issue_mmas2(uint32_t acc, uint32_t a0, uint6
   mma_commit(bar);
 }
 
-// ACC[region d_reg][128 x N] = A(region a_reg) * W^T (K-major image at w_off, N_IMG rows)
-template <int NKS, bool HPART, int N_IMG, int N>
-__device__ __forceinline__ void run_layer2(SlotCtx& c, uint32_t a_reg, uint32_t d_reg, uint32_t w_off) {
+// ACC[region d_reg][128 x N] = A(region a_reg) * W^T (K-major image at w_off, N_IMG rows); `after_issue`: see run_layer (stage_tc.cuh)
+template <int NKS, bool HPART, int N_IMG, int N, class Hook = NoHook>
+__device__ __forceinline__ void run_layer2(SlotCtx& c, uint32_t a_reg, uint32_t d_reg, uint32_t w_off, Hook after_issue = Hook()) {
   STAGE_TRACE(c, 1);
   tmem_st_wait();
   tc_fence_before();
@@ -134,6 +134,7 @@ __device__ __forceinline__ void run_layer2(SlotCtx& c, uint32_t a_reg, uint32_t 
   }
   STAGE_TRACE(c, 4);
   __syncwarp();
+  after_issue();
   if (c.alive && !wait_mma(c.bar, c.phase)) { c.alive = false; *c.status = 1; }
   c.phase ^= 1;
   __syncwarp();
@@ -143,14 +144,8 @@ __device__ __forceinline__ void run_layer2(SlotCtx& c, uint32_t a_reg, uint32_t 
 
 // Hidden-layer epilogue on this thread's 64 columns (hf * 64 ..) of region `reg`, in place:
 //   x = acc + bias [+ z] ;  x = relu(x) ;  [z = x] ;  columns <- (hi pairs | lo pairs) per 16-feature group
-// SAVE: the activation also goes out as the bf16 blob of the weight-gradient kernel (`blob` = this tile's blob + row * 16) and
-// its ReLU mask as two words (`mask_out`, the bit layout of stage_bwd_tc.cu): the backward pass then has nothing to recompute.
-// (The fp16 hi words that are already at hand cannot be used: tcgen05.mma kind::f16 with an fp16 A next to a bf16 B operand is
-// an illegal instruction on sm_100a -- tried, profiles/r02_stage_source_stalls.txt.)
-template <bool RES, bool KEEP, bool SAVE>
-__device__ __forceinline__ void epi2(const SlotCtx& c, uint32_t reg, const float* __restrict__ bias, float (&z)[64], uint8_t* blob,
-                                     uint2* mask_out) {
-  uint32_t mw[2] = {0u, 0u};
+template <bool RES, bool KEEP>
+__device__ __forceinline__ void epi2(const SlotCtx& c, uint32_t reg, const float* __restrict__ bias, float (&z)[64]) {
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const int col = c.hf * 64 + q * 16;
@@ -158,8 +153,6 @@ __device__ __forceinline__ void epi2(const SlotCtx& c, uint32_t reg, const float
     tmem_ld16(c.tmem + c.lane_sel + reg + (uint32_t)col, r);
     tmem_ld_wait();
     uint32_t o[16];
-    uint32_t w[8];
-    uint32_t m = 0u;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float2 b2 = *reinterpret_cast<const float2*>(bias + col + 2 * j);      // same address for the whole warp: broadcast
@@ -170,19 +163,69 @@ __device__ __forceinline__ void epi2(const SlotCtx& c, uint32_t reg, const float
       const uint32_t hi = pack2<true>(x0, x1);
       o[j] = hi;
       o[8 + j] = pack2<true>(x0 - un_lo<true>(hi), x1 - un_hi<true>(hi));
-      if (SAVE) {      // post-ReLU halves are >= +0: adding 0x7FFF sets bit 15 / 31 iff the low / high half is non-zero (no carry across)
-        w[j] = pack_bf16(x0, x1);
-        m |= ((w[j] + 0x7FFF7FFFu) >> ((q & 1) * 8 + j)) & (0x80008000u >> ((q & 1) * 8 + j));
-      }
     }
     tmem_st16(c.tmem + c.lane_sel + reg + (uint32_t)col, o);
-    if (SAVE) mw[q >> 1] |= m;
-    if (SAVE && blob != nullptr) {
-      __stcs(reinterpret_cast<uint4*>(blob + (size_t)(c.hf * 8 + q * 2) * wg::FG_BYTES), make_uint4(w[0], w[1], w[2], w[3]));
-      __stcs(reinterpret_cast<uint4*>(blob + (size_t)(c.hf * 8 + q * 2 + 1) * wg::FG_BYTES), make_uint4(w[4], w[5], w[6], w[7]));
+  }
+}
+
+// Saving for the backward pass (SAVE_ACTS kernels), executed while the tensor core runs the layer that CONSUMES the operand: the
+// hi words of this thread's 64 columns of region `reg` (fp16 pairs; the lo words only matter below bf16 resolution) are read back
+// from tensor memory, converted to the bf16 blob of the weight-gradient kernel (`blob` = this tile's blob + row * 16; a mixed
+// fp16 x bf16 tcgen05.mma is an illegal instruction on sm_100a, so the conversion cannot be skipped) and their non-zero pattern
+// goes out as the ReLU mask (two words, the bit layout of stage_bwd_tc.cu).  In the epilogue itself the same work lengthened the
+// slot's critical path by a third (profiles/r02_stage_source_stalls.txt).
+__device__ __forceinline__ void save_hidden(const SlotCtx& c, uint32_t reg, uint8_t* blob, uint2* mask_out) {
+  uint32_t mw[2] = {0u, 0u};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint32_t r[8];
+    tmem_ld8(c.tmem + c.lane_sel + reg + (uint32_t)(c.hf * 64 + q * 16), r);
+    tmem_ld_wait();
+    uint32_t w[8];
+    uint32_t m = 0u;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      w[j] = pack_bf16(un_lo<true>(r[j]), un_hi<true>(r[j]));
+      // post-ReLU halves are >= +0: adding 0x7FFF sets bit 15 / 31 iff the low / high half is non-zero (no carry across)
+      m |= ((r[j] + 0x7FFF7FFFu) >> ((q & 1) * 8 + j)) & (0x80008000u >> ((q & 1) * 8 + j));
+    }
+    mw[q >> 1] |= m;
+    __stcs(reinterpret_cast<uint4*>(blob + (size_t)(c.hf * 8 + q * 2) * wg::FG_BYTES), make_uint4(w[0], w[1], w[2], w[3]));
+    __stcs(reinterpret_cast<uint4*>(blob + (size_t)(c.hf * 8 + q * 2 + 1) * wg::FG_BYTES), make_uint4(w[4], w[5], w[6], w[7]));
+  }
+  __stcs(mask_out, make_uint2(mw[0], mw[1]));
+}
+
+// the same for the stage input (operand of layer 1): p / v hi words from region X, h hi words from this slot's shared-memory
+// tile, the time-feature group.  Feature groups: p 4 hf + {0..3}, v 8 + 4 hf + {0..3}, h 16 + 2 hf + {0, 1}, [sin, cos, 1, 0..] 20, zeros 21
+__device__ __forceinline__ void save_input(const SlotCtx& c, uint8_t* xb, const uint8_t* htile, float t, float period) {
+  auto cvt4 = [](uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3) {
+    return make_uint4(pack_bf16(un_lo<true>(a0), un_hi<true>(a0)), pack_bf16(un_lo<true>(a1), un_hi<true>(a1)),
+                      pack_bf16(un_lo<true>(a2), un_hi<true>(a2)), pack_bf16(un_lo<true>(a3), un_hi<true>(a3)));
+  };
+#pragma unroll
+  for (int pv = 0; pv < 2; ++pv) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      uint32_t r[8];
+      tmem_ld8(c.tmem + c.lane_sel + f2::RX + (uint32_t)(pv * P + c.hf * 32 + q * 16), r);
+      tmem_ld_wait();
+      uint8_t* g0 = xb + (size_t)(pv * (P / 8) + c.hf * 4 + q * 2) * wg::FG_BYTES;
+      __stcs(reinterpret_cast<uint4*>(g0), cvt4(r[0], r[1], r[2], r[3]));
+      __stcs(reinterpret_cast<uint4*>(g0 + wg::FG_BYTES), cvt4(r[4], r[5], r[6], r[7]));
     }
   }
-  if (SAVE && mask_out != nullptr) __stcs(mask_out, make_uint2(mw[0], mw[1]));
+#pragma unroll
+  for (int kc = 0; kc < 2; ++kc) {
+    const uint4 v = *reinterpret_cast<const uint4*>(htile + off_kmajor_noswz(c.row, c.hf * 16 + kc * 8, f2::HT_LBO, SBO));
+    __stcs(reinterpret_cast<uint4*>(xb + (size_t)(2 * P / 8 + c.hf * 2 + kc) * wg::FG_BYTES), cvt4(v.x, v.y, v.z, v.w));
+  }
+  if (c.hf == 0) {
+    float sn, co;
+    time_features(t, period, sn, co);
+    __stcs(reinterpret_cast<uint4*>(xb + (size_t)((2 * P + H) / 8) * wg::FG_BYTES), make_uint4(pack_bf16(sn, co), pack_bf16(1.0f, 0.0f), 0u, 0u));
+    __stcs(reinterpret_cast<uint4*>(xb + (size_t)((2 * P + H) / 8 + 1) * wg::FG_BYTES), make_uint4(0u, 0u, 0u, 0u));
+  }
 }
 
 // 16 features -> (8 hi columns | 8 lo columns) at tensor-memory column `col` of this thread's lane; `xg` != null: they also go
@@ -299,7 +342,8 @@ __global__ void __launch_bounds__(THREADS, 1) stage_fwd2_tc_kernel(const __grid_
         // the recompute A operand): written here it costs 352 B per agent-stage of a launch that uses little of the DRAM bandwidth,
         // and saves the backward kernel re-reading y0 and up to six a_j (1.5 KB) and spilling the blob.
         // Feature groups: p 4 hf + {0..3}, v 8 + 4 hf + {0..3}, h 16 + 2 hf + {0, 1}, [sin, cos, 1, 0..] 20, zeros 21.
-        uint8_t* xb = (sp.x1_out != nullptr && !(c.flags & 64)) ? sp.x1_out + (size_t)tile * wg::X1_BYTES + (size_t)c.row * 16 : nullptr;
+        // (SAVE_ACTS kernels write it after the issue of layer 1 instead, from the operand itself: save_input)
+        uint8_t* xb = (!SAVE_ACTS && sp.x1_out != nullptr) ? sp.x1_out + (size_t)tile * wg::X1_BYTES + (size_t)c.row * 16 : nullptr;
         auto grp = [&](int g) -> uint8_t* { return xb ? xb + (size_t)g * wg::FG_BYTES : nullptr; };
         st_split16(c, f2::RX + (uint32_t)(c.hf * 32), pin, grp(c.hf * 4));
         st_split16(c, f2::RX + (uint32_t)(c.hf * 32 + 16), pin + 16, grp(c.hf * 4 + 2));
@@ -331,22 +375,26 @@ __global__ void __launch_bounds__(THREADS, 1) stage_fwd2_tc_kernel(const __grid_
       // ---- drift net (regions alternate: X -> Y -> X -> Y -> X -> Y -> X)
       float z[64];
       const wg::FwdSaveLayout FS{a.ntiles};      // SAVE_ACTS launches save every stage (the host checks x1_out != null)
-      const bool no_store = (c.flags & 64) != 0;      // timing experiment only (results invalid): everything but the stores
-      auto act_blob = [&](int l) -> uint8_t* { return (SAVE_ACTS && !no_store) ? sp.x1_out + FS.act(l, tile) + (size_t)c.row * 16 : nullptr; };
-      auto mask_at = [&](int l) -> uint2* {
-        return (SAVE_ACTS && !no_store) ? reinterpret_cast<uint2*>(sp.x1_out + FS.mask(tile)) + (l * 2 * TM + c.hf * TM + c.row) : nullptr;
+      const bool save = SAVE_ACTS && !(c.flags & 64);      // flag 64: timing experiment without the saving work (results invalid)
+      auto hidden_hook = [&](int l, uint32_t reg) {
+        return [=, &c]() {
+          if (save) save_hidden(c, reg, sp.x1_out + FS.act(l, tile) + (size_t)c.row * 16,
+                                reinterpret_cast<uint2*>(sp.x1_out + FS.mask(tile)) + (l * 2 * TM + c.hf * TM + c.row));
+        };
       };
-      run_layer2<2 * P / 16, true, HID, HID>(c, f2::RX, f2::RY, f2::OFF_W1);
-      epi2<false, true, SAVE_ACTS>(c, f2::RY, ct, z, act_blob(0), mask_at(0));
-      run_layer2<HID / 16, false, HID, HID>(c, f2::RY, f2::RX, f2::off_hh(0));
-      epi2<false, false, SAVE_ACTS>(c, f2::RX, tab + f2::T_BHH, z, act_blob(1), mask_at(1));
-      run_layer2<HID / 16, false, HID, HID>(c, f2::RX, f2::RY, f2::off_hh(1));
-      epi2<true, true, SAVE_ACTS>(c, f2::RY, tab + f2::T_BHH + HID, z, act_blob(2), mask_at(2));
-      run_layer2<HID / 16, false, HID, HID>(c, f2::RY, f2::RX, f2::off_hh(2));
-      epi2<false, false, SAVE_ACTS>(c, f2::RX, tab + f2::T_BHH + 2 * HID, z, act_blob(3), mask_at(3));
-      run_layer2<HID / 16, false, HID, HID>(c, f2::RX, f2::RY, f2::off_hh(3));
-      epi2<true, false, SAVE_ACTS>(c, f2::RY, tab + f2::T_BHH + 3 * HID, z, act_blob(4), mask_at(4));
-      run_layer2<HID / 16, false, P, P>(c, f2::RY, f2::RX, f2::OFF_WO);
+      run_layer2<2 * P / 16, true, HID, HID>(c, f2::RX, f2::RY, f2::OFF_W1, [&]() {
+        if (save) save_input(c, sp.x1_out + FS.x1(tile) + (size_t)c.row * 16, htile, sp.t, a.period);
+      });
+      epi2<false, true>(c, f2::RY, ct, z);
+      run_layer2<HID / 16, false, HID, HID>(c, f2::RY, f2::RX, f2::off_hh(0), hidden_hook(0, f2::RY));
+      epi2<false, false>(c, f2::RX, tab + f2::T_BHH, z);
+      run_layer2<HID / 16, false, HID, HID>(c, f2::RX, f2::RY, f2::off_hh(1), hidden_hook(1, f2::RX));
+      epi2<true, true>(c, f2::RY, tab + f2::T_BHH + HID, z);
+      run_layer2<HID / 16, false, HID, HID>(c, f2::RY, f2::RX, f2::off_hh(2), hidden_hook(2, f2::RY));
+      epi2<false, false>(c, f2::RX, tab + f2::T_BHH + 2 * HID, z);
+      run_layer2<HID / 16, false, HID, HID>(c, f2::RX, f2::RY, f2::off_hh(3), hidden_hook(3, f2::RX));
+      epi2<true, false>(c, f2::RY, tab + f2::T_BHH + 3 * HID, z);
+      run_layer2<HID / 16, false, P, P>(c, f2::RY, f2::RX, f2::OFF_WO, hidden_hook(4, f2::RY));
 
       // ---- output epilogue: this thread's 32 acceleration dims (float4 groups hf*8 ..)
       STAGE_TRACE(c, 11);

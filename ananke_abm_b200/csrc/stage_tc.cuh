@@ -139,8 +139,12 @@ static __device__ __noinline__ bool wait_mma(uint64_t* bar, uint32_t phase) { re
 
 // SHARED_ISSUE: use the out-of-line issue routine (backward kernel) or an unrolled inline stream (forward kernel, which
 // is smaller and more sensitive to issue latency; measured 95 vs 103 us).
-template <bool TRANS, int NKS, bool EXT, int N_IMG, int N, bool SHARED_ISSUE = false, bool HALF = false>
-__device__ __forceinline__ void run_layer(SlotCtx& c, uint32_t a_col, uint32_t w_off) {
+// `after_issue` runs on every thread of the slot between the issue of the layer's MMAs and the wait for their completion: work
+// put there (reading the A operand back from tensor memory is allowed -- the tensor core only reads it) stays off the slot's
+// critical path while it fits into the MMA time.
+struct NoHook { __device__ __forceinline__ void operator()() const {} };
+template <bool TRANS, int NKS, bool EXT, int N_IMG, int N, bool SHARED_ISSUE = false, bool HALF = false, class Hook = NoHook>
+__device__ __forceinline__ void run_layer(SlotCtx& c, uint32_t a_col, uint32_t w_off, Hook after_issue = Hook()) {
   STAGE_TRACE(c, 1);
   tmem_st_wait();
   tc_fence_before();
@@ -177,6 +181,7 @@ __device__ __forceinline__ void run_layer(SlotCtx& c, uint32_t a_col, uint32_t w
   }
   STAGE_TRACE(c, 4);
   __syncwarp();
+  after_issue();
   if (c.alive && !(SHARED_ISSUE ? wait_mma(c.bar, c.phase) : mbar_wait(c.bar, c.phase, STAGE_WAIT_CYCLES))) { c.alive = false; *c.status = 1; }
   c.phase ^= 1;
   __syncwarp();
