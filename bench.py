@@ -51,8 +51,14 @@ ALG_FLOP_FWD = 755_712          # rk4, per agent-step: 4 evaluations (SURVEY.md 
 ALG_FLOP_FWDBWD = 3_022_848     # rk4: 4x forward (discrete adjoint with stage recompute)
 ALG_FLOP_FWD_DOPRI5 = 6 * ALG_FLOP_EVAL          # 1,133,568: six new evaluations per accepted step (FSAL)
 ALG_FLOP_FWDBWD_DOPRI5 = 4 * ALG_FLOP_FWD_DOPRI5  # 4,534,272: + recompute + dgrad + wgrad of the same six evaluations
+ALG_FLOP_FWDBWD_DOPRI5_SAVED = 3 * ALG_FLOP_FWD_DOPRI5   # 3,400,704: saved_operands = all has no recompute (forward + dgrad + wgrad)
 ALG_BYTES_FWD = 1_280
 ALG_BYTES_FWDBWD = 3_840
+# DRAM bytes per agent-evaluation of the three stage launches (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full`
+# capture each, 250,112 agents x 6 evaluations per launch; profiles/r02_stage_kernels_ncu_summary.txt)
+NCU_DRAM_PER_UNIT = {"attempt": (4.110471e9 + 4.204920e9) / 2 / 1_500_672,      # 2,770 B (read 1.05 GB + written 3.10 GB per launch)
+                     "backward": (2.191809e9 + 3.250511e9) / 1_500_672,          # 3,627 B
+                     "wgrad": (4.625270e9 + 0.058811e9) / 1_500_672}             # 3,121 B
 
 
 def peaks():
@@ -367,8 +373,80 @@ def run_ours(args):
             fp32_accepted = int(oi._LAST["solver"].n_accepted)
         reps = 5
         k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        if tc_train:
-            # backward stage kernel (stage_bwd_tc_kernel): one fused launch per solver step, the largest share of a training step
+        stage_kernels = None
+        if tc_train and adaptive and args.saved_operands == "all":
+            # the three tensor-core launches of one solver step, as the training step issues them (saved_operands = all): the
+            # attempt (six fused evaluations that also save the backward pass' operands), the fused backward stages (+ gather
+            # entry) and the weight-gradient pass over the step's blobs
+            from ananke_abm_b200 import stage as st
+            Bc = y0.shape[0]
+            eng = st.TcEngine(spec, wflat)
+            eng.fwd_format = st.fwd_format_code("fp16x2")
+            yb = st.rows_block(y0)
+            y_next = st.blocked_zeros(Bc, 160, dev)
+            A = [st.rows_block(torch.randn(Bc, 64, device=dev) * 0.1) for _ in range(7)]
+            sumsq = torch.zeros(1, dtype=torch.float64, device=dev)
+            xb = torch.empty(eng.xblob_bytes(Bc, 2) * 6 // 4, dtype=torch.float32, device=dev)
+            Gb = st.rows_block(torch.randn(Bc, 64, device=dev) * 1e-3)
+            GX = [st.blocked_zeros(Bc, 160, dev) for _ in range(7)]
+            Gy0 = st.blocked_zeros(Bc, 160, dev)
+            lam_a = st.blocked_zeros(Bc, 64, dev)
+            dtk = 0.25
+            times = [1.0 + st.DOPRI5.c[i] * dtk for i in range(7)]
+            eng.backward_begin(Bc, 6)
+
+            def k_attempt():
+                eng.dopri5_attempt(yb, A, 1.0, dtk, Bc, y_next, sumsq, 1e-5, 1e-5, xb, 2)
+
+            def k_backward():
+                eng.used, eng.x_ring = 0, []
+                st.stages_backward(eng, st.DOPRI5, Bc, yb, A, times, dtk, [Gb] * 7, GX, 1, 6, xb, 2, y0_accum=Gy0, fsal_out=lam_a)
+
+            def k_wgrad():
+                eng.used, eng.x_ring, eng.x_level = used0, list(ring0), 2
+                eng.flush()
+
+            def time_kernel(fn):
+                for _ in range(3):
+                    fn()
+                torch.cuda.synchronize()
+                k0.record()
+                for _ in range(reps):
+                    fn()
+                k1.record()
+                torch.cuda.synchronize()
+                return k0.elapsed_time(k1) / reps
+            ms_att = time_kernel(k_attempt)
+            ms_bwd = time_kernel(k_backward)
+            used0, ring0 = eng.used, list(eng.x_ring)
+            ms_wg = time_kernel(k_wgrad)
+            eng.check_status()
+            units = Bc * 6                                   # agent-evaluations per launch
+            att_per_step = (counter["accepted"] + counter["rejected"]) / max(1, counter["accepted"])
+            # algorithmic bytes per agent-evaluation: what the launch must read / write once, with the tile's own
+            # working set (y0, a_j, later stages' gx) counted once per launch; DRAM bytes per unit from `ncu --set full`
+            # (profiles/r02_stage_kernels_ncu_summary.txt, 250,112 agents)
+            stage_kernels = [
+                dict(kernel="stage_fwd2_tc_kernel<save> (one attempted step: 6 fused evaluations, split-fp16 activations; saves stage "
+                            "inputs, hidden activations and ReLU masks for the backward pass)",
+                     kernel_ms=ms_att, launches_per_accepted_step=att_per_step, alg_flop_per_unit=ALG_FLOP_EVAL,
+                     alg_bytes_per_unit=149 + 256 + 107 + 1712, traffic_per_unit=NCU_DRAM_PER_UNIT["attempt"]),
+                dict(kernel="stage_bwd_tc_kernel (backward of the 6 stages of a step: dgrad only, gradient blobs, gather entry)",
+                     kernel_ms=ms_bwd, launches_per_accepted_step=1.0, alg_flop_per_unit=ALG_FLOP_EVAL,
+                     alg_bytes_per_unit=80 + 256 + 213 + 43 + 1408 + 640 + 43, traffic_per_unit=NCU_DRAM_PER_UNIT["backward"]),
+                dict(kernel="wgrad_tc_kernel (weight gradients of a step from its activation / gradient blobs)",
+                     kernel_ms=ms_wg, launches_per_accepted_step=1.0, alg_flop_per_unit=ALG_FLOP_EVAL,
+                     alg_bytes_per_unit=3040, traffic_per_unit=NCU_DRAM_PER_UNIT["wgrad"]),
+            ]
+            for kd in stage_kernels:
+                kd["units_per_launch"] = units
+                kd["ms_per_accepted_step"] = kd["kernel_ms"] * kd["launches_per_accepted_step"]
+            dom = max(stage_kernels, key=lambda kd: kd["ms_per_accepted_step"])
+            kern_ms, kern_units, kern_name = dom["kernel_ms"], units, dom["kernel"]
+            kern_flop_unit, kern_bytes_unit, kern_traffic_unit = dom["alg_flop_per_unit"], dom["alg_bytes_per_unit"], dom["traffic_per_unit"]
+            del eng, yb, y_next, A, xb, Gb, GX, Gy0, lam_a
+        elif tc_train:
+            # backward stage kernel (stage_bwd_tc_kernel) in its recomputing form: one fused launch per solver step
             from ananke_abm_b200 import stage as st
             Bc = y0.shape[0]
             eng = st.TcEngine(spec, wflat)
@@ -383,7 +461,7 @@ def run_ours(args):
             eng.backward_begin(Bc, n_fused)
 
             def one_step_bwd_stages():
-                eng.used = 0
+                eng.used, eng.x_ring = 0, []
                 st.stages_backward(eng, tab, Bc, yb, A[:last], times, dtk, [Gb] * 7, GX, first, last)
             for _ in range(3):
                 one_step_bwd_stages()
@@ -441,12 +519,27 @@ def run_ours(args):
     flops_kernel = kern_units * kern_flop_unit
     achieved_tf = flops_kernel / (kern_ms * 1e-3) / 1e12
     bytes_kernel = kern_units * kern_bytes_unit
+    # which roof bounds the dominant kernel: its algorithmic intensity against the ridge of the measured peaks.  With the backward
+    # pass' operands saved by the forward launch (saved_operands = all) every stage launch sits on the HBM side of the ridge.
+    hbm_gbs = bytes_kernel / (kern_ms * 1e-3) / 1e9
+    if stage_kernels and kern_flop_unit / kern_bytes_unit < pk["tf_burst"] * 1e12 / (pk["hbm"] * 1e9):
+        roof_head = {"bound": "hbm", "achieved": hbm_gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": hbm_gbs / pk["hbm"]}
+    else:
+        roof_head = {"bound": "tensor", "achieved": achieved_tf, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": achieved_tf / pk["tf_burst"]}
+    if stage_kernels:
+        for kd in stage_kernels:
+            tsec = kd["kernel_ms"] * 1e-3
+            kd["alg_gbs"] = kd["units_per_launch"] * kd["alg_bytes_per_unit"] / tsec / 1e9
+            kd["alg_tflops"] = kd["units_per_launch"] * kd["alg_flop_per_unit"] / tsec / 1e12
+            kd["frac_hbm"] = kd["alg_gbs"] / pk["hbm"]
+            kd["frac_tensor"] = kd["alg_tflops"] / pk["tf_burst"]
+            kd["dram_gbs"] = (kd["units_per_launch"] * kd["traffic_per_unit"] / tsec / 1e9) if kd["traffic_per_unit"] else None
     h2d = sum(x.numel() * x.element_size() for x in (h_home, h_work, h_traits, h_t))
     d2h = (B * T * 4) if not train else 4
     acc_per = steps_counted["accepted"] / max(1, steps_counted["solves"])
     rej_per = steps_counted["rejected"] / max(1, steps_counted["solves"])
     if adaptive:
-        fl_fwd, fl_fb = ALG_FLOP_FWD_DOPRI5, ALG_FLOP_FWDBWD_DOPRI5
+        fl_fwd, fl_fb = ALG_FLOP_FWD_DOPRI5, (ALG_FLOP_FWDBWD_DOPRI5_SAVED if stage_kernels else ALG_FLOP_FWDBWD_DOPRI5)
     else:
         fl_fwd, fl_fb = ALG_FLOP_FWD, ALG_FLOP_FWDBWD
     out = {
@@ -466,8 +559,7 @@ def run_ours(args):
                                      "fp32_note": "same solver, drift in strict fp32 (FFMA kernels), first %d agents of rank 0" % min(2048, chunk),
                                      "rtol": model.config.rtol, "atol": model.config.atol} if adaptive else {"grid_intervals": T - 1}),
                    "l2": "trajectory rows written per step (%.0f MB) exceed L2; weights are L2-resident by design" % (chunk * T * 640 / 1e6)},
-        "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": pk["tf_burst"], "unit": "TFLOP/s",
-                     "frac": achieved_tf / pk["tf_burst"],
+        "roofline": {**roof_head,
                      "traffic": (kern_traffic_unit * kern_units if kern_traffic_unit else None),
                      "traffic_note": "DRAM bytes per launch scaled from one ncu --set full capture (profiles/r02_stage_kernels_ncu_summary.txt)"
                      if kern_traffic_unit else None,
@@ -479,7 +571,11 @@ def run_ours(args):
                      "alg_flop_per_agent_step": fl_fb if train else fl_fwd,
                      "alg_bytes_per_agent_step": ALG_BYTES_FWDBWD if train else ALG_BYTES_FWD,
                      "step_tflops_alg": value * (fl_fb if train else fl_fwd) / 1e12,
-                     "hbm_achieved_gbs": bytes_kernel / (kern_ms * 1e-3) / 1e9, "hbm_peak_gbs": pk["hbm"]},
+                     "hbm_achieved_gbs": bytes_kernel / (kern_ms * 1e-3) / 1e9, "hbm_peak_gbs": pk["hbm"],
+                     "tensor_achieved_tflops": achieved_tf, "tensor_peak_tflops": pk["tf_burst"],
+                     "arithmetic_intensity_flop_per_byte": kern_flop_unit / kern_bytes_unit,
+                     "ridge_flop_per_byte": pk["tf_burst"] * 1e12 / (pk["hbm"] * 1e9),
+                     "stage_kernels": stage_kernels},
         "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / e2e_steps, "agent_days_per_s": B_total * e2e_steps / (e2e_ms * 1e-3)},
         "gpu_launches": args.steps * launches_per_step,
