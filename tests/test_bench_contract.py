@@ -34,3 +34,15 @@ def test_equal_part_chunking():
     assert parts(378_880, 378_880) == (1, 378_880)
     n, c = parts(8_000_000, 378_880)
     assert n == 22 and c % 128 == 0 and c <= 378_880 and n * c >= 8_000_000
+
+
+def test_chunk_bounds_cover_the_batch_in_whole_waves():
+    """bench.chunk_bounds: parts cover [0, B) without gaps, none larger than the cap, all but the last a whole number of waves"""
+    import bench
+    for B, cap in [(1_000_000, 265_216), (125_000, 265_216), (700_000, 265_216), (10_000, 265_216), (8_000_000, 265_216), (300_001, 100_000)]:
+        parts = bench.chunk_bounds(B, cap, 296)
+        assert parts[0][0] == 0 and parts[-1][1] == B
+        assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+        assert all(0 < e - s <= cap + 296 * 128 for s, e in parts)
+        if len(parts) > 1 and -(-(-(-B // 128)) // 296) >= len(parts):
+            assert all((e - s) % (296 * 128) == 0 for s, e in parts[:-1])

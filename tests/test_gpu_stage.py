@@ -349,3 +349,33 @@ def test_forward_saved_operands_vs_recomputed_ones(B):
     assert all(s.x is None for s in steps1)
     gy_c, _ = stage.dopri5_backward(eng, steps1, g)
     assert torch.isfinite(gy_c).all()
+
+
+def test_dopri5_many_output_rows_per_step_vs_oracle():
+    """40 requested times inside ~4 accepted steps: every step has ~10 dense-output rows, so the step-level backward combine takes
+    its sources (dL/dy_path rows, read in place row-major) in more than one pass of six and the gather entry folds them; B = 200
+    leaves a ragged last tile.  Same bars as test_stage_dopri5_forward_and_adjoint_vs_oracle."""
+    import importlib
+    import ananke_abm_b200 as ab
+    oi = importlib.import_module("ananke_abm_b200.odeint")
+    dev = _cuda()
+    oracle, model = _pair()
+    model = model.to(dev)
+    B, T = 200, 40
+    home, work, traits = _agents(B, 8)
+    t = torch.linspace(0.0, 6.0, T)
+    wgt = torch.linspace(0.5, 1.5, T)[:, None, None]
+    y0r = oracle.initial_state(home, work, traits).detach().requires_grad_(True)
+    ref = tdq.odeint(oracle.rhs, y0r, t, method="dopri5", rtol=1e-3, atol=1e-3)
+    ((ref * wgt) ** 2).mean().backward()          # all 160 columns carry gradient, including the context part
+    y0 = model.initial_state(home.to(dev), work.to(dev), traits.to(dev)).detach().requires_grad_(True)
+    out = ab.odeint(model.odefunc, y0, t.to(dev), method="dopri5", rtol=1e-3, atol=1e-3, options={"precision": "bf16"})
+    stats = oi._LAST["solver"]
+    ((out * wgt.to(dev)) ** 2).mean().backward()
+    torch.cuda.synchronize()
+    assert stats.n_accepted < 12          # i.e. several output rows per step
+    assert _rel(out.detach().cpu(), ref.detach()) < 2e-2
+    assert _rms(y0.grad.cpu(), y0r.grad) < 0.12
+    assert _rms(y0.grad[:, 128:].cpu(), y0r.grad[:, 128:]) < 0.12          # dL/dh: only the gather entry produces it
+    for (n, p), (_, q) in zip(model.odefunc.func.net.named_parameters(), oracle.odefunc.func.net.named_parameters()):
+        assert _rms(p.grad.cpu(), q.grad) < 5e-2, (n, _rms(p.grad.cpu(), q.grad))
