@@ -575,7 +575,10 @@ def run_ours(args):
                      "tensor_achieved_tflops": achieved_tf, "tensor_peak_tflops": pk["tf_burst"],
                      "arithmetic_intensity_flop_per_byte": kern_flop_unit / kern_bytes_unit,
                      "ridge_flop_per_byte": pk["tf_burst"] * 1e12 / (pk["hbm"] * 1e9),
-                     "stage_kernels": stage_kernels},
+                     "stage_kernels": stage_kernels,
+                     # the three stage launches together: algorithmic-byte fraction of the HBM roof weighted by their time per accepted step
+                     "stage_kernels_time_weighted_frac_hbm": (sum(kd["frac_hbm"] * kd["ms_per_accepted_step"] for kd in stage_kernels)
+                                                              / sum(kd["ms_per_accepted_step"] for kd in stage_kernels)) if stage_kernels else None},
         "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / e2e_steps, "agent_days_per_s": B_total * e2e_steps / (e2e_ms * 1e-3)},
         "gpu_launches": args.steps * launches_per_step,
