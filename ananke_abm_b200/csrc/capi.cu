@@ -56,7 +56,8 @@ int stage_bwd_tc(const ab200_drift_desc* d, const uint8_t* image, const float* y
                  int64_t B, const float* g_base, const float* const* gx_ptrs, int n_g, const float* dp, const float* dv, float* gx_out,
                  void* spill, int blob0, int nblobs, float* g_bout, cudaStream_t st);
 int pv_combine_bwd_multi(const ab200_drift_desc* d, const float* const* g, int n_src, const float* cpv, const float* cpa, const float* cva,
-                         int n_a, int64_t B, float* G_y0, float* const* G_a, int accumulate, int rowmajor_mask, cudaStream_t st);
+                         int n_a, int64_t B, float* G_y0, float* const* G_a, int accumulate, int rowmajor_mask, const float* add_a, int add_idx,
+                         cudaStream_t st);
 int ga_assemble(const ab200_drift_desc* d, const float* base, const float* const* gx, int n, const float* dp, const float* dv,
                 int64_t B, float* out, cudaStream_t st);
 int stage_bwd_tc_multi(const ab200_drift_desc* d, const uint8_t* image, const float* y0, const float* const* a_ptrs,
@@ -404,9 +405,10 @@ int ab200_stage_backward_fused(const ab200_drift_desc* d, const void* image, con
 
 int ab200_pv_combine_backward_multi(const ab200_drift_desc* d, const float* const* g, int32_t n_src, const float* cpv_host,
                                     const float* cpa_host, const float* cva_host, int32_t n_a, int64_t B, float* G_y0,
-                                    float* const* G_a, int32_t accumulate, int32_t rowmajor_mask, ab200_stream_t stream) {
+                                    float* const* G_a, int32_t accumulate, int32_t rowmajor_mask, const float* add_a, int32_t add_index,
+                                    ab200_stream_t stream) {
   if (!desc_ok(d) || !g || !cpv_host || !G_y0 || B <= 0 || (n_a > 0 && (!G_a || !cpa_host || !cva_host))) return AB200_ERR_BAD_ARG;
-  return pv_combine_bwd_multi(d, g, n_src, cpv_host, cpa_host, cva_host, n_a, B, G_y0, G_a, accumulate, rowmajor_mask, (cudaStream_t)stream);
+  return pv_combine_bwd_multi(d, g, n_src, cpv_host, cpa_host, cva_host, n_a, B, G_y0, G_a, accumulate, rowmajor_mask, add_a, add_index, (cudaStream_t)stream);
 }
 
 int ab200_stage_upstream(const ab200_drift_desc* d, const float* g_base, const float* const* gx, int32_t n_g, const float* dp_host,

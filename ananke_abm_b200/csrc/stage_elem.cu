@@ -116,6 +116,8 @@ struct MultiBwdArgs {
   int n_src, n_a, accumulate, ntiles, P, H;
   int rowmajor_mask;      // bit s: source s is a ROW-MAJOR [B][D] row of the caller's gradient tensor (read in place: no transposed copy)
   int64_t B;
+  const float* add_a;     // or null: blocked [Bp][P] added to G_a[add_idx] (the gradient a following step hands to its FSAL evaluation)
+  int add_idx;
 };
 // float4 `f4` (of Y4 per agent) of agent (tile, row) from a blocked or a row-major source; row-major rows beyond B read as zero
 __device__ __forceinline__ float4 src_f4(const float* g, bool rowmajor, int tile, int row, int f4, int Y4, int64_t B) {
@@ -169,6 +171,10 @@ __global__ void __launch_bounds__(256) pv_combine_bwd_multi_kernel(const __grid_
     for (int j = 0; j < a.n_a; ++j) {
       float4* q = reinterpret_cast<float4*>(a.G_a[j]) + ((size_t)tile * P4 + grp) * EL_TM + row;
       float4 x = acc ? *q : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a.add_a != nullptr && j == a.add_idx) {
+        const float4 e = (reinterpret_cast<const float4*>(a.add_a) + ((size_t)tile * P4 + grp) * EL_TM)[row];
+        x.x += e.x; x.y += e.y; x.z += e.z; x.w += e.w;
+      }
 #pragma unroll
       for (int s = 0; s < EL_MAX_SRC; ++s)
         if (s < a.n_src) {
@@ -490,11 +496,14 @@ int adjoint_gather(const ab200_drift_desc* d, const float* base, const float* co
 }
 
 int pv_combine_bwd_multi(const ab200_drift_desc* d, const float* const* g, int n_src, const float* cpv, const float* cpa, const float* cva,
-                         int n_a, int64_t B, float* G_y0, float* const* G_a, int accumulate, int rowmajor_mask, cudaStream_t st) {
+                         int n_a, int64_t B, float* G_y0, float* const* G_a, int accumulate, int rowmajor_mask, const float* add_a, int add_idx,
+                         cudaStream_t st) {
+  if (add_a != nullptr && (add_idx < 0 || add_idx >= n_a)) return AB200_ERR_BAD_ARG;
   if (n_src < 1 || n_src > EL_MAX_SRC || n_a < 0 || n_a > EL_MAX_A || d->pos_dim % 4 || d->ctx_dim % 4) return AB200_ERR_BAD_ARG;
   MultiBwdArgs k{};
   k.G_y0 = G_y0; k.n_src = n_src; k.n_a = n_a; k.accumulate = accumulate; k.P = d->pos_dim; k.H = d->ctx_dim;
   k.rowmajor_mask = rowmajor_mask; k.B = B;
+  k.add_a = add_a; k.add_idx = add_idx;
   k.ntiles = (int)((B + EL_TM - 1) / EL_TM);
   for (int s = 0; s < n_src; ++s) {
     k.g[s] = g[s];

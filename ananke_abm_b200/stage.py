@@ -314,9 +314,11 @@ class TcEngine:
         self.used += self.ntiles
         self.x_ring.append(None)
 
-    def combine_backward_multi(self, sources: Sequence, B: int, G_y0, G_a: Sequence[torch.Tensor], accumulate: bool) -> None:
+    def combine_backward_multi(self, sources: Sequence, B: int, G_y0, G_a: Sequence[torch.Tensor], accumulate: bool, add_a=None,
+                               add_index: int = 0) -> None:
         """`sources` = [(g, Combo), ...]: all folded into G_y0 / G_a in passes of up to 6 sources.  g is a blocked tensor, or a
-        contiguous ROW-MAJOR [B, D] row of the caller's gradient tensor (2-D: read in place, no transposed copy)."""
+        contiguous ROW-MAJOR [B, D] row of the caller's gradient tensor (2-D: read in place, no transposed copy).
+        `add_a` (blocked [Bp, P]) is added to G_a[add_index] in the first pass."""
         n_a = len(G_a)
         for s0 in range(0, len(sources), 6):
             grp = sources[s0:s0 + 6]
@@ -337,7 +339,7 @@ class TcEngine:
             rc = self.L.ab200_pv_combine_backward_multi(C.byref(self.desc), C.cast(gp, C.c_void_p), n, C.cast(cpv, C.c_void_p),
                                                         C.cast(cpa, C.c_void_p), C.cast(cva, C.c_void_p), n_a, B, G_y0.data_ptr(),
                                                         C.cast(_ptr_array(G_a), C.c_void_p), 1 if (accumulate or s0 > 0) else 0, rm_mask,
-                                                        _stream())
+                                                        add_a.data_ptr() if (add_a is not None and s0 == 0) else None, int(add_index), _stream())
             _lib.check(rc, "ab200_pv_combine_backward_multi")
 
     def stage_upstream(self, g_base, gx: Sequence[torch.Tensor], dp: Sequence[float], dv: Sequence[float], B: int, out) -> None:
@@ -793,9 +795,7 @@ def dopri5_backward(eng: TcEngine, steps: List[_Dopri5Step], grad_y_path: torch.
         sources = [(lam, DOPRI5.combo(DOPRI5.b, dt))]
         for (k, x) in st.outputs:
             sources.append((grad_rows[k], DOPRI5.combo(dopri5_interp_weights(x), dt)))
-        eng.combine_backward_multi(sources, B, G_y0, G_a, accumulate=False)
-        if lam_a is not None:
-            G_a[6].add_(lam_a)
+        eng.combine_backward_multi(sources, B, G_y0, G_a, accumulate=False, add_a=lam_a, add_index=6)
         last = 6 if (st.outputs or lam_a is not None) else 5      # stage 7 only matters if something used k_7
         first = 0 if si == 0 else 1                                # k_1 of a later step belongs to the previous step
         combos = [DOPRI5.stage_input(i, dt) for i in range(7)]

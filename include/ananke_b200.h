@@ -278,10 +278,13 @@ int ab200_adjoint_gather_upstream(const ab200_drift_desc* d, const float* base, 
 /* ab200_pv_combine_backward for up to 6 linear outputs of the same step in ONE pass (source i: gradient g[i] and its
  * combination cpv[i], cpa[i * 8 + j], cva[i * 8 + j], j < n_a): the accumulators are written once instead of once per output
  * (a dopri5 step's end state plus the dense-output rows that fall inside it).  Source i is blocked [Bp][D], or -- bit i of
- * rowmajor_mask set -- a ROW-MAJOR [B][D] row of the caller's own gradient tensor (dL/dy_path[k]), read in place. */
+ * rowmajor_mask set -- a ROW-MAJOR [B][D] row of the caller's own gradient tensor (dL/dy_path[k]), read in place.
+ * add_a (or NULL): blocked [Bp][P] buffer added to G_a[add_index] in the same pass (dopri5: the gradient the following step hands
+ * back to this step's FSAL evaluation a_7). */
 int ab200_pv_combine_backward_multi(const ab200_drift_desc* d, const float* const* g, int32_t n_src, const float* cpv_host,
                                     const float* cpa_host, const float* cva_host, int32_t n_a, int64_t B, float* G_y0,
-                                    float* const* G_a, int32_t accumulate, int32_t rowmajor_mask, ab200_stream_t stream);
+                                    float* const* G_a, int32_t accumulate, int32_t rowmajor_mask, const float* add_a, int32_t add_index,
+                                    ab200_stream_t stream);
 /* The upstream gradient of a stage written out as a buffer instead of being consumed by ab200_stage_backward:
  *     g_a_out (blocked [Bp][P]) = g_base + sum_l dp[l] gx[l].p + dv[l] gx[l].v
  * dopri5's first stage of a step IS the last (FSAL) evaluation of the previous step (tdq rk_common.py _adaptive_step:

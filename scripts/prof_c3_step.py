@@ -42,4 +42,24 @@ if prof is not None:
     print(f"kernel time of the last repetition: {tot / 1e3:.1f} ms")
     for k, n, us in rows[:16]:
         print(f"  {100 * us / tot:5.1f} %  {us / 1e3:8.2f} ms  {n:4d} x {us / n:8.1f} us  {k[:90]}")
+    # GPU idle time: gaps between consecutive kernels on the device timeline, attributed to the kernel that ran BEFORE the gap
+    from torch.autograd import DeviceType
+    ev = sorted((e for e in prof.events() if e.device_type == DeviceType.CUDA and e.time_range.end > e.time_range.start),
+                key=lambda e: e.time_range.start)
+    span = ev[-1].time_range.end - ev[0].time_range.start
+    gaps = {}
+    end = ev[0].time_range.end
+    prev = ev[0].name
+    for e in ev[1:]:
+        g = e.time_range.start - end
+        if g > 0:
+            gaps.setdefault(prev[:60], [0, 0.0])
+            gaps[prev[:60]][0] += 1
+            gaps[prev[:60]][1] += g
+        if e.time_range.end > end:
+            end, prev = e.time_range.end, e.name
+    tot_gap = sum(v[1] for v in gaps.values())
+    print(f"device timeline: span {span / 1e3:.1f} ms, idle {tot_gap / 1e3:.2f} ms")
+    for k, (n, us) in sorted(gaps.items(), key=lambda kv: -kv[1][1])[:10]:
+        print(f"   idle after {k:60s} {n:4d} gaps {us / 1e3:7.2f} ms  ({us / n:6.1f} us each)")
 print("ok")
