@@ -237,7 +237,15 @@ def run_ours(args):
     # agents are processed in chunks of at most --chunk agents, cut at whole WAVES of the stage kernels (#SMs x 2 slots x 128
     # agents): 1 M agents = 7,813 tiles = 26.4 waves run as 7 + 7 + 7 + 6 waves (four equal parts would each pay a partial wave);
     # the saved steps of ONE chunk live in HBM (peak_mem_gb in the JSON line)
-    bounds = chunk_bounds(B, args.chunk, 2 * torch.cuda.get_device_properties(dev).multi_processor_count)
+    chunk_cap = args.chunk
+    if train and cfg["method"] == "dopri5" and args.precision == "bf16":
+        # keep one chunk's saved steps inside the memory that is actually free (measured per agent of a chunk at ~30 accepted steps:
+        # 471 KB with saved_operands = all, 288 KB inputs, 112 KB none; 15 % headroom for a longer step sequence)
+        per_agent = {"all": 471e3, "inputs": 288e3, "none": 112e3}[args.saved_operands] * 1.15
+        free_b, _ = torch.cuda.mem_get_info(dev)
+        fit = int(free_b / per_agent) // (128 * 296) * (128 * 296)
+        chunk_cap = max(128 * 296, min(chunk_cap, fit))
+    bounds = chunk_bounds(B, chunk_cap, 2 * torch.cuda.get_device_properties(dev).multi_processor_count)
     chunk = max(e - s for s, e in bounds)
     model, zfeat, csr = build_model(cfg, args.precision, dev, args.saved_operands)
     pin = lambda x: x.pin_memory()   # noqa: E731
