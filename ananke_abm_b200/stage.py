@@ -701,6 +701,8 @@ def dopri5_forward(eng: TcEngine, y0: torch.Tensor, t_host: Sequence[float], rto
     # A training forward in the split-activation format also keeps every stage INPUT of the accepted steps as the bf16 operand
     # image of the backward kernels (352 B per agent-stage): the backward pass is bound by its HBM traffic, and loading that
     # image replaces re-reading y0 and up to six a_j (1.5 KB) and spilling it for the weight-gradient kernel.
+    if saved_operands not in SAVE_LEVELS:
+        raise ValueError("saved_operands must be one of %s, got %r" % (sorted(SAVE_LEVELS), saved_operands))
     save_level = SAVE_LEVELS[saved_operands] if (save_steps and eng.fwd_format == 2) else 0
     xb_floats = eng.xblob_bytes(B, save_level) * 6 // 4 if save_level else 0
     x_cur = torch.empty(xb_floats, dtype=torch.float32, device=dev) if xb_floats else None
