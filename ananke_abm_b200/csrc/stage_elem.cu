@@ -127,13 +127,28 @@ __device__ __forceinline__ float4 src_f4(const float* g, bool rowmajor, int tile
   return __ldcs(reinterpret_cast<const float4*>(g) + agent * Y4 + f4);      // 16 B of a 640-byte row per lane: the neighbouring lanes of
                                                                             // the other feature groups pick the rest of the sector up from L2
 }
+// work item i -> (tile, group, row) for kernels that read ROW-MAJOR sources next to blocked ones: a warp covers 8 consecutive
+// rows x 4 consecutive float4 groups, so a row-major access is 8 fully used 64-byte segments (decode(): 32 rows x 16 B = 32
+// half-used sectors, every sector fetched twice) and a blocked access is 4 fully used 128-byte lines.  Needs (P4 + H4) % 4 == 0.
+__device__ __forceinline__ void decode_8x4(int64_t i, int P4, int H4, int& tile, int& grp, int& row) {
+  const int c = (int)(i & 3), r_lo = (int)((i >> 2) & 7);
+  int64_t q = i >> 5;
+  const int r_hi = (int)(q % (EL_TM / 8));
+  q /= (EL_TM / 8);
+  const int g_hi = (int)(q % ((P4 + H4) / 4));
+  tile = (int)(q / ((P4 + H4) / 4));
+  row = r_hi * 8 + r_lo;
+  grp = g_hi * 4 + c;
+}
 __global__ void __launch_bounds__(256) pv_combine_bwd_multi_kernel(const __grid_constant__ MultiBwdArgs a) {
   const int P4 = a.P / 4, H4 = a.H / 4, Y4 = 2 * P4 + H4;
   const int64_t n = (int64_t)a.ntiles * (P4 + H4) * EL_TM;
   const bool acc = a.accumulate != 0;
+  const bool lanes_8x4 = a.rowmajor_mask != 0 && (P4 % 4) == 0 && (H4 % 4) == 0;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     int tile, grp, row;
-    decode(i, P4, H4, tile, grp, row);
+    if (lanes_8x4) decode_8x4(i, P4, H4, tile, grp, row);
+    else decode(i, P4, H4, tile, grp, row);
     const size_t t0 = (size_t)tile * Y4 * EL_TM + row;
     float4* o4 = reinterpret_cast<float4*>(a.G_y0) + t0;
     if (grp >= P4) {

@@ -465,6 +465,17 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+_SIDE_STREAMS: dict = {}
+
+
+def _side_stream(device) -> "torch.cuda.Stream":
+    """one extra stream per device for the per-attempt read of dopri5's error norm (see dopri5_forward)"""
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=key)
+    return _SIDE_STREAMS[key]
+
+
 # --------------------------------------------------------------------------------------------------------
 # blocked buffers
 # --------------------------------------------------------------------------------------------------------
@@ -689,6 +700,10 @@ def dopri5_forward(eng: TcEngine, y0: torch.Tensor, t_host: Sequence[float], rto
     pool_n = 256
     pool = torch.zeros(pool_n, dtype=torch.float64, device=dev)
     pending = None                              # (y, A, dt, outs) of the last accepted step whose dense rows are not launched yet
+    side = done = host_sumsq = None
+    if dev.type == "cuda":
+        side, done = _side_stream(dev), torch.cuda.Event()
+        host_sumsq = torch.empty(1, dtype=torch.float64, pin_memory=True)
 
     def flush_rows():
         nonlocal pending
@@ -724,10 +739,25 @@ def dopri5_forward(eng: TcEngine, y0: torch.Tensor, t_host: Sequence[float], rto
         sumsq = pool[slot:slot + 1]
         eng.dopri5_attempt(y_cur, A, ta, dt, B, y_next, sumsq, rtol, atol, x_cur, save_level)
         stats.n_evals += 6
+        if side is not None:
+            done.record()            # right behind the attempt, BEFORE the dense rows of the previous step
         flush_rows()
-        if use_global:
-            dist.all_reduce(sumsq, group=group)
-        ratio = math.sqrt(float(sumsq.item()) / n_elems)      # ONE device->host read per attempt (NaN stays NaN)
+        if side is not None:
+            # The error norm travels on a side stream that waits for the attempt only: the host decides accept / reject and
+            # launches the next attempt while the dense-output rows of the previous step (~0.2 ms) still run on the main stream,
+            # so its turn-around (~50 us, more with the all-reduce of the global norm) is not GPU idle time.
+            with torch.cuda.stream(side):
+                side.wait_event(done)
+                if use_global:
+                    dist.all_reduce(sumsq, group=group)
+                host_sumsq.copy_(sumsq, non_blocking=True)
+            side.synchronize()
+            ssq = float(host_sumsq[0])
+        else:
+            if use_global:
+                dist.all_reduce(sumsq, group=group)
+            ssq = float(sumsq.item())
+        ratio = math.sqrt(ssq / n_elems)      # ONE device->host read per attempt (NaN stays NaN)
         if ratio != ratio:
             eng.check_status()       # a kernel whose bounded barrier wait expired poisons the norm: report that, not an overflow
             raise _lib.Ab200Error("dopri5: non-finite error estimate (state or drift overflowed)")
