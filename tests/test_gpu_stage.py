@@ -379,3 +379,59 @@ def test_dopri5_many_output_rows_per_step_vs_oracle():
     assert _rms(y0.grad[:, 128:].cpu(), y0r.grad[:, 128:]) < 0.12          # dL/dh: only the gather entry produces it
     for (n, p), (_, q) in zip(model.odefunc.func.net.named_parameters(), oracle.odefunc.func.net.named_parameters()):
         assert _rms(p.grad.cpu(), q.grad) < 5e-2, (n, _rms(p.grad.cpu(), q.grad))
+
+
+@pytest.mark.parametrize("B", [1, 7, 127, 128, 129, 1000])
+@pytest.mark.parametrize("n_rowmajor", [0, 1, 3, 8])
+def test_step_level_combine_mixed_blocked_and_rowmajor_sources(B, n_rowmajor):
+    """`ab200_pv_combine_backward_multi` (adjoint of the linear outputs of a step: end state + dense-output rows, torchdiffeq
+    rk_common.py `_runge_kutta_step` / interp.py `_interp_evaluate`) against the plain formula
+        G_y0.p = sum g.p ;  G_y0.v = sum cpv g.p + g.v ;  G_y0.h = sum g.h ;  G_a[j] = sum cpa[j] g.p + cva[j] g.v (+ add_a)
+    with one blocked source and `n_rowmajor` ROW-MAJOR rows read in place (the 8 rows x 4 groups lane mapping), at ragged sizes,
+    in one pass and in several (more than 6 sources), with and without accumulation."""
+    import ananke_abm_b200 as ab
+    from ananke_abm_b200 import stage
+    dev = _cuda()
+    _, model = _pair()
+    spec = ab.describe_drift(model.to(dev).odefunc)
+    eng = stage.TcEngine(spec, spec.flat_params().detach())
+    D, P = eng.D, eng.P
+    gen = torch.Generator(device=dev).manual_seed(100 * B + n_rowmajor)
+    rnd = lambda *s: torch.randn(*s, device=dev, generator=gen)
+    n_a = 7
+    lam = rnd(B, D)
+    rows = rnd(max(n_rowmajor, 1), B, D)
+    srcs, ref_src = [], []
+    for i in range(1 + n_rowmajor):
+        c = stage.Combo(float(torch.rand(1)), [float(x) for x in torch.randn(n_a)], [float(x) for x in torch.randn(n_a)])
+        g = lam if i == 0 else rows[i - 1]
+        srcs.append((stage.rows_block(g) if i == 0 else g, c))
+        ref_src.append((g.double(), c))
+    add_a = rnd(B, P)
+    G0 = rnd(B, D)
+    Ga0 = [rnd(B, P) for _ in range(n_a)]
+    for accumulate in (False, True):
+        G_y0 = stage.rows_block(G0)
+        G_a = [stage.rows_block(x) for x in Ga0]
+        eng.combine_backward_multi(srcs, B, G_y0, G_a, accumulate=accumulate, add_a=stage.rows_block(add_a), add_index=6)
+        torch.cuda.synchronize()
+        ry = G0.double() if accumulate else torch.zeros(B, D, dtype=torch.float64, device=dev)
+        ra = [(x.double() if accumulate else torch.zeros(B, P, dtype=torch.float64, device=dev)) for x in Ga0]
+        ra[6] = ra[6] + add_a.double()
+        for g, c in ref_src:
+            gp, gv, gh = g[:, :P], g[:, P:2 * P], g[:, 2 * P:]
+            ry = ry + torch.cat([gp, float(np.float32(c.cpv)) * gp + gv, gh], dim=1)
+            for j in range(n_a):
+                ra[j] = ra[j] + float(np.float32(c.cpa[j])) * gp + float(np.float32(c.cva[j])) * gv
+        got_y = stage.rows_unblock(G_y0, B, D).double()
+        scale = max(1.0, float(ry.abs().max()))
+        assert float((got_y - ry).abs().max()) < 2e-5 * scale, (accumulate, float((got_y - ry).abs().max()))
+        for j in range(n_a):
+            got = stage.rows_unblock(G_a[j], B, P).double()
+            sj = max(1.0, float(ra[j].abs().max()))
+            assert float((got - ra[j]).abs().max()) < 2e-5 * sj, (accumulate, j, float((got - ra[j]).abs().max()))
+        # padding rows of the blocked outputs stay zero when nothing is accumulated into them
+        if not accumulate:
+            Bp = stage.padded_rows(B)
+            v = G_y0.view(Bp // 128, D // 4, 128, 4).permute(0, 2, 1, 3).reshape(Bp, D)
+            assert float(v[B:].abs().sum()) == 0.0
