@@ -144,7 +144,7 @@ def chunk_bounds(B, max_chunk, slots, tile=128):
     return out
 
 
-def build_model(cfg, precision, device, saved_operands="all"):
+def build_model(cfg, precision, device, saved_operands="all", adjoint_mode="discrete"):
     """GAT-ODE: zone tables from the graph-attention layers, drift net + fused solver, random init (seed 42)."""
     import ananke_abm_b200 as ab
     from ananke_abm_b200.graph import synthetic_zone_graph
@@ -153,7 +153,10 @@ def build_model(cfg, precision, device, saved_operands="all"):
     mc.precision = precision
     mc.ode_method = cfg["method"]            # rtol = atol = 1e-5 (mode_sep/config.py:27-28) apply to dopri5 only
     mc.adjoint = bool(cfg.get("adjoint", False))
-    mc.adjoint_mode = "discrete"             # c5: the odeint_adjoint seam with the explicit discrete-adjoint opt-in (tensor-core stage path)
+    # c5 = the odeint_adjoint seam.  "discrete" (default of the bench): the explicit discrete-adjoint opt-in on the tensor-core stage
+    # path.  "continuous": torchdiffeq's own scheme -- forward without saved steps, backward = the augmented system [y, a_y, a_theta]
+    # integrated per output interval with f and its vector-Jacobian products on the fp32 kernels (O(1) memory in solver steps)
+    mc.adjoint_mode = adjoint_mode
     mc.error_norm = "global"                 # N > 1: one RMS error norm over all ranks' agents, as a single process would use
     mc.saved_operands = saved_operands
     model = ab.GATODEModel(7, mc, heads=cfg["heads"]).to(device)
@@ -238,7 +241,8 @@ def run_ours(args):
     # agents): 1 M agents = 7,813 tiles = 26.4 waves run as 7 + 7 + 7 + 6 waves (four equal parts would each pay a partial wave);
     # the saved steps of ONE chunk live in HBM (peak_mem_gb in the JSON line)
     chunk_cap = args.chunk
-    if train and cfg["method"] == "dopri5" and args.precision == "bf16":
+    cont_adj = bool(cfg.get("adjoint", False)) and args.adjoint_mode == "continuous"
+    if train and cfg["method"] == "dopri5" and args.precision == "bf16" and not cont_adj:
         # keep one chunk's saved steps inside the memory that is actually free (measured per agent of a chunk at ~30 accepted steps:
         # 471 KB with saved_operands = all, 288 KB inputs, 112 KB none; 15 % headroom for a longer step sequence)
         per_agent = {"all": 471e3, "inputs": 288e3, "none": 112e3}[args.saved_operands] * 1.15
@@ -247,7 +251,7 @@ def run_ours(args):
         chunk_cap = max(128 * 296, min(chunk_cap, fit))
     bounds = chunk_bounds(B, chunk_cap, 2 * torch.cuda.get_device_properties(dev).multi_processor_count)
     chunk = max(e - s for s, e in bounds)
-    model, zfeat, csr = build_model(cfg, args.precision, dev, args.saved_operands)
+    model, zfeat, csr = build_model(cfg, args.precision, dev, args.saved_operands, args.adjoint_mode)
     pin = lambda x: x.pin_memory()   # noqa: E731
     h_home, h_work, h_traits, h_t = pin(home), pin(work), pin(traits), pin(t)
     d_home, d_work, d_traits, d_t = (x.to(dev) for x in (home, work, traits, t))
@@ -365,7 +369,7 @@ def run_ours(args):
 
     # kernel-only time of the dominant kernel: raw C-ABI launches into preallocated buffers, CUDA events on the
     # launching stream, no allocation or host sync between launches
-    tc_train = train and args.precision == "bf16"
+    tc_train = train and args.precision == "bf16" and not cont_adj
     fp32_accepted = None
     with torch.no_grad():
         table, zemb = model.zone_tables(zfeat, csr)
@@ -554,13 +558,14 @@ def run_ours(args):
         "metric": METRIC + (" fwd+bwd" if train else " fwd (inference)"), "value": value, "unit": "agent-steps/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": ("strong" if strong else "weak"), "vs_baseline": None,
-        "dtype": "f32" if args.precision == "f32" else ("fp16 weights x split-fp16 (hi+lo) activations fwd / bf16 bwd operands (fp32 accumulate, fp32 state)" if (train and adaptive) else ("fp16 fwd / bf16 bwd operands (fp32 accumulate, fp32 state)" if train else "fp16 operands on tcgen05 (fp32 accumulate, fp32 state)")), "data": "synthetic",
+        "dtype": "f32" if args.precision == "f32" else "fp16 weights x split-fp16 (hi+lo) activations in the forward solve / fp32 FFMA kernels for the augmented adjoint system" if cont_adj else ("fp16 weights x split-fp16 (hi+lo) activations fwd / bf16 bwd operands (fp32 accumulate, fp32 state)" if (train and adaptive) else ("fp16 fwd / bf16 bwd operands (fp32 accumulate, fp32 state)" if train else "fp16 operands on tcgen05 (fp32 accumulate, fp32 state)")), "data": "synthetic",
         # equal-work figure: simulated agent-days (whole trajectories, forward + backward) per second, independent of how
         # many solver steps the adaptive controller needed
         "agent_days_per_s": B_total * args.steps / (ms * 1e-3),
         "config": {"workload": cfg["name"], "agents_total": B_total, "agents_per_gpu": B, "zones": cfg["Z"], "time_points": T,
                    "solver": cfg["method"], "agent_chunk": chunk, "agent_chunks": [e - s for s, e in bounds], "saved_operands": (args.saved_operands if (train and cfg["method"] == "dopri5" and args.precision == "bf16") else None),
                    "precision": args.precision, "loss": (args.loss if train else None),
+                   "adjoint_mode": (args.adjoint_mode if cfg.get("adjoint") else None),
                    "solver_steps": ({"accepted_per_trajectory": acc_per, "rejected_per_trajectory": rej_per,
                                      "fp32_accepted_per_trajectory": fp32_accepted,
                                      "accepted_steps_vs_fp32": (acc_per / fp32_accepted if fp32_accepted else None),
@@ -727,6 +732,9 @@ def main():
                     help="dopri5 training: what an accepted attempt's forward launch keeps for the backward pass as operand images "
                          "(all: stage inputs + hidden activations + ReLU masks, the backward kernel recomputes nothing; inputs: "
                          "stage inputs only; none: the backward pass rebuilds everything from (y, a_j))")
+    ap.add_argument("--adjoint-mode", default="discrete", choices=["discrete", "continuous"],
+                    help="--workload c5 (the odeint_adjoint seam): discrete adjoint of the accepted steps on the tensor-core stage path, or "
+                         "torchdiffeq's continuous adjoint (no saved steps; augmented system on the fp32 kernels)")
     ap.add_argument("--solver", default="", choices=["", "rk4", "dopri5"], help="override the workload's solver")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--loss", default="traj", choices=["traj", "ce"],
