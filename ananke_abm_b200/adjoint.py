@@ -91,8 +91,14 @@ class _ContinuousAdjoint(torch.autograd.Function):
         adj_options = dict(options or {})
         for k_ in ("precision", "error_norm", "forward_operands", "fp16_forward", "group", "adjoint_mode", "saved_operands"):
             adj_options.pop(k_, None)      # forward-solve switches of the tensor-core path mean nothing to the augmented system
+        # torchdiffeq adjoint.py `handle_adjoint_norm_`: adjoint_options["norm"] == "seminorm" keeps the parameter adjoints out of
+        # the accepted-error norm (they are integrals, nothing depends on them: Kidger et al., "Hey, that's not an ODE"); the
+        # default is the mixed norm over every component.  A callable norm is not supported by the fused error-norm kernel.
+        adj_norm = adj_options.pop("norm", None)
+        if adj_norm is not None and adj_norm != "seminorm":
+            raise NotImplementedError("adjoint_options['norm']: only 'seminorm' (or nothing: torchdiffeq's default mixed norm) is supported")
         if method == "dopri5":
-            adj_options["segments"] = segments
+            adj_options["segments"] = segments[:2] if adj_norm == "seminorm" else segments
             if spec is not None:
                 adj_options["time_as_float"] = True
         with torch.no_grad():

@@ -148,9 +148,14 @@ class ModeSepModel(nn.Module):
             return sdeint(_ScaledSDE(self.odefunc, self.config.sde_noise_strength), y0, times_union,
                           method=self.config.sde_method, dt=self.config.sde_dt, seed=getattr(self.config, "sde_seed", None))
         # config.adjoint (not a reference field): go through the odeint_adjoint seam (latent_ode/architecture/ode_components.py:50)
-        solve = odeint_adjoint if getattr(self.config, "adjoint", False) else odeint
-        return solve(self.odefunc, y0, times_union, method=self.config.ode_method, rtol=self.config.rtol,
-                     atol=self.config.atol, options=_solver_options(self.config))
+        if getattr(self.config, "adjoint", False):
+            extra = {}
+            if getattr(self.config, "adjoint_options", None) and getattr(self.config, "adjoint_mode", "continuous") != "discrete":
+                extra["adjoint_options"] = dict(self.config.adjoint_options)      # e.g. {"norm": "seminorm"} (torchdiffeq adjoint.py)
+            return odeint_adjoint(self.odefunc, y0, times_union, method=self.config.ode_method, rtol=self.config.rtol,
+                                  atol=self.config.atol, options=_solver_options(self.config), **extra)
+        return odeint(self.odefunc, y0, times_union, method=self.config.ode_method, rtol=self.config.rtol,
+                      atol=self.config.atol, options=_solver_options(self.config))
 
     def head(self, y_path: torch.Tensor):
         E, H = self.config.emb_dim, self.config.context_dim

@@ -44,9 +44,14 @@ class GATODEModel(nn.Module):
         return torch.cat([p0, torch.zeros_like(p0), h], dim=-1)
 
     def integrate(self, y0, times_union) -> torch.Tensor:
-        solve = odeint_adjoint if getattr(self.config, "adjoint", False) else odeint     # the odeint_adjoint seam on request
-        return solve(self.odefunc, y0, times_union, method=self.config.ode_method, rtol=self.config.rtol,
-                     atol=self.config.atol, options=_solver_options(self.config))
+        if getattr(self.config, "adjoint", False):                                       # the odeint_adjoint seam on request
+            extra = {}
+            if getattr(self.config, "adjoint_options", None) and getattr(self.config, "adjoint_mode", "continuous") != "discrete":
+                extra["adjoint_options"] = dict(self.config.adjoint_options)             # e.g. {"norm": "seminorm"} (torchdiffeq adjoint.py)
+            return odeint_adjoint(self.odefunc, y0, times_union, method=self.config.ode_method, rtol=self.config.rtol,
+                                  atol=self.config.atol, options=_solver_options(self.config), **extra)
+        return odeint(self.odefunc, y0, times_union, method=self.config.ode_method, rtol=self.config.rtol,
+                      atol=self.config.atol, options=_solver_options(self.config))
 
     def head(self, y_path, class_table):
         E, H = self.config.emb_dim, self.config.context_dim

@@ -156,7 +156,8 @@ def build_model(cfg, precision, device, saved_operands="all", adjoint_mode="disc
     # c5 = the odeint_adjoint seam.  "discrete" (default of the bench): the explicit discrete-adjoint opt-in on the tensor-core stage
     # path.  "continuous": torchdiffeq's own scheme -- forward without saved steps, backward = the augmented system [y, a_y, a_theta]
     # integrated per output interval with f and its vector-Jacobian products on the fp32 kernels (O(1) memory in solver steps)
-    mc.adjoint_mode = adjoint_mode
+    mc.adjoint_mode = "continuous" if adjoint_mode.startswith("continuous") else adjoint_mode
+    mc.adjoint_options = {"norm": "seminorm"} if adjoint_mode == "continuous-seminorm" else None
     mc.error_norm = "global"                 # N > 1: one RMS error norm over all ranks' agents, as a single process would use
     mc.saved_operands = saved_operands
     model = ab.GATODEModel(7, mc, heads=cfg["heads"]).to(device)
@@ -241,7 +242,7 @@ def run_ours(args):
     # agents): 1 M agents = 7,813 tiles = 26.4 waves run as 7 + 7 + 7 + 6 waves (four equal parts would each pay a partial wave);
     # the saved steps of ONE chunk live in HBM (peak_mem_gb in the JSON line)
     chunk_cap = args.chunk
-    cont_adj = bool(cfg.get("adjoint", False)) and args.adjoint_mode == "continuous"
+    cont_adj = bool(cfg.get("adjoint", False)) and args.adjoint_mode.startswith("continuous")
     if train and cfg["method"] == "dopri5" and args.precision == "bf16" and not cont_adj:
         # keep one chunk's saved steps inside the memory that is actually free (measured per agent of a chunk at ~30 accepted steps:
         # 471 KB with saved_operands = all, 288 KB inputs, 112 KB none; 15 % headroom for a longer step sequence)
@@ -732,7 +733,7 @@ def main():
                     help="dopri5 training: what an accepted attempt's forward launch keeps for the backward pass as operand images "
                          "(all: stage inputs + hidden activations + ReLU masks, the backward kernel recomputes nothing; inputs: "
                          "stage inputs only; none: the backward pass rebuilds everything from (y, a_j))")
-    ap.add_argument("--adjoint-mode", default="discrete", choices=["discrete", "continuous"],
+    ap.add_argument("--adjoint-mode", default="discrete", choices=["discrete", "continuous", "continuous-seminorm"],
                     help="--workload c5 (the odeint_adjoint seam): discrete adjoint of the accepted steps on the tensor-core stage path, or "
                          "torchdiffeq's continuous adjoint (no saved steps; augmented system on the fp32 kernels)")
     ap.add_argument("--solver", default="", choices=["", "rk4", "dopri5"], help="override the workload's solver")

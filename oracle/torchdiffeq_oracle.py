@@ -420,10 +420,16 @@ class _OdeintAdjoint(torch.autograd.Function):
                 vjp_params = [torch.zeros_like(p) if v is None else v for p, v in zip(adjoint_params, vjp_params)]
                 return (torch.zeros_like(t_), func_eval, vjp_y, *vjp_params)
 
+            # adjoint.py `handle_adjoint_norm_`: "seminorm" = the default mixed norm without the parameter adjoints
+            adjoint_options = dict(adjoint_options)
+            if adjoint_options.get("norm") == "seminorm":
+                keep = _mixed_norm_factory([a.shape for a in aug_state[:3]])      # (t, y, a_y) lead the flattened state
+                adjoint_options["norm"] = keep
+
             for i in range(len(t) - 1, 0, -1):
                 sol = odeint(augmented_dynamics, tuple(aug_state), t[i - 1:i + 1].flip(0),
                              rtol=adjoint_rtol, atol=adjoint_atol, method=adjoint_method,
-                             options=adjoint_options)
+                             options=dict(adjoint_options))
                 aug_state = [a[1] for a in sol]
                 aug_state[1] = y[i - 1]
                 aug_state[2] = aug_state[2] + grad_y[i - 1]

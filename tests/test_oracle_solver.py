@@ -162,3 +162,36 @@ def test_adjoint_matches_autograd_through_solver(method):
     tol = 2e-4 if method == "rk4" else 1e-6      # rk4 on 8 coarse steps: continuous vs discrete adjoint differ at O(h^4)
     for a, b in zip(g_direct, g_adj):
         assert torch.allclose(a, b, rtol=tol, atol=tol), float((a - b).abs().max())
+
+
+def test_adjoint_seminorm_ignores_parameter_adjoints_in_the_step_control():
+    """adjoint.py `handle_adjoint_norm_`: adjoint_options = {"norm": "seminorm"} keeps the parameter adjoints out of the accepted-error
+    norm.  The gradients still agree with autograd through the solver (to the tolerance of the solve), and the backward solve takes
+    no more attempts than under the default mixed norm -- fewer when the parameter adjoints are what the mixed norm was resolving."""
+    f = _Lin()
+    calls = {"n": 0}
+    fwd = f.forward
+
+    def counted(t, y):
+        calls["n"] += 1
+        return fwd(t, y)
+    f.forward = counted
+    y0 = torch.tensor([[0.3, -0.2, 0.5], [0.1, 0.4, -0.6]], dtype=torch.float64, requires_grad=True)
+    t = torch.linspace(0, 1.0, 4, dtype=torch.float64)
+    w = torch.arange(1, 1 + t.numel() * 6, dtype=torch.float64).view(t.numel(), 2, 3) * 10.0
+    kw = dict(method="dopri5", rtol=1e-6, atol=1e-8)
+    y = tdq.odeint(f, y0, t, **kw)
+    (y * w).sum().backward()
+    g_direct = [y0.grad.clone()] + [p.grad.clone() for p in f.parameters()]
+    res = {}
+    for name, ao in (("mixed", None), ("seminorm", {"norm": "seminorm"})):
+        y0.grad = None
+        f.zero_grad()
+        ya = tdq.odeint_adjoint(f, y0, t, adjoint_options=ao, **kw)
+        n0 = calls["n"]
+        (ya * w).sum().backward()
+        res[name] = (calls["n"] - n0, [y0.grad.clone()] + [p.grad.clone() for p in f.parameters()])
+    assert res["seminorm"][0] <= res["mixed"][0], (res["seminorm"][0], res["mixed"][0])
+    for name in res:
+        for a, b in zip(g_direct, res[name][1]):
+            assert torch.allclose(a, b, rtol=2e-4, atol=2e-4 * float(a.abs().max())), (name, float((a - b).abs().max()))
