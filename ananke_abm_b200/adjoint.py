@@ -114,8 +114,40 @@ class _ContinuousAdjoint(torch.autograd.Function):
         return (None, a_y.view(shape), None, None, *outs)
 
 
+def _tensor_core_rk4(func, y0, t, method, options, adjoint_method, adjoint_options, adjoint_params):
+    """The fixed-grid rk4 solve of a recognised drift in the tensor-core mode (options['precision'] = 'bf16'): forward and
+    augmented backward system on the tcgen05 stage kernels (adjoint_tc.py).  -> the solution, or None when the call is not of
+    that form (other solver, strict fp32, a generic func, hand-picked adjoint_params, decreasing t)."""
+    from .odeint import _DEFAULT_PRECISION, _check_t, _require_cuda
+    from .drift import describe_drift
+    opts = dict(options or {})
+    if method != "rk4" or (adjoint_method is not None and adjoint_method != "rk4"):
+        return None
+    if opts.get("precision", _DEFAULT_PRECISION["value"]) != "bf16" or not torch.is_tensor(y0) or y0.dim() != 2 or y0.dtype != torch.float32:
+        return None
+    spec = describe_drift(func)
+    if spec is None or not spec.tc_stage_supported() or y0.shape[1] != spec.state_dim or y0.shape[0] == 0:
+        return None
+    if adjoint_params is not None:
+        want, have = {id(p) for p in adjoint_params if p.requires_grad}, {id(p) for p in spec.params}
+        if want != have:
+            return None
+    _require_cuda(y0, "y0")
+    t_host = _check_t(t)
+    if t_host.numel() > 1 and bool(t_host[0] > t_host[1]):
+        return None
+    step = opts.get("step_size")
+    adj_step = step if adjoint_options is None else dict(adjoint_options).get("step_size")
+    from .adjoint_tc import _ContinuousAdjointRK4TC
+    return _ContinuousAdjointRK4TC.apply(y0, t, spec.flat_params(), spec, t_host, None if step is None else float(step),
+                                         None if adj_step is None else float(adj_step), opts.get("forward_operands"))
+
+
 def continuous_adjoint(func, y0, t, *, rtol, atol, method, options, adjoint_rtol=None, adjoint_atol=None,
                        adjoint_method=None, adjoint_options=None, adjoint_params=None):
+    out = _tensor_core_rk4(func, y0, t, method, options, adjoint_method, adjoint_options, adjoint_params)
+    if out is not None:
+        return out
     if adjoint_params is None:
         adjoint_params = tuple(p for p in func.parameters() if p.requires_grad)
     else:

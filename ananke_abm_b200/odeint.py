@@ -488,12 +488,16 @@ def odeint(func, y0, t, *, rtol: float = 1e-7, atol: float = 1e-9, method: Optio
                 raise _lib.Ab200Error("error_norm='global' needs at least one agent on every rank (and the same number of solves "
                                       "per rank): an empty shard cannot take part in the per-attempt all-reduce")
         return y0.unsqueeze(0).repeat(t_host.numel(), *([1] * y0.dim()))
-    precision = _lib.PRECISIONS[options.pop("precision", _DEFAULT_PRECISION["value"])]
+    prec_name = options.pop("precision", _DEFAULT_PRECISION["value"])
+    precision = _lib.PRECISIONS[prec_name]
 
     decreasing = t_host.numel() > 1 and bool(t_host[0] > t_host[1])
     spec = describe_drift(func) if (y0.dim() == 2 and not decreasing) else None
 
     if method == "rk4":
+        step_size = options.pop("step_size", None)
+        if step_size is not None and t_host.numel() > 1:
+            return _rk4_step_size(func, y0, t, t_host, float(step_size), dict(options, precision=prec_name))
         time_as_float = bool(options.pop("time_as_float", False))
         for k in ("dtype", "norm", "segments", "adjoint_mode"):
             options.pop(k, None)
@@ -545,6 +549,33 @@ def odeint(func, y0, t, *, rtol: float = 1e-7, atol: float = 1e-9, method: Optio
         _LAST["solver"] = solver
         return solver.integrate(th)
     raise ValueError(f'Invalid method "{method}".')
+
+
+def _rk4_step_size(func, y0, t, t_host, step_size: float, options: dict):
+    """torchdiffeq solvers.py `FixedGridODESolver` with options['step_size']: the solver steps over t[0] + k step_size (last
+    point moved onto t[-1]) and every requested time is a LINEAR interpolant of the two grid rows around it (the grid row itself
+    where they coincide).  General form: solve on the grid through the path `odeint` would take anyway, then interpolate with
+    torch ops (differentiable).  It materialises every grid row; the memory-light variant that keeps two state buffers is the
+    tensor-core continuous adjoint (adjoint_tc.py)."""
+    import numpy as np
+    from .adjoint_tc import step_grid
+    th = [float(v) for v in t_host.tolist()]
+    npdt = np.float64 if t_host.dtype == torch.float64 else np.float32
+    grid = step_grid(th[0], th[-1], step_size, npdt)
+    sign = 1.0 if th[-1] >= th[0] else -1.0
+    yg = odeint(func, y0, torch.tensor(grid, dtype=t.dtype, device=y0.device), method="rk4", options=options)
+    rows, j = [yg[0]], 1
+    for n in range(len(grid) - 1):
+        t0, t1 = grid[n], grid[n + 1]
+        while j < len(th) and sign * t1 >= sign * th[j]:
+            if th[j] == t1:
+                rows.append(yg[n + 1])
+            elif th[j] == t0:
+                rows.append(yg[n])
+            else:
+                rows.append(yg[n] + ((th[j] - t0) / (t1 - t0)) * (yg[n + 1] - yg[n]))
+            j += 1
+    return torch.stack(rows, dim=0)
 
 
 def _wrap_func(func, y0, decreasing: bool):

@@ -158,6 +158,7 @@ def build_model(cfg, precision, device, saved_operands="all", adjoint_mode="disc
     # integrated per output interval with f and its vector-Jacobian products on the fp32 kernels (O(1) memory in solver steps)
     mc.adjoint_mode = "continuous" if adjoint_mode.startswith("continuous") else adjoint_mode
     mc.adjoint_options = {"norm": "seminorm"} if adjoint_mode == "continuous-seminorm" else None
+    mc.step_size = cfg.get("step_size")      # rk4 only: torchdiffeq's fixed-grid option (continuous-rk4: 0.25 h over t = [0, 24])
     mc.error_norm = "global"                 # N > 1: one RMS error norm over all ranks' agents, as a single process would use
     mc.saved_operands = saved_operands
     model = ab.GATODEModel(7, mc, heads=cfg["heads"]).to(device)
@@ -199,6 +200,14 @@ def _config_for(args):
     cfg = dict(WORKLOADS[args.workload])
     if args.agents:
         cfg["B"] = args.agents
+    if cfg.get("adjoint") and args.adjoint_mode == "continuous-rk4":
+        # configs[4] as named: ONE solve over all agents, torchdiffeq's continuous adjoint with the fixed-grid rk4 solver on the
+        # tensor-core stage kernels (adjoint_tc.py).  t = [0, 24] with options['step_size'] = 0.25: 96 steps per day forward, 96
+        # augmented steps backward, and only y(0), y(24) exist as rows -- memory does not grow with the step count.
+        cfg["method"], cfg["T"], cfg["step_size"], cfg["grid_steps"] = "rk4", 2, 0.25, 96
+        cfg["name"] = ("configs[4]: 8M agents x 10k zones, 4-head GAT, rk4 step_size=0.25 (96 steps/day), odeint_adjoint = continuous "
+                       "adjoint on the tensor-core stage kernels, fwd+bwd, one solve (no saved steps)")
+        return cfg
     if args.solver:
         cfg["method"] = args.solver
         cfg["name"] = cfg["name"].replace("96 RK4 steps", "dopri5 rtol=atol=1e-5") if args.solver == "dopri5" else \
@@ -243,6 +252,9 @@ def run_ours(args):
     # the saved steps of ONE chunk live in HBM (peak_mem_gb in the JSON line)
     chunk_cap = args.chunk
     cont_adj = bool(cfg.get("adjoint", False)) and args.adjoint_mode.startswith("continuous")
+    cont_rk4 = cont_adj and args.adjoint_mode == "continuous-rk4"
+    if cont_rk4:
+        chunk_cap = max(chunk_cap, hi - lo)      # the point of the scheme: all agents in one solve
     if train and cfg["method"] == "dopri5" and args.precision == "bf16" and not cont_adj:
         # keep one chunk's saved steps inside the memory that is actually free (measured per agent of a chunk at ~30 accepted steps:
         # 471 KB with saved_operands = all, 288 KB inputs, 112 KB none; 15 % headroom for a longer step sequence)
@@ -273,7 +285,7 @@ def run_ours(args):
             counter["accepted"] += st.n_accepted
             counter["rejected"] += st.n_rejected
         else:
-            counter["agent_steps"] += nb * (T - 1)
+            counter["agent_steps"] += nb * cfg.get("grid_steps", T - 1)
 
     def hot_step(hm, wk, tr, tt):
         """device-resident pass over all agents of this rank; returns a small device tensor"""
@@ -370,11 +382,12 @@ def run_ours(args):
 
     # kernel-only time of the dominant kernel: raw C-ABI launches into preallocated buffers, CUDA events on the
     # launching stream, no allocation or host sync between launches
-    tc_train = train and args.precision == "bf16" and not cont_adj
+    tc_train = train and args.precision == "bf16" and (not cont_adj or cont_rk4)
     fp32_accepted = None
     with torch.no_grad():
         table, zemb = model.zone_tables(zfeat, csr)
-        y0 = model.initial_state(table, zemb, d_home[:chunk], d_work[:chunk], d_traits[:chunk]).contiguous()
+        kchunk = min(chunk, 1_000_064) if cont_rk4 else chunk      # kernel timing of the 8M-agent solve: on 1M of its agents
+        y0 = model.initial_state(table, zemb, d_home[:kchunk], d_work[:kchunk], d_traits[:kchunk]).contiguous()
         spec = ab.describe_drift(model.odefunc)
         wflat = spec.flat_params().detach().contiguous()
         if adaptive and rank == 0:
@@ -469,6 +482,8 @@ def run_ours(args):
             GX = [st.blocked_zeros(Bc, 160, dev) for _ in range(7)]
             dtk = 0.25
             tab, first, last = (st.DOPRI5, 1, 6) if adaptive else (st.RK38, 0, 3)      # the fused launch of one step's backward stages
+            if cont_rk4:
+                first = 3      # the continuous adjoint issues ONE stage per launch (upstream = the stage value of a_v)
             times = [1.0 + tab.c[i] * dtk for i in range(last + 1)]
             n_fused = last - first + 1
             eng.backward_begin(Bc, n_fused)
@@ -492,7 +507,7 @@ def run_ours(args):
             kern_bytes_unit = ALG_BYTES_FWDBWD / 4.0
             # DRAM bytes per agent-stage of this kernel from `ncu --set full` (dram__bytes_read.sum + dram__bytes_write.sum =
             # 5.746 + 7.312 GB for the fused 6-stage launch over 333,440 agents; profiles/r02_stage_kernels_ncu_summary.txt)
-            kern_traffic_unit = (5.745611e9 + 7.312489e9) / (333440 * 6)
+            kern_traffic_unit = None if cont_rk4 else (5.745611e9 + 7.312489e9) / (333440 * 6)
             del eng, yb, A, Gb, GX
         else:
             prec = {"f32": 0, "bf16": 1}[args.precision]
@@ -555,11 +570,13 @@ def run_ours(args):
         fl_fwd, fl_fb = ALG_FLOP_FWD_DOPRI5, (ALG_FLOP_FWDBWD_DOPRI5_SAVED if stage_kernels else ALG_FLOP_FWDBWD_DOPRI5)
     else:
         fl_fwd, fl_fb = ALG_FLOP_FWD, ALG_FLOP_FWDBWD
+        if cont_rk4:      # per grid step: 4 evaluations forward; backward 4 x (y stage + recompute inside the VJP launch + dgrad + wgrad)
+            fl_fb = 20 * ALG_FLOP_EVAL
     out = {
         "metric": METRIC + (" fwd+bwd" if train else " fwd (inference)"), "value": value, "unit": "agent-steps/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
         "higher_is_better": True, "scaling": ("strong" if strong else "weak"), "vs_baseline": None,
-        "dtype": "f32" if args.precision == "f32" else "fp16 weights x split-fp16 (hi+lo) activations in the forward solve / fp32 FFMA kernels for the augmented adjoint system" if cont_adj else ("fp16 weights x split-fp16 (hi+lo) activations fwd / bf16 bwd operands (fp32 accumulate, fp32 state)" if (train and adaptive) else ("fp16 fwd / bf16 bwd operands (fp32 accumulate, fp32 state)" if train else "fp16 operands on tcgen05 (fp32 accumulate, fp32 state)")), "data": "synthetic",
+        "dtype": "f32" if args.precision == "f32" else "fp16 operands in the forward stages / bf16 operands in the vector-Jacobian products of the augmented adjoint system (tcgen05, fp32 accumulate; fp32 y, a_y, a_theta)" if cont_rk4 else "fp16 weights x split-fp16 (hi+lo) activations in the forward solve / fp32 FFMA kernels for the augmented adjoint system" if cont_adj else ("fp16 weights x split-fp16 (hi+lo) activations fwd / bf16 bwd operands (fp32 accumulate, fp32 state)" if (train and adaptive) else ("fp16 fwd / bf16 bwd operands (fp32 accumulate, fp32 state)" if train else "fp16 operands on tcgen05 (fp32 accumulate, fp32 state)")), "data": "synthetic",
         # equal-work figure: simulated agent-days (whole trajectories, forward + backward) per second, independent of how
         # many solver steps the adaptive controller needed
         "agent_days_per_s": B_total * args.steps / (ms * 1e-3),
@@ -571,7 +588,7 @@ def run_ours(args):
                                      "fp32_accepted_per_trajectory": fp32_accepted,
                                      "accepted_steps_vs_fp32": (acc_per / fp32_accepted if fp32_accepted else None),
                                      "fp32_note": "same solver, drift in strict fp32 (FFMA kernels), first %d agents of rank 0" % min(2048, chunk),
-                                     "rtol": model.config.rtol, "atol": model.config.atol} if adaptive else {"grid_intervals": T - 1}),
+                                     "rtol": model.config.rtol, "atol": model.config.atol} if adaptive else {"grid_intervals": cfg.get("grid_steps", T - 1), "step_size": cfg.get("step_size")}),
                    "l2": "trajectory rows written per step (%.0f MB) exceed L2; weights are L2-resident by design" % (chunk * T * 640 / 1e6)},
         "roofline": {**roof_head,
                      "traffic": (kern_traffic_unit * kern_units if kern_traffic_unit else None),
@@ -599,7 +616,7 @@ def run_ours(args):
         "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9,
         "clocks": clocks,
     }
-    if not args.no_cpu_baseline and world == 1:      # the CPU leg is timed on rank 0 at N = 1 only (torchrun pins OMP threads)
+    if not args.no_cpu_baseline and world == 1 and not cont_rk4:      # the CPU leg is timed on rank 0 at N = 1 only (torchrun pins OMP threads)
         out["cpu_baseline"] = reference_step_timer(cfg, train, "cpu", steps=1, warmup=0, budget_agents=args.ref_agents)
     print(json.dumps(out))
     if world > 1:
@@ -733,7 +750,7 @@ def main():
                     help="dopri5 training: what an accepted attempt's forward launch keeps for the backward pass as operand images "
                          "(all: stage inputs + hidden activations + ReLU masks, the backward kernel recomputes nothing; inputs: "
                          "stage inputs only; none: the backward pass rebuilds everything from (y, a_j))")
-    ap.add_argument("--adjoint-mode", default="discrete", choices=["discrete", "continuous", "continuous-seminorm"],
+    ap.add_argument("--adjoint-mode", default="discrete", choices=["discrete", "continuous", "continuous-seminorm", "continuous-rk4"],
                     help="--workload c5 (the odeint_adjoint seam): discrete adjoint of the accepted steps on the tensor-core stage path, or "
                          "torchdiffeq's continuous adjoint (no saved steps; augmented system on the fp32 kernels)")
     ap.add_argument("--solver", default="", choices=["", "rk4", "dopri5"], help="override the workload's solver")

@@ -132,16 +132,50 @@ def rk4_alt_step(func, t0, dt, t1, y0):
     return (k1 + 3 * (k2 + k3) + k4) * dt * 0.125
 
 
-def _rk4_fixed_grid(func, y0, t):
-    # solvers.py `FixedGridODESolver.integrate` with the default grid constructor (grid == t), so every
-    # output lands exactly on a step end and `_linear_interp` returns y1 itself.
+def _grid_from_step_size(t, step_size):
+    """solvers.py `FixedGridODESolver._grid_constructor_from_step_size`: t[0] + k * step_size, the last point moved onto t[-1]."""
+    niters = int(torch.ceil((t[-1] - t[0]) / step_size + 1).item())
+    grid = torch.arange(0, niters, dtype=t.dtype, device=t.device) * step_size + t[0]
+    grid[-1] = t[-1]
+    return grid
+
+
+def _linear_interp(t0, t1, y0, y1, t):
+    """solvers.py `FixedGridODESolver._linear_interp`."""
+    if t == t0:
+        return y0
+    if t == t1:
+        return y1
+    slope = (t - t0) / (t1 - t0)
+    return y0 + slope * (y1 - y0)
+
+
+def _rk4_fixed_grid(func, y0, t, step_size=None):
+    # solvers.py `FixedGridODESolver.integrate`.  Default grid constructor: grid == t, every output lands exactly on a
+    # step end and `_linear_interp` returns y1 itself.  options["step_size"]: the solver steps over t[0] + k * step_size
+    # and the outputs are linear interpolants between the two grid points around each requested time.
+    if step_size is None:
+        sol = [y0]
+        y = y0
+        for i in range(t.shape[0] - 1):
+            t0, t1 = t[i], t[i + 1]
+            dt = t1 - t0
+            y = y + rk4_alt_step(func, t0, dt, t1, y)
+            sol.append(y)
+        return torch.stack(sol, dim=0)
+    grid = _grid_from_step_size(t, step_size)
+    assert grid[0] == t[0] and grid[-1] == t[-1]
     sol = [y0]
+    j = 1
     y = y0
-    for i in range(t.shape[0] - 1):
-        t0, t1 = t[i], t[i + 1]
+    for i in range(grid.shape[0] - 1):
+        t0, t1 = grid[i], grid[i + 1]
         dt = t1 - t0
-        y = y + rk4_alt_step(func, t0, dt, t1, y)
-        sol.append(y)
+        y1 = y + rk4_alt_step(func, t0, dt, t1, y)
+        while j < t.shape[0] and t1 >= t[j]:
+            sol.append(_linear_interp(t0, t1, y, y1, t[j]))
+            j += 1
+        y = y1
     return torch.stack(sol, dim=0)
 
 
@@ -361,7 +395,7 @@ def odeint(func: Callable, y0, t: torch.Tensor, *, rtol: float = 1e-7, atol: flo
     if method == "rk4":
         options.pop("norm", None)
         options.pop("dtype", None)
-        sol = _rk4_fixed_grid(f, y0, t)
+        sol = _rk4_fixed_grid(f, y0, t, options.pop("step_size", None))
     elif method == "euler":
         options.pop("norm", None)
         sol = _euler_fixed_grid(f, y0, t)
