@@ -17,7 +17,7 @@ feeds back into the dynamics, so its stage values are not formed: the stage's up
 c_s = -h b_s (h < 0 going backward) and the weight-gradient accumulators ARE a_theta.  The vector-Jacobian product is
 linear in its upstream, so gx comes back scaled by c_s and is divided out in the stage algebra.
 
-The stage algebra of a_y (a handful of axpy passes per stage) runs as torch ops on views of the tile-blocked buffers.
+The stage algebra of a_y is two fused elementwise passes per stage (`ab200_aug_stage_prepare` / `ab200_aug_stage_finish`).
 Every evaluation of A and of its vector-Jacobian product is a tcgen05 kernel (fp16 / bf16 operands, fp32 accumulate);
 y, a_y and a_theta are fp32.  Stated tolerance: that of the tensor-core path.
 """
@@ -99,9 +99,9 @@ def rk4_forward_rows(eng, y0: torch.Tensor, t_host: Sequence[float], step_size: 
 class _AugBuffers:
     def __init__(self, B: int, D: int, P: int, device, lay):
         self.A = [lay.zeros(B, P, device) for _ in range(3)]      # stage accelerations of the y part
-        self.U = lay.zeros(B, P, device)                          # upstream of the stage's vector-Jacobian product: c_s a_v
-        self.AS = lay.zeros(B, D, device)                         # stage value of a_y
-        self.KA = [lay.zeros(B, D, device) for _ in range(4)]     # stage derivatives of a_y
+        self.U = lay.zeros(B, P, device)                          # upstream of the stage's vector-Jacobian product: c_s a_v,s
+        self.ASP = lay.zeros(B, P, device)                        # p part of the stage value of a_y
+        self.KA = [lay.zeros(B, D, device) for _ in range(4)]     # stage derivatives of a_y (zeroed: padding rows stay zero)
         self.y_next = lay.zeros(B, D, device)
         self.a_next = lay.zeros(B, D, device)
 
@@ -109,36 +109,23 @@ class _AugBuffers:
 def _aug_step(eng, yb: torch.Tensor, ab: torch.Tensor, t0: float, t1: float, B: int, w: _AugBuffers):
     """one 3/8-rule step of the augmented system from t0 to t1 (h = t1 - t0, negative in the backward pass).
     Returns (y(t1), a_y(t1)) as buffers of `w` swapped with the inputs; a_theta accumulates inside the engine."""
-    D, P = eng.D, eng.P
     h = t1 - t0
-    w.a_next.copy_(ab)
     for s in range(4):
         cin = RK38.stage_input(s, h)
         ts = t1 if s == 3 else t0 + RK38.c[s] * h
-        # stage value of a_y:  a0 + h sum_j beta_sj ka_j
-        if s == 0:
-            a_s = ab
-        else:
-            a_s = w.AS
-            a_s.copy_(ab)
-            for j, bj in enumerate(RK38.beta[s]):
-                if bj != 0.0:
-                    a_s.add_(w.KA[j], alpha=h * bj)
         c = -h * RK38.b[s]
-        ap_s, av_s, _ = _views(a_s, D, P)
-        torch.mul(av_s, c, out=w.U.view(-1, P // 4, TM, 4))
+        # stage value of a_y:  a_s = a0 + h sum_j beta_sj ka_j  ->  its p part and the upstream  c a_s.v
+        src = [(w.KA[j], h * bj) for j, bj in enumerate(RK38.beta[s]) if bj != 0.0]
+        eng.aug_stage_prepare(ab, [k for k, _ in src], [x for _, x in src], c, B, w.ASP, w.U)
         # stage of y:  A_s = A(stage input); the last stage also writes y(t1)
         if s < 3:
             eng.stage_forward(yb, w.A[:s], cin, ts, B, a_out=w.A[s])
         else:
             eng.stage_forward(yb, w.A[:3], cin, ts, B, y_out=w.y_next, cout=RK38.combo(RK38.b, h))
-        # c_s J_A^T a_v  (+ the weight-gradient blobs of this stage with the same scale)
-        gx = w.KA[s]
-        eng.stage_backward(yb, w.A[:s], cin, ts, B, w.U, [], [], [], gx)
-        # ka_s = -[gx.p, a_p + gx.v, gx.h] / c_s   (in place)
-        gx.mul_(-1.0 / c)
-        _views(gx, D, P)[1].sub_(ap_s)
-        w.a_next.add_(gx, alpha=h * RK38.b[s])
+        # c J_A^T a_v,s  (+ the weight-gradient blobs of this stage, with the same scale)
+        eng.stage_backward(yb, w.A[:s], cin, ts, B, w.U, [], [], [], w.KA[s])
+        # ka_s = -[gx.p, a_p,s + gx.v, gx.h]  (in place) ;  a_next (+)= h b_s ka_s
+        eng.aug_stage_finish(w.KA[s], w.ASP, ab if s == 0 else w.a_next, w.a_next, -1.0 / c, h * RK38.b[s], s < 3, B)
     eng.flush()
     y_new, a_new = w.y_next, w.a_next
     w.y_next, w.a_next = yb, ab

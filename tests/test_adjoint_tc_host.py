@@ -94,6 +94,25 @@ class FakeEngine:
                 acc_.add_(gi)
         self.n_vjp += 1
 
+    def aug_stage_prepare(self, a0, ka, hb, c, B, as_p, u):
+        """the formula ab200_aug_stage_prepare implements, on views of the blocked buffers"""
+        D, P = self.D, self.P
+        a_s = a0.clone()
+        for k, w in zip(ka, hb):
+            a_s.add_(k, alpha=w)
+        ap, av, _ = adjoint_tc._views(a_s, D, P)
+        as_p.view(-1, P // 4, TM, 4).copy_(ap)
+        torch.mul(av, c, out=u.view(-1, P // 4, TM, 4))
+
+    def aug_stage_finish(self, gx, as_p, a_in, a_next, inv, hb, write_ka, B):
+        """the formula ab200_aug_stage_finish implements"""
+        D, P = self.D, self.P
+        ka = gx * inv
+        adjoint_tc._views(ka, D, P)[1].sub_(as_p.view(-1, P // 4, TM, 4))
+        a_next.copy_(a_in + hb * ka)
+        if write_ka:
+            gx.copy_(ka)
+
     def flush(self):
         pass
 
