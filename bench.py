@@ -272,7 +272,7 @@ def run_ours(args):
 
     adaptive = cfg["method"] == "dopri5"
     counter = {"agent_steps": 0, "accepted": 0, "rejected": 0, "solves": 0}
-    snap_idx = torch.arange(4, T, 8, device=dev)[:12] if train else None                    # 12 snap rows of the day grid
+    snap_idx = torch.arange(4, T, 8, device=dev)[:12] if (train and T > 4) else None        # 12 snap rows of the day grid
     snap_target = (torch.randint(0, cfg["Z"], (12, B), generator=torch.Generator().manual_seed(99 + rank)).to(dev)
                    if (train and args.loss == "ce") else None)
 
