@@ -143,7 +143,8 @@ def test_tc_continuous_adjoint_memory_does_not_grow_with_the_step_count():
         peaks.append(torch.cuda.max_memory_allocated(dev))
         grads.append(y.grad)
         assert torch.isfinite(y.grad).all()
-    assert peaks[1] <= peaks[0] * 1.02 + (1 << 20), peaks
+    # 88 more steps: a scheme that kept per-step state would add >= 88 x 40,000 x 640 B = 2.2 GB to the ~1 GB peak
+    assert peaks[1] <= peaks[0] * 1.10, peaks
 
 
 @pytest.mark.parametrize("B", [1, 127, 129, 1000])
