@@ -273,7 +273,7 @@ struct StageFwd2Args {
   int* status;
 };
 
-template <bool SAVE_ACTS>
+template <bool SAVE_ACTS, bool L2POL = false>
 __global__ void __launch_bounds__(THREADS, 1) stage_fwd2_tc_kernel(const __grid_constant__ StageFwd2Args a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bars[NSLOT + 1];
@@ -286,6 +286,8 @@ __global__ void __launch_bounds__(THREADS, 1) stage_fwd2_tc_kernel(const __grid_
   float* ct = reinterpret_cast<float*>(smem + f2::OFF_CT) + c.slot * HID;
   uint8_t* htile = smem + f2::OFF_HT + (uint32_t)c.slot * f2::SZ_HT;
   double err_local = 0.0;
+  uint64_t pol_keep = 0, pol_drop = 0;
+  if (L2POL) { pol_keep = l2_policy_keep(); pol_drop = l2_policy_drop(); }
 
 #pragma unroll 1
   for (int it = 0;; ++it) {
@@ -330,7 +332,10 @@ __global__ void __launch_bounds__(THREADS, 1) stage_fwd2_tc_kernel(const __grid_
           const float cp = sp.in.cpa[s], cv = sp.in.cva[s];
           float4 x[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) x[j] = *blk4(a.a[s], tile, AF4, f0 + j, c.row);   // coherent: may have been written by this launch
+          for (int j = 0; j < 8; ++j) {      // coherent: may have been written by this launch
+            const float4* ptr = blk4(a.a[s], tile, AF4, f0 + j, c.row);
+            x[j] = L2POL ? ld_l2hint(ptr, pol_keep) : *ptr;
+          }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             pin[4 * j] += cp * x[j].x; pin[4 * j + 1] += cp * x[j].y; pin[4 * j + 2] += cp * x[j].z; pin[4 * j + 3] += cp * x[j].w;
@@ -418,9 +423,11 @@ __global__ void __launch_bounds__(THREADS, 1) stage_fwd2_tc_kernel(const __grid_
         }
         if (sp.a_out != nullptr) {      // padding rows of the last tile are written as zeros: output buffers need no initialisation
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            *blk4(sp.a_out, tile, AF4, fq + j, c.row) = valid ? make_float4(ao[4 * j], ao[4 * j + 1], ao[4 * j + 2], ao[4 * j + 3])
-                                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int j = 0; j < 4; ++j) {
+            const float4 v4 = valid ? make_float4(ao[4 * j], ao[4 * j + 1], ao[4 * j + 2], ao[4 * j + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (L2POL && si + 1 < a.n_stage) st_l2hint(blk4(sp.a_out, tile, AF4, fq + j, c.row), v4, pol_keep);
+            else *blk4(sp.a_out, tile, AF4, fq + j, c.row) = v4;
+          }
         }
         if (want_y) {
           float po[16], vo[16], ep[16], ev[16];
@@ -442,7 +449,10 @@ __global__ void __launch_bounds__(THREADS, 1) stage_fwd2_tc_kernel(const __grid_
           for (int s = 0; s < n_a; ++s) {
             float4 x[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) x[j] = *blk4(a.a[s], tile, AF4, fq + j, c.row);
+            for (int j = 0; j < 4; ++j) {      // the launch's last use of a_j (only the final stage produces y_out): demote the line
+              const float4* ptr = blk4(a.a[s], tile, AF4, fq + j, c.row);
+              x[j] = L2POL ? ld_l2hint(ptr, pol_drop) : *ptr;
+            }
             const float cp = sp.out.cpa[s], cv = sp.out.cva[s], xp = sp.err.cpa[s], xv = sp.err.cva[s];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -562,6 +572,7 @@ int stage_fwd2_tc_multi(const ab200_drift_desc* d, const uint8_t* image, const f
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = k.ntiles < sms ? k.ntiles : sms;      // a partial wave uses one slot per CTA first
   auto kern = save_level >= 2 ? stage_fwd2_tc_kernel<true> : stage_fwd2_tc_kernel<false>;
+  if (k.flags & 128) kern = save_level >= 2 ? stage_fwd2_tc_kernel<true, true> : stage_fwd2_tc_kernel<false, true>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f2::SMEM_BYTES);
   if (e != cudaSuccess) { set_cuda_error(e); return AB200_ERR_CUDA; }
   kern<<<grid, THREADS, f2::SMEM_BYTES, st>>>(k);

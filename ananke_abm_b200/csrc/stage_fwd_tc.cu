@@ -81,7 +81,7 @@ int stage_flags() {
     // bits 16 / 32 skip the backward kernel's stores (timing experiments, results INVALID): honoured only together with
     // AB200_STAGE_TIMING_ONLY=1 so that a stray environment variable cannot silently corrupt gradients
     const char* u = getenv("AB200_STAGE_TIMING_ONLY");
-    if (!(u && atoi(u) == 1)) v &= 15;
+    if (!(u && atoi(u) == 1)) v &= (15 | 128);      // bit 128 (L2 eviction hints) changes no result
     f = v;
   }
   return f;

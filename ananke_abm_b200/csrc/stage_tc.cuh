@@ -348,6 +348,32 @@ __device__ __forceinline__ void stage_teardown(uint32_t tmem_base) {
 
 }  // namespace stc
 
+// L2 residency hints (kernel instantiations L2POL = true; backward kernel: default, AB200_STAGE_FLAGS bit 4 = off; forward attempt
+// kernel: AB200_STAGE_FLAGS bit 128 = on, it measured SLOWER there: 1,151 -> 1,207 us): the accelerations a_j of a forward attempt
+// (and the gx tiles of a fused backward launch) are written and re-read by the same thread over ~160 us while the launch streams ~600 MB of blobs through the 126 MB L2 (hit rate
+// 22 %).  Tag the a_out stores and the a_j loads of all but their last use evict_last, and the LAST use evict_first (demotes the
+// line so that dead lines do not pile up -- the un-demoted variant of round 2 was slower).
+__device__ __forceinline__ uint64_t l2_policy_keep() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_drop() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ float4 ld_l2hint(const float4* ptr, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(ptr), "l"(pol) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_l2hint(float4* ptr, const float4& v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;"
+               :: "l"(ptr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+}
+
 // tuning switches, read once from the environment (AB200_STAGE_FLAGS, default 0 = both off)
 int stage_flags();
 
