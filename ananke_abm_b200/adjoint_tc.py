@@ -12,12 +12,14 @@ torchdiffeq semantics (adjoint.py `OdeintAdjointMethod`, fixed_grid.py `RK4`, so
 Mapping onto the stage kernels.  The drift is second order, f = [v, A(p, v, h, t), 0], so with gx = J_A^T a_v:
   -a_y^T df/dy = -[ gx.p, a_p + gx.v, gx.h ]            (one `ab200_stage_backward` launch with upstream a_v)
   -a_y^T df/dtheta = -J_theta^T a_v                      (the blobs of the same launch, folded by `ab200_wgrad_accumulate`)
-and a Runge-Kutta stage of y is the usual combination of (y0, A_1 .. A_{s-1}) (`ab200_stage_forward`).  a_theta never
+and the Runge-Kutta stages of y are the usual combinations of (y0, A_1 .. A_{s-1}), independent of a_y: one fused forward launch
+per step (`ab200_stage_forward_fused`), as in the forward solve.  a_theta never
 feeds back into the dynamics, so its stage values are not formed: the stage's upstream gradient is scaled by
 c_s = -h b_s (h < 0 going backward) and the weight-gradient accumulators ARE a_theta.  The vector-Jacobian product is
 linear in its upstream, so gx comes back scaled by c_s and is divided out in the stage algebra.
 
-The stage algebra of a_y is two fused elementwise passes per stage (`ab200_aug_stage_prepare` / `ab200_aug_stage_finish`).
+The stage algebra of a_y is ONE fused elementwise pass per stage (`ab200_aug_stage_finish_prepare`: derivative of this stage, running
+solution, value and upstream of the next stage; `ab200_aug_stage_prepare` / `ab200_aug_stage_finish` open and close a step).
 Every evaluation of A and of its vector-Jacobian product is a tcgen05 kernel (fp16 / bf16 operands, fp32 accumulate);
 y, a_y and a_theta are fp32.  Stated tolerance: that of the tensor-core path.
 """
@@ -110,22 +112,28 @@ def _aug_step(eng, yb: torch.Tensor, ab: torch.Tensor, t0: float, t1: float, B: 
     """one 3/8-rule step of the augmented system from t0 to t1 (h = t1 - t0, negative in the backward pass).
     Returns (y(t1), a_y(t1)) as buffers of `w` swapped with the inputs; a_theta accumulates inside the engine."""
     h = t1 - t0
+    cins = [RK38.stage_input(s, h) for s in range(4)]
+    times = [t0 + RK38.c[s] * h for s in range(3)] + [t1]
+    # The y part of the augmented system does not depend on a_y: its four stages (A_1..A_3 and y(t1)) are ONE fused forward launch,
+    # exactly the step of the forward solve (the tile's y and A_j stay in L2 between the stages: 345 us instead of 4 x 169 us over
+    # 250,112 agents); the vector-Jacobian products below re-read A_1..A_3.
+    eng.stage_forward_fused(yb, w.A, [(s, cins[s], times[s], w.A[s] if s < 3 else None) for s in range(4)], B, y_out=w.y_next,
+                            cout=RK38.combo(RK38.b, h))
+    # stage value of a_y:  a_s = a0 + h sum_j beta_sj ka_j  ->  its p part (ASP) and the upstream  c_s a_s.v (U)
+    eng.aug_stage_prepare(ab, [], [], -h * RK38.b[0], B, w.ASP, w.U)
     for s in range(4):
-        cin = RK38.stage_input(s, h)
-        ts = t1 if s == 3 else t0 + RK38.c[s] * h
         c = -h * RK38.b[s]
-        # stage value of a_y:  a_s = a0 + h sum_j beta_sj ka_j  ->  its p part and the upstream  c a_s.v
-        src = [(w.KA[j], h * bj) for j, bj in enumerate(RK38.beta[s]) if bj != 0.0]
-        eng.aug_stage_prepare(ab, [k for k, _ in src], [x for _, x in src], c, B, w.ASP, w.U)
-        # stage of y:  A_s = A(stage input); the last stage also writes y(t1)
+        # c_s J_A^T a_v,s  (+ the weight-gradient blobs of this stage, with the same scale)
+        eng.stage_backward(yb, w.A[:s], cins[s], times[s], B, w.U, [], [], [], w.KA[s])
+        # ka_s = -[gx.p, a_p,s + gx.v, gx.h]  (in place) ;  a_next (+)= h b_s ka_s ;  and the next stage's ASP / U in the same pass
+        a_in = ab if s == 0 else w.a_next
         if s < 3:
-            eng.stage_forward(yb, w.A[:s], cin, ts, B, a_out=w.A[s])
+            nxt = RK38.beta[s + 1]
+            src = [(w.KA[j], h * nxt[j]) for j in range(s) if nxt[j] != 0.0]
+            eng.aug_stage_finish_prepare(w.KA[s], w.ASP, a_in, w.a_next, -1.0 / c, h * RK38.b[s], ab, [k for k, _ in src],
+                                         [x for _, x in src] + [h * nxt[s]], -h * RK38.b[s + 1], w.U, B)
         else:
-            eng.stage_forward(yb, w.A[:3], cin, ts, B, y_out=w.y_next, cout=RK38.combo(RK38.b, h))
-        # c J_A^T a_v,s  (+ the weight-gradient blobs of this stage, with the same scale)
-        eng.stage_backward(yb, w.A[:s], cin, ts, B, w.U, [], [], [], w.KA[s])
-        # ka_s = -[gx.p, a_p,s + gx.v, gx.h]  (in place) ;  a_next (+)= h b_s ka_s
-        eng.aug_stage_finish(w.KA[s], w.ASP, ab if s == 0 else w.a_next, w.a_next, -1.0 / c, h * RK38.b[s], s < 3, B)
+            eng.aug_stage_finish(w.KA[s], w.ASP, a_in, w.a_next, -1.0 / c, h * RK38.b[s], False, B)
     eng.flush()
     y_new, a_new = w.y_next, w.a_next
     w.y_next, w.a_next = yb, ab

@@ -62,6 +62,9 @@ int aug_stage_prepare(const ab200_drift_desc* d, const float* a0, const float* c
                       float* as_p, float* u, cudaStream_t st);
 int aug_stage_finish(const ab200_drift_desc* d, float* gx, const float* as_p, const float* a_in, float* a_next, float inv, float hb,
                      int write_ka, int64_t B, cudaStream_t st);
+int aug_stage_finish_prepare(const ab200_drift_desc* d, float* gx, float* as_p, const float* a_in, float* a_next, float inv, float hb,
+                             const float* a0, const float* const* ka, int n, const float* hbn, float cn, float* u, int64_t B,
+                             cudaStream_t st);
 int ga_assemble(const ab200_drift_desc* d, const float* base, const float* const* gx, int n, const float* dp, const float* dv,
                 int64_t B, float* out, cudaStream_t st);
 int stage_bwd_tc_multi(const ab200_drift_desc* d, const uint8_t* image, const float* y0, const float* const* a_ptrs,
@@ -425,6 +428,13 @@ int ab200_aug_stage_finish(const ab200_drift_desc* d, float* gx, const float* as
                            int32_t write_ka, int64_t B, ab200_stream_t stream) {
   if (!desc_ok(d) || !gx || !as_p || !a_in || !a_next || B <= 0) return AB200_ERR_BAD_ARG;
   return aug_stage_finish(d, gx, as_p, a_in, a_next, inv, hb, write_ka, B, (cudaStream_t)stream);
+}
+
+int ab200_aug_stage_finish_prepare(const ab200_drift_desc* d, float* gx, float* as_p, const float* a_in, float* a_next, float inv, float hb,
+                                   const float* a0, const float* const* ka, int32_t n, const float* hbn_host, float c_next, float* u,
+                                   int64_t B, ab200_stream_t stream) {
+  if (!desc_ok(d) || !gx || !as_p || !a_in || !a_next || !a0 || !hbn_host || !u || B <= 0 || n < 0 || (n > 0 && !ka)) return AB200_ERR_BAD_ARG;
+  return aug_stage_finish_prepare(d, gx, as_p, a_in, a_next, inv, hb, a0, ka, n, hbn_host, c_next, u, B, (cudaStream_t)stream);
 }
 
 int ab200_stage_upstream(const ab200_drift_desc* d, const float* g_base, const float* const* gx, int32_t n_g, const float* dp_host,

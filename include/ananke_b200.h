@@ -300,6 +300,12 @@ int ab200_aug_stage_prepare(const ab200_drift_desc* d, const float* a0, const fl
                             int64_t B, float* as_p, float* u, ab200_stream_t stream);
 int ab200_aug_stage_finish(const ab200_drift_desc* d, float* gx, const float* as_p, const float* a_in, float* a_next, float inv, float hb,
                            int32_t write_ka, int64_t B, ab200_stream_t stream);
+/* ab200_aug_stage_finish of stage s (write_ka = 1) and ab200_aug_stage_prepare of stage s + 1 in ONE pass: the next stage value is
+ * a0 + sum_{j<n} hbn[j] ka[j] + hbn[n] ka_s with ka_s taken from registers (n <= 2 earlier stages); as_p is read (stage s) and
+ * overwritten (stage s + 1) in place; u = c_next a_{s+1}.v. */
+int ab200_aug_stage_finish_prepare(const ab200_drift_desc* d, float* gx, float* as_p, const float* a_in, float* a_next, float inv, float hb,
+                                   const float* a0, const float* const* ka, int32_t n, const float* hbn_host, float c_next, float* u,
+                                   int64_t B, ab200_stream_t stream);
 int ab200_stage_upstream(const ab200_drift_desc* d, const float* g_base, const float* const* gx, int32_t n_g,
                          const float* dp_host, const float* dv_host, int64_t B, float* g_a_out, ab200_stream_t stream);
 int ab200_wgrad_accumulate(const ab200_drift_desc* d, const void* spill, int32_t nblobs, int32_t used, void* partial,

@@ -113,6 +113,11 @@ class FakeEngine:
         if write_ka:
             gx.copy_(ka)
 
+    def aug_stage_finish_prepare(self, gx, as_p, a_in, a_next, inv, hb, a0, ka, hbn, c_next, u, B):
+        """finish of a stage + prepare of the next one (the formula ab200_aug_stage_finish_prepare implements)"""
+        self.aug_stage_finish(gx, as_p, a_in, a_next, inv, hb, True, B)
+        self.aug_stage_prepare(a0, list(ka) + [gx], hbn, c_next, B, as_p, u)
+
     def flush(self):
         pass
 

@@ -188,3 +188,31 @@ def test_aug_stage_kernels_match_the_formula(B, n):
         for buf, F in ((as_p, P), (u, P), (acc, D)):
             rows = buf.view(-1, F // 4, TM, 4)[-1, :, B % TM:, :]
             assert float(rows.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("B", [1, 129, 1000])
+@pytest.mark.parametrize("n", [0, 2])
+def test_aug_stage_finish_prepare_equals_the_two_passes(B, n):
+    """the fused pass == ab200_aug_stage_finish (write_ka) followed by ab200_aug_stage_prepare with ka_s appended, bit for bit apart
+    from fma contraction (1e-6)"""
+    import ananke_abm_b200 as ab
+    from ananke_abm_b200 import stage
+    dev = _cuda()
+    _, model = _pair()
+    model = model.to(dev)
+    spec = ab.describe_drift(model.odefunc)
+    eng = stage.TcEngine(spec, spec.flat_params().detach())
+    D, P = eng.D, eng.P
+    g = torch.Generator().manual_seed(7 * B + n)
+    rnd = lambda F: stage.rows_block(torch.randn(B, F, generator=g).to(dev))      # noqa: E731
+    a0, ka, gx, asp, acc = rnd(D), [rnd(D) for _ in range(n)], rnd(D), rnd(P), rnd(D)
+    hbn, inv, hb, cn = [0.3, -0.7, 1.1][:n + 1], -2.5, -0.125, 0.6
+    # reference: the two separate passes
+    gx_r, acc_r, asp_r, u_r = gx.clone(), acc.clone(), stage.blocked_zeros(B, P, dev), stage.blocked_zeros(B, P, dev)
+    eng.aug_stage_finish(gx_r, asp, acc_r, acc_r, inv, hb, True, B)
+    eng.aug_stage_prepare(a0, ka + [gx_r], hbn, cn, B, asp_r, u_r)
+    # fused, as_p in place, a_in aliasing a_next
+    gx_f, acc_f, asp_f, u_f = gx.clone(), acc.clone(), asp.clone(), stage.blocked_zeros(B, P, dev)
+    eng.aug_stage_finish_prepare(gx_f, asp_f, acc_f, acc_f, inv, hb, a0, ka, hbn, cn, u_f, B)
+    for got, ref in ((gx_f, gx_r), (acc_f, acc_r), (asp_f, asp_r), (u_f, u_r)):
+        assert torch.allclose(got, ref, atol=1e-6, rtol=1e-6)
