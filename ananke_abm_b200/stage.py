@@ -607,24 +607,28 @@ def step_backward(eng: TcEngine, tab: Tableau, B: int, yn, A: Sequence[torch.Ten
 
 
 def rk4_backward(eng: TcEngine, t_host: Sequence[float], saved, grad_y_path: torch.Tensor):
-    """-> (grad_y0 row-major [B, D], grad_w_flat)."""
+    """-> (grad_y0 row-major [B, D], grad_w_flat).  Per step: ONE elementwise pass (the step-level gradients from dL/dy_{n+1} of the
+    later steps and the caller's row-major dL/dy_path[n + 1], read in place), one fused launch of the four backward stages whose
+    gather entry folds the stages' gx into dL/dy_n in place, one weight-gradient pass -- the same three launches as a dopri5 step."""
     yb, acc = saved
     T, B, D = grad_y_path.shape
     dev = grad_y_path.device
     eng.backward_begin(B, stages_per_flush=4)
-    lam = rows_block(grad_y_path[T - 1])
-    lam_next = blocked_zeros(B, D, dev)
+    grad_rows = grad_y_path if (grad_y_path.is_contiguous() and grad_y_path.dtype == torch.float32) else grad_y_path.contiguous().float()
+    lam = blocked_zeros(B, D, dev)          # dL/dy_{n+1} through the later steps (without the row's own gradient)
     G_y0 = blocked_zeros(B, D, dev)
     G_a = [blocked_zeros(B, eng.P, dev) for _ in range(4)]
     gx = [blocked_zeros(B, D, dev) for _ in range(4)]
     for n in range(T - 2, -1, -1):
         t0, dt = float(t_host[n]), float(t_host[n + 1]) - float(t_host[n])
-        eng.combine_backward(lam, RK38.combo(RK38.b, dt), B, G_y0, G_a, accumulate=False)
+        cb = RK38.combo(RK38.b, dt)
+        sources = [(grad_rows[n + 1], cb)] + ([(lam, cb)] if n < T - 2 else [])
+        eng.combine_backward_multi(sources, B, G_y0, G_a, accumulate=False)
         times = [t0, t0 + RK38.c[1] * dt, t0 + RK38.c[2] * dt, float(t_host[n + 1])]
-        step_backward(eng, RK38, B, yb[n], [acc[n][j] for j in range(3)], times, dt, G_y0, G_a, gx, lam_next)
+        stages_backward(eng, RK38, B, yb[n], [acc[n][j] for j in range(3)], times, dt, G_a, gx, 0, 3, y0_accum=G_y0)
         eng.flush()
-        rows_block(grad_y_path[n], lam_next, accumulate=True)
-        lam, lam_next = lam_next, lam
+        lam, G_y0 = G_y0, lam
+    rows_block(grad_rows[0], lam, accumulate=True)
     gw = eng.backward_end()
     return rows_unblock(lam, B, D), gw
 
