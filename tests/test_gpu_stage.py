@@ -435,3 +435,52 @@ def test_step_level_combine_mixed_blocked_and_rowmajor_sources(B, n_rowmajor):
             Bp = stage.padded_rows(B)
             v = G_y0.view(Bp // 128, D // 4, 128, 4).permute(0, 2, 1, 3).reshape(Bp, D)
             assert float(v[B:].abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("B", [129, 1000])
+def test_step_backward_three_compositions_agree(B):
+    """One rk4 step's backward pass composed three ways from the C ABI -- (1) fused stage launch + `ab200_adjoint_gather` pass,
+    (2) one `ab200_stage_backward` launch per stage + gather pass, (3) fused launch whose GATHER ENTRY folds the stages' gx into
+    dL/dy0 in place (what rk4_backward / dopri5_backward issue) -- must give the same dL/dy0 and the same weight gradients."""
+    import ananke_abm_b200 as ab
+    from ananke_abm_b200 import stage
+    dev = _cuda()
+    _, model = _pair()
+    model = model.to(dev)
+    spec = ab.describe_drift(model.odefunc)
+    eng = stage.TcEngine(spec, spec.flat_params().detach())
+    D, P = eng.D, eng.P
+    home, work, traits = _agents(B, 8)
+    y0 = model.initial_state(home.to(dev), work.to(dev), traits.to(dev)).detach()
+    t0, dt = 1.0, 0.3
+    yb = stage.rows_block(y0.contiguous())
+    A = [stage.blocked_zeros(B, P, dev) for _ in range(3)]
+    y1 = stage.blocked_zeros(B, D, dev)
+    times = [t0, t0 + stage.RK38.c[1] * dt, t0 + stage.RK38.c[2] * dt, t0 + dt]
+    stages = [(i, stage.RK38.stage_input(i, dt), times[i], A[i]) for i in range(3)] + [(3, stage.RK38.stage_input(3, dt), times[3], None)]
+    eng.stage_forward_fused(yb, A, stages, B, y_out=y1, cout=stage.RK38.combo(stage.RK38.b, dt))
+    g = torch.Generator().manual_seed(B)
+    lam = stage.rows_block(torch.randn(B, D, generator=g).to(dev))
+    outs, gws = [], []
+    for mode in (1, 2, 3):
+        G_y0 = stage.blocked_zeros(B, D, dev)
+        G_a = [stage.blocked_zeros(B, P, dev) for _ in range(4)]
+        gx = [stage.blocked_zeros(B, D, dev) for _ in range(4)]
+        eng.backward_begin(B, 4)
+        eng.combine_backward(lam, stage.RK38.combo(stage.RK38.b, dt), B, G_y0, G_a, accumulate=False)
+        if mode == 1:
+            out = stage.blocked_zeros(B, D, dev)
+            stage.step_backward(eng, stage.RK38, B, yb, A, times, dt, G_y0, G_a, gx, out)
+        elif mode == 2:
+            out = stage.blocked_zeros(B, D, dev)
+            stage._step_backward_n(eng, stage.RK38, B, yb, A, times, dt, G_y0, G_a, gx, out, 4)
+        else:
+            stage.stages_backward(eng, stage.RK38, B, yb, A, times, dt, G_a, gx, 0, 3, y0_accum=G_y0)
+            out = G_y0
+        gws.append(eng.backward_end())
+        outs.append(stage.rows_unblock(out, B, D))
+    torch.cuda.synchronize()
+    for k in (1, 2):
+        assert _rel(outs[k], outs[0]) < 1e-5, (k, _rel(outs[k], outs[0]))
+        assert _rel(gws[k], gws[0]) < 1e-5, (k, _rel(gws[k], gws[0]))
+    assert float(outs[0].abs().max()) > 0 and float(gws[0].abs().max()) > 0
