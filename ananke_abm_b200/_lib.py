@@ -77,6 +77,7 @@ SIGNATURES = {
     "ab200_stage_pack": (C.c_int, [_dp, _vp, _vp, _sz, _vp]),
     "ab200_stage_forward": (C.c_int, [_dp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i32, _vp]),
     "ab200_stage_forward_fused": (C.c_int, [_dp, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _vp, _vp, _i32, _vp]),
+    "ab200_stage_forward_fused_save": (C.c_int, [_dp, _vp, _vp, _vp, _vp, _i32, _vp, _i64, _vp, _vp, _vp, _i32, _vp]),
     "ab200_dopri5_attempt": (C.c_int, [_dp, _vp, _vp, _vp, C.c_double, C.c_double, _i64, _vp, _vp, _f32, _f32, _i32, _vp, _i32, _vp]),
     "ab200_stage_xblob_bytes": (_sz, [_dp, _i64, _i32]),
     "ab200_dopri5_dense_rows": (C.c_int, [_dp, _vp, _vp, C.c_double, _i32, _vp, _i64, _vp, _vp]),

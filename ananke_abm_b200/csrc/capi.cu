@@ -284,6 +284,18 @@ int ab200_stage_forward_fused(const ab200_drift_desc* d, const void* image, cons
                             (cudaStream_t)stream);
 }
 
+int ab200_stage_forward_fused_save(const ab200_drift_desc* d, const void* image, const float* y0, const float* const* a,
+                                   const ab200_stage_desc* stages, int32_t n_stage, float* const* a_out, int64_t B, float* y_out,
+                                   double* err_sumsq, void* const* x_outs, int32_t save_level, ab200_stream_t stream) {
+  if (!d || !image || !y0 || !stages || !a || !x_outs || B <= 0 || n_stage < 1 || n_stage > AB200_STAGE_MAX_A) return AB200_ERR_BAD_ARG;
+  if (!stage_shape_ok(d)) return AB200_ERR_UNSUPPORTED;
+  if ((err_sumsq && !y_out) || save_level < 1 || save_level > 2) return AB200_ERR_BAD_ARG;
+  for (int i = 0; i < n_stage; ++i)
+    if (!x_outs[i]) return AB200_ERR_BAD_ARG;
+  return stage_fwd2_tc_multi(d, (const uint8_t*)image, y0, a, stages, n_stage, a_out, B, y_out, err_sumsq, x_outs, save_level,
+                             (cudaStream_t)stream);
+}
+
 size_t ab200_stage_xblob_bytes(const ab200_drift_desc* d, int64_t B, int32_t save_level) {
   if (!stage_shape_ok(d) || B <= 0 || save_level < 1 || save_level > 2) return 0;
   return wg::FwdSaveLayout{(int)((B + 127) / 128)}.total(save_level);

@@ -140,21 +140,21 @@ class _StageRK4TC(torch.autograd.Function):
     the training path of `precision='bf16'`.  Saves the trajectory rows and the three stage accelerations per step."""
 
     @staticmethod
-    def forward(ctx, y0, t, w_flat, spec: DriftSpec, t_host):
+    def forward(ctx, y0, t, w_flat, spec: DriftSpec, t_host, saved_operands="inputs"):
         from . import stage
         eng = stage.TcEngine(spec, w_flat)
         th = [float(v) for v in t_host.tolist()]
-        y_path, (yb, acc) = stage.rk4_forward(eng, y0.contiguous().float(), th, save_stages=True)
-        ctx.eng, ctx.th = eng, th
-        ctx.save_for_backward(yb, acc)
+        y_path, (yb, acc, xs, level) = stage.rk4_forward(eng, y0.contiguous().float(), th, save_stages=True, saved_operands=saved_operands)
+        ctx.eng, ctx.th, ctx.level = eng, th, level
+        ctx.save_for_backward(yb, acc, *([xs] if xs is not None else []))
         return y_path
 
     @staticmethod
     def backward(ctx, grad_y_path):
         from . import stage
-        yb, acc = ctx.saved_tensors
-        gy0, gw = stage.rk4_backward(ctx.eng, ctx.th, (yb, acc), grad_y_path.contiguous().float())
-        return gy0, None, gw, None, None
+        yb, acc, *rest = ctx.saved_tensors
+        gy0, gw = stage.rk4_backward(ctx.eng, ctx.th, (yb, acc, rest[0] if rest else None, ctx.level), grad_y_path.contiguous().float())
+        return gy0, None, gw, None, None, None
 
 
 class _StageDopri5TC(torch.autograd.Function):
@@ -501,13 +501,14 @@ def odeint(func, y0, t, *, rtol: float = 1e-7, atol: float = 1e-9, method: Optio
         time_as_float = bool(options.pop("time_as_float", False))
         for k in ("dtype", "norm", "segments", "adjoint_mode"):
             options.pop(k, None)
+        saved_operands = options.pop("saved_operands", "inputs")      # tensor-core training path: what the forward saves (stage.rk4_forward)
         if options:
             warnings.warn(f"rk4: Unexpected arguments {options}")
         if spec is not None and y0.shape[1] == spec.state_dim and y0.dtype == torch.float32:
             w_flat = spec.flat_params()
             needs_grad = torch.is_grad_enabled() and (y0.requires_grad or w_flat.requires_grad)
             if precision == _lib.PREC_BF16 and needs_grad and spec.tc_stage_supported():
-                return _StageRK4TC.apply(y0, t, w_flat, spec, t_host)
+                return _StageRK4TC.apply(y0, t, w_flat, spec, t_host, saved_operands)
             return _FusedRK4.apply(y0, t, w_flat, spec, precision, t_host)
         if y0.dtype != torch.float32:
             raise _lib.Ab200Error(f"rk4: the fused stage-combine kernels are fp32, got y0 of {y0.dtype} (cast the state)")

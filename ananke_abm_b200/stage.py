@@ -178,7 +178,7 @@ class TcEngine:
 
     def stage_forward_fused(self, y0, a_bufs: Sequence[torch.Tensor], stages: Sequence, B: int, y_out=None, cout: Optional[Combo] = None,
                             err_sumsq=None, cerr: Optional[Combo] = None, rtol: float = 0.0, atol: float = 0.0,
-                            fp16: Optional[bool] = None) -> None:
+                            fp16: Optional[bool] = None, x_outs: Optional[Sequence[int]] = None, save_level: int = 0) -> None:
         """Consecutive stages of one step in ONE launch.  `stages` = [(n_a, Combo in, t, a_out tensor or None), ...]: stage s
         reads a_bufs[:n_a] (possibly written by earlier stages of this call) and writes its a_out; the last stage may
         also produce y_out (cout) and the error norm (cerr)."""
@@ -204,6 +204,16 @@ class TcEngine:
             _fill(last.err_va, cerr.cva[:n_last + 1])
         last.rtol, last.atol = float(rtol), float(atol)
         ptrs = (C.c_void_p * MAX_A)(*([t.data_ptr() for t in a_bufs[:MAX_A]] + [None] * (MAX_A - min(len(a_bufs), MAX_A))))
+        if x_outs is not None:      # split-activation format; every stage saves its backward operands (device pointers, one per stage)
+            assert len(x_outs) == n and save_level in (1, 2)
+            rc = self.L.ab200_stage_forward_fused_save(C.byref(self.desc), self.image.data_ptr(), y0.data_ptr(), C.cast(ptrs, C.c_void_p),
+                                                       C.cast(descs, C.c_void_p), n, C.cast(outs, C.c_void_p), B,
+                                                       None if y_out is None else y_out.data_ptr(),
+                                                       None if err_sumsq is None else err_sumsq.data_ptr(),
+                                                       C.cast((C.c_void_p * n)(*[int(x) for x in x_outs]), C.c_void_p), int(save_level),
+                                                       _stream())
+            _lib.check(rc, "ab200_stage_forward_fused_save")
+            return
         rc = self.L.ab200_stage_forward_fused(C.byref(self.desc), self.image.data_ptr(), y0.data_ptr(), C.cast(ptrs, C.c_void_p),
                                               C.cast(descs, C.c_void_p), n, C.cast(outs, C.c_void_p), B,
                                               None if y_out is None else y_out.data_ptr(),
@@ -544,17 +554,23 @@ def rows_unblock(src: torch.Tensor, B: int, F: int, out: Optional[torch.Tensor] 
 # --------------------------------------------------------------------------------------------------------
 # fixed-grid rk4 (3/8 rule) with the discrete adjoint
 # --------------------------------------------------------------------------------------------------------
-def rk4_forward(eng: TcEngine, y0: torch.Tensor, t_host: Sequence[float], save_stages: bool):
+def rk4_forward(eng: TcEngine, y0: torch.Tensor, t_host: Sequence[float], save_stages: bool, saved_operands: str = "none"):
     """y0 row-major [B, D] -> y_path row-major [T, B, D]; when `save_stages`, also the blocked per-step states
-    yb [T, Bp*D] and stage accelerations acc [T-1, 3, Bp*P] the adjoint needs."""
+    yb [T, Bp*D] and stage accelerations acc [T-1, 3, Bp*P] the adjoint needs.  `saved_operands` ("none" | "inputs" | "all", training
+    only): the four stage evaluations of every step run in the split-activation format and write what their backward pass would
+    recompute (`ab200_stage_forward_fused_save`: the stage inputs, 352 B per agent-stage, or also the hidden activations and ReLU
+    masks, 1,712 B) -- returned as xs [T-1, 4 * xblob_bytes]."""
     B, T = y0.shape[0], len(t_host)
     dev = y0.device
     Bp = padded_rows(B)
+    level = SAVE_LEVELS[saved_operands] if save_stages else 0
     y_path = torch.empty((T, B, eng.D), dtype=torch.float32, device=dev)
     y_path[0].copy_(y0)
     n_keep = T - 1 if save_stages else 1
     acc = torch.zeros((n_keep, 3, Bp * eng.P), dtype=torch.float32, device=dev)
     yb = torch.zeros((T if save_stages else 2, Bp * eng.D), dtype=torch.float32, device=dev)
+    per = eng.xblob_bytes(B, level) if level else 0
+    xs = torch.empty((max(T - 1, 1), 4 * per), dtype=torch.uint8, device=dev) if level else None
     rows_block(y0, yb[0])
     for n in range(T - 1):
         t0, dt = float(t_host[n]), float(t_host[n + 1]) - float(t_host[n])
@@ -563,15 +579,20 @@ def rk4_forward(eng: TcEngine, y0: torch.Tensor, t_host: Sequence[float], save_s
         yn1 = yb[n + 1 if save_stages else (n + 1) % 2]
         stages = [(i, RK38.stage_input(i, dt), t0 + RK38.c[i] * dt, A[i]) for i in range(3)]
         stages.append((3, RK38.stage_input(3, dt), float(t_host[n + 1]), None))
-        eng.stage_forward_fused(yn, [A[0], A[1], A[2]], stages, B, y_out=yn1, cout=RK38.combo(RK38.b, dt))
+        if level:
+            base = xs[n].data_ptr()
+            eng.stage_forward_fused(yn, [A[0], A[1], A[2]], stages, B, y_out=yn1, cout=RK38.combo(RK38.b, dt),
+                                    x_outs=[base + i * per for i in range(4)], save_level=level)
+        else:
+            eng.stage_forward_fused(yn, [A[0], A[1], A[2]], stages, B, y_out=yn1, cout=RK38.combo(RK38.b, dt))
         rows_unblock(yn1, B, eng.D, out=y_path[n + 1])
     eng.check_status()
-    return y_path, ((yb, acc) if save_stages else None)
+    return y_path, ((yb, acc, xs, level) if save_stages else None)
 
 
 def stages_backward(eng: TcEngine, tab: Tableau, B: int, yn, A: Sequence[torch.Tensor], stage_times: Sequence[float], dt: float,
                     G_a_base: Sequence[Optional[torch.Tensor]], gx: Sequence[torch.Tensor], first: int, last: int, x_blobs=None,
-                    save_level: int = 0, y0_accum=None, fsal_out=None):
+                    save_level: int = 0, y0_accum=None, fsal_out=None, x_first: int = 1):
     """Backward of stages last..first of ONE explicit Runge-Kutta step in a single fused launch (latest stage first).
     Returns the stage input combinations (their cpv feed `adjoint_gather`).  `x_blobs`: what the step's forward attempt saved
     (tensor, stage i >= 1 at byte offset (i - 1) * xblob_bytes(B, save_level)) or None.  `y0_accum`: see `stage_backward_fused`.
@@ -587,7 +608,7 @@ def stages_backward(eng: TcEngine, tab: Tableau, B: int, yn, A: Sequence[torch.T
     xs = None
     if x_blobs is not None:
         per = eng.xblob_bytes(B, save_level)
-        xs = [x_blobs.data_ptr() + (i - 1) * per if i >= 1 else None for i in order]
+        xs = [x_blobs.data_ptr() + (i - x_first) * per if i >= x_first else None for i in order]      # dopri5: stage 1 is the FSAL evaluation
     upstream = None
     if fsal_out is not None:
         assert first >= 1
@@ -610,7 +631,7 @@ def rk4_backward(eng: TcEngine, t_host: Sequence[float], saved, grad_y_path: tor
     """-> (grad_y0 row-major [B, D], grad_w_flat).  Per step: ONE elementwise pass (the step-level gradients from dL/dy_{n+1} of the
     later steps and the caller's row-major dL/dy_path[n + 1], read in place), one fused launch of the four backward stages whose
     gather entry folds the stages' gx into dL/dy_n in place, one weight-gradient pass -- the same three launches as a dopri5 step."""
-    yb, acc = saved
+    yb, acc, xs, level = saved
     T, B, D = grad_y_path.shape
     dev = grad_y_path.device
     eng.backward_begin(B, stages_per_flush=4)
@@ -625,7 +646,8 @@ def rk4_backward(eng: TcEngine, t_host: Sequence[float], saved, grad_y_path: tor
         sources = [(grad_rows[n + 1], cb)] + ([(lam, cb)] if n < T - 2 else [])
         eng.combine_backward_multi(sources, B, G_y0, G_a, accumulate=False)
         times = [t0, t0 + RK38.c[1] * dt, t0 + RK38.c[2] * dt, float(t_host[n + 1])]
-        stages_backward(eng, RK38, B, yb[n], [acc[n][j] for j in range(3)], times, dt, G_a, gx, 0, 3, y0_accum=G_y0)
+        stages_backward(eng, RK38, B, yb[n], [acc[n][j] for j in range(3)], times, dt, G_a, gx, 0, 3, xs[n] if level else None, level,
+                        y0_accum=G_y0, x_first=0)
         eng.flush()
         lam, G_y0 = G_y0, lam
     rows_block(grad_rows[0], lam, accumulate=True)

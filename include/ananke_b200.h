@@ -222,6 +222,13 @@ int ab200_dopri5_attempt(const ab200_drift_desc* d, const void* image, const flo
  * with the same save_level: at level 1 the backward kernel loads the stage input instead of rebuilding it from (y0, a_j); at
  * level 2 it recomputes nothing (no stage input, no forward GEMMs, no activation spills) and reads neither y0 nor a. */
 size_t ab200_stage_xblob_bytes(const ab200_drift_desc* d, int64_t B, int32_t save_level);
+/* ab200_stage_forward_fused in the split-activation format (operand_format 2) that also SAVES, for every stage s of the launch, what
+ * its backward pass would recompute into x_outs[s] (ab200_stage_xblob_bytes(d, B, save_level) bytes each; levels as above): the
+ * fixed-grid rk4 training step uses it for its four stages (stage.py rk4_forward), ab200_dopri5_attempt is the same launch with the
+ * Dormand-Prince descriptors built in C. */
+int ab200_stage_forward_fused_save(const ab200_drift_desc* d, const void* image, const float* y0, const float* const* a,
+                                   const ab200_stage_desc* stages, int32_t n_stage, float* const* a_out, int64_t B, float* y_out,
+                                   double* err_sumsq, void* const* x_outs, int32_t save_level, ab200_stream_t stream);
 /* The dense-output rows of an accepted dopri5 step at relative positions x[q] = (t_q - t0) / dt in (0, 1] (tdq interp.py
  * `_interp_fit` / `_interp_evaluate`: the quartic through y0, y1, y_mid, f0, f1, expanded over the seven stage derivatives):
  * out_rowmajor[q] (row-major [B][D]) for q < n_rows, all in one pass over (y0, a[0..6]). */

@@ -484,3 +484,36 @@ def test_step_backward_three_compositions_agree(B):
         assert _rel(outs[k], outs[0]) < 1e-5, (k, _rel(outs[k], outs[0]))
         assert _rel(gws[k], gws[0]) < 1e-5, (k, _rel(gws[k], gws[0]))
     assert float(outs[0].abs().max()) > 0 and float(gws[0].abs().max()) > 0
+
+
+@pytest.mark.parametrize("B,T", [(130, 5), (300, 9)])
+def test_rk4_training_saved_operands_levels_vs_oracle(B, T):
+    """rk4 training on the tensor-core path with the forward launch saving nothing / the stage inputs (default) / every layer input
+    (`options['saved_operands']`, `ab200_stage_forward_fused_save`): each level within the stated tolerance of autograd through the
+    oracle solver, and the levels close to each other (the saving forward runs in the split-activation format)."""
+    import ananke_abm_b200 as ab
+    dev = _cuda()
+    oracle, model = _pair()
+    model = model.to(dev)
+    home, work, traits = _agents(B, 8)
+    t = torch.linspace(0.0, 3.0, T)
+    wgt = torch.linspace(0.5, 1.5, T)[:, None, None]
+    y0r = oracle.initial_state(home, work, traits).detach().requires_grad_(True)
+    ref = tdq.odeint(oracle.rhs, y0r, t, method="rk4")
+    ((ref[:, :, :128] * wgt) ** 2).mean().backward()
+    ref_gw = torch.cat([p.grad.reshape(-1) for p in oracle.odefunc.func.net.parameters()])
+    got = {}
+    for level in ("none", "inputs", "all"):
+        model.zero_grad(set_to_none=True)
+        y0 = model.initial_state(home.to(dev), work.to(dev), traits.to(dev)).detach().requires_grad_(True)
+        out = ab.odeint(model.odefunc, y0, t.to(dev), method="rk4", options={"precision": "bf16", "saved_operands": level})
+        ((out[:, :, :128] * wgt.to(dev)) ** 2).mean().backward()
+        gw = torch.cat([p.grad.reshape(-1) for p in model.odefunc.func.net.parameters()])
+        assert _rel(out.detach().cpu(), ref.detach()) < TOL_TRAJ, level
+        assert _rel(y0.grad.cpu(), y0r.grad) < TOL_GRAD_MAX and _rms(y0.grad.cpu(), y0r.grad) < TOL_GRAD_RMS, \
+            (level, _rel(y0.grad.cpu(), y0r.grad), _rms(y0.grad.cpu(), y0r.grad))
+        assert _rms(gw.cpu(), ref_gw) < TOL_GRAD_RMS, (level, _rms(gw.cpu(), ref_gw))
+        got[level] = (out.detach().clone(), y0.grad.clone(), gw.clone())
+    assert torch.equal(got["inputs"][0], got["all"][0])          # the same forward arithmetic, more of it saved
+    for level in ("inputs", "all"):
+        assert _rms(got[level][1], got["none"][1]) < TOL_GRAD_RMS and _rms(got[level][2], got["none"][2]) < TOL_GRAD_RMS
