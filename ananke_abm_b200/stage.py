@@ -556,8 +556,8 @@ def rows_unblock(src: torch.Tensor, B: int, F: int, out: Optional[torch.Tensor] 
 # --------------------------------------------------------------------------------------------------------
 def rk4_forward(eng: TcEngine, y0: torch.Tensor, t_host: Sequence[float], save_stages: bool, saved_operands: str = "none"):
     """y0 row-major [B, D] -> y_path row-major [T, B, D]; when `save_stages`, also the blocked per-step states
-    yb [T, Bp*D] and stage accelerations acc [T-1, 3, Bp*P] the adjoint needs.  `saved_operands` ("none" | "inputs" | "all", training
-    only): the four stage evaluations of every step run in the split-activation format and write what their backward pass would
+    yb [T, Bp*D] and stage accelerations acc [T-1, 3, Bp*P] the adjoint needs.  `saved_operands` ("none" = default | "inputs" | "all",
+    training only): the four stage evaluations of every step run in the split-activation format and write what their backward pass would
     recompute (`ab200_stage_forward_fused_save`: the stage inputs, 352 B per agent-stage, or also the hidden activations and ReLU
     masks, 1,712 B) -- returned as xs [T-1, 4 * xblob_bytes]."""
     B, T = y0.shape[0], len(t_host)

@@ -488,7 +488,7 @@ def test_step_backward_three_compositions_agree(B):
 
 @pytest.mark.parametrize("B,T", [(130, 5), (300, 9)])
 def test_rk4_training_saved_operands_levels_vs_oracle(B, T):
-    """rk4 training on the tensor-core path with the forward launch saving nothing / the stage inputs (default) / every layer input
+    """rk4 training on the tensor-core path with the forward launch saving nothing (default) / the stage inputs / every layer input
     (`options['saved_operands']`, `ab200_stage_forward_fused_save`): each level within the stated tolerance of autograd through the
     oracle solver, and the levels close to each other (the saving forward runs in the split-activation format)."""
     import ananke_abm_b200 as ab
