@@ -195,3 +195,47 @@ def test_adjoint_seminorm_ignores_parameter_adjoints_in_the_step_control():
     for name in res:
         for a, b in zip(g_direct, res[name][1]):
             assert torch.allclose(a, b, rtol=2e-4, atol=2e-4 * float(a.abs().max())), (name, float((a - b).abs().max()))
+
+
+def test_rk4_step_size_grid_and_linear_interpolation():
+    """options['step_size'] (solvers.py FixedGridODESolver): the solver steps over t[0] + k h with the last point moved onto t[-1];
+    a requested time on a grid point returns the grid row, any other one the LINEAR interpolant of its two neighbours."""
+    f = lambda t, y: -y * torch.cos(t)      # noqa: E731
+    y0 = torch.tensor([1.0, 2.0], dtype=torch.float64)
+    t = torch.linspace(0.0, 2.0, 5, dtype=torch.float64)
+    same = tdq.odeint(f, y0, t, method="rk4", options={"step_size": 0.5})
+    assert torch.equal(same, tdq.odeint(f, y0, t, method="rk4"))           # grid == t: identical arithmetic
+    exact = y0 * torch.exp(-torch.sin(t))[:, None]
+    errs = [float((tdq.odeint(f, y0, t, method="rk4", options={"step_size": h}) - exact).abs().max()) for h in (0.25, 0.125)]
+    assert 12.0 < errs[0] / errs[1] < 20.0                                  # fourth order in the step size, not in the output spacing
+    grid = tdq._grid_from_step_size(torch.tensor([0.0, 2.0], dtype=torch.float64), 0.75)
+    assert grid.tolist() == [0.0, 0.75, 1.5, 2.0]                           # shortened last step
+    rows = tdq.odeint(f, y0, grid, method="rk4")                            # the same steps, every grid row kept
+    tq = torch.tensor([0.0, 0.3, 0.75, 1.8, 2.0], dtype=torch.float64)
+    out = tdq.odeint(f, y0, tq, method="rk4", options={"step_size": 0.75})
+    assert torch.equal(out[2], rows[1]) and torch.equal(out[4], rows[3])
+    assert torch.allclose(out[1], rows[0] + (0.3 / 0.75) * (rows[1] - rows[0]), atol=1e-15)
+    assert torch.allclose(out[3], rows[2] + ((1.8 - 1.5) / 0.5) * (rows[3] - rows[2]), atol=1e-15)
+
+
+def test_adjoint_with_step_size_converges_to_the_exact_gradient():
+    """odeint_adjoint(method='rk4', options={'step_size': h}): forward and augmented backward solve on the step_size grid; the
+    gradient of y(T) w.r.t. y0 of dy/dt = -y cos t is exp(-sin T), reached at fourth order"""
+    class F(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.k = torch.nn.Parameter(torch.tensor(1.0, dtype=torch.float64))
+
+        def forward(self, t, y):
+            return -self.k * y * torch.cos(t)
+    f = F()
+    t = torch.tensor([0.0, 2.0], dtype=torch.float64)
+    errs = []
+    for h in (0.25, 0.125):
+        y0 = torch.tensor([1.5], dtype=torch.float64, requires_grad=True)
+        f.zero_grad()
+        tdq.odeint_adjoint(f, y0, t, method="rk4", options={"step_size": h})[-1].sum().backward()
+        exact_y0 = float(torch.exp(-torch.sin(t[1])))
+        exact_k = float(-torch.sin(t[1]) * 1.5 * torch.exp(-torch.sin(t[1])))
+        errs.append(max(abs(float(y0.grad) - exact_y0), abs(float(f.k.grad) - exact_k)))
+    assert errs[0] < 1e-4 and 10.0 < errs[0] / errs[1] < 40.0      # fourth order (measured ratio 25)
