@@ -140,7 +140,8 @@ def _tensor_core_rk4(func, y0, t, method, options, adjoint_method, adjoint_optio
     adj_step = step if adjoint_options is None else dict(adjoint_options).get("step_size")
     from .adjoint_tc import _ContinuousAdjointRK4TC
     return _ContinuousAdjointRK4TC.apply(y0, t, spec.flat_params(), spec, t_host, None if step is None else float(step),
-                                         None if adj_step is None else float(adj_step), opts.get("forward_operands"))
+                                         None if adj_step is None else float(adj_step), opts.get("forward_operands"),
+                                         opts.get("adjoint_fused"))
 
 
 def continuous_adjoint(func, y0, t, *, rtol, atol, method, options, adjoint_rtol=None, adjoint_atol=None,

@@ -18,8 +18,13 @@ feeds back into the dynamics, so its stage values are not formed: the stage's up
 c_s = -h b_s (h < 0 going backward) and the weight-gradient accumulators ARE a_theta.  The vector-Jacobian product is
 linear in its upstream, so gx comes back scaled by c_s and is divided out in the stage algebra.
 
-The stage algebra of a_y is ONE fused elementwise pass per stage (`ab200_aug_stage_finish_prepare`: derivative of this stage, running
-solution, value and upstream of the next stage; `ab200_aug_stage_prepare` / `ab200_aug_stage_finish` open and close a step).
+Two launch structures (`rk4_continuous_adjoint(fused=...)`, `options["adjoint_fused"]`):
+  fused (default while the blobs of four stages fit, up to ~4.6M agents per GPU): every stage's upstream gradient is LINEAR in a0 and
+        the earlier stages' products (`fused_step_coefficients`), so the four vector-Jacobian products of a step are ONE
+        `ab200_stage_backward_fused` launch whose entries feed each other through their gx, framed by `ab200_pv_combine_backward`
+        (the a0 parts) and `ab200_adjoint_gather` (the step's solution): five launches per step;
+  staged (8M agents on one GPU: a one-stage blob ring): one `ab200_stage_backward` launch per stage and ONE fused elementwise pass
+        per stage (`ab200_aug_stage_finish_prepare`; `ab200_aug_stage_prepare` / `_finish` open and close a step).
 Every evaluation of A and of its vector-Jacobian product is a tcgen05 kernel (fp16 / bf16 operands, fp32 accumulate);
 y, a_y and a_theta are fp32.  Stated tolerance: that of the tensor-core path.
 """
@@ -140,15 +145,70 @@ def _aug_step(eng, yb: torch.Tensor, ab: torch.Tensor, t0: float, t1: float, B: 
     return y_new, a_new
 
 
+class _FusedBuffers:
+    def __init__(self, B: int, D: int, P: int, device, lay):
+        self.A = [lay.zeros(B, P, device) for _ in range(3)]      # stage accelerations of the y part
+        self.GB = [lay.zeros(B, P, device) for _ in range(4)]     # the a0 part of every stage's upstream gradient
+        self.GX = [lay.zeros(B, D, device) for _ in range(4)]     # c_s J_A^T a_v,s of every stage
+        self.base = lay.zeros(B, D, device)
+        self.y_next = lay.zeros(B, D, device)
+        self.a_next = lay.zeros(B, D, device)
+
+
+def fused_step_coefficients(h: float):
+    """The augmented 3/8-rule step written over (a0, gx'_0 .. gx'_3), gx'_s = c_s J_A^T a_v,s, c_s = -h b_s.  With
+    ka_s = -[gx_s.p, a_p,s + gx_s.v, gx_s.h] and a_s = a0 + h sum_j beta_sj ka_j, everything a stage needs is LINEAR in a0 and
+    the earlier stages' products:
+        upstream_s = c_s a_v,s = cva[s] a0.v + cpa[s] a0.p + sum_{i<s} dp[s][i] gx'_i.p + dv[s][i] gx'_i.v
+        a_y(t + h) = [a0.p, a0.v - h a0.p, a0.h] + sum_i [gx'_i.p, w[i] gx'_i.p + gx'_i.v, gx'_i.h]
+    -- the shapes `ab200_pv_combine_backward`, `ab200_stage_backward_fused` (sources = earlier entries of the launch) and
+    `ab200_adjoint_gather` already compute.  -> (c, cpa, cva, dp, dv, w)."""
+    beta = [list(r) + [0.0] * (4 - len(r)) for r in RK38.beta]
+    b, crk = RK38.b, RK38.c
+    c = [-h * b[s] for s in range(4)]
+    cva = [c[s] for s in range(4)]
+    cpa = [-c[s] * h * crk[s] for s in range(4)]
+    dp = [[c[s] * h * h * sum(beta[s][j] * beta[j][i] for j in range(4)) / c[i] for i in range(s)] for s in range(4)]
+    dv = [[-c[s] * h * beta[s][i] / c[i] for i in range(s)] for s in range(4)]
+    w = [h * h * sum(b[s] * beta[s][i] for s in range(4)) / c[i] for i in range(4)]
+    return c, cpa, cva, dp, dv, w
+
+
+def _aug_step_fused(eng, yb: torch.Tensor, ab: torch.Tensor, t0: float, t1: float, B: int, w: _FusedBuffers):
+    """`_aug_step` as FIVE launches: the fused forward launch of the y stages, one elementwise pass for the a0 part of all four
+    upstream gradients (and the a0 part of the step's solution), ONE fused backward launch whose entries feed each other through their
+    gx (upstream_s needs the earlier stages' products of the same agent only), the weight-gradient pass, one gather pass."""
+    h = t1 - t0
+    cins = [RK38.stage_input(s, h) for s in range(4)]
+    times = [t0 + RK38.c[s] * h for s in range(3)] + [t1]
+    c, cpa, cva, dp, dv, wv = fused_step_coefficients(h)
+    eng.stage_forward_fused(yb, w.A, [(s, cins[s], times[s], w.A[s] if s < 3 else None) for s in range(4)], B, y_out=w.y_next,
+                            cout=RK38.combo(RK38.b, h))
+    # base = [a0.p, a0.v - h a0.p, a0.h] ;  GB[s] = cpa[s] a0.p + cva[s] a0.v
+    eng.combine_backward(ab, stage.Combo(-h, cpa, cva), B, w.base, w.GB, accumulate=False)
+    stages = [(s, cins[s], times[s], w.GB[s], [(i, dp[s][i], dv[s][i]) for i in range(s) if dp[s][i] != 0.0 or dv[s][i] != 0.0], w.GX[s])
+              for s in range(4)]
+    eng.stage_backward_fused(yb, w.A, stages, B)
+    eng.flush()
+    eng.adjoint_gather(w.base, w.GX, wv, B, w.a_next)
+    y_new, a_new = w.y_next, w.a_next
+    w.y_next, w.a_next = yb, ab
+    return y_new, a_new
+
+
 def rk4_continuous_adjoint(eng, t_host: Sequence[float], y_rows: torch.Tensor, grad_rows: torch.Tensor,
-                           step_size: Optional[float] = None, lay=_CudaLayout, np_dtype=np.float32, stages_per_flush: Optional[int] = None):
-    """-> (dL/dy0 row-major [B, D], a_theta(t[0]) = dL/dtheta in the drift's flat parameter order)."""
+                           step_size: Optional[float] = None, lay=_CudaLayout, np_dtype=np.float32, fused: Optional[bool] = None):
+    """-> (dL/dy0 row-major [B, D], a_theta(t[0]) = dL/dtheta in the drift's flat parameter order).
+    `fused` (default: when the blobs of four stages fit in ~56 GB, i.e. up to ~4.6M agents): the four vector-Jacobian products of a
+    step in one launch (`_aug_step_fused`); otherwise one launch per stage with a one-stage blob ring (`_aug_step`: 8M agents on
+    one GPU)."""
     T, B, D = grad_rows.shape
     dev = grad_rows.device
-    if stages_per_flush is None:      # the blob ring of one flush: keep it under ~16 GB
-        stages_per_flush = 4 if stage.padded_rows(B) * 3100 * 4 < (16 << 30) else 1
-    eng.backward_begin(B, stages_per_flush)
-    w = _AugBuffers(B, D, eng.P, dev, lay)
+    if fused is None:
+        fused = stage.padded_rows(B) * 3100 * 4 < (56 << 30)
+    eng.backward_begin(B, 4 if fused else 1)
+    w = (_FusedBuffers if fused else _AugBuffers)(B, D, eng.P, dev, lay)
+    step = _aug_step_fused if fused else _aug_step
     ab = lay.block(grad_rows[T - 1].contiguous())
     yb = None
     for i in range(T - 1, 0, -1):
@@ -156,7 +216,7 @@ def rk4_continuous_adjoint(eng, t_host: Sequence[float], y_rows: torch.Tensor, g
         yb = lay.block(row) if yb is None else lay.block(row, yb)      # re-seed y with the saved row (adjoint.py: aug_state[1] = y[i - 1])
         grid = step_grid(t_host[i], t_host[i - 1], step_size, np_dtype)
         for n in range(len(grid) - 1):
-            yb, ab = _aug_step(eng, yb, ab, grid[n], grid[n + 1], B, w)
+            yb, ab = step(eng, yb, ab, grid[n], grid[n + 1], B, w)
         lay.block(grad_rows[i - 1].contiguous(), ab, accumulate=True)
     gw = eng.backward_end()
     return lay.unblock(ab, B, D), gw
@@ -164,7 +224,7 @@ def rk4_continuous_adjoint(eng, t_host: Sequence[float], y_rows: torch.Tensor, g
 
 class _ContinuousAdjointRK4TC(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, y0, t, w_flat, spec, t_host, step_size, adj_step_size, fwd_format):
+    def forward(ctx, y0, t, w_flat, spec, t_host, step_size, adj_step_size, fwd_format, fused=None):
         eng = stage.TcEngine(spec, w_flat)
         if fwd_format is not None:
             eng.fwd_format = stage.fwd_format_code(fwd_format)
@@ -172,12 +232,13 @@ class _ContinuousAdjointRK4TC(torch.autograd.Function):
         npdt = np.float64 if t_host.dtype == torch.float64 else np.float32
         with torch.no_grad():
             y = rk4_forward_rows(eng, y0.contiguous().float(), th, step_size, np_dtype=npdt)
-        ctx.eng, ctx.th, ctx.adj_step_size, ctx.npdt = eng, th, adj_step_size, npdt
+        ctx.eng, ctx.th, ctx.adj_step_size, ctx.npdt, ctx.fused = eng, th, adj_step_size, npdt, fused
         ctx.save_for_backward(y)
         return y
 
     @staticmethod
     def backward(ctx, grad_y):
         (y,) = ctx.saved_tensors
-        gy0, gw = rk4_continuous_adjoint(ctx.eng, ctx.th, y, grad_y.contiguous().float(), ctx.adj_step_size, np_dtype=ctx.npdt)
-        return gy0, None, gw, None, None, None, None, None
+        gy0, gw = rk4_continuous_adjoint(ctx.eng, ctx.th, y, grad_y.contiguous().float(), ctx.adj_step_size, np_dtype=ctx.npdt,
+                                         fused=ctx.fused)
+        return gy0, None, gw, None, None, None, None, None, None

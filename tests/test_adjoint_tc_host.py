@@ -118,6 +118,41 @@ class FakeEngine:
         self.aug_stage_finish(gx, as_p, a_in, a_next, inv, hb, True, B)
         self.aug_stage_prepare(a0, list(ka) + [gx], hbn, c_next, B, as_p, u)
 
+    def combine_backward(self, g, c, B, G_y0, G_a, accumulate):
+        """ab200_pv_combine_backward: G_y0 = [g.p, cpv g.p + g.v, g.h] ; G_a[j] = cpa[j] g.p + cva[j] g.v"""
+        assert not accumulate
+        D, P = self.D, self.P
+        gp, gv, gh = adjoint_tc._views(g, D, P)
+        op, ov, oh = adjoint_tc._views(G_y0, D, P)
+        op.copy_(gp)
+        ov.copy_(c.cpv * gp + gv)
+        oh.copy_(gh)
+        for j, buf in enumerate(G_a):
+            buf.view(-1, P // 4, TM, 4).copy_(c.cpa[j] * gp + c.cva[j] * gv)
+
+    def stage_backward_fused(self, y0, a_bufs, stages, B, x_blobs=None, save_level=0, y0_accum=None, upstream=None):
+        """ab200_stage_backward_fused without a gather entry: entry k's upstream = g_base + sum over earlier entries' gx"""
+        assert y0_accum is None and upstream is None and x_blobs is None
+        D, P = self.D, self.P
+        for (n_a, cin, t, g_base, sources, gx_out) in stages:
+            u = g_base.clone()
+            uv = u.view(-1, P // 4, TM, 4)
+            for (src, dp, dv) in sources:
+                sp_, sv_, _ = adjoint_tc._views(stages[src][5], D, P)
+                uv.add_(dp * sp_ + dv * sv_)
+            self.stage_backward(y0, a_bufs[:n_a], cin, t, B, u, [], [], [], gx_out)
+
+    def adjoint_gather(self, base, gx, cpv, B, out):
+        """ab200_adjoint_gather: out = base + sum_l [gx_l.p, cpv_l gx_l.p + gx_l.v, gx_l.h]"""
+        D, P = self.D, self.P
+        out.copy_(base)
+        op, ov, oh = adjoint_tc._views(out, D, P)
+        for g, cv in zip(gx, cpv):
+            gp, gv, gh = adjoint_tc._views(g, D, P)
+            op.add_(gp)
+            ov.add_(cv * gp + gv)
+            oh.add_(gh)
+
     def flush(self):
         pass
 
@@ -152,8 +187,9 @@ def test_step_grid_mirrors_the_package_grid_constructor():
         adjoint_tc.step_grid(0.0, 1.0, 0.0)
 
 
+@pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("B,step_size", [(3, None), (130, None), (5, 0.25), (5, 0.4)])
-def test_tc_continuous_adjoint_algebra_matches_the_oracle(B, step_size):
+def test_tc_continuous_adjoint_algebra_matches_the_oracle(B, step_size, fused):
     oracle, y0 = _setup(B)
     func = oracle.odefunc
     E = oracle.dims.emb_dim if hasattr(oracle, "dims") else 64
@@ -172,7 +208,7 @@ def test_tc_continuous_adjoint_algebra_matches_the_oracle(B, step_size):
     rows = adjoint_tc.rk4_forward_rows(eng, y0, th, step_size, lay=FakeLayout, np_dtype=np.float64)
     assert torch.allclose(rows, ref.detach(), atol=1e-12, rtol=1e-12)
     grad_rows = (2.0 * rows * wgt * wgt / rows.numel())
-    gy0, gw = adjoint_tc.rk4_continuous_adjoint(eng, th, rows, grad_rows, step_size, lay=FakeLayout, np_dtype=np.float64)
+    gy0, gw = adjoint_tc.rk4_continuous_adjoint(eng, th, rows, grad_rows, step_size, lay=FakeLayout, np_dtype=np.float64, fused=fused)
     assert torch.allclose(gy0, y0r.grad, atol=1e-12, rtol=1e-9), float((gy0 - y0r.grad).abs().max())
     assert torch.allclose(gw, ref_gw, atol=1e-12, rtol=1e-9), float((gw - ref_gw).abs().max())
     n_steps = sum(len(adjoint_tc.step_grid(th[i], th[i - 1], step_size, np.float64)) - 1 for i in range(1, len(th)))

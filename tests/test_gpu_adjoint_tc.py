@@ -45,12 +45,13 @@ def _agents(B, Z, seed=1):
     return torch.randint(0, Z, (B,), generator=g), torch.randint(0, Z, (B,), generator=g), torch.rand(B, 2, generator=g)
 
 
+@pytest.mark.parametrize("fused", [True, False])       # the two launch structures of adjoint_tc.py (default: fused while it fits)
 @pytest.mark.parametrize("B,times,step_size", [
     (130, [0.0, 0.4, 1.0, 1.5, 2.0, 3.0], None),       # one 3/8-rule step per output interval, y re-seeded at every row
     (300, [0.0, 3.0], 0.25),                            # 12 steps forward, 12 augmented steps backward, two rows exist
     (129, [0.0, 0.7, 2.0], 0.3),                        # outputs between grid points (linear interpolation), shortened last step
 ])
-def test_tc_continuous_adjoint_rk4_vs_oracle(B, times, step_size):
+def test_tc_continuous_adjoint_rk4_vs_oracle(B, times, step_size, fused):
     import ananke_abm_b200 as ab
     dev = _cuda()
     oracle, model = _pair()
@@ -66,7 +67,7 @@ def test_tc_continuous_adjoint_rk4_vs_oracle(B, times, step_size):
     ((ref[:, :, :128] * wgt) ** 2).mean().backward()
 
     y0 = model.initial_state(home.to(dev), work.to(dev), traits.to(dev)).detach().requires_grad_(True)
-    out = ab.odeint_adjoint(model.odefunc, y0, t.to(dev), method="rk4", options=dict(opts, precision="bf16"))
+    out = ab.odeint_adjoint(model.odefunc, y0, t.to(dev), method="rk4", options=dict(opts, precision="bf16", adjoint_fused=fused))
     assert type(out.grad_fn).__name__.startswith("_ContinuousAdjointRK4TC")      # the tensor-core path, not the fp32 augmented solve
     ((out[:, :, :128] * wgt.to(dev)) ** 2).mean().backward()
     torch.cuda.synchronize()
