@@ -196,6 +196,30 @@ def _aug_step_fused(eng, yb: torch.Tensor, ab: torch.Tensor, t0: float, t1: floa
     return y_new, a_new
 
 
+def _aug_step_linear(eng, yb: torch.Tensor, ab: torch.Tensor, t0: float, t1: float, B: int, w: _FusedBuffers, flush_each: bool):
+    """`_aug_step_fused` with one `ab200_stage_backward` launch per stage: the earlier stages' products enter as external sources of
+    the launch's upstream gather, so there is still no elementwise pass between the stages, and a one-stage blob ring is enough
+    (`flush_each`: the weight-gradient pass runs after every stage)."""
+    h = t1 - t0
+    cins = [RK38.stage_input(s, h) for s in range(4)]
+    times = [t0 + RK38.c[s] * h for s in range(3)] + [t1]
+    c, cpa, cva, dp, dv, wv = fused_step_coefficients(h)
+    eng.stage_forward_fused(yb, w.A, [(s, cins[s], times[s], w.A[s] if s < 3 else None) for s in range(4)], B, y_out=w.y_next,
+                            cout=RK38.combo(RK38.b, h))
+    eng.combine_backward(ab, stage.Combo(-h, cpa, cva), B, w.base, w.GB, accumulate=False)
+    for s in range(4):
+        src = [i for i in range(s) if dp[s][i] != 0.0 or dv[s][i] != 0.0]
+        eng.stage_backward(yb, w.A[:s], cins[s], times[s], B, w.GB[s], [w.GX[i] for i in src], [dp[s][i] for i in src],
+                           [dv[s][i] for i in src], w.GX[s])
+        if flush_each:
+            eng.flush()
+    eng.flush()
+    eng.adjoint_gather(w.base, w.GX, wv, B, w.a_next)
+    y_new, a_new = w.y_next, w.a_next
+    w.y_next, w.a_next = yb, ab
+    return y_new, a_new
+
+
 def rk4_continuous_adjoint(eng, t_host: Sequence[float], y_rows: torch.Tensor, grad_rows: torch.Tensor,
                            step_size: Optional[float] = None, lay=_CudaLayout, np_dtype=np.float32, fused: Optional[bool] = None):
     """-> (dL/dy0 row-major [B, D], a_theta(t[0]) = dL/dtheta in the drift's flat parameter order).
@@ -206,9 +230,15 @@ def rk4_continuous_adjoint(eng, t_host: Sequence[float], y_rows: torch.Tensor, g
     dev = grad_rows.device
     if fused is None:
         fused = stage.padded_rows(B) * 3100 * 4 < (56 << 30)
-    eng.backward_begin(B, 4 if fused else 1)
-    w = (_FusedBuffers if fused else _AugBuffers)(B, D, eng.P, dev, lay)
-    step = _aug_step_fused if fused else _aug_step
+    if fused == "linear" or fused == "linear1":      # experiment / large-batch structure: per-stage launches over the linear form
+        eng.backward_begin(B, 1 if fused == "linear1" else 4)
+        w = _FusedBuffers(B, D, eng.P, dev, lay)
+        fe = fused == "linear1"
+        step = lambda e, y, a, ta, tb, b, ww: _aug_step_linear(e, y, a, ta, tb, b, ww, fe)      # noqa: E731
+    else:
+        eng.backward_begin(B, 4 if fused else 1)
+        w = (_FusedBuffers if fused else _AugBuffers)(B, D, eng.P, dev, lay)
+        step = _aug_step_fused if fused else _aug_step
     ab = lay.block(grad_rows[T - 1].contiguous())
     yb = None
     for i in range(T - 1, 0, -1):

@@ -63,6 +63,8 @@ def _solver_options(config) -> dict:
     opt = {"precision": getattr(config, "precision", "f32")}
     if getattr(config, "adjoint", False) and getattr(config, "adjoint_mode", None):
         opt["adjoint_mode"] = config.adjoint_mode          # "continuous" (torchdiffeq semantics, default) | "discrete"
+    if getattr(config, "adjoint", False) and getattr(config, "adjoint_fused", None) is not None:
+        opt["adjoint_fused"] = config.adjoint_fused      # launch structure of the tensor-core continuous adjoint (adjoint_tc.py)
     if config.ode_method == "rk4" and getattr(config, "step_size", None):
         opt["step_size"] = float(config.step_size)          # torchdiffeq fixed-grid option: solver grid t[0] + k step_size
     if config.ode_method == "dopri5" and opt["precision"] == "bf16":
