@@ -90,9 +90,6 @@ SIGNATURES = {
     "ab200_adjoint_gather_upstream": (C.c_int, [_dp, _vp, _vp, _i32, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ab200_pv_combine_backward_multi": (C.c_int, [_dp, _vp, _i32, _vp, _vp, _vp, _i32, _i64, _vp, _vp, _i32, _i32, _vp, _i32, _vp]),
     "ab200_stage_upstream": (C.c_int, [_dp, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _vp]),
-    "ab200_aug_stage_prepare": (C.c_int, [_dp, _vp, _vp, _i32, _vp, _f32, _i64, _vp, _vp, _vp]),
-    "ab200_aug_stage_finish": (C.c_int, [_dp, _vp, _vp, _vp, _vp, _f32, _f32, _i32, _i64, _vp]),
-    "ab200_aug_stage_finish_prepare": (C.c_int, [_dp, _vp, _vp, _vp, _vp, _f32, _f32, _vp, _vp, _i32, _vp, _f32, _vp, _i64, _vp]),
     "ab200_wgrad_accumulate": (C.c_int, [_dp, _vp, _i32, _i32, _vp, _vp, _i32, _i32, _i32, _vp]),
     "ab200_wgrad_finalize": (C.c_int, [_dp, _vp, _vp, _vp]),
     "ab200_stage_status_offset": (C.c_int, [_dp, _vp, _vp]),

@@ -18,13 +18,13 @@ feeds back into the dynamics, so its stage values are not formed: the stage's up
 c_s = -h b_s (h < 0 going backward) and the weight-gradient accumulators ARE a_theta.  The vector-Jacobian product is
 linear in its upstream, so gx comes back scaled by c_s and is divided out in the stage algebra.
 
-Two launch structures (`rk4_continuous_adjoint(fused=...)`, `options["adjoint_fused"]`):
-  fused (default while the blobs of four stages fit, up to ~4.6M agents per GPU): every stage's upstream gradient is LINEAR in a0 and
-        the earlier stages' products (`fused_step_coefficients`), so the four vector-Jacobian products of a step are ONE
-        `ab200_stage_backward_fused` launch whose entries feed each other through their gx, framed by `ab200_pv_combine_backward`
-        (the a0 parts) and `ab200_adjoint_gather` (the step's solution): five launches per step;
-  staged (8M agents on one GPU: a one-stage blob ring): one `ab200_stage_backward` launch per stage and ONE fused elementwise pass
-        per stage (`ab200_aug_stage_finish_prepare`; `ab200_aug_stage_prepare` / `_finish` open and close a step).
+Every stage's upstream gradient c_s a_v,s is LINEAR in a0 and the earlier stages' products (`fused_step_coefficients`), and so is
+the step's solution a_y(t + h): an augmented step is the fused forward launch of the y stages, `ab200_pv_combine_backward` (the a0
+parts of the four upstream gradients and of the solution), the vector-Jacobian products with the earlier products as gather sources
+of the launch, the weight-gradient pass, and `ab200_adjoint_gather` (the solution) -- no elementwise pass between the stages.
+Two launch structures (`rk4_continuous_adjoint(fused=...)`, `options["adjoint_fused"]`): the four products as ONE
+`ab200_stage_backward_fused` launch (default while the blobs of four stages fit, up to ~4.6M agents per GPU), or one
+`ab200_stage_backward` launch per stage with a one-stage blob ring (8M agents on one GPU).
 Every evaluation of A and of its vector-Jacobian product is a tcgen05 kernel (fp16 / bf16 operands, fp32 accumulate);
 y, a_y and a_theta are fp32.  Stated tolerance: that of the tensor-core path.
 """
@@ -103,48 +103,6 @@ def rk4_forward_rows(eng, y0: torch.Tensor, t_host: Sequence[float], step_size: 
     return y_path
 
 
-class _AugBuffers:
-    def __init__(self, B: int, D: int, P: int, device, lay):
-        self.A = [lay.zeros(B, P, device) for _ in range(3)]      # stage accelerations of the y part
-        self.U = lay.zeros(B, P, device)                          # upstream of the stage's vector-Jacobian product: c_s a_v,s
-        self.ASP = lay.zeros(B, P, device)                        # p part of the stage value of a_y
-        self.KA = [lay.zeros(B, D, device) for _ in range(4)]     # stage derivatives of a_y (zeroed: padding rows stay zero)
-        self.y_next = lay.zeros(B, D, device)
-        self.a_next = lay.zeros(B, D, device)
-
-
-def _aug_step(eng, yb: torch.Tensor, ab: torch.Tensor, t0: float, t1: float, B: int, w: _AugBuffers):
-    """one 3/8-rule step of the augmented system from t0 to t1 (h = t1 - t0, negative in the backward pass).
-    Returns (y(t1), a_y(t1)) as buffers of `w` swapped with the inputs; a_theta accumulates inside the engine."""
-    h = t1 - t0
-    cins = [RK38.stage_input(s, h) for s in range(4)]
-    times = [t0 + RK38.c[s] * h for s in range(3)] + [t1]
-    # The y part of the augmented system does not depend on a_y: its four stages (A_1..A_3 and y(t1)) are ONE fused forward launch,
-    # exactly the step of the forward solve (the tile's y and A_j stay in L2 between the stages: 345 us instead of 4 x 169 us over
-    # 250,112 agents); the vector-Jacobian products below re-read A_1..A_3.
-    eng.stage_forward_fused(yb, w.A, [(s, cins[s], times[s], w.A[s] if s < 3 else None) for s in range(4)], B, y_out=w.y_next,
-                            cout=RK38.combo(RK38.b, h))
-    # stage value of a_y:  a_s = a0 + h sum_j beta_sj ka_j  ->  its p part (ASP) and the upstream  c_s a_s.v (U)
-    eng.aug_stage_prepare(ab, [], [], -h * RK38.b[0], B, w.ASP, w.U)
-    for s in range(4):
-        c = -h * RK38.b[s]
-        # c_s J_A^T a_v,s  (+ the weight-gradient blobs of this stage, with the same scale)
-        eng.stage_backward(yb, w.A[:s], cins[s], times[s], B, w.U, [], [], [], w.KA[s])
-        # ka_s = -[gx.p, a_p,s + gx.v, gx.h]  (in place) ;  a_next (+)= h b_s ka_s ;  and the next stage's ASP / U in the same pass
-        a_in = ab if s == 0 else w.a_next
-        if s < 3:
-            nxt = RK38.beta[s + 1]
-            src = [(w.KA[j], h * nxt[j]) for j in range(s) if nxt[j] != 0.0]
-            eng.aug_stage_finish_prepare(w.KA[s], w.ASP, a_in, w.a_next, -1.0 / c, h * RK38.b[s], ab, [k for k, _ in src],
-                                         [x for _, x in src] + [h * nxt[s]], -h * RK38.b[s + 1], w.U, B)
-        else:
-            eng.aug_stage_finish(w.KA[s], w.ASP, a_in, w.a_next, -1.0 / c, h * RK38.b[s], False, B)
-    eng.flush()
-    y_new, a_new = w.y_next, w.a_next
-    w.y_next, w.a_next = yb, ab
-    return y_new, a_new
-
-
 class _FusedBuffers:
     def __init__(self, B: int, D: int, P: int, device, lay):
         self.A = [lay.zeros(B, P, device) for _ in range(3)]      # stage accelerations of the y part
@@ -174,32 +132,15 @@ def fused_step_coefficients(h: float):
     return c, cpa, cva, dp, dv, w
 
 
-def _aug_step_fused(eng, yb: torch.Tensor, ab: torch.Tensor, t0: float, t1: float, B: int, w: _FusedBuffers):
-    """`_aug_step` as FIVE launches: the fused forward launch of the y stages, one elementwise pass for the a0 part of all four
-    upstream gradients (and the a0 part of the step's solution), ONE fused backward launch whose entries feed each other through their
-    gx (upstream_s needs the earlier stages' products of the same agent only), the weight-gradient pass, one gather pass."""
-    h = t1 - t0
-    cins = [RK38.stage_input(s, h) for s in range(4)]
-    times = [t0 + RK38.c[s] * h for s in range(3)] + [t1]
-    c, cpa, cva, dp, dv, wv = fused_step_coefficients(h)
-    eng.stage_forward_fused(yb, w.A, [(s, cins[s], times[s], w.A[s] if s < 3 else None) for s in range(4)], B, y_out=w.y_next,
-                            cout=RK38.combo(RK38.b, h))
-    # base = [a0.p, a0.v - h a0.p, a0.h] ;  GB[s] = cpa[s] a0.p + cva[s] a0.v
-    eng.combine_backward(ab, stage.Combo(-h, cpa, cva), B, w.base, w.GB, accumulate=False)
-    stages = [(s, cins[s], times[s], w.GB[s], [(i, dp[s][i], dv[s][i]) for i in range(s) if dp[s][i] != 0.0 or dv[s][i] != 0.0], w.GX[s])
-              for s in range(4)]
-    eng.stage_backward_fused(yb, w.A, stages, B)
-    eng.flush()
-    eng.adjoint_gather(w.base, w.GX, wv, B, w.a_next)
-    y_new, a_new = w.y_next, w.a_next
-    w.y_next, w.a_next = yb, ab
-    return y_new, a_new
-
-
-def _aug_step_linear(eng, yb: torch.Tensor, ab: torch.Tensor, t0: float, t1: float, B: int, w: _FusedBuffers, flush_each: bool):
-    """`_aug_step_fused` with one `ab200_stage_backward` launch per stage: the earlier stages' products enter as external sources of
-    the launch's upstream gather, so there is still no elementwise pass between the stages, and a one-stage blob ring is enough
-    (`flush_each`: the weight-gradient pass runs after every stage)."""
+def _aug_step(eng, yb: torch.Tensor, ab: torch.Tensor, t0: float, t1: float, B: int, w: _FusedBuffers, fused: bool):
+    """One 3/8-rule step of the augmented system from t0 to t1 (h = t1 - t0, negative in the backward pass); a_theta accumulates
+    inside the engine.  Returns (y(t1), a_y(t1)) as buffers of `w` swapped with the inputs.
+      1. the four y stages (A_1..A_3, y(t1)): ONE fused forward launch, exactly the step of the forward solve (they do not depend on a_y)
+      2. `ab200_pv_combine_backward`: base = [a0.p, a0.v - h a0.p, a0.h] and the a0 part GB[s] of every stage's upstream gradient
+      3. the vector-Jacobian products GX[s] = c_s J_A^T a_v,s (+ the stage's weight-gradient blobs with the same scale); the earlier
+         stages' products enter through the launch's upstream gather: `fused` = ONE `ab200_stage_backward_fused` launch whose
+         entries feed each other, else one `ab200_stage_backward` launch and one weight-gradient pass per stage (one-stage blob ring)
+      4. the weight-gradient pass;  5. `ab200_adjoint_gather`: a_y(t1) = base + sum_i [GX_i.p, w_i GX_i.p + GX_i.v, GX_i.h]"""
     h = t1 - t0
     cins = [RK38.stage_input(s, h) for s in range(4)]
     times = [t0 + RK38.c[s] * h for s in range(3)] + [t1]
@@ -207,11 +148,14 @@ def _aug_step_linear(eng, yb: torch.Tensor, ab: torch.Tensor, t0: float, t1: flo
     eng.stage_forward_fused(yb, w.A, [(s, cins[s], times[s], w.A[s] if s < 3 else None) for s in range(4)], B, y_out=w.y_next,
                             cout=RK38.combo(RK38.b, h))
     eng.combine_backward(ab, stage.Combo(-h, cpa, cva), B, w.base, w.GB, accumulate=False)
-    for s in range(4):
-        src = [i for i in range(s) if dp[s][i] != 0.0 or dv[s][i] != 0.0]
-        eng.stage_backward(yb, w.A[:s], cins[s], times[s], B, w.GB[s], [w.GX[i] for i in src], [dp[s][i] for i in src],
-                           [dv[s][i] for i in src], w.GX[s])
-        if flush_each:
+    srcs = [[i for i in range(s) if dp[s][i] != 0.0 or dv[s][i] != 0.0] for s in range(4)]
+    if fused:
+        eng.stage_backward_fused(yb, w.A, [(s, cins[s], times[s], w.GB[s], [(i, dp[s][i], dv[s][i]) for i in srcs[s]], w.GX[s])
+                                           for s in range(4)], B)
+    else:
+        for s in range(4):
+            eng.stage_backward(yb, w.A[:s], cins[s], times[s], B, w.GB[s], [w.GX[i] for i in srcs[s]], [dp[s][i] for i in srcs[s]],
+                               [dv[s][i] for i in srcs[s]], w.GX[s])
             eng.flush()
     eng.flush()
     eng.adjoint_gather(w.base, w.GX, wv, B, w.a_next)
@@ -223,22 +167,15 @@ def _aug_step_linear(eng, yb: torch.Tensor, ab: torch.Tensor, t0: float, t1: flo
 def rk4_continuous_adjoint(eng, t_host: Sequence[float], y_rows: torch.Tensor, grad_rows: torch.Tensor,
                            step_size: Optional[float] = None, lay=_CudaLayout, np_dtype=np.float32, fused: Optional[bool] = None):
     """-> (dL/dy0 row-major [B, D], a_theta(t[0]) = dL/dtheta in the drift's flat parameter order).
-    `fused` (default: when the blobs of four stages fit in ~56 GB, i.e. up to ~4.6M agents): the four vector-Jacobian products of a
-    step in one launch (`_aug_step_fused`); otherwise one launch per stage with a one-stage blob ring (`_aug_step`: 8M agents on
-    one GPU)."""
+    `fused` (default: while the blobs of four stages fit in ~56 GB, i.e. up to ~4.6M agents): the four vector-Jacobian products of a
+    step in one launch; otherwise one launch per stage with a one-stage blob ring and the weight-gradient pass after every stage
+    (8M agents on one GPU)."""
     T, B, D = grad_rows.shape
     dev = grad_rows.device
     if fused is None:
         fused = stage.padded_rows(B) * 3100 * 4 < (56 << 30)
-    if fused == "linear" or fused == "linear1":      # experiment / large-batch structure: per-stage launches over the linear form
-        eng.backward_begin(B, 1 if fused == "linear1" else 4)
-        w = _FusedBuffers(B, D, eng.P, dev, lay)
-        fe = fused == "linear1"
-        step = lambda e, y, a, ta, tb, b, ww: _aug_step_linear(e, y, a, ta, tb, b, ww, fe)      # noqa: E731
-    else:
-        eng.backward_begin(B, 4 if fused else 1)
-        w = (_FusedBuffers if fused else _AugBuffers)(B, D, eng.P, dev, lay)
-        step = _aug_step_fused if fused else _aug_step
+    eng.backward_begin(B, 4 if fused else 1)
+    w = _FusedBuffers(B, D, eng.P, dev, lay)
     ab = lay.block(grad_rows[T - 1].contiguous())
     yb = None
     for i in range(T - 1, 0, -1):
@@ -246,7 +183,7 @@ def rk4_continuous_adjoint(eng, t_host: Sequence[float], y_rows: torch.Tensor, g
         yb = lay.block(row) if yb is None else lay.block(row, yb)      # re-seed y with the saved row (adjoint.py: aug_state[1] = y[i - 1])
         grid = step_grid(t_host[i], t_host[i - 1], step_size, np_dtype)
         for n in range(len(grid) - 1):
-            yb, ab = step(eng, yb, ab, grid[n], grid[n + 1], B, w)
+            yb, ab = _aug_step(eng, yb, ab, grid[n], grid[n + 1], B, w, bool(fused))
         lay.block(grad_rows[i - 1].contiguous(), ab, accumulate=True)
     gw = eng.backward_end()
     return lay.unblock(ab, B, D), gw

@@ -58,13 +58,6 @@ int stage_bwd_tc(const ab200_drift_desc* d, const uint8_t* image, const float* y
 int pv_combine_bwd_multi(const ab200_drift_desc* d, const float* const* g, int n_src, const float* cpv, const float* cpa, const float* cva,
                          int n_a, int64_t B, float* G_y0, float* const* G_a, int accumulate, int rowmajor_mask, const float* add_a, int add_idx,
                          cudaStream_t st);
-int aug_stage_prepare(const ab200_drift_desc* d, const float* a0, const float* const* ka, int n, const float* hb, float c, int64_t B,
-                      float* as_p, float* u, cudaStream_t st);
-int aug_stage_finish(const ab200_drift_desc* d, float* gx, const float* as_p, const float* a_in, float* a_next, float inv, float hb,
-                     int write_ka, int64_t B, cudaStream_t st);
-int aug_stage_finish_prepare(const ab200_drift_desc* d, float* gx, float* as_p, const float* a_in, float* a_next, float inv, float hb,
-                             const float* a0, const float* const* ka, int n, const float* hbn, float cn, float* u, int64_t B,
-                             cudaStream_t st);
 int ga_assemble(const ab200_drift_desc* d, const float* base, const float* const* gx, int n, const float* dp, const float* dv,
                 int64_t B, float* out, cudaStream_t st);
 int stage_bwd_tc_multi(const ab200_drift_desc* d, const uint8_t* image, const float* y0, const float* const* a_ptrs,
@@ -428,25 +421,6 @@ int ab200_pv_combine_backward_multi(const ab200_drift_desc* d, const float* cons
                                     ab200_stream_t stream) {
   if (!desc_ok(d) || !g || !cpv_host || !G_y0 || B <= 0 || (n_a > 0 && (!G_a || !cpa_host || !cva_host))) return AB200_ERR_BAD_ARG;
   return pv_combine_bwd_multi(d, g, n_src, cpv_host, cpa_host, cva_host, n_a, B, G_y0, G_a, accumulate, rowmajor_mask, add_a, add_index, (cudaStream_t)stream);
-}
-
-int ab200_aug_stage_prepare(const ab200_drift_desc* d, const float* a0, const float* const* ka, int32_t n, const float* hb_host, float c,
-                            int64_t B, float* as_p, float* u, ab200_stream_t stream) {
-  if (!desc_ok(d) || !a0 || !as_p || !u || B <= 0 || n < 0 || (n > 0 && (!ka || !hb_host))) return AB200_ERR_BAD_ARG;
-  return aug_stage_prepare(d, a0, ka, n, hb_host, c, B, as_p, u, (cudaStream_t)stream);
-}
-
-int ab200_aug_stage_finish(const ab200_drift_desc* d, float* gx, const float* as_p, const float* a_in, float* a_next, float inv, float hb,
-                           int32_t write_ka, int64_t B, ab200_stream_t stream) {
-  if (!desc_ok(d) || !gx || !as_p || !a_in || !a_next || B <= 0) return AB200_ERR_BAD_ARG;
-  return aug_stage_finish(d, gx, as_p, a_in, a_next, inv, hb, write_ka, B, (cudaStream_t)stream);
-}
-
-int ab200_aug_stage_finish_prepare(const ab200_drift_desc* d, float* gx, float* as_p, const float* a_in, float* a_next, float inv, float hb,
-                                   const float* a0, const float* const* ka, int32_t n, const float* hbn_host, float c_next, float* u,
-                                   int64_t B, ab200_stream_t stream) {
-  if (!desc_ok(d) || !gx || !as_p || !a_in || !a_next || !a0 || !hbn_host || !u || B <= 0 || n < 0 || (n > 0 && !ka)) return AB200_ERR_BAD_ARG;
-  return aug_stage_finish_prepare(d, gx, as_p, a_in, a_next, inv, hb, a0, ka, n, hbn_host, c_next, u, B, (cudaStream_t)stream);
 }
 
 int ab200_stage_upstream(const ab200_drift_desc* d, const float* g_base, const float* const* gx, int32_t n_g, const float* dp_host,

@@ -541,176 +541,6 @@ int ga_assemble(const ab200_drift_desc* d, const float* base, const float* const
   return check_launch();
 }
 
-// ---- continuous adjoint on the stage kernels (adjoint_tc.py): stage algebra of the adjoint state a_y = [a_p, a_v, a_h] ------------
-// Augmented dynamics of the second-order drift f = [v, A(p, v, h, t), 0]:  da_y/dt = -[gx.p, a_p + gx.v, gx.h],  gx = J_A^T a_v.
-// prepare: the stage value a_s = a0 + sum_j hb[j] ka_j of an explicit Runge-Kutta stage; only what the stage needs leaves the
-//          kernel: its p part (enters ka_s) and u = c a_s.v, the upstream gradient of the stage's vector-Jacobian product.
-// finish : ka_s = -[gx.p, a_p,s + gx.v, gx.h] from the SCALED product gx' = c gx the stage-backward launch returned (inv = -1 / c),
-//          folded into the step's solution: a_next = a_in + hb ka_s; ka_s replaces gx' when later stages need it.
-struct AugPrepArgs {
-  const float* a0;
-  const float* ka[3];
-  float hb[3];
-  float c;
-  float* as_p;
-  float* u;
-  int n, ntiles, P, H;
-};
-__global__ void __launch_bounds__(256) aug_stage_prepare_kernel(const __grid_constant__ AugPrepArgs a) {
-  const int P4 = a.P / 4, Y4 = 2 * P4 + a.H / 4;
-  const int64_t n = (int64_t)a.ntiles * P4 * EL_TM;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int row = (int)(i % EL_TM);
-    const int64_t q = i / EL_TM;
-    const int grp = (int)(q % P4), tile = (int)(q / P4);
-    const size_t t0 = (size_t)tile * Y4 * EL_TM + row, fp = (size_t)grp * EL_TM, fv = (size_t)(P4 + grp) * EL_TM;
-    float4 p = (reinterpret_cast<const float4*>(a.a0) + t0)[fp], v = (reinterpret_cast<const float4*>(a.a0) + t0)[fv];
-#pragma unroll
-    for (int j = 0; j < 3; ++j)
-      if (j < a.n) {
-        const float4 kp = (reinterpret_cast<const float4*>(a.ka[j]) + t0)[fp], kv = (reinterpret_cast<const float4*>(a.ka[j]) + t0)[fv];
-        const float w = a.hb[j];
-        p.x += w * kp.x; p.y += w * kp.y; p.z += w * kp.z; p.w += w * kp.w;
-        v.x += w * kv.x; v.y += w * kv.y; v.z += w * kv.z; v.w += w * kv.w;
-      }
-    const size_t o = ((size_t)tile * P4 + grp) * EL_TM + row;
-    reinterpret_cast<float4*>(a.as_p)[o] = p;
-    reinterpret_cast<float4*>(a.u)[o] = make_float4(a.c * v.x, a.c * v.y, a.c * v.z, a.c * v.w);
-  }
-}
-
-struct AugFinArgs {
-  float* gx;
-  const float* as_p;
-  const float* a_in;
-  float* a_next;
-  float inv, hb;
-  int write_ka, ntiles, P, H;
-};
-__global__ void __launch_bounds__(256) aug_stage_finish_kernel(const __grid_constant__ AugFinArgs a) {
-  const int P4 = a.P / 4, H4 = a.H / 4, Y4 = 2 * P4 + H4;
-  const int64_t n = (int64_t)a.ntiles * (P4 + H4) * EL_TM;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    int tile, grp, row;
-    decode(i, P4, H4, tile, grp, row);
-    const size_t t0 = (size_t)tile * Y4 * EL_TM + row;
-    float4* g4 = reinterpret_cast<float4*>(a.gx) + t0;
-    const float4* i4 = reinterpret_cast<const float4*>(a.a_in) + t0;
-    float4* o4 = reinterpret_cast<float4*>(a.a_next) + t0;
-    if (grp >= P4) {
-      const size_t f = (size_t)(2 * P4 + (grp - P4)) * EL_TM;
-      const float4 g = g4[f], x = i4[f];
-      const float4 k = make_float4(a.inv * g.x, a.inv * g.y, a.inv * g.z, a.inv * g.w);
-      o4[f] = make_float4(x.x + a.hb * k.x, x.y + a.hb * k.y, x.z + a.hb * k.z, x.w + a.hb * k.w);
-      if (a.write_ka) g4[f] = k;
-      continue;
-    }
-    const size_t fp = (size_t)grp * EL_TM, fv = (size_t)(P4 + grp) * EL_TM;
-    const float4 gp = g4[fp], gv = g4[fv], xp = i4[fp], xv = i4[fv];
-    const float4 ap = reinterpret_cast<const float4*>(a.as_p)[((size_t)tile * P4 + grp) * EL_TM + row];
-    const float4 kp = make_float4(a.inv * gp.x, a.inv * gp.y, a.inv * gp.z, a.inv * gp.w);
-    const float4 kv = make_float4(a.inv * gv.x - ap.x, a.inv * gv.y - ap.y, a.inv * gv.z - ap.z, a.inv * gv.w - ap.w);
-    o4[fp] = make_float4(xp.x + a.hb * kp.x, xp.y + a.hb * kp.y, xp.z + a.hb * kp.z, xp.w + a.hb * kp.w);
-    o4[fv] = make_float4(xv.x + a.hb * kv.x, xv.y + a.hb * kv.y, xv.z + a.hb * kv.z, xv.w + a.hb * kv.w);
-    if (a.write_ka) { g4[fp] = kp; g4[fv] = kv; }
-  }
-}
-
-// finish of stage s and prepare of stage s + 1 in ONE pass (ka_s never re-read from HBM; one launch less per stage):
-//   ka_s = inv gx - [0, as_p, 0];  a_next = a_in + hb ka_s;  gx <- ka_s;
-//   a_{s+1} = a0 + sum_{j<n} hbn[j] ka[j] + hbn[n] ka_s;  as_p <- a_{s+1}.p (in place);  u = cn a_{s+1}.v
-struct AugFinPrepArgs {
-  float* gx;
-  float* as_p;
-  const float* a_in;
-  float* a_next;
-  const float* a0;
-  const float* ka[2];
-  float hbn[3];
-  float inv, hb, cn;
-  float* u;
-  int n, ntiles, P, H;
-};
-__global__ void __launch_bounds__(256) aug_stage_finish_prepare_kernel(const __grid_constant__ AugFinPrepArgs a) {
-  const int P4 = a.P / 4, H4 = a.H / 4, Y4 = 2 * P4 + H4;
-  const int64_t n = (int64_t)a.ntiles * (P4 + H4) * EL_TM;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    int tile, grp, row;
-    decode(i, P4, H4, tile, grp, row);
-    const size_t t0 = (size_t)tile * Y4 * EL_TM + row;
-    float4* g4 = reinterpret_cast<float4*>(a.gx) + t0;
-    const float4* i4 = reinterpret_cast<const float4*>(a.a_in) + t0;
-    float4* o4 = reinterpret_cast<float4*>(a.a_next) + t0;
-    if (grp >= P4) {
-      const size_t f = (size_t)(2 * P4 + (grp - P4)) * EL_TM;
-      const float4 g = g4[f], x = i4[f];
-      const float4 k = make_float4(a.inv * g.x, a.inv * g.y, a.inv * g.z, a.inv * g.w);
-      o4[f] = make_float4(x.x + a.hb * k.x, x.y + a.hb * k.y, x.z + a.hb * k.z, x.w + a.hb * k.w);
-      g4[f] = k;
-      continue;
-    }
-    const size_t fp = (size_t)grp * EL_TM, fv = (size_t)(P4 + grp) * EL_TM, o = ((size_t)tile * P4 + grp) * EL_TM + row;
-    const float4 gp = g4[fp], gv = g4[fv], xp = i4[fp], xv = i4[fv];
-    const float4 ap = reinterpret_cast<const float4*>(a.as_p)[o];
-    const float4 kp = make_float4(a.inv * gp.x, a.inv * gp.y, a.inv * gp.z, a.inv * gp.w);
-    const float4 kv = make_float4(a.inv * gv.x - ap.x, a.inv * gv.y - ap.y, a.inv * gv.z - ap.z, a.inv * gv.w - ap.w);
-    o4[fp] = make_float4(xp.x + a.hb * kp.x, xp.y + a.hb * kp.y, xp.z + a.hb * kp.z, xp.w + a.hb * kp.w);
-    o4[fv] = make_float4(xv.x + a.hb * kv.x, xv.y + a.hb * kv.y, xv.z + a.hb * kv.z, xv.w + a.hb * kv.w);
-    g4[fp] = kp;
-    g4[fv] = kv;
-    float4 p = (reinterpret_cast<const float4*>(a.a0) + t0)[fp], v = (reinterpret_cast<const float4*>(a.a0) + t0)[fv];
-#pragma unroll
-    for (int j = 0; j < 2; ++j)
-      if (j < a.n) {
-        const float4 qp = (reinterpret_cast<const float4*>(a.ka[j]) + t0)[fp], qv = (reinterpret_cast<const float4*>(a.ka[j]) + t0)[fv];
-        const float w = a.hbn[j];
-        p.x += w * qp.x; p.y += w * qp.y; p.z += w * qp.z; p.w += w * qp.w;
-        v.x += w * qv.x; v.y += w * qv.y; v.z += w * qv.z; v.w += w * qv.w;
-      }
-    const float w = a.hbn[a.n];
-    p.x += w * kp.x; p.y += w * kp.y; p.z += w * kp.z; p.w += w * kp.w;
-    v.x += w * kv.x; v.y += w * kv.y; v.z += w * kv.z; v.w += w * kv.w;
-    reinterpret_cast<float4*>(a.as_p)[o] = p;
-    reinterpret_cast<float4*>(a.u)[o] = make_float4(a.cn * v.x, a.cn * v.y, a.cn * v.z, a.cn * v.w);
-  }
-}
-
-int aug_stage_finish_prepare(const ab200_drift_desc* d, float* gx, float* as_p, const float* a_in, float* a_next, float inv, float hb,
-                             const float* a0, const float* const* ka, int n, const float* hbn, float cn, float* u, int64_t B,
-                             cudaStream_t st) {
-  if (n < 0 || n > 2 || d->pos_dim % 4 || d->ctx_dim % 4) return AB200_ERR_BAD_ARG;
-  AugFinPrepArgs k{};
-  k.gx = gx; k.as_p = as_p; k.a_in = a_in; k.a_next = a_next; k.inv = inv; k.hb = hb; k.a0 = a0; k.cn = cn; k.u = u; k.n = n;
-  k.P = d->pos_dim; k.H = d->ctx_dim;
-  k.ntiles = (int)((B + EL_TM - 1) / EL_TM);
-  for (int j = 0; j < n; ++j) k.ka[j] = ka[j];
-  for (int j = 0; j <= n; ++j) k.hbn[j] = hbn[j];
-  aug_stage_finish_prepare_kernel<<<launch_cfg((int64_t)k.ntiles * EL_TM * ((k.P + k.H) / 4)), 256, 0, st>>>(k);
-  return check_launch();
-}
-
-int aug_stage_prepare(const ab200_drift_desc* d, const float* a0, const float* const* ka, int n, const float* hb, float c, int64_t B,
-                      float* as_p, float* u, cudaStream_t st) {
-  if (n < 0 || n > 3 || d->pos_dim % 4 || d->ctx_dim % 4) return AB200_ERR_BAD_ARG;
-  AugPrepArgs k{};
-  k.a0 = a0; k.c = c; k.as_p = as_p; k.u = u; k.n = n; k.P = d->pos_dim; k.H = d->ctx_dim;
-  k.ntiles = (int)((B + EL_TM - 1) / EL_TM);
-  for (int j = 0; j < n; ++j) { k.ka[j] = ka[j]; k.hb[j] = hb[j]; }
-  aug_stage_prepare_kernel<<<launch_cfg((int64_t)k.ntiles * EL_TM * (k.P / 4)), 256, 0, st>>>(k);
-  return check_launch();
-}
-
-int aug_stage_finish(const ab200_drift_desc* d, float* gx, const float* as_p, const float* a_in, float* a_next, float inv, float hb,
-                     int write_ka, int64_t B, cudaStream_t st) {
-  if (d->pos_dim % 4 || d->ctx_dim % 4) return AB200_ERR_BAD_ARG;
-  AugFinArgs k{};
-  k.gx = gx; k.as_p = as_p; k.a_in = a_in; k.a_next = a_next; k.inv = inv; k.hb = hb; k.write_ka = write_ka;
-  k.P = d->pos_dim; k.H = d->ctx_dim;
-  k.ntiles = (int)((B + EL_TM - 1) / EL_TM);
-  aug_stage_finish_kernel<<<launch_cfg((int64_t)k.ntiles * EL_TM * ((k.P + k.H) / 4)), 256, 0, st>>>(k);
-  return check_launch();
-}
-
 int rows_transpose(const float* src, float* dst, int64_t B, int F, int mode, cudaStream_t st) {
   if (F % 4 || F <= 0 || F > 1024 || mode < 0 || mode > 2) return AB200_ERR_BAD_ARG;
   const int64_t Bp = (B + EL_TM - 1) / EL_TM * EL_TM;

@@ -439,31 +439,6 @@ class TcEngine:
                                          C.cast(ca, C.c_void_p), B, out.data_ptr(), _stream())
         _lib.check(rc, "ab200_adjoint_gather")
 
-    def aug_stage_prepare(self, a0, ka: Sequence[torch.Tensor], hb: Sequence[float], c: float, B: int, as_p, u) -> None:
-        """continuous adjoint, stage value of a_y: as_p = (a0 + sum hb[j] ka[j]).p ; u = c (a0 + sum hb[j] ka[j]).v"""
-        n = len(ka)
-        hba = (C.c_float * max(n, 1))(*[float(x) for x in hb])
-        rc = self.L.ab200_aug_stage_prepare(C.byref(self.desc), a0.data_ptr(), C.cast(_ptr_array(ka), C.c_void_p), n,
-                                            C.cast(hba, C.c_void_p), float(c), B, as_p.data_ptr(), u.data_ptr(), _stream())
-        _lib.check(rc, "ab200_aug_stage_prepare")
-
-    def aug_stage_finish(self, gx, as_p, a_in, a_next, inv: float, hb: float, write_ka: bool, B: int) -> None:
-        """continuous adjoint: ka = inv gx - [0, as_p, 0] ; a_next = a_in + hb ka ; write_ka: gx <- ka"""
-        rc = self.L.ab200_aug_stage_finish(C.byref(self.desc), gx.data_ptr(), as_p.data_ptr(), a_in.data_ptr(), a_next.data_ptr(),
-                                           float(inv), float(hb), 1 if write_ka else 0, B, _stream())
-        _lib.check(rc, "ab200_aug_stage_finish")
-
-    def aug_stage_finish_prepare(self, gx, as_p, a_in, a_next, inv: float, hb: float, a0, ka: Sequence[torch.Tensor],
-                                 hbn: Sequence[float], c_next: float, u, B: int) -> None:
-        """`aug_stage_finish` of a stage (gx <- ka_s) and `aug_stage_prepare` of the next one in one pass: next stage value =
-        a0 + sum hbn[j] ka[j] + hbn[len(ka)] ka_s; as_p in place; u = c_next (next stage value).v"""
-        n = len(ka)
-        hba = (C.c_float * (n + 1))(*[float(x) for x in hbn])
-        rc = self.L.ab200_aug_stage_finish_prepare(C.byref(self.desc), gx.data_ptr(), as_p.data_ptr(), a_in.data_ptr(), a_next.data_ptr(),
-                                                   float(inv), float(hb), a0.data_ptr(), C.cast(_ptr_array(ka), C.c_void_p), n,
-                                                   C.cast(hba, C.c_void_p), float(c_next), u.data_ptr(), B, _stream())
-        _lib.check(rc, "ab200_aug_stage_finish_prepare")
-
     def flush(self) -> None:
         if self.used:
             nx = len(self.x_ring) if any(x is not None for x in self.x_ring) else 0

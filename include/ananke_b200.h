@@ -296,23 +296,6 @@ int ab200_pv_combine_backward_multi(const ab200_drift_desc* d, const float* cons
  *     g_a_out (blocked [Bp][P]) = g_base + sum_l dp[l] gx[l].p + dv[l] gx[l].v
  * dopri5's first stage of a step IS the last (FSAL) evaluation of the previous step (tdq rk_common.py _adaptive_step:
  * f1 is carried over as f0), so its gradient is handed to that step's stage 7 rather than differentiated twice. */
-/* Stage algebra of torchdiffeq's continuous adjoint (adjoint.py `augmented_dynamics` under fixed_grid.py RK4) for the second-order
- * drift f = [v, A(p, v, h, t), 0], adjoint state a_y = [a_p, a_v, a_h] (blocked [Bp][D]):  da_y/dt = -[gx.p, a_p + gx.v, gx.h] with
- * gx = J_A^T a_v from ab200_stage_backward.  (ananke_abm_b200/adjoint_tc.py; replaces ~8 elementwise torch passes per stage.)
- *   prepare: stage value a_s = a0 + sum_{j<n} hb[j] ka[j] (n <= 3);  as_p = a_s.p,  u = c a_s.v  (both blocked [Bp][P]; u is the
- *            g_base of the stage's ab200_stage_backward call, c = -h b_s folds the Runge-Kutta weight into the weight gradients);
- *   finish : gx holds c J_A^T a_v,s; ka_s = inv [gx.p, gx.v, gx.h] - [0, as_p, 0] with inv = -1 / c;  a_next = a_in + hb ka_s;
- *            write_ka != 0: gx <- ka_s (a later stage's `ka` input).  a_in may alias a_next. */
-int ab200_aug_stage_prepare(const ab200_drift_desc* d, const float* a0, const float* const* ka, int32_t n, const float* hb_host, float c,
-                            int64_t B, float* as_p, float* u, ab200_stream_t stream);
-int ab200_aug_stage_finish(const ab200_drift_desc* d, float* gx, const float* as_p, const float* a_in, float* a_next, float inv, float hb,
-                           int32_t write_ka, int64_t B, ab200_stream_t stream);
-/* ab200_aug_stage_finish of stage s (write_ka = 1) and ab200_aug_stage_prepare of stage s + 1 in ONE pass: the next stage value is
- * a0 + sum_{j<n} hbn[j] ka[j] + hbn[n] ka_s with ka_s taken from registers (n <= 2 earlier stages); as_p is read (stage s) and
- * overwritten (stage s + 1) in place; u = c_next a_{s+1}.v. */
-int ab200_aug_stage_finish_prepare(const ab200_drift_desc* d, float* gx, float* as_p, const float* a_in, float* a_next, float inv, float hb,
-                                   const float* a0, const float* const* ka, int32_t n, const float* hbn_host, float c_next, float* u,
-                                   int64_t B, ab200_stream_t stream);
 int ab200_stage_upstream(const ab200_drift_desc* d, const float* g_base, const float* const* gx, int32_t n_g,
                          const float* dp_host, const float* dv_host, int64_t B, float* g_a_out, ab200_stream_t stream);
 int ab200_wgrad_accumulate(const ab200_drift_desc* d, const void* spill, int32_t nblobs, int32_t used, void* partial,

@@ -10,8 +10,8 @@ dev = torch.device('cuda:0')
 args = types.SimpleNamespace(workload="c5", agents=B, solver="", adjoint_mode="continuous-rk4")
 cfg = bench._config_for(args)
 model, zfeat, csr = bench.build_model(cfg, "bf16", dev, "all", "continuous-rk4")
-if len(sys.argv) > 3:      # launch structure of the backward pass: fused | staged | linear | linear1 (adjoint_tc.rk4_continuous_adjoint)
-    model.config.adjoint_fused = {"fused": True, "staged": False}.get(sys.argv[3], sys.argv[3])
+if len(sys.argv) > 3:      # launch structure of the backward pass: fused | staged (adjoint_tc.rk4_continuous_adjoint)
+    model.config.adjoint_fused = {"fused": True, "staged": False}[sys.argv[3]]
 home, work, traits, t = (x.to(dev) for x in bench.make_inputs(cfg, seed=42))
 params = list(model.parameters())
 prof = None

@@ -99,30 +99,6 @@ class FakeEngine:
                 acc_.add_(gi)
         self.n_vjp += 1
 
-    def aug_stage_prepare(self, a0, ka, hb, c, B, as_p, u):
-        """the formula ab200_aug_stage_prepare implements, on views of the blocked buffers"""
-        D, P = self.D, self.P
-        a_s = a0.clone()
-        for k, w in zip(ka, hb):
-            a_s.add_(k, alpha=w)
-        ap, av, _ = adjoint_tc._views(a_s, D, P)
-        as_p.view(-1, P // 4, TM, 4).copy_(ap)
-        torch.mul(av, c, out=u.view(-1, P // 4, TM, 4))
-
-    def aug_stage_finish(self, gx, as_p, a_in, a_next, inv, hb, write_ka, B):
-        """the formula ab200_aug_stage_finish implements"""
-        D, P = self.D, self.P
-        ka = gx * inv
-        adjoint_tc._views(ka, D, P)[1].sub_(as_p.view(-1, P // 4, TM, 4))
-        a_next.copy_(a_in + hb * ka)
-        if write_ka:
-            gx.copy_(ka)
-
-    def aug_stage_finish_prepare(self, gx, as_p, a_in, a_next, inv, hb, a0, ka, hbn, c_next, u, B):
-        """finish of a stage + prepare of the next one (the formula ab200_aug_stage_finish_prepare implements)"""
-        self.aug_stage_finish(gx, as_p, a_in, a_next, inv, hb, True, B)
-        self.aug_stage_prepare(a0, list(ka) + [gx], hbn, c_next, B, as_p, u)
-
     def combine_backward(self, g, c, B, G_y0, G_a, accumulate):
         """ab200_pv_combine_backward: G_y0 = [g.p, cpv g.p + g.v, g.h] ; G_a[j] = cpa[j] g.p + cva[j] g.v"""
         assert not accumulate
@@ -192,7 +168,7 @@ def test_step_grid_mirrors_the_package_grid_constructor():
         adjoint_tc.step_grid(0.0, 1.0, 0.0)
 
 
-@pytest.mark.parametrize("fused", [False, True, "linear", "linear1"])
+@pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("B,step_size", [(3, None), (130, None), (5, 0.25), (5, 0.4)])
 def test_tc_continuous_adjoint_algebra_matches_the_oracle(B, step_size, fused):
     oracle, y0 = _setup(B)

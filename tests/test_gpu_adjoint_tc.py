@@ -146,74 +146,3 @@ def test_tc_continuous_adjoint_memory_does_not_grow_with_the_step_count():
         assert torch.isfinite(y.grad).all()
     # 88 more steps: a scheme that kept per-step state would add >= 88 x 40,000 x 640 B = 2.2 GB to the ~1 GB peak
     assert peaks[1] <= peaks[0] * 1.10, peaks
-
-
-@pytest.mark.parametrize("B", [1, 127, 129, 1000])
-@pytest.mark.parametrize("n", [0, 1, 3])
-def test_aug_stage_kernels_match_the_formula(B, n):
-    """ab200_aug_stage_prepare / ab200_aug_stage_finish against the same expressions in torch on views of the blocked buffers
-    (the CPU stand-in of tests/test_adjoint_tc_host.py, which is pinned on the oracle), ragged sizes, padding rows untouched"""
-    import ananke_abm_b200 as ab
-    from ananke_abm_b200 import adjoint_tc, stage
-    dev = _cuda()
-    _, model = _pair()
-    model = model.to(dev)
-    spec = ab.describe_drift(model.odefunc)
-    eng = stage.TcEngine(spec, spec.flat_params().detach())
-    D, P, TM = eng.D, eng.P, stage.TM
-    g = torch.Generator().manual_seed(B + n)
-    rnd = lambda F: stage.rows_block(torch.randn(B, F, generator=g).to(dev))      # noqa: E731  (padding rows: zeros)
-    a0, ka, gx, asp_in = rnd(D), [rnd(D) for _ in range(n)], rnd(D), rnd(P)
-    hb, c = [0.3, -0.7, 1.1][:n], 0.42
-    as_p, u = stage.blocked_zeros(B, P, dev), stage.blocked_zeros(B, P, dev)
-    eng.aug_stage_prepare(a0, ka, hb, c, B, as_p, u)
-    a_s = a0.clone()
-    for k, w in zip(ka, hb):
-        a_s.add_(k, alpha=w)
-    ap, av, _ = adjoint_tc._views(a_s, D, P)
-    assert torch.allclose(as_p.view(-1, P // 4, TM, 4), ap, atol=1e-6, rtol=1e-6)
-    assert torch.allclose(u.view(-1, P // 4, TM, 4), c * av, atol=1e-6, rtol=1e-6)
-
-    inv, hbs = -1.0 / c, -0.125
-    ka_ref = gx * inv
-    adjoint_tc._views(ka_ref, D, P)[1].sub_(asp_in.view(-1, P // 4, TM, 4))
-    for write_ka in (False, True):
-        gxc, a_next = gx.clone(), stage.blocked_zeros(B, D, dev)
-        eng.aug_stage_finish(gxc, asp_in, a0, a_next, inv, hbs, write_ka, B)
-        assert torch.allclose(a_next, a0 + hbs * ka_ref, atol=1e-6, rtol=1e-6)
-        assert torch.allclose(gxc, ka_ref if write_ka else gx, atol=1e-6, rtol=1e-6)
-    acc = a0.clone()                                       # a_in aliasing a_next (stages 2..4 of a step)
-    eng.aug_stage_finish(gx.clone(), asp_in, acc, acc, inv, hbs, False, B)
-    assert torch.allclose(acc, a0 + hbs * ka_ref, atol=1e-6, rtol=1e-6)
-    if B % TM:                                             # padding rows of every output stay zero
-        for buf, F in ((as_p, P), (u, P), (acc, D)):
-            rows = buf.view(-1, F // 4, TM, 4)[-1, :, B % TM:, :]
-            assert float(rows.abs().max()) == 0.0
-
-
-@pytest.mark.parametrize("B", [1, 129, 1000])
-@pytest.mark.parametrize("n", [0, 2])
-def test_aug_stage_finish_prepare_equals_the_two_passes(B, n):
-    """the fused pass == ab200_aug_stage_finish (write_ka) followed by ab200_aug_stage_prepare with ka_s appended, bit for bit apart
-    from fma contraction (1e-6)"""
-    import ananke_abm_b200 as ab
-    from ananke_abm_b200 import stage
-    dev = _cuda()
-    _, model = _pair()
-    model = model.to(dev)
-    spec = ab.describe_drift(model.odefunc)
-    eng = stage.TcEngine(spec, spec.flat_params().detach())
-    D, P = eng.D, eng.P
-    g = torch.Generator().manual_seed(7 * B + n)
-    rnd = lambda F: stage.rows_block(torch.randn(B, F, generator=g).to(dev))      # noqa: E731
-    a0, ka, gx, asp, acc = rnd(D), [rnd(D) for _ in range(n)], rnd(D), rnd(P), rnd(D)
-    hbn, inv, hb, cn = [0.3, -0.7, 1.1][:n + 1], -2.5, -0.125, 0.6
-    # reference: the two separate passes
-    gx_r, acc_r, asp_r, u_r = gx.clone(), acc.clone(), stage.blocked_zeros(B, P, dev), stage.blocked_zeros(B, P, dev)
-    eng.aug_stage_finish(gx_r, asp, acc_r, acc_r, inv, hb, True, B)
-    eng.aug_stage_prepare(a0, ka + [gx_r], hbn, cn, B, asp_r, u_r)
-    # fused, as_p in place, a_in aliasing a_next
-    gx_f, acc_f, asp_f, u_f = gx.clone(), acc.clone(), asp.clone(), stage.blocked_zeros(B, P, dev)
-    eng.aug_stage_finish_prepare(gx_f, asp_f, acc_f, acc_f, inv, hb, a0, ka, hbn, cn, u_f, B)
-    for got, ref in ((gx_f, gx_r), (acc_f, acc_r), (asp_f, asp_r), (u_f, u_r)):
-        assert torch.allclose(got, ref, atol=1e-6, rtol=1e-6)
