@@ -138,6 +138,12 @@ def _tensor_core_rk4(func, y0, t, method, options, adjoint_method, adjoint_optio
         return None
     step = opts.get("step_size")
     adj_step = step if adjoint_options is None else dict(adjoint_options).get("step_size")
+    known = {"precision", "step_size", "forward_operands", "adjoint_fused", "adjoint_mode", "saved_operands", "dtype", "norm",
+             "time_as_float", "segments"}
+    extra = sorted((set(opts) | set(dict(adjoint_options or {}))) - known)
+    if extra:      # torchdiffeq warns about options a solver does not use and carries on
+        import warnings
+        warnings.warn(f"rk4: Unexpected arguments {extra}")
     from .adjoint_tc import _ContinuousAdjointRK4TC
     return _ContinuousAdjointRK4TC.apply(y0, t, spec.flat_params(), spec, t_host, None if step is None else float(step),
                                          None if adj_step is None else float(adj_step), opts.get("forward_operands"),

@@ -46,3 +46,55 @@ def test_chunk_bounds_cover_the_batch_in_whole_waves():
         assert all(0 < e - s <= cap + 296 * 128 for s, e in parts)
         if len(parts) > 1 and -(-(-(-B // 128)) // 296) >= len(parts):
             assert all((e - s) % (296 * 128) == 0 for s, e in parts[:-1])
+
+
+def test_continuous_rk4_mode_is_configs4_as_one_solve():
+    """--workload c5 --adjoint-mode continuous-rk4: t = [0, 24] with step_size 0.25 = 96 grid steps, rk4, all agents in one solve;
+    an agent-step of that line is one grid step (not one output interval)."""
+    import types
+    sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+    import bench
+    args = types.SimpleNamespace(workload="c5", agents=0, solver="", adjoint_mode="continuous-rk4")
+    cfg = bench._config_for(args)
+    assert cfg["method"] == "rk4" and cfg["T"] == 2 and cfg["step_size"] == 0.25 and cfg["grid_steps"] == 96 and cfg["B"] == 8_000_000
+    assert cfg["adjoint"] and "configs[4]" in cfg["name"]
+    _, _, _, t = bench.make_inputs(dict(cfg, B=4))
+    assert t.tolist() == [0.0, 24.0]
+    from ananke_abm_b200.adjoint_tc import step_grid
+    assert len(step_grid(0.0, 24.0, cfg["step_size"])) - 1 == cfg["grid_steps"]
+    args = types.SimpleNamespace(workload="c5", agents=1000, solver="", adjoint_mode="discrete")
+    cfg = bench._config_for(args)
+    assert cfg["method"] == "dopri5" and cfg["T"] == 97 and cfg["B"] == 1000 and "grid_steps" not in cfg
+
+
+def test_fused_step_coefficients_reproduce_the_stage_recursion():
+    """adjoint_tc.fused_step_coefficients: the linear form of an augmented 3/8-rule step over (a0, gx'_0..gx'_3) against the stage
+    recursion written out directly on scalars (a_p, a_v) with an arbitrary linear 'Jacobian' per stage"""
+    import random
+    from ananke_abm_b200 import adjoint_tc
+    from ananke_abm_b200.stage import RK38
+    rnd = random.Random(3)
+    h = -0.37
+    a0p, a0v = rnd.uniform(-1, 1), rnd.uniform(-1, 1)
+    Jp = [rnd.uniform(-1, 1) for _ in range(4)]      # gx_s.p = Jp[s] * a_v,s ; gx_s.v = Jv[s] * a_v,s
+    Jv = [rnd.uniform(-1, 1) for _ in range(4)]
+    # direct recursion: ka_s = -[gx_s.p, a_p,s + gx_s.v]
+    ka, gxs = [], []
+    for s in range(4):
+        ap = a0p + h * sum(b * ka[j][0] for j, b in enumerate(RK38.beta[s]))
+        av = a0v + h * sum(b * ka[j][1] for j, b in enumerate(RK38.beta[s]))
+        gx = (Jp[s] * av, Jv[s] * av)
+        gxs.append((gx, av))
+        ka.append((-gx[0], -(ap + gx[1])))
+    a1p = a0p + h * sum(RK38.b[s] * ka[s][0] for s in range(4))
+    a1v = a0v + h * sum(RK38.b[s] * ka[s][1] for s in range(4))
+    # linear form
+    c, cpa, cva, dp, dv, w = adjoint_tc.fused_step_coefficients(h)
+    gxp = []
+    for s in range(4):
+        up = cva[s] * a0v + cpa[s] * a0p + sum(dp[s][i] * gxp[i][0] + dv[s][i] * gxp[i][1] for i in range(s))
+        assert abs(up - c[s] * gxs[s][1]) < 1e-12                       # upstream_s == c_s a_v,s
+        gxp.append((Jp[s] * up, Jv[s] * up))                            # the scaled product c_s gx_s
+    b1p = a0p + sum(g[0] for g in gxp)
+    b1v = a0v - h * a0p + sum(w[i] * gxp[i][0] + gxp[i][1] for i in range(4))
+    assert abs(b1p - a1p) < 1e-12 and abs(b1v - a1v) < 1e-12
