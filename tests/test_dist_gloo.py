@@ -103,3 +103,59 @@ def test_two_rank_gradient_allreduce_equals_full_batch():
     for rank, ok_g, ok_l, ok_p, span in res:
         assert ok_g and ok_l and ok_p, (rank, ok_g, ok_l, ok_p)
     assert sorted(r[4] for r in res) == [(0, 6), (6, 11)]
+
+
+def _worker_adjoint(rank, world, port, q):
+    """configs[4] sharding: every rank runs the tensor-core continuous adjoint (adjoint_tc.py host algebra on the float64 stand-in
+    engine of tests/test_adjoint_tc_host.py) on its block of agents with step_size; the all-reduced parameter adjoints and the
+    concatenated dL/dy0 must equal the single-process solve over the whole batch -- no collective inside the solve (fixed grid)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import sys
+        import numpy as np
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        sys.path.insert(0, root)
+        sys.path.insert(0, os.path.join(root, "tests"))
+        from ananke_abm_b200 import adjoint_tc, dist as abd
+        import test_adjoint_tc_host as th
+
+        torch.set_num_threads(1)
+        B = 9
+        oracle, y0 = th._setup(B)
+        func = oracle.odefunc
+        t = [0.0, 1.0]
+        step = 0.25
+
+        def solve(y0_part, n_total):
+            eng = th.FakeEngine(func, 64, 32)
+            rows = adjoint_tc.rk4_forward_rows(eng, y0_part, t, step, lay=th.FakeLayout, np_dtype=np.float64)
+            grad_rows = 2.0 * rows / (rows.shape[0] * n_total * rows.shape[2])      # d/dy of mean(y^2) over the WHOLE batch
+            return adjoint_tc.rk4_continuous_adjoint(eng, t, rows, grad_rows, step, lay=th.FakeLayout, np_dtype=np.float64, fused=True)
+
+        gy_full, gw_full = solve(y0, B)
+        lo, hi = abd.shard_bounds(B, rank, world)
+        gy, gw = solve(y0[lo:hi].contiguous(), B)
+        dist.all_reduce(gw)                                      # the ONE collective of a training step (dist.allreduce_gradients)
+        ok_w = torch.allclose(gw, gw_full, rtol=1e-9, atol=1e-14)
+        ok_y = torch.allclose(gy, gy_full[lo:hi], rtol=1e-9, atol=1e-14)
+        q.put((rank, bool(ok_w), bool(ok_y), float(gw_full.abs().max())))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(240)
+def test_two_rank_sharded_continuous_adjoint_equals_the_full_batch_solve():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_adjoint, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=200) for _ in range(world)]
+    for p in procs:
+        p.join(30)
+    assert sorted(r[0] for r in res) == [0, 1]
+    for rank, ok_w, ok_y, scale in res:
+        assert ok_w and ok_y and scale > 0, (rank, ok_w, ok_y, scale)
