@@ -164,16 +164,29 @@ def _aug_step(eng, yb: torch.Tensor, ab: torch.Tensor, t0: float, t1: float, B: 
     return y_new, a_new
 
 
+def _fused_fits(B: int, D: int, P: int, device) -> bool:
+    """the fused structure keeps the blobs of FOUR stages (~3.1 KB per agent-stage) next to the 9 [Bp, D] + 7 [Bp, P] work buffers;
+    it is chosen while that stays under 70 % of the memory that is free right now (device-free + the caching allocator's idle blocks),
+    and under 56 GB of blobs where that cannot be asked (CPU stand-in)"""
+    Bp = stage.padded_rows(B)
+    blobs = Bp * 3100 * 4
+    if torch.device(device).type != "cuda":
+        return blobs < (56 << 30)
+    free, _ = torch.cuda.mem_get_info(device)
+    idle = torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)
+    return blobs + Bp * 4 * (9 * D + 7 * P) < 0.7 * (free + idle)
+
+
 def rk4_continuous_adjoint(eng, t_host: Sequence[float], y_rows: torch.Tensor, grad_rows: torch.Tensor,
                            step_size: Optional[float] = None, lay=_CudaLayout, np_dtype=np.float32, fused: Optional[bool] = None):
     """-> (dL/dy0 row-major [B, D], a_theta(t[0]) = dL/dtheta in the drift's flat parameter order).
-    `fused` (default: while the blobs of four stages fit in ~56 GB, i.e. up to ~4.6M agents): the four vector-Jacobian products of a
-    step in one launch; otherwise one launch per stage with a one-stage blob ring and the weight-gradient pass after every stage
+    `fused` (default: while the blobs of four stages fit into the free memory, `_fused_fits`: up to ~5M agents on an otherwise empty
+    180 GB GPU): the four vector-Jacobian products of a step in one launch; otherwise one launch per stage with a one-stage blob ring and the weight-gradient pass after every stage
     (8M agents on one GPU)."""
     T, B, D = grad_rows.shape
     dev = grad_rows.device
     if fused is None:
-        fused = stage.padded_rows(B) * 3100 * 4 < (56 << 30)
+        fused = _fused_fits(B, D, eng.P, dev)
     eng.backward_begin(B, 4 if fused else 1)
     w = _FusedBuffers(B, D, eng.P, dev, lay)
     ab = lay.block(grad_rows[T - 1].contiguous())
