@@ -23,7 +23,7 @@ the step's solution a_y(t + h): an augmented step is the fused forward launch of
 parts of the four upstream gradients and of the solution), the vector-Jacobian products with the earlier products as gather sources
 of the launch, the weight-gradient pass, and `ab200_adjoint_gather` (the solution) -- no elementwise pass between the stages.
 Two launch structures (`rk4_continuous_adjoint(fused=...)`, `options["adjoint_fused"]`): the four products as ONE
-`ab200_stage_backward_fused` launch (default while the blobs of four stages fit, up to ~4.6M agents per GPU), or one
+`ab200_stage_backward_fused` launch (default while the blobs of four stages fit into the free memory, ~5M agents on an empty GPU), or one
 `ab200_stage_backward` launch per stage with a one-stage blob ring (8M agents on one GPU).
 Every evaluation of A and of its vector-Jacobian product is a tcgen05 kernel (fp16 / bf16 operands, fp32 accumulate);
 y, a_y and a_theta are fp32.  Stated tolerance: that of the tensor-core path.
