@@ -482,8 +482,8 @@ def run_ours(args):
             GX = [st.blocked_zeros(Bc, 160, dev) for _ in range(7)]
             dtk = 0.25
             tab, first, last = (st.DOPRI5, 1, 6) if adaptive else (st.RK38, 0, 3)      # the fused launch of one step's backward stages
-            if cont_rk4:
-                first = 3      # the continuous adjoint issues ONE stage per launch (upstream = the stage value of a_v)
+            if cont_rk4 and chunk > 5_000_000:
+                first = 3      # too many agents for a four-stage blob ring: the continuous adjoint issues ONE stage per launch
             times = [1.0 + tab.c[i] * dtk for i in range(last + 1)]
             n_fused = last - first + 1
             eng.backward_begin(Bc, n_fused)
